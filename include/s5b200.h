@@ -1,0 +1,256 @@
+/*
+ * s5b200.h - C ABI of libs5b200.so: B200-native (sm_100a) S5 / NDNS forward path.
+ *
+ * The reference (stevenabreu7/SparseRNNs) has no FFI or plugin interface: the seams of this path are
+ * Python callables.  Each entry point below names the reference callable it
+ * replaces (paths relative to the reference repository root) and is what a `jax.ffi` custom call /
+ * ctypes stub binds (INTEGRATION.md shows both bindings).
+ *
+ * Conventions
+ *   - plain C, no C++/torch types; all tensors are caller-owned, row-major, DEVICE pointers unless the
+ *     argument name ends in `_host`;
+ *   - `stream` is a cudaStream_t passed as void*; every call is asynchronous on it, never synchronises
+ *     the device and never allocates on the hot path (scratch comes from caller-provided workspaces or
+ *     from the handle);
+ *   - return value: 0 on success, negative S5_E_* otherwise; `s5b200_last_error()` returns a
+ *     thread-local message for the last failing call on this thread;
+ *   - complex values are interleaved (re, im) pairs, i.e. the memory layout of complex64;
+ *   - handles are immutable after creation and may be used concurrently from several streams.
+ */
+#ifndef S5B200_H_
+#define S5B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define S5B200_VERSION 100 /* major*10000 + minor*100 + patch */
+
+enum s5_status {
+  S5_OK = 0,
+  S5_E_BADSHAPE = -1,    /* dimension out of the supported range / inconsistent sizes */
+  S5_E_BADARG = -2,      /* null pointer, misaligned pointer, bad enum value, workspace too small */
+  S5_E_CUDA = -3,        /* a CUDA runtime call failed (message carries cudaGetErrorString) */
+  S5_E_UNSUPPORTED = -4  /* configuration the reference cannot reach either (e.g. bidirectional) */
+};
+
+/* fxparray.py:13-17 RoundingMode */
+enum s5_round_mode { S5_ROUND_FLOOR = 0, S5_ROUND_CEIL = 1, S5_ROUND_HALF_UP = 2 };
+
+/* numerics flavour of a model handle */
+enum s5_flavour {
+  S5_FLOAT = 0,  /* quantization=none: build_apply_ssm, nn.Dense (ssm.py:80-187) */
+  S5_STATIC = 1  /* static fake-quant, frozen scales: build_apply_ssm_static_quant (ssm.py:190-345) */
+};
+
+enum s5_activation { S5_ACT_GELU_TANH = 0, S5_ACT_RELU = 1 };
+
+int s5b200_version(void);
+const char* s5b200_last_error(void);
+/* Number of kernels launched by this library on the calling thread since the last reset (bench.py's
+ * `gpu_launches`). */
+long long s5b200_launch_count(void);
+void s5b200_reset_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * (1) Diagonal complex linear recurrence  x_k = lam * x_{k-1} + Bu_k,  x_{-1} = 0.
+ * Replaces jax.lax.associative_scan / jax.lax.scan in sparseRNNs/model/ssm.py:127, :150, :313.
+ *   Bu, xs : [B][L][P] complex64 (xs may alias Bu);  lam : [P] complex64.
+ *   relu != 0 applies the lexicographic complex ReLU of ssm.py:159/:325 to the OUTPUT only.
+ * Chunked single-pass scan with decoupled look-back; `workspace` holds the chunk carries/flags.
+ * ---------------------------------------------------------------------------------------------- */
+size_t s5b200_scan_c64_workspace_bytes(int B, int L, int P);
+int s5b200_scan_c64(const float* Bu, const float* lam, float* xs, int B, int L, int P, int relu,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (3a) Integer recurrence, bit-exact with make_ssm_step_fn / recurrent_loop
+ * (sparseRNNs/fxpmodel.py:147-208): per-product arithmetic >>, wrapping int32 state, no saturation.
+ *   Bu_re, Bu_im, xs_re, xs_im : [B][L][P] int32 (planar, as the reference's FxpArray payloads);
+ *   A_re, A_im : [P] int32.  relu != 0 applies fxp_relu (fxpmodel.py:27-52) to the output.
+ * ---------------------------------------------------------------------------------------------- */
+int s5b200_scan_i32(const int32_t* Bu_re, const int32_t* Bu_im, const int32_t* A_re, const int32_t* A_im,
+                    int32_t* xs_re, int32_t* xs_im, int B, int L, int P, int eA_re, int eA_im,
+                    int eBu_re, int eBu_im, int ex_re, int ex_im, int relu, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (2) Sparse projection  Y[rows][N] = X[rows][K] @ W[K][N]  with W in compressed form.
+ * Replaces jnp.dot / lax.dot_general in ssm.py:116-124, :179-185, quantization.py:772-776 and
+ * `op1.data @ op2.data` in fxparray.py:662.  The non-zero index set is taken from the matrix that
+ * is handed in (the already-quantised weights), so it is bit-exact by construction;
+ * s5b200_sparse_export returns it for checking.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct s5_sparse s5_sparse;
+enum s5_dtype { S5_F32 = 0, S5_I32 = 1 };
+/* W_host: dense [K][N] row-major, float32 or int32.  dense_format != 0 keeps every entry. */
+int s5b200_sparse_create(const void* W_host, int K, int N, int dtype, int dense_format, s5_sparse** out);
+int s5b200_sparse_destroy(s5_sparse* w);
+int s5b200_sparse_nnz(const s5_sparse* w);
+/* k_idx, n_idx : host arrays of s5b200_sparse_nnz() entries, ordered by (n, k). */
+int s5b200_sparse_export(const s5_sparse* w, int32_t* k_idx_host, int32_t* n_idx_host);
+/* Y = X @ W (+ bias[N] if non-null).  skip_zero_cols != 0 enables tile-level zero-activation skipping. */
+int s5b200_spmm_f32(const s5_sparse* w, const float* X, const float* bias, float* Y, long long rows,
+                    int skip_zero_cols, void* stream);
+/* fxp_matmul (fxparray.py:640-678): int32 accumulate (wraps), rshift-round, saturate to `bits`. */
+int s5b200_spmm_i32(const s5_sparse* w, const int32_t* X, int32_t* Y, long long rows, int rshift,
+                    int round_mode, int bits, int skip_zero_cols, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (1)+(2) Float / static-quant model.  Host code (Python) keeps the reference's parameter pytree,
+ * performs the per-weight-set work (ZOH discretisation ssm.py:37-50, weight fake-quant
+ * ssm.py:231-233, BatchNorm constant folding of running stats) and hands flat arrays over.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct s5_layer_desc {
+  /* SSM (ssm.py:525-622).  For S5_STATIC these are the fake-quantised values. */
+  const float* lambda_bar_host; /* [P][2]    */
+  const float* B_bar_host;      /* [P][H][2] */
+  const float* C_tilde_host;    /* [H][P][2] */
+  const float* D_host;          /* [H]       */
+  /* BatchNorm, running statistics (layers.py:146-152, :210-211): u = (x - mean) * mul + bias */
+  const float* bn_mean_host;    /* [H] */
+  const float* bn_mul_host;     /* [H] rsqrt(var + eps) * gamma */
+  const float* bn_bias_host;    /* [H] beta (zeros if absent) */
+  /* GLU "half1" (layers.py:223-225): x1 * sigmoid(out2(x1)) */
+  const float* out2_kernel_host; /* [H][H] (in, out); fake-quantised for S5_STATIC */
+  const float* out2_bias_host;   /* [H]; fake-quantised for S5_STATIC */
+  /* frozen power-of-two scales, S5_STATIC only (ssm.py:408-421, quantization.py:699-702, layers.py:168-174) */
+  float s_ut, s_But_re, s_But_im, s_yt;
+  float s_out2_act, s_out2_out, s_gate_left, s_gate_right;
+} s5_layer_desc;
+
+typedef struct s5_model_desc {
+  int flavour;       /* enum s5_flavour */
+  int n_layers, H, P, d_input, d_output;
+  int activation;    /* enum s5_activation: GELU(tanh) if relufication is off, ReLU if on */
+  int relufication;  /* ReLU after encoder, on xs (complex) and on the block output */
+  int conj_sym;      /* y = 2*Re(C x) */
+  int ssm_act_bits, non_ssm_act_bits; /* S5_STATIC activation widths (16 for w8a16) */
+  int use_sparse;    /* build compressed weights from the non-zeros; 0 keeps dense tiles */
+  const float* enc_kernel_host; /* [d_input][H] */
+  const float* enc_bias_host;   /* [H] */
+  float s_enc_act, s_enc_out;   /* S5_STATIC */
+  const float* dec_kernel_host; /* [H][d_output] */
+  const float* dec_bias_host;   /* [d_output] */
+  float s_dec_act, s_dec_out;   /* S5_STATIC */
+  const s5_layer_desc* layers;  /* [n_layers] */
+} s5_model_desc;
+
+typedef struct s5_model s5_model;
+int s5b200_model_create(const s5_model_desc* desc, s5_model** out);
+int s5b200_model_destroy(s5_model* m);
+size_t s5b200_model_workspace_bytes(const s5_model* m, int B, int L);
+/* QBatchRegressionModel.apply (seq_model.py:439-473): x [B][L][d_input] -> y [B][L][d_output]. */
+int s5b200_model_forward(const s5_model* m, const float* x, float* y, int B, int L, void* workspace,
+                         size_t workspace_bytes, void* stream);
+/* QSequenceLayer.__call__ (layers.py:180-241) for block `layer`: x [B][L][H] -> y [B][L][H];
+ * xs_out (optional, may be NULL) receives pre_C = xs [B][L][P] complex64 (after ReLU if relufication). */
+int s5b200_layer_forward(const s5_model* m, int layer, const float* x, float* y, float* xs_out, int B,
+                         int L, void* workspace, size_t workspace_bytes, void* stream);
+/* qS5SSM.__call__ (ssm.py:525-622) for block `layer`: u [B][L][H] (already normalised) ->
+ * y = ys + D*u [B][L][H] (quantised for S5_STATIC) and xs [B][L][P] complex64. */
+int s5b200_ssm_forward(const s5_model* m, int layer, const float* u, float* y, float* xs_out, int B, int L,
+                       void* workspace, size_t workspace_bytes, void* stream);
+/* Same as s5b200_model_forward with HOST buffers: H2D copy, forward, D2H copy, stream-synchronous on
+ * return.  This is the call the end-to-end benchmark times. */
+int s5b200_model_forward_host(const s5_model* m, const float* x_host, float* y_host, int B, int L,
+                              void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (3) Fixed-point model, bit-exact with sparseRNNs/fxpmodel.py driven as in fxprun.py:25-95.
+ * All integer parameters are produced on the host exactly as FxpDense.setup / FxpSSM.setup /
+ * FxpBatchNorm.setup do (fxp_from_fp ROUND at the qconfig exponents) and passed as int32.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct s5_fxp_dense_desc {
+  const int32_t* weight_host; /* [in][out] */
+  const int32_t* bias_host;   /* [out] */
+  int w_exp, b_exp, b_bits, inp_bits, inp_exp, out_bits, out_exp;
+} s5_fxp_dense_desc;
+
+typedef struct s5_fxp_layer_desc {
+  /* FxpBatchNorm (fxpmodel.py:850-944); scale/bias may be NULL ("simple" BatchNorm) */
+  const int32_t* bn_minus_mean_host; int bn_mean_exp, bn_mean_bits;
+  const int32_t* bn_invsq_var_host;  int bn_invsq_exp, bn_invsq_bits;
+  const int32_t* bn_scale_host;      int bn_scale_exp, bn_scale_bits;
+  const int32_t* bn_bias_host;       int bn_bias_exp, bn_bias_bits;
+  /* FxpSSM (fxpmodel.py:396-794) */
+  const int32_t* A_re_host; const int32_t* A_im_host; /* [P] */
+  const int32_t* B_re_host; const int32_t* B_im_host; /* [P][H] */
+  const int32_t* C_re_host; const int32_t* C_im_host; /* [H][P] */
+  const int32_t* D_host;                              /* [H] */
+  int eA_re, eA_im, eB_re, eB_im, eC_re, eC_im, eD;
+  int u_bits, u_exp, Bu_re_bits, Bu_re_exp, Bu_im_bits, Bu_im_exp, x_re_exp, x_im_exp, y_bits, y_exp;
+  /* out2 + sigmoid LUT + mult_gate (fxpmodel.py:1075-1104) */
+  s5_fxp_dense_desc out2;
+  int sig_x_exp, sig_y_exp; int32_t sig_lut[8];
+  int gate_l_bits, gate_l_exp, gate_r_bits, gate_r_exp, gate_res_bits, gate_res_exp;
+} s5_fxp_layer_desc;
+
+typedef struct s5_fxp_model_desc {
+  int n_layers, H, P, d_input, d_output;
+  int use_sparse;
+  s5_fxp_dense_desc encoder, decoder;
+  const s5_fxp_layer_desc* layers;
+} s5_fxp_model_desc;
+
+typedef struct s5_fxp_model s5_fxp_model;
+int s5b200_fxp_model_create(const s5_fxp_model_desc* desc, s5_fxp_model** out);
+int s5b200_fxp_model_destroy(s5_fxp_model* m);
+size_t s5b200_fxp_model_workspace_bytes(const s5_fxp_model* m, int B, int L);
+/* run_validation's hot part (fxprun.py:69-77): x float32 [B][L][d_input] is quantised with
+ * fxp_from_fp(FLOOR, encoder inp bits/exp), the integer model runs, and
+ *   y_int [B][L][d_output] int32 (payload, exponent = decoder out_exp) and/or
+ *   y_float [B][L][d_output] = to_float() are written (either may be NULL).
+ * status_dev (optional int32[4] device): [0] != 0 if an op the reference would raise on was hit
+ * (negative shift in fxp_mul, fxparray.py:619-621). */
+int s5b200_fxp_model_forward(const s5_fxp_model* m, const float* x, int32_t* y_int, float* y_float, int B,
+                             int L, void* workspace, size_t workspace_bytes, int32_t* status_dev, void* stream);
+/* Same, taking an already quantised int32 input (model(fxp_x), fxprun.py:76). */
+int s5b200_fxp_model_forward_int(const s5_fxp_model* m, const int32_t* x_int, int32_t* y_int, float* y_float,
+                                 int B, int L, void* workspace, size_t workspace_bytes, int32_t* status_dev,
+                                 void* stream);
+/* Intermediate tap after a forward: copies the named per-layer tensor out of the workspace for
+ * verification (names follow the `sow` keys of fxpmodel.py).  tap ids: */
+enum s5_fxp_tap {
+  S5_TAP_LAYER_INPUT = 0,  /* "ssm_input"  int32 [B][L][H]  + exponent */
+  S5_TAP_PRE_S5 = 1,       /* "pre_s5" (u after change_cfg) int32 [B][L][H] */
+  S5_TAP_XS = 2,           /* "xs_relu"  int32 [B][L][P][2] interleaved (re, im) */
+  S5_TAP_POST_GLU = 3,     /* "post_GLU" int32 [B][L][H] */
+  S5_TAP_OUTPUT = 4        /* "output"   int32 [B][L][H] + exponent */
+};
+/* Runs the forward up to and including block `layer` and copies tap `tap` of that block to `dst`
+ * (device); `exp_out_host` receives the tensor's (possibly data-dependent) exponent.  Synchronises. */
+int s5b200_fxp_model_tap(const s5_fxp_model* m, const int32_t* x_int, int layer, int tap, int32_t* dst,
+                         int* exp_out_host, int B, int L, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Granular fixed-point ops mirroring sparseRNNs/fxparray.py (element-wise, device int32 payloads).
+ * `b` is broadcast along the last axis when nb < n (nb must divide n). */
+int s5b200_fxp_from_fp(const float* x, int32_t* y, long long n, int bits, int exp, int round_mode, void* stream);          /* fxparray.py:287-307 */
+int s5b200_fxp_change_cfg(const int32_t* x, int32_t* y, long long n, int bits, int exp, int new_bits, int new_exp,
+                          int round_mode, void* stream);                                                                   /* fxparray.py:232-271 */
+int s5b200_fxp_add(const int32_t* a, const int32_t* b, int32_t* y, long long n, long long nb, int a_bits, int a_exp,
+                   int b_bits, int b_exp, int result_bits, int result_exp, int round_mode, void* stream);                  /* fxparray.py:449-455 */
+int s5b200_fxp_mul(const int32_t* a, const int32_t* b, int32_t* y, long long n, long long nb, int a_exp, int b_exp,
+                   int result_bits, int result_exp, int round_mode, void* stream);                                         /* fxparray.py:573-637 */
+/* result_exp="compute_best" variants: the exponent is derived on the device from max|.| in float32
+ * (fxparray.py:420-448, :601-609) and returned through result_exp_host.  Synchronises the stream. */
+int s5b200_fxp_add_compute_best(const int32_t* a, const int32_t* b, int32_t* y, long long n, long long nb, int a_bits,
+                                int a_exp, int b_bits, int b_exp, int result_bits, int* result_exp_host, void* stream);
+int s5b200_fxp_mul_compute_best(const int32_t* a, const int32_t* b, int32_t* y, long long n, long long nb, int a_exp,
+                                int b_exp, int result_bits, int* result_exp_host, void* stream);
+int s5b200_fxp_relu(const int32_t* x, int32_t* y, long long n, void* stream);                                              /* fxpmodel.py:53-63 */
+int s5b200_fxp_sigmoid(const int32_t* x, int32_t* y, long long n, int bits, int exp, int x_exp, int y_exp,
+                       const int32_t* lut8_host, void* stream);                                                            /* fxpmodel.py:70-144 */
+
+#ifdef __cplusplus
+}
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#endif /* S5B200_H_ */

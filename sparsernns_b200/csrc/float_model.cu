@@ -1,0 +1,592 @@
+// float_model.cu - float32 and static fake-quant (w8a16) S5 / NDNS forward.
+//
+// Reference path (paths relative to the reference repo):
+//   QRegressionModel.__call__        sparseRNNs/model/seq_model.py:439-456  (encoder Dense -> blocks -> decoder Dense)
+//   QSequenceLayer.__call__          sparseRNNs/model/layers.py:180-241     (BN -> SSM -> act -> GLU half1 -> +skip -> ReLU)
+//   qS5SSM.__call__ / apply_ssm      sparseRNNs/model/ssm.py:84-185, 194-343, 525-622
+//   QuantizedDense / FakeQuant       sparseRNNs/utils/quantization.py:386-448, 684-816
+//
+// Kernels per forward: encoder linear, then per block {BN+B-projection linear, scan_c64, C-projection+GLU},
+// decoder linear.  Bu/xs are the only SSM intermediates that touch HBM.
+#include <algorithm>
+#include <mutex>
+#include <vector>
+
+#include "proj.cuh"
+#include "scan.cuh"
+
+namespace s5 {
+
+// ------------------------------------------------------------------------------------------- sparse
+int sparse_build(const void* W_host, int K, int N, int dtype, int dense_format, SparseDev* out) {
+  if (!W_host || !out) S5_FAIL(S5_E_BADARG, "sparse_create: null pointer");
+  if (K <= 0 || N <= 0 || K > 4096 || N > 4096) S5_FAIL(S5_E_BADSHAPE, "sparse_create: K=%d N=%d outside [1,4096]", K, N);
+  if (dtype != S5_F32 && dtype != S5_I32) S5_FAIL(S5_E_BADARG, "sparse_create: dtype %d", dtype);
+  const int* wb = reinterpret_cast<const int*>(W_host);
+  const float* wf = reinterpret_cast<const float*>(W_host);
+  out->K = K; out->N = N; out->dense = dense_format ? 1 : 0; out->dtype = dtype;
+  std::vector<int> colptr(N + 1, 0);
+  std::vector<SpEntry> ent;
+  out->h_k.clear(); out->h_n.clear();
+  for (int n = 0; n < N; ++n) {
+    for (int k = 0; k < K; ++k) {
+      const size_t i = (size_t)k * N + n;
+      const bool nz = dtype == S5_F32 ? (wf[i] != 0.0f) : (wb[i] != 0);
+      if (nz) {
+        ent.push_back(SpEntry{k, wb[i]});
+        out->h_k.push_back(k);
+        out->h_n.push_back(n);
+      }
+    }
+    colptr[n + 1] = (int)ent.size();
+  }
+  out->nnz = (int)ent.size();
+  S5_CUDA(cudaMalloc(&out->colptr, (N + 1) * sizeof(int)));
+  S5_CUDA(cudaMemcpy(out->colptr, colptr.data(), (N + 1) * sizeof(int), cudaMemcpyHostToDevice));
+  S5_CUDA(cudaMalloc(&out->ent, std::max<size_t>(1, ent.size()) * sizeof(SpEntry)));
+  if (!ent.empty()) S5_CUDA(cudaMemcpy(out->ent, ent.data(), ent.size() * sizeof(SpEntry), cudaMemcpyHostToDevice));
+  if (out->dense) {
+    std::vector<int> wd((size_t)K * N);
+    for (int n = 0; n < N; ++n)
+      for (int k = 0; k < K; ++k) wd[(size_t)n * K + k] = wb[(size_t)k * N + n];
+    S5_CUDA(cudaMalloc(&out->wdense, wd.size() * sizeof(int)));
+    S5_CUDA(cudaMemcpy(out->wdense, wd.data(), wd.size() * sizeof(int), cudaMemcpyHostToDevice));
+  }
+  return S5_OK;
+}
+
+void sparse_free(SparseDev* w) {
+  if (!w) return;
+  cudaFree(w->colptr); cudaFree(w->ent); cudaFree(w->wdense);
+  w->colptr = nullptr; w->ent = nullptr; w->wdense = nullptr;
+}
+
+static inline size_t wsmem_words_host(const WView& s) {
+  size_t w = s.dense ? (size_t)s.K * s.N : (size_t)s.nnz * 2 + (size_t)(s.N + 1);
+  return (w + 1) & ~(size_t)1;
+}
+
+constexpr size_t kSmemMax = 227 * 1024;
+
+// ------------------------------------------------------------------------------------------- linear
+struct LinearParams {
+  const float* X; float* Y; long long rows; WView w;
+  const float* in_sub; const float* in_mul; const float* in_add;  // u = (x - sub) * mul + add when in_sub != null
+  int in_quant; float in_scale, in_qmin, in_qmax;
+  const float* bias;
+  int out_quant; float out_scale0, out_scale1, out_qmin, out_qmax;  // scale0 for even n, scale1 for odd n
+  int relu;
+};
+
+template <int TR>
+__global__ void __launch_bounds__(kProjThreads) linear_f32_kernel(LinearParams p) {
+  constexpr int R = TR / 32;
+  extern __shared__ __align__(16) int smem_i[];
+  const int K = p.w.K, N = p.w.N;
+  size_t ww = wsmem_words(p.w);
+  ww = (ww + 1) & ~(size_t)1;
+  const WSmem w = wsmem_load(smem_i, p.w);
+  float* xt = reinterpret_cast<float*>(smem_i + ww);
+  float* yt = xt + (size_t)K * (TR + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long ntiles = (p.rows + TR - 1) / TR;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long row0 = tile * TR;
+    const int rv = (int)min((long long)TR, p.rows - row0);
+    stage_rows<float, float, TR>(xt, p.X + row0 * K, rv, K, [&](float v, int k) {
+      if (p.in_sub) v = (v - p.in_sub[k]) * p.in_mul[k] + p.in_add[k];
+      if (p.in_quant) v = fake_quant(v, p.in_scale, p.in_qmin, p.in_qmax);
+      return v;
+    });
+    __syncthreads();
+    for (int n = warp; n < N; n += kProjWarps) {
+      float acc[R];
+      column_dot<float, R, TR>(w, K, n, xt, lane, acc);
+      const float bn = p.bias ? p.bias[n] : 0.f;
+      const float sc = (n & 1) ? p.out_scale1 : p.out_scale0;
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+        float v = acc[j] + bn;
+        if (p.out_quant) v = fake_quant(v, sc, p.out_qmin, p.out_qmax);
+        if (p.relu) v = fmaxf(v, 0.f);
+        yt[(size_t)n * (TR + 1) + lane + 32 * j] = v;
+      }
+    }
+    __syncthreads();
+    unstage_rows<float, float, TR>(p.Y + row0 * N, yt, rv, N, [](float v, int, int) { return v; });
+    // the next iteration's staging only writes xt; its __syncthreads orders yt reuse
+  }
+}
+
+static int pick_tr(size_t fixed_bytes, size_t per_row_bytes) {
+  // prefer two resident CTAs per SM, then anything that fits
+  const int cands[3] = {128, 64, 32};
+  for (int tr : cands)
+    if (fixed_bytes + per_row_bytes * (tr + 1) <= kSmemMax / 2 - 1024) return tr;
+  for (int tr : cands)
+    if (fixed_bytes + per_row_bytes * (tr + 1) <= kSmemMax) return tr;
+  return 0;
+}
+
+template <typename KernelT>
+static int persistent_grid(KernelT kernel, size_t smem, long long ntiles, int* grid_out) {
+  int per_sm = 0;
+  S5_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  S5_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kProjThreads, smem));
+  if (per_sm < 1) S5_FAIL(S5_E_BADSHAPE, "kernel does not fit on an SM with %zu bytes of shared memory", smem);
+  const long long g = std::min<long long>(ntiles, (long long)per_sm * sm_count());
+  *grid_out = (int)std::max<long long>(1, g);
+  return S5_OK;
+}
+
+static int launch_linear(LinearParams p, cudaStream_t st) {
+  if (p.rows <= 0) S5_FAIL(S5_E_BADSHAPE, "linear: rows=%lld must be positive", p.rows);
+  const size_t wbytes = ((wsmem_words_host(p.w)) * 4);
+  const int tr = pick_tr(wbytes, (size_t)(p.w.K + p.w.N) * 4);
+  if (!tr) S5_FAIL(S5_E_BADSHAPE, "linear: K=%d N=%d weights (%zu B) do not fit in shared memory", p.w.K, p.w.N, wbytes);
+  const size_t smem = wbytes + (size_t)(p.w.K + p.w.N) * (tr + 1) * 4;
+  const long long ntiles = (p.rows + tr - 1) / tr;
+  int grid = 1, rc;
+  switch (tr) {
+    case 128:
+      if ((rc = persistent_grid(linear_f32_kernel<128>, smem, ntiles, &grid))) return rc;
+      linear_f32_kernel<128><<<grid, kProjThreads, smem, st>>>(p);
+      break;
+    case 64:
+      if ((rc = persistent_grid(linear_f32_kernel<64>, smem, ntiles, &grid))) return rc;
+      linear_f32_kernel<64><<<grid, kProjThreads, smem, st>>>(p);
+      break;
+    default:
+      if ((rc = persistent_grid(linear_f32_kernel<32>, smem, ntiles, &grid))) return rc;
+      linear_f32_kernel<32><<<grid, kProjThreads, smem, st>>>(p);
+  }
+  S5_LAUNCH_CHECK();
+  return S5_OK;
+}
+
+// ------------------------------------------------------------------------------------------- C-projection + GLU
+struct GluParams {
+  const float* XS;   // [rows][2P]  scan output (ReLU already applied when relufication)
+  const float* X;    // [rows][H]   block input (skip connection and BatchNorm source); u itself when !bn
+  float* OUT;        // [rows][H]   block output, or y of the SSM when ssm_only
+  long long rows;
+  WView wc, wo;      // C: K = 2P, N = H ; out2: K = H, N = H
+  const float* bn_sub; const float* bn_mul; const float* bn_add;  // null: X already holds u
+  const float* D; const float* out2_bias;
+  float conj_mul;
+  int static_q; float s_ut, s_yt, s_o_act, s_o_out, s_gl, s_gr;
+  float qs_min, qs_max, qn_min, qn_max;  // SSM-activation / non-SSM-activation integer ranges
+  int act, relu_out, ssm_only;
+};
+
+__device__ __forceinline__ float gelu_tanh_f(float x) {
+  // jax.nn.gelu(approximate=True)
+  const float c = 0.7978845608028654f;
+  return x * (0.5f * (1.0f + tanhf(c * (x + 0.044715f * (x * x * x)))));
+}
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+template <int TR>
+__global__ void __launch_bounds__(kProjThreads) glu_f32_kernel(GluParams p) {
+  constexpr int R = TR / 32;
+  constexpr int LD = TR + 1;
+  extern __shared__ __align__(16) int smem_i[];
+  const int K1 = p.wc.K, H = p.wc.N;
+  size_t w1 = (wsmem_words(p.wc) + 1) & ~(size_t)1;
+  size_t w2 = p.ssm_only ? 0 : ((wsmem_words(p.wo) + 1) & ~(size_t)1);
+  const WSmem wc = wsmem_load(smem_i, p.wc);
+  WSmem wo{nullptr, nullptr, nullptr};
+  if (!p.ssm_only) wo = wsmem_load(smem_i + w1, p.wo);
+  const int rowsA = K1 > H ? K1 : H;
+  float* bufA = reinterpret_cast<float*>(smem_i + w1 + w2);  // xs tile, later g
+  float* bufB = bufA + (size_t)rowsA * LD;                   // x tile (u source), later FQ(x1) for out2
+  float* bufC = bufB + (size_t)H * LD;                       // x1
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long ntiles = (p.rows + TR - 1) / TR;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long row0 = tile * TR;
+    const int rv = (int)min((long long)TR, p.rows - row0);
+    __syncthreads();  // previous tile's write-out reads bufA
+    stage_rows<float, float, TR>(bufA, p.XS + row0 * K1, rv, K1, [](float v, int) { return v; });
+    stage_rows<float, float, TR>(bufB, p.X + row0 * H, rv, H, [&](float v, int k) {
+      if (p.bn_sub) v = (v - p.bn_sub[k]) * p.bn_mul[k] + p.bn_add[k];
+      if (p.static_q) v = fake_quant(v, p.s_ut, p.qs_min, p.qs_max);
+      return v;  // u (u_q for the static flavour), ssm.py:230
+    });
+    __syncthreads();
+    // y = conj_mul * Re(C x) + D * u  [-> FQ]  -> x1 = act(y)
+    for (int n = warp; n < H; n += kProjWarps) {
+      float acc[R];
+      column_dot<float, R, TR>(wc, K1, n, bufA, lane, acc);
+      const float dn = p.D[n];
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+        const size_t o = (size_t)n * LD + lane + 32 * j;
+        float y = p.conj_mul * acc[j] + dn * bufB[o];
+        if (p.static_q) y = fake_quant(y, p.s_yt, p.qs_min, p.qs_max);
+        if (p.ssm_only) {
+          bufC[o] = y;
+        } else {
+          const float x1 = p.act == S5_ACT_RELU ? fmaxf(y, 0.f) : gelu_tanh_f(y);
+          bufC[o] = x1;
+          bufB[o] = p.static_q ? fake_quant(x1, p.s_o_act, p.qn_min, p.qn_max) : x1;  // QuantizedDense input
+        }
+      }
+    }
+    __syncthreads();
+    if (p.ssm_only) {
+      unstage_rows<float, float, TR>(p.OUT + row0 * H, bufC, rv, H, [](float v, int, int) { return v; });
+      continue;
+    }
+    // o = out2(x1) ; g = FQ(x1) * FQ(sigmoid(o))
+    for (int n = warp; n < H; n += kProjWarps) {
+      float acc[R];
+      column_dot<float, R, TR>(wo, H, n, bufB, lane, acc);
+      const float bn = p.out2_bias[n];
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+        const size_t o = (size_t)n * LD + lane + 32 * j;
+        float ov = acc[j] + bn;
+        if (p.static_q) ov = fake_quant(ov, p.s_o_out, p.qn_min, p.qn_max);
+        float sg = sigmoid_f(ov);
+        float l = bufC[o];
+        if (p.static_q) {
+          sg = fake_quant(sg, p.s_gr, p.qn_min, p.qn_max);
+          l = fake_quant(l, p.s_gl, p.qn_min, p.qn_max);
+        }
+        bufA[o] = l * sg;
+      }
+    }
+    __syncthreads();
+    const float* skip = p.X + row0 * H;
+    const int relu_out = p.relu_out;
+    unstage_rows<float, float, TR>(p.OUT + row0 * H, bufA, rv, H, [=](float g, int r, int n) {
+      const float v = g + skip[(size_t)r * H + n];
+      return relu_out ? fmaxf(v, 0.f) : v;
+    });
+  }
+}
+
+static int launch_glu(GluParams p, cudaStream_t st) {
+  if (p.rows <= 0) S5_FAIL(S5_E_BADSHAPE, "glu: rows=%lld must be positive", p.rows);
+  const int K1 = p.wc.K, H = p.wc.N;
+  const size_t wbytes = (wsmem_words_host(p.wc) + (p.ssm_only ? 0 : wsmem_words_host(p.wo))) * 4;
+  const size_t per_row = (size_t)(std::max(K1, H) + 2 * H) * 4;
+  const int tr = pick_tr(wbytes, per_row);
+  if (!tr) S5_FAIL(S5_E_BADSHAPE, "glu: H=%d 2P=%d weights (%zu B) do not fit in shared memory", H, K1, wbytes);
+  const size_t smem = wbytes + per_row * (tr + 1);
+  const long long ntiles = (p.rows + tr - 1) / tr;
+  int grid = 1, rc;
+  switch (tr) {
+    case 128:
+      if ((rc = persistent_grid(glu_f32_kernel<128>, smem, ntiles, &grid))) return rc;
+      glu_f32_kernel<128><<<grid, kProjThreads, smem, st>>>(p);
+      break;
+    case 64:
+      if ((rc = persistent_grid(glu_f32_kernel<64>, smem, ntiles, &grid))) return rc;
+      glu_f32_kernel<64><<<grid, kProjThreads, smem, st>>>(p);
+      break;
+    default:
+      if ((rc = persistent_grid(glu_f32_kernel<32>, smem, ntiles, &grid))) return rc;
+      glu_f32_kernel<32><<<grid, kProjThreads, smem, st>>>(p);
+  }
+  S5_LAUNCH_CHECK();
+  return S5_OK;
+}
+
+}  // namespace s5
+
+// ------------------------------------------------------------------------------------------- handles
+namespace s5 {
+
+struct LayerDev {
+  SparseDev wb, wc, wo;
+  float *lam = nullptr, *D = nullptr, *bn_mean = nullptr, *bn_mul = nullptr, *bn_bias = nullptr, *o_bias = nullptr;
+  s5_layer_desc sc;  // scales only (pointers unused)
+};
+
+static int upload(const float* h, size_t n, float** d) {
+  if (!h) S5_FAIL(S5_E_BADARG, "model_create: null parameter array");
+  S5_CUDA(cudaMalloc(d, std::max<size_t>(1, n) * sizeof(float)));
+  S5_CUDA(cudaMemcpy(*d, h, n * sizeof(float), cudaMemcpyHostToDevice));
+  return S5_OK;
+}
+
+}  // namespace s5
+
+struct s5_model {
+  s5_model_desc desc;
+  s5::SparseDev enc, dec;
+  float *enc_bias = nullptr, *dec_bias = nullptr;
+  std::vector<s5::LayerDev> layers;
+  // cached device buffers for the host-buffer entry point
+  std::mutex mu;
+  float *hx = nullptr, *hy = nullptr; void* hws = nullptr;
+  size_t hx_cap = 0, hy_cap = 0, hws_cap = 0;
+};
+
+namespace s5 {
+
+static void qrange(int bits, float* lo, float* hi) {
+  *lo = -(float)(1 << (bits - 1));
+  *hi = (float)((1 << (bits - 1)) - 1);
+}
+
+struct WsLayout {
+  size_t off_a, off_b, off_bu, off_scan, scan_bytes, total;
+};
+static WsLayout ws_layout(const s5_model* m, int B, int L) {
+  const size_t rows = (size_t)B * L;
+  WsLayout w;
+  const size_t act = round_up(rows * m->desc.H * sizeof(float), 256);
+  w.off_a = 0;
+  w.off_b = act;
+  w.off_bu = 2 * act;
+  w.off_scan = w.off_bu + round_up(rows * m->desc.P * 2 * sizeof(float), 256);
+  w.scan_bytes = s5b200_scan_c64_workspace_bytes(B, L, m->desc.P);
+  w.total = w.off_scan + round_up(w.scan_bytes, 256);
+  return w;
+}
+
+static int check_model_args(const s5_model* m, const void* a, const void* b, int B, int L, void* ws, size_t wsb,
+                            const char* what) {
+  if (!m || !a || !b || !ws) S5_FAIL(S5_E_BADARG, "%s: null pointer", what);
+  if (B <= 0 || L <= 0 || B > 65535) S5_FAIL(S5_E_BADSHAPE, "%s: B=%d L=%d outside the supported range", what, B, L);
+  const size_t need = ws_layout(m, B, L).total;
+  if (wsb < need) S5_FAIL(S5_E_BADARG, "%s: workspace %zu < %zu bytes", what, wsb, need);
+  if (!aligned16(ws)) S5_FAIL(S5_E_BADARG, "%s: workspace must be 16-byte aligned", what);
+  return S5_OK;
+}
+
+static LinearParams bproj_params(const s5_model* m, const LayerDev& ld, const float* x, float* bu, long long rows, bool bn) {
+  const bool sq = m->desc.flavour == S5_STATIC;
+  LinearParams p{};
+  p.X = x; p.Y = bu; p.rows = rows; p.w = wview(ld.wb);
+  if (bn) { p.in_sub = ld.bn_mean; p.in_mul = ld.bn_mul; p.in_add = ld.bn_bias; }
+  p.in_quant = sq; p.in_scale = ld.sc.s_ut;
+  qrange(m->desc.ssm_act_bits, &p.in_qmin, &p.in_qmax);
+  p.bias = nullptr;
+  p.out_quant = sq; p.out_scale0 = ld.sc.s_But_re; p.out_scale1 = ld.sc.s_But_im;
+  qrange(m->desc.ssm_act_bits, &p.out_qmin, &p.out_qmax);
+  p.relu = 0;
+  return p;
+}
+
+static GluParams glu_params(const s5_model* m, const LayerDev& ld, const float* xs, const float* x, float* out,
+                            long long rows, bool bn, bool ssm_only) {
+  const bool sq = m->desc.flavour == S5_STATIC;
+  GluParams p{};
+  p.XS = xs; p.X = x; p.OUT = out; p.rows = rows; p.wc = wview(ld.wc); p.wo = wview(ld.wo);
+  if (bn) { p.bn_sub = ld.bn_mean; p.bn_mul = ld.bn_mul; p.bn_add = ld.bn_bias; }
+  p.D = ld.D; p.out2_bias = ld.o_bias;
+  p.conj_mul = m->desc.conj_sym ? 2.f : 1.f;
+  p.static_q = sq;
+  p.s_ut = ld.sc.s_ut; p.s_yt = ld.sc.s_yt; p.s_o_act = ld.sc.s_out2_act; p.s_o_out = ld.sc.s_out2_out;
+  p.s_gl = ld.sc.s_gate_left; p.s_gr = ld.sc.s_gate_right;
+  qrange(m->desc.ssm_act_bits, &p.qs_min, &p.qs_max);
+  qrange(m->desc.non_ssm_act_bits, &p.qn_min, &p.qn_max);
+  p.act = m->desc.activation; p.relu_out = m->desc.relufication; p.ssm_only = ssm_only;
+  return p;
+}
+
+// One S5 block: x [rows][H] -> out [rows][H]; bu is the [rows][P] complex scratch (Bu, then xs in place).
+static int run_block(const s5_model* m, int li, const float* x, float* out, float* bu, int B, int L, void* scan_ws,
+                     size_t scan_ws_bytes, bool bn, bool ssm_only, cudaStream_t st) {
+  const LayerDev& ld = m->layers[li];
+  const long long rows = (long long)B * L;
+  int rc;
+  if ((rc = launch_linear(bproj_params(m, ld, x, bu, rows, bn), st))) return rc;
+  if ((rc = launch_scan_c64(bu, ld.lam, bu, B, L, m->desc.P, m->desc.relufication, scan_ws, scan_ws_bytes, st))) return rc;
+  return launch_glu(glu_params(m, ld, bu, x, out, rows, bn, ssm_only), st);
+}
+
+static LinearParams dense_params(const s5_model* m, const SparseDev& w, const float* bias, const float* x, float* y,
+                                 long long rows, float s_act, float s_out, int relu) {
+  const bool sq = m->desc.flavour == S5_STATIC;
+  LinearParams p{};
+  p.X = x; p.Y = y; p.rows = rows; p.w = wview(w);
+  p.in_quant = sq; p.in_scale = s_act;
+  qrange(m->desc.non_ssm_act_bits, &p.in_qmin, &p.in_qmax);
+  p.bias = bias;
+  p.out_quant = sq; p.out_scale0 = p.out_scale1 = s_out;
+  qrange(m->desc.non_ssm_act_bits, &p.out_qmin, &p.out_qmax);
+  p.relu = relu;
+  return p;
+}
+
+}  // namespace s5
+
+extern "C" int s5b200_sparse_create(const void* W_host, int K, int N, int dtype, int dense_format, s5_sparse** out) {
+  if (!out) S5_FAIL(S5_E_BADARG, "sparse_create: null out");
+  s5_sparse* h = new s5_sparse();
+  const int rc = s5::sparse_build(W_host, K, N, dtype, dense_format, &h->d);
+  if (rc) { s5::sparse_free(&h->d); delete h; return rc; }
+  *out = h;
+  return S5_OK;
+}
+extern "C" int s5b200_sparse_destroy(s5_sparse* w) {
+  if (!w) return S5_OK;
+  s5::sparse_free(&w->d);
+  delete w;
+  return S5_OK;
+}
+extern "C" int s5b200_sparse_nnz(const s5_sparse* w) { return w ? w->d.nnz : 0; }
+extern "C" int s5b200_sparse_export(const s5_sparse* w, int32_t* k_idx_host, int32_t* n_idx_host) {
+  if (!w || !k_idx_host || !n_idx_host) S5_FAIL(S5_E_BADARG, "sparse_export: null pointer");
+  std::copy(w->d.h_k.begin(), w->d.h_k.end(), k_idx_host);
+  std::copy(w->d.h_n.begin(), w->d.h_n.end(), n_idx_host);
+  return S5_OK;
+}
+extern "C" int s5b200_spmm_f32(const s5_sparse* w, const float* X, const float* bias, float* Y, long long rows,
+                               int skip_zero_cols, void* stream) {
+  (void)skip_zero_cols;
+  if (!w || !X || !Y) S5_FAIL(S5_E_BADARG, "spmm_f32: null pointer");
+  if (w->d.dtype != S5_F32) S5_FAIL(S5_E_BADARG, "spmm_f32: handle holds int32 weights");
+  s5::LinearParams p{};
+  p.X = X; p.Y = Y; p.rows = rows; p.w = s5::wview(w->d); p.bias = bias;
+  return s5::launch_linear(p, (cudaStream_t)stream);
+}
+
+extern "C" int s5b200_model_create(const s5_model_desc* d, s5_model** out) {
+  using namespace s5;
+  if (!d || !out || !d->layers) S5_FAIL(S5_E_BADARG, "model_create: null pointer");
+  if (d->flavour != S5_FLOAT && d->flavour != S5_STATIC) S5_FAIL(S5_E_BADARG, "model_create: flavour %d", d->flavour);
+  if (d->n_layers < 1 || d->n_layers > 64 || d->H < 1 || d->H > 1024 || d->P < 2 || d->P > 256 || (d->P & 1) ||
+      d->d_input < 1 || d->d_input > 4096 || d->d_output < 1 || d->d_output > 4096)
+    S5_FAIL(S5_E_BADSHAPE, "model_create: n_layers=%d H=%d P=%d d_input=%d d_output=%d unsupported", d->n_layers, d->H,
+            d->P, d->d_input, d->d_output);
+  if (d->flavour == S5_STATIC && (d->ssm_act_bits < 2 || d->ssm_act_bits > 24 || d->non_ssm_act_bits < 2 || d->non_ssm_act_bits > 24))
+    S5_FAIL(S5_E_BADARG, "model_create: activation bit widths must be in [2, 24]");
+  s5_model* m = new s5_model();
+  m->desc = *d;
+  m->desc.layers = nullptr;
+  const int H = d->H, P = d->P, dense = d->use_sparse ? 0 : 1;
+  int rc = S5_OK;
+  auto fail = [&](int code) { s5b200_model_destroy(m); return code; };
+  if ((rc = sparse_build(d->enc_kernel_host, d->d_input, H, S5_F32, dense, &m->enc))) return fail(rc);
+  if ((rc = sparse_build(d->dec_kernel_host, H, d->d_output, S5_F32, dense, &m->dec))) return fail(rc);
+  if ((rc = upload(d->enc_bias_host, H, &m->enc_bias))) return fail(rc);
+  if ((rc = upload(d->dec_bias_host, d->d_output, &m->dec_bias))) return fail(rc);
+  m->layers.resize(d->n_layers);
+  for (int i = 0; i < d->n_layers; ++i) {
+    const s5_layer_desc& l = d->layers[i];
+    LayerDev& ld = m->layers[i];
+    ld.sc = l;
+    if (!l.B_bar_host || !l.C_tilde_host) return fail((set_error("model_create: null SSM matrix"), S5_E_BADARG));
+    // B: [P][H][2] -> W[h][2p + c];  C: [H][P][2] -> W[2p][h] = C_re, W[2p+1][h] = -C_im  (Re(C x))
+    std::vector<float> wb((size_t)H * 2 * P), wc((size_t)2 * P * H);
+    for (int p = 0; p < P; ++p)
+      for (int h = 0; h < H; ++h) {
+        wb[(size_t)h * 2 * P + 2 * p] = l.B_bar_host[((size_t)p * H + h) * 2];
+        wb[(size_t)h * 2 * P + 2 * p + 1] = l.B_bar_host[((size_t)p * H + h) * 2 + 1];
+        wc[(size_t)(2 * p) * H + h] = l.C_tilde_host[((size_t)h * P + p) * 2];
+        wc[(size_t)(2 * p + 1) * H + h] = -l.C_tilde_host[((size_t)h * P + p) * 2 + 1];
+      }
+    if ((rc = sparse_build(wb.data(), H, 2 * P, S5_F32, dense, &ld.wb))) return fail(rc);
+    if ((rc = sparse_build(wc.data(), 2 * P, H, S5_F32, dense, &ld.wc))) return fail(rc);
+    if ((rc = sparse_build(l.out2_kernel_host, H, H, S5_F32, dense, &ld.wo))) return fail(rc);
+    if ((rc = upload(l.lambda_bar_host, 2 * P, &ld.lam))) return fail(rc);
+    if ((rc = upload(l.D_host, H, &ld.D))) return fail(rc);
+    if ((rc = upload(l.bn_mean_host, H, &ld.bn_mean))) return fail(rc);
+    if ((rc = upload(l.bn_mul_host, H, &ld.bn_mul))) return fail(rc);
+    if ((rc = upload(l.bn_bias_host, H, &ld.bn_bias))) return fail(rc);
+    if ((rc = upload(l.out2_bias_host, H, &ld.o_bias))) return fail(rc);
+  }
+  *out = m;
+  return S5_OK;
+}
+
+extern "C" int s5b200_model_destroy(s5_model* m) {
+  if (!m) return S5_OK;
+  s5::sparse_free(&m->enc); s5::sparse_free(&m->dec);
+  cudaFree(m->enc_bias); cudaFree(m->dec_bias);
+  for (auto& l : m->layers) {
+    s5::sparse_free(&l.wb); s5::sparse_free(&l.wc); s5::sparse_free(&l.wo);
+    cudaFree(l.lam); cudaFree(l.D); cudaFree(l.bn_mean); cudaFree(l.bn_mul); cudaFree(l.bn_bias); cudaFree(l.o_bias);
+  }
+  cudaFree(m->hx); cudaFree(m->hy); cudaFree(m->hws);
+  delete m;
+  return S5_OK;
+}
+
+extern "C" size_t s5b200_model_workspace_bytes(const s5_model* m, int B, int L) {
+  if (!m || B <= 0 || L <= 0) return 0;
+  return s5::ws_layout(m, B, L).total;
+}
+
+extern "C" int s5b200_model_forward(const s5_model* m, const float* x, float* y, int B, int L, void* workspace,
+                                    size_t workspace_bytes, void* stream) {
+  using namespace s5;
+  int rc;
+  if ((rc = check_model_args(m, x, y, B, L, workspace, workspace_bytes, "model_forward"))) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const WsLayout w = ws_layout(m, B, L);
+  unsigned char* base = reinterpret_cast<unsigned char*>(workspace);
+  float* a = reinterpret_cast<float*>(base + w.off_a);
+  float* b = reinterpret_cast<float*>(base + w.off_b);
+  float* bu = reinterpret_cast<float*>(base + w.off_bu);
+  const long long rows = (long long)B * L;
+  const s5_model_desc& d = m->desc;
+  if ((rc = launch_linear(dense_params(m, m->enc, m->enc_bias, x, a, rows, d.s_enc_act, d.s_enc_out, d.relufication), st))) return rc;
+  for (int i = 0; i < d.n_layers; ++i) {
+    if ((rc = run_block(m, i, a, b, bu, B, L, base + w.off_scan, w.scan_bytes, true, false, st))) return rc;
+    std::swap(a, b);
+  }
+  return launch_linear(dense_params(m, m->dec, m->dec_bias, a, y, rows, d.s_dec_act, d.s_dec_out, 0), st);
+}
+
+extern "C" int s5b200_layer_forward(const s5_model* m, int layer, const float* x, float* y, float* xs_out, int B, int L,
+                                    void* workspace, size_t workspace_bytes, void* stream) {
+  using namespace s5;
+  int rc;
+  if ((rc = check_model_args(m, x, y, B, L, workspace, workspace_bytes, "layer_forward"))) return rc;
+  if (layer < 0 || layer >= m->desc.n_layers) S5_FAIL(S5_E_BADARG, "layer_forward: layer %d out of range", layer);
+  const WsLayout w = ws_layout(m, B, L);
+  unsigned char* base = reinterpret_cast<unsigned char*>(workspace);
+  float* bu = xs_out ? xs_out : reinterpret_cast<float*>(base + w.off_bu);
+  if (!aligned16(bu)) S5_FAIL(S5_E_BADARG, "layer_forward: xs_out must be 16-byte aligned");
+  return run_block(m, layer, x, y, bu, B, L, base + w.off_scan, w.scan_bytes, true, false, (cudaStream_t)stream);
+}
+
+extern "C" int s5b200_ssm_forward(const s5_model* m, int layer, const float* u, float* y, float* xs_out, int B, int L,
+                                  void* workspace, size_t workspace_bytes, void* stream) {
+  using namespace s5;
+  int rc;
+  if ((rc = check_model_args(m, u, y, B, L, workspace, workspace_bytes, "ssm_forward"))) return rc;
+  if (layer < 0 || layer >= m->desc.n_layers) S5_FAIL(S5_E_BADARG, "ssm_forward: layer %d out of range", layer);
+  const WsLayout w = ws_layout(m, B, L);
+  unsigned char* base = reinterpret_cast<unsigned char*>(workspace);
+  float* bu = xs_out ? xs_out : reinterpret_cast<float*>(base + w.off_bu);
+  if (!aligned16(bu)) S5_FAIL(S5_E_BADARG, "ssm_forward: xs_out must be 16-byte aligned");
+  return run_block(m, layer, u, y, bu, B, L, base + w.off_scan, w.scan_bytes, false, true, (cudaStream_t)stream);
+}
+
+extern "C" int s5b200_model_forward_host(const s5_model* mc, const float* x_host, float* y_host, int B, int L,
+                                         void* stream) {
+  using namespace s5;
+  s5_model* m = const_cast<s5_model*>(mc);
+  if (!m || !x_host || !y_host) S5_FAIL(S5_E_BADARG, "model_forward_host: null pointer");
+  if (B <= 0 || L <= 0 || B > 65535) S5_FAIL(S5_E_BADSHAPE, "model_forward_host: B=%d L=%d outside the supported range", B, L);
+  cudaStream_t st = (cudaStream_t)stream;
+  std::lock_guard<std::mutex> lock(m->mu);
+  const size_t rows = (size_t)B * L;
+  const size_t xb = rows * m->desc.d_input * sizeof(float), yb = rows * m->desc.d_output * sizeof(float);
+  const size_t wsb = ws_layout(m, B, L).total;
+  auto grow = [&](void** p, size_t* cap, size_t need) -> int {
+    if (*cap >= need) return S5_OK;
+    if (*p) S5_CUDA(cudaFree(*p));
+    *p = nullptr; *cap = 0;
+    S5_CUDA(cudaMalloc(p, need));
+    *cap = need;
+    return S5_OK;
+  };
+  int rc;
+  if ((rc = grow(reinterpret_cast<void**>(&m->hx), &m->hx_cap, xb))) return rc;
+  if ((rc = grow(reinterpret_cast<void**>(&m->hy), &m->hy_cap, yb))) return rc;
+  if ((rc = grow(&m->hws, &m->hws_cap, wsb))) return rc;
+  S5_CUDA(cudaMemcpyAsync(m->hx, x_host, xb, cudaMemcpyHostToDevice, st));
+  if ((rc = s5b200_model_forward(m, m->hx, m->hy, B, L, m->hws, m->hws_cap, stream))) return rc;
+  S5_CUDA(cudaMemcpyAsync(y_host, m->hy, yb, cudaMemcpyDeviceToHost, st));
+  S5_CUDA(cudaStreamSynchronize(st));
+  return S5_OK;
+}

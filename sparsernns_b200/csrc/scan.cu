@@ -1,0 +1,312 @@
+// scan.cu - diagonal linear recurrences of the S5 SSM.
+//
+//  (1) scan_c64: x_k = lam * x_{k-1} + Bu_k in complex64, replacing jax.lax.associative_scan /
+//      jax.lax.scan (reference sparseRNNs/model/ssm.py:127, :150, :313).  Single pass over HBM:
+//      each CTA owns one time chunk [TL][P] of one clip, brought in by one 1-D bulk async copy (TMA
+//      engine, UBLKCP) and written back by one bulk store.  Inside the chunk every thread owns one
+//      state p of one sub-chunk of T consecutive steps; sub-chunk and chunk carries are combined with
+//      Horner steps on lam^T / lam^TL, the cross-chunk carry travels through a decoupled look-back
+//      (aggregate / inclusive records + flags in a caller-provided workspace).
+//  (2) scan_i32: the integer recurrence of fxpmodel.py:147-208.  It floors every product separately, so it
+//      is not associative and must be sequential in time; one lane per (clip, state), register
+//      prefetch ring over time.
+#include "scan.cuh"
+
+namespace s5 {
+
+constexpr int kScanT = 16;        // steps a thread scans sequentially (sub-chunk length)
+constexpr int kScanThreads = 256;  // upper bound for nsub * P
+
+struct ScanGeom {
+  int nsub, threads, TL, nchunks;
+  size_t flags_bytes, rec_floats2;  // per-(clip, chunk) record: agg[P] + incl[P] (double2 each)
+  size_t smem_bytes;
+};
+
+static ScanGeom scan_geom(int L, int P) {
+  ScanGeom g;
+  g.nsub = kScanThreads / P;
+  if (g.nsub < 1) g.nsub = 1;
+  g.threads = g.nsub * P;
+  g.TL = g.nsub * kScanT;
+  g.nchunks = (L + g.TL - 1) / g.TL;
+  g.rec_floats2 = 2 * (size_t)round_up((size_t)P, 16);
+  g.smem_bytes = (size_t)g.TL * P * 8 + (size_t)g.nsub * P * 8 + (size_t)P * 16 + 16;
+  return g;
+}
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+// a * x + v
+__device__ __forceinline__ float2 cfma(float2 a, float2 x, float2 v) {
+  return make_float2(fmaf(a.x, x.x, fmaf(-a.y, x.y, v.x)), fmaf(a.x, x.y, fmaf(a.y, x.x, v.y)));
+}
+__device__ __forceinline__ float2 relu_lex(float2 z) {
+  const bool keep = (z.x > 0.f) || (z.x == 0.f && z.y > 0.f);
+  return keep ? z : make_float2(0.f, 0.f);
+}
+
+// double-precision complex helpers: chunk carries are combined in fp64 so that the powers lam^T, lam^TL,
+// lam^(k*TL) do not accumulate an O(k * eps_f32) error (the states themselves stay fp32 like the reference).
+__device__ __forceinline__ double2 zmul(double2 a, double2 b) {
+  return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ double2 zfma(double2 a, double2 x, double2 v) {
+  return make_double2(fma(a.x, x.x, fma(-a.y, x.y, v.x)), fma(a.x, x.y, fma(a.y, x.x, v.y)));
+}
+__device__ __forceinline__ double2 f2z(float2 v) { return make_double2((double)v.x, (double)v.y); }
+
+__global__ void __launch_bounds__(kScanThreads)
+scan_c64_kernel(const float2* __restrict__ Bu, const float2* __restrict__ lam, float2* xs, int L, int P, int nsub,
+                int nchunks, int relu, uint32_t* flags, double2* recs, int rec_stride) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int TL = nsub * kScanT;
+  float2* tile = reinterpret_cast<float2*>(smem_raw);        // [TL][P]
+  float2* sub_agg = tile + (size_t)TL * P;                    // [nsub][P]
+  double2* carry_s = reinterpret_cast<double2*>(sub_agg + (size_t)nsub * P);  // [P]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(carry_s + P);
+
+  const int c = blockIdx.x, b = blockIdx.y;
+  const int tid = threadIdx.x;
+  const int p = tid % P, s = tid / P;
+  const int t0 = c * TL;
+  const int rows = min(TL, L - t0);
+  const size_t base = ((size_t)b * L + t0) * P;
+  const uint32_t bytes = (uint32_t)rows * P * 8u;
+
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(bar, bytes);
+    bulk_g2s(tile, Bu + base, bytes, bar);
+  }
+
+  // lam^T and lam^TL (fp64) while the tile is in flight
+  const float2 a = lam[p];
+  double2 aT = f2z(a);
+#pragma unroll
+  for (int i = 1; i < kScanT; i <<= 1) aT = zmul(aT, aT);
+  double2 aTL = aT;
+  for (int i = 1; i < nsub; ++i) aTL = zmul(aTL, aT);
+
+  mbar_wait(bar, 0);
+
+  // pass 1: local recurrence from zero -> sub-chunk aggregate
+  const int ts = s * kScanT;
+  float2 x = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int j = 0; j < kScanT; ++j) {
+    const int t = ts + j;
+    if (t < rows) x = cfma(a, x, tile[(size_t)t * P + p]);
+  }
+  sub_agg[s * P + p] = x;
+  __syncthreads();
+
+  uint32_t* flag_row = flags + (size_t)b * nchunks;
+  double2* rec_row = recs + (size_t)b * nchunks * rec_stride;
+  const int half = rec_stride >> 1;
+  double2 e = make_double2(0., 0.);
+  const bool publish = (c + 1 < nchunks);  // nobody looks back at the last chunk
+  if (tid < P) {
+    e = f2z(sub_agg[p]);
+    for (int q = 1; q < nsub; ++q) e = zfma(aT, e, f2z(sub_agg[q * P + p]));
+    if (publish) {
+      double2* rec = rec_row + (size_t)c * rec_stride;
+      if (c == 0) __stcg(rec + half + p, e);  // chunk 0: aggregate == inclusive prefix
+      else __stcg(rec + p, e);
+    }
+    if (c == 0) carry_s[p] = make_double2(0., 0.);
+  }
+  if (publish) {
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) st_release_u32(flag_row + c, c == 0 ? 2u : 1u);
+  }
+
+  if (c > 0) {
+    if (tid < P) {
+      // decoupled look-back: walk predecessors until one has published its inclusive prefix
+      double2 mult = make_double2(1., 0.);
+      double2 acc = make_double2(0., 0.);
+      for (int j = c - 1; j >= 0; --j) {
+        uint32_t f;
+        do {
+          f = ld_acquire_u32(flag_row + j);
+        } while (f == 0u);
+        const double2* rec = rec_row + (size_t)j * rec_stride;
+        if (f == 2u) {
+          acc = zfma(mult, __ldcg(rec + half + p), acc);
+          break;
+        }
+        acc = zfma(mult, __ldcg(rec + p), acc);
+        mult = zmul(mult, aTL);
+      }
+      carry_s[p] = acc;
+      if (publish) __stcg(rec_row + (size_t)c * rec_stride + half + p, zfma(aTL, acc, e));
+    }
+    if (publish) {
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) st_release_u32(flag_row + c, 2u);
+    }
+  }
+  __syncthreads();
+
+  // pass 2: recurrence with the true carry-in, results in place
+  double2 cin = carry_s[p];
+  for (int q = 0; q < s; ++q) cin = zfma(aT, cin, f2z(sub_agg[q * P + p]));
+  x = make_float2((float)cin.x, (float)cin.y);
+#pragma unroll
+  for (int j = 0; j < kScanT; ++j) {
+    const int t = ts + j;
+    if (t < rows) {
+      x = cfma(a, x, tile[(size_t)t * P + p]);
+      tile[(size_t)t * P + p] = relu ? relu_lex(x) : x;
+    }
+  }
+  fence_proxy_async_smem();
+  __syncthreads();
+  if (tid == 0) {
+    bulk_s2g(xs + base, tile, bytes);
+    bulk_commit();
+    bulk_wait_read0();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- int
+// int32 product with two's-complement wrap-around (what jnp gives in 32-bit mode)
+__device__ __forceinline__ int mulw(int a, int b) { return (int)((unsigned)a * (unsigned)b); }
+
+__device__ __forceinline__ int shift_align(int v, int e_from, int e_to) {
+  // fxpmodel.py:158-167: >> when the source exponent is larger, << otherwise (wrapping)
+  return (e_from > e_to) ? (v >> (e_from - e_to)) : (int)((unsigned)v << (e_to - e_from));
+}
+
+// fxp_relu on a complex value (fxpmodel.py:30-45): the reference builds complex64, so both parts take a
+// float32 round trip (round-to-nearest-even in, truncation with saturation out).
+__device__ __forceinline__ void fxp_relu_complex(int& re, int& im) {
+  const float fr = (float)re, fi = (float)im;
+  const bool keep = (fr > 0.f) || (fr == 0.f && fi > 0.f);
+  re = keep ? __float2int_rz(fr) : 0;
+  im = keep ? __float2int_rz(fi) : 0;
+}
+
+
+template <bool INTERLEAVED, int DEPTH>
+__global__ void __launch_bounds__(128) scan_i32_kernel(ScanI32Params q) {
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= q.lanes) return;
+  const int p = (int)(g % q.P);
+  const long long b = g / q.P;
+  const int ar = q.A_re[p], ai = q.A_im[p];
+  const size_t stride = (size_t)q.P;
+  size_t idx = (size_t)b * q.L * q.P + p;
+  int xr = 0, xi = 0;
+  int br[DEPTH], bi[DEPTH];
+  auto load = [&](int t, int& r, int& i) {
+    if (t < q.L) {
+      const size_t o = idx + (size_t)t * stride;
+      if (INTERLEAVED) {
+        const int2 v = __ldg(reinterpret_cast<const int2*>(q.Bu_re) + o);
+        r = v.x; i = v.y;
+      } else {
+        r = __ldg(q.Bu_re + o); i = __ldg(q.Bu_im + o);
+      }
+    }
+  };
+#pragma unroll
+  for (int k = 0; k < DEPTH; ++k) load(k, br[k], bi[k]);
+  for (int t0 = 0; t0 < q.L; t0 += DEPTH) {
+#pragma unroll
+    for (int k = 0; k < DEPTH; ++k) {
+      const int t = t0 + k;
+      if (t < q.L) {
+        const int cr = shift_align(br[k], q.eBu_re, q.ex_re);
+        const int ci = shift_align(bi[k], q.eBu_im, q.ex_im);
+        load(t + DEPTH, br[k], bi[k]);
+        // fxpmodel.py:155-156: each product is floored on its own; products and sums wrap in int32
+        const int nr = (int)((unsigned)(mulw(ar, xr) >> q.eA_re) - (unsigned)(mulw(ai, xi) >> q.eA_re) + (unsigned)cr);
+        const int ni = (int)((unsigned)(mulw(ar, xi) >> q.eA_im) + (unsigned)(mulw(ai, xr) >> q.eA_im) + (unsigned)ci);
+        xr = nr; xi = ni;
+        int orr = xr, oi = xi;
+        if (q.relu) fxp_relu_complex(orr, oi);
+        const size_t o = idx + (size_t)t * stride;
+        if (INTERLEAVED) {
+          reinterpret_cast<int2*>(q.xs_re)[o] = make_int2(orr, oi);
+        } else {
+          q.xs_re[o] = orr; q.xs_im[o] = oi;
+        }
+      }
+    }
+  }
+}
+
+int launch_scan_i32(const ScanI32Params& q, bool interleaved, cudaStream_t st) {
+  const int threads = 128;
+  const long long blocks = (q.lanes + threads - 1) / threads;
+  if (blocks > 0x7fffffffLL) S5_FAIL(S5_E_BADSHAPE, "scan_i32: too many lanes");
+  if (interleaved) scan_i32_kernel<true, 8><<<(unsigned)blocks, threads, 0, st>>>(q);
+  else scan_i32_kernel<false, 8><<<(unsigned)blocks, threads, 0, st>>>(q);
+  S5_LAUNCH_CHECK();
+  return S5_OK;
+}
+
+int launch_scan_c64(const float* Bu, const float* lam, float* xs, int B, int L, int P, int relu, void* workspace,
+                    size_t workspace_bytes, cudaStream_t st) {
+  if (B <= 0 || L <= 0) S5_FAIL(S5_E_BADSHAPE, "scan_c64: B=%d L=%d must be positive", B, L);
+  if (P < 2 || P > kScanThreads || (P & 1)) S5_FAIL(S5_E_BADSHAPE, "scan_c64: P=%d must be even and in [2, %d]", P, kScanThreads);
+  if (B > 65535) S5_FAIL(S5_E_BADSHAPE, "scan_c64: B=%d exceeds 65535 clips per call", B);
+  if (!Bu || !lam || !xs || !workspace) S5_FAIL(S5_E_BADARG, "scan_c64: null pointer");
+  if (!aligned16(Bu) || !aligned16(xs) || !aligned16(workspace)) S5_FAIL(S5_E_BADARG, "scan_c64: pointers must be 16-byte aligned");
+  const size_t need = s5b200_scan_c64_workspace_bytes(B, L, P);
+  if (workspace_bytes < need) S5_FAIL(S5_E_BADARG, "scan_c64: workspace %zu < %zu bytes", workspace_bytes, need);
+  const ScanGeom g = scan_geom(L, P);
+  static bool attr_set = false;
+  if (!attr_set) {
+    S5_CUDA(cudaFuncSetAttribute(scan_c64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    attr_set = true;
+  }
+  const size_t flags_bytes = round_up((size_t)B * g.nchunks * sizeof(uint32_t), 256);
+  uint32_t* flags = reinterpret_cast<uint32_t*>(workspace);
+  double2* recs = reinterpret_cast<double2*>(reinterpret_cast<unsigned char*>(workspace) + flags_bytes);
+  S5_CUDA(cudaMemsetAsync(flags, 0, flags_bytes, st));
+  dim3 grid(g.nchunks, B);
+  scan_c64_kernel<<<grid, g.threads, g.smem_bytes, st>>>(reinterpret_cast<const float2*>(Bu),
+                                                         reinterpret_cast<const float2*>(lam),
+                                                         reinterpret_cast<float2*>(xs), L, P, g.nsub, g.nchunks, relu,
+                                                         flags, recs, (int)g.rec_floats2);
+  S5_LAUNCH_CHECK();
+  return S5_OK;
+}
+
+}  // namespace s5
+
+extern "C" size_t s5b200_scan_c64_workspace_bytes(int B, int L, int P) {
+  if (B <= 0 || L <= 0 || P <= 0 || P > s5::kScanThreads) return 0;
+  const s5::ScanGeom g = s5::scan_geom(L, P);
+  return s5::round_up((size_t)B * g.nchunks * sizeof(uint32_t), 256) + (size_t)B * g.nchunks * g.rec_floats2 * sizeof(double2);
+}
+
+extern "C" int s5b200_scan_c64(const float* Bu, const float* lam, float* xs, int B, int L, int P, int relu,
+                               void* workspace, size_t workspace_bytes, void* stream) {
+  return s5::launch_scan_c64(Bu, lam, xs, B, L, P, relu, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int s5b200_scan_i32(const int32_t* Bu_re, const int32_t* Bu_im, const int32_t* A_re, const int32_t* A_im,
+                               int32_t* xs_re, int32_t* xs_im, int B, int L, int P, int eA_re, int eA_im, int eBu_re,
+                               int eBu_im, int ex_re, int ex_im, int relu, void* stream) {
+  if (B <= 0 || L <= 0 || P <= 0) S5_FAIL(S5_E_BADSHAPE, "scan_i32: B=%d L=%d P=%d must be positive", B, L, P);
+  if (!Bu_re || !Bu_im || !A_re || !A_im || !xs_re || !xs_im) S5_FAIL(S5_E_BADARG, "scan_i32: null pointer");
+  if (eA_re < 0 || eA_re > 31 || eA_im < 0 || eA_im > 31) S5_FAIL(S5_E_BADARG, "scan_i32: A exponent outside [0,31]");
+  if (eBu_re - ex_re > 31 || ex_re - eBu_re > 31 || eBu_im - ex_im > 31 || ex_im - eBu_im > 31)
+    S5_FAIL(S5_E_BADARG, "scan_i32: Bu/x exponent gap above 31");
+  s5::ScanI32Params q;
+  q.Bu_re = Bu_re; q.Bu_im = Bu_im; q.A_re = A_re; q.A_im = A_im; q.xs_re = xs_re; q.xs_im = xs_im;
+  q.L = L; q.P = P; q.lanes = (long long)B * P;
+  q.eA_re = eA_re; q.eA_im = eA_im; q.eBu_re = eBu_re; q.eBu_im = eBu_im; q.ex_re = ex_re; q.ex_im = ex_im; q.relu = relu;
+  return s5::launch_scan_i32(q, false, (cudaStream_t)stream);
+}

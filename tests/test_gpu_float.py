@@ -1,0 +1,148 @@
+"""GPU parity: float32 and static-w8a16 model / block / SSM through the C ABI vs the oracle."""
+import numpy as np
+import pytest
+
+import modelzoo as Z
+from oracle import model as OM
+from oracle import ssm as OS
+
+pytestmark = pytest.mark.gpu
+
+TOL_F32 = 1e-5     # fp32 within 1e-5 relative
+TOL_W8A16 = 1e-2   # w8a16 within 1e-2 relative
+
+
+def relerr(a, b):
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+@pytest.fixture(scope="module")
+def zoo():
+    return Z.build_sparse_calibrated(0.5, n_clips=3, n_frames=300)
+
+
+def _bound(zoo, *, static, relufication, use_sparse=True, variables=None):
+    from sparsernns_b200.model import BoundModel, S5Config
+
+    d = zoo["dims"]
+    cfg = S5Config(n_layers=d.n_layers, d_model=d.d_model, ssm_size=d.ssm_size, relufication=relufication,
+                   quantization="w8a16" if static else "none", use_sparse=use_sparse)
+    if variables is None:
+        variables = ({"params": zoo["cal_params"], "batch_stats": zoo["variables"]["batch_stats"]} if static
+                     else zoo["variables"])
+    return BoundModel(cfg, variables), variables
+
+
+@pytest.mark.parametrize("relufication,use_sparse", [(False, False), (False, True), (True, True)])
+def test_float_model_matches_oracle(cuda_device, zoo, relufication, use_sparse):
+    import torch
+
+    m, var = _bound(zoo, static=False, relufication=relufication, use_sparse=use_sparse)
+    x = torch.from_numpy(zoo["x"]).to(cuda_device)
+    got = m(x).cpu().numpy()
+    ocfg = Z.oracle_cfg(zoo["dims"], relufication=relufication, static_quant=False, associative_scan=True)
+    ref64 = OM.model_forward(zoo["x"], var, ocfg, dtype=np.float64)
+    ref32 = OM.model_forward(zoo["x"], var, ocfg, dtype=np.float32)
+    e, e_ref = relerr(got, ref64), relerr(ref32, ref64)
+    print(f"float model relufication={relufication} sparse={use_sparse}: cuda vs f64 {e:.2e}; numpy f32 vs f64 {e_ref:.2e}")
+    assert e <= TOL_F32
+
+
+def test_float_layer_and_ssm_match_oracle(cuda_device, zoo):
+    import torch
+
+    m, var = _bound(zoo, static=False, relufication=False)
+    d = zoo["dims"]
+    rng = np.random.default_rng(3)
+    h = rng.standard_normal((2, 257, d.d_model)).astype(np.float32)
+    ocfg = Z.oracle_cfg(d, relufication=False, static_quant=False, associative_scan=False)
+    for i in range(d.n_layers):
+        lp, ls = var["params"]["encoder"][f"layers_{i}"], var["batch_stats"]["encoder"][f"layers_{i}"]
+        taps = {}
+        ref = OM.layer_forward(h.astype(np.float64), lp, ls, ocfg, dtype=np.float64, taps=taps)
+        y, xs = m.layer(i, torch.from_numpy(h).to(cuda_device), return_xs=True)
+        assert relerr(y.cpu().numpy(), ref) <= TOL_F32
+        assert relerr(xs.cpu().numpy(), taps["pre_C"]) <= TOL_F32
+        # apply_ssm level: u -> (ys + D u, xs)
+        Lb, Bb, Ct, D = OS.ssm_discrete_params(lp["mixer"], clip_eigs=True, dtype=np.float64)
+        ys_ref, xs_ref = OS.apply_ssm_float(Lb, Bb, Ct, h.astype(np.float64), associative_scan=False)
+        y2, xs2 = m.apply_ssm(i, torch.from_numpy(h).to(cuda_device))
+        assert relerr(y2.cpu().numpy(), ys_ref + D * h) <= TOL_F32
+        assert relerr(xs2.cpu().numpy(), xs_ref) <= TOL_F32
+
+
+def test_static_model_matches_oracle(cuda_device, zoo):
+    import torch
+
+    m, var = _bound(zoo, static=True, relufication=True)
+    x = torch.from_numpy(zoo["x"]).to(cuda_device)
+    got = m(x).cpu().numpy()
+    ocfg = Z.oracle_cfg(zoo["dims"], relufication=True, static_quant=True)
+    taps = {}
+    ref = OM.model_forward(zoo["x"], var, ocfg, dtype=np.float32, taps=taps)
+    e = relerr(got, ref)
+    exact = float((got == ref).mean())
+    print(f"static w8a16 model: rel err {e:.2e}, bit-identical outputs {exact:.4f}")
+    assert e <= TOL_W8A16
+    # block level, fed with the oracle's own block inputs so that errors do not compound
+    h = taps["encoder_output"]
+    for i in range(zoo["dims"].n_layers):
+        y = m.layer(i, torch.from_numpy(h).to(cuda_device)).cpu().numpy()
+        ref_i = taps[f"layers_{i}"]["output"]
+        assert relerr(y, ref_i) <= TOL_W8A16
+        h = ref_i
+
+
+def test_sparse_index_sets_bit_exact(cuda_device, zoo):
+    """The compressed weights hold exactly the non-zeros of the QUANTISED matrices."""
+    import ctypes as C
+    from oracle.quant import quant_int
+    from sparsernns_b200 import _abi
+    from sparsernns_b200.model import fake_quant
+
+    lib = _abi.lib()
+    p = zoo["cal_params"]["encoder"]["layers_0"]["out2"]
+    wq = fake_quant(p["kernel"], p["weight_scale"], 8)
+    h = C.c_void_p()
+    _abi.check(lib.s5b200_sparse_create(wq.ctypes.data, wq.shape[0], wq.shape[1], _abi.F32, 0, C.byref(h)))
+    nnz = lib.s5b200_sparse_nnz(h)
+    k = np.empty(nnz, np.int32)
+    n = np.empty(nnz, np.int32)
+    _abi.check(lib.s5b200_sparse_export(h, k.ctypes.data, n.ctypes.data))
+    lib.s5b200_sparse_destroy(h)
+    codes = quant_int(p["kernel"], p["weight_scale"], 8)
+    kk, nn = np.nonzero(codes.T)[1], np.nonzero(codes.T)[0]   # ordered by (n, k)
+    assert nnz == len(kk) and np.array_equal(k, kk) and np.array_equal(n, nn)
+    assert nnz < 0.2 * codes.size  # the pruned model really is sparse
+
+
+def test_spmm_f32_ragged_rows(cuda_device):
+    import ctypes as C
+    import torch
+    from sparsernns_b200 import _abi
+
+    lib = _abi.lib()
+    rng = np.random.default_rng(0)
+    for (rows, K, N, dens, dense_fmt) in [(1, 7, 5, 1.0, 1), (33, 96, 128, 0.2, 0), (300, 257, 96, 0.1, 0), (129, 96, 257, 0.0, 0)]:
+        W = (rng.standard_normal((K, N)) * (rng.uniform(size=(K, N)) < dens)).astype(np.float32)
+        X = rng.standard_normal((rows, K)).astype(np.float32)
+        bias = rng.standard_normal(N).astype(np.float32)
+        h = C.c_void_p()
+        _abi.check(lib.s5b200_sparse_create(W.ctypes.data, K, N, _abi.F32, dense_fmt, C.byref(h)))
+        dX, db = torch.from_numpy(X).to(cuda_device), torch.from_numpy(bias).to(cuda_device)
+        dY = torch.empty(rows, N, device=cuda_device)
+        _abi.check(lib.s5b200_spmm_f32(h, dX.data_ptr(), db.data_ptr(), dY.data_ptr(), rows, 0,
+                                       C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        ref = X.astype(np.float64) @ W.astype(np.float64) + bias
+        assert relerr(dY.cpu().numpy(), ref) <= TOL_F32
+        lib.s5b200_sparse_destroy(h)
+
+
+def test_forward_host_matches_device_path(cuda_device, zoo):
+    import torch
+
+    m, _ = _bound(zoo, static=True, relufication=True)
+    x = torch.from_numpy(zoo["x"])
+    y_dev = m(x.to(cuda_device)).cpu()
+    y_host = m.forward_host(x.pin_memory())
+    assert torch.equal(y_dev, y_host)

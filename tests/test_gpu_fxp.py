@@ -1,0 +1,181 @@
+"""GPU parity: fixed-point ops and the integer model through the C ABI vs the oracle - BIT-EXACT."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import modelzoo as Z
+from oracle import fxp as OF
+from oracle import fxpmodel as OFM
+from oracle.fxp import FxpArray, RoundingMode
+
+pytestmark = pytest.mark.gpu
+
+RM = {RoundingMode.FLOOR: 0, RoundingMode.CEIL: 1, RoundingMode.ROUND: 2}
+
+
+def _lib():
+    from sparsernns_b200 import _abi
+    return _abi, _abi.lib()
+
+
+def _stream():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _dev(a, dev):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+def test_from_fp_and_change_cfg(cuda_device):
+    import torch
+    abi, lib = _lib()
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.standard_normal(5000) * 3, [0.5, 1.5, 2.5, -0.5, -1.5, 1e9, -1e9, 0.0]]).astype(np.float32)
+    for bits, exp in [(16, 12), (8, 0), (16, 0), (8, 5)]:
+        for rm in (RoundingMode.FLOOR, RoundingMode.ROUND, RoundingMode.CEIL):
+            ref = OF.fxp_from_fp(x, bits=bits, exp=exp, round_mode=rm).data
+            y = torch.empty(len(x), dtype=torch.int32, device=cuda_device)
+            abi.check(lib.s5b200_fxp_from_fp(_dev(x, cuda_device).data_ptr(), y.data_ptr(), len(x), bits, exp, RM[rm], _stream()))
+            assert np.array_equal(y.cpu().numpy(), ref), (bits, exp, rm)
+    v = rng.integers(-40000, 40000, 6000).astype(np.int32)
+    for (b, e, nb, ne) in [(16, 8, 32, 10), (16, 8, 8, 6), (16, 11, 16, 11), (16, 15, 16, 11), (16, 3, 24, 9), (24, 9, 16, 9)]:
+        for rm in (RoundingMode.FLOOR, RoundingMode.ROUND, RoundingMode.CEIL):
+            if rm == RoundingMode.ROUND and e - ne < 1 and e > ne:
+                continue
+            ref = OF.fxp_change_cfg(FxpArray(v, b, e), nb, ne, True, rm).data
+            y = torch.empty(len(v), dtype=torch.int32, device=cuda_device)
+            abi.check(lib.s5b200_fxp_change_cfg(_dev(v, cuda_device).data_ptr(), y.data_ptr(), len(v), b, e, nb, ne, RM[rm], _stream()))
+            assert np.array_equal(y.cpu().numpy(), ref), (b, e, nb, ne, rm)
+
+
+def test_add_mul_explicit_and_compute_best(cuda_device):
+    import torch
+    abi, lib = _lib()
+    rng = np.random.default_rng(1)
+    H = 96
+    a = rng.integers(-32768, 32767, (7, 50, H)).astype(np.int32)
+    b = rng.integers(-32768, 32767, H).astype(np.int32)
+    da, db = _dev(a, cuda_device), _dev(b, cuda_device)
+    y = torch.empty_like(da)
+    for (ae, be, rb, re_) in [(12, 15, 16, 11), (15, 9, 16, 15), (8, 8, 16, 8), (4, 13, 12, 9)]:
+        ref = OF.fxp_add(FxpArray(a, 16, ae), FxpArray(b, 16, be), result_bits=rb, result_exp=re_).data
+        abi.check(lib.s5b200_fxp_add(da.data_ptr(), db.data_ptr(), y.data_ptr(), a.size, H, 16, ae, 16, be, rb, re_, 0, _stream()))
+        assert np.array_equal(y.cpu().numpy(), ref)
+    for (ae, be, rb, re_) in [(12, 15, 16, 11), (15, 9, 16, 15), (8, 8, 16, 16), (4, 6, 12, 0)]:
+        for rm in (RoundingMode.FLOOR, RoundingMode.ROUND):
+            if rm == RoundingMode.ROUND and ae + be - re_ < 1:
+                continue
+            ref = OF.fxp_mul(FxpArray(a, 16, ae), FxpArray(b, 16, be), result_exp=re_, result_bits=rb, round_mode=rm).data
+            abi.check(lib.s5b200_fxp_mul(da.data_ptr(), db.data_ptr(), y.data_ptr(), a.size, H, ae, be, rb, re_, RM[rm], _stream()))
+            assert np.array_equal(y.cpu().numpy(), ref)
+    e = C.c_int(0)
+    for scale_a, (ae, be) in [(1, (12, 15)), (8, (15, 6)), (64, (14, 14)), (1, (3, 15)), (4096, (15, 15))]:
+        a2 = (a // scale_a).astype(np.int32)
+        da2 = _dev(a2, cuda_device)
+        ref = OF.fxp_add(FxpArray(a2, 16, ae), FxpArray(b, 16, be), result_exp="compute_best")
+        abi.check(lib.s5b200_fxp_add_compute_best(da2.data_ptr(), db.data_ptr(), y.data_ptr(), a2.size, H, 16, ae, 16, be, 16, C.byref(e), _stream()))
+        assert e.value == ref.exp and np.array_equal(y.cpu().numpy(), ref.data), (scale_a, ae, be)
+        ref = OF.fxp_mul(FxpArray(a2, 16, ae), FxpArray(b, 16, be), result_exp="compute_best")
+        abi.check(lib.s5b200_fxp_mul_compute_best(da2.data_ptr(), db.data_ptr(), y.data_ptr(), a2.size, H, ae, be, 16, C.byref(e), _stream()))
+        assert e.value == ref.exp and np.array_equal(y.cpu().numpy(), ref.data), (scale_a, ae, be)
+    # the reference raises ValueError when the product would need a left shift (fxparray.py:619-621)
+    with pytest.raises(abi.S5Error):
+        abi.check(lib.s5b200_fxp_mul(da.data_ptr(), db.data_ptr(), y.data_ptr(), a.size, H, 3, 3, 16, 10, 0, _stream()))
+
+
+def test_relu_sigmoid_matmul(cuda_device):
+    import torch
+    abi, lib = _lib()
+    rng = np.random.default_rng(2)
+    v = np.concatenate([rng.integers(-32768, 32767, 9000), np.arange(-600, 600)]).astype(np.int32)
+    dv = _dev(v, cuda_device)
+    y = torch.empty_like(dv)
+    abi.check(lib.s5b200_fxp_relu(dv.data_ptr(), y.data_ptr(), len(v), _stream()))
+    assert np.array_equal(y.cpu().numpy(), np.maximum(v, 0))
+    for (e, out_bits) in [(13, 16), (6, 16), (4, 16), (9, 8)]:
+        sx, sy = min(e, 6), out_bits - 2
+        s = OFM.FxpSigmoid(x_exp=sx, y_exp=sy)
+        ref = s.apply(FxpArray(v, out_bits, e)).data
+        lut = np.ascontiguousarray(s.lut, dtype=np.int32)
+        abi.check(lib.s5b200_fxp_sigmoid(dv.data_ptr(), y.data_ptr(), len(v), out_bits, e, sx, sy, lut.ctypes.data, _stream()))
+        assert np.array_equal(y.cpu().numpy(), ref), (e, out_bits)
+    # fxp_matmul incl. int32 wrap, the three rounding modes and saturation; ragged row counts
+    for (rows, K, N, dens, wmax, xmax, rs, bits) in [(1, 5, 3, 1.0, 127, 32767, 7, 16), (70, 96, 128, 0.15, 127, 32767, 11, 16),
+                                                     (257, 257, 96, 0.1, 127, 32767, 0, 16), (40, 64, 64, 0.5, 2 ** 20, 2 ** 20, 3, 32),
+                                                     (129, 128, 96, 0.0, 127, 1000, 2, 8)]:
+        W = (rng.integers(-wmax, wmax, (K, N)) * (rng.uniform(size=(K, N)) < dens)).astype(np.int32)
+        X = rng.integers(-xmax, xmax, (rows, K)).astype(np.int32)
+        h = C.c_void_p()
+        abi.check(lib.s5b200_sparse_create(W.ctypes.data, K, N, abi.I32, 0, C.byref(h)))
+        dX = _dev(X, cuda_device)
+        dY = torch.empty(rows, N, dtype=torch.int32, device=cuda_device)
+        for rm in (RoundingMode.FLOOR, RoundingMode.ROUND, RoundingMode.CEIL):
+            if rm == RoundingMode.ROUND and rs < 1:
+                continue
+            ref = OF.fxp_matmul(FxpArray(X, 16, rs), FxpArray(W, 8, 0), result_bits=bits, result_exp=0, round_mode=rm).data
+            abi.check(lib.s5b200_spmm_i32(h, dX.data_ptr(), dY.data_ptr(), rows, rs, RM[rm], bits, 0, _stream()))
+            assert np.array_equal(dY.cpu().numpy(), ref), (rows, K, N, rm)
+        lib.s5b200_sparse_destroy(h)
+
+
+@pytest.fixture(scope="module", params=[True, False], ids=["bn_affine", "simple_bn"])
+def fxp_case(request):
+    zoo = Z.build_sparse_calibrated(0.5, n_clips=3, n_frames=200, bn_affine=request.param)
+    md, q = Z.fxp_setup(zoo)
+    return zoo, md, q
+
+
+def test_fxp_model_bit_exact(cuda_device, fxp_case):
+    import torch
+    from sparsernns_b200 import fxpmodel as PF
+
+    zoo, md, q = fxp_case
+    n_layers = zoo["dims"].n_layers
+    om = OFM.FxpRegressionModel(md, q, n_layers)
+    pm = PF.FxpRegressionModel(md, q, n_layers)
+    x = zoo["x"]
+    xq_ref = om.quantize_input(x)
+    xq = pm.quantize_input(torch.from_numpy(x).to(cuda_device))
+    assert np.array_equal(xq.data.cpu().numpy(), xq_ref.data)
+    taps = {}
+    y_ref = om(xq_ref, taps)
+    # every sown intermediate that crosses a kernel boundary, block by block
+    for i in range(n_layers):
+        T = taps[f"layers_{i}"]
+        t_in = pm.tap(xq, i, PF.TAP_LAYER_INPUT)
+        ref_in = taps["encoder_output_relu"] if i == 0 else taps[f"layers_{i-1}"]["output"]
+        assert t_in.exp == ref_in.exp and np.array_equal(t_in.data.cpu().numpy(), ref_in.data), f"layer {i} input"
+        t_u = pm.tap(xq, i, PF.TAP_PRE_S5)
+        assert np.array_equal(t_u.data.cpu().numpy(), T["mixer"]["u"].data), f"layer {i} pre_s5"
+        t_xs = pm.tap(xq, i, PF.TAP_XS).data.cpu().numpy()
+        assert np.array_equal(t_xs[..., 0], T["pre_C"].real.data) and np.array_equal(t_xs[..., 1], T["pre_C"].imag.data), f"layer {i} xs"
+        t_g = pm.tap(xq, i, PF.TAP_POST_GLU)
+        assert np.array_equal(t_g.data.cpu().numpy(), T["post_GLU"].data), f"layer {i} post_GLU"
+        t_o = pm.tap(xq, i, PF.TAP_OUTPUT)
+        assert t_o.exp == T["output"].exp and np.array_equal(t_o.data.cpu().numpy(), T["output"].data), f"layer {i} output"
+    y = pm(xq)
+    assert y.exp == y_ref.exp and y.bits == y_ref.bits
+    assert np.array_equal(y.data.cpu().numpy(), y_ref.data)
+    # float entry point: quantise + forward + to_float in one call
+    y2, mask = pm.forward_float(torch.from_numpy(x).to(cuda_device))
+    assert np.array_equal(y2.data.cpu().numpy(), y_ref.data)
+    assert np.array_equal(mask.cpu().numpy(), y_ref.to_float())
+
+
+def test_fxp_model_batch_of_one_and_dense_tiles(cuda_device, fxp_case):
+    """bsz = 1 (the reference's verification mode, fxprun.py:460-463) and the dense-tile weight format."""
+    import torch
+    from sparsernns_b200 import fxpmodel as PF
+
+    zoo, md, q = fxp_case
+    n_layers = zoo["dims"].n_layers
+    om = OFM.FxpRegressionModel(md, q, n_layers)
+    x1 = zoo["x"][:1, :77]
+    ref = om(om.quantize_input(x1))
+    for use_sparse in (True, False):
+        pm = PF.FxpRegressionModel(md, q, n_layers, use_sparse=use_sparse)
+        y = pm(pm.quantize_input(torch.from_numpy(x1).to(cuda_device)))
+        assert np.array_equal(y.data.cpu().numpy(), ref.data)
