@@ -1,0 +1,388 @@
+#!/usr/bin/env python
+"""bench.py - S5 NDNS inference throughput on B200 (BASELINE.json metric), one JSON line on stdout.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one forward pass of the NDNS model (encoder Dense -> 3 S5 blocks -> decoder Dense) over one
+batch of synthetic STFT-magnitude clips per GPU.  Workload at every N: BASELINE.json configs[1] - the
+ndns.json recipe at dim_scale 0.5 (H 96, P 64), 90 % magnitude-pruned, ReLU-ified, static w8a16 - with the
+recipe's batch of 32 clips x 3751 frames per GPU (weak scaling: clips are independent, no data-path
+collective; NCCL only reduces the metric checksum after the timed region).
+
+  value      frames/s with inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e        same through the host-buffer entry point (pinned H2D of the inputs + D2H of the mask per step)
+  roofline   dominant kernel: algorithmic bytes per launch / mean device time per launch (CUDA events
+             recorded by the library around each launch) against the measured HBM peak
+  cpu_baseline / --impl reference   the NumPy port of the reference (oracle/) on the box's host cores;
+             JAX is not installable here, so the reference itself cannot run
+"""
+
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+L_FRAMES = 3751
+D_IO = 257
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--clips-per-gpu", type=int, default=32)
+    ap.add_argument("--frames", type=int, default=L_FRAMES)
+    ap.add_argument("--dim-scale", type=float, default=0.5, choices=[0.5, 1.0])
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary flavours and the CPU baseline")
+    return ap.parse_args()
+
+
+def load_fixture(dim_scale):
+    from sparsernns_b200.checkpoint import load_npz
+
+    path = os.path.join(ROOT, "tests", "golden", f"ndns_ds{dim_scale}_sparse_w8a16.npz")
+    tree = load_npz(path)
+    return tree["params"], tree["batch_stats"], tree["cal_stats"]
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.lines, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            p = [s.strip() for s in ln.split(",")]
+            if len(p) < 7:
+                continue
+            try:
+                sm.append(float(p[0])); mx.append(float(p[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def synth_inputs(torch, n_batches, clips, frames, seed, device):
+    """|STFT| of white noise - 0.0007, drawn directly from its Rayleigh law (sparsernns_b200.synth docstring)."""
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    sigma = 0.05 * (512 / 2.0) ** 0.5 / 512
+    out = []
+    for _ in range(n_batches):
+        re = torch.randn(clips, frames, D_IO, generator=g, device=device)
+        im = torch.randn(clips, frames, D_IO, generator=g, device=device)
+        out.append((sigma * torch.sqrt(re * re + im * im) - 0.0007).contiguous())
+    return out
+
+
+def algorithmic_bytes(rows, H, P):
+    """Bytes that must cross HBM per launch of each kernel class ('Kernels')."""
+    return {"enc": rows * (D_IO + H) * 4, "bproj": rows * (H * 4 + P * 8), "scan_c64": rows * P * 16,
+            "glu": rows * (P * 8 + 2 * H * 4), "dec": rows * (H + D_IO) * 4,
+            "fxp_enc": rows * (D_IO + H) * 4, "fxp_bn": rows * H * 4, "fxp_bproj": rows * (H * 4 + P * 8),
+            "scan_i32": rows * P * 16, "fxp_glu": rows * (P * 8 + 2 * H * 4), "fxp_resid": rows * H * 12,
+            "fxp_dec": rows * (H + D_IO) * 4}
+
+
+def cpu_port_forward_fn(params, batch_stats, dims):
+    """The NumPy port of the reference's static-w8a16 forward (oracle/): cpu_baseline and --impl reference only."""
+    from oracle import model as OM
+
+    cfg = OM.ModelConfig(n_layers=dims.n_layers, d_model=dims.d_model, ssm_size=dims.ssm_size, relufication=True,
+                         static_quant=True, associative_scan=False)
+    var = {"params": params, "batch_stats": batch_stats}
+    return lambda x: OM.model_forward(x, var, cfg)
+
+
+def host_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        n = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
+        return int(n)
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def reference_arm(args, rank, world):
+    """--impl reference: the reference's CPU path.  JAX/Flax are not installable in this image (no wheel, no
+    network), so the reference is represented by its NumPy port under oracle/ (kind 'port')."""
+    if rank != 0:
+        return
+    import numpy as np
+    from sparsernns_b200 import synth
+
+    dims = synth.ndns_dims(args.dim_scale)
+    params, batch_stats, _ = load_fixture(args.dim_scale)
+    fwd = cpu_port_forward_fn(params, batch_stats, dims)
+    probe = synth.synthetic_stft_batch(1, args.frames, seed=1)
+    t0 = time.perf_counter(); fwd(probe); t1 = time.perf_counter() - t0
+    budget = 150.0  # seconds for the whole run
+    clips = max(1, min(args.clips_per_gpu, int(budget / max(t1, 1e-3) / max(1, args.steps + args.warmup))))
+    x = synth.synthetic_stft_batch(clips, args.frames, seed=2)
+    for _ in range(args.warmup):
+        fwd(x)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        fwd(x)
+    dt = time.perf_counter() - t0
+    fps = clips * args.frames * args.steps / dt
+    cores = host_threads()
+    line = {
+        "impl": "reference", "metric": "S5 NDNS inference frames/sec (sparse static w8a16, dim_scale %.1f)" % args.dim_scale,
+        "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "ndns.json dim_scale %.1f, 90%% magnitude-pruned, relufication, static w8a16 forward" % args.dim_scale,
+                   "clips_per_step": clips, "frames_per_clip": args.frames, "H": dims.d_model, "P": dims.ssm_size,
+                   "note": "NumPy port of the reference (oracle/); the JAX reference is not installable offline"},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+                         "sample": "%d clip(s) x %d frames per step, %d steps" % (clips, args.frames, args.steps)},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return reference_arm(args, rank, world)
+
+    import numpy as np
+    import torch
+
+    from sparsernns_b200 import _abi, synth
+    from sparsernns_b200.build import build_library
+    from sparsernns_b200.model import BoundModel, S5Config
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device; there is no CPU fallback for the product path")
+    build_library()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    dims = synth.ndns_dims(args.dim_scale)
+    params, batch_stats, cal_stats = load_fixture(args.dim_scale)
+    cfg = S5Config(n_layers=dims.n_layers, d_model=dims.d_model, ssm_size=dims.ssm_size, relufication=True,
+                   quantization="w8a16", use_sparse=True)
+    model = BoundModel(cfg, {"params": params, "batch_stats": batch_stats})
+    lib = _abi.lib()
+    B, L, K, W = args.clips_per_gpu, args.frames, args.steps, args.warmup
+    rows = B * L
+    n_rot = 4  # rotate over 4 input batches (4 x 123 MB at B=32) so that no step finds its input in the 126 MB L2
+    xs = synth_inputs(torch, n_rot, B, L, 1000 + rank, dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if dist is not None:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    y = None
+
+    def step(i):
+        nonlocal y
+        y = model(xs[i % n_rot])
+
+    for i in range(max(W, 3)):
+        step(i)
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    lib.s5b200_reset_launch_count()
+    ms_total = timed(step, K)
+    launches = int(lib.s5b200_launch_count())
+    clock_info = clocks.stop() if rank == 0 else None
+    fps = world * rows * K / (ms_total / 1e3)
+
+    # metric checksum: the only collective of the run (NCCL), after the timed region
+    chk = torch.stack([y.double().sum(), y.double().abs().max()])
+    if dist is not None:
+        from sparsernns_b200.dist import reduce_metrics
+        chk = reduce_metrics(chk, "sum")
+
+    # end to end through the host-buffer entry point
+    xh = [t.cpu().pin_memory() for t in xs[:2]]
+    yh = torch.empty((B, L, D_IO), dtype=torch.float32).pin_memory()
+    model.forward_host(xh[0], out=yh)
+    barrier()
+    t0 = time.perf_counter()
+    ke = max(3, min(K, 10))
+    for i in range(ke):
+        model.forward_host(xh[i % 2], out=yh)
+    torch.cuda.synchronize()
+    e2e_s = torch.tensor([time.perf_counter() - t0], device=dev)
+    if dist is not None:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_fps = world * rows * ke / float(e2e_s.item())
+
+    # per-kernel device time (events recorded by the library around each launch)
+    lib.s5b200_profile_begin()
+    for i in range(K):
+        step(i)
+    ms_cls = (C.c_double * 13)()
+    n_cls = (C.c_longlong * 13)()
+    _abi.check(lib.s5b200_profile_end(ms_cls, n_cls))
+    peak, peak_src = measured_peak()
+    alg = algorithmic_bytes(rows, dims.d_model, dims.ssm_size)
+    kernels = {}
+    for i, name in enumerate(_abi.KERNEL_CLASSES):
+        if n_cls[i]:
+            per = ms_cls[i] / n_cls[i]
+            gbs = alg.get(name, 0) / (per * 1e-3) / 1e9 if name in alg else None
+            kernels[name] = {"launches_per_step": n_cls[i] / K, "ms_per_launch": per, "ms_per_step": ms_cls[i] / K,
+                             "alg_bytes_per_launch": alg.get(name), "achieved_gbs": gbs, "frac": gbs / peak if gbs else None}
+    dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"])
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get(dom)
+    except Exception:
+        pass
+    roofline = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                "frac": kernels[dom]["frac"], "traffic": traffic, "peak_source": peak_src,
+                "share_of_step": kernels[dom]["ms_per_step"] / sum(k["ms_per_step"] for k in kernels.values())}
+
+    extras = {}
+    cpu_baseline = None
+    if rank == 0 and not args.no_extras:
+        try:
+            extras = secondary_flavours(torch, model, params, batch_stats, cal_stats, dims, xs, B, L, dev)
+        except Exception as e:  # secondary numbers must never take the headline down
+            extras = {"error": repr(e)}
+        if world == 1:
+            fwd = cpu_port_forward_fn(params, batch_stats, dims)
+            nclip = min(B, 8)
+            xc = xs[0][:nclip].cpu().numpy()
+            t0 = time.perf_counter(); yc = fwd(xc); dt = time.perf_counter() - t0
+            rel = float(np.abs(model(xs[0])[:nclip].cpu().numpy() - yc).max() / np.abs(yc).max())
+            cpu_baseline = {"value": nclip * L / dt, "unit": "frames/s", "cores": host_threads(), "kind": "port",
+                            "sample": "%d of the %d clips of one step, 1 run (NumPy port of the reference, oracle/)" % (nclip, B),
+                            "gpu_vs_port_rel_err": rel}
+
+    if rank == 0:
+        line = {
+            "metric": "S5 NDNS inference frames/sec (sparse static w8a16, dim_scale %.1f)" % args.dim_scale,
+            "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": max(W, 3), "ms_per_step": ms_total / K,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "BASELINE configs[1]: ndns.json dim_scale %.1f, 90%% iterative-magnitude-pruned (ERK), "
+                                   "relufication, static w8a16 forward" % args.dim_scale,
+                       "clips_per_gpu": B, "frames_per_clip": L, "H": dims.d_model, "P": dims.ssm_size, "n_layers": dims.n_layers,
+                       "parallelism": "clips sharded over %d GPU(s), no data-path collective" % world,
+                       "l2": "inputs rotate over %d batches (%.0f MB) > 126 MB L2" % (n_rot, n_rot * rows * D_IO * 4 / 1e6),
+                       "weights": "random-init recipe shapes, scales from a one-batch calibration (tests/golden fixture)"},
+            "clocks": clock_info,
+            "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": rows * D_IO * 4, "d2h_bytes_per_step": rows * D_IO * 4,
+                    "steps": ke},
+            "gpu_launches": launches,
+            "roofline": roofline,
+            "kernels": kernels,
+            "cpu_baseline": cpu_baseline,
+            "checksum": [float(chk[0].item()), float(chk[1].item())],
+        }
+        if extras:
+            line["flavours"] = extras
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def secondary_flavours(torch, model, params, batch_stats, cal_stats, dims, xs, B, L, dev):
+    """Device-timed frames/s of the other two numerics flavours on the same batch (informational)."""
+    from sparsernns_b200 import fxputils
+    from sparsernns_b200.fxpmodel import FxpRegressionModel
+    from sparsernns_b200.model import BoundModel, S5Config
+
+    out = {}
+
+    def t(fn, n=5):
+        for _ in range(2):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(); e0.record()
+        for i in range(n):
+            fn(i)
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    md = fxputils.load_modeldict(params, cal_stats)
+    q = fxputils.create_fxp_qconfig(md, "w8a16", shared_exp=True)
+    fx = FxpRegressionModel(md, q, dims.n_layers)
+    ms = t(lambda i=0: fx.forward_float(xs[i % len(xs)]))
+    out["fixed_point_w8a16"] = {"frames_per_s": B * L / (ms / 1e3), "ms_per_step": ms}
+    cfg = S5Config(n_layers=dims.n_layers, d_model=dims.d_model, ssm_size=dims.ssm_size, relufication=False,
+                   quantization="none", use_sparse=False)
+    fm = BoundModel(cfg, {"params": params, "batch_stats": batch_stats})
+    ms = t(lambda i=0: fm(xs[i % len(xs)]))
+    out["dense_fp32_gelu"] = {"frames_per_s": B * L / (ms / 1e3), "ms_per_step": ms}
+    return out
+
+
+if __name__ == "__main__":
+    main()

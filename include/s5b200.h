@@ -58,6 +58,18 @@ const char* s5b200_last_error(void);
 long long s5b200_launch_count(void);
 void s5b200_reset_launch_count(void);
 
+/* Per-kernel-class device timing (CUDA events recorded on the launching stream around every kernel this
+ * library launches on the calling thread).  begin() clears and enables, end() synchronises the recorded
+ * events, accumulates milliseconds and launch counts per class into the S5_K_COUNT-long arrays, and
+ * disables.  Meant for bench.py's roofline figures; adds two event records per launch while enabled. */
+enum s5_kernel_class {
+  S5_K_ENC = 0, S5_K_BPROJ = 1, S5_K_SCAN_C64 = 2, S5_K_GLU = 3, S5_K_DEC = 4,
+  S5_K_FXP_ENC = 5, S5_K_FXP_BN = 6, S5_K_FXP_BPROJ = 7, S5_K_SCAN_I32 = 8, S5_K_FXP_GLU = 9,
+  S5_K_FXP_RESID = 10, S5_K_FXP_DEC = 11, S5_K_OTHER = 12, S5_K_COUNT = 13
+};
+int s5b200_profile_begin(void);
+int s5b200_profile_end(double* ms_per_class, long long* launches_per_class);
+
 /* ------------------------------------------------------------------------------------------------
  * (1) Diagonal complex linear recurrence  x_k = lam * x_{k-1} + Bu_k,  x_{-1} = 0.
  * Replaces jax.lax.associative_scan / jax.lax.scan in sparseRNNs/model/ssm.py:127, :150, :313.

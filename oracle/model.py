@@ -63,7 +63,8 @@ def gelu_tanh(x):
 def sigmoid(x):
     """jax.nn.sigmoid (layers.py:224)."""
     dt = x.dtype.type
-    return (dt(1.0) / (dt(1.0) + np.exp(-x))).astype(x.dtype)
+    with np.errstate(over="ignore"):  # exp(-x) -> inf for very negative x gives exactly 0, as in XLA
+        return (dt(1.0) / (dt(1.0) + np.exp(-x))).astype(x.dtype)
 
 
 def batchnorm_eval(x, norm_params: dict, norm_stats: dict, eps: float):

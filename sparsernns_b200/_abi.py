@@ -16,6 +16,8 @@ ROUND_FLOOR, ROUND_CEIL, ROUND_HALF_UP = 0, 1, 2
 FLOAT, STATIC = 0, 1
 ACT_GELU_TANH, ACT_RELU = 0, 1
 F32, I32 = 0, 1
+KERNEL_CLASSES = ["enc", "bproj", "scan_c64", "glu", "dec", "fxp_enc", "fxp_bn", "fxp_bproj", "scan_i32", "fxp_glu",
+                  "fxp_resid", "fxp_dec", "other"]
 
 c_float_p = C.POINTER(C.c_float)
 c_int32_p = C.POINTER(C.c_int32)
@@ -94,6 +96,8 @@ PROTOTYPES = {
     "s5b200_last_error": (C.c_char_p, []),
     "s5b200_launch_count": (_LL, []),
     "s5b200_reset_launch_count": (None, []),
+    "s5b200_profile_begin": (_I, []),
+    "s5b200_profile_end": (_I, [C.POINTER(C.c_double), C.POINTER(_LL)]),
     "s5b200_scan_c64_workspace_bytes": (_SZ, [_I, _I, _I]),
     "s5b200_scan_c64": (_I, [_V, _V, _V, _I, _I, _I, _I, _V, _SZ, _V]),
     "s5b200_scan_i32": (_I, [_V, _V, _V, _V, _V, _V, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _V]),

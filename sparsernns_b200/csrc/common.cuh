@@ -44,6 +44,14 @@ inline size_t round_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 int sm_count();
 
+// RAII event pair around one kernel launch when profiling is enabled on this thread (s5b200_profile_begin)
+struct ProfScope {
+  int idx;
+  cudaStream_t st;
+  ProfScope(int kernel_class, cudaStream_t stream);
+  ~ProfScope();
+};
+
 // ---------------------------------------------------------------------------- device helpers
 #ifdef __CUDACC__
 

@@ -139,7 +139,7 @@ static int persistent_grid(KernelT kernel, size_t smem, long long ntiles, int* g
   return S5_OK;
 }
 
-static int launch_linear(LinearParams p, cudaStream_t st) {
+static int launch_linear(LinearParams p, cudaStream_t st, int kclass = S5_K_OTHER) {
   if (p.rows <= 0) S5_FAIL(S5_E_BADSHAPE, "linear: rows=%lld must be positive", p.rows);
   const size_t wbytes = ((wsmem_words_host(p.w)) * 4);
   const int tr = pick_tr(wbytes, (size_t)(p.w.K + p.w.N) * 4);
@@ -147,6 +147,7 @@ static int launch_linear(LinearParams p, cudaStream_t st) {
   const size_t smem = wbytes + (size_t)(p.w.K + p.w.N) * (tr + 1) * 4;
   const long long ntiles = (p.rows + tr - 1) / tr;
   int grid = 1, rc;
+  ProfScope prof(kclass, st);
   switch (tr) {
     case 128:
       if ((rc = persistent_grid(linear_f32_kernel<128>, smem, ntiles, &grid))) return rc;
@@ -277,6 +278,7 @@ static int launch_glu(GluParams p, cudaStream_t st) {
   const size_t smem = wbytes + per_row * (tr + 1);
   const long long ntiles = (p.rows + tr - 1) / tr;
   int grid = 1, rc;
+  ProfScope prof(S5_K_GLU, st);
   switch (tr) {
     case 128:
       if ((rc = persistent_grid(glu_f32_kernel<128>, smem, ntiles, &grid))) return rc;
@@ -395,7 +397,7 @@ static int run_block(const s5_model* m, int li, const float* x, float* out, floa
   const LayerDev& ld = m->layers[li];
   const long long rows = (long long)B * L;
   int rc;
-  if ((rc = launch_linear(bproj_params(m, ld, x, bu, rows, bn), st))) return rc;
+  if ((rc = launch_linear(bproj_params(m, ld, x, bu, rows, bn), st, S5_K_BPROJ))) return rc;
   if ((rc = launch_scan_c64(bu, ld.lam, bu, B, L, m->desc.P, m->desc.relufication, scan_ws, scan_ws_bytes, st))) return rc;
   return launch_glu(glu_params(m, ld, bu, x, out, rows, bn, ssm_only), st);
 }
@@ -527,12 +529,12 @@ extern "C" int s5b200_model_forward(const s5_model* m, const float* x, float* y,
   float* bu = reinterpret_cast<float*>(base + w.off_bu);
   const long long rows = (long long)B * L;
   const s5_model_desc& d = m->desc;
-  if ((rc = launch_linear(dense_params(m, m->enc, m->enc_bias, x, a, rows, d.s_enc_act, d.s_enc_out, d.relufication), st))) return rc;
+  if ((rc = launch_linear(dense_params(m, m->enc, m->enc_bias, x, a, rows, d.s_enc_act, d.s_enc_out, d.relufication), st, S5_K_ENC))) return rc;
   for (int i = 0; i < d.n_layers; ++i) {
     if ((rc = run_block(m, i, a, b, bu, B, L, base + w.off_scan, w.scan_bytes, true, false, st))) return rc;
     std::swap(a, b);
   }
-  return launch_linear(dense_params(m, m->dec, m->dec_bias, a, y, rows, d.s_dec_act, d.s_dec_out, 0), st);
+  return launch_linear(dense_params(m, m->dec, m->dec_bias, a, y, rows, d.s_dec_act, d.s_dec_out, 0), st, S5_K_DEC);
 }
 
 extern "C" int s5b200_layer_forward(const s5_model* m, int layer, const float* x, float* y, float* xs_out, int B, int L,

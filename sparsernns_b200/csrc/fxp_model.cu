@@ -276,7 +276,7 @@ static int pgrid(KernelT kernel, size_t smem, long long ntiles, int* grid_out) {
   return S5_OK;
 }
 
-static int launch_fxp_linear(const FxpLinearParams& p, cudaStream_t st) {
+static int launch_fxp_linear(const FxpLinearParams& p, cudaStream_t st, int kclass = S5_K_OTHER) {
   if (p.rows <= 0) S5_FAIL(S5_E_BADSHAPE, "fxp linear: rows=%lld must be positive", p.rows);
   const size_t wbytes = wwords_h(p.w) * 4;
   const int tr = pick_tr_f(wbytes, (size_t)(p.w.K + p.w.N) * 4);
@@ -284,6 +284,7 @@ static int launch_fxp_linear(const FxpLinearParams& p, cudaStream_t st) {
   const size_t smem = wbytes + (size_t)(p.w.K + p.w.N) * (tr + 1) * 4;
   const long long ntiles = (p.rows + tr - 1) / tr;
   int grid = 1, rc;
+  ProfScope prof(kclass, st);
   switch (tr) {
     case 128:
       if ((rc = pgrid(fxp_linear_kernel<128>, smem, ntiles, &grid))) return rc;
@@ -411,6 +412,7 @@ static int launch_fxp_glu(const FxpGluParams& p, cudaStream_t st) {
   const size_t smem = wbytes + per_row * (tr + 1);
   const long long ntiles = (p.rows + tr - 1) / tr;
   int grid = 1, rc;
+  ProfScope prof(S5_K_FXP_GLU, st);
   switch (tr) {
     case 128:
       if ((rc = pgrid(fxp_glu_kernel<128>, smem, ntiles, &grid))) return rc;
@@ -582,10 +584,8 @@ static int fxp_run(const FxpRun& r, const void* x, bool x_is_float, int upto_lay
     p.bias_aligned = m->enc.bias_aligned; p.relu = 1;
     p.next_mmean = m->layers[0].mmean; p.next_e_mean = m->layers[0].q.bn_mean_exp; p.next_fm = r.fm(0); p.out_exp = q.out_exp;
     p.status = r.status();
-    int e0 = q.out_exp;
     S5_CUDA(cudaMemcpyAsync(r.ex(0) + E_IN, &m->enc.q.out_exp, sizeof(int), cudaMemcpyHostToDevice, r.st));
-    (void)e0;
-    if ((rc = launch_fxp_linear(p, r.st))) return rc;
+    if ((rc = launch_fxp_linear(p, r.st, S5_K_FXP_ENC))) return rc;
   }
   for (int li = 0; li <= upto_layer; ++li) {
     const FxpLayerDev& l = m->layers[li];
@@ -593,6 +593,7 @@ static int fxp_run(const FxpRun& r, const void* x, bool x_is_float, int upto_lay
     const long long n = rows * d.H;
     auto reduce = [&](int upto, int next) -> int {
       BnReduceParams p{a, n, d.H, c, r.fm(li), r.ex(li), r.status(), upto, next};
+      ProfScope prof(S5_K_FXP_BN, r.st);
       fxp_bn_reduce_kernel<<<ew_grid(n), 256, 0, r.st>>>(p);
       S5_LAUNCH_CHECK();
       return S5_OK;
@@ -613,7 +614,7 @@ static int fxp_run(const FxpRun& r, const void* x, bool x_is_float, int upto_lay
       p.rshift0 = l.q.u_exp + l.q.eB_re - l.q.Bu_re_exp; p.rshift1 = l.q.u_exp + l.q.eB_im - l.q.Bu_im_exp;
       p.round_mode = S5_ROUND_FLOOR; p.out_bits = l.q.Bu_re_bits;
       p.c = c; p.fm = r.fm(li); p.ex = r.ex(li); p.status = r.status();
-      if ((rc = launch_fxp_linear(p, r.st))) return rc;
+      if ((rc = launch_fxp_linear(p, r.st, S5_K_FXP_BPROJ))) return rc;
     }
     {  // recurrent_loop + fxp_relu (fxpmodel.py:682-742)
       ScanI32Params q{};
@@ -653,6 +654,7 @@ static int fxp_run(const FxpRun& r, const void* x, bool x_is_float, int upto_lay
       if (li + 1 < d.n_layers) {
         p.next_mmean = m->layers[li + 1].mmean; p.next_e_mean = m->layers[li + 1].q.bn_mean_exp; p.next_fm = r.fm(li + 1);
       }
+      ProfScope prof(S5_K_FXP_RESID, r.st);
       fxp_resid_kernel<<<ew_grid(n), 256, 0, r.st>>>(p);
       S5_LAUNCH_CHECK();
     }
@@ -678,7 +680,7 @@ static int fxp_forward_impl(const s5_fxp_model* m, const void* x, bool x_is_floa
   p.out_scale = 1.0f / (float)(1ll << q.out_exp);
   p.ex = r.ex(m->desc.n_layers); p.status = r.status();
   p.dec_inp_bits = q.inp_bits; p.dec_inp_exp = q.inp_exp; p.dec_w_exp = q.w_exp; p.dec_out_exp = q.out_exp;
-  if ((rc = launch_fxp_linear(p, r.st))) return rc;
+  if ((rc = launch_fxp_linear(p, r.st, S5_K_FXP_DEC))) return rc;
   if (status_dev) S5_CUDA(cudaMemcpyAsync(status_dev, r.status(), 4 * sizeof(int), cudaMemcpyDeviceToDevice, r.st));
   return S5_OK;
 }

@@ -249,6 +249,7 @@ int launch_scan_i32(const ScanI32Params& q, bool interleaved, cudaStream_t st) {
   const int threads = 128;
   const long long blocks = (q.lanes + threads - 1) / threads;
   if (blocks > 0x7fffffffLL) S5_FAIL(S5_E_BADSHAPE, "scan_i32: too many lanes");
+  ProfScope prof(S5_K_SCAN_I32, st);
   if (interleaved) scan_i32_kernel<true, 8><<<(unsigned)blocks, threads, 0, st>>>(q);
   else scan_i32_kernel<false, 8><<<(unsigned)blocks, threads, 0, st>>>(q);
   S5_LAUNCH_CHECK();
@@ -275,6 +276,7 @@ int launch_scan_c64(const float* Bu, const float* lam, float* xs, int B, int L, 
   double2* recs = reinterpret_cast<double2*>(reinterpret_cast<unsigned char*>(workspace) + flags_bytes);
   S5_CUDA(cudaMemsetAsync(flags, 0, flags_bytes, st));
   dim3 grid(g.nchunks, B);
+  ProfScope prof(S5_K_SCAN_C64, st);
   scan_c64_kernel<<<grid, g.threads, g.smem_bytes, st>>>(reinterpret_cast<const float2*>(Bu),
                                                          reinterpret_cast<const float2*>(lam),
                                                          reinterpret_cast<float2*>(xs), L, P, g.nsub, g.nchunks, relu,
