@@ -113,6 +113,12 @@ int s5b200_spmm_f32(const s5_sparse* w, const float* X, const float* bias, float
 int s5b200_spmm_i32(const s5_sparse* w, const int32_t* X, int32_t* Y, long long rows, int rshift,
                     int round_mode, int bits, int skip_zero_cols, void* stream);
 
+/* Dense-tile projection primitive on the tcgen05 tensor cores (throughput batches, where the projection is a
+ * genuine dense contraction): Y[rows][N] (f32) = A[rows][K] (f16) * W[N][K]^T (f16), fp32 accumulation in TMEM.
+ * K and N multiples of 16, N <= 256.  Integer codes of up to 11 bits are exact in f16, so int8 weights times
+ * hi/lo-split int16 activations give exact integer sums ("dense-tile path"). */
+int s5b200_tc_gemm_f16(const void* A, const void* W, float* Y, long long rows, int K, int N, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * (1)+(2) Float / static-quant model.  Host code (Python) keeps the reference's parameter pytree,
  * performs the per-weight-set work (ZOH discretisation ssm.py:37-50, weight fake-quant

@@ -107,6 +107,7 @@ PROTOTYPES = {
     "s5b200_sparse_export": (_I, [_V, _V, _V]),
     "s5b200_spmm_f32": (_I, [_V, _V, _V, _V, _LL, _I, _V]),
     "s5b200_spmm_i32": (_I, [_V, _V, _V, _LL, _I, _I, _I, _I, _V]),
+    "s5b200_tc_gemm_f16": (_I, [_V, _V, _V, _LL, _I, _I, _V]),
     "s5b200_model_create": (_I, [C.POINTER(ModelDesc), C.POINTER(_V)]),
     "s5b200_model_destroy": (_I, [_V]),
     "s5b200_model_workspace_bytes": (_SZ, [_V, _I, _I]),

@@ -57,7 +57,7 @@ __device__ __forceinline__ double2 zfma(double2 a, double2 x, double2 v) {
 }
 __device__ __forceinline__ double2 f2z(float2 v) { return make_double2((double)v.x, (double)v.y); }
 
-__global__ void __launch_bounds__(kScanThreads)
+__global__ void __launch_bounds__(kScanThreads, 4)
 scan_c64_kernel(const float2* __restrict__ Bu, const float2* __restrict__ lam, float2* xs, int L, int P, int nsub,
                 int nchunks, int relu, uint32_t* flags, double2* recs, int rec_stride) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -67,7 +67,9 @@ scan_c64_kernel(const float2* __restrict__ Bu, const float2* __restrict__ lam, f
   double2* carry_s = reinterpret_cast<double2*>(sub_agg + (size_t)nsub * P);  // [P]
   uint64_t* bar = reinterpret_cast<uint64_t*>(carry_s + P);
 
-  const int c = blockIdx.x, b = blockIdx.y;
+  // Block order is clip-fastest: all clips' chunk c are dispatched before any chunk c+1, so by the time a chunk
+  // starts, its predecessors are usually finished and the look-back finds an inclusive prefix after 1-2 steps.
+  const int c = blockIdx.y, b = blockIdx.x;
   const int tid = threadIdx.x;
   const int p = tid % P, s = tid / P;
   const int t0 = c * TL;
@@ -106,52 +108,55 @@ scan_c64_kernel(const float2* __restrict__ Bu, const float2* __restrict__ lam, f
   sub_agg[s * P + p] = x;
   __syncthreads();
 
+  // Only the first P threads (the "carry warps") take part in the aggregate / look-back / publish protocol;
+  // they synchronise among themselves on named barrier 1 and the rest of the CTA waits at the barrier below.
   uint32_t* flag_row = flags + (size_t)b * nchunks;
   double2* rec_row = recs + (size_t)b * nchunks * rec_stride;
   const int half = rec_stride >> 1;
-  double2 e = make_double2(0., 0.);
   const bool publish = (c + 1 < nchunks);  // nobody looks back at the last chunk
-  if (tid < P) {
-    e = f2z(sub_agg[p]);
-    for (int q = 1; q < nsub; ++q) e = zfma(aT, e, f2z(sub_agg[q * P + p]));
-    if (publish) {
-      double2* rec = rec_row + (size_t)c * rec_stride;
-      if (c == 0) __stcg(rec + half + p, e);  // chunk 0: aggregate == inclusive prefix
-      else __stcg(rec + p, e);
-    }
-    if (c == 0) carry_s[p] = make_double2(0., 0.);
-  }
-  if (publish) {
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) st_release_u32(flag_row + c, c == 0 ? 2u : 1u);
-  }
-
-  if (c > 0) {
+  const int carry_threads = (P + 31) & ~31;
+  if (tid < carry_threads) {
+    double2 e = make_double2(0., 0.);
     if (tid < P) {
-      // decoupled look-back: walk predecessors until one has published its inclusive prefix
-      double2 mult = make_double2(1., 0.);
-      double2 acc = make_double2(0., 0.);
-      for (int j = c - 1; j >= 0; --j) {
-        uint32_t f;
-        do {
-          f = ld_acquire_u32(flag_row + j);
-        } while (f == 0u);
-        const double2* rec = rec_row + (size_t)j * rec_stride;
-        if (f == 2u) {
-          acc = zfma(mult, __ldcg(rec + half + p), acc);
-          break;
-        }
-        acc = zfma(mult, __ldcg(rec + p), acc);
-        mult = zmul(mult, aTL);
+      e = f2z(sub_agg[p]);
+      for (int q = 1; q < nsub; ++q) e = zfma(aT, e, f2z(sub_agg[q * P + p]));
+      if (publish) {
+        double2* rec = rec_row + (size_t)c * rec_stride;
+        __stcg(rec + (c == 0 ? half : 0) + p, e);  // chunk 0: aggregate == inclusive prefix
+        __threadfence();
       }
-      carry_s[p] = acc;
-      if (publish) __stcg(rec_row + (size_t)c * rec_stride + half + p, zfma(aTL, acc, e));
+      if (c == 0) carry_s[p] = make_double2(0., 0.);
     }
     if (publish) {
-      __threadfence();
-      __syncthreads();
-      if (tid == 0) st_release_u32(flag_row + c, 2u);
+      asm volatile("bar.sync 1, %0;" ::"r"(carry_threads) : "memory");
+      if (tid == 0) st_release_u32(flag_row + c, c == 0 ? 2u : 1u);
+    }
+    if (c > 0) {
+      if (tid < P) {
+        // decoupled look-back: walk predecessors until one has published its inclusive prefix
+        double2 mult = make_double2(1., 0.);
+        double2 acc = make_double2(0., 0.);
+        for (int j = c - 1; j >= 0; --j) {
+          uint32_t f;
+          do {
+            f = ld_acquire_u32(flag_row + j);
+          } while (f == 0u);
+          const double2* rec = rec_row + (size_t)j * rec_stride;
+          const double2 v = __ldcg(rec + (f == 2u ? half : 0) + p);
+          acc = zfma(mult, v, acc);
+          if (f == 2u) break;
+          mult = zmul(mult, aTL);
+        }
+        carry_s[p] = acc;
+        if (publish) {
+          __stcg(rec_row + (size_t)c * rec_stride + half + p, zfma(aTL, acc, e));
+          __threadfence();
+        }
+      }
+      if (publish) {
+        asm volatile("bar.sync 1, %0;" ::"r"(carry_threads) : "memory");
+        if (tid == 0) st_release_u32(flag_row + c, 2u);
+      }
     }
   }
   __syncthreads();
@@ -260,7 +265,6 @@ int launch_scan_c64(const float* Bu, const float* lam, float* xs, int B, int L, 
                     size_t workspace_bytes, cudaStream_t st) {
   if (B <= 0 || L <= 0) S5_FAIL(S5_E_BADSHAPE, "scan_c64: B=%d L=%d must be positive", B, L);
   if (P < 2 || P > kScanThreads || (P & 1)) S5_FAIL(S5_E_BADSHAPE, "scan_c64: P=%d must be even and in [2, %d]", P, kScanThreads);
-  if (B > 65535) S5_FAIL(S5_E_BADSHAPE, "scan_c64: B=%d exceeds 65535 clips per call", B);
   if (!Bu || !lam || !xs || !workspace) S5_FAIL(S5_E_BADARG, "scan_c64: null pointer");
   if (!aligned16(Bu) || !aligned16(xs) || !aligned16(workspace)) S5_FAIL(S5_E_BADARG, "scan_c64: pointers must be 16-byte aligned");
   const size_t need = s5b200_scan_c64_workspace_bytes(B, L, P);
@@ -275,7 +279,8 @@ int launch_scan_c64(const float* Bu, const float* lam, float* xs, int B, int L, 
   uint32_t* flags = reinterpret_cast<uint32_t*>(workspace);
   double2* recs = reinterpret_cast<double2*>(reinterpret_cast<unsigned char*>(workspace) + flags_bytes);
   S5_CUDA(cudaMemsetAsync(flags, 0, flags_bytes, st));
-  dim3 grid(g.nchunks, B);
+  if (g.nchunks > 65535) S5_FAIL(S5_E_BADSHAPE, "scan_c64: L=%d needs more than 65535 chunks", L);
+  dim3 grid(B, g.nchunks);
   ProfScope prof(S5_K_SCAN_C64, st);
   scan_c64_kernel<<<grid, g.threads, g.smem_bytes, st>>>(reinterpret_cast<const float2*>(Bu),
                                                          reinterpret_cast<const float2*>(lam),
