@@ -9,11 +9,13 @@
 // Kernels per forward: encoder linear, then per block {BN+B-projection linear, scan_c64, C-projection+GLU},
 // decoder linear.  Bu/xs are the only SSM intermediates that touch HBM.
 #include <algorithm>
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 
 #include "proj.cuh"
 #include "scan.cuh"
+#include "tc_model.cuh"
 
 namespace s5 {
 
@@ -303,6 +305,8 @@ namespace s5 {
 
 struct LayerDev {
   SparseDev wb, wc, wo;
+  TcLinearDev tb;  // dense-tile form of the B projection (static flavour)
+  TcGluDev tg;     // dense-tile form of the C projection + GLU
   float *lam = nullptr, *D = nullptr, *bn_mean = nullptr, *bn_mul = nullptr, *bn_bias = nullptr, *o_bias = nullptr;
   s5_layer_desc sc;  // scales only (pointers unused)
 };
@@ -319,6 +323,8 @@ static int upload(const float* h, size_t n, float** d) {
 struct s5_model {
   s5_model_desc desc;
   s5::SparseDev enc, dec;
+  s5::TcLinearDev enc_tc, dec_tc;
+  long long tc_min_rows = 4096;  // below this the compressed CUDA-core kernels are used
   float *enc_bias = nullptr, *dec_bias = nullptr;
   std::vector<s5::LayerDev> layers;
   // cached device buffers for the host-buffer entry point
@@ -397,8 +403,28 @@ static int run_block(const s5_model* m, int li, const float* x, float* out, floa
   const LayerDev& ld = m->layers[li];
   const long long rows = (long long)B * L;
   int rc;
-  if ((rc = launch_linear(bproj_params(m, ld, x, bu, rows, bn), st, S5_K_BPROJ))) return rc;
+  const bool sq = m->desc.flavour == S5_STATIC;
+  if (sq && ld.tb.ok && rows >= m->tc_min_rows && is_pow2(ld.sc.s_ut) && is_pow2(ld.sc.s_But_re) && is_pow2(ld.sc.s_But_im)) {
+    float qlo, qhi;
+    qrange(m->desc.ssm_act_bits, &qlo, &qhi);
+    if ((rc = tc_linear_launch(ld.tb, x, bu, rows, bn ? ld.bn_mean : nullptr, bn ? ld.bn_mul : nullptr, bn ? ld.bn_bias : nullptr,
+                               ld.sc.s_ut, qlo, qhi, nullptr, ld.sc.s_But_re, ld.sc.s_But_im, qlo, qhi, 0, S5_K_BPROJ, st)))
+      return rc;
+  } else if ((rc = launch_linear(bproj_params(m, ld, x, bu, rows, bn), st, S5_K_BPROJ))) return rc;
   if ((rc = launch_scan_c64(bu, ld.lam, bu, B, L, m->desc.P, m->desc.relufication, scan_ws, scan_ws_bytes, st))) return rc;
+  if (sq && ld.tg.ok && !ssm_only && rows >= m->tc_min_rows && is_pow2(ld.sc.s_ut) && is_pow2(ld.sc.s_yt) &&
+      is_pow2(ld.sc.s_out2_act) && is_pow2(ld.sc.s_out2_out) && is_pow2(ld.sc.s_gate_left) && is_pow2(ld.sc.s_gate_right)) {
+    TcGluArgs a{};
+    a.XS = bu; a.X = x; a.OUT = out; a.rows = rows;
+    a.bn_sub = bn ? ld.bn_mean : nullptr; a.bn_mul = bn ? ld.bn_mul : nullptr; a.bn_add = bn ? ld.bn_bias : nullptr;
+    a.D = ld.D; a.o_bias = ld.o_bias;
+    a.s_ut = ld.sc.s_ut; a.s_yt = ld.sc.s_yt; a.s_o_act = ld.sc.s_out2_act; a.s_o_out = ld.sc.s_out2_out;
+    a.s_gl = ld.sc.s_gate_left; a.s_gr = ld.sc.s_gate_right;
+    qrange(m->desc.ssm_act_bits, &a.qs_min, &a.qs_max);
+    qrange(m->desc.non_ssm_act_bits, &a.qn_min, &a.qn_max);
+    a.relu_out = m->desc.relufication;
+    return tc_glu_launch(ld.tg, a, st);
+  }
   return launch_glu(glu_params(m, ld, bu, x, out, rows, bn, ssm_only), st);
 }
 
@@ -462,6 +488,9 @@ extern "C" int s5b200_model_create(const s5_model_desc* d, s5_model** out) {
   s5_model* m = new s5_model();
   m->desc = *d;
   m->desc.layers = nullptr;
+  // S5B200_TC_MIN_ROWS: row count from which the dense-tile (tcgen05) kernels replace the compressed ones
+  // (1 forces them, a huge value disables them); default 4096.
+  if (const char* e = getenv("S5B200_TC_MIN_ROWS")) m->tc_min_rows = atoll(e);
   const int H = d->H, P = d->P, dense = d->use_sparse ? 0 : 1;
   int rc = S5_OK;
   auto fail = [&](int code) { s5b200_model_destroy(m); return code; };
@@ -469,6 +498,10 @@ extern "C" int s5b200_model_create(const s5_model_desc* d, s5_model** out) {
   if ((rc = sparse_build(d->dec_kernel_host, H, d->d_output, S5_F32, dense, &m->dec))) return fail(rc);
   if ((rc = upload(d->enc_bias_host, H, &m->enc_bias))) return fail(rc);
   if ((rc = upload(d->dec_bias_host, d->d_output, &m->dec_bias))) return fail(rc);
+  if (d->flavour == S5_STATIC) {
+    if ((rc = tc_linear_build(d->enc_kernel_host, d->d_input, H, d->s_enc_act, &m->enc_tc))) return fail(rc);
+    if ((rc = tc_linear_build(d->dec_kernel_host, H, d->d_output, d->s_dec_act, &m->dec_tc))) return fail(rc);
+  }
   m->layers.resize(d->n_layers);
   for (int i = 0; i < d->n_layers; ++i) {
     const s5_layer_desc& l = d->layers[i];
@@ -485,6 +518,10 @@ extern "C" int s5b200_model_create(const s5_model_desc* d, s5_model** out) {
         wc[(size_t)(2 * p + 1) * H + h] = -l.C_tilde_host[((size_t)h * P + p) * 2 + 1];
       }
     if ((rc = sparse_build(wb.data(), H, 2 * P, S5_F32, dense, &ld.wb))) return fail(rc);
+    if (d->flavour == S5_STATIC && (rc = tc_linear_build(wb.data(), H, 2 * P, l.s_ut, &ld.tb))) return fail(rc);
+    if (d->flavour == S5_STATIC && d->activation == S5_ACT_RELU && l.out2_kernel_host &&
+        (rc = tc_glu_build(l.C_tilde_host, l.out2_kernel_host, H, P, d->conj_sym ? 2.f : 1.f, l.s_out2_act, &ld.tg)))
+      return fail(rc);
     if ((rc = sparse_build(wc.data(), 2 * P, H, S5_F32, dense, &ld.wc))) return fail(rc);
     if ((rc = sparse_build(l.out2_kernel_host, H, H, S5_F32, dense, &ld.wo))) return fail(rc);
     if ((rc = upload(l.lambda_bar_host, 2 * P, &ld.lam))) return fail(rc);
@@ -501,9 +538,12 @@ extern "C" int s5b200_model_create(const s5_model_desc* d, s5_model** out) {
 extern "C" int s5b200_model_destroy(s5_model* m) {
   if (!m) return S5_OK;
   s5::sparse_free(&m->enc); s5::sparse_free(&m->dec);
+  s5::tc_linear_free(&m->enc_tc); s5::tc_linear_free(&m->dec_tc);
   cudaFree(m->enc_bias); cudaFree(m->dec_bias);
   for (auto& l : m->layers) {
     s5::sparse_free(&l.wb); s5::sparse_free(&l.wc); s5::sparse_free(&l.wo);
+    s5::tc_linear_free(&l.tb);
+    s5::tc_glu_free(&l.tg);
     cudaFree(l.lam); cudaFree(l.D); cudaFree(l.bn_mean); cudaFree(l.bn_mul); cudaFree(l.bn_bias); cudaFree(l.o_bias);
   }
   cudaFree(m->hx); cudaFree(m->hy); cudaFree(m->hws);
@@ -529,11 +569,20 @@ extern "C" int s5b200_model_forward(const s5_model* m, const float* x, float* y,
   float* bu = reinterpret_cast<float*>(base + w.off_bu);
   const long long rows = (long long)B * L;
   const s5_model_desc& d = m->desc;
-  if ((rc = launch_linear(dense_params(m, m->enc, m->enc_bias, x, a, rows, d.s_enc_act, d.s_enc_out, d.relufication), st, S5_K_ENC))) return rc;
+  const bool tc = d.flavour == S5_STATIC && rows >= m->tc_min_rows;
+  float nlo = 0.f, nhi = 0.f;
+  if (tc) qrange(d.non_ssm_act_bits, &nlo, &nhi);
+  if (tc && m->enc_tc.ok && is_pow2(d.s_enc_act) && is_pow2(d.s_enc_out)) {
+    if ((rc = tc_linear_launch(m->enc_tc, x, a, rows, nullptr, nullptr, nullptr, d.s_enc_act, nlo, nhi, m->enc_bias, d.s_enc_out,
+                               d.s_enc_out, nlo, nhi, d.relufication, S5_K_ENC, st))) return rc;
+  } else if ((rc = launch_linear(dense_params(m, m->enc, m->enc_bias, x, a, rows, d.s_enc_act, d.s_enc_out, d.relufication), st, S5_K_ENC))) return rc;
   for (int i = 0; i < d.n_layers; ++i) {
     if ((rc = run_block(m, i, a, b, bu, B, L, base + w.off_scan, w.scan_bytes, true, false, st))) return rc;
     std::swap(a, b);
   }
+  if (tc && m->dec_tc.ok && is_pow2(d.s_dec_act) && is_pow2(d.s_dec_out))
+    return tc_linear_launch(m->dec_tc, a, y, rows, nullptr, nullptr, nullptr, d.s_dec_act, nlo, nhi, m->dec_bias, d.s_dec_out,
+                            d.s_dec_out, nlo, nhi, 0, S5_K_DEC, st);
   return launch_linear(dense_params(m, m->dec, m->dec_bias, a, y, rows, d.s_dec_act, d.s_dec_out, 0), st, S5_K_DEC);
 }
 

@@ -28,6 +28,10 @@ __device__ __forceinline__ uint64_t tc_smem_desc(uint32_t smem_addr, uint32_t lb
 __host__ __device__ __forceinline__ uint32_t tc_idesc_f16(int M, int N) {
   return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// same with A = B = BF16 (a_format, b_format = 1)
+__host__ __device__ __forceinline__ uint32_t tc_idesc_bf16(int M, int N) {
+  return tc_idesc_f16(M, N) | (1u << 7) | (1u << 10);
+}
 
 __device__ __forceinline__ void tc_alloc(uint32_t* smem_slot, uint32_t ncols) {  // one full warp
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)), "r"(ncols)

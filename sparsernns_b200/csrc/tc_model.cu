@@ -1,0 +1,592 @@
+// tc_model.cu - dense-tile (tcgen05) projection kernels of the static w8a16 flavour, for throughput batches.
+//
+// Why dense tiles: at rows = B*L >= 1e5 the projections are genuine [rows x K] x [K x N] contractions with tiny
+// weight matrices; the CUDA-core compressed kernels are instruction bound there (profiles/r01_*), the tensor cores
+// are not.  Exactness: static fake-quant values are integer codes times power-of-two scales.  int8 weight codes and
+// the hi/lo bytes of int16 activation codes are exact in f16, their products and the running sums (< 2^24 per
+// byte plane) are exact in the fp32 TMEM accumulators, and  acc = 256 * acc_hi + acc_lo  is recombined in int32 -
+// the tensor cores reproduce the exact integer sum; a single float rounding follows, as in the reference's fp32 dot.
+//
+//   tc_linear_kernel : encoder Dense / BatchNorm + B projection / decoder Dense of the reference
+//                      (quantization.py:684-816; ssm.py:230-246; layers.py:210-211)
+//   tc_glu_kernel    : C projection + D feed-through + ReLU + out2 Dense + sigmoid + mult_gate + skip + ReLU
+//                      (ssm.py:332-337, 594-601; layers.py:217-238)
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#include "proj.cuh"
+#include "tc.cuh"
+#include <cuda_bf16.h>
+
+#include "tc_model.cuh"
+
+namespace s5 {
+
+constexpr int kTcThreads = 256;
+constexpr int kTcRows = 128;
+constexpr int kTcKI = 8;  // K <= 256: each lane stages at most 8 input columns
+
+struct TcLinParams {
+  const float* X; float* Y; long long rows;
+  int K, N;                 // MMA dims (multiples of 16); the matrix may have one extra input row / output column
+  int x_stride, y_stride;   // floats per input / output row
+  const __half* Wh;         // [N][K] weight codes
+  const float* in_sub; const float* in_mul; const float* in_add;  // BatchNorm on the input (nullable)
+  float in_inv, in_qmin, in_qmax;   // 1 / s_in (s_in is a power of two, so x * in_inv == x / s_in exactly)
+  const float* col_scale;   // [y_stride] s_in * s_w[n]
+  const float* bias;        // [y_stride] fake-quantised bias, nullable
+  float out_scale0, out_scale1, out_inv0, out_inv1, out_qmin, out_qmax; int relu;
+  const float* w_extra_k;   // [N]  codes of weight row k = K   (encoder: K = 256 of 257), nullable
+  const float* w_extra_n;   // [K]  codes of weight column n = N (decoder: N = 256 of 257), nullable
+};
+
+// clip(round_half_even(x / s)) with 1/s passed in: exact for the power-of-two scales of the static recipe
+// (quantization.py:368-369, :395-396); the dense-tile path is only enabled when every scale is a power of two.
+__device__ __forceinline__ int quant_code(float v, float inv, float qmin, float qmax) {
+  return __float2int_rn(fminf(fmaxf(rintf(v * inv), qmin), qmax));
+}
+__device__ __forceinline__ float fq_from(float v, float s, float inv, float qmin, float qmax) {
+  return fminf(fmaxf(rintf(v * inv), qmin), qmax) * s;
+}
+__device__ __forceinline__ uint32_t pack_h2(int a, int b) {
+  const __half2 h = __halves2half2(__int2half_rn(a), __int2half_rn(b));
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+// Operand tiles use a padded leading-byte-offset (K-chunk stride = rows*16 + 16 bytes): with it both the
+// lanes-along-k 2-byte staging writes and lanes-along-rows 16-byte writes are bank-conflict free.
+__host__ __device__ __forceinline__ uint32_t tc_lbo(int rows) { return (uint32_t)rows * 16u + 16u; }
+__host__ __device__ __forceinline__ size_t tc_tile_bytes(int rows, int K) { return (size_t)(K >> 3) * tc_lbo(rows); }
+
+// copy a plain row-major [R][K] f16 matrix into the canonical operand layout
+__device__ __forceinline__ void tc_load_weights(unsigned char* dst, const __half* __restrict__ W, int R, int K) {
+  const int kchunks = K >> 3;
+  const uint32_t lbo = tc_lbo(R);
+  for (int i = threadIdx.x; i < R * kchunks; i += blockDim.x) {
+    const int r = i / kchunks, kc = i % kchunks;
+    *reinterpret_cast<int4*>(dst + (size_t)kc * lbo + (size_t)r * 16) = *reinterpret_cast<const int4*>(W + (size_t)r * K + kc * 8);
+  }
+}
+
+// issue the K/16 MMAs of one [128 x K] x [K x N] product (A and B in the padded canonical layout)
+__device__ __forceinline__ void tc_issue(uint32_t d_tmem, const void* A, const void* B, int K, int N, bool accumulate_first,
+                                         bool bf16 = false) {
+  const uint32_t a0 = smem_u32(A), b0 = smem_u32(B);
+  const uint32_t la = tc_lbo(kTcRows), lb = tc_lbo(N);
+  const uint32_t idesc = bf16 ? tc_idesc_bf16(kTcRows, N) : tc_idesc_f16(kTcRows, N);
+  for (int j = 0; j < (K >> 4); ++j)
+    tc_mma_f16(d_tmem, tc_smem_desc(a0 + j * 2 * la, la, 128), tc_smem_desc(b0 + j * 2 * lb, lb, 128), idesc, accumulate_first || j > 0);
+}
+
+__global__ void __launch_bounds__(kTcThreads, 2) tc_linear_kernel(TcLinParams p, uint32_t tmem_cols, uint32_t lo_col) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int K = p.K, N = p.N;
+  const size_t a_bytes = tc_tile_bytes(kTcRows, K);
+  unsigned char* Wt = smem;                                   // [N][K] weight codes
+  unsigned char* Ah = Wt + tc_tile_bytes(N, K);               // [128][K] high bytes of the activation codes
+  unsigned char* Al = Ah + a_bytes;                           // [128][K] low bytes
+  float* outT = reinterpret_cast<float*>(Ah);                 // output tile [128][NC + 4], aliases the dead A tiles
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  __shared__ int extra_n[kTcRows];                            // integer dot of the extra output column
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (warp == 0) tc_alloc(&tmem_slot, tmem_cols);
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+  }
+  tc_load_weights(Wt, p.Wh, N, K);
+  const uint32_t lbo = tc_lbo(kTcRows);
+  const int NC = N > 128 ? 128 : N;                           // columns per epilogue pass
+  const int ld_out = NC + 4;
+  const int erow = (warp & 3) * 32 + lane;                    // epilogue: TMEM lane = row
+  const int cw = NC >> 1;                                     // columns per warp half within a pass
+  // per-lane constants of the staging loop: lane owns input columns k = lane + 32 i
+  float sub[kTcKI], mul[kTcKI], add[kTcKI];
+  int wn[kTcKI];
+#pragma unroll
+  for (int i = 0; i < kTcKI; ++i) {
+    const int k = lane + 32 * i;
+    const bool in = k < K;
+    sub[i] = (in && p.in_sub) ? p.in_sub[k] : 0.f;
+    mul[i] = (in && p.in_sub) ? p.in_mul[k] : 1.f;
+    add[i] = (in && p.in_sub) ? p.in_add[k] : 0.f;
+    wn[i] = (in && p.w_extra_n) ? __float2int_rn(p.w_extra_n[k]) : 0;
+  }
+  uint32_t phase = 0;
+  const long long ntiles = (p.rows + kTcRows - 1) / kTcRows;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long row0 = tile * kTcRows;
+    const int rv = (int)min((long long)kTcRows, p.rows - row0);
+    // ---- stage (coalesced, lanes along k): quantise to int16 codes, split into hi / lo bytes stored as f16.
+    // Four rows are loaded before any of them is converted so that each lane keeps 4 * K/32 loads in flight.
+    for (int rb = warp * 4; rb < kTcRows; rb += (kTcThreads / 32) * 4) {
+      float raw[4][kTcKI];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float* xr = p.X + (size_t)(row0 + rb + q) * p.x_stride;
+#pragma unroll
+        for (int i = 0; i < kTcKI; ++i) {
+          const int k = lane + 32 * i;
+          raw[q][i] = (k < K && rb + q < rv) ? xr[k] : 0.f;
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int r = rb + q;
+        int part = 0;
+#pragma unroll
+        for (int i = 0; i < kTcKI; ++i) {
+          const int k = lane + 32 * i;
+          if (k < K) {
+            int c = 0;
+            if (r < rv) {
+              float v = raw[q][i];
+              if (p.in_sub) v = (v - sub[i]) * mul[i] + add[i];
+              c = quant_code(v, p.in_inv, p.in_qmin, p.in_qmax);
+            }
+            const size_t o = (size_t)(k >> 3) * lbo + (size_t)(k & 7) * 2 + (size_t)r * 16;
+            *reinterpret_cast<__half*>(Ah + o) = __int2half_rn(c >> 8);
+            *reinterpret_cast<__half*>(Al + o) = __int2half_rn(c & 255);
+            part += c * wn[i];
+          }
+        }
+        if (p.w_extra_n) {
+          part = __reduce_add_sync(0xffffffffu, part);
+          if (lane == 0) extra_n[r] = part;
+        }
+      }
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t taddr = tmem_slot;
+    if (tid == 0) {
+      tc_issue(taddr, Ah, Wt, K, N, false);
+      tc_issue(taddr + lo_col, Al, Wt, K, N, false);
+      tc_commit(&bar);
+    }
+    mbar_wait(&bar, phase);
+    phase ^= 1;
+    tc_fence_after();
+    // ---- epilogue: exact integer recombination, scale, bias, fake-quant, ReLU -> shared tile -> coalesced stores
+    const bool ok = erow < rv;
+    int code_k = 0;
+    if (p.w_extra_k && ok) code_k = quant_code(p.X[(size_t)(row0 + erow) * p.x_stride + K], p.in_inv, p.in_qmin, p.in_qmax);
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    for (int pass0 = 0; pass0 < N; pass0 += NC) {
+      const int cbeg = pass0 + (warp >> 2) * cw;
+      for (int c0 = cbeg; c0 < cbeg + cw; c0 += 16) {
+        uint32_t vh[16], vl[16];
+        tc_ld16(taddr + lane_base + c0, vh);
+        tc_ld16(taddr + lane_base + lo_col + c0, vl);
+        tc_wait_ld();
+        float out[16], cs[16], bs[16], wk[16];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          *reinterpret_cast<float4*>(cs + 4 * q) = *reinterpret_cast<const float4*>(p.col_scale + c0 + 4 * q);
+          *reinterpret_cast<float4*>(bs + 4 * q) = p.bias ? *reinterpret_cast<const float4*>(p.bias + c0 + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+          *reinterpret_cast<float4*>(wk + 4 * q) = p.w_extra_k ? *reinterpret_cast<const float4*>(p.w_extra_k + c0 + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          int acc = __float2int_rn(__uint_as_float(vh[j])) * 256 + __float2int_rn(__uint_as_float(vl[j]));
+          acc += code_k * __float2int_rn(wk[j]);
+          float v = __int2float_rn(acc) * cs[j] + bs[j];
+          v = (j & 1) ? fq_from(v, p.out_scale1, p.out_inv1, p.out_qmin, p.out_qmax) : fq_from(v, p.out_scale0, p.out_inv0, p.out_qmin, p.out_qmax);
+          out[j] = p.relu ? fmaxf(v, 0.f) : v;
+        }
+        float* dst = outT + (size_t)erow * ld_out + (c0 - pass0);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(dst + 4 * q) = make_float4(out[4 * q], out[4 * q + 1], out[4 * q + 2], out[4 * q + 3]);
+      }
+      __syncthreads();
+      for (int r = warp; r < rv; r += kTcThreads / 32) {
+        float* yr = p.Y + (size_t)(row0 + r) * p.y_stride + pass0;
+        const float* src = outT + (size_t)r * ld_out;
+        for (int n = lane; n < NC; n += 32) yr[n] = src[n];
+      }
+      __syncthreads();
+    }
+    if (p.w_extra_n) {  // output column n = N on the CUDA cores (decoder: 257 = 256 + 1)
+      if (tid < rv) {
+        float v = __int2float_rn(extra_n[tid]) * p.col_scale[N];
+        if (p.bias) v += p.bias[N];
+        v = (N & 1) ? fq_from(v, p.out_scale1, p.out_inv1, p.out_qmin, p.out_qmax) : fq_from(v, p.out_scale0, p.out_inv0, p.out_qmin, p.out_qmax);
+        p.Y[(size_t)(row0 + tid) * p.y_stride + N] = p.relu ? fmaxf(v, 0.f) : v;
+      }
+    }
+    tc_fence_before();
+    __syncthreads();  // TMEM, the A tiles / output tile and extra_n are free again
+  }
+  if (warp == 0) tc_dealloc(tmem_slot, tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------- C projection + GLU
+struct TcGluParams {
+  const float* XS;   // [rows][2P] scan output (complex64 interleaved, ReLU applied)
+  const float* X;    // [rows][H] block input (BatchNorm source, skip connection)
+  float* OUT;        // [rows][H]
+  long long rows; int H, K1;   // K1 = 2P
+  const __nv_bfloat16* Wc;     // [H][K1] codes of (C_re, -C_im) interleaved along k
+  const __half* Wo;            // [H][H]  codes of the out2 kernel
+  float xs_odd_mul;            // s_C_im / s_C_re folded into the odd (imaginary) inputs
+  float c_scale;               // conj_mul * s_C_re
+  const float* bn_sub; const float* bn_mul; const float* bn_add;
+  const float* D; const float* o_bias;
+  float o_col_scale;           // s_o_act * s_w_out2
+  float ut_s, ut_inv, yt_s, yt_inv, oa_inv, oo_s, oo_inv, gl_s, gl_inv, gr_s, gr_inv;
+  float qs_min, qs_max, qn_min, qn_max;
+  int relu_out;
+};
+
+__global__ void __launch_bounds__(kTcThreads, 1) tc_glu_kernel(TcGluParams p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int H = p.H, K1 = p.K1;
+  const int ld = H + 4;
+  unsigned char* Wc = smem;                                   // [H][K1] bf16
+  unsigned char* Wo = Wc + tc_tile_bytes(H, K1);              // [H][H]  f16
+  unsigned char* A1h = Wo + tc_tile_bytes(H, H);              // xs tile, bf16 high part
+  unsigned char* A1l = A1h + tc_tile_bytes(kTcRows, K1);      // xs tile, bf16 residual
+  unsigned char* A2h = A1h;                                   // x1 codes (alias: the xs tiles are dead after MMA 1)
+  unsigned char* A2l = A2h + tc_tile_bytes(kTcRows, H);
+  float* xT = reinterpret_cast<float*>(A1l + tc_tile_bytes(kTcRows, K1));  // [128][H+4] block input
+  float* oT = xT + (size_t)kTcRows * ld;                                    // [128][H+4] x1, then the block output
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (warp == 0) tc_alloc(&tmem_slot, 256);
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+  }
+  tc_load_weights(Wc, reinterpret_cast<const __half*>(p.Wc), H, K1);
+  tc_load_weights(Wo, p.Wo, H, H);
+  const uint32_t lbo = tc_lbo(kTcRows);
+  const int erow = (warp & 3) * 32 + lane;
+  const int cw = H >> 1;
+  const int cbeg = (warp >> 2) * cw;
+  const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+  uint32_t phase = 0;
+  const long long ntiles = (p.rows + kTcRows - 1) / kTcRows;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long row0 = tile * kTcRows;
+    const int rv = (int)min((long long)kTcRows, p.rows - row0);
+    // ---- stage: xs -> two bf16 planes (value = hi + lo to 16 mantissa bits); block input -> shared (coalesced)
+    for (int rb = warp * 4; rb < kTcRows; rb += (kTcThreads / 32) * 4) {
+      float raw[4][kTcKI];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float* xr = p.XS + (size_t)(row0 + rb + q) * K1;
+#pragma unroll
+        for (int i = 0; i < kTcKI; ++i) {
+          const int k = lane + 32 * i;
+          raw[q][i] = (k < K1 && rb + q < rv) ? xr[k] : 0.f;
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+#pragma unroll
+        for (int i = 0; i < kTcKI; ++i) {
+          const int k = lane + 32 * i;
+          if (k < K1) {
+            const float v = (k & 1) ? raw[q][i] * p.xs_odd_mul : raw[q][i];
+            const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+            const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+            const size_t o = (size_t)(k >> 3) * lbo + (size_t)(k & 7) * 2 + (size_t)(rb + q) * 16;
+            *reinterpret_cast<__nv_bfloat16*>(A1h + o) = hi;
+            *reinterpret_cast<__nv_bfloat16*>(A1l + o) = lo;
+          }
+        }
+      }
+    }
+    for (int r = warp; r < kTcRows; r += kTcThreads / 32) {
+      const float* xr = p.X + (size_t)(row0 + r) * H;
+      for (int n = lane; n < H; n += 32) xT[(size_t)r * ld + n] = r < rv ? xr[n] : 0.f;
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t taddr = tmem_slot;
+    if (tid == 0) {
+      tc_issue(taddr, A1h, Wc, K1, H, false, true);
+      tc_issue(taddr, A1l, Wc, K1, H, true, true);
+      tc_commit(&bar);
+    }
+    mbar_wait(&bar, phase);
+    phase ^= 1;
+    tc_fence_after();
+    // ---- epilogue 1: y = conj * Re(C x) + D u -> FQ -> x1 = ReLU(y); x1 codes -> operand tiles of the out2 product
+    for (int c0 = cbeg; c0 < cbeg + cw; c0 += 16) {
+      uint32_t v[16];
+      tc_ld16(taddr + lane_base + c0, v);
+      tc_wait_ld();
+      int code[16];
+      float x1[16], xu[16], bsub[16], bmul[16], badd[16], dd[16];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        *reinterpret_cast<float4*>(xu + 4 * q) = *reinterpret_cast<const float4*>(xT + (size_t)erow * ld + c0 + 4 * q);
+        *reinterpret_cast<float4*>(dd + 4 * q) = *reinterpret_cast<const float4*>(p.D + c0 + 4 * q);
+        if (p.bn_sub) {
+          *reinterpret_cast<float4*>(bsub + 4 * q) = *reinterpret_cast<const float4*>(p.bn_sub + c0 + 4 * q);
+          *reinterpret_cast<float4*>(bmul + 4 * q) = *reinterpret_cast<const float4*>(p.bn_mul + c0 + 4 * q);
+          *reinterpret_cast<float4*>(badd + 4 * q) = *reinterpret_cast<const float4*>(p.bn_add + c0 + 4 * q);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        float u = xu[j];
+        if (p.bn_sub) u = (u - bsub[j]) * bmul[j] + badd[j];
+        u = fq_from(u, p.ut_s, p.ut_inv, p.qs_min, p.qs_max);
+        float y = __uint_as_float(v[j]) * p.c_scale + dd[j] * u;
+        y = fq_from(y, p.yt_s, p.yt_inv, p.qs_min, p.qs_max);
+        x1[j] = fmaxf(y, 0.f);
+        code[j] = quant_code(x1[j], p.oa_inv, p.qn_min, p.qn_max);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        *reinterpret_cast<float4*>(oT + (size_t)erow * ld + c0 + 4 * q) = make_float4(x1[4 * q], x1[4 * q + 1], x1[4 * q + 2], x1[4 * q + 3]);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint4 hi, lo;
+        const int* c = code + 8 * h;
+        hi.x = pack_h2(c[0] >> 8, c[1] >> 8); hi.y = pack_h2(c[2] >> 8, c[3] >> 8);
+        hi.z = pack_h2(c[4] >> 8, c[5] >> 8); hi.w = pack_h2(c[6] >> 8, c[7] >> 8);
+        lo.x = pack_h2(c[0] & 255, c[1] & 255); lo.y = pack_h2(c[2] & 255, c[3] & 255);
+        lo.z = pack_h2(c[4] & 255, c[5] & 255); lo.w = pack_h2(c[6] & 255, c[7] & 255);
+        const size_t o = (size_t)((c0 >> 3) + h) * lbo + (size_t)erow * 16;
+        *reinterpret_cast<uint4*>(A2h + o) = hi;
+        *reinterpret_cast<uint4*>(A2l + o) = lo;
+      }
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (tid == 0) {
+      tc_issue(taddr, A2h, Wo, H, H, false);
+      tc_issue(taddr + 128, A2l, Wo, H, H, false);
+      tc_commit(&bar);
+    }
+    mbar_wait(&bar, phase);
+    phase ^= 1;
+    tc_fence_after();
+    // ---- epilogue 2: o = out2(x1) -> FQ ; g = FQ(x1) * FQ(sigmoid(o)) ; out = ReLU(g + skip)
+    for (int c0 = cbeg; c0 < cbeg + cw; c0 += 16) {
+      uint32_t vh[16], vl[16];
+      tc_ld16(taddr + lane_base + c0, vh);
+      tc_ld16(taddr + lane_base + 128 + c0, vl);
+      tc_wait_ld();
+      float xs_[16], x1[16], ob[16], res[16];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        *reinterpret_cast<float4*>(xs_ + 4 * q) = *reinterpret_cast<const float4*>(xT + (size_t)erow * ld + c0 + 4 * q);
+        *reinterpret_cast<float4*>(x1 + 4 * q) = *reinterpret_cast<const float4*>(oT + (size_t)erow * ld + c0 + 4 * q);
+        *reinterpret_cast<float4*>(ob + 4 * q) = *reinterpret_cast<const float4*>(p.o_bias + c0 + 4 * q);
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int acc = __float2int_rn(__uint_as_float(vh[j])) * 256 + __float2int_rn(__uint_as_float(vl[j]));
+        float o = __int2float_rn(acc) * p.o_col_scale + ob[j];
+        o = fq_from(o, p.oo_s, p.oo_inv, p.qn_min, p.qn_max);
+        float sg = 1.0f / (1.0f + expf(-o));
+        sg = fq_from(sg, p.gr_s, p.gr_inv, p.qn_min, p.qn_max);
+        const float l = fq_from(x1[j], p.gl_s, p.gl_inv, p.qn_min, p.qn_max);
+        const float out = l * sg + xs_[j];
+        res[j] = p.relu_out ? fmaxf(out, 0.f) : out;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        *reinterpret_cast<float4*>(oT + (size_t)erow * ld + c0 + 4 * q) = make_float4(res[4 * q], res[4 * q + 1], res[4 * q + 2], res[4 * q + 3]);
+    }
+    tc_fence_before();
+    __syncthreads();
+    for (int r = warp; r < rv; r += kTcThreads / 32) {
+      float* yr = p.OUT + (size_t)(row0 + r) * H;
+      for (int n = lane; n < H; n += 32) yr[n] = oT[(size_t)r * ld + n];
+    }
+    __syncthreads();
+  }
+  if (warp == 0) tc_dealloc(tmem_slot, 256);
+}
+
+// ------------------------------------------------------------------------------------------- host side
+
+static int upload_f(const std::vector<float>& h, float** d) {
+  S5_CUDA(cudaMalloc(d, std::max<size_t>(1, h.size()) * sizeof(float)));
+  S5_CUDA(cudaMemcpy(*d, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
+  return S5_OK;
+}
+
+// resident CTAs per SM from the three budgets that matter here: shared memory, registers, TMEM columns
+static int tc_ctas_per_sm(const void* kernel, size_t dyn_smem, int tmem_ctas) {
+  cudaFuncAttributes fa{};
+  if (cudaFuncGetAttributes(&fa, kernel) != cudaSuccess) return 1;
+  const int by_smem = (int)((227 * 1024) / (dyn_smem + fa.sharedSizeBytes + 1024));
+  const int by_regs = 65536 / std::max(1, fa.numRegs * kTcThreads);
+  return std::max(1, std::min(std::min(by_smem, by_regs), tmem_ctas));
+}
+
+bool is_pow2(float s) {
+  int e;
+  return s > 0.f && std::frexp(s, &e) == 0.5f;
+}
+
+// Largest power of two g such that every value of `w` (stride-strided subset) is an integer multiple of g.
+float pow2_grid(const float* w, size_t n, size_t start, size_t stride) {
+  int best = 1 << 30;
+  for (size_t i = start; i < n; i += stride) {
+    const float v = w[i];
+    if (v == 0.f || !std::isfinite(v)) continue;
+    int e;
+    const float m = std::frexp(std::fabs(v), &e);              // v = m * 2^e, m in [0.5, 1)
+    const uint32_t mi = (uint32_t)std::ldexp(m, 24);           // 24-bit integer mantissa
+    const int low = e - 24 + __builtin_ctz(mi);                // exponent of the lowest set bit
+    best = std::min(best, low);
+  }
+  return best == (1 << 30) ? 1.f : std::ldexp(1.f, best);
+}
+
+// W: fake-quantised weights [Kfull][Nfull]; even / odd output columns may sit on different power-of-two grids
+// (real / imaginary parts of the B projection).  s_in: activation scale.  out->ok stays false when the matrix is
+// not covered (shape, or codes that are not exact in f16), in which case the compressed kernels are used.
+int tc_linear_build(const float* W, int Kfull, int Nfull, float s_in, TcLinearDev* out) {
+  const int K = Kfull & ~15, N = Nfull & ~15;
+  out->ok = false;
+  if (!is_pow2(s_in)) return S5_OK;
+  std::vector<float> col0, col1;
+  for (int k = 0; k < Kfull; ++k)
+    for (int n = 0; n < Nfull; ++n) ((n & 1) ? col1 : col0).push_back(W[(size_t)k * Nfull + n]);
+  const float w_scale0 = pow2_grid(col0.data(), col0.size(), 0, 1);
+  const float w_scale1 = pow2_grid(col1.data(), col1.size(), 0, 1);
+  if (Kfull - K > 1 || Nfull - N > 1 || K < 16 || K > 32 * kTcKI || N < 32 || (N & 31) || N > 256) return S5_OK;  // shape not covered
+  if (tc_tile_bytes(N, K) + std::max(2 * tc_tile_bytes(kTcRows, K), (size_t)kTcRows * ((N > 128 ? 128 : N) + 4) * 4) > 225 * 1024) return S5_OK;
+  std::vector<__half> wh((size_t)N * K);
+  std::vector<float> cs(Nfull), wk, wn;
+  auto code = [&](int k, int n) {
+    const float s = (n & 1) ? w_scale1 : w_scale0;
+    return std::nearbyint(W[(size_t)k * Nfull + n] / s);
+  };
+  for (int n = 0; n < N; ++n)
+    for (int k = 0; k < K; ++k) {
+      const float c = code(k, n);
+      if (std::fabs(c) > 2048.f) return S5_OK;  // not exact in f16: leave this matrix to the compressed kernels
+      wh[(size_t)n * K + k] = __float2half_rn(c);
+    }
+  for (int n = 0; n < Nfull; ++n) cs[n] = s_in * ((n & 1) ? w_scale1 : w_scale0);
+  if (Kfull > K) { wk.resize(N); for (int n = 0; n < N; ++n) wk[n] = code(K, n); }
+  if (Nfull > N) { wn.resize(K); for (int k = 0; k < K; ++k) wn[k] = code(k, N); }
+  if (Kfull > K && Nfull > N) return S5_OK;
+  out->K = K; out->N = N; out->x_stride = Kfull; out->y_stride = Nfull;
+  S5_CUDA(cudaMalloc(&out->Wh, wh.size() * sizeof(__half)));
+  S5_CUDA(cudaMemcpy(out->Wh, wh.data(), wh.size() * sizeof(__half), cudaMemcpyHostToDevice));
+  int rc;
+  if ((rc = upload_f(cs, &out->col_scale))) return rc;
+  if (!wk.empty() && (rc = upload_f(wk, &out->w_extra_k))) return rc;
+  if (!wn.empty() && (rc = upload_f(wn, &out->w_extra_n))) return rc;
+  out->ok = true;
+  return S5_OK;
+}
+
+void tc_linear_free(TcLinearDev* d) {
+  cudaFree(d->Wh); cudaFree(d->col_scale); cudaFree(d->w_extra_k); cudaFree(d->w_extra_n);
+  *d = TcLinearDev();
+}
+
+int tc_linear_launch(const TcLinearDev& d, const float* X, float* Y, long long rows, const float* in_sub, const float* in_mul,
+                     const float* in_add, float in_scale, float in_qmin, float in_qmax, const float* bias, float out_scale0,
+                     float out_scale1, float out_qmin, float out_qmax, int relu, int kclass, cudaStream_t st) {
+  if (!d.ok || !is_pow2(in_scale) || !is_pow2(out_scale0) || !is_pow2(out_scale1)) S5_FAIL(S5_E_BADARG, "dense-tile linear: not eligible");
+  TcLinParams p{};
+  p.X = X; p.Y = Y; p.rows = rows; p.K = d.K; p.N = d.N; p.x_stride = d.x_stride; p.y_stride = d.y_stride; p.Wh = d.Wh;
+  p.in_sub = in_sub; p.in_mul = in_mul; p.in_add = in_add; p.in_inv = 1.0f / in_scale; p.in_qmin = in_qmin; p.in_qmax = in_qmax;
+  p.col_scale = d.col_scale; p.bias = bias; p.out_scale0 = out_scale0; p.out_scale1 = out_scale1;
+  p.out_inv0 = 1.0f / out_scale0; p.out_inv1 = 1.0f / out_scale1;
+  p.out_qmin = out_qmin; p.out_qmax = out_qmax; p.relu = relu; p.w_extra_k = d.w_extra_k; p.w_extra_n = d.w_extra_n;
+  const int NC = d.N > 128 ? 128 : d.N;
+  size_t smem = tc_tile_bytes(d.N, d.K) + std::max(2 * tc_tile_bytes(kTcRows, d.K), (size_t)kTcRows * (NC + 4) * 4);
+  const uint32_t lo_col = d.N <= 128 ? 128 : 256;
+  const uint32_t cols = 2 * lo_col;
+  // TMEM has 512 columns per SM: never let more CTAs become resident than can allocate their accumulators
+  const int tmem_ctas = (int)(512 / cols);
+  smem = std::max(smem, (size_t)(227 * 1024) / (tmem_ctas + 1) + 1024);
+  S5_CUDA(cudaFuncSetAttribute(tc_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  S5_CUDA(cudaFuncSetAttribute(tc_linear_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  const int per_sm = tc_ctas_per_sm(reinterpret_cast<const void*>(tc_linear_kernel), smem, tmem_ctas);
+  const long long ntiles = (rows + kTcRows - 1) / kTcRows;
+  const int grid = (int)std::max<long long>(1, std::min<long long>(ntiles, (long long)per_sm * sm_count()));
+  ProfScope prof(kclass, st);
+  tc_linear_kernel<<<grid, kTcThreads, smem, st>>>(p, cols, lo_col);
+  S5_LAUNCH_CHECK();
+  return S5_OK;
+}
+
+
+// ---- C projection + GLU handle
+int tc_glu_build(const float* C_tilde /*[H][P][2] quantised*/, const float* out2_kernel /*[H][H] quantised*/, int H, int P,
+                 float conj_mul, float s_o_act, TcGluDev* out) {
+  out->ok = false;
+  const int K1 = 2 * P;
+  if ((H & 31) || H > 128 || (K1 & 15) || K1 > 32 * kTcKI || !is_pow2(s_o_act)) return S5_OK;
+  const size_t smem = tc_tile_bytes(H, K1) + tc_tile_bytes(H, H) + 2 * tc_tile_bytes(kTcRows, K1) + 2 * (size_t)kTcRows * (H + 4) * 4;
+  if (smem > 226 * 1024 || 2 * tc_tile_bytes(kTcRows, H) > 2 * tc_tile_bytes(kTcRows, K1)) return S5_OK;
+  const size_t nC = (size_t)H * P * 2;
+  const float s_re = pow2_grid(C_tilde, nC, 0, 2), s_im = pow2_grid(C_tilde, nC, 1, 2);
+  const float s_w = pow2_grid(out2_kernel, (size_t)H * H, 0, 1);
+  std::vector<__nv_bfloat16> wc((size_t)H * K1);
+  std::vector<__half> wo((size_t)H * H);
+  for (int h = 0; h < H; ++h)
+    for (int p = 0; p < P; ++p) {
+      const float cre = std::nearbyint(C_tilde[((size_t)h * P + p) * 2] / s_re);
+      const float cim = std::nearbyint(C_tilde[((size_t)h * P + p) * 2 + 1] / s_im);
+      if (std::fabs(cre) > 256.f || std::fabs(cim) > 256.f) return S5_OK;  // not exact in bf16
+      wc[(size_t)h * K1 + 2 * p] = __float2bfloat16_rn(cre);
+      wc[(size_t)h * K1 + 2 * p + 1] = __float2bfloat16_rn(-cim);          // Re(C x) = C_re x_re - C_im x_im
+    }
+  for (int n = 0; n < H; ++n)
+    for (int k = 0; k < H; ++k) {
+      const float c = std::nearbyint(out2_kernel[(size_t)k * H + n] / s_w);
+      if (std::fabs(c) > 2048.f) return S5_OK;
+      wo[(size_t)n * H + k] = __float2half_rn(c);
+    }
+  out->H = H; out->K1 = K1; out->smem = smem;
+  out->xs_odd_mul = s_im / s_re; out->c_scale = conj_mul * s_re; out->o_col_scale = s_o_act * s_w;
+  S5_CUDA(cudaMalloc(&out->Wc, wc.size() * sizeof(__nv_bfloat16)));
+  S5_CUDA(cudaMemcpy(out->Wc, wc.data(), wc.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
+  S5_CUDA(cudaMalloc(&out->Wo, wo.size() * sizeof(__half)));
+  S5_CUDA(cudaMemcpy(out->Wo, wo.data(), wo.size() * sizeof(__half), cudaMemcpyHostToDevice));
+  out->ok = true;
+  return S5_OK;
+}
+
+void tc_glu_free(TcGluDev* d) {
+  cudaFree(d->Wc); cudaFree(d->Wo);
+  *d = TcGluDev();
+}
+
+int tc_glu_launch(const TcGluDev& d, const TcGluArgs& a, cudaStream_t st) {
+  const float sc[] = {a.s_ut, a.s_yt, a.s_o_act, a.s_o_out, a.s_gl, a.s_gr};
+  for (float s : sc)
+    if (!is_pow2(s)) S5_FAIL(S5_E_BADARG, "dense-tile glu: scales must be powers of two");
+  if (!d.ok) S5_FAIL(S5_E_BADARG, "dense-tile glu: not eligible");
+  TcGluParams p{};
+  p.XS = a.XS; p.X = a.X; p.OUT = a.OUT; p.rows = a.rows; p.H = d.H; p.K1 = d.K1;
+  p.Wc = reinterpret_cast<const __nv_bfloat16*>(d.Wc); p.Wo = reinterpret_cast<const __half*>(d.Wo);
+  p.xs_odd_mul = d.xs_odd_mul; p.c_scale = d.c_scale; p.o_col_scale = d.o_col_scale;
+  p.bn_sub = a.bn_sub; p.bn_mul = a.bn_mul; p.bn_add = a.bn_add; p.D = a.D; p.o_bias = a.o_bias;
+  p.ut_s = a.s_ut; p.ut_inv = 1.f / a.s_ut; p.yt_s = a.s_yt; p.yt_inv = 1.f / a.s_yt; p.oa_inv = 1.f / a.s_o_act;
+  p.oo_s = a.s_o_out; p.oo_inv = 1.f / a.s_o_out; p.gl_s = a.s_gl; p.gl_inv = 1.f / a.s_gl; p.gr_s = a.s_gr; p.gr_inv = 1.f / a.s_gr;
+  p.qs_min = a.qs_min; p.qs_max = a.qs_max; p.qn_min = a.qn_min; p.qn_max = a.qn_max; p.relu_out = a.relu_out;
+  S5_CUDA(cudaFuncSetAttribute(tc_glu_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d.smem));
+  const long long ntiles = (a.rows + kTcRows - 1) / kTcRows;
+  const int grid = (int)std::max<long long>(1, std::min<long long>(ntiles, (long long)sm_count()));
+  ProfScope prof(S5_K_GLU, st);
+  tc_glu_kernel<<<grid, kTcThreads, d.smem, st>>>(p);
+  S5_LAUNCH_CHECK();
+  return S5_OK;
+}
+
+}  // namespace s5

@@ -1,0 +1,39 @@
+// tc_model.cuh - host-side handles of the dense-tile (tcgen05) kernels in tc_model.cu.
+#pragma once
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+
+namespace s5 {
+
+struct TcLinearDev {
+  int K = 0, N = 0, x_stride = 0, y_stride = 0;
+  __half* Wh = nullptr;
+  float* col_scale = nullptr; float* w_extra_k = nullptr; float* w_extra_n = nullptr;
+  bool ok = false;
+};
+
+struct TcGluDev {
+  int H = 0, K1 = 0; size_t smem = 0;
+  void* Wc = nullptr; void* Wo = nullptr;   // bf16 [H][2P] and f16 [H][H] weight codes
+  float xs_odd_mul = 1.f, c_scale = 1.f, o_col_scale = 1.f;
+  bool ok = false;
+};
+struct TcGluArgs {
+  const float* XS; const float* X; float* OUT; long long rows;
+  const float* bn_sub; const float* bn_mul; const float* bn_add; const float* D; const float* o_bias;
+  float s_ut, s_yt, s_o_act, s_o_out, s_gl, s_gr, qs_min, qs_max, qn_min, qn_max; int relu_out;
+};
+
+bool is_pow2(float s);
+float pow2_grid(const float* w, size_t n, size_t start, size_t stride);
+int tc_glu_build(const float* C_tilde, const float* out2_kernel, int H, int P, float conj_mul, float s_o_act, TcGluDev* out);
+void tc_glu_free(TcGluDev* d);
+int tc_glu_launch(const TcGluDev& d, const TcGluArgs& a, cudaStream_t st);
+int tc_linear_build(const float* W, int Kfull, int Nfull, float s_in, TcLinearDev* out);
+void tc_linear_free(TcLinearDev* d);
+int tc_linear_launch(const TcLinearDev& d, const float* X, float* Y, long long rows, const float* in_sub, const float* in_mul,
+                     const float* in_add, float in_scale, float in_qmin, float in_qmax, const float* bias, float out_scale0,
+                     float out_scale1, float out_qmin, float out_qmax, int relu, int kclass, cudaStream_t st);
+
+}  // namespace s5
