@@ -327,10 +327,14 @@ struct s5_model {
   long long tc_min_rows = 4096;  // below this the compressed CUDA-core kernels are used
   float *enc_bias = nullptr, *dec_bias = nullptr;
   std::vector<s5::LayerDev> layers;
-  // cached device buffers for the host-buffer entry point
+  // host-buffer entry point: ring of device buffers, three streams (H2D | forward | D2H) and their events
+  static constexpr int kSlots = 3;
   std::mutex mu;
-  float *hx = nullptr, *hy = nullptr; void* hws = nullptr;
-  size_t hx_cap = 0, hy_cap = 0, hws_cap = 0;
+  float* hx[kSlots] = {nullptr, nullptr, nullptr}; float* hy[kSlots] = {nullptr, nullptr, nullptr};
+  void* hws[kSlots] = {nullptr, nullptr, nullptr};
+  size_t hx_cap[kSlots] = {0, 0, 0}, hy_cap[kSlots] = {0, 0, 0}, hws_cap[kSlots] = {0, 0, 0};
+  cudaStream_t hs[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev_h2d[kSlots] = {}, ev_cmp[kSlots] = {}, ev_d2h[kSlots] = {}, ev_user = nullptr;
 };
 
 namespace s5 {
@@ -546,7 +550,15 @@ extern "C" int s5b200_model_destroy(s5_model* m) {
     s5::tc_glu_free(&l.tg);
     cudaFree(l.lam); cudaFree(l.D); cudaFree(l.bn_mean); cudaFree(l.bn_mul); cudaFree(l.bn_bias); cudaFree(l.o_bias);
   }
-  cudaFree(m->hx); cudaFree(m->hy); cudaFree(m->hws);
+  for (int i = 0; i < s5_model::kSlots; ++i) {
+    cudaFree(m->hx[i]); cudaFree(m->hy[i]); cudaFree(m->hws[i]);
+    if (m->ev_h2d[i]) cudaEventDestroy(m->ev_h2d[i]);
+    if (m->ev_cmp[i]) cudaEventDestroy(m->ev_cmp[i]);
+    if (m->ev_d2h[i]) cudaEventDestroy(m->ev_d2h[i]);
+  }
+  if (m->ev_user) cudaEventDestroy(m->ev_user);
+  for (int i = 0; i < 3; ++i)
+    if (m->hs[i]) cudaStreamDestroy(m->hs[i]);
   delete m;
   return S5_OK;
 }
@@ -614,15 +626,20 @@ extern "C" int s5b200_ssm_forward(const s5_model* m, int layer, const float* u, 
 
 extern "C" int s5b200_model_forward_host(const s5_model* mc, const float* x_host, float* y_host, int B, int L,
                                          void* stream) {
+  // End-to-end entry point: the batch is cut into clip chunks that flow through a three-stage pipeline
+  // (H2D copy | forward | D2H copy) on three internal streams with a ring of kSlots device buffers, so that
+  // the two PCIe directions and the kernels overlap.  Clips are independent, so chunking does not change results.
   using namespace s5;
   s5_model* m = const_cast<s5_model*>(mc);
   if (!m || !x_host || !y_host) S5_FAIL(S5_E_BADARG, "model_forward_host: null pointer");
   if (B <= 0 || L <= 0 || B > 65535) S5_FAIL(S5_E_BADSHAPE, "model_forward_host: B=%d L=%d outside the supported range", B, L);
-  cudaStream_t st = (cudaStream_t)stream;
+  cudaStream_t user = (cudaStream_t)stream;
   std::lock_guard<std::mutex> lock(m->mu);
-  const size_t rows = (size_t)B * L;
-  const size_t xb = rows * m->desc.d_input * sizeof(float), yb = rows * m->desc.d_output * sizeof(float);
-  const size_t wsb = ws_layout(m, B, L).total;
+  constexpr int kSlots = s5_model::kSlots;
+  const int nchunks = B >= 8 ? 4 : 1;
+  const int cb = (B + nchunks - 1) / nchunks;  // clips per chunk
+  const size_t xb = (size_t)cb * L * m->desc.d_input * sizeof(float), yb = (size_t)cb * L * m->desc.d_output * sizeof(float);
+  const size_t wsb = ws_layout(m, cb, L).total;
   auto grow = [&](void** p, size_t* cap, size_t need) -> int {
     if (*cap >= need) return S5_OK;
     if (*p) S5_CUDA(cudaFree(*p));
@@ -632,12 +649,41 @@ extern "C" int s5b200_model_forward_host(const s5_model* mc, const float* x_host
     return S5_OK;
   };
   int rc;
-  if ((rc = grow(reinterpret_cast<void**>(&m->hx), &m->hx_cap, xb))) return rc;
-  if ((rc = grow(reinterpret_cast<void**>(&m->hy), &m->hy_cap, yb))) return rc;
-  if ((rc = grow(&m->hws, &m->hws_cap, wsb))) return rc;
-  S5_CUDA(cudaMemcpyAsync(m->hx, x_host, xb, cudaMemcpyHostToDevice, st));
-  if ((rc = s5b200_model_forward(m, m->hx, m->hy, B, L, m->hws, m->hws_cap, stream))) return rc;
-  S5_CUDA(cudaMemcpyAsync(y_host, m->hy, yb, cudaMemcpyDeviceToHost, st));
-  S5_CUDA(cudaStreamSynchronize(st));
+  if (!m->hs[0]) {
+    for (int i = 0; i < 3; ++i) S5_CUDA(cudaStreamCreateWithFlags(&m->hs[i], cudaStreamNonBlocking));
+    for (int i = 0; i < kSlots; ++i) {
+      S5_CUDA(cudaEventCreateWithFlags(&m->ev_h2d[i], cudaEventDisableTiming));
+      S5_CUDA(cudaEventCreateWithFlags(&m->ev_cmp[i], cudaEventDisableTiming));
+      S5_CUDA(cudaEventCreateWithFlags(&m->ev_d2h[i], cudaEventDisableTiming));
+    }
+    S5_CUDA(cudaEventCreateWithFlags(&m->ev_user, cudaEventDisableTiming));
+  }
+  for (int i = 0; i < kSlots; ++i) {
+    if ((rc = grow(reinterpret_cast<void**>(&m->hx[i]), &m->hx_cap[i], xb))) return rc;
+    if ((rc = grow(reinterpret_cast<void**>(&m->hy[i]), &m->hy_cap[i], yb))) return rc;
+    if ((rc = grow(&m->hws[i], &m->hws_cap[i], wsb))) return rc;
+  }
+  cudaStream_t s_in = m->hs[0], s_cmp = m->hs[1], s_out = m->hs[2];
+  S5_CUDA(cudaEventRecord(m->ev_user, user));  // order after whatever the caller queued before
+  S5_CUDA(cudaStreamWaitEvent(s_in, m->ev_user, 0));
+  for (int c = 0; c < nchunks; ++c) {
+    const int b0 = c * cb, nb = std::min(cb, B - b0);
+    if (nb <= 0) break;
+    const int slot = c % kSlots;
+    const size_t xoff = (size_t)b0 * L * m->desc.d_input, yoff = (size_t)b0 * L * m->desc.d_output;
+    const size_t xbytes = (size_t)nb * L * m->desc.d_input * sizeof(float), ybytes = (size_t)nb * L * m->desc.d_output * sizeof(float);
+    if (c >= kSlots) S5_CUDA(cudaStreamWaitEvent(s_in, m->ev_d2h[slot], 0));  // slot buffers are free again
+    S5_CUDA(cudaMemcpyAsync(m->hx[slot], x_host + xoff, xbytes, cudaMemcpyHostToDevice, s_in));
+    S5_CUDA(cudaEventRecord(m->ev_h2d[slot], s_in));
+    S5_CUDA(cudaStreamWaitEvent(s_cmp, m->ev_h2d[slot], 0));
+    if ((rc = s5b200_model_forward(m, m->hx[slot], m->hy[slot], nb, L, m->hws[slot], m->hws_cap[slot], s_cmp))) return rc;
+    S5_CUDA(cudaEventRecord(m->ev_cmp[slot], s_cmp));
+    S5_CUDA(cudaStreamWaitEvent(s_out, m->ev_cmp[slot], 0));
+    S5_CUDA(cudaMemcpyAsync(y_host + yoff, m->hy[slot], ybytes, cudaMemcpyDeviceToHost, s_out));
+    S5_CUDA(cudaEventRecord(m->ev_d2h[slot], s_out));
+  }
+  S5_CUDA(cudaStreamSynchronize(s_out));
+  S5_CUDA(cudaStreamSynchronize(s_cmp));
+  S5_CUDA(cudaStreamSynchronize(s_in));
   return S5_OK;
 }

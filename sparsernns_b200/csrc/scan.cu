@@ -250,11 +250,124 @@ __global__ void __launch_bounds__(128) scan_i32_kernel(ScanI32Params q) {
   }
 }
 
+// Ring variant of the integer recurrence for throughput AND latency: one CTA per clip, one thread per state, the
+// clip's [L][P] stream flows through a ring of kRingStages shared-memory tiles filled by 1-D bulk async copies
+// (TMA engine) kRingStages-2 tiles ahead and drained by bulk stores, so the sequential dependency chain never waits
+// on DRAM: time per clip ~ L x (one IMAD -> shift -> add chain).
+constexpr int kRingStages = 4;
+constexpr int kRingSteps = 32;
+
+template <bool INTERLEAVED>
+__global__ void __launch_bounds__(256) scan_i32_ring_kernel(ScanI32Params q) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t full[kRingStages];
+  const int P = q.P, L = q.L;
+  const int p = threadIdx.x;
+  const long long b = blockIdx.x;
+  const size_t tile_elems = (size_t)kRingSteps * P;                 // states per tile
+  const size_t stage_bytes = tile_elems * 8;
+  int* tiles = reinterpret_cast<int*>(smem_raw);
+  const int ntiles = (L + kRingSteps - 1) / kRingSteps;
+  const size_t clip_off = (size_t)b * L * P;
+  if (p == 0) {
+    for (int s = 0; s < kRingStages; ++s) mbar_init(&full[s], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  auto issue_load = [&](int t) {
+    const int s = t % kRingStages;
+    const int rows = min(kRingSteps, L - t * kRingSteps);
+    const uint32_t bytes = (uint32_t)rows * P * 4u;
+    unsigned char* dst = smem_raw + (size_t)s * stage_bytes;
+    const size_t off = clip_off + (size_t)t * tile_elems;
+    mbar_expect_tx(&full[s], 2 * bytes);
+    if (INTERLEAVED) {
+      bulk_g2s(dst, reinterpret_cast<const int2*>(q.Bu_re) + off, 2 * bytes, &full[s]);
+    } else {
+      bulk_g2s(dst, q.Bu_re + off, bytes, &full[s]);
+      bulk_g2s(dst + tile_elems * 4, q.Bu_im + off, bytes, &full[s]);
+    }
+  };
+  if (p == 0)
+    for (int t = 0; t < min(kRingStages - 2, ntiles); ++t) issue_load(t);
+  const bool active = p < P;
+  const int ar = active ? q.A_re[p] : 0, ai = active ? q.A_im[p] : 0;
+  int xr = 0, xi = 0;
+  for (int i = 0; i < ntiles; ++i) {
+    const int s = i % kRingStages;
+    if (p == 0) {
+      const int j = i + kRingStages - 2;
+      if (j < ntiles) {
+        bulk_wait_read1();  // the store that last used stage j % S (iteration i-2) has released it
+        issue_load(j);
+      }
+    }
+    mbar_wait(&full[s], (uint32_t)(i / kRingStages) & 1u);
+    const int rows = min(kRingSteps, L - i * kRingSteps);
+    int* tre = reinterpret_cast<int*>(smem_raw + (size_t)s * stage_bytes);
+    int* tim = tre + tile_elems;
+    if (active) {
+#pragma unroll 4
+      for (int t = 0; t < rows; ++t) {
+        int br, bi;
+        if (INTERLEAVED) {
+          const int2 v = reinterpret_cast<const int2*>(tre)[(size_t)t * P + p];
+          br = v.x; bi = v.y;
+        } else {
+          br = tre[(size_t)t * P + p]; bi = tim[(size_t)t * P + p];
+        }
+        const int cr = shift_align(br, q.eBu_re, q.ex_re);
+        const int ci = shift_align(bi, q.eBu_im, q.ex_im);
+        const int nr = (int)((unsigned)(mulw(ar, xr) >> q.eA_re) - (unsigned)(mulw(ai, xi) >> q.eA_re) + (unsigned)cr);
+        const int ni = (int)((unsigned)(mulw(ar, xi) >> q.eA_im) + (unsigned)(mulw(ai, xr) >> q.eA_im) + (unsigned)ci);
+        xr = nr; xi = ni;
+        int orr = xr, oi = xi;
+        if (q.relu) fxp_relu_complex(orr, oi);
+        if (INTERLEAVED) {
+          reinterpret_cast<int2*>(tre)[(size_t)t * P + p] = make_int2(orr, oi);
+        } else {
+          tre[(size_t)t * P + p] = orr; tim[(size_t)t * P + p] = oi;
+        }
+      }
+    }
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (p == 0) {
+      const uint32_t bytes = (uint32_t)rows * P * 4u;
+      const size_t off = clip_off + (size_t)i * tile_elems;
+      if (INTERLEAVED) {
+        bulk_s2g(reinterpret_cast<int2*>(q.xs_re) + off, tre, 2 * bytes);
+      } else {
+        bulk_s2g(q.xs_re + off, tre, bytes);
+        bulk_s2g(q.xs_im + off, tim, bytes);
+      }
+      bulk_commit();
+    }
+  }
+  if (p == 0) bulk_wait0();
+}
+
 int launch_scan_i32(const ScanI32Params& q, bool interleaved, cudaStream_t st) {
+  const long long B = q.lanes / q.P;
+  const bool ptr_ok = aligned16(q.Bu_re) && aligned16(q.xs_re) && (interleaved || (aligned16(q.Bu_im) && aligned16(q.xs_im)));
+  const bool ring_ok = ptr_ok && q.P <= 256 && (interleaved ? (q.P % 2 == 0) : (q.P % 4 == 0)) && B <= 0x7fffffffLL;
+  ProfScope prof(S5_K_SCAN_I32, st);
+  if (ring_ok) {
+    const size_t smem = (size_t)kRingStages * kRingSteps * q.P * 8;
+    const int threads = (q.P + 31) & ~31;
+    if (interleaved) {
+      S5_CUDA(cudaFuncSetAttribute(scan_i32_ring_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      scan_i32_ring_kernel<true><<<(unsigned)B, threads, smem, st>>>(q);
+    } else {
+      S5_CUDA(cudaFuncSetAttribute(scan_i32_ring_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      scan_i32_ring_kernel<false><<<(unsigned)B, threads, smem, st>>>(q);
+    }
+    S5_LAUNCH_CHECK();
+    return S5_OK;
+  }
   const int threads = 128;
   const long long blocks = (q.lanes + threads - 1) / threads;
   if (blocks > 0x7fffffffLL) S5_FAIL(S5_E_BADSHAPE, "scan_i32: too many lanes");
-  ProfScope prof(S5_K_SCAN_I32, st);
   if (interleaved) scan_i32_kernel<true, 8><<<(unsigned)blocks, threads, 0, st>>>(q);
   else scan_i32_kernel<false, 8><<<(unsigned)blocks, threads, 0, st>>>(q);
   S5_LAUNCH_CHECK();
