@@ -213,6 +213,7 @@ def main():
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout for the single JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     dims = synth.ndns_dims(args.dim_scale)

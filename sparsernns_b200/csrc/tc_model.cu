@@ -79,6 +79,7 @@ __device__ __forceinline__ void tc_issue(uint32_t d_tmem, const void* A, const v
     tc_mma_f16(d_tmem, tc_smem_desc(a0 + j * 2 * la, la, 128), tc_smem_desc(b0 + j * 2 * lb, lb, 128), idesc, accumulate_first || j > 0);
 }
 
+template <bool VEC4>
 __global__ void __launch_bounds__(kTcThreads, 2) tc_linear_kernel(TcLinParams p, uint32_t tmem_cols, uint32_t lo_col) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int K = p.K, N = p.N;
@@ -102,59 +103,117 @@ __global__ void __launch_bounds__(kTcThreads, 2) tc_linear_kernel(TcLinParams p,
   const int ld_out = NC + 4;
   const int erow = (warp & 3) * 32 + lane;                    // epilogue: TMEM lane = row
   const int cw = NC >> 1;                                     // columns per warp half within a pass
-  // per-lane constants of the staging loop: lane owns input columns k = lane + 32 i
+  // per-lane constants of the staging loop.  Scalar form: lane owns columns k = lane + 32 i; vector form (rows
+  // 16-byte aligned): lane owns columns 4 lane + 128 i .. + 3.
+  constexpr bool vec4 = VEC4;
   float sub[kTcKI], mul[kTcKI], add[kTcKI];
   int wn[kTcKI];
+  float sub4[2][4], mul4[2][4], add4[2][4];
+  int wn4[2][4];
 #pragma unroll
   for (int i = 0; i < kTcKI; ++i) {
     const int k = lane + 32 * i;
-    const bool in = k < K;
+    const bool in = k < K && !vec4;
     sub[i] = (in && p.in_sub) ? p.in_sub[k] : 0.f;
     mul[i] = (in && p.in_sub) ? p.in_mul[k] : 1.f;
     add[i] = (in && p.in_sub) ? p.in_add[k] : 0.f;
     wn[i] = (in && p.w_extra_n) ? __float2int_rn(p.w_extra_n[k]) : 0;
   }
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int k = 4 * lane + 128 * i + e;
+      const bool in = k < K && vec4;
+      sub4[i][e] = (in && p.in_sub) ? p.in_sub[k] : 0.f;
+      mul4[i][e] = (in && p.in_sub) ? p.in_mul[k] : 1.f;
+      add4[i][e] = (in && p.in_sub) ? p.in_add[k] : 0.f;
+      wn4[i][e] = (in && p.w_extra_n) ? __float2int_rn(p.w_extra_n[k]) : 0;
+    }
   uint32_t phase = 0;
   const long long ntiles = (p.rows + kTcRows - 1) / kTcRows;
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const long long row0 = tile * kTcRows;
     const int rv = (int)min((long long)kTcRows, p.rows - row0);
     // ---- stage (coalesced, lanes along k): quantise to int16 codes, split into hi / lo bytes stored as f16.
-    // Four rows are loaded before any of them is converted so that each lane keeps 4 * K/32 loads in flight.
-    for (int rb = warp * 4; rb < kTcRows; rb += (kTcThreads / 32) * 4) {
-      float raw[4][kTcKI];
+    // Several rows are loaded before any of them is converted so that every lane keeps many loads in flight.
+    if constexpr (VEC4) {
+      // 16-byte aligned rows: each lane owns 4 consecutive input columns (one LDG.128, two 8-byte operand stores)
+      for (int rb = warp * 4; rb < kTcRows; rb += (kTcThreads / 32) * 4) {
+        float4 raw[4][2];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float* xr = p.X + (size_t)(row0 + rb + q) * p.x_stride;
+        for (int q = 0; q < 4; ++q) {
+          const float* xr = p.X + (size_t)(row0 + rb + q) * p.x_stride;
 #pragma unroll
-        for (int i = 0; i < kTcKI; ++i) {
-          const int k = lane + 32 * i;
-          raw[q][i] = (k < K && rb + q < rv) ? xr[k] : 0.f;
-        }
-      }
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int r = rb + q;
-        int part = 0;
-#pragma unroll
-        for (int i = 0; i < kTcKI; ++i) {
-          const int k = lane + 32 * i;
-          if (k < K) {
-            int c = 0;
-            if (r < rv) {
-              float v = raw[q][i];
-              if (p.in_sub) v = (v - sub[i]) * mul[i] + add[i];
-              c = quant_code(v, p.in_inv, p.in_qmin, p.in_qmax);
-            }
-            const size_t o = (size_t)(k >> 3) * lbo + (size_t)(k & 7) * 2 + (size_t)r * 16;
-            *reinterpret_cast<__half*>(Ah + o) = __int2half_rn(c >> 8);
-            *reinterpret_cast<__half*>(Al + o) = __int2half_rn(c & 255);
-            part += c * wn[i];
+          for (int i = 0; i < 2; ++i) {
+            const int k = 4 * lane + 128 * i;
+            raw[q][i] = (k < K && rb + q < rv) ? *reinterpret_cast<const float4*>(xr + k) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
-        if (p.w_extra_n) {
-          part = __reduce_add_sync(0xffffffffu, part);
-          if (lane == 0) extra_n[r] = part;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int r = rb + q;
+          int part = 0;
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const int k = 4 * lane + 128 * i;
+            if (k < K) {
+              const float xv[4] = {raw[q][i].x, raw[q][i].y, raw[q][i].z, raw[q][i].w};
+              int c[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float v = xv[e];
+                if (p.in_sub) v = (v - sub4[i][e]) * mul4[i][e] + add4[i][e];
+                c[e] = r < rv ? quant_code(v, p.in_inv, p.in_qmin, p.in_qmax) : 0;
+                part += c[e] * wn4[i][e];
+              }
+              const size_t o = (size_t)(k >> 3) * lbo + (size_t)(k & 7) * 2 + (size_t)r * 16;
+              *reinterpret_cast<uint2*>(Ah + o) = make_uint2(pack_h2(c[0] >> 8, c[1] >> 8), pack_h2(c[2] >> 8, c[3] >> 8));
+              *reinterpret_cast<uint2*>(Al + o) = make_uint2(pack_h2(c[0] & 255, c[1] & 255), pack_h2(c[2] & 255, c[3] & 255));
+            }
+          }
+          if (p.w_extra_n) {
+            part = __reduce_add_sync(0xffffffffu, part);
+            if (lane == 0) extra_n[r] = part;
+          }
+        }
+      }
+    } else {
+      for (int rb = warp * 4; rb < kTcRows; rb += (kTcThreads / 32) * 4) {
+        float raw[4][kTcKI];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float* xr = p.X + (size_t)(row0 + rb + q) * p.x_stride;
+#pragma unroll
+          for (int i = 0; i < kTcKI; ++i) {
+            const int k = lane + 32 * i;
+            raw[q][i] = (k < K && rb + q < rv) ? xr[k] : 0.f;
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int r = rb + q;
+          int part = 0;
+#pragma unroll
+          for (int i = 0; i < kTcKI; ++i) {
+            const int k = lane + 32 * i;
+            if (k < K) {
+              int c = 0;
+              if (r < rv) {
+                float v = raw[q][i];
+                if (p.in_sub) v = (v - sub[i]) * mul[i] + add[i];
+                c = quant_code(v, p.in_inv, p.in_qmin, p.in_qmax);
+              }
+              const size_t o = (size_t)(k >> 3) * lbo + (size_t)(k & 7) * 2 + (size_t)r * 16;
+              *reinterpret_cast<__half*>(Ah + o) = __int2half_rn(c >> 8);
+              *reinterpret_cast<__half*>(Al + o) = __int2half_rn(c & 255);
+              part += c * wn[i];
+            }
+          }
+          if (p.w_extra_n) {
+            part = __reduce_add_sync(0xffffffffu, part);
+            if (lane == 0) extra_n[r] = part;
+          }
         }
       }
     }
@@ -274,38 +333,48 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_glu_kernel(TcGluParams p) {
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const long long row0 = tile * kTcRows;
     const int rv = (int)min((long long)kTcRows, p.rows - row0);
-    // ---- stage: xs -> two bf16 planes (value = hi + lo to 16 mantissa bits); block input -> shared (coalesced)
+    // ---- stage: block input -> shared with asynchronous 4-byte copies (in flight during the conversion below);
+    //      xs -> two bf16 planes (value = hi + lo to 16 mantissa bits), coalesced, four rows of loads in flight
+    for (int r = warp; r < kTcRows; r += kTcThreads / 32) {
+      const float* xr = p.X + (size_t)(row0 + r) * H;
+      for (int n = lane; n < H; n += 32) {
+        if (r < rv) cp_async4(xT + (size_t)r * ld + n, xr + n);
+        else xT[(size_t)r * ld + n] = 0.f;
+      }
+    }
+    // xs rows are 16-byte aligned (K1 = 2P floats): each lane owns 4 consecutive columns = 2 complex states
     for (int rb = warp * 4; rb < kTcRows; rb += (kTcThreads / 32) * 4) {
-      float raw[4][kTcKI];
+      float4 raw[4][2];
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const float* xr = p.XS + (size_t)(row0 + rb + q) * K1;
 #pragma unroll
-        for (int i = 0; i < kTcKI; ++i) {
-          const int k = lane + 32 * i;
-          raw[q][i] = (k < K1 && rb + q < rv) ? xr[k] : 0.f;
+        for (int i = 0; i < 2; ++i) {
+          const int k = 4 * lane + 128 * i;
+          raw[q][i] = (k < K1 && rb + q < rv) ? *reinterpret_cast<const float4*>(xr + k) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
 #pragma unroll
-        for (int i = 0; i < kTcKI; ++i) {
-          const int k = lane + 32 * i;
+        for (int i = 0; i < 2; ++i) {
+          const int k = 4 * lane + 128 * i;
           if (k < K1) {
-            const float v = (k & 1) ? raw[q][i] * p.xs_odd_mul : raw[q][i];
-            const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-            const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+            const float v[4] = {raw[q][i].x, raw[q][i].y * p.xs_odd_mul, raw[q][i].z, raw[q][i].w * p.xs_odd_mul};
+            __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              hi[e] = __float2bfloat16_rn(v[e]);
+              lo[e] = __float2bfloat16_rn(v[e] - __bfloat162float(hi[e]));
+            }
             const size_t o = (size_t)(k >> 3) * lbo + (size_t)(k & 7) * 2 + (size_t)(rb + q) * 16;
-            *reinterpret_cast<__nv_bfloat16*>(A1h + o) = hi;
-            *reinterpret_cast<__nv_bfloat16*>(A1l + o) = lo;
+            *reinterpret_cast<uint2*>(A1h + o) = *reinterpret_cast<const uint2*>(hi);
+            *reinterpret_cast<uint2*>(A1l + o) = *reinterpret_cast<const uint2*>(lo);
           }
         }
       }
     }
-    for (int r = warp; r < kTcRows; r += kTcThreads / 32) {
-      const float* xr = p.X + (size_t)(row0 + r) * H;
-      for (int n = lane; n < H; n += 32) xT[(size_t)r * ld + n] = r < rv ? xr[n] : 0.f;
-    }
+    cp_async_wait_all();  // block-input tile (issued below, before the conversion loop of this tile)
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -392,7 +461,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_glu_kernel(TcGluParams p) {
         const int acc = __float2int_rn(__uint_as_float(vh[j])) * 256 + __float2int_rn(__uint_as_float(vl[j]));
         float o = __int2float_rn(acc) * p.o_col_scale + ob[j];
         o = fq_from(o, p.oo_s, p.oo_inv, p.qn_min, p.qn_max);
-        float sg = 1.0f / (1.0f + expf(-o));
+        // sigmoid with the SFU exponential and reciprocal: |error| ~ 2 ulp, far below the 2^-15 grid of FQ16 that follows
+        float sg = __frcp_rn(1.0f + __expf(-o));
         sg = fq_from(sg, p.gr_s, p.gr_inv, p.qn_min, p.qn_max);
         const float l = fq_from(x1[j], p.gl_s, p.gl_inv, p.qn_min, p.qn_max);
         const float out = l * sg + xs_[j];
@@ -513,13 +583,15 @@ int tc_linear_launch(const TcLinearDev& d, const float* X, float* Y, long long r
   // TMEM has 512 columns per SM: never let more CTAs become resident than can allocate their accumulators
   const int tmem_ctas = (int)(512 / cols);
   smem = std::max(smem, (size_t)(227 * 1024) / (tmem_ctas + 1) + 1024);
-  S5_CUDA(cudaFuncSetAttribute(tc_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  S5_CUDA(cudaFuncSetAttribute(tc_linear_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  const int per_sm = tc_ctas_per_sm(reinterpret_cast<const void*>(tc_linear_kernel), smem, tmem_ctas);
+  const bool vec4 = (d.x_stride & 3) == 0 && aligned16(X) && d.K <= 256;
+  auto kernel = vec4 ? tc_linear_kernel<true> : tc_linear_kernel<false>;
+  S5_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  S5_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  const int per_sm = tc_ctas_per_sm(reinterpret_cast<const void*>(kernel), smem, tmem_ctas);
   const long long ntiles = (rows + kTcRows - 1) / kTcRows;
   const int grid = (int)std::max<long long>(1, std::min<long long>(ntiles, (long long)per_sm * sm_count()));
   ProfScope prof(kclass, st);
-  tc_linear_kernel<<<grid, kTcThreads, smem, st>>>(p, cols, lo_col);
+  kernel<<<grid, kTcThreads, smem, st>>>(p, cols, lo_col);
   S5_LAUNCH_CHECK();
   return S5_OK;
 }
