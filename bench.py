@@ -354,6 +354,20 @@ def main():
         dist.destroy_process_group()
 
 
+def kernel_breakdown(fn, reps=3):
+    """ms per step of every kernel class the library launched while running fn() (CUDA events per launch)."""
+    from sparsernns_b200 import _abi
+
+    lib = _abi.lib()
+    lib.s5b200_profile_begin()
+    for _ in range(reps):
+        fn()
+    ms = (C.c_double * 13)()
+    n = (C.c_longlong * 13)()
+    _abi.check(lib.s5b200_profile_end(ms, n))
+    return {name: round(ms[i] / reps, 4) for i, name in enumerate(_abi.KERNEL_CLASSES) if n[i]}
+
+
 def secondary_flavours(torch, model, params, batch_stats, cal_stats, dims, xs, B, L, dev):
     """Device-timed frames/s of the other two numerics flavours on the same batch (informational)."""
     from sparsernns_b200 import fxputils
@@ -376,12 +390,12 @@ def secondary_flavours(torch, model, params, batch_stats, cal_stats, dims, xs, B
     q = fxputils.create_fxp_qconfig(md, "w8a16", shared_exp=True)
     fx = FxpRegressionModel(md, q, dims.n_layers)
     ms = t(lambda i=0: fx.forward_float(xs[i % len(xs)]))
-    out["fixed_point_w8a16"] = {"frames_per_s": B * L / (ms / 1e3), "ms_per_step": ms}
+    out["fixed_point_w8a16"] = {"frames_per_s": B * L / (ms / 1e3), "ms_per_step": ms, "kernels_ms_per_step": kernel_breakdown(lambda: fx.forward_float(xs[0]))}
     cfg = S5Config(n_layers=dims.n_layers, d_model=dims.d_model, ssm_size=dims.ssm_size, relufication=False,
                    quantization="none", use_sparse=False)
     fm = BoundModel(cfg, {"params": params, "batch_stats": batch_stats})
     ms = t(lambda i=0: fm(xs[i % len(xs)]))
-    out["dense_fp32_gelu"] = {"frames_per_s": B * L / (ms / 1e3), "ms_per_step": ms}
+    out["dense_fp32_gelu"] = {"frames_per_s": B * L / (ms / 1e3), "ms_per_step": ms, "kernels_ms_per_step": kernel_breakdown(lambda: fm(xs[0]))}
     return out
 
 

@@ -636,7 +636,9 @@ extern "C" int s5b200_model_forward_host(const s5_model* mc, const float* x_host
   cudaStream_t user = (cudaStream_t)stream;
   std::lock_guard<std::mutex> lock(m->mu);
   constexpr int kSlots = s5_model::kSlots;
-  const int nchunks = B >= 8 ? 4 : 1;
+  // enough chunks to keep pipeline fill/drain small next to the PCIe time, but at least 2 clips (>= 4096 rows at
+  // NDNS length) per chunk so that the dense-tile kernels stay eligible
+  const int nchunks = std::max(1, std::min(16, B / 2));
   const int cb = (B + nchunks - 1) / nchunks;  // clips per chunk
   const size_t xb = (size_t)cb * L * m->desc.d_input * sizeof(float), yb = (size_t)cb * L * m->desc.d_output * sizeof(float);
   const size_t wsb = ws_layout(m, cb, L).total;

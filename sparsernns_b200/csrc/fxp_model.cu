@@ -110,16 +110,33 @@ __global__ void __launch_bounds__(256) fxp_bn_reduce_kernel(BnReduceParams p) {
   __syncthreads();
   float m0 = 0.f, m1 = 0.f;
   const int e_prev = p.upto == 1 ? pl.e1 : (p.upto == 2 ? pl.e2 : pl.e3);
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += (long long)gridDim.x * blockDim.x) {
-    const int k = (int)(i % p.H);
-    const int v = bn_apply(p.X[i], k, p.c, pl, p.upto);
-    const float f = fx_to_float(v, e_prev);
-    if (p.next == 2) {
-      m0 = fmaxf(m0, fabsf(f * fx_to_float(p.c.inv[k], p.c.e_inv)));
-    } else if (p.next == 3) {
-      m0 = fmaxf(m0, fabsf(f * fx_to_float(p.c.scale[k], p.c.e_scale)));
-    } else {
-      m0 = fmaxf(m0, fabsf(f + fx_to_float(p.c.bias[k], p.c.e_bias)));
+  // to_float scale factors hoisted out of the element loop (powers of two: exact)
+  const float s_prev = exp2f((float)-e_prev);
+  const int* pv = p.next == 2 ? p.c.inv : (p.next == 3 ? p.c.scale : p.c.bias);
+  const float s_par = exp2f((float)-(p.next == 2 ? p.c.e_inv : (p.next == 3 ? p.c.e_scale : p.c.e_bias)));
+  const bool is_mul = p.next != 4;
+  if ((p.H & 3) == 0) {
+    const long long n4 = p.n >> 2;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+      const int4 xv = reinterpret_cast<const int4*>(p.X)[i];
+      const int k = (int)((i << 2) % p.H);
+      const int xs4[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int v = bn_apply(xs4[e], k + e, p.c, pl, p.upto);
+        const float f = __int2float_rn(v) * s_prev;
+        const float g = __int2float_rn(pv[k + e]) * s_par;
+        m0 = fmaxf(m0, fabsf(is_mul ? f * g : f + g));
+        m1 = fmaxf(m1, fabsf(f));
+      }
+    }
+  } else {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += (long long)gridDim.x * blockDim.x) {
+      const int k = (int)(i % p.H);
+      const int v = bn_apply(p.X[i], k, p.c, pl, p.upto);
+      const float f = __int2float_rn(v) * s_prev;
+      const float g = __int2float_rn(pv[k]) * s_par;
+      m0 = fmaxf(m0, fabsf(is_mul ? f * g : f + g));
       m1 = fmaxf(m1, fabsf(f));
     }
   }

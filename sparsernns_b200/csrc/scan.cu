@@ -10,6 +10,8 @@
 //  (2) scan_i32: the integer recurrence of fxpmodel.py:147-208.  It floors every product separately, so it
 //      is not associative and must be sequential in time; one lane per (clip, state), register
 //      prefetch ring over time.
+#include <algorithm>
+
 #include "scan.cuh"
 
 namespace s5 {
@@ -252,16 +254,16 @@ __global__ void __launch_bounds__(128) scan_i32_kernel(ScanI32Params q) {
 
 // Ring variant of the integer recurrence for throughput AND latency: one CTA per clip, one thread per state, the
 // clip's [L][P] stream flows through a ring of kRingStages shared-memory tiles filled by 1-D bulk async copies
-// (TMA engine) kRingStages-2 tiles ahead and drained by bulk stores, so the sequential dependency chain never waits
+// (TMA engine) stages-2 tiles ahead (deep enough to cover DRAM + TMA latency) and drained by bulk stores, so the sequential dependency chain never waits
 // on DRAM: time per clip ~ L x (one IMAD -> shift -> add chain).
-constexpr int kRingStages = 4;
+constexpr int kRingMaxStages = 10;
 constexpr int kRingSteps = 32;
 
-template <bool INTERLEAVED>
-__global__ void __launch_bounds__(256) scan_i32_ring_kernel(ScanI32Params q) {
+template <bool INTERLEAVED, int CP>
+__global__ void __launch_bounds__(256) scan_i32_ring_kernel(ScanI32Params q, int kRingStages) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ __align__(8) uint64_t full[kRingStages];
-  const int P = q.P, L = q.L;
+  __shared__ __align__(8) uint64_t full[kRingMaxStages];
+  const int P = CP ? CP : q.P, L = q.L;  // compile-time row stride for the usual state sizes: immediate offsets
   const int p = threadIdx.x;
   const long long b = blockIdx.x;
   const size_t tile_elems = (size_t)kRingSteps * P;                 // states per tile
@@ -292,6 +294,8 @@ __global__ void __launch_bounds__(256) scan_i32_ring_kernel(ScanI32Params q) {
     for (int t = 0; t < min(kRingStages - 2, ntiles); ++t) issue_load(t);
   const bool active = p < P;
   const int ar = active ? q.A_re[p] : 0, ai = active ? q.A_im[p] : 0;
+  const int sl_re = max(0, q.ex_re - q.eBu_re), sr_re = max(0, q.eBu_re - q.ex_re);
+  const int sl_im = max(0, q.ex_im - q.eBu_im), sr_im = max(0, q.eBu_im - q.ex_im);
   int xr = 0, xi = 0;
   for (int i = 0; i < ntiles; ++i) {
     const int s = i % kRingStages;
@@ -307,26 +311,56 @@ __global__ void __launch_bounds__(256) scan_i32_ring_kernel(ScanI32Params q) {
     int* tre = reinterpret_cast<int*>(smem_raw + (size_t)s * stage_bytes);
     int* tim = tre + tile_elems;
     if (active) {
-#pragma unroll 4
-      for (int t = 0; t < rows; ++t) {
-        int br, bi;
-        if (INTERLEAVED) {
-          const int2 v = reinterpret_cast<const int2*>(tre)[(size_t)t * P + p];
-          br = v.x; bi = v.y;
-        } else {
-          br = tre[(size_t)t * P + p]; bi = tim[(size_t)t * P + p];
+      // The whole tile column of this state goes through registers: (1) load and exponent-align all kRingSteps
+      // inputs (independent, pipelined), (2) run the dependent chain - per step only 4 IMAD, 4 shifts and the adds -
+      // (3) apply the complex ReLU and store (independent again).  With one warp per scheduler nothing else hides
+      // ALU latency, so everything that is not on the recurrence chain is kept out of the chain loop.
+      int vr[kRingSteps], vi[kRingSteps];
+      const int2* t2 = reinterpret_cast<const int2*>(tre) + p;
+      const int* tr1 = tre + p;
+      const int* ti1 = tim + p;
+#pragma unroll
+      for (int t = 0; t < kRingSteps; ++t) {
+        int br = 0, bi = 0;
+        if (t < rows) {
+          if (INTERLEAVED) {
+            const int2 v = t2[t * P];
+            br = v.x; bi = v.y;
+          } else {
+            br = tr1[t * P]; bi = ti1[t * P];
+          }
         }
-        const int cr = shift_align(br, q.eBu_re, q.ex_re);
-        const int ci = shift_align(bi, q.eBu_im, q.ex_im);
-        const int nr = (int)((unsigned)(mulw(ar, xr) >> q.eA_re) - (unsigned)(mulw(ai, xi) >> q.eA_re) + (unsigned)cr);
-        const int ni = (int)((unsigned)(mulw(ar, xi) >> q.eA_im) + (unsigned)(mulw(ai, xr) >> q.eA_im) + (unsigned)ci);
+        // fxpmodel.py:158-167 without a branch: one of the two shift counts is zero
+        vr[t] = (int)((unsigned)br << sl_re) >> sr_re;
+        vi[t] = (int)((unsigned)bi << sl_im) >> sr_im;
+      }
+#pragma unroll
+      for (int t = 0; t < kRingSteps; ++t) {
+        // fxpmodel.py:155-156: each product is floored on its own; products and sums wrap in int32
+        const int nr = (int)((unsigned)(mulw(ar, xr) >> q.eA_re) - (unsigned)(mulw(ai, xi) >> q.eA_re) + (unsigned)vr[t]);
+        const int ni = (int)((unsigned)(mulw(ar, xi) >> q.eA_im) + (unsigned)(mulw(ai, xr) >> q.eA_im) + (unsigned)vi[t]);
         xr = nr; xi = ni;
-        int orr = xr, oi = xi;
-        if (q.relu) fxp_relu_complex(orr, oi);
-        if (INTERLEAVED) {
-          reinterpret_cast<int2*>(tre)[(size_t)t * P + p] = make_int2(orr, oi);
-        } else {
-          tre[(size_t)t * P + p] = orr; tim[(size_t)t * P + p] = oi;
+        vr[t] = nr; vi[t] = ni;
+      }
+      int2* o2 = reinterpret_cast<int2*>(tre) + p;
+      int* or1 = tre + p;
+      int* oi1 = tim + p;
+#pragma unroll
+      for (int t = 0; t < kRingSteps; ++t) {
+        if (t < rows) {
+          int orr = vr[t], oi = vi[t];
+          if (q.relu) {
+            // |v| < 2^24 survives the float32 round trip of fxp_relu unchanged: integer compare, no conversions
+            const bool small = ((unsigned)(orr + (1 << 24)) < (1u << 25)) && ((unsigned)(oi + (1 << 24)) < (1u << 25));
+            if (small) {
+              const bool keep = orr > 0 || (orr == 0 && oi > 0);
+              orr = keep ? orr : 0; oi = keep ? oi : 0;
+            } else {
+              fxp_relu_complex(orr, oi);
+            }
+          }
+          if (INTERLEAVED) o2[t * P] = make_int2(orr, oi);
+          else { or1[t * P] = orr; oi1[t * P] = oi; }
         }
       }
     }
@@ -347,21 +381,189 @@ __global__ void __launch_bounds__(256) scan_i32_ring_kernel(ScanI32Params q) {
   if (p == 0) bulk_wait0();
 }
 
+// Warp-specialised form of the ring kernel (P a multiple of 32).  The recurrence is one dependent chain per
+// state, and with one warp per scheduler nothing hides ALU latency, so every instruction that is not on the chain
+// is moved to other warps.  Per 32 states there are three warps working on different tiles of the ring:
+//   pre   : wait for the TMA load, align Bu to the state exponent in place          (fxpmodel.py:158-167)
+//   chain : column -> registers, the kRingSteps dependent steps, raw states back     (fxpmodel.py:155-156, :169)
+//   post  : complex ReLU in place (fxpmodel.py:30-45), bulk store, refill of the ring
+// handing tiles over through per-(stage, column-half) mbarriers.
+constexpr int kWsMaxHalves = 8;
+
+template <bool INTERLEAVED>
+__global__ void __launch_bounds__(384) scan_i32_ws_kernel(ScanI32Params q, int S) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t full[kRingMaxStages];
+  __shared__ __align__(8) uint64_t aligned[kRingMaxStages][kWsMaxHalves];
+  __shared__ __align__(8) uint64_t scanned[kRingMaxStages][kWsMaxHalves];
+  const int P = q.P, L = q.L;
+  const int nh = P >> 5;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int role = warp / nh, h = warp % nh;   // 0 pre, 1 chain, 2 post
+  const int p = h * 32 + lane;
+  const long long b = blockIdx.x;
+  const size_t tile_elems = (size_t)kRingSteps * P;
+  const size_t stage_bytes = tile_elems * 8;
+  const int ntiles = (L + kRingSteps - 1) / kRingSteps;
+  const size_t clip_off = (size_t)b * L * P;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&full[s], 1);
+      for (int j = 0; j < nh; ++j) { mbar_init(&aligned[s][j], 1); mbar_init(&scanned[s][j], 1); }
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+  auto issue_load = [&](int t) {
+    const int s = t % S;
+    const int rows = min(kRingSteps, L - t * kRingSteps);
+    const uint32_t bytes = (uint32_t)rows * P * 4u;
+    unsigned char* dst = smem_raw + (size_t)s * stage_bytes;
+    const size_t off = clip_off + (size_t)t * tile_elems;
+    mbar_expect_tx(&full[s], 2 * bytes);
+    if (INTERLEAVED) {
+      bulk_g2s(dst, reinterpret_cast<const int2*>(q.Bu_re) + off, 2 * bytes, &full[s]);
+    } else {
+      bulk_g2s(dst, q.Bu_re + off, bytes, &full[s]);
+      bulk_g2s(dst + tile_elems * 4, q.Bu_im + off, bytes, &full[s]);
+    }
+  };
+  const bool leader = (role == 2 && h == 0 && lane == 0);
+  if (leader)
+    for (int t = 0; t < min(S, ntiles); ++t) issue_load(t);
+  const int sl_re = max(0, q.ex_re - q.eBu_re), sr_re = max(0, q.eBu_re - q.ex_re);
+  const int sl_im = max(0, q.ex_im - q.eBu_im), sr_im = max(0, q.eBu_im - q.ex_im);
+  const int ar = q.A_re[p], ai = q.A_im[p];
+  int xr = 0, xi = 0;
+  for (int i = 0; i < ntiles; ++i) {
+    const int s = i % S;
+    const uint32_t par = (uint32_t)(i / S) & 1u;
+    const int rows = min(kRingSteps, L - i * kRingSteps);
+    int* tre = reinterpret_cast<int*>(smem_raw + (size_t)s * stage_bytes);
+    int* tim = tre + tile_elems;
+    int2* c2 = reinterpret_cast<int2*>(tre) + p;
+    if (role == 0) {
+      mbar_wait(&full[s], par);
+#pragma unroll 8
+      for (int t = 0; t < rows; ++t) {
+        if (INTERLEAVED) {
+          int2 v = c2[(size_t)t * P];
+          v.x = (int)((unsigned)v.x << sl_re) >> sr_re;
+          v.y = (int)((unsigned)v.y << sl_im) >> sr_im;
+          c2[(size_t)t * P] = v;
+        } else {
+          tre[(size_t)t * P + p] = (int)((unsigned)tre[(size_t)t * P + p] << sl_re) >> sr_re;
+          tim[(size_t)t * P + p] = (int)((unsigned)tim[(size_t)t * P + p] << sl_im) >> sr_im;
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&aligned[s][h]);
+    } else if (role == 1) {
+      mbar_wait(&aligned[s][h], par);
+      int vr[kRingSteps], vi[kRingSteps];
+#pragma unroll
+      for (int t = 0; t < kRingSteps; ++t) {
+        vr[t] = 0; vi[t] = 0;
+        if (t < rows) {
+          if (INTERLEAVED) { const int2 v = c2[(size_t)t * P]; vr[t] = v.x; vi[t] = v.y; }
+          else { vr[t] = tre[(size_t)t * P + p]; vi[t] = tim[(size_t)t * P + p]; }
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < kRingSteps; ++t) {
+        const int nr = (int)((unsigned)(mulw(ar, xr) >> q.eA_re) - (unsigned)(mulw(ai, xi) >> q.eA_re) + (unsigned)vr[t]);
+        const int ni = (int)((unsigned)(mulw(ar, xi) >> q.eA_im) + (unsigned)(mulw(ai, xr) >> q.eA_im) + (unsigned)vi[t]);
+        xr = nr; xi = ni;
+        vr[t] = nr; vi[t] = ni;
+      }
+#pragma unroll
+      for (int t = 0; t < kRingSteps; ++t) {
+        if (t < rows) {
+          if (INTERLEAVED) c2[(size_t)t * P] = make_int2(vr[t], vi[t]);
+          else { tre[(size_t)t * P + p] = vr[t]; tim[(size_t)t * P + p] = vi[t]; }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&scanned[s][h]);
+    } else {
+      mbar_wait(&scanned[s][h], par);
+      if (q.relu) {
+#pragma unroll 8
+        for (int t = 0; t < rows; ++t) {
+          int orr, oi;
+          if (INTERLEAVED) { const int2 v = c2[(size_t)t * P]; orr = v.x; oi = v.y; }
+          else { orr = tre[(size_t)t * P + p]; oi = tim[(size_t)t * P + p]; }
+          const bool small = ((unsigned)(orr + (1 << 24)) < (1u << 25)) && ((unsigned)(oi + (1 << 24)) < (1u << 25));
+          if (small) {
+            const bool keep = orr > 0 || (orr == 0 && oi > 0);
+            orr = keep ? orr : 0; oi = keep ? oi : 0;
+          } else {
+            fxp_relu_complex(orr, oi);
+          }
+          if (INTERLEAVED) c2[(size_t)t * P] = make_int2(orr, oi);
+          else { tre[(size_t)t * P + p] = orr; tim[(size_t)t * P + p] = oi; }
+        }
+      }
+      fence_proxy_async_smem();
+      asm volatile("bar.sync 1, %0;" ::"r"(nh * 32) : "memory");   // all post warps of this tile
+      if (leader) {
+        const uint32_t bytes = (uint32_t)rows * P * 4u;
+        const size_t off = clip_off + (size_t)i * tile_elems;
+        if (INTERLEAVED) {
+          bulk_s2g(reinterpret_cast<int2*>(q.xs_re) + off, tre, 2 * bytes);
+        } else {
+          bulk_s2g(q.xs_re + off, tre, bytes);
+          bulk_s2g(q.xs_im + off, tim, bytes);
+        }
+        bulk_commit();
+        // the store of tile i-1 has released its stage: refill it with tile i-1+S
+        if (i >= 1 && i - 1 + S < ntiles) {
+          bulk_wait_read1();
+          issue_load(i - 1 + S);
+        }
+      }
+    }
+  }
+  if (leader) bulk_wait0();
+}
+
 int launch_scan_i32(const ScanI32Params& q, bool interleaved, cudaStream_t st) {
   const long long B = q.lanes / q.P;
   const bool ptr_ok = aligned16(q.Bu_re) && aligned16(q.xs_re) && (interleaved || (aligned16(q.Bu_im) && aligned16(q.xs_im)));
   const bool ring_ok = ptr_ok && q.P <= 256 && (interleaved ? (q.P % 2 == 0) : (q.P % 4 == 0)) && B <= 0x7fffffffLL;
   ProfScope prof(S5_K_SCAN_I32, st);
   if (ring_ok) {
-    const size_t smem = (size_t)kRingStages * kRingSteps * q.P * 8;
-    const int threads = (q.P + 31) & ~31;
-    if (interleaved) {
-      S5_CUDA(cudaFuncSetAttribute(scan_i32_ring_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      scan_i32_ring_kernel<true><<<(unsigned)B, threads, smem, st>>>(q);
-    } else {
-      S5_CUDA(cudaFuncSetAttribute(scan_i32_ring_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      scan_i32_ring_kernel<false><<<(unsigned)B, threads, smem, st>>>(q);
+    // ring depth: ~8 tiles (6 in flight = 192 steps of look-ahead, about 2 us of dependent-chain time) when there are
+    // few clips; shallower when many clips share an SM so that several CTAs stay resident
+    const size_t tile = (size_t)kRingSteps * q.P * 8;
+    int stages = B >= 2LL * sm_count() ? 4 : 8;
+    while (stages > 3 && stages * tile > 200 * 1024) --stages;
+    stages = std::min(stages, kRingMaxStages);
+    const size_t smem = (size_t)stages * tile;
+    if (q.P % 32 == 0 && q.P / 32 <= kWsMaxHalves && 3 * q.P <= 384) {
+      auto kernel = interleaved ? scan_i32_ws_kernel<true> : scan_i32_ws_kernel<false>;
+      S5_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      kernel<<<(unsigned)B, 3 * q.P, smem, st>>>(q, stages);
+      S5_LAUNCH_CHECK();
+      return S5_OK;
     }
+    const int threads = (q.P + 31) & ~31;
+    auto go = [&](auto kernel) -> int {
+      S5_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      kernel<<<(unsigned)B, threads, smem, st>>>(q, stages);
+      return S5_OK;
+    };
+    int rc;
+    if (interleaved) {
+      if (q.P == 64) rc = go(scan_i32_ring_kernel<true, 64>);
+      else if (q.P == 128) rc = go(scan_i32_ring_kernel<true, 128>);
+      else rc = go(scan_i32_ring_kernel<true, 0>);
+    } else {
+      if (q.P == 64) rc = go(scan_i32_ring_kernel<false, 64>);
+      else if (q.P == 128) rc = go(scan_i32_ring_kernel<false, 128>);
+      else rc = go(scan_i32_ring_kernel<false, 0>);
+    }
+    if (rc) return rc;
     S5_LAUNCH_CHECK();
     return S5_OK;
   }
