@@ -636,9 +636,10 @@ extern "C" int s5b200_model_forward_host(const s5_model* mc, const float* x_host
   cudaStream_t user = (cudaStream_t)stream;
   std::lock_guard<std::mutex> lock(m->mu);
   constexpr int kSlots = s5_model::kSlots;
-  // enough chunks to keep pipeline fill/drain small next to the PCIe time, but at least 2 clips (>= 4096 rows at
-  // NDNS length) per chunk so that the dense-tile kernels stay eligible
-  const int nchunks = std::max(1, std::min(16, B / 2));
+  // enough chunks to keep pipeline fill/drain small next to the PCIe time, few enough that every chunk still
+  // fills the GPU (measured on B200: 4 chunks 31 M frames/s, 16 chunks 21 M; S5B200_E2E_CHUNKS overrides)
+  int nchunks = std::max(1, std::min(8, B / 4));
+  if (const char* e = getenv("S5B200_E2E_CHUNKS")) nchunks = std::max(1, std::min(B, atoi(e)));
   const int cb = (B + nchunks - 1) / nchunks;  // clips per chunk
   const size_t xb = (size_t)cb * L * m->desc.d_input * sizeof(float), yb = (size_t)cb * L * m->desc.d_output * sizeof(float);
   const size_t wsb = ws_layout(m, cb, L).total;

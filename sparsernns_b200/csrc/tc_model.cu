@@ -80,7 +80,7 @@ __device__ __forceinline__ void tc_issue(uint32_t d_tmem, const void* A, const v
 }
 
 template <bool VEC4>
-__global__ void __launch_bounds__(kTcThreads, 2) tc_linear_kernel(TcLinParams p, uint32_t tmem_cols, uint32_t lo_col) {
+__global__ void __launch_bounds__(512, 1) tc_linear_kernel(TcLinParams p, uint32_t tmem_cols, uint32_t lo_col) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int K = p.K, N = p.N;
   const size_t a_bytes = tc_tile_bytes(kTcRows, K);
@@ -92,6 +92,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) tc_linear_kernel(TcLinParams p,
   __shared__ uint32_t tmem_slot;
   __shared__ int extra_n[kTcRows];                            // integer dot of the extra output column
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int NW = blockDim.x >> 5;                             // 8 or 16 warps
   if (warp == 0) tc_alloc(&tmem_slot, tmem_cols);
   if (tid == 0) {
     mbar_init(&bar, 1);
@@ -102,7 +103,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) tc_linear_kernel(TcLinParams p,
   const int NC = N > 128 ? 128 : N;                           // columns per epilogue pass
   const int ld_out = NC + 4;
   const int erow = (warp & 3) * 32 + lane;                    // epilogue: TMEM lane = row
-  const int cw = NC >> 1;                                     // columns per warp half within a pass
+  const int cw = NC / (NW >> 2);                              // columns per warp group within a pass
   // per-lane constants of the staging loop.  Scalar form: lane owns columns k = lane + 32 i; vector form (rows
   // 16-byte aligned): lane owns columns 4 lane + 128 i .. + 3.
   constexpr bool vec4 = VEC4;
@@ -139,7 +140,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) tc_linear_kernel(TcLinParams p,
     // Several rows are loaded before any of them is converted so that every lane keeps many loads in flight.
     if constexpr (VEC4) {
       // 16-byte aligned rows: each lane owns 4 consecutive input columns (one LDG.128, two 8-byte operand stores)
-      for (int rb = warp * 4; rb < kTcRows; rb += (kTcThreads / 32) * 4) {
+      for (int rb = warp * 4; rb < kTcRows; rb += NW * 4) {
         float4 raw[4][2];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -179,7 +180,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) tc_linear_kernel(TcLinParams p,
         }
       }
     } else {
-      for (int rb = warp * 4; rb < kTcRows; rb += (kTcThreads / 32) * 4) {
+      for (int rb = warp * 4; rb < kTcRows; rb += NW * 4) {
         float raw[4][kTcKI];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -237,20 +238,20 @@ __global__ void __launch_bounds__(kTcThreads, 2) tc_linear_kernel(TcLinParams p,
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     for (int pass0 = 0; pass0 < N; pass0 += NC) {
       const int cbeg = pass0 + (warp >> 2) * cw;
-      for (int c0 = cbeg; c0 < cbeg + cw; c0 += 16) {
-        uint32_t vh[16], vl[16];
-        tc_ld16(taddr + lane_base + c0, vh);
-        tc_ld16(taddr + lane_base + lo_col + c0, vl);
+      for (int c0 = cbeg; c0 < cbeg + cw; c0 += 8) {
+        uint32_t vh[8], vl[8];
+        tc_ld8(taddr + lane_base + c0, vh);
+        tc_ld8(taddr + lane_base + lo_col + c0, vl);
         tc_wait_ld();
-        float out[16], cs[16], bs[16], wk[16];
+        float out[8], cs[8], bs[8], wk[8];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < 2; ++q) {
           *reinterpret_cast<float4*>(cs + 4 * q) = *reinterpret_cast<const float4*>(p.col_scale + c0 + 4 * q);
           *reinterpret_cast<float4*>(bs + 4 * q) = p.bias ? *reinterpret_cast<const float4*>(p.bias + c0 + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
           *reinterpret_cast<float4*>(wk + 4 * q) = p.w_extra_k ? *reinterpret_cast<const float4*>(p.w_extra_k + c0 + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
+        for (int j = 0; j < 8; ++j) {
           int acc = __float2int_rn(__uint_as_float(vh[j])) * 256 + __float2int_rn(__uint_as_float(vl[j]));
           acc += code_k * __float2int_rn(wk[j]);
           float v = __int2float_rn(acc) * cs[j] + bs[j];
@@ -259,10 +260,10 @@ __global__ void __launch_bounds__(kTcThreads, 2) tc_linear_kernel(TcLinParams p,
         }
         float* dst = outT + (size_t)erow * ld_out + (c0 - pass0);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(dst + 4 * q) = make_float4(out[4 * q], out[4 * q + 1], out[4 * q + 2], out[4 * q + 3]);
+        for (int q = 0; q < 2; ++q) *reinterpret_cast<float4*>(dst + 4 * q) = make_float4(out[4 * q], out[4 * q + 1], out[4 * q + 2], out[4 * q + 3]);
       }
       __syncthreads();
-      for (int r = warp; r < rv; r += kTcThreads / 32) {
+      for (int r = warp; r < rv; r += NW) {
         float* yr = p.Y + (size_t)(row0 + r) * p.y_stride + pass0;
         const float* src = outT + (size_t)r * ld_out;
         for (int n = lane; n < NC; n += 32) yr[n] = src[n];
@@ -301,7 +302,9 @@ struct TcGluParams {
   int relu_out;
 };
 
-__global__ void __launch_bounds__(kTcThreads, 1) tc_glu_kernel(TcGluParams p) {
+constexpr int kGluThreads = 512;   // 16 warps: 4 TMEM lane quadrants x 4 column groups
+
+__global__ void __launch_bounds__(kGluThreads, 1) tc_glu_kernel(TcGluParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int H = p.H, K1 = p.K1;
   const int ld = H + 4;
@@ -315,6 +318,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_glu_kernel(TcGluParams p) {
   float* oT = xT + (size_t)kTcRows * ld;                                    // [128][H+4] x1, then the block output
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t tmem_slot;
+  constexpr int NW = kGluThreads / 32;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (warp == 0) tc_alloc(&tmem_slot, 256);
   if (tid == 0) {
@@ -324,8 +328,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_glu_kernel(TcGluParams p) {
   tc_load_weights(Wc, reinterpret_cast<const __half*>(p.Wc), H, K1);
   tc_load_weights(Wo, p.Wo, H, H);
   const uint32_t lbo = tc_lbo(kTcRows);
-  const int erow = (warp & 3) * 32 + lane;
-  const int cw = H >> 1;
+  const int erow = (warp & 3) * 32 + lane;      // TMEM lane = tile row
+  const int cw = H >> 2;                        // columns per warp group (H % 32 == 0)
   const int cbeg = (warp >> 2) * cw;
   const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
   uint32_t phase = 0;
@@ -334,19 +338,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_glu_kernel(TcGluParams p) {
     const long long row0 = tile * kTcRows;
     const int rv = (int)min((long long)kTcRows, p.rows - row0);
     // ---- stage: block input -> shared with asynchronous 4-byte copies (in flight during the conversion below);
-    //      xs -> two bf16 planes (value = hi + lo to 16 mantissa bits), coalesced, four rows of loads in flight
-    for (int r = warp; r < kTcRows; r += kTcThreads / 32) {
+    //      xs -> two bf16 planes (value = hi + lo to 16 mantissa bits): each lane owns 4 consecutive columns
+    //      (2 complex states) of 8 rows, all 8 x K1/128 loads issued before the first conversion
+    for (int r = warp; r < kTcRows; r += NW) {
       const float* xr = p.X + (size_t)(row0 + r) * H;
       for (int n = lane; n < H; n += 32) {
         if (r < rv) cp_async4(xT + (size_t)r * ld + n, xr + n);
         else xT[(size_t)r * ld + n] = 0.f;
       }
     }
-    // xs rows are 16-byte aligned (K1 = 2P floats): each lane owns 4 consecutive columns = 2 complex states
-    for (int rb = warp * 4; rb < kTcRows; rb += (kTcThreads / 32) * 4) {
-      float4 raw[4][2];
+    {
+      const int rb = warp * 8;                  // 16 warps x 8 rows = 128
+      float4 raw[8][2];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
+      for (int q = 0; q < 8; ++q) {
         const float* xr = p.XS + (size_t)(row0 + rb + q) * K1;
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
@@ -355,7 +360,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_glu_kernel(TcGluParams p) {
         }
       }
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
+      for (int q = 0; q < 8; ++q) {
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
           const int k = 4 * lane + 128 * i;
@@ -374,7 +379,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_glu_kernel(TcGluParams p) {
         }
       }
     }
-    cp_async_wait_all();  // block-input tile (issued below, before the conversion loop of this tile)
+    cp_async_wait_all();
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -389,14 +394,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_glu_kernel(TcGluParams p) {
     phase ^= 1;
     tc_fence_after();
     // ---- epilogue 1: y = conj * Re(C x) + D u -> FQ -> x1 = ReLU(y); x1 codes -> operand tiles of the out2 product
-    for (int c0 = cbeg; c0 < cbeg + cw; c0 += 16) {
-      uint32_t v[16];
-      tc_ld16(taddr + lane_base + c0, v);
+    for (int c0 = cbeg; c0 < cbeg + cw; c0 += 8) {
+      uint32_t v[8];
+      tc_ld8(taddr + lane_base + c0, v);
       tc_wait_ld();
-      int code[16];
-      float x1[16], xu[16], bsub[16], bmul[16], badd[16], dd[16];
+      int code[8];
+      float x1[8], xu[8], bsub[8], bmul[8], badd[8], dd[8];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
+      for (int q = 0; q < 2; ++q) {
         *reinterpret_cast<float4*>(xu + 4 * q) = *reinterpret_cast<const float4*>(xT + (size_t)erow * ld + c0 + 4 * q);
         *reinterpret_cast<float4*>(dd + 4 * q) = *reinterpret_cast<const float4*>(p.D + c0 + 4 * q);
         if (p.bn_sub) {
@@ -406,7 +411,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_glu_kernel(TcGluParams p) {
         }
       }
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
+      for (int j = 0; j < 8; ++j) {
         float u = xu[j];
         if (p.bn_sub) u = (u - bsub[j]) * bmul[j] + badd[j];
         u = fq_from(u, p.ut_s, p.ut_inv, p.qs_min, p.qs_max);
@@ -416,20 +421,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_glu_kernel(TcGluParams p) {
         code[j] = quant_code(x1[j], p.oa_inv, p.qn_min, p.qn_max);
       }
 #pragma unroll
-      for (int q = 0; q < 4; ++q)
+      for (int q = 0; q < 2; ++q)
         *reinterpret_cast<float4*>(oT + (size_t)erow * ld + c0 + 4 * q) = make_float4(x1[4 * q], x1[4 * q + 1], x1[4 * q + 2], x1[4 * q + 3]);
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        uint4 hi, lo;
-        const int* c = code + 8 * h;
-        hi.x = pack_h2(c[0] >> 8, c[1] >> 8); hi.y = pack_h2(c[2] >> 8, c[3] >> 8);
-        hi.z = pack_h2(c[4] >> 8, c[5] >> 8); hi.w = pack_h2(c[6] >> 8, c[7] >> 8);
-        lo.x = pack_h2(c[0] & 255, c[1] & 255); lo.y = pack_h2(c[2] & 255, c[3] & 255);
-        lo.z = pack_h2(c[4] & 255, c[5] & 255); lo.w = pack_h2(c[6] & 255, c[7] & 255);
-        const size_t o = (size_t)((c0 >> 3) + h) * lbo + (size_t)erow * 16;
-        *reinterpret_cast<uint4*>(A2h + o) = hi;
-        *reinterpret_cast<uint4*>(A2l + o) = lo;
-      }
+      uint4 hi, lo;
+      hi.x = pack_h2(code[0] >> 8, code[1] >> 8); hi.y = pack_h2(code[2] >> 8, code[3] >> 8);
+      hi.z = pack_h2(code[4] >> 8, code[5] >> 8); hi.w = pack_h2(code[6] >> 8, code[7] >> 8);
+      lo.x = pack_h2(code[0] & 255, code[1] & 255); lo.y = pack_h2(code[2] & 255, code[3] & 255);
+      lo.z = pack_h2(code[4] & 255, code[5] & 255); lo.w = pack_h2(code[6] & 255, code[7] & 255);
+      const size_t o = (size_t)(c0 >> 3) * lbo + (size_t)erow * 16;
+      *reinterpret_cast<uint4*>(A2h + o) = hi;
+      *reinterpret_cast<uint4*>(A2l + o) = lo;
     }
     fence_proxy_async_smem();
     tc_fence_before();
@@ -444,20 +445,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_glu_kernel(TcGluParams p) {
     phase ^= 1;
     tc_fence_after();
     // ---- epilogue 2: o = out2(x1) -> FQ ; g = FQ(x1) * FQ(sigmoid(o)) ; out = ReLU(g + skip)
-    for (int c0 = cbeg; c0 < cbeg + cw; c0 += 16) {
-      uint32_t vh[16], vl[16];
-      tc_ld16(taddr + lane_base + c0, vh);
-      tc_ld16(taddr + lane_base + 128 + c0, vl);
+    for (int c0 = cbeg; c0 < cbeg + cw; c0 += 8) {
+      uint32_t vh[8], vl[8];
+      tc_ld8(taddr + lane_base + c0, vh);
+      tc_ld8(taddr + lane_base + 128 + c0, vl);
       tc_wait_ld();
-      float xs_[16], x1[16], ob[16], res[16];
+      float xs_[8], x1[8], ob[8], res[8];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
+      for (int q = 0; q < 2; ++q) {
         *reinterpret_cast<float4*>(xs_ + 4 * q) = *reinterpret_cast<const float4*>(xT + (size_t)erow * ld + c0 + 4 * q);
         *reinterpret_cast<float4*>(x1 + 4 * q) = *reinterpret_cast<const float4*>(oT + (size_t)erow * ld + c0 + 4 * q);
         *reinterpret_cast<float4*>(ob + 4 * q) = *reinterpret_cast<const float4*>(p.o_bias + c0 + 4 * q);
       }
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
+      for (int j = 0; j < 8; ++j) {
         const int acc = __float2int_rn(__uint_as_float(vh[j])) * 256 + __float2int_rn(__uint_as_float(vl[j]));
         float o = __int2float_rn(acc) * p.o_col_scale + ob[j];
         o = fq_from(o, p.oo_s, p.oo_inv, p.qn_min, p.qn_max);
@@ -469,12 +470,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_glu_kernel(TcGluParams p) {
         res[j] = p.relu_out ? fmaxf(out, 0.f) : out;
       }
 #pragma unroll
-      for (int q = 0; q < 4; ++q)
+      for (int q = 0; q < 2; ++q)
         *reinterpret_cast<float4*>(oT + (size_t)erow * ld + c0 + 4 * q) = make_float4(res[4 * q], res[4 * q + 1], res[4 * q + 2], res[4 * q + 3]);
     }
     tc_fence_before();
     __syncthreads();
-    for (int r = warp; r < rv; r += kTcThreads / 32) {
+    for (int r = warp; r < rv; r += NW) {
       float* yr = p.OUT + (size_t)(row0 + r) * H;
       for (int n = lane; n < H; n += 32) yr[n] = oT[(size_t)r * ld + n];
     }
@@ -587,11 +588,16 @@ int tc_linear_launch(const TcLinearDev& d, const float* X, float* Y, long long r
   auto kernel = vec4 ? tc_linear_kernel<true> : tc_linear_kernel<false>;
   S5_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   S5_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  const int per_sm = tc_ctas_per_sm(reinterpret_cast<const void*>(kernel), smem, tmem_ctas);
+  int per_sm = tc_ctas_per_sm(reinterpret_cast<const void*>(kernel), smem, tmem_ctas);
+  // 16 warps per SM either way: two 8-warp CTAs when two fit (shared memory, TMEM), else one 16-warp CTA
+  const int NCp = d.N > 128 ? 128 : d.N;
+  const bool wide_ok = (NCp % 32) == 0;   // 4 column groups of whole 8-column chunks
+  const int threads = (per_sm >= 2 || !wide_ok) ? kTcThreads : 512;
+  if (threads == 512) per_sm = 1;
   const long long ntiles = (rows + kTcRows - 1) / kTcRows;
   const int grid = (int)std::max<long long>(1, std::min<long long>(ntiles, (long long)per_sm * sm_count()));
   ProfScope prof(kclass, st);
-  kernel<<<grid, kTcThreads, smem, st>>>(p, cols, lo_col);
+  kernel<<<grid, threads, smem, st>>>(p, cols, lo_col);
   S5_LAUNCH_CHECK();
   return S5_OK;
 }
@@ -656,7 +662,7 @@ int tc_glu_launch(const TcGluDev& d, const TcGluArgs& a, cudaStream_t st) {
   const long long ntiles = (a.rows + kTcRows - 1) / kTcRows;
   const int grid = (int)std::max<long long>(1, std::min<long long>(ntiles, (long long)sm_count()));
   ProfScope prof(S5_K_GLU, st);
-  tc_glu_kernel<<<grid, kTcThreads, d.smem, st>>>(p);
+  tc_glu_kernel<<<grid, kGluThreads, d.smem, st>>>(p);
   S5_LAUNCH_CHECK();
   return S5_OK;
 }
