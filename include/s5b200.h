@@ -118,6 +118,9 @@ int s5b200_spmm_i32(const s5_sparse* w, const int32_t* X, int32_t* Y, long long 
  * K and N multiples of 16, N <= 256.  Integer codes of up to 11 bits are exact in f16, so int8 weights times
  * hi/lo-split int16 activations give exact integer sums ("dense-tile path"). */
 int s5b200_tc_gemm_f16(const void* A, const void* W, float* Y, long long rows, int K, int N, void* stream);
+/* The integer form the model kernels use (tcgen05 kind::i8, int32 accumulation in TMEM):
+ * Y[rows][N] (int32) = A[rows][K] (int8 if a_signed else uint8) * W[N][K]^T (int8).  K multiple of 32, N of 16, N <= 256. */
+int s5b200_tc_gemm_i8(const void* A, const void* W, int32_t* Y, long long rows, int K, int N, int a_signed, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * (1)+(2) Float / static-quant model.  Host code (Python) keeps the reference's parameter pytree,
@@ -174,10 +177,17 @@ int s5b200_layer_forward(const s5_model* m, int layer, const float* x, float* y,
  * y = ys + D*u [B][L][H] (quantised for S5_STATIC) and xs [B][L][P] complex64. */
 int s5b200_ssm_forward(const s5_model* m, int layer, const float* u, float* y, float* xs_out, int B, int L,
                        void* workspace, size_t workspace_bytes, void* stream);
-/* Same as s5b200_model_forward with HOST buffers: H2D copy, forward, D2H copy, stream-synchronous on
- * return.  This is the call the end-to-end benchmark times. */
+/* Same as s5b200_model_forward with HOST buffers (pinned for full speed): the batch flows in clip chunks through an
+ * internal H2D | forward | D2H pipeline.  Host-synchronous: y_host is complete on return.  This is the call the
+ * end-to-end benchmark times (bench.py "e2e"). */
 int s5b200_model_forward_host(const s5_model* m, const float* x_host, float* y_host, int B, int L,
                               void* stream);
+/* Stream-ordered form of the same call: returns after enqueueing; `stream` is made to wait for the last
+ * device-to-host copy, so y_host is complete once work queued on `stream` after this call has run (e.g. after
+ * cudaStreamSynchronize(stream)).  x_host / y_host must stay valid until then.  Back-to-back calls overlap the
+ * drain of one batch with the fill of the next. */
+int s5b200_model_forward_host_async(const s5_model* m, const float* x_host, float* y_host, int B, int L,
+                                    void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * (3) Fixed-point model, bit-exact with sparseRNNs/fxpmodel.py driven as in fxprun.py:25-95.

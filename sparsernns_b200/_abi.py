@@ -108,6 +108,7 @@ PROTOTYPES = {
     "s5b200_spmm_f32": (_I, [_V, _V, _V, _V, _LL, _I, _V]),
     "s5b200_spmm_i32": (_I, [_V, _V, _V, _LL, _I, _I, _I, _I, _V]),
     "s5b200_tc_gemm_f16": (_I, [_V, _V, _V, _LL, _I, _I, _V]),
+    "s5b200_tc_gemm_i8": (_I, [_V, _V, _V, _LL, _I, _I, _I, _V]),
     "s5b200_model_create": (_I, [C.POINTER(ModelDesc), C.POINTER(_V)]),
     "s5b200_model_destroy": (_I, [_V]),
     "s5b200_model_workspace_bytes": (_SZ, [_V, _I, _I]),
@@ -115,6 +116,7 @@ PROTOTYPES = {
     "s5b200_layer_forward": (_I, [_V, _I, _V, _V, _V, _I, _I, _V, _SZ, _V]),
     "s5b200_ssm_forward": (_I, [_V, _I, _V, _V, _V, _I, _I, _V, _SZ, _V]),
     "s5b200_model_forward_host": (_I, [_V, _V, _V, _I, _I, _V]),
+    "s5b200_model_forward_host_async": (_I, [_V, _V, _V, _I, _I, _V]),
     "s5b200_fxp_model_create": (_I, [C.POINTER(FxpModelDesc), C.POINTER(_V)]),
     "s5b200_fxp_model_destroy": (_I, [_V]),
     "s5b200_fxp_model_workspace_bytes": (_SZ, [_V, _I, _I]),

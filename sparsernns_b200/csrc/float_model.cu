@@ -9,7 +9,10 @@
 // Kernels per forward: encoder linear, then per block {BN+B-projection linear, scan_c64, C-projection+GLU},
 // decoder linear.  Bu/xs are the only SSM intermediates that touch HBM.
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <mutex>
 #include <vector>
 
@@ -328,13 +331,14 @@ struct s5_model {
   float *enc_bias = nullptr, *dec_bias = nullptr;
   std::vector<s5::LayerDev> layers;
   // host-buffer entry point: ring of device buffers, three streams (H2D | forward | D2H) and their events
-  static constexpr int kSlots = 3;
+  static constexpr int kSlots = 5;
   std::mutex mu;
-  float* hx[kSlots] = {nullptr, nullptr, nullptr}; float* hy[kSlots] = {nullptr, nullptr, nullptr};
-  void* hws[kSlots] = {nullptr, nullptr, nullptr};
-  size_t hx_cap[kSlots] = {0, 0, 0}, hy_cap[kSlots] = {0, 0, 0}, hws_cap[kSlots] = {0, 0, 0};
-  cudaStream_t hs[3] = {nullptr, nullptr, nullptr};
-  cudaEvent_t ev_h2d[kSlots] = {}, ev_cmp[kSlots] = {}, ev_d2h[kSlots] = {}, ev_user = nullptr;
+  float* hx[kSlots] = {}; float* hy[kSlots] = {};
+  void* hws[kSlots] = {};
+  size_t hx_cap[kSlots] = {}, hy_cap[kSlots] = {}, hws_cap[kSlots] = {};
+  cudaStream_t hs[4] = {nullptr, nullptr, nullptr, nullptr};   // H2D, D2H, two forward streams
+  cudaEvent_t ev_h2d[kSlots] = {}, ev_cmp[kSlots] = {}, ev_d2h[kSlots] = {}, ev_user = nullptr, ev_done = nullptr;
+  unsigned long long chunk_seq = 0;
 };
 
 namespace s5 {
@@ -557,7 +561,8 @@ extern "C" int s5b200_model_destroy(s5_model* m) {
     if (m->ev_d2h[i]) cudaEventDestroy(m->ev_d2h[i]);
   }
   if (m->ev_user) cudaEventDestroy(m->ev_user);
-  for (int i = 0; i < 3; ++i)
+  if (m->ev_done) cudaEventDestroy(m->ev_done);
+  for (int i = 0; i < 4; ++i)
     if (m->hs[i]) cudaStreamDestroy(m->hs[i]);
   delete m;
   return S5_OK;
@@ -624,10 +629,9 @@ extern "C" int s5b200_ssm_forward(const s5_model* m, int layer, const float* u, 
   return run_block(m, layer, u, y, bu, B, L, base + w.off_scan, w.scan_bytes, false, true, (cudaStream_t)stream);
 }
 
-extern "C" int s5b200_model_forward_host(const s5_model* mc, const float* x_host, float* y_host, int B, int L,
-                                         void* stream) {
+static int forward_host_impl(const s5_model* mc, const float* x_host, float* y_host, int B, int L, void* stream, bool sync) {
   // End-to-end entry point: the batch is cut into clip chunks that flow through a three-stage pipeline
-  // (H2D copy | forward | D2H copy) on three internal streams with a ring of kSlots device buffers, so that
+  // (H2D copy | forward | D2H copy) on four internal streams (two alternating forward streams) with a ring of kSlots device buffers, so that
   // the two PCIe directions and the kernels overlap.  Clips are independent, so chunking does not change results.
   using namespace s5;
   s5_model* m = const_cast<s5_model*>(mc);
@@ -636,11 +640,40 @@ extern "C" int s5b200_model_forward_host(const s5_model* mc, const float* x_host
   cudaStream_t user = (cudaStream_t)stream;
   std::lock_guard<std::mutex> lock(m->mu);
   constexpr int kSlots = s5_model::kSlots;
-  // enough chunks to keep pipeline fill/drain small next to the PCIe time, few enough that every chunk still
-  // fills the GPU (measured on B200: 4 chunks 31 M frames/s, 16 chunks 21 M; S5B200_E2E_CHUNKS overrides)
-  int nchunks = std::max(1, std::min(8, B / 4));
-  if (const char* e = getenv("S5B200_E2E_CHUNKS")) nchunks = std::max(1, std::min(B, atoi(e)));
-  const int cb = (B + nchunks - 1) / nchunks;  // clips per chunk
+  // Chunk schedule (S5B200_E2E_CHUNKS=n forces n equal chunks, "a,b,c" explicit clip counts).
+  std::vector<int> sched;
+  const char* e = getenv("S5B200_E2E_CHUNKS");
+  if (e && strchr(e, ',')) {                    // explicit clip counts, e.g. "6,6,6,6,4,4"; the rest goes into a last chunk
+    int used = 0;
+    for (const char* q = e; *q && used < B;) {
+      const int v = std::max(1, std::min(B - used, atoi(q)));
+      sched.push_back(v);
+      used += v;
+      q = strchr(q, ',');
+      if (!q) break;
+      ++q;
+    }
+    if (used < B) sched.push_back(B - used);
+  } else if (e) {
+    const int n = std::max(1, std::min(B, atoi(e)));
+    const int cbu = (B + n - 1) / n;
+    for (int b0 = 0; b0 < B; b0 += cbu) sched.push_back(std::min(cbu, B - b0));
+  } else {
+    // The device-to-host direction is the bottleneck of the pipeline (measured: ~42 GB/s under bidirectional load),
+    // so it should start as early as possible: ramp up 1, 1, 2, 4 clips, then chunks of about 6 that amortise the
+    // fixed latency of a forward (11 launches, ~0.3 ms) while two forward streams keep the GPU busy.
+    int rem = B;
+    for (int t : {1, 1, 2, 4})
+      if (rem > 2 * t) { sched.push_back(t); rem -= t; }
+    const int nbody = std::max(1, (rem + 5) / 6);
+    for (int i = 0; i < nbody; ++i) {
+      const int take = (rem + (nbody - i) - 1) / (nbody - i);
+      sched.push_back(take);
+      rem -= take;
+    }
+  }
+  const int nchunks = (int)sched.size();
+  const int cb = *std::max_element(sched.begin(), sched.end());  // largest chunk sizes the slot buffers
   const size_t xb = (size_t)cb * L * m->desc.d_input * sizeof(float), yb = (size_t)cb * L * m->desc.d_output * sizeof(float);
   const size_t wsb = ws_layout(m, cb, L).total;
   auto grow = [&](void** p, size_t* cap, size_t need) -> int {
@@ -653,40 +686,88 @@ extern "C" int s5b200_model_forward_host(const s5_model* mc, const float* x_host
   };
   int rc;
   if (!m->hs[0]) {
-    for (int i = 0; i < 3; ++i) S5_CUDA(cudaStreamCreateWithFlags(&m->hs[i], cudaStreamNonBlocking));
+    for (int i = 0; i < 4; ++i) S5_CUDA(cudaStreamCreateWithFlags(&m->hs[i], cudaStreamNonBlocking));
     for (int i = 0; i < kSlots; ++i) {
       S5_CUDA(cudaEventCreateWithFlags(&m->ev_h2d[i], cudaEventDisableTiming));
       S5_CUDA(cudaEventCreateWithFlags(&m->ev_cmp[i], cudaEventDisableTiming));
       S5_CUDA(cudaEventCreateWithFlags(&m->ev_d2h[i], cudaEventDisableTiming));
     }
     S5_CUDA(cudaEventCreateWithFlags(&m->ev_user, cudaEventDisableTiming));
+    S5_CUDA(cudaEventCreateWithFlags(&m->ev_done, cudaEventDisableTiming));
   }
   for (int i = 0; i < kSlots; ++i) {
     if ((rc = grow(reinterpret_cast<void**>(&m->hx[i]), &m->hx_cap[i], xb))) return rc;
     if ((rc = grow(reinterpret_cast<void**>(&m->hy[i]), &m->hy_cap[i], yb))) return rc;
     if ((rc = grow(&m->hws[i], &m->hws_cap[i], wsb))) return rc;
   }
-  cudaStream_t s_in = m->hs[0], s_cmp = m->hs[1], s_out = m->hs[2];
+  cudaStream_t s_in = m->hs[0], s_out = m->hs[1];
   S5_CUDA(cudaEventRecord(m->ev_user, user));  // order after whatever the caller queued before
   S5_CUDA(cudaStreamWaitEvent(s_in, m->ev_user, 0));
-  for (int c = 0; c < nchunks; ++c) {
-    const int b0 = c * cb, nb = std::min(cb, B - b0);
-    if (nb <= 0) break;
-    const int slot = c % kSlots;
+  // S5B200_E2E_TRACE=1: print the device timeline of the pipeline (debug aid; adds timing events)
+  const bool trace = getenv("S5B200_E2E_TRACE") != nullptr;
+  std::vector<cudaEvent_t> tev;
+  std::vector<double> thost;
+  const auto host_t0 = std::chrono::steady_clock::now();
+  auto mark = [&](cudaStream_t st) {
+    if (!trace) return;
+    cudaEvent_t ev;
+    cudaEventCreate(&ev);
+    cudaEventRecord(ev, st);
+    tev.push_back(ev);
+    thost.push_back(std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count());
+  };
+  mark(s_in);
+  int b0 = 0;
+  for (int c = 0; c < nchunks; b0 += sched[c], ++c) {
+    const int nb = sched[c];
+    const unsigned long long seq = m->chunk_seq++;   // slots and forward streams rotate across calls, too
+    const int slot = (int)(seq % kSlots);
+    cudaStream_t s_cmp = m->hs[2 + (seq & 1)];   // consecutive chunks run concurrently: a chunk alone does not fill the GPU
     const size_t xoff = (size_t)b0 * L * m->desc.d_input, yoff = (size_t)b0 * L * m->desc.d_output;
     const size_t xbytes = (size_t)nb * L * m->desc.d_input * sizeof(float), ybytes = (size_t)nb * L * m->desc.d_output * sizeof(float);
-    if (c >= kSlots) S5_CUDA(cudaStreamWaitEvent(s_in, m->ev_d2h[slot], 0));  // slot buffers are free again
+    if (seq >= (unsigned long long)kSlots) S5_CUDA(cudaStreamWaitEvent(s_in, m->ev_d2h[slot], 0));  // slot buffers are free again
     S5_CUDA(cudaMemcpyAsync(m->hx[slot], x_host + xoff, xbytes, cudaMemcpyHostToDevice, s_in));
     S5_CUDA(cudaEventRecord(m->ev_h2d[slot], s_in));
+    mark(s_in);
     S5_CUDA(cudaStreamWaitEvent(s_cmp, m->ev_h2d[slot], 0));
-    if ((rc = s5b200_model_forward(m, m->hx[slot], m->hy[slot], nb, L, m->hws[slot], m->hws_cap[slot], s_cmp))) return rc;
+    mark(s_cmp);
+    if (!(trace && getenv("S5B200_E2E_TRACE_COPY_ONLY")) &&   // debug: measure the copy pipeline alone
+        (rc = s5b200_model_forward(m, m->hx[slot], m->hy[slot], nb, L, m->hws[slot], m->hws_cap[slot], s_cmp))) return rc;
     S5_CUDA(cudaEventRecord(m->ev_cmp[slot], s_cmp));
+    mark(s_cmp);
     S5_CUDA(cudaStreamWaitEvent(s_out, m->ev_cmp[slot], 0));
     S5_CUDA(cudaMemcpyAsync(y_host + yoff, m->hy[slot], ybytes, cudaMemcpyDeviceToHost, s_out));
     S5_CUDA(cudaEventRecord(m->ev_d2h[slot], s_out));
+    mark(s_out);
   }
-  S5_CUDA(cudaStreamSynchronize(s_out));
-  S5_CUDA(cudaStreamSynchronize(s_cmp));
-  S5_CUDA(cudaStreamSynchronize(s_in));
+  // the caller's stream continues after the last device-to-host copy (which is after everything else)
+  S5_CUDA(cudaEventRecord(m->ev_done, s_out));
+  S5_CUDA(cudaStreamWaitEvent(user, m->ev_done, 0));
+  if (sync || trace) {
+    S5_CUDA(cudaStreamSynchronize(s_out));
+    S5_CUDA(cudaStreamSynchronize(m->hs[2]));
+    S5_CUDA(cudaStreamSynchronize(m->hs[3]));
+    S5_CUDA(cudaStreamSynchronize(s_in));
+  }
+  if (trace) {
+    const double host_end = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
+    fprintf(stderr, "[s5b200 e2e trace] chunk clips | h2d done | fwd start..done | d2h done (ms, device) | host enqueue done (ms)\n");
+    for (int c = 0; c < nchunks; ++c) {
+      float t[4];
+      for (int j = 0; j < 4; ++j) cudaEventElapsedTime(&t[j], tev[0], tev[1 + 4 * c + j]);
+      fprintf(stderr, "[s5b200 e2e trace] %2d %3d | %7.3f | %7.3f .. %7.3f | %7.3f | %7.3f\n", c, sched[c], t[0], t[1], t[2], t[3], thost[4 + 4 * c]);
+    }
+    fprintf(stderr, "[s5b200 e2e trace] host returned at %.3f ms\n", host_end);
+    for (cudaEvent_t ev : tev) cudaEventDestroy(ev);
+  }
   return S5_OK;
+}
+
+extern "C" int s5b200_model_forward_host(const s5_model* m, const float* x_host, float* y_host, int B, int L, void* stream) {
+  return forward_host_impl(m, x_host, y_host, B, L, stream, true);
+}
+
+extern "C" int s5b200_model_forward_host_async(const s5_model* m, const float* x_host, float* y_host, int B, int L,
+                                               void* stream) {
+  return forward_host_impl(m, x_host, y_host, B, L, stream, false);
 }

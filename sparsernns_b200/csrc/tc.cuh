@@ -4,6 +4,8 @@
 // core matrices, element (row r, column k) of a [R][K] f16 tile at byte offset
 //     (k / 8) * (R * 16) + r * 16 + (k % 8) * 2
 // i.e. stride-byte-offset (next 8-row group) = 128 B, leading-byte-offset (next 16-byte K chunk) = R * 16 B.
+// 8-bit operands (kind::i8) use the same byte geometry with 16 elements per 16-byte chunk:
+//     (k / 16) * LBO + r * 16 + (k % 16);  one MMA consumes K = 32 elements = two chunks, as for f16.
 // Accumulators live in TMEM (lane = tile row, column = output column) and are read back with tcgen05.ld.
 #pragma once
 
@@ -33,6 +35,12 @@ __host__ __device__ __forceinline__ uint32_t tc_idesc_bf16(int M, int N) {
   return tc_idesc_f16(M, N) | (1u << 7) | (1u << 10);
 }
 
+// kind::i8: A, B 8-bit integers (format 1 = signed, 0 = unsigned), D = S32 (c_format 2), both K-major.  MMA K = 32.
+__host__ __device__ __forceinline__ uint32_t tc_idesc_i8(int M, int N, bool a_signed, bool b_signed) {
+  return (2u << 4) | ((a_signed ? 1u : 0u) << 7) | ((b_signed ? 1u : 0u) << 10) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
+}
+
 __device__ __forceinline__ void tc_alloc(uint32_t* smem_slot, uint32_t ncols) {  // one full warp
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)), "r"(ncols)
                : "memory");
@@ -51,6 +59,16 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uin
       ".reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_i8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t"
       "}" ::"r"(d_tmem),
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
       : "memory");

@@ -29,16 +29,17 @@ constexpr int kTcKI = 8;  // K <= 256: each lane stages at most 8 input columns
 
 struct TcLinParams {
   const float* X; float* Y; long long rows;
-  int K, N;                 // MMA dims (multiples of 16); the matrix may have one extra input row / output column
+  int Kfull, Nfull;         // matrix dims
+  int Kp, Np;               // padded dims of the operand tiles: Kp multiple of 32, Np multiple of 16
+  int NP;                   // output columns per pass (MMA N), multiple of 16, <= 128
+  int alias_out;            // single pass: the output tile may reuse the (dead) activation planes
   int x_stride, y_stride;   // floats per input / output row
-  const __half* Wh;         // [N][K] weight codes
-  const float* in_sub; const float* in_mul; const float* in_add;  // BatchNorm on the input (nullable)
+  const signed char* W8;    // [Np][Kp] int8 weight codes, K in the physical (staging) order, zero padded
+  const float* in_sub; const float* in_mul; const float* in_add;  // BatchNorm on the input (BN instantiation only)
   float in_inv, in_qmin, in_qmax;   // 1 / s_in (s_in is a power of two, so x * in_inv == x / s_in exactly)
-  const float* col_scale;   // [y_stride] s_in * s_w[n]
-  const float* bias;        // [y_stride] fake-quantised bias, nullable
+  const float* col_scale;   // [Nfull] s_in * s_w[n]
+  const float* bias;        // [Nfull] fake-quantised bias, nullable
   float out_scale0, out_scale1, out_inv0, out_inv1, out_qmin, out_qmax; int relu;
-  const float* w_extra_k;   // [N]  codes of weight row k = K   (encoder: K = 256 of 257), nullable
-  const float* w_extra_n;   // [K]  codes of weight column n = N (decoder: N = 256 of 257), nullable
 };
 
 // clip(round_half_even(x / s)) with 1/s passed in: exact for the power-of-two scales of the static recipe
@@ -54,10 +55,28 @@ __device__ __forceinline__ uint32_t pack_h2(int a, int b) {
   return *reinterpret_cast<const uint32_t*>(&h);
 }
 
-// Operand tiles use a padded leading-byte-offset (K-chunk stride = rows*16 + 16 bytes): with it both the
-// lanes-along-k 2-byte staging writes and lanes-along-rows 16-byte writes are bank-conflict free.
+// Rounding without the conversion pipe.  For |t| <= 2^22, t + 1.5 * 2^23 is rounded to an integer by the add itself
+// (round-half-even, the mode of rintf / jnp.round), and the low mantissa bits of the sum hold that integer in two's
+// complement: bits = 0x4B400000 + code.  Clipping to the integer bounds BEFORE rounding gives the same result as after.
+constexpr float kRoundMagic = 12582912.0f;
+__device__ __forceinline__ uint32_t quant_bits(float v, float inv, float qmin, float qmax) {   // low 16 bits = int16 code
+  return __float_as_uint(fminf(fmaxf(v * inv, qmin), qmax) + kRoundMagic);
+}
+__device__ __forceinline__ float round_clip(float t, float qmin, float qmax) {                  // clip(rint(t))
+  return (fminf(fmaxf(t, qmin), qmax) + kRoundMagic) - kRoundMagic;
+}
+// four int16 codes (low halves of b0..b3) -> word of the four low bytes, word of the four high bytes
+__device__ __forceinline__ void split_planes(uint32_t b0, uint32_t b1, uint32_t b2, uint32_t b3, uint32_t& lo, uint32_t& hi) {
+  const uint32_t t01 = __byte_perm(b0, b1, 0x5140), t23 = __byte_perm(b2, b3, 0x5140);   // {lo0, lo1, hi0, hi1}
+  lo = __byte_perm(t01, t23, 0x5410);
+  hi = __byte_perm(t01, t23, 0x7632);
+}
+
+// Operand tiles use a padded leading-byte-offset (K-chunk stride = rows*16 + 16 bytes): with it the staging stores
+// (lanes along k) are bank-conflict free.
 __host__ __device__ __forceinline__ uint32_t tc_lbo(int rows) { return (uint32_t)rows * 16u + 16u; }
-__host__ __device__ __forceinline__ size_t tc_tile_bytes(int rows, int K) { return (size_t)(K >> 3) * tc_lbo(rows); }
+__host__ __device__ __forceinline__ size_t tc_tile_bytes(int rows, int K) { return (size_t)(K >> 3) * tc_lbo(rows); }   // f16 / bf16
+__host__ __device__ __forceinline__ size_t tc_tile_bytes8(int rows, int K) { return (size_t)(K >> 4) * tc_lbo(rows); }  // 8-bit
 
 // copy a plain row-major [R][K] f16 matrix into the canonical operand layout
 __device__ __forceinline__ void tc_load_weights(unsigned char* dst, const __half* __restrict__ W, int R, int K) {
@@ -66,6 +85,15 @@ __device__ __forceinline__ void tc_load_weights(unsigned char* dst, const __half
   for (int i = threadIdx.x; i < R * kchunks; i += blockDim.x) {
     const int r = i / kchunks, kc = i % kchunks;
     *reinterpret_cast<int4*>(dst + (size_t)kc * lbo + (size_t)r * 16) = *reinterpret_cast<const int4*>(W + (size_t)r * K + kc * 8);
+  }
+}
+// same for a row-major [R][K] int8 matrix (16 codes per 16-byte chunk)
+__device__ __forceinline__ void tc_load_weights8(unsigned char* dst, const signed char* __restrict__ W, int R, int K) {
+  const int kchunks = K >> 4;
+  const uint32_t lbo = tc_lbo(R);
+  for (int i = threadIdx.x; i < R * kchunks; i += blockDim.x) {
+    const int r = i / kchunks, kc = i % kchunks;
+    *reinterpret_cast<int4*>(dst + (size_t)kc * lbo + (size_t)r * 16) = *reinterpret_cast<const int4*>(W + (size_t)r * K + kc * 16);
   }
 }
 
@@ -78,143 +106,123 @@ __device__ __forceinline__ void tc_issue(uint32_t d_tmem, const void* A, const v
   for (int j = 0; j < (K >> 4); ++j)
     tc_mma_f16(d_tmem, tc_smem_desc(a0 + j * 2 * la, la, 128), tc_smem_desc(b0 + j * 2 * lb, lb, 128), idesc, accumulate_first || j > 0);
 }
+// int8 form: K/32 MMAs of [128 x K] (8-bit, signed or unsigned) x [K x N] (int8; `brows` rows in the whole B tile)
+__device__ __forceinline__ void tc_issue8(uint32_t d_tmem, const void* A, const void* B, int K, int N, int brows, bool a_signed) {
+  const uint32_t a0 = smem_u32(A), b0 = smem_u32(B);
+  const uint32_t la = tc_lbo(kTcRows), lb = tc_lbo(brows);
+  const uint32_t idesc = tc_idesc_i8(kTcRows, N, a_signed, true);
+  for (int j = 0; j < (K >> 5); ++j)
+    tc_mma_i8(d_tmem, tc_smem_desc(a0 + j * 2 * la, la, 128), tc_smem_desc(b0 + j * 2 * lb, lb, 128), idesc, j > 0);
+}
 
-template <bool VEC4>
-__global__ void __launch_bounds__(512, 1) tc_linear_kernel(TcLinParams p, uint32_t tmem_cols, uint32_t lo_col) {
+// Dense / B-projection tile kernel.  Per 128-row tile:
+//   stage   : rows -> (BatchNorm) -> int16 codes -> signed high-byte plane + unsigned low-byte plane (8-bit operands)
+//   MMA     : acc_hi = Ah * W^T, acc_lo = Al * W^T  (tcgen05 kind::i8, int32 in TMEM), NP output columns per pass
+//   epilogue: acc = 256 acc_hi + acc_lo (exact) -> scale, bias, fake-quant, ReLU -> shared tile -> coalesced stores
+// VEC4: rows are 16-byte aligned, lane owns input columns 4 lane .. 4 lane + 3 of each 128-column block.  Otherwise
+// lane owns columns lane + 32 e (coalesced 4-byte loads) and the K axis is PERMUTED inside each block (the same
+// permutation is baked into W8 by the host), so that the four codes of a lane still form one 32-bit store.
+template <bool VEC4, int KV, bool BN>
+__global__ void __launch_bounds__(kTcThreads, 2) tc_linear_kernel(TcLinParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
-  const int K = p.K, N = p.N;
-  const size_t a_bytes = tc_tile_bytes(kTcRows, K);
-  unsigned char* Wt = smem;                                   // [N][K] weight codes
-  unsigned char* Ah = Wt + tc_tile_bytes(N, K);               // [128][K] high bytes of the activation codes
-  unsigned char* Al = Ah + a_bytes;                           // [128][K] low bytes
-  float* outT = reinterpret_cast<float*>(Ah);                 // output tile [128][NC + 4], aliases the dead A tiles
+  const int Kp = p.Kp, Np = p.Np, NP = p.NP;
+  const size_t a_bytes = tc_tile_bytes8(kTcRows, Kp);
+  unsigned char* Wt = smem;                                   // [Np][Kp] weight codes
+  unsigned char* Ah = Wt + tc_tile_bytes8(Np, Kp);            // [128][Kp] high bytes of the activation codes
+  unsigned char* Al = Ah + a_bytes;                           // [128][Kp] low bytes
+  const int ld_out = NP + 4;
+  float* outT = reinterpret_cast<float*>(p.alias_out ? Ah : Al + a_bytes);      // output tile [128][NP + 4]
+  float2* cst = reinterpret_cast<float2*>(reinterpret_cast<unsigned char*>(outT) +
+                                          (p.alias_out ? max(2 * a_bytes, (size_t)kTcRows * ld_out * 4) : (size_t)kTcRows * ld_out * 4));
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t tmem_slot;
-  __shared__ int extra_n[kTcRows];                            // integer dot of the extra output column
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int NW = blockDim.x >> 5;                             // 8 or 16 warps
-  if (warp == 0) tc_alloc(&tmem_slot, tmem_cols);
+  constexpr int NW = kTcThreads / 32;
+  if (warp == 0) tc_alloc(&tmem_slot, 256);
   if (tid == 0) {
     mbar_init(&bar, 1);
     fence_mbar_init();
   }
-  tc_load_weights(Wt, p.Wh, N, K);
-  const uint32_t lbo = tc_lbo(kTcRows);
-  const int NC = N > 128 ? 128 : N;                           // columns per epilogue pass
-  const int ld_out = NC + 4;
-  const int erow = (warp & 3) * 32 + lane;                    // epilogue: TMEM lane = row
-  const int cw = NC / (NW >> 2);                              // columns per warp group within a pass
-  // per-lane constants of the staging loop.  Scalar form: lane owns columns k = lane + 32 i; vector form (rows
-  // 16-byte aligned): lane owns columns 4 lane + 128 i .. + 3.
-  constexpr bool vec4 = VEC4;
-  float sub[kTcKI], mul[kTcKI], add[kTcKI];
-  int wn[kTcKI];
-  float sub4[2][4], mul4[2][4], add4[2][4];
-  int wn4[2][4];
-#pragma unroll
-  for (int i = 0; i < kTcKI; ++i) {
-    const int k = lane + 32 * i;
-    const bool in = k < K && !vec4;
-    sub[i] = (in && p.in_sub) ? p.in_sub[k] : 0.f;
-    mul[i] = (in && p.in_sub) ? p.in_mul[k] : 1.f;
-    add[i] = (in && p.in_sub) ? p.in_add[k] : 0.f;
-    wn[i] = (in && p.w_extra_n) ? __float2int_rn(p.w_extra_n[k]) : 0;
+  tc_load_weights8(Wt, p.W8, Np, Kp);
+  for (size_t i = (size_t)tid * 16; i < 2 * a_bytes; i += kTcThreads * 16) *reinterpret_cast<int4*>(Ah + i) = make_int4(0, 0, 0, 0);
+  // per-column epilogue constants: t = acc * a + b with a = s_in s_w / s_out, b = bias / s_out (all scales powers of two)
+  for (int n = tid; n < Np; n += kTcThreads) {
+    const float inv = (n & 1) ? p.out_inv1 : p.out_inv0;
+    cst[n] = n < p.Nfull ? make_float2(p.col_scale[n] * inv, p.bias ? p.bias[n] * inv : 0.f) : make_float2(0.f, 0.f);
   }
+  const uint32_t lbo = tc_lbo(kTcRows);
+  // per-lane staging constants
+  float sub[KV][4], mul[KV][4], add[KV][4];
+  bool kval[KV][4];
+  uint32_t loff[KV];
 #pragma unroll
-  for (int i = 0; i < 2; ++i)
+  for (int i = 0; i < KV; ++i) {
+    loff[i] = (uint32_t)(8 * i + (lane >> 2)) * lbo + 4u * (lane & 3);
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const int k = 4 * lane + 128 * i + e;
-      const bool in = k < K && vec4;
-      sub4[i][e] = (in && p.in_sub) ? p.in_sub[k] : 0.f;
-      mul4[i][e] = (in && p.in_sub) ? p.in_mul[k] : 1.f;
-      add4[i][e] = (in && p.in_sub) ? p.in_add[k] : 0.f;
-      wn4[i][e] = (in && p.w_extra_n) ? __float2int_rn(p.w_extra_n[k]) : 0;
+      const int k = VEC4 ? 128 * i + 4 * lane + e : 128 * i + lane + 32 * e;
+      kval[i][e] = k < p.Kfull;
+      sub[i][e] = (BN && kval[i][e]) ? p.in_sub[k] : 0.f;
+      mul[i][e] = (BN && kval[i][e]) ? p.in_mul[k] : 1.f;
+      add[i][e] = (BN && kval[i][e]) ? p.in_add[k] : 0.f;
     }
+  }
+  const bool tail = p.Kfull > 128 * KV;                       // one more input column (encoder: 257 = 2 * 128 + 1)
+  const int erow = (warp & 3) * 32 + lane;                    // epilogue: TMEM lane = row
+  const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+  const int egrp = warp >> 2;                                 // column half of a pass
+  const bool wvec = (p.y_stride & 3) == 0 && (NP & 3) == 0 && (p.Nfull & 3) == 0 &&
+                    (reinterpret_cast<uintptr_t>(p.Y) & 15) == 0;
   uint32_t phase = 0;
   const long long ntiles = (p.rows + kTcRows - 1) / kTcRows;
+  __syncthreads();
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const long long row0 = tile * kTcRows;
     const int rv = (int)min((long long)kTcRows, p.rows - row0);
-    // ---- stage (coalesced, lanes along k): quantise to int16 codes, split into hi / lo bytes stored as f16.
-    // Several rows are loaded before any of them is converted so that every lane keeps many loads in flight.
-    if constexpr (VEC4) {
-      // 16-byte aligned rows: each lane owns 4 consecutive input columns (one LDG.128, two 8-byte operand stores)
-      for (int rb = warp * 4; rb < kTcRows; rb += NW * 4) {
-        float4 raw[4][2];
+    // ---- stage: RB rows are loaded before any of them is converted so that every lane keeps many loads in flight
+    constexpr int RB = 8 / KV;
+    for (int rb = warp * RB; rb < kTcRows; rb += NW * RB) {
+      float raw[RB][KV][4];
+      float rawt[RB];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float* xr = p.X + (size_t)(row0 + rb + q) * p.x_stride;
+      for (int q = 0; q < RB; ++q) {
+        const bool rin = rb + q < rv;
+        const float* xr = p.X + (size_t)(row0 + rb + q) * p.x_stride;
 #pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            const int k = 4 * lane + 128 * i;
-            raw[q][i] = (k < K && rb + q < rv) ? *reinterpret_cast<const float4*>(xr + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < KV; ++i) {
+          if constexpr (VEC4) {
+            const float4 v = (rin && kval[i][0]) ? *reinterpret_cast<const float4*>(xr + 128 * i + 4 * lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+            raw[q][i][0] = v.x; raw[q][i][1] = v.y; raw[q][i][2] = v.z; raw[q][i][3] = v.w;
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) raw[q][i][e] = (rin && kval[i][e]) ? xr[128 * i + lane + 32 * e] : 0.f;
           }
         }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int r = rb + q;
-          int part = 0;
-#pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            const int k = 4 * lane + 128 * i;
-            if (k < K) {
-              const float xv[4] = {raw[q][i].x, raw[q][i].y, raw[q][i].z, raw[q][i].w};
-              int c[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                float v = xv[e];
-                if (p.in_sub) v = (v - sub4[i][e]) * mul4[i][e] + add4[i][e];
-                c[e] = r < rv ? quant_code(v, p.in_inv, p.in_qmin, p.in_qmax) : 0;
-                part += c[e] * wn4[i][e];
-              }
-              const size_t o = (size_t)(k >> 3) * lbo + (size_t)(k & 7) * 2 + (size_t)r * 16;
-              *reinterpret_cast<uint2*>(Ah + o) = make_uint2(pack_h2(c[0] >> 8, c[1] >> 8), pack_h2(c[2] >> 8, c[3] >> 8));
-              *reinterpret_cast<uint2*>(Al + o) = make_uint2(pack_h2(c[0] & 255, c[1] & 255), pack_h2(c[2] & 255, c[3] & 255));
-            }
-          }
-          if (p.w_extra_n) {
-            part = __reduce_add_sync(0xffffffffu, part);
-            if (lane == 0) extra_n[r] = part;
-          }
-        }
+        rawt[q] = (tail && rin && lane == 0) ? xr[128 * KV] : 0.f;
       }
-    } else {
-      for (int rb = warp * 4; rb < kTcRows; rb += NW * 4) {
-        float raw[4][kTcKI];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float* xr = p.X + (size_t)(row0 + rb + q) * p.x_stride;
+      for (int q = 0; q < RB; ++q) {
+        const uint32_t roff = (uint32_t)(rb + q) * 16u;
 #pragma unroll
-          for (int i = 0; i < kTcKI; ++i) {
-            const int k = lane + 32 * i;
-            raw[q][i] = (k < K && rb + q < rv) ? xr[k] : 0.f;
+        for (int i = 0; i < KV; ++i) {
+          uint32_t b[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float v = raw[q][i][e];
+            if constexpr (BN) v = (v - sub[i][e]) * mul[i][e] + add[i][e];
+            b[e] = kval[i][e] ? quant_bits(v, p.in_inv, p.in_qmin, p.in_qmax) : 0u;
+          }
+          uint32_t lo, hi;
+          split_planes(b[0], b[1], b[2], b[3], lo, hi);
+          if (kval[i][0]) {   // element 0 is the lowest k of the lane in both orders: no valid element without it
+            *reinterpret_cast<uint32_t*>(Ah + loff[i] + roff) = hi;
+            *reinterpret_cast<uint32_t*>(Al + loff[i] + roff) = lo;
           }
         }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int r = rb + q;
-          int part = 0;
-#pragma unroll
-          for (int i = 0; i < kTcKI; ++i) {
-            const int k = lane + 32 * i;
-            if (k < K) {
-              int c = 0;
-              if (r < rv) {
-                float v = raw[q][i];
-                if (p.in_sub) v = (v - sub[i]) * mul[i] + add[i];
-                c = quant_code(v, p.in_inv, p.in_qmin, p.in_qmax);
-              }
-              const size_t o = (size_t)(k >> 3) * lbo + (size_t)(k & 7) * 2 + (size_t)r * 16;
-              *reinterpret_cast<__half*>(Ah + o) = __int2half_rn(c >> 8);
-              *reinterpret_cast<__half*>(Al + o) = __int2half_rn(c & 255);
-              part += c * wn[i];
-            }
-          }
-          if (p.w_extra_n) {
-            part = __reduce_add_sync(0xffffffffu, part);
-            if (lane == 0) extra_n[r] = part;
-          }
+        if (tail && lane == 0) {
+          const uint32_t bt = quant_bits(rawt[q], p.in_inv, p.in_qmin, p.in_qmax);
+          *reinterpret_cast<uint32_t*>(Ah + (size_t)(8 * KV) * lbo + roff) = (bt >> 8) & 0xFFu;
+          *reinterpret_cast<uint32_t*>(Al + (size_t)(8 * KV) * lbo + roff) = bt & 0xFFu;
         }
       }
     }
@@ -224,64 +232,76 @@ __global__ void __launch_bounds__(512, 1) tc_linear_kernel(TcLinParams p, uint32
     tc_fence_after();
     const uint32_t taddr = tmem_slot;
     if (tid == 0) {
-      tc_issue(taddr, Ah, Wt, K, N, false);
-      tc_issue(taddr + lo_col, Al, Wt, K, N, false);
+      const int np = min(NP, Np);
+      tc_issue8(taddr, Ah, Wt, Kp, np, Np, true);
+      tc_issue8(taddr + 128, Al, Wt, Kp, np, Np, false);
       tc_commit(&bar);
     }
-    mbar_wait(&bar, phase);
-    phase ^= 1;
-    tc_fence_after();
-    // ---- epilogue: exact integer recombination, scale, bias, fake-quant, ReLU -> shared tile -> coalesced stores
-    const bool ok = erow < rv;
-    int code_k = 0;
-    if (p.w_extra_k && ok) code_k = quant_code(p.X[(size_t)(row0 + erow) * p.x_stride + K], p.in_inv, p.in_qmin, p.in_qmax);
-    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    for (int pass0 = 0; pass0 < N; pass0 += NC) {
-      const int cbeg = pass0 + (warp >> 2) * cw;
-      for (int c0 = cbeg; c0 < cbeg + cw; c0 += 8) {
+    for (int pass0 = 0; pass0 < Np; pass0 += NP) {
+      const int np = min(NP, Np - pass0);                     // MMA width of this pass (multiple of 16)
+      const int npv = min(np, p.Nfull - pass0);               // columns that exist in Y
+      mbar_wait(&bar, phase);
+      phase ^= 1;
+      tc_fence_after();
+      // ---- epilogue: exact integer recombination, scale, bias, fake-quant, ReLU -> shared tile
+      const int cw = np >> 1;
+      for (int c0 = egrp * cw; c0 < (egrp + 1) * cw; c0 += 8) {
         uint32_t vh[8], vl[8];
         tc_ld8(taddr + lane_base + c0, vh);
-        tc_ld8(taddr + lane_base + lo_col + c0, vl);
+        tc_ld8(taddr + lane_base + 128 + c0, vl);
         tc_wait_ld();
-        float out[8], cs[8], bs[8], wk[8];
+        float out[8];
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          *reinterpret_cast<float4*>(cs + 4 * q) = *reinterpret_cast<const float4*>(p.col_scale + c0 + 4 * q);
-          *reinterpret_cast<float4*>(bs + 4 * q) = p.bias ? *reinterpret_cast<const float4*>(p.bias + c0 + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
-          *reinterpret_cast<float4*>(wk + 4 * q) = p.w_extra_k ? *reinterpret_cast<const float4*>(p.w_extra_k + c0 + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = 0; j < 8; j += 2) {
+          const float4 c2 = *reinterpret_cast<const float4*>(cst + pass0 + c0 + j);   // (a, b) of two columns
+          const float f0 = __int2float_rn((int)vh[j] * 256 + (int)vl[j]);
+          const float f1 = __int2float_rn((int)vh[j + 1] * 256 + (int)vl[j + 1]);
+          float o0 = round_clip(fmaf(f0, c2.x, c2.y), p.out_qmin, p.out_qmax) * p.out_scale0;
+          float o1 = round_clip(fmaf(f1, c2.z, c2.w), p.out_qmin, p.out_qmax) * p.out_scale1;
+          out[j] = p.relu ? fmaxf(o0, 0.f) : o0;
+          out[j + 1] = p.relu ? fmaxf(o1, 0.f) : o1;
         }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          int acc = __float2int_rn(__uint_as_float(vh[j])) * 256 + __float2int_rn(__uint_as_float(vl[j]));
-          acc += code_k * __float2int_rn(wk[j]);
-          float v = __int2float_rn(acc) * cs[j] + bs[j];
-          v = (j & 1) ? fq_from(v, p.out_scale1, p.out_inv1, p.out_qmin, p.out_qmax) : fq_from(v, p.out_scale0, p.out_inv0, p.out_qmin, p.out_qmax);
-          out[j] = p.relu ? fmaxf(v, 0.f) : v;
+        float* dst = outT + (size_t)erow * ld_out + c0;
+        *reinterpret_cast<float4*>(dst) = make_float4(out[0], out[1], out[2], out[3]);
+        *reinterpret_cast<float4*>(dst + 4) = make_float4(out[4], out[5], out[6], out[7]);
+      }
+      tc_fence_before();
+      __syncthreads();                                        // tile complete; TMEM and (last pass) the planes are free
+      if (tid == 0 && pass0 + NP < Np) {                      // next pass overlaps the write-out below
+        tc_fence_after();
+        const int np2 = min(NP, Np - pass0 - NP);
+        tc_issue8(taddr, Ah, Wt + (size_t)(pass0 + NP) * 16, Kp, np2, Np, true);
+        tc_issue8(taddr + 128, Al, Wt + (size_t)(pass0 + NP) * 16, Kp, np2, Np, false);
+        tc_commit(&bar);
+      }
+      // ---- write-out, coalesced
+      if (wvec) {
+        const int q4 = npv >> 2;                              // float4 per row
+        const int rpi = q4 >= 32 ? 1 : 32 / q4;               // rows per warp iteration
+        const int lr = lane / q4, lc = lane - lr * q4;
+        if (q4 <= 32) {
+          if (lr < rpi)
+            for (int r = warp * rpi + lr; r < rv; r += NW * rpi)
+              *reinterpret_cast<float4*>(p.Y + (size_t)(row0 + r) * p.y_stride + pass0 + 4 * lc) =
+                  *reinterpret_cast<const float4*>(outT + (size_t)r * ld_out + 4 * lc);
         }
-        float* dst = outT + (size_t)erow * ld_out + (c0 - pass0);
+      } else {
+        for (int r = warp; r < rv; r += NW) {
+          float* yr = p.Y + (size_t)(row0 + r) * p.y_stride + pass0;
+          const float* src = outT + (size_t)r * ld_out;
 #pragma unroll
-        for (int q = 0; q < 2; ++q) *reinterpret_cast<float4*>(dst + 4 * q) = make_float4(out[4 * q], out[4 * q + 1], out[4 * q + 2], out[4 * q + 3]);
+          for (int j = 0; j < 4; ++j) {
+            const int n = lane + 32 * j;
+            if (n < npv) yr[n] = src[n];
+          }
+        }
       }
-      __syncthreads();
-      for (int r = warp; r < rv; r += NW) {
-        float* yr = p.Y + (size_t)(row0 + r) * p.y_stride + pass0;
-        const float* src = outT + (size_t)r * ld_out;
-        for (int n = lane; n < NC; n += 32) yr[n] = src[n];
-      }
-      __syncthreads();
+      __syncthreads();                                        // output tile free again
     }
-    if (p.w_extra_n) {  // output column n = N on the CUDA cores (decoder: 257 = 256 + 1)
-      if (tid < rv) {
-        float v = __int2float_rn(extra_n[tid]) * p.col_scale[N];
-        if (p.bias) v += p.bias[N];
-        v = (N & 1) ? fq_from(v, p.out_scale1, p.out_inv1, p.out_qmin, p.out_qmax) : fq_from(v, p.out_scale0, p.out_inv0, p.out_qmin, p.out_qmax);
-        p.Y[(size_t)(row0 + tid) * p.y_stride + N] = p.relu ? fmaxf(v, 0.f) : v;
-      }
-    }
-    tc_fence_before();
-    __syncthreads();  // TMEM, the A tiles / output tile and extra_n are free again
   }
-  if (warp == 0) tc_dealloc(tmem_slot, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc_dealloc(tmem_slot, 256);
 }
 
 // ------------------------------------------------------------------------------------------- C projection + GLU
@@ -523,48 +543,77 @@ float pow2_grid(const float* w, size_t n, size_t start, size_t stride) {
 
 // W: fake-quantised weights [Kfull][Nfull]; even / odd output columns may sit on different power-of-two grids
 // (real / imaginary parts of the B projection).  s_in: activation scale.  out->ok stays false when the matrix is
-// not covered (shape, or codes that are not exact in f16), in which case the compressed kernels are used.
+// not covered (shape, or codes outside int8), in which case the compressed kernels are used.
 int tc_linear_build(const float* W, int Kfull, int Nfull, float s_in, TcLinearDev* out) {
-  const int K = Kfull & ~15, N = Nfull & ~15;
   out->ok = false;
   if (!is_pow2(s_in)) return S5_OK;
+  const bool tail = Kfull > 128 && (Kfull % 128) == 1;
+  const int KV = tail ? Kfull / 128 : (Kfull + 127) / 128;
+  if (KV < 1 || KV > 2 || Kfull < 16 || Nfull < 16 || Nfull > 512) return S5_OK;   // shape not covered
+  // padded K of the operand tiles: natural order / lane-interleaved order (whole 128-column blocks)
+  const int Kp[2] = {(Kfull + 31) & ~31, 128 * KV + (tail ? 32 : 0)};
+  const int Np = (Nfull + 15) & ~15;
   std::vector<float> col0, col1;
   for (int k = 0; k < Kfull; ++k)
     for (int n = 0; n < Nfull; ++n) ((n & 1) ? col1 : col0).push_back(W[(size_t)k * Nfull + n]);
   const float w_scale0 = pow2_grid(col0.data(), col0.size(), 0, 1);
   const float w_scale1 = pow2_grid(col1.data(), col1.size(), 0, 1);
-  if (Kfull - K > 1 || Nfull - N > 1 || K < 16 || K > 32 * kTcKI || N < 32 || (N & 31) || N > 256) return S5_OK;  // shape not covered
-  if (tc_tile_bytes(N, K) + std::max(2 * tc_tile_bytes(kTcRows, K), (size_t)kTcRows * ((N > 128 ? 128 : N) + 4) * 4) > 225 * 1024) return S5_OK;
-  std::vector<__half> wh((size_t)N * K);
-  std::vector<float> cs(Nfull), wk, wn;
-  auto code = [&](int k, int n) {
-    const float s = (n & 1) ? w_scale1 : w_scale0;
-    return std::nearbyint(W[(size_t)k * Nfull + n] / s);
-  };
-  for (int n = 0; n < N; ++n)
-    for (int k = 0; k < K; ++k) {
-      const float c = code(k, n);
-      if (std::fabs(c) > 2048.f) return S5_OK;  // not exact in f16: leave this matrix to the compressed kernels
-      wh[(size_t)n * K + k] = __float2half_rn(c);
+  // physical position of logical column k: identity for 16-byte aligned rows; lane-interleaved inside each
+  // 128-column block for the 4-byte staging path (lane owns k = lane + 32 e  <->  bytes 4 lane + e)
+  auto perm = [&](int k) { return k >= 128 * KV ? k : (k & ~127) + 4 * (k & 31) + ((k & 127) >> 5); };
+  std::vector<signed char> w8[2];
+  for (int o = 0; o < 2; ++o) w8[o].assign((size_t)Np * Kp[o], 0);
+  std::vector<float> cs(Nfull);
+  for (int n = 0; n < Nfull; ++n) {
+    const float sw = (n & 1) ? w_scale1 : w_scale0;
+    cs[n] = s_in * sw;
+    for (int k = 0; k < Kfull; ++k) {
+      const float c = std::nearbyint(W[(size_t)k * Nfull + n] / sw);
+      if (c < -128.f || c > 127.f) return S5_OK;  // not an int8 code: leave this matrix to the compressed kernels
+      w8[0][(size_t)n * Kp[0] + k] = (signed char)c;
+      w8[1][(size_t)n * Kp[1] + perm(k)] = (signed char)c;
     }
-  for (int n = 0; n < Nfull; ++n) cs[n] = s_in * ((n & 1) ? w_scale1 : w_scale0);
-  if (Kfull > K) { wk.resize(N); for (int n = 0; n < N; ++n) wk[n] = code(K, n); }
-  if (Nfull > N) { wn.resize(K); for (int k = 0; k < K; ++k) wn[k] = code(k, N); }
-  if (Kfull > K && Nfull > N) return S5_OK;
-  out->K = K; out->N = N; out->x_stride = Kfull; out->y_stride = Nfull;
-  S5_CUDA(cudaMalloc(&out->Wh, wh.size() * sizeof(__half)));
-  S5_CUDA(cudaMemcpy(out->Wh, wh.data(), wh.size() * sizeof(__half), cudaMemcpyHostToDevice));
+  }
+  out->Kfull = Kfull; out->Nfull = Nfull; out->Kp[0] = Kp[0]; out->Kp[1] = Kp[1]; out->Np = Np; out->KV = KV;
+  for (int o = 0; o < 2; ++o) {
+    S5_CUDA(cudaMalloc(&out->W8[o], w8[o].size()));
+    S5_CUDA(cudaMemcpy(out->W8[o], w8[o].data(), w8[o].size(), cudaMemcpyHostToDevice));
+  }
   int rc;
   if ((rc = upload_f(cs, &out->col_scale))) return rc;
-  if (!wk.empty() && (rc = upload_f(wk, &out->w_extra_k))) return rc;
-  if (!wn.empty() && (rc = upload_f(wn, &out->w_extra_n))) return rc;
   out->ok = true;
   return S5_OK;
 }
 
 void tc_linear_free(TcLinearDev* d) {
-  cudaFree(d->Wh); cudaFree(d->col_scale); cudaFree(d->w_extra_k); cudaFree(d->w_extra_n);
+  cudaFree(d->W8[0]); cudaFree(d->W8[1]); cudaFree(d->col_scale);
   *d = TcLinearDev();
+}
+
+template <bool VEC4, int KV, bool BN>
+static int tc_linear_go(const TcLinParams& p0, int kclass, cudaStream_t st) {
+  TcLinParams p = p0;
+  auto kernel = tc_linear_kernel<VEC4, KV, BN>;
+  const size_t w_bytes = tc_tile_bytes8(p.Np, p.Kp), a2 = 2 * tc_tile_bytes8(kTcRows, p.Kp);
+  // output columns per pass: as wide as possible while two CTAs (2 x 8 warps, 2 x 256 TMEM columns) share an SM
+  size_t smem = 0;
+  for (int NP : {128, 64, 32, 16}) {
+    p.NP = std::min(NP, p.Np);
+    p.alias_out = p.NP >= p.Np;
+    const size_t out_bytes = (size_t)kTcRows * (p.NP + 4) * 4;
+    smem = w_bytes + (p.alias_out ? std::max(a2, out_bytes) : a2 + out_bytes) + (size_t)p.Np * sizeof(float2);
+    if (2 * (smem + 1024 + 64) <= 227 * 1024) break;
+  }
+  if (smem + 64 > 227 * 1024) S5_FAIL(S5_E_BADSHAPE, "dense-tile linear: tile does not fit in shared memory");
+  S5_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  S5_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  const int per_sm = 2 * (smem + 1024 + 64) <= 227 * 1024 ? 2 : 1;
+  const long long ntiles = (p.rows + kTcRows - 1) / kTcRows;
+  const int grid = (int)std::max<long long>(1, std::min<long long>(ntiles, (long long)per_sm * sm_count()));
+  ProfScope prof(kclass, st);
+  kernel<<<grid, kTcThreads, smem, st>>>(p);
+  S5_LAUNCH_CHECK();
+  return S5_OK;
 }
 
 int tc_linear_launch(const TcLinearDev& d, const float* X, float* Y, long long rows, const float* in_sub, const float* in_mul,
@@ -572,34 +621,22 @@ int tc_linear_launch(const TcLinearDev& d, const float* X, float* Y, long long r
                      float out_scale1, float out_qmin, float out_qmax, int relu, int kclass, cudaStream_t st) {
   if (!d.ok || !is_pow2(in_scale) || !is_pow2(out_scale0) || !is_pow2(out_scale1)) S5_FAIL(S5_E_BADARG, "dense-tile linear: not eligible");
   TcLinParams p{};
-  p.X = X; p.Y = Y; p.rows = rows; p.K = d.K; p.N = d.N; p.x_stride = d.x_stride; p.y_stride = d.y_stride; p.Wh = d.Wh;
+  p.X = X; p.Y = Y; p.rows = rows; p.Kfull = d.Kfull; p.Nfull = d.Nfull; p.Np = d.Np;
+  p.x_stride = d.Kfull; p.y_stride = d.Nfull;
   p.in_sub = in_sub; p.in_mul = in_mul; p.in_add = in_add; p.in_inv = 1.0f / in_scale; p.in_qmin = in_qmin; p.in_qmax = in_qmax;
   p.col_scale = d.col_scale; p.bias = bias; p.out_scale0 = out_scale0; p.out_scale1 = out_scale1;
   p.out_inv0 = 1.0f / out_scale0; p.out_inv1 = 1.0f / out_scale1;
-  p.out_qmin = out_qmin; p.out_qmax = out_qmax; p.relu = relu; p.w_extra_k = d.w_extra_k; p.w_extra_n = d.w_extra_n;
-  const int NC = d.N > 128 ? 128 : d.N;
-  size_t smem = tc_tile_bytes(d.N, d.K) + std::max(2 * tc_tile_bytes(kTcRows, d.K), (size_t)kTcRows * (NC + 4) * 4);
-  const uint32_t lo_col = d.N <= 128 ? 128 : 256;
-  const uint32_t cols = 2 * lo_col;
-  // TMEM has 512 columns per SM: never let more CTAs become resident than can allocate their accumulators
-  const int tmem_ctas = (int)(512 / cols);
-  smem = std::max(smem, (size_t)(227 * 1024) / (tmem_ctas + 1) + 1024);
-  const bool vec4 = (d.x_stride & 3) == 0 && aligned16(X) && d.K <= 256;
-  auto kernel = vec4 ? tc_linear_kernel<true> : tc_linear_kernel<false>;
-  S5_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  S5_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  int per_sm = tc_ctas_per_sm(reinterpret_cast<const void*>(kernel), smem, tmem_ctas);
-  // 16 warps per SM either way: two 8-warp CTAs when two fit (shared memory, TMEM), else one 16-warp CTA
-  const int NCp = d.N > 128 ? 128 : d.N;
-  const bool wide_ok = (NCp % 32) == 0;   // 4 column groups of whole 8-column chunks
-  const int threads = (per_sm >= 2 || !wide_ok) ? kTcThreads : 512;
-  if (threads == 512) per_sm = 1;
-  const long long ntiles = (rows + kTcRows - 1) / kTcRows;
-  const int grid = (int)std::max<long long>(1, std::min<long long>(ntiles, (long long)per_sm * sm_count()));
-  ProfScope prof(kclass, st);
-  kernel<<<grid, threads, smem, st>>>(p, cols, lo_col);
-  S5_LAUNCH_CHECK();
-  return S5_OK;
+  p.out_qmin = out_qmin; p.out_qmax = out_qmax; p.relu = relu;
+  const bool vec4 = (d.Kfull & 3) == 0 && aligned16(X);
+  p.W8 = d.W8[vec4 ? 0 : 1];
+  p.Kp = d.Kp[vec4 ? 0 : 1];
+  const bool bn = in_sub != nullptr;
+  if (d.KV == 1) {
+    if (vec4) return bn ? tc_linear_go<true, 1, true>(p, kclass, st) : tc_linear_go<true, 1, false>(p, kclass, st);
+    return bn ? tc_linear_go<false, 1, true>(p, kclass, st) : tc_linear_go<false, 1, false>(p, kclass, st);
+  }
+  if (vec4) return bn ? tc_linear_go<true, 2, true>(p, kclass, st) : tc_linear_go<true, 2, false>(p, kclass, st);
+  return bn ? tc_linear_go<false, 2, true>(p, kclass, st) : tc_linear_go<false, 2, false>(p, kclass, st);
 }
 
 

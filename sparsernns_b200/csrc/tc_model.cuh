@@ -7,9 +7,9 @@
 namespace s5 {
 
 struct TcLinearDev {
-  int K = 0, N = 0, x_stride = 0, y_stride = 0;
-  __half* Wh = nullptr;
-  float* col_scale = nullptr; float* w_extra_k = nullptr; float* w_extra_n = nullptr;
+  int Kfull = 0, Nfull = 0, Kp[2] = {0, 0}, Np = 0, KV = 0;
+  signed char* W8[2] = {nullptr, nullptr};   // int8 codes [Np][Kp]: K in natural order / in the lane-interleaved order
+  float* col_scale = nullptr;
   bool ok = false;
 };
 

@@ -281,8 +281,12 @@ class BoundModel:
                                                 ws.data_ptr(), need, self._stream()), "s5b200_ssm_forward")
         return y, t.view_as_complex(xs)
 
-    def forward_host(self, x_host, out=None):
-        """End-to-end call on HOST buffers (CPU tensors, ideally pinned): H2D, forward, D2H, synchronous."""
+    def forward_host(self, x_host, out=None, sync=True):
+        """End-to-end call on HOST buffers (CPU tensors, ideally pinned): H2D, forward, D2H.
+
+        ``sync=True`` returns when ``out`` is complete.  ``sync=False`` is stream-ordered like any CUDA call: it returns
+        after enqueueing and ``out`` is complete after the current stream has been synchronised; keep ``x_host`` and
+        ``out`` alive (and unmodified) until then.  Back-to-back calls then overlap across batches."""
         t = self._torch
         if not (isinstance(x_host, t.Tensor) and not x_host.is_cuda and x_host.dtype == t.float32 and x_host.dim() == 3):
             raise ValueError("expected a float32 CPU tensor of shape (B, L, d_input)")
@@ -290,8 +294,8 @@ class BoundModel:
         B, L, _ = x_host.shape
         if out is None:
             out = t.empty((B, L, self.cfg.d_output), dtype=t.float32, pin_memory=True)
-        _abi.check(self._lib.s5b200_model_forward_host(self._handle, x_host.data_ptr(), out.data_ptr(), B, L,
-                                                       self._stream()), "s5b200_model_forward_host")
+        fn = self._lib.s5b200_model_forward_host if sync else self._lib.s5b200_model_forward_host_async
+        _abi.check(fn(self._handle, x_host.data_ptr(), out.data_ptr(), B, L, self._stream()), "s5b200_model_forward_host")
         return out
 
 

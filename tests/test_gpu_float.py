@@ -148,3 +148,12 @@ def test_forward_host_matches_device_path(cuda_device, zoo):
     y_dev = m(x.to(cuda_device)).cpu()
     y_host = m.forward_host(x.pin_memory())
     assert torch.equal(y_dev, y_host)
+    # stream-ordered form: several batches in flight (more chunks than pipeline slots), complete after a stream sync
+    xp = [x.pin_memory(), torch.flip(x, dims=[0]).contiguous().pin_memory()]
+    outs = [torch.full_like(y_host, float("nan")).pin_memory() for _ in range(6)]
+    for i, o in enumerate(outs):
+        m.forward_host(xp[i % 2], out=o, sync=False)
+    torch.cuda.current_stream().synchronize()
+    y_flip = m(xp[1].to(cuda_device)).cpu()
+    for i, o in enumerate(outs):
+        assert torch.equal(o, y_host if i % 2 == 0 else y_flip)
