@@ -15,7 +15,7 @@ struct TcLinearDev {
 
 struct TcGluDev {
   int H = 0, K1 = 0; size_t smem = 0;
-  void* Wc = nullptr; void* Wo = nullptr;   // bf16 [H][2P] and f16 [H][H] weight codes
+  void* Wc = nullptr; void* Wo = nullptr;   // bf16 [H][2P] and int8 [H][128] (lane-interleaved K) weight codes
   float xs_odd_mul = 1.f, c_scale = 1.f, o_col_scale = 1.f;
   bool ok = false;
 };
