@@ -33,8 +33,13 @@ def _sources():
     return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
 
 
+def _extra_flags():
+    return os.environ.get("S5B200_NVCC_FLAGS", "").split()   # e.g. -DS5_TC_TRACE (phase timeline printf, debugging)
+
+
 def _digest() -> str:
     h = hashlib.sha256()
+    h.update(" ".join(_extra_flags()).encode())
     for f in sorted(os.listdir(CSRC)) + ["../../include/s5b200.h"]:
         with open(os.path.join(CSRC, f), "rb") as fh:
             h.update(f.encode())
@@ -53,7 +58,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     logs = []
     for src in _sources():
         obj = os.path.join(LIBDIR, os.path.basename(src)[:-3] + ".o")
-        cmd = [nvcc, *ARCH, *FLAGS, "-c", src, "-o", obj]
+        cmd = [nvcc, *ARCH, *FLAGS, *_extra_flags(), "-c", src, "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         logs.append(f"$ {' '.join(cmd)}\n{r.stdout}{r.stderr}")
         if r.returncode != 0:

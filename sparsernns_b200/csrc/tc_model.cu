@@ -23,6 +23,29 @@
 
 namespace s5 {
 
+// -DS5_TC_TRACE: thread 0 of CTA 0 prints the phase timeline (ns, %globaltimer) of its second tile; debugging only
+#ifdef S5_TC_TRACE
+#include <cstdio>
+__device__ int g_trace_budget = 12;
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define TC_TRACE_DECL unsigned long long tr_[12]; int tr_n = 0; int tr_tile = 0; const unsigned long long tr_entry = tr_t0_; unsigned long long tr_loop = gtime();
+#define TC_TRACE_ENTRY const unsigned long long tr_t0_ = gtime();
+#define TC_TRACE_MARK(cond) do { if ((cond) && blockIdx.x == 0 && tr_tile == 1 && tr_n < 12) tr_[tr_n++] = gtime(); } while (0)
+#define TC_TRACE_NEXT() do { ++tr_tile; } while (0)
+#define TC_TRACE_PRINT(cond, name) do { if ((cond) && blockIdx.x == 0 && tr_n > 1 && atomicSub(&g_trace_budget, 1) > 0) { \
+    printf("[trace %s] prologue %llu total %llu tiles %d |", name, tr_loop - tr_entry, gtime() - tr_entry, tr_tile); for (int i_ = 1; i_ < tr_n; ++i_) printf(" %llu", tr_[i_] - tr_[i_ - 1]); printf(" ns\n"); } } while (0)
+#else
+#define TC_TRACE_DECL
+#define TC_TRACE_ENTRY
+#define TC_TRACE_MARK(cond)
+#define TC_TRACE_NEXT()
+#define TC_TRACE_PRINT(cond, name)
+#endif
+
 constexpr int kTcThreads = 256;
 constexpr int kTcRows = 128;
 constexpr int kTcKI = 8;  // K <= 256: each lane stages at most 8 input columns
@@ -124,6 +147,7 @@ __device__ __forceinline__ void tc_issue8(uint32_t d_tmem, const void* A, const 
 // permutation is baked into W8 by the host), so that the four codes of a lane still form one 32-bit store.
 template <bool VEC4, int KV, bool BN>
 __global__ void __launch_bounds__(kTcThreads, 2) tc_linear_kernel(TcLinParams p) {
+  TC_TRACE_ENTRY
   extern __shared__ __align__(128) unsigned char smem[];
   const int Kp = p.Kp, Np = p.Np, NP = p.NP;
   const size_t a_bytes = tc_tile_bytes8(kTcRows, Kp);
@@ -151,54 +175,64 @@ __global__ void __launch_bounds__(kTcThreads, 2) tc_linear_kernel(TcLinParams p)
     cst[n] = n < p.Nfull ? make_float2(p.col_scale[n] * inv, p.bias ? p.bias[n] * inv : 0.f) : make_float2(0.f, 0.f);
   }
   const uint32_t lbo = tc_lbo(kTcRows);
-  // per-lane staging constants
+  // per-lane staging constants.  Loads are never predicated (a predicated LDG costs three extra instructions):
+  // rows beyond the end are clamped to the last row, columns beyond Kfull to the last column; what they produce
+  // is multiplied by zero weights (pad columns of W8) or never written out (pad rows).
   float sub[KV][4], mul[KV][4], add[KV][4];
-  bool kval[KV][4];
+  int koff[KV][4];
+  bool wval[KV];
   uint32_t loff[KV];
 #pragma unroll
   for (int i = 0; i < KV; ++i) {
     loff[i] = (uint32_t)(8 * i + (lane >> 2)) * lbo + 4u * (lane & 3);
+    wval[i] = 128 * i + 4 * lane < Kp;                        // the lane's 32-bit word lies inside the tile
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const int k = VEC4 ? 128 * i + 4 * lane + e : 128 * i + lane + 32 * e;
-      kval[i][e] = k < p.Kfull;
-      sub[i][e] = (BN && kval[i][e]) ? p.in_sub[k] : 0.f;
-      mul[i][e] = (BN && kval[i][e]) ? p.in_mul[k] : 1.f;
-      add[i][e] = (BN && kval[i][e]) ? p.in_add[k] : 0.f;
+      const bool in = k < p.Kfull;
+      koff[i][e] = in ? k : (VEC4 ? e : p.Kfull - 1);
+      sub[i][e] = (BN && in) ? p.in_sub[k] : 0.f;
+      mul[i][e] = (BN && in) ? p.in_mul[k] : 1.f;
+      add[i][e] = (BN && in) ? p.in_add[k] : 0.f;
     }
   }
   const bool tail = p.Kfull > 128 * KV;                       // one more input column (encoder: 257 = 2 * 128 + 1)
-  const int erow = (warp & 3) * 32 + lane;                    // epilogue: TMEM lane = row
-  const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+  const float inv = p.in_inv, qmin = p.in_qmin, qmax = p.in_qmax;
+  const float oqmin = p.relu ? fmaxf(p.out_qmin, 0.f) : p.out_qmin, oqmax = p.out_qmax, os0 = p.out_scale0, os1 = p.out_scale1;
+  const int erow0 = (warp & 3) * 32, erow = erow0 + lane;     // epilogue: TMEM lane = row
+  const uint32_t lane_base = (uint32_t)erow0 << 16;
   const int egrp = warp >> 2;                                 // column half of a pass
   const bool wvec = (p.y_stride & 3) == 0 && (NP & 3) == 0 && (p.Nfull & 3) == 0 &&
                     (reinterpret_cast<uintptr_t>(p.Y) & 15) == 0;
   uint32_t phase = 0;
-  const long long ntiles = (p.rows + kTcRows - 1) / kTcRows;
+  TC_TRACE_DECL
   __syncthreads();
-  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const long long row0 = tile * kTcRows;
-    const int rv = (int)min((long long)kTcRows, p.rows - row0);
+  // Balanced partition: every CTA owns one contiguous row range (full tiles plus one short tile whose row loops and
+  // TMEM passes stop at its last row) instead of a whole number of 128-row tiles.
+  const long long row_begin = p.rows * blockIdx.x / gridDim.x, row_end = p.rows * (blockIdx.x + 1) / gridDim.x;
+  for (long long row0 = row_begin; row0 < row_end; row0 += kTcRows) {
+    const int rv = (int)min((long long)kTcRows, row_end - row0);
+    TC_TRACE_MARK(tid == 0);
     // ---- stage: RB rows are loaded before any of them is converted so that every lane keeps many loads in flight
     constexpr int RB = 8 / KV;
-    for (int rb = warp * RB; rb < kTcRows; rb += NW * RB) {
+    const long long last_row = p.rows - 1;
+    for (int rb = warp * RB; rb < rv; rb += NW * RB) {
       float raw[RB][KV][4];
       float rawt[RB];
 #pragma unroll
       for (int q = 0; q < RB; ++q) {
-        const bool rin = rb + q < rv;
-        const float* xr = p.X + (size_t)(row0 + rb + q) * p.x_stride;
+        const float* xr = p.X + (size_t)min(row0 + rb + q, last_row) * p.x_stride;
 #pragma unroll
         for (int i = 0; i < KV; ++i) {
           if constexpr (VEC4) {
-            const float4 v = (rin && kval[i][0]) ? *reinterpret_cast<const float4*>(xr + 128 * i + 4 * lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 v = *reinterpret_cast<const float4*>(xr + koff[i][0]);
             raw[q][i][0] = v.x; raw[q][i][1] = v.y; raw[q][i][2] = v.z; raw[q][i][3] = v.w;
           } else {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) raw[q][i][e] = (rin && kval[i][e]) ? xr[128 * i + lane + 32 * e] : 0.f;
+            for (int e = 0; e < 4; ++e) raw[q][i][e] = xr[koff[i][e]];
           }
         }
-        rawt[q] = (tail && rin && lane == 0) ? xr[128 * KV] : 0.f;
+        rawt[q] = tail ? xr[128 * KV] : 0.f;                  // same address in every lane: one broadcast load
       }
 #pragma unroll
       for (int q = 0; q < RB; ++q) {
@@ -210,26 +244,28 @@ __global__ void __launch_bounds__(kTcThreads, 2) tc_linear_kernel(TcLinParams p)
           for (int e = 0; e < 4; ++e) {
             float v = raw[q][i][e];
             if constexpr (BN) v = (v - sub[i][e]) * mul[i][e] + add[i][e];
-            b[e] = kval[i][e] ? quant_bits(v, p.in_inv, p.in_qmin, p.in_qmax) : 0u;
+            b[e] = quant_bits(v, inv, qmin, qmax);
           }
           uint32_t lo, hi;
           split_planes(b[0], b[1], b[2], b[3], lo, hi);
-          if (kval[i][0]) {   // element 0 is the lowest k of the lane in both orders: no valid element without it
+          if (wval[i]) {
             *reinterpret_cast<uint32_t*>(Ah + loff[i] + roff) = hi;
             *reinterpret_cast<uint32_t*>(Al + loff[i] + roff) = lo;
           }
         }
         if (tail && lane == 0) {
-          const uint32_t bt = quant_bits(rawt[q], p.in_inv, p.in_qmin, p.in_qmax);
+          const uint32_t bt = quant_bits(rawt[q], inv, qmin, qmax);
           *reinterpret_cast<uint32_t*>(Ah + (size_t)(8 * KV) * lbo + roff) = (bt >> 8) & 0xFFu;
           *reinterpret_cast<uint32_t*>(Al + (size_t)(8 * KV) * lbo + roff) = bt & 0xFFu;
         }
       }
     }
+    TC_TRACE_MARK(tid == 0);
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    TC_TRACE_MARK(tid == 0);
     const uint32_t taddr = tmem_slot;
     if (tid == 0) {
       const int np = min(NP, Np);
@@ -243,9 +279,10 @@ __global__ void __launch_bounds__(kTcThreads, 2) tc_linear_kernel(TcLinParams p)
       mbar_wait(&bar, phase);
       phase ^= 1;
       tc_fence_after();
+      TC_TRACE_MARK(tid == 0);
       // ---- epilogue: exact integer recombination, scale, bias, fake-quant, ReLU -> shared tile
       const int cw = np >> 1;
-      for (int c0 = egrp * cw; c0 < (egrp + 1) * cw; c0 += 8) {
+      for (int c0 = egrp * cw; c0 < (erow0 < rv ? (egrp + 1) * cw : 0); c0 += 8) {
         uint32_t vh[8], vl[8];
         tc_ld8(taddr + lane_base + c0, vh);
         tc_ld8(taddr + lane_base + 128 + c0, vl);
@@ -256,17 +293,18 @@ __global__ void __launch_bounds__(kTcThreads, 2) tc_linear_kernel(TcLinParams p)
           const float4 c2 = *reinterpret_cast<const float4*>(cst + pass0 + c0 + j);   // (a, b) of two columns
           const float f0 = __int2float_rn((int)vh[j] * 256 + (int)vl[j]);
           const float f1 = __int2float_rn((int)vh[j + 1] * 256 + (int)vl[j + 1]);
-          float o0 = round_clip(fmaf(f0, c2.x, c2.y), p.out_qmin, p.out_qmax) * p.out_scale0;
-          float o1 = round_clip(fmaf(f1, c2.z, c2.w), p.out_qmin, p.out_qmax) * p.out_scale1;
-          out[j] = p.relu ? fmaxf(o0, 0.f) : o0;
-          out[j + 1] = p.relu ? fmaxf(o1, 0.f) : o1;
+          // ReLU after the fake-quant = lower clip bound raised to zero
+          out[j] = round_clip(fmaf(f0, c2.x, c2.y), oqmin, oqmax) * os0;
+          out[j + 1] = round_clip(fmaf(f1, c2.z, c2.w), oqmin, oqmax) * os1;
         }
         float* dst = outT + (size_t)erow * ld_out + c0;
         *reinterpret_cast<float4*>(dst) = make_float4(out[0], out[1], out[2], out[3]);
         *reinterpret_cast<float4*>(dst + 4) = make_float4(out[4], out[5], out[6], out[7]);
       }
+      TC_TRACE_MARK(tid == 0);
       tc_fence_before();
       __syncthreads();                                        // tile complete; TMEM and (last pass) the planes are free
+      TC_TRACE_MARK(tid == 0);
       if (tid == 0 && pass0 + NP < Np) {                      // next pass overlaps the write-out below
         tc_fence_after();
         const int np2 = min(NP, Np - pass0 - NP);
@@ -274,31 +312,46 @@ __global__ void __launch_bounds__(kTcThreads, 2) tc_linear_kernel(TcLinParams p)
         tc_issue8(taddr + 128, Al, Wt + (size_t)(pass0 + NP) * 16, Kp, np2, Np, false);
         tc_commit(&bar);
       }
-      // ---- write-out, coalesced
+      // ---- write-out, coalesced.  (One bulk copy per row through the TMA engine was measured 3-4x slower: ~50 ns per
+      // 512-byte copy, 128 copies per tile.)
       if (wvec) {
         const int q4 = npv >> 2;                              // float4 per row
         const int rpi = q4 >= 32 ? 1 : 32 / q4;               // rows per warp iteration
         const int lr = lane / q4, lc = lane - lr * q4;
-        if (q4 <= 32) {
-          if (lr < rpi)
-            for (int r = warp * rpi + lr; r < rv; r += NW * rpi)
-              *reinterpret_cast<float4*>(p.Y + (size_t)(row0 + r) * p.y_stride + pass0 + 4 * lc) =
-                  *reinterpret_cast<const float4*>(outT + (size_t)r * ld_out + 4 * lc);
+        if (lr < rpi) {
+          for (int rb = warp * rpi + lr; rb < rv; rb += 4 * NW * rpi) {   // four rows in flight per lane
+            float4 v[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) v[q] = *reinterpret_cast<const float4*>(outT + (size_t)min(rb + q * NW * rpi, kTcRows - 1) * ld_out + 4 * lc);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              if (rb + q * NW * rpi < rv)
+                *reinterpret_cast<float4*>(p.Y + (size_t)(row0 + rb + q * NW * rpi) * p.y_stride + pass0 + 4 * lc) = v[q];
+          }
         }
       } else {
-        for (int r = warp; r < rv; r += NW) {
-          float* yr = p.Y + (size_t)(row0 + r) * p.y_stride + pass0;
-          const float* src = outT + (size_t)r * ld_out;
+        // unaligned rows (decoder, 257 floats): 4-byte stores, lanes along columns, four rows in flight per warp
+        for (int rb = warp * 4; rb < rv; rb += NW * 4) {
+          float v[4][4];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int n = lane + 32 * j;
-            if (n < npv) yr[n] = src[n];
+          for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[q][j] = outT[(size_t)(rb + q) * ld_out + lane + 32 * j];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float* yr = p.Y + (size_t)(row0 + rb + q) * p.y_stride + pass0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (rb + q < rv && lane + 32 * j < npv) yr[lane + 32 * j] = v[q][j];
           }
         }
       }
       __syncthreads();                                        // output tile free again
+      TC_TRACE_MARK(tid == 0);
     }
+    TC_TRACE_NEXT();
   }
+  TC_TRACE_PRINT(tid == 0, BN ? "linear bn: stage sync mma epi sync writeout" : "linear: stage sync mma epi sync writeout [per pass: mma epi sync writeout]");
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tc_dealloc(tmem_slot, 256);
@@ -345,6 +398,7 @@ __device__ __forceinline__ uint32_t pack_bf2(float a, float b) {   // {lo half =
 //   P2 : lanes along columns: out = ReLU(l * sg + x), coalesced stores
 template <int HJ>
 __global__ void __launch_bounds__(kGluThreads, 1) tc_glu_kernel(TcGluParams p) {
+  TC_TRACE_ENTRY
   extern __shared__ __align__(128) unsigned char smem[];
   const int H = p.H, K1 = p.K1;
   const int ldT = H + 4;                                      // floats per row of T
@@ -377,39 +431,50 @@ __global__ void __launch_bounds__(kGluThreads, 1) tc_glu_kernel(TcGluParams p) {
   for (int n = tid; n < H; n += kGluThreads) ob[n] = p.o_bias[n] * p.oo_inv;
   // the int8 planes carry a zero pad byte per lane (column 4 lane + 3 when HJ < 4): clear them once
   for (size_t i = (size_t)htid * 16; i < 2 * a2_bytes; i += kGluHalf * 16) *reinterpret_cast<int4*>(A2h + i) = make_int4(0, 0, 0, 0);
-  // per-lane constants of the lanes-along-columns passes
-  float bsub[HJ], bmul[HJ], badd[HJ], dd[HJ];
+  // per-lane constants of the lanes-along-columns passes.  All scales are powers of two, so folding them into the
+  // BatchNorm / feed-through constants changes no rounding: (x - sub) * (mul / s_u) + add / s_u == BN(x) / s_u.
+  float bsub[HJ], bmulq[HJ], baddq[HJ], ddq[HJ];
 #pragma unroll
   for (int j = 0; j < HJ; ++j) {
     const int c = lane + 32 * j;
     bsub[j] = p.bn_sub ? p.bn_sub[c] : 0.f;
-    bmul[j] = p.bn_sub ? p.bn_mul[c] : 1.f;
-    badd[j] = p.bn_sub ? p.bn_add[c] : 0.f;
-    dd[j] = p.D[c];
+    bmulq[j] = (p.bn_sub ? p.bn_mul[c] : 1.f) * p.ut_inv;
+    baddq[j] = (p.bn_sub ? p.bn_add[c] : 0.f) * p.ut_inv;
+    ddq[j] = p.D[c] * p.ut_s * p.yt_inv;                      // D u / s_y = (D s_u / s_y) * code(u)
   }
+  const float k_c = p.c_scale * p.yt_inv;                     // conj Re(C x) / s_y = acc * k_c
+  const float a_o = p.o_col_scale * p.oo_inv;
+  const float k_e = -p.oo_s * 1.4426950408889634f;            // exp(-o) = 2^(code(o) * k_e)
   const bool kin = 4 * lane < K1;
+  const int xs_col = kin ? 4 * lane : 0;                      // loads are never predicated: pad lanes / rows re-read valid data
+  const long long last_row = p.rows - 1;
   const uint32_t lbo = tc_lbo(kTcRows);
   const uint32_t soff = (uint32_t)(lane >> 1) * lbo + (uint32_t)(lane & 1) * 8u;   // bf16 planes: k = 4 lane
   const uint32_t aoff = (uint32_t)(lane >> 2) * lbo + 4u * (lane & 3);             // int8 planes: bytes 4 lane .. 4 lane + 3
-  const int erow = (warp & 3) * 32 + lane;                    // TMEM lane = tile row
-  const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+  const int erow0 = (warp & 3) * 32;                          // first tile row of this warp's TMEM lane quadrant
+  const int erow = erow0 + lane;                              // TMEM lane = tile row
+  const uint32_t lane_base = (uint32_t)erow0 << 16;
   const int cw = H >> 1, cbeg = (warp >> 2) * cw;             // column half of this warp in the TMEM passes
   const float y_to_gl = p.yt_s * p.gl_inv, y_to_oa = p.yt_s * p.oa_inv;   // powers of two
-  const float qrelu_min = fmaxf(p.qs_min, 0.f);
+  const float qs_min = p.qs_min, qs_max = p.qs_max, qn_min = p.qn_min, qn_max = p.qn_max;
+  const float qrelu_min = fmaxf(qs_min, 0.f);
   uint32_t phase = 0;
+  TC_TRACE_DECL
   __syncthreads();
   const uint32_t tcol = tmem_slot + 256u * half;
-  const long long ntiles = (p.rows + kTcRows - 1) / kTcRows;
-  for (long long tile = (long long)blockIdx.x * 2 + half; tile < ntiles; tile += 2LL * gridDim.x) {
-    const long long row0 = tile * kTcRows;
-    const int rv = (int)min((long long)kTcRows, p.rows - row0);
+  // Balanced partition: every pipeline owns one contiguous row range (full tiles plus one short tile whose row loops
+  // and TMEM passes stop at its last row), instead of a whole number of 128-row tiles.
+  const long long npipe = 2LL * gridDim.x, pipe = 2LL * blockIdx.x + half;
+  const long long row_begin = p.rows * pipe / npipe, row_end = p.rows * (pipe + 1) / npipe;
+  for (long long row0 = row_begin; row0 < row_end; row0 += kTcRows) {
+    const int rv = (int)min((long long)kTcRows, row_end - row0);
+    TC_TRACE_MARK(tid == 0);
     // ---- S: xs -> two bf16 planes (value = hi + lo to 16 mantissa bits); 8 rows in flight per lane
-    for (int rb = warp * 8; rb < kTcRows; rb += NW * 8) {
+    for (int rb = warp * 8; rb < rv; rb += NW * 8) {
       float4 raw[8];
 #pragma unroll
       for (int q = 0; q < 8; ++q)
-        raw[q] = (kin && rb + q < rv) ? *reinterpret_cast<const float4*>(p.XS + (size_t)(row0 + rb + q) * K1 + 4 * lane)
-                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+        raw[q] = *reinterpret_cast<const float4*>(p.XS + (size_t)min(row0 + rb + q, last_row) * K1 + xs_col);
       if (kin) {
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
@@ -427,53 +492,66 @@ __global__ void __launch_bounds__(kGluThreads, 1) tc_glu_kernel(TcGluParams p) {
     tc_fence_before();
     half_barrier(half);
     tc_fence_after();
+    TC_TRACE_MARK(tid == 0);
     if (htid == 0) {
       tc_issue(tcol, P1h, Wc, K1, H, false, true);
       tc_issue(tcol, P1l, Wc, K1, H, true, true);
       tc_commit(&bar[half]);
     }
+    // the block-input rows of the first P1 batch travel while the tensor core works
+    constexpr int PB = 8;                                     // rows per warp batch in the lanes-along-columns passes
+    float xin[PB][HJ];
+#pragma unroll
+    for (int q = 0; q < PB; ++q) {
+      const float* xr = p.X + (size_t)min(row0 + warp * PB + q, last_row) * H;
+#pragma unroll
+      for (int j = 0; j < HJ; ++j) xin[q][j] = xr[lane + 32 * j];
+    }
     mbar_wait(&bar[half], phase);
     phase ^= 1;
     tc_fence_after();
+    TC_TRACE_MARK(tid == 0);
     // ---- E1: raw accumulators -> T (the xs planes are dead)
-    for (int c0 = cbeg; c0 < cbeg + cw; c0 += 8) {
-      uint32_t v[8];
-      tc_ld8(tcol + lane_base + c0, v);
-      tc_wait_ld();
-      float* dst = T + (size_t)erow * ldT + c0;
-      *reinterpret_cast<uint4*>(dst) = make_uint4(v[0], v[1], v[2], v[3]);
-      *reinterpret_cast<uint4*>(dst + 4) = make_uint4(v[4], v[5], v[6], v[7]);
+    if (erow0 < rv) {
+      for (int c0 = cbeg; c0 < cbeg + cw; c0 += 8) {
+        uint32_t v[8];
+        tc_ld8(tcol + lane_base + c0, v);
+        tc_wait_ld();
+        float* dst = T + (size_t)erow * ldT + c0;
+        *reinterpret_cast<uint4*>(dst) = make_uint4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<uint4*>(dst + 4) = make_uint4(v[4], v[5], v[6], v[7]);
+      }
     }
     tc_fence_before();
     half_barrier(half);
-    // ---- P1: one warp per row, 4 rows in flight
-    for (int rb = warp * 4; rb < kTcRows; rb += NW * 4) {
-      float xin[4][HJ], tin[4][HJ];
+    TC_TRACE_MARK(tid == 0);
+    // ---- P1: one warp per row, PB rows in flight
+    for (int rb = warp * PB; rb < rv; rb += NW * PB) {
+      float tin[PB][HJ];
+      if (rb != warp * PB) {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const bool rin = rb + q < rv;
-        const float* xr = p.X + (size_t)(row0 + rb + q) * H;
+        for (int q = 0; q < PB; ++q) {
+          const float* xr = p.X + (size_t)min(row0 + rb + q, last_row) * H;
 #pragma unroll
-        for (int j = 0; j < HJ; ++j) {
-          xin[q][j] = rin ? xr[lane + 32 * j] : 0.f;
-          tin[q][j] = T[(size_t)(rb + q) * ldT + lane + 32 * j];
+          for (int j = 0; j < HJ; ++j) xin[q][j] = xr[lane + 32 * j];
         }
       }
+#pragma unroll
+      for (int q = 0; q < PB; ++q)
+#pragma unroll
+        for (int j = 0; j < HJ; ++j) tin[q][j] = T[(size_t)(rb + q) * ldT + lane + 32 * j];
       __syncwarp();   // every lane holds its raw values of these rows before the rows are overwritten with codes
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
+      for (int q = 0; q < PB; ++q) {
         const int r = rb + q;
         uint32_t ob4[4] = {0u, 0u, 0u, 0u};
         unsigned short* trow = reinterpret_cast<unsigned short*>(T + (size_t)r * ldT);
 #pragma unroll
         for (int j = 0; j < HJ; ++j) {
-          float u = (xin[q][j] - bsub[j]) * bmul[j] + badd[j];
-          u = round_clip(u * p.ut_inv, p.qs_min, p.qs_max) * p.ut_s;
-          const float y = tin[q][j] * p.c_scale + dd[j] * u;
-          const float cy = round_clip(y * p.yt_inv, qrelu_min, p.qs_max);          // code of x1 = ReLU(FQ(y)) on the y grid
-          const uint32_t lbits = __float_as_uint(fminf(fmaxf(cy * y_to_gl, p.qn_min), p.qn_max) + kRoundMagic);
-          trow[lane + 32 * j] = (unsigned short)lbits;                             // left-gate code (>= 0)
-          ob4[j] = __float_as_uint(fminf(fmaxf(cy * y_to_oa, p.qn_min), p.qn_max) + kRoundMagic);
+          const float uc = round_clip((xin[q][j] - bsub[j]) * bmulq[j] + baddq[j], qs_min, qs_max);   // code of u = FQ(BN(x))
+          const float cy = round_clip(fmaf(ddq[j], uc, tin[q][j] * k_c), qrelu_min, qs_max);          // code of x1 = ReLU(FQ(y))
+          trow[lane + 32 * j] = (unsigned short)__float_as_uint(fminf(cy * y_to_gl, qn_max) + kRoundMagic);   // left gate (>= 0)
+          ob4[j] = __float_as_uint(fminf(cy * y_to_oa, qn_max) + kRoundMagic);                        // out2 input code (>= 0)
         }
         uint32_t lo, hi;
         split_planes(ob4[0], ob4[1], ob4[2], ob4[3], lo, hi);
@@ -485,52 +563,67 @@ __global__ void __launch_bounds__(kGluThreads, 1) tc_glu_kernel(TcGluParams p) {
     tc_fence_before();
     half_barrier(half);
     tc_fence_after();
+    TC_TRACE_MARK(tid == 0);
     if (htid == 0) {
       tc_issue8(tcol, A2h, Wo, kGluK2, H, H, true);
       tc_issue8(tcol + 128, A2l, Wo, kGluK2, H, H, false);
       tc_commit(&bar[half]);
     }
+    // skip-connection rows of the first P2 batch (L2 hits) travel during the second product and E2
+#pragma unroll
+    for (int q = 0; q < PB; ++q) {
+      const float* xr = p.X + (size_t)min(row0 + warp * PB + q, last_row) * H;
+#pragma unroll
+      for (int j = 0; j < HJ; ++j) xin[q][j] = xr[lane + 32 * j];
+    }
     mbar_wait(&bar[half], phase);
     phase ^= 1;
     tc_fence_after();
+    TC_TRACE_MARK(tid == 0);
     // ---- E2: o = FQ(out2(x1)); right-gate code FQ(sigmoid(o)) -> second half of the T row
-    for (int c0 = cbeg; c0 < cbeg + cw; c0 += 8) {
-      uint32_t vh[8], vl[8];
-      tc_ld8(tcol + lane_base + c0, vh);
-      tc_ld8(tcol + lane_base + 128 + c0, vl);
-      tc_wait_ld();
-      uint32_t sb[8];
+    if (erow0 < rv) {
+      for (int c0 = cbeg; c0 < cbeg + cw; c0 += 8) {
+        uint32_t vh[8], vl[8];
+        tc_ld8(tcol + lane_base + c0, vh);
+        tc_ld8(tcol + lane_base + 128 + c0, vl);
+        tc_wait_ld();
+        uint32_t sb[8];
 #pragma unroll
-      for (int j = 0; j < 8; j += 4) {
-        const float4 b4 = *reinterpret_cast<const float4*>(ob + c0 + j);
-        const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+        for (int j = 0; j < 8; j += 4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(ob + c0 + j);
+          const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float f = __int2float_rn((int)vh[j + e] * 256 + (int)vl[j + e]);
-          const float o = round_clip(fmaf(f, p.o_col_scale * p.oo_inv, bb[e]), p.qn_min, p.qn_max) * p.oo_s;
-          // sigmoid with the SFU exponential and reciprocal: |error| ~ 2 ulp, far below the 2^-15 grid of FQ16 that follows
-          const float sg = __frcp_rn(1.0f + __expf(-o));
-          sb[j + e] = __float_as_uint(fminf(fmaxf(sg * p.gr_inv, p.qn_min), p.qn_max) + kRoundMagic);
+          for (int e = 0; e < 4; ++e) {
+            const float f = __int2float_rn((int)vh[j + e] * 256 + (int)vl[j + e]);
+            const float oc = round_clip(fmaf(f, a_o, bb[e]), qn_min, qn_max);                 // code of o = FQ(out2(x1))
+            // sigmoid with the SFU exponential and reciprocal (~2 ulp), far below the 2^-15 grid of the FQ16 that follows
+            float ex, sg;
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(oc * k_e));
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(sg) : "f"(1.0f + ex));
+            sb[j + e] = __float_as_uint(fminf(sg * p.gr_inv, qn_max) + kRoundMagic);           // right gate (> 0)
+          }
         }
+        uint4 pk;
+        pk.x = __byte_perm(sb[0], sb[1], 0x5410); pk.y = __byte_perm(sb[2], sb[3], 0x5410);
+        pk.z = __byte_perm(sb[4], sb[5], 0x5410); pk.w = __byte_perm(sb[6], sb[7], 0x5410);
+        *reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(T + (size_t)erow * ldT) + 2 * H + 2 * c0) = pk;
       }
-      uint4 pk;
-      pk.x = __byte_perm(sb[0], sb[1], 0x5410); pk.y = __byte_perm(sb[2], sb[3], 0x5410);
-      pk.z = __byte_perm(sb[4], sb[5], 0x5410); pk.w = __byte_perm(sb[6], sb[7], 0x5410);
-      *reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(T + (size_t)erow * ldT) + 2 * H + 2 * c0) = pk;
     }
     tc_fence_before();
     half_barrier(half);
+    TC_TRACE_MARK(tid == 0);
     // ---- P2: out = ReLU(FQ_gl(x1) * FQ(sigmoid) + x), coalesced
-    for (int rb = warp * 4; rb < rv; rb += NW * 4) {
-      float xin[4][HJ];
+    for (int rb = warp * PB; rb < rv; rb += NW * PB) {
+      if (rb != warp * PB) {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float* xr = p.X + (size_t)(row0 + rb + q) * H;
+        for (int q = 0; q < PB; ++q) {
+          const float* xr = p.X + (size_t)min(row0 + rb + q, last_row) * H;
 #pragma unroll
-        for (int j = 0; j < HJ; ++j) xin[q][j] = rb + q < rv ? xr[lane + 32 * j] : 0.f;
+          for (int j = 0; j < HJ; ++j) xin[q][j] = xr[lane + 32 * j];
+        }
       }
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
+      for (int q = 0; q < PB; ++q) {
         if (rb + q < rv) {
           const unsigned short* trow = reinterpret_cast<const unsigned short*>(T + (size_t)(rb + q) * ldT);
           float* yr = p.OUT + (size_t)(row0 + rb + q) * H;
@@ -540,14 +633,17 @@ __global__ void __launch_bounds__(kGluThreads, 1) tc_glu_kernel(TcGluParams p) {
             // codes are non-negative: int -> float through the magic constant (no conversion pipe)
             const float l = (__uint_as_float(0x4B400000u + trow[c]) - kRoundMagic) * p.gl_s;
             const float sg = (__uint_as_float(0x4B400000u + trow[H + c]) - kRoundMagic) * p.gr_s;
-            const float out = l * sg + xin[q][j];
+            const float out = fmaf(l, sg, xin[q][j]);
             yr[c] = p.relu_out ? fmaxf(out, 0.f) : out;
           }
         }
       }
     }
     half_barrier(half);   // T is free: the next tile's planes may overwrite it
+    TC_TRACE_MARK(tid == 0);
+    TC_TRACE_NEXT();
   }
+  TC_TRACE_PRINT(tid == 0, "glu: S+sync mma1 E1+sync P1+sync mma2 E2+sync P2+sync");
   tc_fence_before();
   __syncthreads();
   if (tid < 32) tc_dealloc(tmem_slot, 512);
@@ -646,19 +742,20 @@ static int tc_linear_go(const TcLinParams& p0, int kclass, cudaStream_t st) {
   const size_t w_bytes = tc_tile_bytes8(p.Np, p.Kp), a2 = 2 * tc_tile_bytes8(kTcRows, p.Kp);
   // output columns per pass: as wide as possible while two CTAs (2 x 8 warps, 2 x 256 TMEM columns) share an SM
   size_t smem = 0;
+  auto fits2 = [&](size_t b) { return 2 * (b + 1024 + 64) <= (size_t)227 * 1024; };
   for (int NP : {128, 64, 32, 16}) {
     p.NP = std::min(NP, p.Np);
-    p.alias_out = p.NP >= p.Np;
+    p.alias_out = p.NP >= p.Np;                               // single pass: the output tile reuses the dead planes
     const size_t out_bytes = (size_t)kTcRows * (p.NP + 4) * 4;
     smem = w_bytes + (p.alias_out ? std::max(a2, out_bytes) : a2 + out_bytes) + (size_t)p.Np * sizeof(float2);
-    if (2 * (smem + 1024 + 64) <= 227 * 1024) break;
+    if (fits2(smem)) break;
   }
   if (smem + 64 > 227 * 1024) S5_FAIL(S5_E_BADSHAPE, "dense-tile linear: tile does not fit in shared memory");
   S5_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   S5_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   const int per_sm = 2 * (smem + 1024 + 64) <= 227 * 1024 ? 2 : 1;
-  const long long ntiles = (p.rows + kTcRows - 1) / kTcRows;
-  const int grid = (int)std::max<long long>(1, std::min<long long>(ntiles, (long long)per_sm * sm_count()));
+  // rows are split evenly over the CTAs (balanced partition); at least 32 rows per CTA
+  const int grid = (int)std::max<long long>(1, std::min<long long>((p.rows + 31) / 32, (long long)per_sm * sm_count()));
   ProfScope prof(kclass, st);
   kernel<<<grid, kTcThreads, smem, st>>>(p);
   S5_LAUNCH_CHECK();
@@ -740,8 +837,8 @@ template <int HJ>
 static int tc_glu_go(const TcGluParams& p, size_t smem, cudaStream_t st) {
   auto kernel = tc_glu_kernel<HJ>;
   S5_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const long long ntiles = (p.rows + kTcRows - 1) / kTcRows;
-  const int grid = (int)std::max<long long>(1, std::min<long long>((ntiles + 1) / 2, (long long)sm_count()));
+  // rows are split evenly over 2 x grid pipelines (balanced partition); at least 32 rows per pipeline
+  const int grid = (int)std::max<long long>(1, std::min<long long>((p.rows + 63) / 64, (long long)sm_count()));
   ProfScope prof(S5_K_GLU, st);
   kernel<<<grid, kGluThreads, smem, st>>>(p);
   S5_LAUNCH_CHECK();
