@@ -328,6 +328,7 @@ struct s5_model {
   s5::SparseDev enc, dec;
   s5::TcLinearDev enc_tc, dec_tc;
   long long tc_min_rows = 4096;  // below this the compressed CUDA-core kernels are used
+  bool fuse_scan = true;         // static dense-tile path: run the recurrence inside the GLU kernel (S5B200_FUSE_SCAN=0 disables)
   float *enc_bias = nullptr, *dec_bias = nullptr;
   std::vector<s5::LayerDev> layers;
   // host-buffer entry point: ring of device buffers, three streams (H2D | forward | D2H) and their events
@@ -358,8 +359,9 @@ static WsLayout ws_layout(const s5_model* m, int B, int L) {
   w.off_a = 0;
   w.off_b = act;
   w.off_bu = 2 * act;
-  w.off_scan = w.off_bu + round_up(rows * m->desc.P * 2 * sizeof(float), 256);
-  w.scan_bytes = s5b200_scan_c64_workspace_bytes(B, L, m->desc.P);
+  // + 32 rows of slack: the fused recurrence reads whole 32-frame segments without clamping at the end of the buffer
+  w.off_scan = w.off_bu + round_up((rows + 32) * m->desc.P * 2 * sizeof(float), 256);
+  w.scan_bytes = std::max(s5b200_scan_c64_workspace_bytes(B, L, m->desc.P), tc_glu_scan_workspace_bytes(B, L, m->desc.P));
   w.total = w.off_scan + round_up(w.scan_bytes, 256);
   return w;
 }
@@ -407,7 +409,7 @@ static GluParams glu_params(const s5_model* m, const LayerDev& ld, const float* 
 
 // One S5 block: x [rows][H] -> out [rows][H]; bu is the [rows][P] complex scratch (Bu, then xs in place).
 static int run_block(const s5_model* m, int li, const float* x, float* out, float* bu, int B, int L, void* scan_ws,
-                     size_t scan_ws_bytes, bool bn, bool ssm_only, cudaStream_t st) {
+                     size_t scan_ws_bytes, bool bn, bool ssm_only, cudaStream_t st, bool want_xs = false) {
   const LayerDev& ld = m->layers[li];
   const long long rows = (long long)B * L;
   int rc;
@@ -419,11 +421,17 @@ static int run_block(const s5_model* m, int li, const float* x, float* out, floa
                                ld.sc.s_ut, qlo, qhi, nullptr, ld.sc.s_But_re, ld.sc.s_But_im, qlo, qhi, 0, S5_K_BPROJ, st)))
       return rc;
   } else if ((rc = launch_linear(bproj_params(m, ld, x, bu, rows, bn), st, S5_K_BPROJ))) return rc;
-  if ((rc = launch_scan_c64(bu, ld.lam, bu, B, L, m->desc.P, m->desc.relufication, scan_ws, scan_ws_bytes, st))) return rc;
-  if (sq && ld.tg.ok && !ssm_only && rows >= m->tc_min_rows && is_pow2(ld.sc.s_ut) && is_pow2(ld.sc.s_yt) &&
-      is_pow2(ld.sc.s_out2_act) && is_pow2(ld.sc.s_out2_out) && is_pow2(ld.sc.s_gate_left) && is_pow2(ld.sc.s_gate_right)) {
+  const bool glu_tc = sq && ld.tg.ok && !ssm_only && rows >= m->tc_min_rows && is_pow2(ld.sc.s_ut) && is_pow2(ld.sc.s_yt) &&
+                      is_pow2(ld.sc.s_out2_act) && is_pow2(ld.sc.s_out2_out) && is_pow2(ld.sc.s_gate_left) && is_pow2(ld.sc.s_gate_right);
+  // the recurrence runs inside the GLU kernel (states never leave the SM) unless the caller wants to see them
+  const bool fuse_scan = glu_tc && m->fuse_scan && !want_xs && tc_glu_scan_ok(ld.tg);
+  if (!fuse_scan && (rc = launch_scan_c64(bu, ld.lam, bu, B, L, m->desc.P, m->desc.relufication, scan_ws, scan_ws_bytes, st))) return rc;
+  if (glu_tc) {
     TcGluArgs a{};
     a.XS = bu; a.X = x; a.OUT = out; a.rows = rows;
+    if (fuse_scan) {
+      a.lam = ld.lam; a.B = B; a.L = L; a.relu_scan = m->desc.relufication; a.scan_ws = scan_ws; a.scan_ws_bytes = scan_ws_bytes;
+    }
     a.bn_sub = bn ? ld.bn_mean : nullptr; a.bn_mul = bn ? ld.bn_mul : nullptr; a.bn_add = bn ? ld.bn_bias : nullptr;
     a.D = ld.D; a.o_bias = ld.o_bias;
     a.s_ut = ld.sc.s_ut; a.s_yt = ld.sc.s_yt; a.s_o_act = ld.sc.s_out2_act; a.s_o_out = ld.sc.s_out2_out;
@@ -499,6 +507,7 @@ extern "C" int s5b200_model_create(const s5_model_desc* d, s5_model** out) {
   // S5B200_TC_MIN_ROWS: row count from which the dense-tile (tcgen05) kernels replace the compressed ones
   // (1 forces them, a huge value disables them); default 4096.
   if (const char* e = getenv("S5B200_TC_MIN_ROWS")) m->tc_min_rows = atoll(e);
+  if (const char* e = getenv("S5B200_FUSE_SCAN")) m->fuse_scan = atoi(e) != 0;
   const int H = d->H, P = d->P, dense = d->use_sparse ? 0 : 1;
   int rc = S5_OK;
   auto fail = [&](int code) { s5b200_model_destroy(m); return code; };
@@ -613,7 +622,7 @@ extern "C" int s5b200_layer_forward(const s5_model* m, int layer, const float* x
   unsigned char* base = reinterpret_cast<unsigned char*>(workspace);
   float* bu = xs_out ? xs_out : reinterpret_cast<float*>(base + w.off_bu);
   if (!aligned16(bu)) S5_FAIL(S5_E_BADARG, "layer_forward: xs_out must be 16-byte aligned");
-  return run_block(m, layer, x, y, bu, B, L, base + w.off_scan, w.scan_bytes, true, false, (cudaStream_t)stream);
+  return run_block(m, layer, x, y, bu, B, L, base + w.off_scan, w.scan_bytes, true, false, (cudaStream_t)stream, xs_out != nullptr);
 }
 
 extern "C" int s5b200_ssm_forward(const s5_model* m, int layer, const float* u, float* y, float* xs_out, int B, int L,

@@ -13,6 +13,7 @@
 //                      (ssm.py:332-337, 594-601; layers.py:217-238)
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "proj.cuh"
@@ -32,9 +33,9 @@ __device__ __forceinline__ unsigned long long gtime() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-#define TC_TRACE_DECL unsigned long long tr_[12]; int tr_n = 0; int tr_tile = 0; const unsigned long long tr_entry = tr_t0_; unsigned long long tr_loop = gtime();
+#define TC_TRACE_DECL unsigned long long tr_[16]; int tr_n = 0; int tr_tile = 0; const unsigned long long tr_entry = tr_t0_; unsigned long long tr_loop = gtime();
 #define TC_TRACE_ENTRY const unsigned long long tr_t0_ = gtime();
-#define TC_TRACE_MARK(cond) do { if ((cond) && blockIdx.x == 0 && tr_tile == 1 && tr_n < 12) tr_[tr_n++] = gtime(); } while (0)
+#define TC_TRACE_MARK(cond) do { if ((cond) && blockIdx.x == 0 && tr_tile == 1 && tr_n < 16) tr_[tr_n++] = gtime(); } while (0)
 #define TC_TRACE_NEXT() do { ++tr_tile; } while (0)
 #define TC_TRACE_PRINT(cond, name) do { if ((cond) && blockIdx.x == 0 && tr_n > 1 && atomicSub(&g_trace_budget, 1) > 0) { \
     printf("[trace %s] prologue %llu total %llu tiles %d |", name, tr_loop - tr_entry, gtime() - tr_entry, tr_tile); for (int i_ = 1; i_ < tr_n; ++i_) printf(" %llu", tr_[i_] - tr_[i_ - 1]); printf(" ns\n"); } } while (0)
@@ -373,7 +374,18 @@ struct TcGluParams {
   float ut_s, ut_inv, yt_s, yt_inv, oa_inv, oo_s, oo_inv, gl_s, gl_inv, gr_s, gr_inv;
   float qs_min, qs_max, qn_min, qn_max;
   int relu_out;
+  // fused recurrence (SCAN instantiation): XS holds Bu [B][L][P] complex64 and the kernel runs x_k = lam x_{k-1} + Bu_k itself
+  const float2* lam;           // [P]
+  int B, L, R, tiles_per_clip; // tile = R <= 128 consecutive frames of one clip
+  int relu_scan;               // lexicographic complex ReLU on the states handed to C (relufication)
+  uint32_t* flags;             // [B][tiles_per_clip] look-back flags (0 none, 1 aggregate, 2 inclusive prefix), zeroed per launch
+  float2* recs;                // [B][tiles_per_clip][2][P] aggregate / inclusive prefix
 };
+
+__device__ __forceinline__ float2 cmulf(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ float2 cfmaf(float2 a, float2 x, float2 v) {   // a * x + v
+  return make_float2(fmaf(a.x, x.x, fmaf(-a.y, x.y, v.x)), fmaf(a.x, x.y, fmaf(a.y, x.x, v.y)));
+}
 
 constexpr int kGluThreads = 512;   // two independent 256-thread tile pipelines per CTA that share the weight tiles
 constexpr int kGluHalf = 256;
@@ -396,7 +408,13 @@ __device__ __forceinline__ uint32_t pack_bf2(float a, float b) {   // {lo half =
 //   MMA2 (int8): acc2 = 256 (hi * Wo^T) + lo * Wo^T, exact
 //   E2 : o = FQ(out2) ; right-gate code FQ(sigmoid(o)) -> T (int16, second half of the row)
 //   P2 : lanes along columns: out = ReLU(l * sg + x), coalesced stores
-template <int HJ>
+//
+// SCAN: the S pass runs the diagonal recurrence itself.  A tile is R <= 128 consecutive frames of ONE clip, tiles are
+// handed out clip-fastest and round-robin over the pipelines; thread (state p, segment s) keeps its <= 32 Bu values in
+// registers, scans them twice (local aggregate, then with the true carry-in) and the carry across tiles of a clip
+// travels by decoupled look-back (aggregate / inclusive-prefix records + acquire / release flags in global memory).
+// The states never touch HBM: they go from registers straight into the bf16 operand planes of the C projection.
+template <int HJ, bool SCAN>
 __global__ void __launch_bounds__(kGluThreads, 1) tc_glu_kernel(TcGluParams p) {
   TC_TRACE_ENTRY
   extern __shared__ __align__(128) unsigned char smem[];
@@ -411,7 +429,12 @@ __global__ void __launch_bounds__(kGluThreads, 1) tc_glu_kernel(TcGluParams p) {
   unsigned char* Wo = Wc + wc_bytes;
   float* ob = reinterpret_cast<float*>(Wo + wo_bytes);        // [H] out2 bias / s_o_out
   const int tid = threadIdx.x, half = tid >> 8, htid = tid & (kGluHalf - 1), warp = htid >> 5, lane = tid & 31;
-  unsigned char* R = reinterpret_cast<unsigned char*>(ob) + (((size_t)H * 4 + 127) & ~(size_t)127) + (size_t)half * r_bytes;
+  unsigned char* Rbase = reinterpret_cast<unsigned char*>(ob) + (((size_t)H * 4 + 127) & ~(size_t)127);
+  unsigned char* R = Rbase + (size_t)half * r_bytes;
+  // SCAN: per pipeline, segment aggregates + multipliers [nseg][P] and the tile carry [P]
+  float2* seg_agg = reinterpret_cast<float2*>(Rbase + 2 * r_bytes) + (size_t)half * (2 * kGluHalf + 128);
+  float2* seg_mul = seg_agg + kGluHalf;
+  float2* carry_s = seg_mul + kGluHalf;
   unsigned char* P1h = R;                                     // xs planes (dead after MMA 1)
   unsigned char* P1l = R + p1_bytes;
   float* T = reinterpret_cast<float*>(R);                     // aliases the xs planes
@@ -462,13 +485,126 @@ __global__ void __launch_bounds__(kGluThreads, 1) tc_glu_kernel(TcGluParams p) {
   TC_TRACE_DECL
   __syncthreads();
   const uint32_t tcol = tmem_slot + 256u * half;
-  // Balanced partition: every pipeline owns one contiguous row range (full tiles plus one short tile whose row loops
-  // and TMEM passes stop at its last row), instead of a whole number of 128-row tiles.
+  // Without SCAN: balanced partition, every pipeline owns one contiguous row range (full tiles plus one short tile whose
+  // row loops and TMEM passes stop at its last row).  With SCAN: tile t = chunk * B + clip, pipeline g takes t = g, g + G, ...
   const long long npipe = 2LL * gridDim.x, pipe = 2LL * blockIdx.x + half;
-  const long long row_begin = p.rows * pipe / npipe, row_end = p.rows * (pipe + 1) / npipe;
-  for (long long row0 = row_begin; row0 < row_end; row0 += kTcRows) {
-    const int rv = (int)min((long long)kTcRows, row_end - row0);
+  const long long row_begin = SCAN ? 0 : p.rows * pipe / npipe, row_end = SCAN ? 0 : p.rows * (pipe + 1) / npipe;
+  const long long ntiles = SCAN ? (long long)p.B * p.tiles_per_clip : 0;
+  // SCAN per-thread constants: state, segment, lam and lam^R (full tiles) for the look-back
+  const int P = K1 >> 1;
+  const int sp = SCAN ? htid % P : 0, sseg = SCAN ? htid / P : 0, nseg = SCAN ? kGluHalf / P : 1;
+  const int sr = SCAN ? (p.R + nseg - 1) / nseg : 0;          // rows per segment (<= 32)
+  float2 lam = make_float2(0.f, 0.f), lamR = make_float2(1.f, 0.f), lamS = make_float2(1.f, 0.f);
+  if constexpr (SCAN) {
+    lam = p.lam[sp];
+    float2 sq = lam;                                          // lam^R (full tile) and lam^sr (full segment), binary powers
+    for (int bit = 0; bit < 8; ++bit) {
+      if ((p.R >> bit) & 1) lamR = cmulf(lamR, sq);
+      if ((sr >> bit) & 1) lamS = cmulf(lamS, sq);
+      sq = cmulf(sq, sq);
+    }
+  }
+  const float xs_odd_mul = p.xs_odd_mul;
+  const bool relu_scan = p.relu_scan != 0;
+  const float gl_s = p.gl_s, gr_s = p.gr_s, out_floor = p.relu_out ? 0.f : -INFINITY;
+  const uint32_t poff = (uint32_t)(sp >> 2) * lbo + 4u * (sp & 3);   // plane offset of column k = 2 sp
+  for (long long it = SCAN ? pipe : row_begin; SCAN ? it < ntiles : it < row_end; it += SCAN ? npipe : (long long)kTcRows) {
+    long long row0;
+    int rv;
+    int clip = 0, chunk = 0;
+    if constexpr (SCAN) {
+      chunk = (int)(it / p.B);
+      clip = (int)(it - (long long)chunk * p.B);
+      row0 = (long long)clip * p.L + (long long)chunk * p.R;
+      rv = min(p.R, p.L - chunk * p.R);
+    } else {
+      row0 = it;
+      rv = (int)min((long long)kTcRows, row_end - row0);
+    }
     TC_TRACE_MARK(tid == 0);
+    if constexpr (SCAN) {
+      // ---- S (fused recurrence): Bu -> registers -> local aggregate -> look-back -> states -> bf16 planes
+      const int len = max(0, min(sr, rv - sseg * sr));
+      const float2* bu = reinterpret_cast<const float2*>(p.XS) + (size_t)row0 * P + sp;
+      // 32 unpredicated, unclamped loads: rows past the segment are ignored, rows past the end of Bu fall into the
+      // slack the workspace layout keeps behind it
+      float2 v[32];
+      {
+        const float2* q = bu + (size_t)(sseg * sr) * P;
+#pragma unroll
+        for (int i = 0; i < 32; ++i, q += P) v[i] = *q;
+      }
+      float2 x = make_float2(0.f, 0.f), mm = lamS;
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (i < len) x = cfmaf(lam, x, v[i]);
+      if (len != sr) {                                        // short segment (end of a clip): lam^len
+        mm = make_float2(1.f, 0.f);
+        for (int i = 0; i < len; ++i) mm = cmulf(mm, lam);
+      }
+      seg_agg[sseg * P + sp] = x;
+      seg_mul[sseg * P + sp] = mm;
+      TC_TRACE_MARK(tid == 0);
+      half_barrier(half);
+      TC_TRACE_MARK(tid == 0);
+      if (htid < P) {                                          // carry threads: segment 0 of every state (whole warps)
+        float2 e = seg_agg[sp], M = seg_mul[sp];
+        for (int q = 1; q < nseg; ++q) {
+          e = cfmaf(seg_mul[q * P + sp], e, seg_agg[q * P + sp]);
+          M = cmulf(M, seg_mul[q * P + sp]);
+        }
+        uint32_t* flag_row = p.flags + (size_t)clip * p.tiles_per_clip;
+        float2* rec_row = p.recs + (size_t)clip * p.tiles_per_clip * 2 * P;
+        const bool publish = chunk + 1 < p.tiles_per_clip;    // nobody looks back at the last tile of a clip
+        float2 carry = make_float2(0.f, 0.f);
+        if (publish) {
+          __stcg(rec_row + ((size_t)chunk * 2 + (chunk == 0 ? 1 : 0)) * P + sp, e);   // tile 0: aggregate == inclusive prefix
+          // records -> barrier among the carry threads -> release store of the flag by one of them: the release is
+          // cumulative over the writes ordered before it by the barrier, no __threadfence needed
+          asm volatile("bar.sync %0, %1;" ::"r"(3 + half), "r"(P) : "memory");
+          if (htid == 0) st_release_u32(flag_row + chunk, chunk == 0 ? 2u : 1u);
+        }
+        if (chunk > 0) {
+          // decoupled look-back: walk the predecessors until one has published its inclusive prefix.  (Reading a window
+          // of 8 flags / records at once was measured slower: the extra live registers spill the 64 held Bu values.)
+          float2 mult = make_float2(1.f, 0.f);
+          for (int j = chunk - 1; j >= 0; --j) {
+            uint32_t f;
+            do {
+              f = ld_acquire_u32(flag_row + j);
+            } while (f == 0u);
+            const float2 w = __ldcg(rec_row + ((size_t)j * 2 + (f == 2u ? 1 : 0)) * P + sp);
+            carry = cfmaf(mult, w, carry);
+            if (f == 2u) break;
+            mult = cmulf(mult, lamR);
+          }
+          if (publish) {
+            __stcg(rec_row + ((size_t)chunk * 2 + 1) * P + sp, cfmaf(M, carry, e));
+              asm volatile("bar.sync %0, %1;" ::"r"(3 + half), "r"(P) : "memory");
+            if (htid == 0) st_release_u32(flag_row + chunk, 2u);
+          }
+        }
+        carry_s[sp] = carry;
+      }
+      TC_TRACE_MARK(tid == 0);
+      half_barrier(half);
+      TC_TRACE_MARK(tid == 0);
+      float2 cin = carry_s[sp];
+      for (int q = 0; q < sseg; ++q) cin = cfmaf(seg_mul[q * P + sp], cin, seg_agg[q * P + sp]);
+      x = cin;
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (i < len) {
+          x = cfmaf(lam, x, v[i]);
+          const bool keep = !relu_scan || (x.x > 0.f) || (x.x == 0.f && x.y > 0.f);
+          const float v0 = keep ? x.x : 0.f, v1 = keep ? x.y * xs_odd_mul : 0.f;
+          const uint32_t h01 = pack_bf2(v0, v1);
+          const uint32_t l01 = pack_bf2(v0 - __uint_as_float(h01 << 16), v1 - __uint_as_float(h01 & 0xFFFF0000u));
+          const uint32_t o = poff + (uint32_t)(sseg * sr + i) * 16u;
+          *reinterpret_cast<uint32_t*>(P1h + o) = h01;
+          *reinterpret_cast<uint32_t*>(P1l + o) = l01;
+        }
+    } else {
     // ---- S: xs -> two bf16 planes (value = hi + lo to 16 mantissa bits); 8 rows in flight per lane
     for (int rb = warp * 8; rb < rv; rb += NW * 8) {
       float4 raw[8];
@@ -487,6 +623,7 @@ __global__ void __launch_bounds__(kGluThreads, 1) tc_glu_kernel(TcGluParams p) {
           *reinterpret_cast<uint2*>(P1l + o) = make_uint2(l01, l23);
         }
       }
+    }
     }
     fence_proxy_async_smem();
     tc_fence_before();
@@ -622,20 +759,18 @@ __global__ void __launch_bounds__(kGluThreads, 1) tc_glu_kernel(TcGluParams p) {
           for (int j = 0; j < HJ; ++j) xin[q][j] = xr[lane + 32 * j];
         }
       }
+      const unsigned short* trow = reinterpret_cast<const unsigned short*>(T + (size_t)rb * ldT) + lane;
+      float* yr = p.OUT + (size_t)(row0 + rb) * H + lane;
 #pragma unroll
       for (int q = 0; q < PB; ++q) {
-        if (rb + q < rv) {
-          const unsigned short* trow = reinterpret_cast<const unsigned short*>(T + (size_t)(rb + q) * ldT);
-          float* yr = p.OUT + (size_t)(row0 + rb + q) * H;
+        if (rb + q >= rv) break;                              // warp-uniform
 #pragma unroll
-          for (int j = 0; j < HJ; ++j) {
-            const int c = lane + 32 * j;
-            // codes are non-negative: int -> float through the magic constant (no conversion pipe)
-            const float l = (__uint_as_float(0x4B400000u + trow[c]) - kRoundMagic) * p.gl_s;
-            const float sg = (__uint_as_float(0x4B400000u + trow[H + c]) - kRoundMagic) * p.gr_s;
-            const float out = fmaf(l, sg, xin[q][j]);
-            yr[c] = p.relu_out ? fmaxf(out, 0.f) : out;
-          }
+        for (int j = 0; j < HJ; ++j) {
+          // codes are non-negative: int -> float through the magic constant (no conversion pipe)
+          const float l = (__uint_as_float(0x4B400000u + trow[(size_t)q * 2 * ldT + 32 * j]) - kRoundMagic) * gl_s;
+          const float sg = (__uint_as_float(0x4B400000u + trow[(size_t)q * 2 * ldT + H + 32 * j]) - kRoundMagic) * gr_s;
+          const float out = fmaf(l, sg, xin[q][j]);
+          yr[(size_t)q * H + 32 * j] = fmaxf(out, out_floor);
         }
       }
     }
@@ -643,7 +778,7 @@ __global__ void __launch_bounds__(kGluThreads, 1) tc_glu_kernel(TcGluParams p) {
     TC_TRACE_MARK(tid == 0);
     TC_TRACE_NEXT();
   }
-  TC_TRACE_PRINT(tid == 0, "glu: S+sync mma1 E1+sync P1+sync mma2 E2+sync P2+sync");
+  TC_TRACE_PRINT(tid == 0, SCAN ? "glu+scan: load+pass1 bar lookback bar pass2+sync mma1 E1+sync P1+sync mma2 E2+sync P2+sync" : "glu: S+sync mma1 E1+sync P1+sync mma2 E2+sync P2+sync");
   tc_fence_before();
   __syncthreads();
   if (tid < 32) tc_dealloc(tmem_slot, 512);
@@ -789,7 +924,8 @@ int tc_linear_launch(const TcLinearDev& d, const float* X, float* Y, long long r
 // ---- C projection + GLU handle
 static size_t tc_glu_smem(int H, int K1) {
   const size_t r_bytes = std::max(2 * tc_tile_bytes(kTcRows, K1), (size_t)kTcRows * (H + 4) * 4 + 2 * tc_tile_bytes8(kTcRows, kGluK2));
-  return tc_tile_bytes(H, K1) + tc_tile_bytes8(H, kGluK2) + (((size_t)H * 4 + 127) & ~(size_t)127) + 2 * r_bytes;
+  return tc_tile_bytes(H, K1) + tc_tile_bytes8(H, kGluK2) + (((size_t)H * 4 + 127) & ~(size_t)127) + 2 * r_bytes +
+         2 * (2 * kGluHalf + 128) * sizeof(float2);   // + segment aggregates / multipliers / carries of the fused recurrence
 }
 
 int tc_glu_build(const float* C_tilde /*[H][P][2] quantised*/, const float* out2_kernel /*[H][H] quantised*/, int H, int P,
@@ -833,16 +969,19 @@ void tc_glu_free(TcGluDev* d) {
   *d = TcGluDev();
 }
 
-template <int HJ>
-static int tc_glu_go(const TcGluParams& p, size_t smem, cudaStream_t st) {
-  auto kernel = tc_glu_kernel<HJ>;
+template <int HJ, bool SCAN>
+static int tc_glu_go(const TcGluParams& p, size_t smem, int grid, cudaStream_t st) {
+  auto kernel = tc_glu_kernel<HJ, SCAN>;
   S5_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  // rows are split evenly over 2 x grid pipelines (balanced partition); at least 32 rows per pipeline
-  const int grid = (int)std::max<long long>(1, std::min<long long>((p.rows + 63) / 64, (long long)sm_count()));
   ProfScope prof(S5_K_GLU, st);
   kernel<<<grid, kGluThreads, smem, st>>>(p);
   S5_LAUNCH_CHECK();
   return S5_OK;
+}
+
+size_t tc_glu_scan_workspace_bytes(int B, int L, int P) {
+  const int cmax = (L + 31) / 32 + 1;                          // upper bound on tiles per clip
+  return round_up((size_t)B * cmax * sizeof(uint32_t), 256) + (size_t)B * cmax * 2 * P * sizeof(float2);
 }
 
 int tc_glu_launch(const TcGluDev& d, const TcGluArgs& a, cudaStream_t st) {
@@ -859,12 +998,51 @@ int tc_glu_launch(const TcGluDev& d, const TcGluArgs& a, cudaStream_t st) {
   p.ut_s = a.s_ut; p.ut_inv = 1.f / a.s_ut; p.yt_s = a.s_yt; p.yt_inv = 1.f / a.s_yt; p.oa_inv = 1.f / a.s_o_act;
   p.oo_s = a.s_o_out; p.oo_inv = 1.f / a.s_o_out; p.gl_s = a.s_gl; p.gl_inv = 1.f / a.s_gl; p.gr_s = a.s_gr; p.gr_inv = 1.f / a.s_gr;
   p.qs_min = a.qs_min; p.qs_max = a.qs_max; p.qn_min = a.qn_min; p.qn_max = a.qn_max; p.relu_out = a.relu_out;
-  switch (d.H >> 5) {
-    case 1: return tc_glu_go<1>(p, d.smem, st);
-    case 2: return tc_glu_go<2>(p, d.smem, st);
-    case 3: return tc_glu_go<3>(p, d.smem, st);
-    default: return tc_glu_go<4>(p, d.smem, st);
+  const int HJ = d.H >> 5;
+  if (!a.lam) {
+    // rows are split evenly over 2 x grid pipelines (balanced partition); at least 32 rows per pipeline
+    const int grid = (int)std::max<long long>(1, std::min<long long>((p.rows + 63) / 64, (long long)sm_count()));
+    switch (HJ) {
+      case 1: return tc_glu_go<1, false>(p, d.smem, grid, st);
+      case 2: return tc_glu_go<2, false>(p, d.smem, grid, st);
+      case 3: return tc_glu_go<3, false>(p, d.smem, grid, st);
+      default: return tc_glu_go<4, false>(p, d.smem, grid, st);
+    }
   }
+  // ---- fused recurrence: XS is Bu.  Tiles are R consecutive frames of one clip; pick the number of tiles per clip
+  // that minimises (rounds over the pipelines) x (rows per tile), i.e. the time of the slowest pipeline.
+  const int P = d.K1 >> 1;
+  if (!tc_glu_scan_ok(d) || a.B <= 0 || a.L <= 0 || (long long)a.B * a.L != a.rows) S5_FAIL(S5_E_BADARG, "dense-tile glu: fused recurrence not eligible");
+  // Rows per tile depend on L only (never on B): the grouping of the floating-point recurrence, and with it every
+  // output bit, is then independent of how clips are batched, chunked by the host pipeline or sharded over GPUs.
+  // S5B200_SCAN_TILE_ROWS (<= 128) overrides the tile height; measured on B200 at 32 x 3751 frames: 128 -> 98.6 us,
+  // 104 (a whole number of rounds over the 296 pipelines) -> 100.6 us, 96 -> 110.5 us, 64 -> 125 us.
+  static const int tile_rows = [] { const char* e = getenv("S5B200_SCAN_TILE_ROWS"); return e ? std::max(8, std::min(kTcRows, atoi(e))) : kTcRows; }();
+  const int nseg = kGluHalf / P, rmax = std::min(tile_rows, 32 * nseg);
+  const int c = (a.L + rmax - 1) / rmax;
+  p.R = (a.L + c - 1) / c;
+  p.tiles_per_clip = (a.L + p.R - 1) / p.R;
+  const long long tiles = (long long)a.B * p.tiles_per_clip;
+  const int grid = (int)std::max<long long>(1, std::min<long long>((tiles + 1) / 2, (long long)sm_count()));
+  p.lam = reinterpret_cast<const float2*>(a.lam); p.B = a.B; p.L = a.L;
+  p.relu_scan = a.relu_scan;
+  const size_t flags_bytes = round_up((size_t)a.B * p.tiles_per_clip * sizeof(uint32_t), 256);
+  const size_t need = flags_bytes + (size_t)a.B * p.tiles_per_clip * 2 * P * sizeof(float2);
+  if (!a.scan_ws || a.scan_ws_bytes < need || !aligned16(a.scan_ws)) S5_FAIL(S5_E_BADARG, "dense-tile glu: recurrence workspace %zu < %zu bytes", a.scan_ws_bytes, need);
+  p.flags = reinterpret_cast<uint32_t*>(a.scan_ws);
+  p.recs = reinterpret_cast<float2*>(reinterpret_cast<unsigned char*>(a.scan_ws) + flags_bytes);
+  S5_CUDA(cudaMemsetAsync(p.flags, 0, flags_bytes, st));
+  switch (HJ) {
+    case 1: return tc_glu_go<1, true>(p, d.smem, grid, st);
+    case 2: return tc_glu_go<2, true>(p, d.smem, grid, st);
+    case 3: return tc_glu_go<3, true>(p, d.smem, grid, st);
+    default: return tc_glu_go<4, true>(p, d.smem, grid, st);
+  }
+}
+
+bool tc_glu_scan_ok(const TcGluDev& d) {
+  const int P = d.K1 >> 1;
+  return d.ok && (P == 32 || P == 64);   // whole warps of carry threads, <= 32 frames per segment
 }
 
 }  // namespace s5

@@ -23,6 +23,8 @@ struct TcGluArgs {
   const float* XS; const float* X; float* OUT; long long rows;
   const float* bn_sub; const float* bn_mul; const float* bn_add; const float* D; const float* o_bias;
   float s_ut, s_yt, s_o_act, s_o_out, s_gl, s_gr, qs_min, qs_max, qn_min, qn_max; int relu_out;
+  // fused recurrence (optional): lam != nullptr means XS holds Bu [B][L][P] and the kernel runs the scan itself
+  const float* lam = nullptr; int B = 0, L = 0, relu_scan = 0; void* scan_ws = nullptr; size_t scan_ws_bytes = 0;
 };
 
 bool is_pow2(float s);
@@ -30,6 +32,8 @@ float pow2_grid(const float* w, size_t n, size_t start, size_t stride);
 int tc_glu_build(const float* C_tilde, const float* out2_kernel, int H, int P, float conj_mul, float s_o_act, TcGluDev* out);
 void tc_glu_free(TcGluDev* d);
 int tc_glu_launch(const TcGluDev& d, const TcGluArgs& a, cudaStream_t st);
+bool tc_glu_scan_ok(const TcGluDev& d);
+size_t tc_glu_scan_workspace_bytes(int B, int L, int P);
 int tc_linear_build(const float* W, int Kfull, int Nfull, float s_in, TcLinearDev* out);
 void tc_linear_free(TcLinearDev* d);
 int tc_linear_launch(const TcLinearDev& d, const float* X, float* Y, long long rows, const float* in_sub, const float* in_mul,
