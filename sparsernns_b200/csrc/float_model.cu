@@ -329,6 +329,7 @@ struct s5_model {
   s5::TcLinearDev enc_tc, dec_tc;
   long long tc_min_rows = 4096;  // below this the compressed CUDA-core kernels are used
   bool fuse_scan = true;         // static dense-tile path: run the recurrence inside the GLU kernel (S5B200_FUSE_SCAN=0 disables)
+  bool fuse_bproj = true;        // ... and the B projection as well: one kernel per block (S5B200_FUSE_BPROJ=0 disables)
   float *enc_bias = nullptr, *dec_bias = nullptr;
   std::vector<s5::LayerDev> layers;
   // host-buffer entry point: ring of device buffers, three streams (H2D | forward | D2H) and their events
@@ -414,23 +415,28 @@ static int run_block(const s5_model* m, int li, const float* x, float* out, floa
   const long long rows = (long long)B * L;
   int rc;
   const bool sq = m->desc.flavour == S5_STATIC;
-  if (sq && ld.tb.ok && rows >= m->tc_min_rows && is_pow2(ld.sc.s_ut) && is_pow2(ld.sc.s_But_re) && is_pow2(ld.sc.s_But_im)) {
+  const bool glu_tc = sq && ld.tg.ok && !ssm_only && rows >= m->tc_min_rows && is_pow2(ld.sc.s_ut) && is_pow2(ld.sc.s_yt) &&
+                      is_pow2(ld.sc.s_out2_act) && is_pow2(ld.sc.s_out2_out) && is_pow2(ld.sc.s_gate_left) && is_pow2(ld.sc.s_gate_right);
+  // the recurrence runs inside the GLU kernel (states never leave the SM) unless the caller wants to see them,
+  // and so does the B projection: the whole block is then one kernel
+  const bool fuse_scan = glu_tc && m->fuse_scan && !want_xs && tc_glu_scan_ok(ld.tg);
+  const bool fuse_bproj = fuse_scan && m->fuse_bproj && ld.tg.bpj_ok && is_pow2(ld.sc.s_But_re) && is_pow2(ld.sc.s_But_im);
+  if (fuse_bproj) {
+    // nothing to launch here
+  } else if (sq && ld.tb.ok && rows >= m->tc_min_rows && is_pow2(ld.sc.s_ut) && is_pow2(ld.sc.s_But_re) && is_pow2(ld.sc.s_But_im)) {
     float qlo, qhi;
     qrange(m->desc.ssm_act_bits, &qlo, &qhi);
     if ((rc = tc_linear_launch(ld.tb, x, bu, rows, bn ? ld.bn_mean : nullptr, bn ? ld.bn_mul : nullptr, bn ? ld.bn_bias : nullptr,
                                ld.sc.s_ut, qlo, qhi, nullptr, ld.sc.s_But_re, ld.sc.s_But_im, qlo, qhi, 0, S5_K_BPROJ, st)))
       return rc;
   } else if ((rc = launch_linear(bproj_params(m, ld, x, bu, rows, bn), st, S5_K_BPROJ))) return rc;
-  const bool glu_tc = sq && ld.tg.ok && !ssm_only && rows >= m->tc_min_rows && is_pow2(ld.sc.s_ut) && is_pow2(ld.sc.s_yt) &&
-                      is_pow2(ld.sc.s_out2_act) && is_pow2(ld.sc.s_out2_out) && is_pow2(ld.sc.s_gate_left) && is_pow2(ld.sc.s_gate_right);
-  // the recurrence runs inside the GLU kernel (states never leave the SM) unless the caller wants to see them
-  const bool fuse_scan = glu_tc && m->fuse_scan && !want_xs && tc_glu_scan_ok(ld.tg);
   if (!fuse_scan && (rc = launch_scan_c64(bu, ld.lam, bu, B, L, m->desc.P, m->desc.relufication, scan_ws, scan_ws_bytes, st))) return rc;
   if (glu_tc) {
     TcGluArgs a{};
     a.XS = bu; a.X = x; a.OUT = out; a.rows = rows;
     if (fuse_scan) {
       a.lam = ld.lam; a.B = B; a.L = L; a.relu_scan = m->desc.relufication; a.scan_ws = scan_ws; a.scan_ws_bytes = scan_ws_bytes;
+      a.fuse_bproj = fuse_bproj; a.s_bu_re = ld.sc.s_But_re; a.s_bu_im = ld.sc.s_But_im;
     }
     a.bn_sub = bn ? ld.bn_mean : nullptr; a.bn_mul = bn ? ld.bn_mul : nullptr; a.bn_add = bn ? ld.bn_bias : nullptr;
     a.D = ld.D; a.o_bias = ld.o_bias;
@@ -508,6 +514,7 @@ extern "C" int s5b200_model_create(const s5_model_desc* d, s5_model** out) {
   // (1 forces them, a huge value disables them); default 4096.
   if (const char* e = getenv("S5B200_TC_MIN_ROWS")) m->tc_min_rows = atoll(e);
   if (const char* e = getenv("S5B200_FUSE_SCAN")) m->fuse_scan = atoi(e) != 0;
+  if (const char* e = getenv("S5B200_FUSE_BPROJ")) m->fuse_bproj = atoi(e) != 0;
   const int H = d->H, P = d->P, dense = d->use_sparse ? 0 : 1;
   int rc = S5_OK;
   auto fail = [&](int code) { s5b200_model_destroy(m); return code; };
@@ -537,7 +544,7 @@ extern "C" int s5b200_model_create(const s5_model_desc* d, s5_model** out) {
     if ((rc = sparse_build(wb.data(), H, 2 * P, S5_F32, dense, &ld.wb))) return fail(rc);
     if (d->flavour == S5_STATIC && (rc = tc_linear_build(wb.data(), H, 2 * P, l.s_ut, &ld.tb))) return fail(rc);
     if (d->flavour == S5_STATIC && d->activation == S5_ACT_RELU && l.out2_kernel_host &&
-        (rc = tc_glu_build(l.C_tilde_host, l.out2_kernel_host, H, P, d->conj_sym ? 2.f : 1.f, l.s_out2_act, &ld.tg)))
+        (rc = tc_glu_build(l.C_tilde_host, l.out2_kernel_host, H, P, d->conj_sym ? 2.f : 1.f, l.s_out2_act, wb.data(), l.s_ut, &ld.tg)))
       return fail(rc);
     if ((rc = sparse_build(wc.data(), 2 * P, H, S5_F32, dense, &ld.wc))) return fail(rc);
     if ((rc = sparse_build(l.out2_kernel_host, H, H, S5_F32, dense, &ld.wo))) return fail(rc);

@@ -380,6 +380,10 @@ struct TcGluParams {
   int relu_scan;               // lexicographic complex ReLU on the states handed to C (relufication)
   uint32_t* flags;             // [B][tiles_per_clip] look-back flags (0 none, 1 aggregate, 2 inclusive prefix), zeroed per launch
   float2* recs;                // [B][tiles_per_clip][2][P] aggregate / inclusive prefix
+  // fused B projection (BPJ instantiation): Bu = FQ(B_bar FQ(BN(x))) is computed in the kernel as well, XS is unused
+  const signed char* WB;       // [K1][128] int8 codes of B_bar (rows = (re, im) interleaved outputs), lane-interleaved K
+  const float* b_col_scale;    // [K1] s_u * s_w[n]
+  float b_out_scale0, b_out_scale1, b_out_inv0, b_out_inv1;   // FQ grid of Re(Bu) / Im(Bu)
 };
 
 __device__ __forceinline__ float2 cmulf(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
@@ -414,8 +418,12 @@ __device__ __forceinline__ uint32_t pack_bf2(float a, float b) {   // {lo half =
 // registers, scans them twice (local aggregate, then with the true carry-in) and the carry across tiles of a clip
 // travels by decoupled look-back (aggregate / inclusive-prefix records + acquire / release flags in global memory).
 // The states never touch HBM: they go from registers straight into the bf16 operand planes of the C projection.
-template <int HJ, bool SCAN>
+// BPJ (implies SCAN): the B projection runs in the kernel, too: x tile -> u codes -> int8 planes -> MMA -> FQ(Bu) -> a
+// shared-memory tile that the recurrence threads read column-wise.  A whole S5 block is then ONE kernel that reads
+// the block input and writes the block output; Bu and the states never leave the SM.
+template <int HJ, bool SCAN, bool BPJ>
 __global__ void __launch_bounds__(kGluThreads, 1) tc_glu_kernel(TcGluParams p) {
+  static_assert(SCAN || !BPJ, "the fused B projection needs the fused recurrence");
   TC_TRACE_ENTRY
   extern __shared__ __align__(128) unsigned char smem[];
   const int H = p.H, K1 = p.K1;
@@ -424,17 +432,24 @@ __global__ void __launch_bounds__(kGluThreads, 1) tc_glu_kernel(TcGluParams p) {
   const size_t p1_bytes = tc_tile_bytes(kTcRows, K1);         // one bf16 plane of the xs tile
   const size_t t_bytes = (size_t)kTcRows * ldT * 4;
   const size_t a2_bytes = tc_tile_bytes8(kTcRows, kGluK2);    // one int8 plane of the x1 codes
-  const size_t r_bytes = max(2 * p1_bytes, t_bytes + 2 * a2_bytes);
+  const int ldB = K1 + 4;                                     // floats per row of the Bu tile (BPJ)
+  const size_t bu_bytes = BPJ ? (size_t)kTcRows * ldB * 4 : 0;
+  const size_t seg_bytes = SCAN ? (size_t)(2 * kGluHalf + 128) * sizeof(float2) : 0;
+  const size_t r_bytes = max(max(2 * p1_bytes, bu_bytes) + seg_bytes, t_bytes + 2 * a2_bytes);
+  const size_t wb_bytes = BPJ ? tc_tile_bytes8(K1, kGluK2) : 0;
   unsigned char* Wc = smem;
   unsigned char* Wo = Wc + wc_bytes;
-  float* ob = reinterpret_cast<float*>(Wo + wo_bytes);        // [H] out2 bias / s_o_out
+  unsigned char* WB = Wo + wo_bytes;
+  float* ob = reinterpret_cast<float*>(WB + wb_bytes);        // [H] out2 bias / s_o_out
+  float* cstB = ob + H;                                       // [K1] s_u s_w / s_Bu (BPJ)
   const int tid = threadIdx.x, half = tid >> 8, htid = tid & (kGluHalf - 1), warp = htid >> 5, lane = tid & 31;
-  unsigned char* Rbase = reinterpret_cast<unsigned char*>(ob) + (((size_t)H * 4 + 127) & ~(size_t)127);
+  unsigned char* Rbase = reinterpret_cast<unsigned char*>(ob) + (((size_t)(H + K1) * 4 + 127) & ~(size_t)127);
   unsigned char* R = Rbase + (size_t)half * r_bytes;
-  // SCAN: per pipeline, segment aggregates + multipliers [nseg][P] and the tile carry [P]
-  float2* seg_agg = reinterpret_cast<float2*>(Rbase + 2 * r_bytes) + (size_t)half * (2 * kGluHalf + 128);
+  // SCAN: segment aggregates + multipliers [nseg][P] and the tile carry [P], behind the planes / the Bu tile
+  float2* seg_agg = reinterpret_cast<float2*>(R + max(2 * p1_bytes, bu_bytes));
   float2* seg_mul = seg_agg + kGluHalf;
   float2* carry_s = seg_mul + kGluHalf;
+  float* BuT = reinterpret_cast<float*>(R);                   // BPJ: FQ(Bu) tile [128][K1 + 4], dead once the recurrence holds it
   unsigned char* P1h = R;                                     // xs planes (dead after MMA 1)
   unsigned char* P1l = R + p1_bytes;
   float* T = reinterpret_cast<float*>(R);                     // aliases the xs planes
@@ -451,6 +466,10 @@ __global__ void __launch_bounds__(kGluThreads, 1) tc_glu_kernel(TcGluParams p) {
   }
   tc_load_weights(Wc, reinterpret_cast<const __half*>(p.Wc), H, K1);
   tc_load_weights8(Wo, p.Wo, H, kGluK2);
+  if constexpr (BPJ) {
+    tc_load_weights8(WB, p.WB, K1, kGluK2);
+    for (int n = tid; n < K1; n += kGluThreads) cstB[n] = p.b_col_scale[n] * ((n & 1) ? p.b_out_inv1 : p.b_out_inv0);
+  }
   for (int n = tid; n < H; n += kGluThreads) ob[n] = p.o_bias[n] * p.oo_inv;
   // the int8 planes carry a zero pad byte per lane (column 4 lane + 3 when HJ < 4): clear them once
   for (size_t i = (size_t)htid * 16; i < 2 * a2_bytes; i += kGluHalf * 16) *reinterpret_cast<int4*>(A2h + i) = make_int4(0, 0, 0, 0);
@@ -525,11 +544,75 @@ __global__ void __launch_bounds__(kGluThreads, 1) tc_glu_kernel(TcGluParams p) {
     if constexpr (SCAN) {
       // ---- S (fused recurrence): Bu -> registers -> local aggregate -> look-back -> states -> bf16 planes
       const int len = max(0, min(sr, rv - sseg * sr));
-      const float2* bu = reinterpret_cast<const float2*>(p.XS) + (size_t)row0 * P + sp;
-      // 32 unpredicated, unclamped loads: rows past the segment are ignored, rows past the end of Bu fall into the
-      // slack the workspace layout keeps behind it
       float2 v[32];
-      {
+      if constexpr (BPJ) {
+        // ---- S0: block input -> u = FQ(BN(x)) codes -> int8 planes (lanes along columns, as in P1)
+        for (int rb = warp * 8; rb < rv; rb += NW * 8) {
+          float xr8[8][HJ];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float* xr = p.X + (size_t)min(row0 + rb + q, last_row) * H;
+#pragma unroll
+            for (int j = 0; j < HJ; ++j) xr8[q][j] = xr[lane + 32 * j];
+          }
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            uint32_t ub[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+            for (int j = 0; j < HJ; ++j)
+              ub[j] = __float_as_uint(fminf(fmaxf((xr8[q][j] - bsub[j]) * bmulq[j] + baddq[j], qs_min), qs_max) + kRoundMagic);
+            uint32_t lo, hi;
+            split_planes(ub[0], ub[1], ub[2], ub[3], lo, hi);
+            *reinterpret_cast<uint32_t*>(A2h + aoff + (uint32_t)(rb + q) * 16u) = hi;
+            *reinterpret_cast<uint32_t*>(A2l + aoff + (uint32_t)(rb + q) * 16u) = lo;
+          }
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        half_barrier(half);
+        tc_fence_after();
+        if (htid == 0) {
+          tc_issue8(tcol, A2h, WB, kGluK2, K1, K1, true);
+          tc_issue8(tcol + 128, A2l, WB, kGluK2, K1, K1, false);
+          tc_commit(&bar[half]);
+        }
+        mbar_wait(&bar[half], phase);
+        phase ^= 1;
+        tc_fence_after();
+        // ---- E_B: Bu = FQ(acc * s_u s_w) -> shared tile (the planes are dead)
+        if (erow0 < rv) {
+          const int cwb = K1 >> 1, cb0 = (warp >> 2) * cwb;
+          for (int c0 = cb0; c0 < cb0 + cwb; c0 += 8) {
+            uint32_t vh[8], vl[8];
+            tc_ld8(tcol + lane_base + c0, vh);
+            tc_ld8(tcol + lane_base + 128 + c0, vl);
+            tc_wait_ld();
+            float o[8];
+#pragma unroll
+            for (int j = 0; j < 8; j += 4) {
+              const float4 c4 = *reinterpret_cast<const float4*>(cstB + c0 + j);
+              const float cc[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float f = __int2float_rn((int)vh[j + e] * 256 + (int)vl[j + e]);
+                o[j + e] = round_clip(f * cc[e], qs_min, qs_max) * ((e & 1) ? p.b_out_scale1 : p.b_out_scale0);
+              }
+            }
+            float* dst = BuT + (size_t)erow * ldB + c0;
+            *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<float4*>(dst + 4) = make_float4(o[4], o[5], o[6], o[7]);
+          }
+        }
+        tc_fence_before();
+        half_barrier(half);
+        // the recurrence threads pick their 32 frames of one state out of the tile
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          v[i] = *reinterpret_cast<const float2*>(BuT + (size_t)min(sseg * sr + i, kTcRows - 1) * ldB + 2 * sp);
+      } else {
+        const float2* bu = reinterpret_cast<const float2*>(p.XS) + (size_t)row0 * P + sp;
+        // 32 unpredicated, unclamped loads: rows past the segment are ignored, rows past the end of Bu fall into the
+        // slack the workspace layout keeps behind it
         const float2* q = bu + (size_t)(sseg * sr) * P;
 #pragma unroll
         for (int i = 0; i < 32; ++i, q += P) v[i] = *q;
@@ -922,18 +1005,21 @@ int tc_linear_launch(const TcLinearDev& d, const float* X, float* Y, long long r
 
 
 // ---- C projection + GLU handle
-static size_t tc_glu_smem(int H, int K1) {
-  const size_t r_bytes = std::max(2 * tc_tile_bytes(kTcRows, K1), (size_t)kTcRows * (H + 4) * 4 + 2 * tc_tile_bytes8(kTcRows, kGluK2));
-  return tc_tile_bytes(H, K1) + tc_tile_bytes8(H, kGluK2) + (((size_t)H * 4 + 127) & ~(size_t)127) + 2 * r_bytes +
-         2 * (2 * kGluHalf + 128) * sizeof(float2);   // + segment aggregates / multipliers / carries of the fused recurrence
+static size_t tc_glu_smem(int H, int K1, bool scan, bool bpj) {
+  const size_t bu_bytes = bpj ? (size_t)kTcRows * (K1 + 4) * 4 : 0;
+  const size_t seg_bytes = scan ? (size_t)(2 * kGluHalf + 128) * sizeof(float2) : 0;
+  const size_t r_bytes = std::max(std::max(2 * tc_tile_bytes(kTcRows, K1), bu_bytes) + seg_bytes,
+                                  (size_t)kTcRows * (H + 4) * 4 + 2 * tc_tile_bytes8(kTcRows, kGluK2));
+  return tc_tile_bytes(H, K1) + tc_tile_bytes8(H, kGluK2) + (bpj ? tc_tile_bytes8(K1, kGluK2) : 0) +
+         (((size_t)(H + K1) * 4 + 127) & ~(size_t)127) + 2 * r_bytes;
 }
 
 int tc_glu_build(const float* C_tilde /*[H][P][2] quantised*/, const float* out2_kernel /*[H][H] quantised*/, int H, int P,
-                 float conj_mul, float s_o_act, TcGluDev* out) {
+                 float conj_mul, float s_o_act, const float* B_bar /*[H][2P] quantised, nullable*/, float s_ut, TcGluDev* out) {
   out->ok = false;
   const int K1 = 2 * P;
   if ((H & 31) || H > 128 || (K1 & 15) || K1 > 128 || !is_pow2(s_o_act)) return S5_OK;
-  const size_t smem = tc_glu_smem(H, K1);
+  const size_t smem = tc_glu_smem(H, K1, false, false);
   if (smem > 226 * 1024) return S5_OK;
   const size_t nC = (size_t)H * P * 2;
   const float s_re = pow2_grid(C_tilde, nC, 0, 2), s_im = pow2_grid(C_tilde, nC, 1, 2);
@@ -961,17 +1047,45 @@ int tc_glu_build(const float* C_tilde /*[H][P][2] quantised*/, const float* out2
   S5_CUDA(cudaMalloc(&out->Wo, wo.size()));
   S5_CUDA(cudaMemcpy(out->Wo, wo.data(), wo.size(), cudaMemcpyHostToDevice));
   out->ok = true;
+  out->smem_scan = tc_glu_smem(H, K1, true, false);
+  out->smem_bpj = tc_glu_smem(H, K1, true, true);
+  // fused B projection: int8 codes of B_bar on per-parity power-of-two grids (real / imaginary outputs)
+  if (B_bar && is_pow2(s_ut) && out->smem_bpj <= 227 * 1024 - 1280) {
+    std::vector<float> c0, c1;
+    for (int k = 0; k < H; ++k)
+      for (int n = 0; n < K1; ++n) ((n & 1) ? c1 : c0).push_back(B_bar[(size_t)k * K1 + n]);
+    const float g0 = pow2_grid(c0.data(), c0.size(), 0, 1), g1 = pow2_grid(c1.data(), c1.size(), 0, 1);
+    std::vector<signed char> wb((size_t)K1 * kGluK2, 0);
+    std::vector<float> cs(K1);
+    bool fits = true;
+    for (int n = 0; n < K1 && fits; ++n) {
+      const float g = (n & 1) ? g1 : g0;
+      cs[n] = s_ut * g;
+      for (int k = 0; k < H; ++k) {
+        const float c = std::nearbyint(B_bar[(size_t)k * K1 + n] / g);
+        if (c < -128.f || c > 127.f) { fits = false; break; }
+        wb[(size_t)n * kGluK2 + 4 * (k & 31) + (k >> 5)] = (signed char)c;
+      }
+    }
+    if (fits) {
+      S5_CUDA(cudaMalloc(&out->WB, wb.size()));
+      S5_CUDA(cudaMemcpy(out->WB, wb.data(), wb.size(), cudaMemcpyHostToDevice));
+      int rc;
+      if ((rc = upload_f(cs, &out->b_col_scale))) return rc;
+      out->bpj_ok = true;
+    }
+  }
   return S5_OK;
 }
 
 void tc_glu_free(TcGluDev* d) {
-  cudaFree(d->Wc); cudaFree(d->Wo);
+  cudaFree(d->Wc); cudaFree(d->Wo); cudaFree(d->WB); cudaFree(d->b_col_scale);
   *d = TcGluDev();
 }
 
-template <int HJ, bool SCAN>
+template <int HJ, bool SCAN, bool BPJ>
 static int tc_glu_go(const TcGluParams& p, size_t smem, int grid, cudaStream_t st) {
-  auto kernel = tc_glu_kernel<HJ, SCAN>;
+  auto kernel = tc_glu_kernel<HJ, SCAN, BPJ>;
   S5_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   ProfScope prof(S5_K_GLU, st);
   kernel<<<grid, kGluThreads, smem, st>>>(p);
@@ -989,7 +1103,7 @@ int tc_glu_launch(const TcGluDev& d, const TcGluArgs& a, cudaStream_t st) {
   for (float s : sc)
     if (!is_pow2(s)) S5_FAIL(S5_E_BADARG, "dense-tile glu: scales must be powers of two");
   if (!d.ok) S5_FAIL(S5_E_BADARG, "dense-tile glu: not eligible");
-  if (!aligned16(a.XS)) S5_FAIL(S5_E_BADARG, "dense-tile glu: xs must be 16-byte aligned");
+  if (!a.fuse_bproj && !aligned16(a.XS)) S5_FAIL(S5_E_BADARG, "dense-tile glu: xs must be 16-byte aligned");
   TcGluParams p{};
   p.XS = a.XS; p.X = a.X; p.OUT = a.OUT; p.rows = a.rows; p.H = d.H; p.K1 = d.K1;
   p.Wc = reinterpret_cast<const __nv_bfloat16*>(d.Wc); p.Wo = reinterpret_cast<const signed char*>(d.Wo);
@@ -1003,10 +1117,10 @@ int tc_glu_launch(const TcGluDev& d, const TcGluArgs& a, cudaStream_t st) {
     // rows are split evenly over 2 x grid pipelines (balanced partition); at least 32 rows per pipeline
     const int grid = (int)std::max<long long>(1, std::min<long long>((p.rows + 63) / 64, (long long)sm_count()));
     switch (HJ) {
-      case 1: return tc_glu_go<1, false>(p, d.smem, grid, st);
-      case 2: return tc_glu_go<2, false>(p, d.smem, grid, st);
-      case 3: return tc_glu_go<3, false>(p, d.smem, grid, st);
-      default: return tc_glu_go<4, false>(p, d.smem, grid, st);
+      case 1: return tc_glu_go<1, false, false>(p, d.smem, grid, st);
+      case 2: return tc_glu_go<2, false, false>(p, d.smem, grid, st);
+      case 3: return tc_glu_go<3, false, false>(p, d.smem, grid, st);
+      default: return tc_glu_go<4, false, false>(p, d.smem, grid, st);
     }
   }
   // ---- fused recurrence: XS is Bu.  Tiles are R consecutive frames of one clip; pick the number of tiles per clip
@@ -1032,11 +1146,22 @@ int tc_glu_launch(const TcGluDev& d, const TcGluArgs& a, cudaStream_t st) {
   p.flags = reinterpret_cast<uint32_t*>(a.scan_ws);
   p.recs = reinterpret_cast<float2*>(reinterpret_cast<unsigned char*>(a.scan_ws) + flags_bytes);
   S5_CUDA(cudaMemsetAsync(p.flags, 0, flags_bytes, st));
+  if (a.fuse_bproj) {
+    if (!d.bpj_ok || !is_pow2(a.s_bu_re) || !is_pow2(a.s_bu_im)) S5_FAIL(S5_E_BADARG, "dense-tile glu: fused B projection not eligible");
+    p.WB = reinterpret_cast<const signed char*>(d.WB); p.b_col_scale = d.b_col_scale;
+    p.b_out_scale0 = a.s_bu_re; p.b_out_scale1 = a.s_bu_im; p.b_out_inv0 = 1.f / a.s_bu_re; p.b_out_inv1 = 1.f / a.s_bu_im;
+    switch (HJ) {
+      case 1: return tc_glu_go<1, true, true>(p, d.smem_bpj, grid, st);
+      case 2: return tc_glu_go<2, true, true>(p, d.smem_bpj, grid, st);
+      case 3: return tc_glu_go<3, true, true>(p, d.smem_bpj, grid, st);
+      default: return tc_glu_go<4, true, true>(p, d.smem_bpj, grid, st);
+    }
+  }
   switch (HJ) {
-    case 1: return tc_glu_go<1, true>(p, d.smem, grid, st);
-    case 2: return tc_glu_go<2, true>(p, d.smem, grid, st);
-    case 3: return tc_glu_go<3, true>(p, d.smem, grid, st);
-    default: return tc_glu_go<4, true>(p, d.smem, grid, st);
+    case 1: return tc_glu_go<1, true, false>(p, d.smem_scan, grid, st);
+    case 2: return tc_glu_go<2, true, false>(p, d.smem_scan, grid, st);
+    case 3: return tc_glu_go<3, true, false>(p, d.smem_scan, grid, st);
+    default: return tc_glu_go<4, true, false>(p, d.smem_scan, grid, st);
   }
 }
 

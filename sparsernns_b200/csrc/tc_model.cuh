@@ -14,7 +14,8 @@ struct TcLinearDev {
 };
 
 struct TcGluDev {
-  int H = 0, K1 = 0; size_t smem = 0;
+  int H = 0, K1 = 0; size_t smem = 0, smem_scan = 0, smem_bpj = 0;
+  void* WB = nullptr; float* b_col_scale = nullptr; bool bpj_ok = false;   // fused B projection (int8 [2P][128], lane-interleaved K)
   void* Wc = nullptr; void* Wo = nullptr;   // bf16 [H][2P] and int8 [H][128] (lane-interleaved K) weight codes
   float xs_odd_mul = 1.f, c_scale = 1.f, o_col_scale = 1.f;
   bool ok = false;
@@ -25,11 +26,14 @@ struct TcGluArgs {
   float s_ut, s_yt, s_o_act, s_o_out, s_gl, s_gr, qs_min, qs_max, qn_min, qn_max; int relu_out;
   // fused recurrence (optional): lam != nullptr means XS holds Bu [B][L][P] and the kernel runs the scan itself
   const float* lam = nullptr; int B = 0, L = 0, relu_scan = 0; void* scan_ws = nullptr; size_t scan_ws_bytes = 0;
+  // fused B projection (optional, needs the fused recurrence): XS is then unused
+  bool fuse_bproj = false; float s_bu_re = 0.f, s_bu_im = 0.f;
 };
 
 bool is_pow2(float s);
 float pow2_grid(const float* w, size_t n, size_t start, size_t stride);
-int tc_glu_build(const float* C_tilde, const float* out2_kernel, int H, int P, float conj_mul, float s_o_act, TcGluDev* out);
+int tc_glu_build(const float* C_tilde, const float* out2_kernel, int H, int P, float conj_mul, float s_o_act, const float* B_bar,
+                 float s_ut, TcGluDev* out);
 void tc_glu_free(TcGluDev* d);
 int tc_glu_launch(const TcGluDev& d, const TcGluArgs& a, cudaStream_t st);
 bool tc_glu_scan_ok(const TcGluDev& d);

@@ -71,13 +71,15 @@ def test_float_layer_and_ssm_match_oracle(cuda_device, zoo):
         assert relerr(xs2.cpu().numpy(), xs_ref) <= TOL_F32
 
 
-@pytest.mark.parametrize("tc_min_rows,fuse_scan", [("1", "1"), ("1", "0"), ("1000000000", "0")],
-                         ids=["dense_tile_tcgen05_fused_recurrence", "dense_tile_tcgen05", "compressed_cuda_cores"])
-def test_static_model_matches_oracle(cuda_device, zoo, tc_min_rows, fuse_scan, monkeypatch):
+@pytest.mark.parametrize("tc_min_rows,fuse_scan,fuse_bproj", [("1", "1", "1"), ("1", "1", "0"), ("1", "0", "0"), ("1000000000", "0", "0")],
+                         ids=["dense_tile_tcgen05_one_kernel_per_block", "dense_tile_tcgen05_fused_recurrence", "dense_tile_tcgen05",
+                              "compressed_cuda_cores"])
+def test_static_model_matches_oracle(cuda_device, zoo, tc_min_rows, fuse_scan, fuse_bproj, monkeypatch):
     import torch
 
     monkeypatch.setenv("S5B200_TC_MIN_ROWS", tc_min_rows)
     monkeypatch.setenv("S5B200_FUSE_SCAN", fuse_scan)
+    monkeypatch.setenv("S5B200_FUSE_BPROJ", fuse_bproj)
     m, var = _bound(zoo, static=True, relufication=True)
     x = torch.from_numpy(zoo["x"]).to(cuda_device)
     got = m(x).cpu().numpy()
