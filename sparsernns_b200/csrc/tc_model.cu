@@ -33,9 +33,9 @@ __device__ __forceinline__ unsigned long long gtime() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-#define TC_TRACE_DECL unsigned long long tr_[16]; int tr_n = 0; int tr_tile = 0; const unsigned long long tr_entry = tr_t0_; unsigned long long tr_loop = gtime();
+#define TC_TRACE_DECL unsigned long long tr_[20]; int tr_n = 0; int tr_tile = 0; const unsigned long long tr_entry = tr_t0_; unsigned long long tr_loop = gtime();
 #define TC_TRACE_ENTRY const unsigned long long tr_t0_ = gtime();
-#define TC_TRACE_MARK(cond) do { if ((cond) && blockIdx.x == 0 && tr_tile == 1 && tr_n < 16) tr_[tr_n++] = gtime(); } while (0)
+#define TC_TRACE_MARK(cond) do { if ((cond) && blockIdx.x == 0 && tr_tile == 1 && tr_n < 20) tr_[tr_n++] = gtime(); } while (0)
 #define TC_TRACE_NEXT() do { ++tr_tile; } while (0)
 #define TC_TRACE_PRINT(cond, name) do { if ((cond) && blockIdx.x == 0 && tr_n > 1 && atomicSub(&g_trace_budget, 1) > 0) { \
     printf("[trace %s] prologue %llu total %llu tiles %d |", name, tr_loop - tr_entry, gtime() - tr_entry, tr_tile); for (int i_ = 1; i_ < tr_n; ++i_) printf(" %llu", tr_[i_] - tr_[i_ - 1]); printf(" ns\n"); } } while (0)
@@ -59,6 +59,7 @@ struct TcLinParams {
   int alias_out;            // single pass: the output tile may reuse the (dead) activation planes
   int x_stride, y_stride;   // floats per input / output row
   const signed char* W8;    // [Np][Kp] int8 weight codes, K in the physical (staging) order, zero padded
+  const signed char* WN;    // XN: [Kp] codes of the one output column beyond Np (decoder: 257 = 256 + 1), same K order
   const float* in_sub; const float* in_mul; const float* in_add;  // BatchNorm on the input (BN instantiation only)
   float in_inv, in_qmin, in_qmax;   // 1 / s_in (s_in is a power of two, so x * in_inv == x / s_in exactly)
   const float* col_scale;   // [Nfull] s_in * s_w[n]
@@ -146,7 +147,8 @@ __device__ __forceinline__ void tc_issue8(uint32_t d_tmem, const void* A, const 
 // VEC4: rows are 16-byte aligned, lane owns input columns 4 lane .. 4 lane + 3 of each 128-column block.  Otherwise
 // lane owns columns lane + 32 e (coalesced 4-byte loads) and the K axis is PERMUTED inside each block (the same
 // permutation is baked into W8 by the host), so that the four codes of a lane still form one 32-bit store.
-template <bool VEC4, int KV, bool BN>
+// XN: Nfull = Np + 1; the last output column is an integer dot product on the CUDA cores, accumulated while staging.
+template <bool VEC4, int KV, bool BN, bool XN>
 __global__ void __launch_bounds__(kTcThreads, 2) tc_linear_kernel(TcLinParams p) {
   TC_TRACE_ENTRY
   extern __shared__ __align__(128) unsigned char smem[];
@@ -161,6 +163,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) tc_linear_kernel(TcLinParams p)
                                           (p.alias_out ? max(2 * a_bytes, (size_t)kTcRows * ld_out * 4) : (size_t)kTcRows * ld_out * 4));
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t tmem_slot;
+  __shared__ int extra_n[XN ? kTcRows : 1];                   // integer dot of the extra output column
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   constexpr int NW = kTcThreads / 32;
   if (warp == 0) tc_alloc(&tmem_slot, 256);
@@ -181,12 +184,15 @@ __global__ void __launch_bounds__(kTcThreads, 2) tc_linear_kernel(TcLinParams p)
   // is multiplied by zero weights (pad columns of W8) or never written out (pad rows).
   float sub[KV][4], mul[KV][4], add[KV][4];
   int koff[KV][4];
+  int wn[KV][4];
   bool wval[KV];
   uint32_t loff[KV];
 #pragma unroll
   for (int i = 0; i < KV; ++i) {
     loff[i] = (uint32_t)(8 * i + (lane >> 2)) * lbo + 4u * (lane & 3);
     wval[i] = 128 * i + 4 * lane < Kp;                        // the lane's 32-bit word lies inside the tile
+#pragma unroll
+    for (int e = 0; e < 4; ++e) wn[i][e] = (XN && wval[i]) ? (int)p.WN[128 * i + 4 * lane + e] : 0;
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const int k = VEC4 ? 128 * i + 4 * lane + e : 128 * i + lane + 32 * e;
@@ -211,33 +217,39 @@ __global__ void __launch_bounds__(kTcThreads, 2) tc_linear_kernel(TcLinParams p)
   // Balanced partition: every CTA owns one contiguous row range (full tiles plus one short tile whose row loops and
   // TMEM passes stop at its last row) instead of a whole number of 128-row tiles.
   const long long row_begin = p.rows * blockIdx.x / gridDim.x, row_end = p.rows * (blockIdx.x + 1) / gridDim.x;
+  constexpr int RB = 8 / KV;
+  const long long last_row = p.rows - 1;
+  float raw[RB][KV][4];
+  float rawt[RB];
+  bool have_first = false;
+  auto load_batch = [&](long long r0, int rb) {
+#pragma unroll
+    for (int q = 0; q < RB; ++q) {
+      const float* xr = p.X + (size_t)min(r0 + rb + q, last_row) * p.x_stride;
+#pragma unroll
+      for (int i = 0; i < KV; ++i) {
+        if constexpr (VEC4) {
+          const float4 v = *reinterpret_cast<const float4*>(xr + koff[i][0]);
+          raw[q][i][0] = v.x; raw[q][i][1] = v.y; raw[q][i][2] = v.z; raw[q][i][3] = v.w;
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) raw[q][i][e] = xr[koff[i][e]];
+        }
+      }
+      rawt[q] = tail ? xr[128 * KV] : 0.f;                    // same address in every lane: one broadcast load
+    }
+  };
   for (long long row0 = row_begin; row0 < row_end; row0 += kTcRows) {
     const int rv = (int)min((long long)kTcRows, row_end - row0);
     TC_TRACE_MARK(tid == 0);
-    // ---- stage: RB rows are loaded before any of them is converted so that every lane keeps many loads in flight
-    constexpr int RB = 8 / KV;
-    const long long last_row = p.rows - 1;
+    // ---- stage: RB rows are loaded before any of them is converted so that every lane keeps many loads in flight;
+    //      the first batch of a tile was already requested before the previous tile's MMA (see below)
     for (int rb = warp * RB; rb < rv; rb += NW * RB) {
-      float raw[RB][KV][4];
-      float rawt[RB];
-#pragma unroll
-      for (int q = 0; q < RB; ++q) {
-        const float* xr = p.X + (size_t)min(row0 + rb + q, last_row) * p.x_stride;
-#pragma unroll
-        for (int i = 0; i < KV; ++i) {
-          if constexpr (VEC4) {
-            const float4 v = *reinterpret_cast<const float4*>(xr + koff[i][0]);
-            raw[q][i][0] = v.x; raw[q][i][1] = v.y; raw[q][i][2] = v.z; raw[q][i][3] = v.w;
-          } else {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) raw[q][i][e] = xr[koff[i][e]];
-          }
-        }
-        rawt[q] = tail ? xr[128 * KV] : 0.f;                  // same address in every lane: one broadcast load
-      }
+      if (!(have_first && rb == warp * RB)) load_batch(row0, rb);
 #pragma unroll
       for (int q = 0; q < RB; ++q) {
         const uint32_t roff = (uint32_t)(rb + q) * 16u;
+        int part = 0;
 #pragma unroll
         for (int i = 0; i < KV; ++i) {
           uint32_t b[4];
@@ -246,6 +258,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) tc_linear_kernel(TcLinParams p)
             float v = raw[q][i][e];
             if constexpr (BN) v = (v - sub[i][e]) * mul[i][e] + add[i][e];
             b[e] = quant_bits(v, inv, qmin, qmax);
+            if constexpr (XN) part += (int)(short)b[e] * wn[i][e];
           }
           uint32_t lo, hi;
           split_planes(b[0], b[1], b[2], b[3], lo, hi);
@@ -259,8 +272,13 @@ __global__ void __launch_bounds__(kTcThreads, 2) tc_linear_kernel(TcLinParams p)
           *reinterpret_cast<uint32_t*>(Ah + (size_t)(8 * KV) * lbo + roff) = (bt >> 8) & 0xFFu;
           *reinterpret_cast<uint32_t*>(Al + (size_t)(8 * KV) * lbo + roff) = bt & 0xFFu;
         }
+        if constexpr (XN) {
+          part = __reduce_add_sync(0xffffffffu, part);
+          if (lane == 0) extra_n[rb + q] = part;
+        }
       }
     }
+    have_first = false;
     TC_TRACE_MARK(tid == 0);
     fence_proxy_async_smem();
     tc_fence_before();
@@ -273,6 +291,11 @@ __global__ void __launch_bounds__(kTcThreads, 2) tc_linear_kernel(TcLinParams p)
       tc_issue8(taddr, Ah, Wt, Kp, np, Np, true);
       tc_issue8(taddr + 128, Al, Wt, Kp, np, Np, false);
       tc_commit(&bar);
+    }
+    // the first batch of the next tile travels while this tile is multiplied, post-processed and written out
+    if (row0 + kTcRows < row_end) {
+      load_batch(row0 + kTcRows, warp * RB);
+      have_first = true;
     }
     for (int pass0 = 0; pass0 < Np; pass0 += NP) {
       const int np = min(NP, Np - pass0);                     // MMA width of this pass (multiple of 16)
@@ -345,6 +368,14 @@ __global__ void __launch_bounds__(kTcThreads, 2) tc_linear_kernel(TcLinParams p)
             for (int j = 0; j < 4; ++j)
               if (rb + q < rv && lane + 32 * j < npv) yr[lane + 32 * j] = v[q][j];
           }
+        }
+      }
+      if constexpr (XN) {
+        if (pass0 + NP >= Np && tid < rv) {                   // the extra column: one value per row
+          const int n = p.Nfull - 1;
+          const float oinv = (n & 1) ? p.out_inv1 : p.out_inv0;
+          const float t = fmaf(__int2float_rn(extra_n[tid]), p.col_scale[n] * oinv, p.bias ? p.bias[n] * oinv : 0.f);
+          p.Y[(size_t)(row0 + tid) * p.y_stride + n] = round_clip(t, oqmin, oqmax) * ((n & 1) ? os1 : os0);
         }
       }
       __syncthreads();                                        // output tile free again
@@ -571,6 +602,7 @@ __global__ void __launch_bounds__(kGluThreads, 1) tc_glu_kernel(TcGluParams p) {
         tc_fence_before();
         half_barrier(half);
         tc_fence_after();
+        TC_TRACE_MARK(tid == 0);
         if (htid == 0) {
           tc_issue8(tcol, A2h, WB, kGluK2, K1, K1, true);
           tc_issue8(tcol + 128, A2l, WB, kGluK2, K1, K1, false);
@@ -579,6 +611,7 @@ __global__ void __launch_bounds__(kGluThreads, 1) tc_glu_kernel(TcGluParams p) {
         mbar_wait(&bar[half], phase);
         phase ^= 1;
         tc_fence_after();
+        TC_TRACE_MARK(tid == 0);
         // ---- E_B: Bu = FQ(acc * s_u s_w) -> shared tile (the planes are dead)
         if (erow0 < rv) {
           const int cwb = K1 >> 1, cb0 = (warp >> 2) * cwb;
@@ -605,6 +638,7 @@ __global__ void __launch_bounds__(kGluThreads, 1) tc_glu_kernel(TcGluParams p) {
         }
         tc_fence_before();
         half_barrier(half);
+        TC_TRACE_MARK(tid == 0);
         // the recurrence threads pick their 32 frames of one state out of the tile
 #pragma unroll
         for (int i = 0; i < 32; ++i)
@@ -861,7 +895,7 @@ __global__ void __launch_bounds__(kGluThreads, 1) tc_glu_kernel(TcGluParams p) {
     TC_TRACE_MARK(tid == 0);
     TC_TRACE_NEXT();
   }
-  TC_TRACE_PRINT(tid == 0, SCAN ? "glu+scan: load+pass1 bar lookback bar pass2+sync mma1 E1+sync P1+sync mma2 E2+sync P2+sync" : "glu: S+sync mma1 E1+sync P1+sync mma2 E2+sync P2+sync");
+  TC_TRACE_PRINT(tid == 0, BPJ ? "block: S0+sync mmaB EB+sync load+pass1 bar lookback bar pass2+sync mma1 E1+sync P1+sync mma2 E2+sync P2+sync" : SCAN ? "glu+scan: load+pass1 bar lookback bar pass2+sync mma1 E1+sync P1+sync mma2 E2+sync P2+sync" : "glu: S+sync mma1 E1+sync P1+sync mma2 E2+sync P2+sync");
   tc_fence_before();
   __syncthreads();
   if (tid < 32) tc_dealloc(tmem_slot, 512);
@@ -915,7 +949,9 @@ int tc_linear_build(const float* W, int Kfull, int Nfull, float s_in, TcLinearDe
   if (KV < 1 || KV > 2 || Kfull < 16 || Nfull < 16 || Nfull > 512) return S5_OK;   // shape not covered
   // padded K of the operand tiles: natural order / lane-interleaved order (whole 128-column blocks)
   const int Kp[2] = {(Kfull + 31) & ~31, 128 * KV + (tail ? 32 : 0)};
-  const int Np = (Nfull + 15) & ~15;
+  // one output column beyond a multiple of 16 (decoder: 257) is computed on the CUDA cores instead of a whole MMA pass
+  const bool xn = (Nfull % 16) == 1 && Nfull > 16 && !tail;
+  const int Np = xn ? Nfull - 1 : (Nfull + 15) & ~15;
   std::vector<float> col0, col1;
   for (int k = 0; k < Kfull; ++k)
     for (int n = 0; n < Nfull; ++n) ((n & 1) ? col1 : col0).push_back(W[(size_t)k * Nfull + n]);
@@ -924,8 +960,11 @@ int tc_linear_build(const float* W, int Kfull, int Nfull, float s_in, TcLinearDe
   // physical position of logical column k: identity for 16-byte aligned rows; lane-interleaved inside each
   // 128-column block for the 4-byte staging path (lane owns k = lane + 32 e  <->  bytes 4 lane + e)
   auto perm = [&](int k) { return k >= 128 * KV ? k : (k & ~127) + 4 * (k & 31) + ((k & 127) >> 5); };
-  std::vector<signed char> w8[2];
-  for (int o = 0; o < 2; ++o) w8[o].assign((size_t)Np * Kp[o], 0);
+  std::vector<signed char> w8[2], wnx[2];
+  for (int o = 0; o < 2; ++o) {
+    w8[o].assign((size_t)Np * Kp[o], 0);
+    wnx[o].assign((size_t)Kp[o] + 256, 0);                    // + slack: every lane reads its four codes
+  }
   std::vector<float> cs(Nfull);
   for (int n = 0; n < Nfull; ++n) {
     const float sw = (n & 1) ? w_scale1 : w_scale0;
@@ -933,14 +972,22 @@ int tc_linear_build(const float* W, int Kfull, int Nfull, float s_in, TcLinearDe
     for (int k = 0; k < Kfull; ++k) {
       const float c = std::nearbyint(W[(size_t)k * Nfull + n] / sw);
       if (c < -128.f || c > 127.f) return S5_OK;  // not an int8 code: leave this matrix to the compressed kernels
-      w8[0][(size_t)n * Kp[0] + k] = (signed char)c;
-      w8[1][(size_t)n * Kp[1] + perm(k)] = (signed char)c;
+      if (n < Np) {
+        w8[0][(size_t)n * Kp[0] + k] = (signed char)c;
+        w8[1][(size_t)n * Kp[1] + perm(k)] = (signed char)c;
+      } else {
+        wnx[0][k] = (signed char)c;
+        wnx[1][perm(k)] = (signed char)c;
+      }
     }
   }
   out->Kfull = Kfull; out->Nfull = Nfull; out->Kp[0] = Kp[0]; out->Kp[1] = Kp[1]; out->Np = Np; out->KV = KV;
+  out->xn = xn;
   for (int o = 0; o < 2; ++o) {
     S5_CUDA(cudaMalloc(&out->W8[o], w8[o].size()));
     S5_CUDA(cudaMemcpy(out->W8[o], w8[o].data(), w8[o].size(), cudaMemcpyHostToDevice));
+    S5_CUDA(cudaMalloc(&out->WN[o], wnx[o].size()));
+    S5_CUDA(cudaMemcpy(out->WN[o], wnx[o].data(), wnx[o].size(), cudaMemcpyHostToDevice));
   }
   int rc;
   if ((rc = upload_f(cs, &out->col_scale))) return rc;
@@ -949,14 +996,14 @@ int tc_linear_build(const float* W, int Kfull, int Nfull, float s_in, TcLinearDe
 }
 
 void tc_linear_free(TcLinearDev* d) {
-  cudaFree(d->W8[0]); cudaFree(d->W8[1]); cudaFree(d->col_scale);
+  cudaFree(d->W8[0]); cudaFree(d->W8[1]); cudaFree(d->WN[0]); cudaFree(d->WN[1]); cudaFree(d->col_scale);
   *d = TcLinearDev();
 }
 
-template <bool VEC4, int KV, bool BN>
+template <bool VEC4, int KV, bool BN, bool XN>
 static int tc_linear_go(const TcLinParams& p0, int kclass, cudaStream_t st) {
   TcLinParams p = p0;
-  auto kernel = tc_linear_kernel<VEC4, KV, BN>;
+  auto kernel = tc_linear_kernel<VEC4, KV, BN, XN>;
   const size_t w_bytes = tc_tile_bytes8(p.Np, p.Kp), a2 = 2 * tc_tile_bytes8(kTcRows, p.Kp);
   // output columns per pass: as wide as possible while two CTAs (2 x 8 warps, 2 x 256 TMEM columns) share an SM
   size_t smem = 0;
@@ -993,14 +1040,21 @@ int tc_linear_launch(const TcLinearDev& d, const float* X, float* Y, long long r
   p.out_qmin = out_qmin; p.out_qmax = out_qmax; p.relu = relu;
   const bool vec4 = (d.Kfull & 3) == 0 && aligned16(X);
   p.W8 = d.W8[vec4 ? 0 : 1];
+  p.WN = d.WN[vec4 ? 0 : 1];
   p.Kp = d.Kp[vec4 ? 0 : 1];
   const bool bn = in_sub != nullptr;
-  if (d.KV == 1) {
-    if (vec4) return bn ? tc_linear_go<true, 1, true>(p, kclass, st) : tc_linear_go<true, 1, false>(p, kclass, st);
-    return bn ? tc_linear_go<false, 1, true>(p, kclass, st) : tc_linear_go<false, 1, false>(p, kclass, st);
+  // instantiated combinations: BatchNorm only occurs on the B projection (no extra column), the extra column only
+  // on 16-byte aligned inputs (decoder)
+  if (d.xn) {
+    if (!vec4 || bn) S5_FAIL(S5_E_BADARG, "dense-tile linear: extra output column needs aligned rows and no BatchNorm");
+    return d.KV == 1 ? tc_linear_go<true, 1, false, true>(p, kclass, st) : tc_linear_go<true, 2, false, true>(p, kclass, st);
   }
-  if (vec4) return bn ? tc_linear_go<true, 2, true>(p, kclass, st) : tc_linear_go<true, 2, false>(p, kclass, st);
-  return bn ? tc_linear_go<false, 2, true>(p, kclass, st) : tc_linear_go<false, 2, false>(p, kclass, st);
+  if (d.KV == 1) {
+    if (vec4) return bn ? tc_linear_go<true, 1, true, false>(p, kclass, st) : tc_linear_go<true, 1, false, false>(p, kclass, st);
+    return bn ? tc_linear_go<false, 1, true, false>(p, kclass, st) : tc_linear_go<false, 1, false, false>(p, kclass, st);
+  }
+  if (vec4) return bn ? tc_linear_go<true, 2, true, false>(p, kclass, st) : tc_linear_go<true, 2, false, false>(p, kclass, st);
+  return bn ? tc_linear_go<false, 2, true, false>(p, kclass, st) : tc_linear_go<false, 2, false, false>(p, kclass, st);
 }
 
 

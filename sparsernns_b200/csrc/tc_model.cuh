@@ -9,6 +9,8 @@ namespace s5 {
 struct TcLinearDev {
   int Kfull = 0, Nfull = 0, Kp[2] = {0, 0}, Np = 0, KV = 0;
   signed char* W8[2] = {nullptr, nullptr};   // int8 codes [Np][Kp]: K in natural order / in the lane-interleaved order
+  signed char* WN[2] = {nullptr, nullptr};   // codes of the extra output column (xn), same two orders
+  bool xn = false;
   float* col_scale = nullptr;
   bool ok = false;
 };
