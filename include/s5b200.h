@@ -65,7 +65,10 @@ void s5b200_reset_launch_count(void);
 enum s5_kernel_class {
   S5_K_ENC = 0, S5_K_BPROJ = 1, S5_K_SCAN_C64 = 2, S5_K_GLU = 3, S5_K_DEC = 4,
   S5_K_FXP_ENC = 5, S5_K_FXP_BN = 6, S5_K_FXP_BPROJ = 7, S5_K_SCAN_I32 = 8, S5_K_FXP_GLU = 9,
-  S5_K_FXP_RESID = 10, S5_K_FXP_DEC = 11, S5_K_OTHER = 12, S5_K_COUNT = 13
+  S5_K_FXP_RESID = 10, S5_K_FXP_DEC = 11, S5_K_OTHER = 12,
+  S5_K_GLU_SCAN = 13,  /* recurrence + C projection + GLU in one kernel */
+  S5_K_BLOCK = 14,     /* B projection + recurrence + C projection + GLU: one kernel per S5 block */
+  S5_K_COUNT = 15
 };
 int s5b200_profile_begin(void);
 int s5b200_profile_end(double* ms_per_class, long long* launches_per_class);

@@ -17,7 +17,7 @@ FLOAT, STATIC = 0, 1
 ACT_GELU_TANH, ACT_RELU = 0, 1
 F32, I32 = 0, 1
 KERNEL_CLASSES = ["enc", "bproj", "scan_c64", "glu", "dec", "fxp_enc", "fxp_bn", "fxp_bproj", "scan_i32", "fxp_glu",
-                  "fxp_resid", "fxp_dec", "other"]
+                  "fxp_resid", "fxp_dec", "other", "glu_scan", "block"]
 
 c_float_p = C.POINTER(C.c_float)
 c_int32_p = C.POINTER(C.c_int32)

@@ -1141,7 +1141,7 @@ template <int HJ, bool SCAN, bool BPJ>
 static int tc_glu_go(const TcGluParams& p, size_t smem, int grid, cudaStream_t st) {
   auto kernel = tc_glu_kernel<HJ, SCAN, BPJ>;
   S5_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  ProfScope prof(S5_K_GLU, st);
+  ProfScope prof(BPJ ? S5_K_BLOCK : SCAN ? S5_K_GLU_SCAN : S5_K_GLU, st);
   kernel<<<grid, kGluThreads, smem, st>>>(p);
   S5_LAUNCH_CHECK();
   return S5_OK;
