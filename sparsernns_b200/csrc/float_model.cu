@@ -327,7 +327,7 @@ struct s5_model {
   s5_model_desc desc;
   s5::SparseDev enc, dec;
   s5::TcLinearDev enc_tc, dec_tc;
-  long long tc_min_rows = 4096;  // below this the compressed CUDA-core kernels are used
+  long long tc_min_rows = 512;   // below this the compressed CUDA-core kernels are used (one 3751-frame clip: 141 us dense-tile, 312 us CUDA-core)
   bool fuse_scan = true;         // static dense-tile path: run the recurrence inside the GLU kernel (S5B200_FUSE_SCAN=0 disables)
   bool fuse_bproj = true;        // ... and the B projection as well: one kernel per block (S5B200_FUSE_BPROJ=0 disables)
   float *enc_bias = nullptr, *dec_bias = nullptr;
