@@ -389,6 +389,142 @@ __global__ void __launch_bounds__(kTcThreads, 2) tc_linear_kernel(TcLinParams p)
   if (warp == 0) tc_dealloc(tmem_slot, 256);
 }
 
+// ------------------------------------------------------------------------------------------- decoder (wide, odd N)
+// Dense layer with K <= 128 aligned input columns and Nfull = Np + 1 <= 257 output columns whose rows are contiguous
+// in memory (decoder: 96 -> 257).  The 1028-byte output rows are not 16-byte aligned, but a 128-row tile of them is one
+// contiguous, 16-byte aligned block: the tile is assembled in shared memory with the global row pitch and leaves as ONE
+// asynchronous bulk copy (TMA engine) that overlaps the next tile.  One CTA of 16 warps per SM, N = Np in a single
+// MMA pass (2 x 256 TMEM columns), the extra column on the CUDA cores.
+constexpr int kDecThreads = 512;
+
+__global__ void __launch_bounds__(kDecThreads, 1) tc_dec_kernel(TcLinParams p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int Kp = p.Kp, Np = p.Np, Nf = p.Nfull;
+  const size_t a_bytes = tc_tile_bytes8(kTcRows, Kp);
+  unsigned char* Wt = smem;                                   // [Np][Kp] weight codes
+  unsigned char* Ah = Wt + tc_tile_bytes8(Np, Kp);
+  unsigned char* Al = Ah + a_bytes;
+  float* outT = reinterpret_cast<float*>(Al + a_bytes);       // [128][Nf] with the pitch of the global rows
+  float2* cst = reinterpret_cast<float2*>(outT + (size_t)kTcRows * Nf);   // per column: (s_in s_w / s_out, bias / s_out)
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  __shared__ int extra_n[kTcRows];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr int NW = kDecThreads / 32;
+  if (warp == 0) tc_alloc(&tmem_slot, 512);
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+  }
+  tc_load_weights8(Wt, p.W8, Np, Kp);
+  for (size_t i = (size_t)tid * 16; i < 2 * a_bytes; i += kDecThreads * 16) *reinterpret_cast<int4*>(Ah + i) = make_int4(0, 0, 0, 0);
+  for (int n = tid; n < Nf; n += kDecThreads) {
+    const float oinv = (n & 1) ? p.out_inv1 : p.out_inv0;
+    cst[n] = make_float2(p.col_scale[n] * oinv, p.bias ? p.bias[n] * oinv : 0.f);
+  }
+  const uint32_t lbo = tc_lbo(kTcRows);
+  const uint32_t loff = (uint32_t)(lane >> 2) * lbo + 4u * (lane & 3);
+  const bool wval = 4 * lane < Kp;
+  const int kcol = 4 * lane < p.Kfull ? 4 * lane : 0;
+  int wn[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) wn[e] = wval ? (int)p.WN[4 * lane + e] : 0;
+  const float inv = p.in_inv, qmin = p.in_qmin, qmax = p.in_qmax;
+  const float oqmin = p.relu ? fmaxf(p.out_qmin, 0.f) : p.out_qmin, oqmax = p.out_qmax, os0 = p.out_scale0, os1 = p.out_scale1;
+  const int erow0 = (warp & 3) * 32, erow = erow0 + lane;
+  const uint32_t lane_base = (uint32_t)erow0 << 16;
+  const int cw = Np >> 2, cbeg = (warp >> 2) * cw;            // 4 column groups
+  uint32_t phase = 0;
+  __syncthreads();
+  const uint32_t taddr = tmem_slot;
+  // contiguous row range per CTA, boundaries on multiples of 4 rows (16-byte alignment of the tile in global memory)
+  const long long rb4 = (p.rows * blockIdx.x / gridDim.x) & ~3LL;
+  const long long re4 = blockIdx.x + 1 == gridDim.x ? p.rows : (p.rows * (blockIdx.x + 1) / gridDim.x) & ~3LL;
+  const long long last_row = p.rows - 1;
+  constexpr int RB = 8;                                       // 16 warps x 8 rows: the whole tile is one batch
+  float4 raw[RB];
+  auto load_batch = [&](long long r0) {
+#pragma unroll
+    for (int q = 0; q < RB; ++q)
+      raw[q] = *reinterpret_cast<const float4*>(p.X + (size_t)min(r0 + warp * RB + q, last_row) * p.x_stride + kcol);
+  };
+  if (rb4 < re4) load_batch(rb4);
+  for (long long row0 = rb4; row0 < re4; row0 += kTcRows) {
+    const int rv = (int)min((long long)kTcRows, re4 - row0);
+    // ---- stage this warp's 8 rows (requested during the previous tile)
+#pragma unroll
+    for (int q = 0; q < RB; ++q) {
+      const int r = warp * RB + q;
+      const float xv[4] = {raw[q].x, raw[q].y, raw[q].z, raw[q].w};
+      uint32_t b[4];
+      int part = 0;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        b[e] = quant_bits(xv[e], inv, qmin, qmax);
+        part += (int)(short)b[e] * wn[e];
+      }
+      uint32_t lo, hi;
+      split_planes(b[0], b[1], b[2], b[3], lo, hi);
+      if (wval) {
+        *reinterpret_cast<uint32_t*>(Ah + loff + (uint32_t)r * 16u) = hi;
+        *reinterpret_cast<uint32_t*>(Al + loff + (uint32_t)r * 16u) = lo;
+      }
+      part = __reduce_add_sync(0xffffffffu, part);
+      if (lane == 0) extra_n[r] = part;
+    }
+    if (tid == 0) bulk_wait_read0();                          // the previous tile has left the output tile
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (tid == 0) {
+      tc_issue8(taddr, Ah, Wt, Kp, Np, Np, true);
+      tc_issue8(taddr + 256, Al, Wt, Kp, Np, Np, false);
+      tc_commit(&bar);
+    }
+    if (row0 + kTcRows < re4) load_batch(row0 + kTcRows);     // next tile's rows travel during MMA + epilogue
+    mbar_wait(&bar, phase);
+    phase ^= 1;
+    tc_fence_after();
+    // ---- epilogue: thread = row, 4-byte stores with the odd row pitch (conflict-free)
+    if (erow0 < rv) {
+      float* orow = outT + (size_t)erow * Nf;
+      for (int c0 = cbeg; c0 < cbeg + cw; c0 += 8) {
+        uint32_t vh[8], vl[8];
+        tc_ld8(taddr + lane_base + c0, vh);
+        tc_ld8(taddr + lane_base + 256 + c0, vl);
+        tc_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+          const float4 c2 = *reinterpret_cast<const float4*>(cst + c0 + j);
+          const float f0 = __int2float_rn((int)vh[j] * 256 + (int)vl[j]);
+          const float f1 = __int2float_rn((int)vh[j + 1] * 256 + (int)vl[j + 1]);
+          orow[c0 + j] = round_clip(fmaf(f0, c2.x, c2.y), oqmin, oqmax) * os0;
+          orow[c0 + j + 1] = round_clip(fmaf(f1, c2.z, c2.w), oqmin, oqmax) * os1;
+        }
+      }
+    }
+    if (tid < rv) {                                           // the extra column
+      const float2 c = cst[Nf - 1];
+      outT[(size_t)tid * Nf + Nf - 1] = round_clip(fmaf(__int2float_rn(extra_n[tid]), c.x, c.y), oqmin, oqmax) * (((Nf - 1) & 1) ? os1 : os0);
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    // ---- one bulk copy for the whole tile; up to 3 rows that would break the 16-byte size rule go by hand
+    const int rv4 = rv & ~3;
+    if (tid == 0 && rv4 > 0) {
+      bulk_s2g(p.Y + (size_t)row0 * Nf, outT, (uint32_t)((size_t)rv4 * Nf * 4));
+      bulk_commit();
+    }
+    for (int i = tid; i < (rv - rv4) * Nf; i += kDecThreads) p.Y[(size_t)(row0 + rv4) * Nf + i] = outT[(size_t)rv4 * Nf + i];
+  }
+  if (tid == 0) bulk_wait0();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc_dealloc(tmem_slot, 512);
+}
+
 // ------------------------------------------------------------------------------------------- C projection + GLU
 struct TcGluParams {
   const float* XS;   // [rows][2P] scan output (complex64 interleaved, ReLU applied)
@@ -672,9 +808,17 @@ __global__ void __launch_bounds__(kGluThreads, 1) tc_glu_kernel(TcGluParams p) {
         }
         uint32_t* flag_row = p.flags + (size_t)clip * p.tiles_per_clip;
         float2* rec_row = p.recs + (size_t)clip * p.tiles_per_clip * 2 * P;
-        const bool publish = chunk + 1 < p.tiles_per_clip;    // nobody looks back at the last tile of a clip
+        // Fixed-stride look-back.  Every tile publishes its aggregate (flag 1); every kStride-th tile (an "anchor") also
+        // publishes its inclusive prefix (flag 2).  The carry-in of tile k is ALWAYS
+        //     incl[a], then Horner over agg[a+1 .. k-1],   a = the last anchor before k,
+        // so the floating-point association is fixed: results do not depend on timing, batching or sharding (a classic
+        // decoupled look-back takes whatever prefix happens to be published and is not bit-reproducible).  All flags
+        // and records of the walk (<= kStride of each) are requested together: two round trips, not 2 per predecessor.
+        constexpr int kStride = 4;
+        const bool last = chunk + 1 >= p.tiles_per_clip;      // nobody looks back at the last tile of a clip
+        const bool anchor = (chunk % kStride) == 0;
         float2 carry = make_float2(0.f, 0.f);
-        if (publish) {
+        if (!last) {
           __stcg(rec_row + ((size_t)chunk * 2 + (chunk == 0 ? 1 : 0)) * P + sp, e);   // tile 0: aggregate == inclusive prefix
           // records -> barrier among the carry threads -> release store of the flag by one of them: the release is
           // cumulative over the writes ordered before it by the barrier, no __threadfence needed
@@ -682,22 +826,26 @@ __global__ void __launch_bounds__(kGluThreads, 1) tc_glu_kernel(TcGluParams p) {
           if (htid == 0) st_release_u32(flag_row + chunk, chunk == 0 ? 2u : 1u);
         }
         if (chunk > 0) {
-          // decoupled look-back: walk the predecessors until one has published its inclusive prefix.  (Reading a window
-          // of 8 flags / records at once was measured slower: the extra live registers spill the 64 held Bu values.)
-          float2 mult = make_float2(1.f, 0.f);
-          for (int j = chunk - 1; j >= 0; --j) {
-            uint32_t f;
-            do {
-              f = ld_acquire_u32(flag_row + j);
-            } while (f == 0u);
-            const float2 w = __ldcg(rec_row + ((size_t)j * 2 + (f == 2u ? 1 : 0)) * P + sp);
-            carry = cfmaf(mult, w, carry);
-            if (f == 2u) break;
-            mult = cmulf(mult, lamR);
-          }
-          if (publish) {
+          const int a0 = ((chunk - 1) / kStride) * kStride;   // anchor
+          const int n = chunk - a0;                           // records to read: incl[a0], agg[a0 + 1 .. chunk - 1]
+          uint32_t f[kStride];
+#pragma unroll
+          for (int w = 0; w < kStride; ++w) f[w] = w < n ? ld_acquire_u32(flag_row + a0 + w) : 2u;
+          while (f[0] != 2u) f[0] = ld_acquire_u32(flag_row + a0);
+#pragma unroll
+          for (int w = 1; w < kStride; ++w)
+            while (f[w] == 0u) f[w] = ld_acquire_u32(flag_row + a0 + w);
+          float2 rec[kStride];
+#pragma unroll
+          for (int w = 0; w < kStride; ++w)
+            if (w < n) rec[w] = __ldcg(rec_row + ((size_t)(a0 + w) * 2 + (w == 0 ? 1 : 0)) * P + sp);
+          carry = rec[0];
+#pragma unroll
+          for (int w = 1; w < kStride; ++w)
+            if (w < n) carry = cfmaf(lamR, carry, rec[w]);
+          if (anchor && !last) {
             __stcg(rec_row + ((size_t)chunk * 2 + 1) * P + sp, cfmaf(M, carry, e));
-              asm volatile("bar.sync %0, %1;" ::"r"(3 + half), "r"(P) : "memory");
+            asm volatile("bar.sync %0, %1;" ::"r"(3 + half), "r"(P) : "memory");
             if (htid == 0) st_release_u32(flag_row + chunk, 2u);
           }
         }
@@ -1047,6 +1195,17 @@ int tc_linear_launch(const TcLinearDev& d, const float* X, float* Y, long long r
   // on 16-byte aligned inputs (decoder)
   if (d.xn) {
     if (!vec4 || bn) S5_FAIL(S5_E_BADARG, "dense-tile linear: extra output column needs aligned rows and no BatchNorm");
+    // wide decoder: contiguous output rows, the whole N in one MMA pass, one bulk copy per tile
+    static const bool dec_tma = [] { const char* e = getenv("S5B200_DEC_TMA"); return !e || atoi(e) != 0; }();
+    const size_t dsm = tc_tile_bytes8(d.Np, p.Kp) + 2 * tc_tile_bytes8(kTcRows, p.Kp) + (size_t)kTcRows * d.Nfull * 4 + (size_t)d.Nfull * sizeof(float2);
+    if (dec_tma && d.KV == 1 && d.Np <= 256 && (d.Np & 31) == 0 && aligned16(Y) && dsm + 2048 <= 227 * 1024) {
+      S5_CUDA(cudaFuncSetAttribute(tc_dec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
+      const int grid = (int)std::max<long long>(1, std::min<long long>((rows + 63) / 64, (long long)sm_count()));
+      ProfScope prof(kclass, st);
+      tc_dec_kernel<<<grid, kDecThreads, dsm, st>>>(p);
+      S5_LAUNCH_CHECK();
+      return S5_OK;
+    }
     return d.KV == 1 ? tc_linear_go<true, 1, false, true>(p, kclass, st) : tc_linear_go<true, 2, false, true>(p, kclass, st);
   }
   if (d.KV == 1) {
