@@ -389,6 +389,192 @@ __global__ void __launch_bounds__(kTcThreads, 2) tc_linear_kernel(TcLinParams p)
   if (warp == 0) tc_dealloc(tmem_slot, 256);
 }
 
+// ------------------------------------------------------------------------------------------- encoder (odd K)
+// Dense layer whose input rows are contiguous but NOT 16-byte aligned (encoder: 257 floats = 1028 bytes per frame).
+// A block of 4n rows is contiguous and 16-byte aligned, so the raw rows are streamed by the TMA engine into a ring of
+// three 32-row buffers (one bulk copy each, mbarrier completion) while the SM converts / multiplies / post-processes
+// earlier rows: loads never stop, and no load instruction is issued by the warps at all.  One CTA of 16 warps per SM.
+// K order: lane-interleaved inside each 128-column block (conflict-free 4-byte shared loads with the odd row pitch).
+constexpr int kEncThreads = 512;
+constexpr int kEncSub = 32;        // rows per ring buffer
+constexpr int kEncRing = 3;
+
+template <int KV>
+__global__ void __launch_bounds__(kEncThreads, 1) tc_enc_kernel(TcLinParams p) {
+  TC_TRACE_ENTRY
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int Kp = p.Kp, Np = p.Np, Kf = p.Kfull;
+  const size_t a_bytes = tc_tile_bytes8(kTcRows, Kp);
+  const int ld_out = Np + 4;
+  unsigned char* Wt = smem;                                   // [Np][Kp] weight codes
+  unsigned char* Ah = Wt + tc_tile_bytes8(Np, Kp);
+  unsigned char* Al = Ah + a_bytes;
+  float* outT = reinterpret_cast<float*>(Ah);                 // output tile [128][Np + 4], aliases the dead planes
+  const size_t raw_bytes = (((size_t)kEncSub * Kf * 4) + 127) & ~(size_t)127;
+  unsigned char* rawb = Al + a_bytes;                         // ring of raw row buffers [32][Kf] floats
+  float2* cst = reinterpret_cast<float2*>(rawb + kEncRing * raw_bytes);
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ __align__(8) uint64_t full[kEncRing];
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr int NW = kEncThreads / 32;
+  if (warp == 0) tc_alloc(&tmem_slot, 256);
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    for (int i = 0; i < kEncRing; ++i) mbar_init(&full[i], 1);
+    fence_mbar_init();
+  }
+  tc_load_weights8(Wt, p.W8, Np, Kp);
+  for (size_t i = (size_t)tid * 16; i < 2 * a_bytes; i += kEncThreads * 16) *reinterpret_cast<int4*>(Ah + i) = make_int4(0, 0, 0, 0);
+  for (int n = tid; n < Np; n += kEncThreads) {
+    const float oinv = (n & 1) ? p.out_inv1 : p.out_inv0;
+    cst[n] = n < p.Nfull ? make_float2(p.col_scale[n] * oinv, p.bias ? p.bias[n] * oinv : 0.f) : make_float2(0.f, 0.f);
+  }
+  const uint32_t lbo = tc_lbo(kTcRows);
+  uint32_t loff[KV];
+  int kq[KV][4];
+#pragma unroll
+  for (int i = 0; i < KV; ++i) {
+    loff[i] = (uint32_t)(8 * i + (lane >> 2)) * lbo + 4u * (lane & 3);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) kq[i][e] = min(128 * i + lane + 32 * e, Kf - 1);   // pad columns meet zero weights
+  }
+  const bool tail = Kf > 128 * KV;
+  const float inv = p.in_inv, qmin = p.in_qmin, qmax = p.in_qmax;
+  const float oqmin = p.relu ? fmaxf(p.out_qmin, 0.f) : p.out_qmin, oqmax = p.out_qmax, os0 = p.out_scale0, os1 = p.out_scale1;
+  const int erow0 = (warp & 3) * 32, erow = erow0 + lane;
+  const uint32_t lane_base = (uint32_t)erow0 << 16;
+  const int cw = Np >> 2, cbeg = (warp >> 2) * cw;            // 4 column groups (Np multiple of 32)
+  __syncthreads();
+  const uint32_t taddr = tmem_slot;
+  // contiguous row range per CTA, boundaries on multiples of 4 rows (16-byte alignment of the bulk copies)
+  const long long rb4 = (p.rows * blockIdx.x / gridDim.x) & ~3LL;
+  const long long re4 = blockIdx.x + 1 == gridDim.x ? p.rows : (p.rows * (blockIdx.x + 1) / gridDim.x) & ~3LL;
+  const int nsub = (int)((re4 - rb4 + kEncSub - 1) / kEncSub);
+  auto issue = [&](int sidx) {                                // thread 0: request sub-tile sidx into its ring slot
+    const long long r0 = rb4 + (long long)sidx * kEncSub;
+    const int nr = (int)min((long long)kEncSub, re4 - r0) & ~3;   // whole groups of 4 rows; the rest is copied by hand
+    const uint32_t bytes = (uint32_t)nr * Kf * 4u;
+    uint64_t* fb = &full[sidx % kEncRing];
+    if (bytes) {
+      mbar_expect_tx(fb, bytes);
+      bulk_g2s(rawb + (size_t)(sidx % kEncRing) * raw_bytes, p.X + (size_t)r0 * Kf, bytes, fb);
+    } else {
+      mbar_arrive(fb);
+    }
+  };
+  if (tid == 0)
+    for (int i = 0; i < kEncRing && i < nsub; ++i) issue(i);
+  uint32_t phase = 0;
+  TC_TRACE_DECL
+  for (int sidx = 0; sidx < nsub; ++sidx) {
+    TC_TRACE_MARK(tid == 0);
+    const long long r0 = rb4 + (long long)sidx * kEncSub;
+    const int nr = (int)min((long long)kEncSub, re4 - r0);
+    const int slot = sidx % kEncRing;
+    float* raw = reinterpret_cast<float*>(rawb + (size_t)slot * raw_bytes);
+    const int trow0 = (sidx & 3) * kEncSub;                   // position of the sub-tile inside the 128-row tile
+    mbar_wait(&full[slot], (uint32_t)(sidx / kEncRing) & 1u);
+    TC_TRACE_MARK(tid == 0);
+    if ((nr & 3) && tid < (nr & 3) * 32) {                    // <= 3 rows at the very end of the input: plain loads
+      const int rr = (nr & ~3) + (tid >> 5);
+      for (int k = tid & 31; k < Kf; k += 32) raw[(size_t)rr * Kf + k] = p.X[(size_t)(r0 + rr) * Kf + k];
+    }
+    if (nr & 3) __syncthreads();
+    // ---- convert: warp w owns rows 2w, 2w + 1 of the sub-tile
+#pragma unroll
+    for (int q = 0; q < kEncSub / NW; ++q) {
+      const int r = warp * (kEncSub / NW) + q;
+      const float* xr = raw + (size_t)min(r, nr - 1) * Kf;
+      const uint32_t roff = (uint32_t)(trow0 + r) * 16u;
+#pragma unroll
+      for (int i = 0; i < KV; ++i) {
+        uint32_t b[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) b[e] = quant_bits(xr[kq[i][e]], inv, qmin, qmax);
+        uint32_t lo, hi;
+        split_planes(b[0], b[1], b[2], b[3], lo, hi);
+        *reinterpret_cast<uint32_t*>(Ah + loff[i] + roff) = hi;
+        *reinterpret_cast<uint32_t*>(Al + loff[i] + roff) = lo;
+      }
+      if (tail && lane == 0) {
+        const uint32_t bt = quant_bits(xr[128 * KV], inv, qmin, qmax);
+        *reinterpret_cast<uint32_t*>(Ah + (size_t)(8 * KV) * lbo + roff) = (bt >> 8) & 0xFFu;
+        *reinterpret_cast<uint32_t*>(Al + (size_t)(8 * KV) * lbo + roff) = bt & 0xFFu;
+      }
+    }
+    const bool tile_done = (sidx & 3) == 3 || sidx + 1 == nsub;
+    if (tile_done) {
+      fence_proxy_async_smem();
+      tc_fence_before();
+    }
+    __syncthreads();                                          // the ring slot is free; (tile_done) the planes are complete
+    if (tid == 0 && sidx + kEncRing < nsub) issue(sidx + kEncRing);
+    if (!tile_done) continue;
+    TC_TRACE_MARK(tid == 0);
+    tc_fence_after();
+    if (tid == 0) {
+      tc_issue8(taddr, Ah, Wt, Kp, Np, Np, true);
+      tc_issue8(taddr + 128, Al, Wt, Kp, Np, Np, false);
+      tc_commit(&bar);
+    }
+    const long long row0 = rb4 + (long long)(sidx & ~3) * kEncSub;
+    const int rv = (int)min((long long)kTcRows, re4 - row0);
+    mbar_wait(&bar, phase);
+    phase ^= 1;
+    tc_fence_after();
+    TC_TRACE_MARK(tid == 0);
+    // ---- epilogue -> padded shared tile (over the dead planes)
+    if (erow0 < rv) {
+      for (int c0 = cbeg; c0 < cbeg + cw; c0 += 8) {
+        uint32_t vh[8], vl[8];
+        tc_ld8(taddr + lane_base + c0, vh);
+        tc_ld8(taddr + lane_base + 128 + c0, vl);
+        tc_wait_ld();
+        float out[8];
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+          const float4 c2 = *reinterpret_cast<const float4*>(cst + c0 + j);
+          const float f0 = __int2float_rn((int)vh[j] * 256 + (int)vl[j]);
+          const float f1 = __int2float_rn((int)vh[j + 1] * 256 + (int)vl[j + 1]);
+          out[j] = round_clip(fmaf(f0, c2.x, c2.y), oqmin, oqmax) * os0;
+          out[j + 1] = round_clip(fmaf(f1, c2.z, c2.w), oqmin, oqmax) * os1;
+        }
+        float* dst = outT + (size_t)erow * ld_out + c0;
+        *reinterpret_cast<float4*>(dst) = make_float4(out[0], out[1], out[2], out[3]);
+        *reinterpret_cast<float4*>(dst + 4) = make_float4(out[4], out[5], out[6], out[7]);
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+    TC_TRACE_MARK(tid == 0);
+    // ---- write-out, coalesced 16-byte stores (output rows are Nfull floats, 16-byte aligned)
+    {
+      const int q4 = p.Nfull >> 2;
+      const int rpi = q4 >= 32 ? 1 : 32 / q4;
+      const int lr = lane / q4, lc = lane - lr * q4;
+      if (lr < rpi) {
+        for (int rb = warp * rpi + lr; rb < rv; rb += 2 * NW * rpi) {
+          float4 v[2];
+#pragma unroll
+          for (int q = 0; q < 2; ++q) v[q] = *reinterpret_cast<const float4*>(outT + (size_t)min(rb + q * NW * rpi, kTcRows - 1) * ld_out + 4 * lc);
+#pragma unroll
+          for (int q = 0; q < 2; ++q)
+            if (rb + q * NW * rpi < rv)
+              *reinterpret_cast<float4*>(p.Y + (size_t)(row0 + rb + q * NW * rpi) * p.y_stride + 4 * lc) = v[q];
+        }
+      }
+    }
+    __syncthreads();                                          // the planes may be overwritten again
+    TC_TRACE_MARK(tid == 0);
+    TC_TRACE_NEXT();
+  }
+  TC_TRACE_PRINT(tid == 0, "enc: [wait convert+sync] x4, mma, epi+sync, writeout+sync");
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc_dealloc(tmem_slot, 256);
+}
+
 // ------------------------------------------------------------------------------------------- decoder (wide, odd N)
 // Dense layer with K <= 128 aligned input columns and Nfull = Np + 1 <= 257 output columns whose rows are contiguous
 // in memory (decoder: 96 -> 257).  The 1028-byte output rows are not 16-byte aligned, but a 128-row tile of them is one
@@ -1207,6 +1393,21 @@ int tc_linear_launch(const TcLinearDev& d, const float* X, float* Y, long long r
       return S5_OK;
     }
     return d.KV == 1 ? tc_linear_go<true, 1, false, true>(p, kclass, st) : tc_linear_go<true, 2, false, true>(p, kclass, st);
+  }
+  // unaligned contiguous rows (encoder): TMA-fed raw-row ring, one CTA per SM
+  static const bool enc_tma = [] { const char* e = getenv("S5B200_ENC_TMA"); return !e || atoi(e) != 0; }();
+  if (enc_tma && !vec4 && !bn && aligned16(X) && aligned16(Y) && d.Np <= 128 && (d.Np & 31) == 0 && (d.Nfull & 3) == 0 && d.Nfull <= d.Np) {
+    const size_t raw_bytes = (((size_t)kEncSub * d.Kfull * 4) + 127) & ~(size_t)127;
+    const size_t esm = tc_tile_bytes8(d.Np, p.Kp) + 2 * tc_tile_bytes8(kTcRows, p.Kp) + kEncRing * raw_bytes + (size_t)d.Np * sizeof(float2);
+    if (esm + 2048 <= 227 * 1024 && 2 * tc_tile_bytes8(kTcRows, p.Kp) >= (size_t)kTcRows * (d.Np + 4) * 4) {
+      auto kernel = d.KV == 1 ? tc_enc_kernel<1> : tc_enc_kernel<2>;
+      S5_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esm));
+      const int grid = (int)std::max<long long>(1, std::min<long long>((rows + 63) / 64, (long long)sm_count()));
+      ProfScope prof(kclass, st);
+      kernel<<<grid, kEncThreads, esm, st>>>(p);
+      S5_LAUNCH_CHECK();
+      return S5_OK;
+    }
   }
   if (d.KV == 1) {
     if (vec4) return bn ? tc_linear_go<true, 1, true, false>(p, kclass, st) : tc_linear_go<true, 1, false, false>(p, kclass, st);
