@@ -880,7 +880,16 @@ __global__ void __launch_bounds__(kGluThreads, 1) tc_glu_kernel(TcGluParams p) {
   const bool relu_scan = p.relu_scan != 0;
   const float gl_s = p.gl_s, gr_s = p.gr_s, out_floor = p.relu_out ? 0.f : -INFINITY;
   const uint32_t poff = (uint32_t)(sp >> 2) * lbo + 4u * (sp & 3);   // plane offset of column k = 2 sp
-  for (long long it = SCAN ? pipe : row_begin; SCAN ? it < ntiles : it < row_end; it += SCAN ? npipe : (long long)kTcRows) {
+  // SCAN tile schedule: whole rounds go round-robin over the pipelines (t = round * G + pipe); the tiles of the last,
+  // partial round go to ONE pipeline per SM first (t = full * G + half * grid + blockIdx), so that an SM gets at most one
+  // tile more than any other.  Every pipeline still walks its tiles in increasing order, and a tile's predecessor
+  // (t - B) always belongs to an earlier round or to another, co-resident pipeline: the look-back cannot deadlock.
+  const long long full_rounds = SCAN ? ntiles / npipe : 0;
+  const long long last_j = (long long)half * gridDim.x + blockIdx.x;
+  const long long my_tiles = SCAN ? full_rounds + (last_j < ntiles - full_rounds * npipe ? 1 : 0) : 0;
+  long long iter = 0;
+  for (long long it0 = row_begin; SCAN ? iter < my_tiles : it0 < row_end; it0 += kTcRows, ++iter) {
+    const long long it = SCAN ? (iter < full_rounds ? iter * npipe + pipe : full_rounds * npipe + last_j) : it0;
     long long row0;
     int rv;
     int clip = 0, chunk = 0;
