@@ -330,6 +330,7 @@ struct s5_model {
   long long tc_min_rows = 512;   // below this the compressed CUDA-core kernels are used (one 3751-frame clip: 141 us dense-tile, 312 us CUDA-core)
   bool fuse_scan = true;         // static dense-tile path: run the recurrence inside the GLU kernel (S5B200_FUSE_SCAN=0 disables)
   bool fuse_bproj = true;        // ... and the B projection as well: one kernel per block (S5B200_FUSE_BPROJ=0 disables)
+  bool fuse_layers = true;       // ... and all blocks in one launch (S5B200_FUSE_LAYERS=0 disables)
   float *enc_bias = nullptr, *dec_bias = nullptr;
   std::vector<s5::LayerDev> layers;
   // host-buffer entry point: ring of device buffers, three streams (H2D | forward | D2H) and their events
@@ -362,7 +363,9 @@ static WsLayout ws_layout(const s5_model* m, int B, int L) {
   w.off_bu = 2 * act;
   // + 32 rows of slack: the fused recurrence reads whole 32-frame segments without clamping at the end of the buffer
   w.off_scan = w.off_bu + round_up((rows + 32) * m->desc.P * 2 * sizeof(float), 256);
-  w.scan_bytes = std::max(s5b200_scan_c64_workspace_bytes(B, L, m->desc.P), tc_glu_scan_workspace_bytes(B, L, m->desc.P));
+  // one look-back region per layer (all blocks may run in one launch) + the cross-layer done flags
+  const size_t glu_ws = round_up(tc_glu_scan_workspace_bytes(B, L, m->desc.P), 256);
+  w.scan_bytes = std::max(s5b200_scan_c64_workspace_bytes(B, L, m->desc.P), (size_t)(m->desc.n_layers + 1) * glu_ws);
   w.total = w.off_scan + round_up(w.scan_bytes, 256);
   return w;
 }
@@ -408,6 +411,38 @@ static GluParams glu_params(const s5_model* m, const LayerDev& ld, const float* 
   return p;
 }
 
+struct BlockPlan {
+  bool glu_tc, fuse_scan, fuse_bproj;
+};
+static BlockPlan block_plan(const s5_model* m, const LayerDev& ld, long long rows, bool ssm_only, bool want_xs) {
+  const bool sq = m->desc.flavour == S5_STATIC;
+  BlockPlan bp;
+  bp.glu_tc = sq && ld.tg.ok && !ssm_only && rows >= m->tc_min_rows && is_pow2(ld.sc.s_ut) && is_pow2(ld.sc.s_yt) &&
+              is_pow2(ld.sc.s_out2_act) && is_pow2(ld.sc.s_out2_out) && is_pow2(ld.sc.s_gate_left) && is_pow2(ld.sc.s_gate_right);
+  // the recurrence runs inside the GLU kernel (states never leave the SM) unless the caller wants to see them,
+  // and so does the B projection: the whole block is then one kernel
+  bp.fuse_scan = bp.glu_tc && m->fuse_scan && !want_xs && tc_glu_scan_ok(ld.tg);
+  bp.fuse_bproj = bp.fuse_scan && m->fuse_bproj && ld.tg.bpj_ok && is_pow2(ld.sc.s_But_re) && is_pow2(ld.sc.s_But_im);
+  return bp;
+}
+static TcGluArgs glu_args(const s5_model* m, const LayerDev& ld, const BlockPlan& bp, const float* x, float* out, float* bu, int B,
+                          int L, void* scan_ws, size_t scan_ws_bytes, bool bn) {
+  TcGluArgs a{};
+  a.XS = bu; a.X = x; a.OUT = out; a.rows = (long long)B * L;
+  if (bp.fuse_scan) {
+    a.lam = ld.lam; a.B = B; a.L = L; a.relu_scan = m->desc.relufication; a.scan_ws = scan_ws; a.scan_ws_bytes = scan_ws_bytes;
+    a.fuse_bproj = bp.fuse_bproj; a.s_bu_re = ld.sc.s_But_re; a.s_bu_im = ld.sc.s_But_im;
+  }
+  a.bn_sub = bn ? ld.bn_mean : nullptr; a.bn_mul = bn ? ld.bn_mul : nullptr; a.bn_add = bn ? ld.bn_bias : nullptr;
+  a.D = ld.D; a.o_bias = ld.o_bias;
+  a.s_ut = ld.sc.s_ut; a.s_yt = ld.sc.s_yt; a.s_o_act = ld.sc.s_out2_act; a.s_o_out = ld.sc.s_out2_out;
+  a.s_gl = ld.sc.s_gate_left; a.s_gr = ld.sc.s_gate_right;
+  qrange(m->desc.ssm_act_bits, &a.qs_min, &a.qs_max);
+  qrange(m->desc.non_ssm_act_bits, &a.qn_min, &a.qn_max);
+  a.relu_out = m->desc.relufication;
+  return a;
+}
+
 // One S5 block: x [rows][H] -> out [rows][H]; bu is the [rows][P] complex scratch (Bu, then xs in place).
 static int run_block(const s5_model* m, int li, const float* x, float* out, float* bu, int B, int L, void* scan_ws,
                      size_t scan_ws_bytes, bool bn, bool ssm_only, cudaStream_t st, bool want_xs = false) {
@@ -415,13 +450,8 @@ static int run_block(const s5_model* m, int li, const float* x, float* out, floa
   const long long rows = (long long)B * L;
   int rc;
   const bool sq = m->desc.flavour == S5_STATIC;
-  const bool glu_tc = sq && ld.tg.ok && !ssm_only && rows >= m->tc_min_rows && is_pow2(ld.sc.s_ut) && is_pow2(ld.sc.s_yt) &&
-                      is_pow2(ld.sc.s_out2_act) && is_pow2(ld.sc.s_out2_out) && is_pow2(ld.sc.s_gate_left) && is_pow2(ld.sc.s_gate_right);
-  // the recurrence runs inside the GLU kernel (states never leave the SM) unless the caller wants to see them,
-  // and so does the B projection: the whole block is then one kernel
-  const bool fuse_scan = glu_tc && m->fuse_scan && !want_xs && tc_glu_scan_ok(ld.tg);
-  const bool fuse_bproj = fuse_scan && m->fuse_bproj && ld.tg.bpj_ok && is_pow2(ld.sc.s_But_re) && is_pow2(ld.sc.s_But_im);
-  if (fuse_bproj) {
+  const BlockPlan bp = block_plan(m, ld, rows, ssm_only, want_xs);
+  if (bp.fuse_bproj) {
     // nothing to launch here
   } else if (sq && ld.tb.ok && rows >= m->tc_min_rows && is_pow2(ld.sc.s_ut) && is_pow2(ld.sc.s_But_re) && is_pow2(ld.sc.s_But_im)) {
     float qlo, qhi;
@@ -430,23 +460,8 @@ static int run_block(const s5_model* m, int li, const float* x, float* out, floa
                                ld.sc.s_ut, qlo, qhi, nullptr, ld.sc.s_But_re, ld.sc.s_But_im, qlo, qhi, 0, S5_K_BPROJ, st)))
       return rc;
   } else if ((rc = launch_linear(bproj_params(m, ld, x, bu, rows, bn), st, S5_K_BPROJ))) return rc;
-  if (!fuse_scan && (rc = launch_scan_c64(bu, ld.lam, bu, B, L, m->desc.P, m->desc.relufication, scan_ws, scan_ws_bytes, st))) return rc;
-  if (glu_tc) {
-    TcGluArgs a{};
-    a.XS = bu; a.X = x; a.OUT = out; a.rows = rows;
-    if (fuse_scan) {
-      a.lam = ld.lam; a.B = B; a.L = L; a.relu_scan = m->desc.relufication; a.scan_ws = scan_ws; a.scan_ws_bytes = scan_ws_bytes;
-      a.fuse_bproj = fuse_bproj; a.s_bu_re = ld.sc.s_But_re; a.s_bu_im = ld.sc.s_But_im;
-    }
-    a.bn_sub = bn ? ld.bn_mean : nullptr; a.bn_mul = bn ? ld.bn_mul : nullptr; a.bn_add = bn ? ld.bn_bias : nullptr;
-    a.D = ld.D; a.o_bias = ld.o_bias;
-    a.s_ut = ld.sc.s_ut; a.s_yt = ld.sc.s_yt; a.s_o_act = ld.sc.s_out2_act; a.s_o_out = ld.sc.s_out2_out;
-    a.s_gl = ld.sc.s_gate_left; a.s_gr = ld.sc.s_gate_right;
-    qrange(m->desc.ssm_act_bits, &a.qs_min, &a.qs_max);
-    qrange(m->desc.non_ssm_act_bits, &a.qn_min, &a.qn_max);
-    a.relu_out = m->desc.relufication;
-    return tc_glu_launch(ld.tg, a, st);
-  }
+  if (!bp.fuse_scan && (rc = launch_scan_c64(bu, ld.lam, bu, B, L, m->desc.P, m->desc.relufication, scan_ws, scan_ws_bytes, st))) return rc;
+  if (bp.glu_tc) return tc_glu_launch(ld.tg, glu_args(m, ld, bp, x, out, bu, B, L, scan_ws, scan_ws_bytes, bn), st);
   return launch_glu(glu_params(m, ld, bu, x, out, rows, bn, ssm_only), st);
 }
 
@@ -515,6 +530,7 @@ extern "C" int s5b200_model_create(const s5_model_desc* d, s5_model** out) {
   if (const char* e = getenv("S5B200_TC_MIN_ROWS")) m->tc_min_rows = atoll(e);
   if (const char* e = getenv("S5B200_FUSE_SCAN")) m->fuse_scan = atoi(e) != 0;
   if (const char* e = getenv("S5B200_FUSE_BPROJ")) m->fuse_bproj = atoi(e) != 0;
+  if (const char* e = getenv("S5B200_FUSE_LAYERS")) m->fuse_layers = atoi(e) != 0;
   const int H = d->H, P = d->P, dense = d->use_sparse ? 0 : 1;
   int rc = S5_OK;
   auto fail = [&](int code) { s5b200_model_destroy(m); return code; };
@@ -609,9 +625,28 @@ extern "C" int s5b200_model_forward(const s5_model* m, const float* x, float* y,
     if ((rc = tc_linear_launch(m->enc_tc, x, a, rows, nullptr, nullptr, nullptr, d.s_enc_act, nlo, nhi, m->enc_bias, d.s_enc_out,
                                d.s_enc_out, nlo, nhi, d.relufication, S5_K_ENC, st))) return rc;
   } else if ((rc = launch_linear(dense_params(m, m->enc, m->enc_bias, x, a, rows, d.s_enc_act, d.s_enc_out, d.relufication), st, S5_K_ENC))) return rc;
-  for (int i = 0; i < d.n_layers; ++i) {
-    if ((rc = run_block(m, i, a, b, bu, B, L, base + w.off_scan, w.scan_bytes, true, false, st))) return rc;
-    std::swap(a, b);
+  // all blocks in ONE launch when every layer runs the block kernel (S5B200_FUSE_LAYERS=0: one launch per block)
+  bool one_launch = m->fuse_layers && d.n_layers >= 2 && d.n_layers <= 4;
+  for (int i = 0; i < d.n_layers && one_launch; ++i)
+    one_launch = block_plan(m, m->layers[i], rows, false, false).fuse_bproj && m->layers[i].tg.H == m->layers[0].tg.H &&
+                 m->layers[i].tg.K1 == m->layers[0].tg.K1;
+  if (one_launch) {
+    const size_t glu_ws = round_up(tc_glu_scan_workspace_bytes(B, L, d.P), 256);
+    const TcGluDev* devs[4];
+    TcGluArgs args[4];
+    for (int i = 0; i < d.n_layers; ++i) {
+      const LayerDev& ld = m->layers[i];
+      devs[i] = &ld.tg;
+      args[i] = glu_args(m, ld, block_plan(m, ld, rows, false, false), a, b, bu, B, L, base + w.off_scan + (size_t)i * glu_ws, glu_ws, true);
+      std::swap(a, b);
+    }
+    if ((rc = tc_glu_launch_multi(devs, args, d.n_layers, reinterpret_cast<uint32_t*>(base + w.off_scan + (size_t)d.n_layers * glu_ws),
+                                  glu_ws, st))) return rc;
+  } else {
+    for (int i = 0; i < d.n_layers; ++i) {
+      if ((rc = run_block(m, i, a, b, bu, B, L, base + w.off_scan, w.scan_bytes, true, false, st))) return rc;
+      std::swap(a, b);
+    }
   }
   if (tc && m->dec_tc.ok && is_pow2(d.s_dec_act) && is_pow2(d.s_dec_out))
     return tc_linear_launch(m->dec_tc, a, y, rows, nullptr, nullptr, nullptr, d.s_dec_act, nlo, nhi, m->dec_bias, d.s_dec_out,

@@ -739,6 +739,16 @@ struct TcGluParams {
   float b_out_scale0, b_out_scale1, b_out_inv0, b_out_inv1;   // FQ grid of Re(Bu) / Im(Bu)
 };
 
+// All blocks of the model in ONE launch (block kernel only): the tiles of layer l + 1 follow those of layer l in the same
+// round-robin order, so a pipeline that would idle in the last, partial round of a layer starts on the next layer
+// instead.  Tile (l + 1, clip, chunk) reads exactly the rows tile (l, clip, chunk) wrote: one done-flag per tile.
+constexpr int kMaxFusedLayers = 4;
+struct TcGluMulti {
+  int nlayers;
+  uint32_t* done;              // [nlayers - 1][tiles per layer], zeroed per launch (nullptr when nlayers == 1)
+  TcGluParams layer[kMaxFusedLayers];
+};
+
 __device__ __forceinline__ float2 cmulf(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 __device__ __forceinline__ float2 cfmaf(float2 a, float2 x, float2 v) {   // a * x + v
   return make_float2(fmaf(a.x, x.x, fmaf(-a.y, x.y, v.x)), fmaf(a.x, x.y, fmaf(a.y, x.x, v.y)));
@@ -775,11 +785,12 @@ __device__ __forceinline__ uint32_t pack_bf2(float a, float b) {   // {lo half =
 // shared-memory tile that the recurrence threads read column-wise.  A whole S5 block is then ONE kernel that reads
 // the block input and writes the block output; Bu and the states never leave the SM.
 template <int HJ, bool SCAN, bool BPJ>
-__global__ void __launch_bounds__(kGluThreads, 1) tc_glu_kernel(TcGluParams p) {
+__global__ void __launch_bounds__(kGluThreads, 1) tc_glu_kernel(const __grid_constant__ TcGluMulti mp) {
   static_assert(SCAN || !BPJ, "the fused B projection needs the fused recurrence");
   TC_TRACE_ENTRY
   extern __shared__ __align__(128) unsigned char smem[];
-  const int H = p.H, K1 = p.K1;
+  const TcGluParams& p0 = mp.layer[0];
+  const int H = p0.H, K1 = p0.K1;                             // the same for every layer
   const int ldT = H + 4;                                      // floats per row of T
   const size_t wc_bytes = tc_tile_bytes(H, K1), wo_bytes = tc_tile_bytes8(H, kGluK2);
   const size_t p1_bytes = tc_tile_bytes(kTcRows, K1);         // one bf16 plane of the xs tile
@@ -795,8 +806,9 @@ __global__ void __launch_bounds__(kGluThreads, 1) tc_glu_kernel(TcGluParams p) {
   unsigned char* WB = Wo + wo_bytes;
   float* ob = reinterpret_cast<float*>(WB + wb_bytes);        // [H] out2 bias / s_o_out
   float* cstB = ob + H;                                       // [K1] s_u s_w / s_Bu (BPJ)
+  float* lcst = cstB + K1;                                    // [4][H] per-column constants of the lanes-along-columns passes
   const int tid = threadIdx.x, half = tid >> 8, htid = tid & (kGluHalf - 1), warp = htid >> 5, lane = tid & 31;
-  unsigned char* Rbase = reinterpret_cast<unsigned char*>(ob) + (((size_t)(H + K1) * 4 + 127) & ~(size_t)127);
+  unsigned char* Rbase = reinterpret_cast<unsigned char*>(ob) + (((size_t)(5 * H + K1) * 4 + 127) & ~(size_t)127);
   unsigned char* R = Rbase + (size_t)half * r_bytes;
   // SCAN: segment aggregates + multipliers [nseg][P] and the tile carry [P], behind the planes / the Bu tile
   float2* seg_agg = reinterpret_cast<float2*>(R + max(2 * p1_bytes, bu_bytes));
@@ -817,87 +829,131 @@ __global__ void __launch_bounds__(kGluThreads, 1) tc_glu_kernel(TcGluParams p) {
     mbar_init(&bar[1], 1);
     fence_mbar_init();
   }
-  tc_load_weights(Wc, reinterpret_cast<const __half*>(p.Wc), H, K1);
-  tc_load_weights8(Wo, p.Wo, H, kGluK2);
-  if constexpr (BPJ) {
-    tc_load_weights8(WB, p.WB, K1, kGluK2);
-    for (int n = tid; n < K1; n += kGluThreads) cstB[n] = p.b_col_scale[n] * ((n & 1) ? p.b_out_inv1 : p.b_out_inv0);
-  }
-  for (int n = tid; n < H; n += kGluThreads) ob[n] = p.o_bias[n] * p.oo_inv;
-  // the int8 planes carry a zero pad byte per lane (column 4 lane + 3 when HJ < 4): clear them once
-  for (size_t i = (size_t)htid * 16; i < 2 * a2_bytes; i += kGluHalf * 16) *reinterpret_cast<int4*>(A2h + i) = make_int4(0, 0, 0, 0);
-  // per-lane constants of the lanes-along-columns passes.  All scales are powers of two, so folding them into the
-  // BatchNorm / feed-through constants changes no rounding: (x - sub) * (mul / s_u) + add / s_u == BN(x) / s_u.
-  float bsub[HJ], bmulq[HJ], baddq[HJ], ddq[HJ];
-#pragma unroll
-  for (int j = 0; j < HJ; ++j) {
-    const int c = lane + 32 * j;
-    bsub[j] = p.bn_sub ? p.bn_sub[c] : 0.f;
-    bmulq[j] = (p.bn_sub ? p.bn_mul[c] : 1.f) * p.ut_inv;
-    baddq[j] = (p.bn_sub ? p.bn_add[c] : 0.f) * p.ut_inv;
-    ddq[j] = p.D[c] * p.ut_s * p.yt_inv;                      // D u / s_y = (D s_u / s_y) * code(u)
-  }
-  const float k_c = p.c_scale * p.yt_inv;                     // conj Re(C x) / s_y = acc * k_c
-  const float a_o = p.o_col_scale * p.oo_inv;
-  const float k_e = -p.oo_s * 1.4426950408889634f;            // exp(-o) = 2^(code(o) * k_e)
+  const long long last_row = p0.rows - 1;
+  const uint32_t lbo = tc_lbo(kTcRows);
   const bool kin = 4 * lane < K1;
   const int xs_col = kin ? 4 * lane : 0;                      // loads are never predicated: pad lanes / rows re-read valid data
-  const long long last_row = p.rows - 1;
-  const uint32_t lbo = tc_lbo(kTcRows);
   const uint32_t soff = (uint32_t)(lane >> 1) * lbo + (uint32_t)(lane & 1) * 8u;   // bf16 planes: k = 4 lane
   const uint32_t aoff = (uint32_t)(lane >> 2) * lbo + 4u * (lane & 3);             // int8 planes: bytes 4 lane .. 4 lane + 3
   const int erow0 = (warp & 3) * 32;                          // first tile row of this warp's TMEM lane quadrant
   const int erow = erow0 + lane;                              // TMEM lane = tile row
   const uint32_t lane_base = (uint32_t)erow0 << 16;
   const int cw = H >> 1, cbeg = (warp >> 2) * cw;             // column half of this warp in the TMEM passes
-  const float y_to_gl = p.yt_s * p.gl_inv, y_to_oa = p.yt_s * p.oa_inv;   // powers of two
-  const float qs_min = p.qs_min, qs_max = p.qs_max, qn_min = p.qn_min, qn_max = p.qn_max;
+  const float qs_min = p0.qs_min, qs_max = p0.qs_max, qn_min = p0.qn_min, qn_max = p0.qn_max;
   const float qrelu_min = fmaxf(qs_min, 0.f);
+  // SCAN per-thread constants: state, segment
+  const int P = K1 >> 1;
+  const int sp = SCAN ? htid % P : 0, sseg = SCAN ? htid / P : 0, nseg = SCAN ? kGluHalf / P : 1;
+  const int sr = SCAN ? (p0.R + nseg - 1) / nseg : 0;         // rows per segment (<= 32)
+  const uint32_t poff = (uint32_t)(sp >> 2) * lbo + 4u * (sp & 3);   // plane offset of column k = 2 sp
+  // ---- per-layer state: weight tiles in shared memory, per-lane constants in registers
+  // All scales are powers of two, so folding them into the BatchNorm / feed-through constants changes no rounding:
+  // (x - sub) * (mul / s_u) + add / s_u == BN(x) / s_u.
+  float2 lam = make_float2(0.f, 0.f), lamR = make_float2(1.f, 0.f), lamS = make_float2(1.f, 0.f);
+  auto load_layer = [&](int l) {                              // called by all threads of the CTA, between two __syncthreads
+    const TcGluParams& p = mp.layer[l];
+    tc_load_weights(Wc, reinterpret_cast<const __half*>(p.Wc), H, K1);
+    tc_load_weights8(Wo, p.Wo, H, kGluK2);
+    if constexpr (BPJ) {
+      tc_load_weights8(WB, p.WB, K1, kGluK2);
+      for (int n = tid; n < K1; n += kGluThreads) cstB[n] = p.b_col_scale[n] * ((n & 1) ? p.b_out_inv1 : p.b_out_inv0);
+    }
+    for (int n = tid; n < H; n += kGluThreads) ob[n] = p.o_bias[n] * p.oo_inv;
+    for (int c = tid; c < H; c += kGluThreads) {
+      lcst[c] = p.bn_sub ? p.bn_sub[c] : 0.f;
+      lcst[H + c] = (p.bn_sub ? p.bn_mul[c] : 1.f) * p.ut_inv;
+      lcst[2 * H + c] = (p.bn_sub ? p.bn_add[c] : 0.f) * p.ut_inv;
+      lcst[3 * H + c] = p.D[c] * p.ut_s * p.yt_inv;           // D u / s_y = (D s_u / s_y) * code(u)
+    }
+    if constexpr (SCAN) {
+      lam = p.lam[sp];
+      lamR = make_float2(1.f, 0.f); lamS = make_float2(1.f, 0.f);
+      float2 sq = lam;                                        // lam^R (full tile) and lam^sr (full segment), binary powers
+      for (int bit = 0; bit < 8; ++bit) {
+        if ((p.R >> bit) & 1) lamR = cmulf(lamR, sq);
+        if ((sr >> bit) & 1) lamS = cmulf(lamS, sq);
+        sq = cmulf(sq, sq);
+      }
+    }
+  };
+  // the int8 planes carry a zero pad byte per lane (column 4 lane + 3 when HJ < 4): clear them once
+  for (size_t i = (size_t)htid * 16; i < 2 * a2_bytes; i += kGluHalf * 16) *reinterpret_cast<int4*>(A2h + i) = make_int4(0, 0, 0, 0);
+  load_layer(0);
+  int cur_layer = 0;
   uint32_t phase = 0;
   TC_TRACE_DECL
   __syncthreads();
   const uint32_t tcol = tmem_slot + 256u * half;
   // Without SCAN: balanced partition, every pipeline owns one contiguous row range (full tiles plus one short tile whose
-  // row loops and TMEM passes stop at its last row).  With SCAN: tile t = chunk * B + clip, pipeline g takes t = g, g + G, ...
+  // row loops and TMEM passes stop at its last row).  With SCAN: tile t = chunk * B + clip, handed out round-robin.
   const long long npipe = 2LL * gridDim.x, pipe = 2LL * blockIdx.x + half;
-  const long long row_begin = SCAN ? 0 : p.rows * pipe / npipe, row_end = SCAN ? 0 : p.rows * (pipe + 1) / npipe;
-  const long long ntiles = SCAN ? (long long)p.B * p.tiles_per_clip : 0;
-  // SCAN per-thread constants: state, segment, lam and lam^R (full tiles) for the look-back
-  const int P = K1 >> 1;
-  const int sp = SCAN ? htid % P : 0, sseg = SCAN ? htid / P : 0, nseg = SCAN ? kGluHalf / P : 1;
-  const int sr = SCAN ? (p.R + nseg - 1) / nseg : 0;          // rows per segment (<= 32)
-  float2 lam = make_float2(0.f, 0.f), lamR = make_float2(1.f, 0.f), lamS = make_float2(1.f, 0.f);
-  if constexpr (SCAN) {
-    lam = p.lam[sp];
-    float2 sq = lam;                                          // lam^R (full tile) and lam^sr (full segment), binary powers
-    for (int bit = 0; bit < 8; ++bit) {
-      if ((p.R >> bit) & 1) lamR = cmulf(lamR, sq);
-      if ((sr >> bit) & 1) lamS = cmulf(lamS, sq);
-      sq = cmulf(sq, sq);
-    }
-  }
-  const float xs_odd_mul = p.xs_odd_mul;
-  const bool relu_scan = p.relu_scan != 0;
-  const float gl_s = p.gl_s, gr_s = p.gr_s, out_floor = p.relu_out ? 0.f : -INFINITY;
-  const uint32_t poff = (uint32_t)(sp >> 2) * lbo + 4u * (sp & 3);   // plane offset of column k = 2 sp
-  // SCAN tile schedule: whole rounds go round-robin over the pipelines (t = round * G + pipe); the tiles of the last,
-  // partial round go to ONE pipeline per SM first (t = full * G + half * grid + blockIdx), so that an SM gets at most one
-  // tile more than any other.  Every pipeline still walks its tiles in increasing order, and a tile's predecessor
-  // (t - B) always belongs to an earlier round or to another, co-resident pipeline: the look-back cannot deadlock.
-  const long long full_rounds = SCAN ? ntiles / npipe : 0;
+  const long long row_begin = SCAN ? 0 : p0.rows * pipe / npipe, row_end = SCAN ? 0 : p0.rows * (pipe + 1) / npipe;
+  const long long ntiles = SCAN ? (long long)p0.B * p0.tiles_per_clip : 0;    // per layer
+  const long long ntp = (ntiles + 1) & ~1LL;                  // padded to even: the two pipelines of a CTA share a layer
+  const long long total = ntp * mp.nlayers;
+  // SCAN tile schedule.  Global tile index g = layer * ntp + t, t = chunk * B + clip; round r hands g = r * G + pipe to
+  // pipeline `pipe`.  When the last, partial round lies inside the last layer its tiles go to ONE pipeline per SM first
+  // (g = full * G + half * grid + blockIdx), so that an SM gets at most one tile more than any other.  Every pipeline
+  // walks its tiles in increasing order and a tile only ever waits for tiles with a smaller index that belong to
+  // another, co-resident pipeline (look-back: t - B of the same layer; layers: the same t one layer down), so the
+  // waits cannot deadlock.  The iteration count and the layer of an iteration are CTA-uniform: the weight tiles are
+  // shared by the two pipelines and are reloaded between two __syncthreads when the layer changes.
+  const long long rounds_all = SCAN ? (total + npipe - 1) / npipe : 0;
+  const long long full_rounds = SCAN ? total / npipe : 0;
+  const long long rem = SCAN ? total - full_rounds * npipe : 0;
+  const bool spread = rem > 0 && full_rounds * npipe >= ntp * (mp.nlayers - 1);
   const long long last_j = (long long)half * gridDim.x + blockIdx.x;
-  const long long my_tiles = SCAN ? full_rounds + (last_j < ntiles - full_rounds * npipe ? 1 : 0) : 0;
   long long iter = 0;
-  for (long long it0 = row_begin; SCAN ? iter < my_tiles : it0 < row_end; it0 += kTcRows, ++iter) {
-    const long long it = SCAN ? (iter < full_rounds ? iter * npipe + pipe : full_rounds * npipe + last_j) : it0;
+  for (long long it0 = row_begin; SCAN ? iter < rounds_all : it0 < row_end; it0 += kTcRows, ++iter) {
+    long long it = it0;
+    int layer = 0;
+    if constexpr (SCAN) {
+      const long long g0 = iter * npipe + 2LL * blockIdx.x;   // CTA-uniform
+      long long g = g0 + half;
+      bool active = g < total;
+      layer = (int)(min(g0, total - 1) / ntp);
+      if (iter == full_rounds && spread) {
+        g = full_rounds * npipe + last_j;
+        active = last_j < rem;
+        layer = mp.nlayers - 1;
+      }
+      if (layer != cur_layer) {                               // CTA-uniform
+        __syncthreads();
+        load_layer(layer);
+        cur_layer = layer;
+        __syncthreads();
+      }
+      it = g - (long long)layer * ntp;
+      if (!active || it >= ntiles) continue;
+    }
+    // scalars of the current layer, straight from the parameter bank (cheap to re-derive, no registers held)
+    const TcGluParams& p = mp.layer[layer];
+    const float k_c = p.c_scale * p.yt_inv;                   // conj Re(C x) / s_y = acc * k_c
+    const float a_o = p.o_col_scale * p.oo_inv;
+    const float k_e = -p.oo_s * 1.4426950408889634f;          // exp(-o) = 2^(code(o) * k_e)
+    const float y_to_gl = p.yt_s * p.gl_inv, y_to_oa = p.yt_s * p.oa_inv;   // powers of two
+    const float xs_odd_mul = p.xs_odd_mul;
+    const bool relu_scan = p.relu_scan != 0;
+    const float gl_s = p.gl_s, gr_s = p.gr_s, gr_inv = p.gr_inv, out_floor = p.relu_out ? 0.f : -INFINITY;
+    const float b_os0 = p.b_out_scale0, b_os1 = p.b_out_scale1;
+    const float* pXS = p.XS; const float* pX = p.X; float* pOUT = p.OUT;
+    uint32_t* pflags = p.flags; float2* precs = p.recs;
     long long row0;
     int rv;
     int clip = 0, chunk = 0;
     if constexpr (SCAN) {
-      chunk = (int)(it / p.B);
-      clip = (int)(it - (long long)chunk * p.B);
-      row0 = (long long)clip * p.L + (long long)chunk * p.R;
-      rv = min(p.R, p.L - chunk * p.R);
+      chunk = (int)(it / p0.B);
+      clip = (int)(it - (long long)chunk * p0.B);
+      row0 = (long long)clip * p0.L + (long long)chunk * p0.R;
+      rv = min(p0.R, p0.L - chunk * p0.R);
+      if (layer > 0) {
+        // The rows of this tile come from the same tile one layer down, possibly written by another SM.  Acquire load of
+        // its done flag by one thread (which also drops this SM's stale L1 lines), then a barrier: every later load of
+        // the pipeline is ordered after the producer's stores.
+        if (htid == 0)
+          while (ld_acquire_u32(mp.done + (size_t)(layer - 1) * ntiles + it) == 0u) {}
+        half_barrier(half);
+      }
     } else {
       row0 = it;
       rv = (int)min((long long)kTcRows, row_end - row0);
@@ -909,11 +965,16 @@ __global__ void __launch_bounds__(kGluThreads, 1) tc_glu_kernel(TcGluParams p) {
       float2 v[32];
       if constexpr (BPJ) {
         // ---- S0: block input -> u = FQ(BN(x)) codes -> int8 planes (lanes along columns, as in P1)
+        float bsub[HJ], bmulq[HJ], baddq[HJ];
+#pragma unroll
+        for (int j = 0; j < HJ; ++j) {
+          bsub[j] = lcst[lane + 32 * j]; bmulq[j] = lcst[H + lane + 32 * j]; baddq[j] = lcst[2 * H + lane + 32 * j];
+        }
         for (int rb = warp * 8; rb < rv; rb += NW * 8) {
           float xr8[8][HJ];
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
-            const float* xr = p.X + (size_t)min(row0 + rb + q, last_row) * H;
+            const float* xr = pX + (size_t)min(row0 + rb + q, last_row) * H;
 #pragma unroll
             for (int j = 0; j < HJ; ++j) xr8[q][j] = xr[lane + 32 * j];
           }
@@ -959,7 +1020,7 @@ __global__ void __launch_bounds__(kGluThreads, 1) tc_glu_kernel(TcGluParams p) {
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 const float f = __int2float_rn((int)vh[j + e] * 256 + (int)vl[j + e]);
-                o[j + e] = round_clip(f * cc[e], qs_min, qs_max) * ((e & 1) ? p.b_out_scale1 : p.b_out_scale0);
+                o[j + e] = round_clip(f * cc[e], qs_min, qs_max) * ((e & 1) ? b_os1 : b_os0);
               }
             }
             float* dst = BuT + (size_t)erow * ldB + c0;
@@ -975,7 +1036,7 @@ __global__ void __launch_bounds__(kGluThreads, 1) tc_glu_kernel(TcGluParams p) {
         for (int i = 0; i < 32; ++i)
           v[i] = *reinterpret_cast<const float2*>(BuT + (size_t)min(sseg * sr + i, kTcRows - 1) * ldB + 2 * sp);
       } else {
-        const float2* bu = reinterpret_cast<const float2*>(p.XS) + (size_t)row0 * P + sp;
+        const float2* bu = reinterpret_cast<const float2*>(pXS) + (size_t)row0 * P + sp;
         // 32 unpredicated, unclamped loads: rows past the segment are ignored, rows past the end of Bu fall into the
         // slack the workspace layout keeps behind it
         const float2* q = bu + (size_t)(sseg * sr) * P;
@@ -1001,8 +1062,8 @@ __global__ void __launch_bounds__(kGluThreads, 1) tc_glu_kernel(TcGluParams p) {
           e = cfmaf(seg_mul[q * P + sp], e, seg_agg[q * P + sp]);
           M = cmulf(M, seg_mul[q * P + sp]);
         }
-        uint32_t* flag_row = p.flags + (size_t)clip * p.tiles_per_clip;
-        float2* rec_row = p.recs + (size_t)clip * p.tiles_per_clip * 2 * P;
+        uint32_t* flag_row = pflags + (size_t)clip * p0.tiles_per_clip;
+        float2* rec_row = precs + (size_t)clip * p0.tiles_per_clip * 2 * P;
         // Fixed-stride look-back.  Every tile publishes its aggregate (flag 1); every kStride-th tile (an "anchor") also
         // publishes its inclusive prefix (flag 2).  The carry-in of tile k is ALWAYS
         //     incl[a], then Horner over agg[a+1 .. k-1],   a = the last anchor before k,
@@ -1010,7 +1071,7 @@ __global__ void __launch_bounds__(kGluThreads, 1) tc_glu_kernel(TcGluParams p) {
         // decoupled look-back takes whatever prefix happens to be published and is not bit-reproducible).  All flags
         // and records of the walk (<= kStride of each) are requested together: two round trips, not 2 per predecessor.
         constexpr int kStride = 4;
-        const bool last = chunk + 1 >= p.tiles_per_clip;      // nobody looks back at the last tile of a clip
+        const bool last = chunk + 1 >= p0.tiles_per_clip;      // nobody looks back at the last tile of a clip
         const bool anchor = (chunk % kStride) == 0;
         float2 carry = make_float2(0.f, 0.f);
         if (!last) {
@@ -1070,11 +1131,11 @@ __global__ void __launch_bounds__(kGluThreads, 1) tc_glu_kernel(TcGluParams p) {
       float4 raw[8];
 #pragma unroll
       for (int q = 0; q < 8; ++q)
-        raw[q] = *reinterpret_cast<const float4*>(p.XS + (size_t)min(row0 + rb + q, last_row) * K1 + xs_col);
+        raw[q] = *reinterpret_cast<const float4*>(pXS + (size_t)min(row0 + rb + q, last_row) * K1 + xs_col);
       if (kin) {
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-          const float v0 = raw[q].x, v1 = raw[q].y * p.xs_odd_mul, v2 = raw[q].z, v3 = raw[q].w * p.xs_odd_mul;
+          const float v0 = raw[q].x, v1 = raw[q].y * xs_odd_mul, v2 = raw[q].z, v3 = raw[q].w * xs_odd_mul;
           const uint32_t h01 = pack_bf2(v0, v1), h23 = pack_bf2(v2, v3);
           const uint32_t l01 = pack_bf2(v0 - __uint_as_float(h01 << 16), v1 - __uint_as_float(h01 & 0xFFFF0000u));
           const uint32_t l23 = pack_bf2(v2 - __uint_as_float(h23 << 16), v3 - __uint_as_float(h23 & 0xFFFF0000u));
@@ -1100,7 +1161,7 @@ __global__ void __launch_bounds__(kGluThreads, 1) tc_glu_kernel(TcGluParams p) {
     float xin[PB][HJ];
 #pragma unroll
     for (int q = 0; q < PB; ++q) {
-      const float* xr = p.X + (size_t)min(row0 + warp * PB + q, last_row) * H;
+      const float* xr = pX + (size_t)min(row0 + warp * PB + q, last_row) * H;
 #pragma unroll
       for (int j = 0; j < HJ; ++j) xin[q][j] = xr[lane + 32 * j];
     }
@@ -1123,12 +1184,18 @@ __global__ void __launch_bounds__(kGluThreads, 1) tc_glu_kernel(TcGluParams p) {
     half_barrier(half);
     TC_TRACE_MARK(tid == 0);
     // ---- P1: one warp per row, PB rows in flight
+    float bsub[HJ], bmulq[HJ], baddq[HJ], ddq[HJ];
+#pragma unroll
+    for (int j = 0; j < HJ; ++j) {
+      bsub[j] = lcst[lane + 32 * j]; bmulq[j] = lcst[H + lane + 32 * j]; baddq[j] = lcst[2 * H + lane + 32 * j];
+      ddq[j] = lcst[3 * H + lane + 32 * j];
+    }
     for (int rb = warp * PB; rb < rv; rb += NW * PB) {
       float tin[PB][HJ];
       if (rb != warp * PB) {
 #pragma unroll
         for (int q = 0; q < PB; ++q) {
-          const float* xr = p.X + (size_t)min(row0 + rb + q, last_row) * H;
+          const float* xr = pX + (size_t)min(row0 + rb + q, last_row) * H;
 #pragma unroll
           for (int j = 0; j < HJ; ++j) xin[q][j] = xr[lane + 32 * j];
         }
@@ -1169,7 +1236,7 @@ __global__ void __launch_bounds__(kGluThreads, 1) tc_glu_kernel(TcGluParams p) {
     // skip-connection rows of the first P2 batch (L2 hits) travel during the second product and E2
 #pragma unroll
     for (int q = 0; q < PB; ++q) {
-      const float* xr = p.X + (size_t)min(row0 + warp * PB + q, last_row) * H;
+      const float* xr = pX + (size_t)min(row0 + warp * PB + q, last_row) * H;
 #pragma unroll
       for (int j = 0; j < HJ; ++j) xin[q][j] = xr[lane + 32 * j];
     }
@@ -1197,7 +1264,7 @@ __global__ void __launch_bounds__(kGluThreads, 1) tc_glu_kernel(TcGluParams p) {
             float ex, sg;
             asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(oc * k_e));
             asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(sg) : "f"(1.0f + ex));
-            sb[j + e] = __float_as_uint(fminf(sg * p.gr_inv, qn_max) + kRoundMagic);           // right gate (> 0)
+            sb[j + e] = __float_as_uint(fminf(sg * gr_inv, qn_max) + kRoundMagic);           // right gate (> 0)
           }
         }
         uint4 pk;
@@ -1214,13 +1281,13 @@ __global__ void __launch_bounds__(kGluThreads, 1) tc_glu_kernel(TcGluParams p) {
       if (rb != warp * PB) {
 #pragma unroll
         for (int q = 0; q < PB; ++q) {
-          const float* xr = p.X + (size_t)min(row0 + rb + q, last_row) * H;
+          const float* xr = pX + (size_t)min(row0 + rb + q, last_row) * H;
 #pragma unroll
           for (int j = 0; j < HJ; ++j) xin[q][j] = xr[lane + 32 * j];
         }
       }
       const unsigned short* trow = reinterpret_cast<const unsigned short*>(T + (size_t)rb * ldT) + lane;
-      float* yr = p.OUT + (size_t)(row0 + rb) * H + lane;
+      float* yr = pOUT + (size_t)(row0 + rb) * H + lane;
 #pragma unroll
       for (int q = 0; q < PB; ++q) {
         if (rb + q >= rv) break;                              // warp-uniform
@@ -1234,7 +1301,11 @@ __global__ void __launch_bounds__(kGluThreads, 1) tc_glu_kernel(TcGluParams p) {
         }
       }
     }
-    half_barrier(half);   // T is free: the next tile's planes may overwrite it
+    half_barrier(half);   // T is free: the next tile's planes may overwrite it; every row of the tile has been stored
+    if constexpr (SCAN) {
+      // release (cumulative over the stores the barrier ordered before it): the same tile one layer up may start
+      if (layer + 1 < mp.nlayers && htid == 0) st_release_u32(mp.done + (size_t)layer * ntiles + it, 1u);
+    }
     TC_TRACE_MARK(tid == 0);
     TC_TRACE_NEXT();
   }
@@ -1434,7 +1505,7 @@ static size_t tc_glu_smem(int H, int K1, bool scan, bool bpj) {
   const size_t r_bytes = std::max(std::max(2 * tc_tile_bytes(kTcRows, K1), bu_bytes) + seg_bytes,
                                   (size_t)kTcRows * (H + 4) * 4 + 2 * tc_tile_bytes8(kTcRows, kGluK2));
   return tc_tile_bytes(H, K1) + tc_tile_bytes8(H, kGluK2) + (bpj ? tc_tile_bytes8(K1, kGluK2) : 0) +
-         (((size_t)(H + K1) * 4 + 127) & ~(size_t)127) + 2 * r_bytes;
+         (((size_t)(5 * H + K1) * 4 + 127) & ~(size_t)127) + 2 * r_bytes;
 }
 
 int tc_glu_build(const float* C_tilde /*[H][P][2] quantised*/, const float* out2_kernel /*[H][H] quantised*/, int H, int P,
@@ -1507,13 +1578,19 @@ void tc_glu_free(TcGluDev* d) {
 }
 
 template <int HJ, bool SCAN, bool BPJ>
-static int tc_glu_go(const TcGluParams& p, size_t smem, int grid, cudaStream_t st) {
+static int tc_glu_go_multi(const TcGluMulti& mp, size_t smem, int grid, cudaStream_t st) {
   auto kernel = tc_glu_kernel<HJ, SCAN, BPJ>;
   S5_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   ProfScope prof(BPJ ? S5_K_BLOCK : SCAN ? S5_K_GLU_SCAN : S5_K_GLU, st);
-  kernel<<<grid, kGluThreads, smem, st>>>(p);
+  kernel<<<grid, kGluThreads, smem, st>>>(mp);
   S5_LAUNCH_CHECK();
   return S5_OK;
+}
+template <int HJ, bool SCAN, bool BPJ>
+static int tc_glu_go(const TcGluParams& p, size_t smem, int grid, cudaStream_t st) {
+  TcGluMulti mp{};
+  mp.nlayers = 1; mp.done = nullptr; mp.layer[0] = p;
+  return tc_glu_go_multi<HJ, SCAN, BPJ>(mp, smem, grid, st);
 }
 
 size_t tc_glu_scan_workspace_bytes(int B, int L, int P) {
@@ -1521,7 +1598,8 @@ size_t tc_glu_scan_workspace_bytes(int B, int L, int P) {
   return round_up((size_t)B * cmax * sizeof(uint32_t), 256) + (size_t)B * cmax * 2 * P * sizeof(float2);
 }
 
-int tc_glu_launch(const TcGluDev& d, const TcGluArgs& a, cudaStream_t st) {
+// fills the kernel parameters of one layer; *grid_out = grid size this layer alone would use
+static int tc_glu_fill(const TcGluDev& d, const TcGluArgs& a, TcGluParams* out, int* grid_out, cudaStream_t st) {
   const float sc[] = {a.s_ut, a.s_yt, a.s_o_act, a.s_o_out, a.s_gl, a.s_gr};
   for (float s : sc)
     if (!is_pow2(s)) S5_FAIL(S5_E_BADARG, "dense-tile glu: scales must be powers of two");
@@ -1535,19 +1613,13 @@ int tc_glu_launch(const TcGluDev& d, const TcGluArgs& a, cudaStream_t st) {
   p.ut_s = a.s_ut; p.ut_inv = 1.f / a.s_ut; p.yt_s = a.s_yt; p.yt_inv = 1.f / a.s_yt; p.oa_inv = 1.f / a.s_o_act;
   p.oo_s = a.s_o_out; p.oo_inv = 1.f / a.s_o_out; p.gl_s = a.s_gl; p.gl_inv = 1.f / a.s_gl; p.gr_s = a.s_gr; p.gr_inv = 1.f / a.s_gr;
   p.qs_min = a.qs_min; p.qs_max = a.qs_max; p.qn_min = a.qn_min; p.qn_max = a.qn_max; p.relu_out = a.relu_out;
-  const int HJ = d.H >> 5;
   if (!a.lam) {
     // rows are split evenly over 2 x grid pipelines (balanced partition); at least 32 rows per pipeline
-    const int grid = (int)std::max<long long>(1, std::min<long long>((p.rows + 63) / 64, (long long)sm_count()));
-    switch (HJ) {
-      case 1: return tc_glu_go<1, false, false>(p, d.smem, grid, st);
-      case 2: return tc_glu_go<2, false, false>(p, d.smem, grid, st);
-      case 3: return tc_glu_go<3, false, false>(p, d.smem, grid, st);
-      default: return tc_glu_go<4, false, false>(p, d.smem, grid, st);
-    }
+    *grid_out = (int)std::max<long long>(1, std::min<long long>((p.rows + 63) / 64, (long long)sm_count()));
+    *out = p;
+    return S5_OK;
   }
-  // ---- fused recurrence: XS is Bu.  Tiles are R consecutive frames of one clip; pick the number of tiles per clip
-  // that minimises (rounds over the pipelines) x (rows per tile), i.e. the time of the slowest pipeline.
+  // ---- fused recurrence: XS is Bu (unused with the fused B projection).  Tiles are R consecutive frames of one clip.
   const int P = d.K1 >> 1;
   if (!tc_glu_scan_ok(d) || a.B <= 0 || a.L <= 0 || (long long)a.B * a.L != a.rows) S5_FAIL(S5_E_BADARG, "dense-tile glu: fused recurrence not eligible");
   // Rows per tile depend on L only (never on B): the grouping of the floating-point recurrence, and with it every
@@ -1560,7 +1632,7 @@ int tc_glu_launch(const TcGluDev& d, const TcGluArgs& a, cudaStream_t st) {
   p.R = (a.L + c - 1) / c;
   p.tiles_per_clip = (a.L + p.R - 1) / p.R;
   const long long tiles = (long long)a.B * p.tiles_per_clip;
-  const int grid = (int)std::max<long long>(1, std::min<long long>((tiles + 1) / 2, (long long)sm_count()));
+  *grid_out = (int)std::max<long long>(1, std::min<long long>((tiles + 1) / 2, (long long)sm_count()));
   p.lam = reinterpret_cast<const float2*>(a.lam); p.B = a.B; p.L = a.L;
   p.relu_scan = a.relu_scan;
   const size_t flags_bytes = round_up((size_t)a.B * p.tiles_per_clip * sizeof(uint32_t), 256);
@@ -1573,6 +1645,25 @@ int tc_glu_launch(const TcGluDev& d, const TcGluArgs& a, cudaStream_t st) {
     if (!d.bpj_ok || !is_pow2(a.s_bu_re) || !is_pow2(a.s_bu_im)) S5_FAIL(S5_E_BADARG, "dense-tile glu: fused B projection not eligible");
     p.WB = reinterpret_cast<const signed char*>(d.WB); p.b_col_scale = d.b_col_scale;
     p.b_out_scale0 = a.s_bu_re; p.b_out_scale1 = a.s_bu_im; p.b_out_inv0 = 1.f / a.s_bu_re; p.b_out_inv1 = 1.f / a.s_bu_im;
+  }
+  *out = p;
+  return S5_OK;
+}
+
+int tc_glu_launch(const TcGluDev& d, const TcGluArgs& a, cudaStream_t st) {
+  TcGluParams p{};
+  int grid = 1, rc;
+  if ((rc = tc_glu_fill(d, a, &p, &grid, st))) return rc;
+  const int HJ = d.H >> 5;
+  if (!a.lam) {
+    switch (HJ) {
+      case 1: return tc_glu_go<1, false, false>(p, d.smem, grid, st);
+      case 2: return tc_glu_go<2, false, false>(p, d.smem, grid, st);
+      case 3: return tc_glu_go<3, false, false>(p, d.smem, grid, st);
+      default: return tc_glu_go<4, false, false>(p, d.smem, grid, st);
+    }
+  }
+  if (a.fuse_bproj) {
     switch (HJ) {
       case 1: return tc_glu_go<1, true, true>(p, d.smem_bpj, grid, st);
       case 2: return tc_glu_go<2, true, true>(p, d.smem_bpj, grid, st);
@@ -1585,6 +1676,34 @@ int tc_glu_launch(const TcGluDev& d, const TcGluArgs& a, cudaStream_t st) {
     case 2: return tc_glu_go<2, true, false>(p, d.smem_scan, grid, st);
     case 3: return tc_glu_go<3, true, false>(p, d.smem_scan, grid, st);
     default: return tc_glu_go<4, true, false>(p, d.smem_scan, grid, st);
+  }
+}
+
+// All blocks in one launch (every layer: block kernel with the same H, P, B, L).  `done` holds (n - 1) * tiles flags.
+int tc_glu_launch_multi(const TcGluDev* const* devs, const TcGluArgs* args, int n, uint32_t* done, size_t done_bytes, cudaStream_t st) {
+  if (n < 1 || n > kMaxFusedLayers) S5_FAIL(S5_E_BADARG, "dense-tile block kernel: %d layers in one launch not supported", n);
+  TcGluMulti mp{};
+  mp.nlayers = n;
+  int grid = 1, rc;
+  for (int l = 0; l < n; ++l) {
+    if (!args[l].lam || !args[l].fuse_bproj || devs[l]->H != devs[0]->H || devs[l]->K1 != devs[0]->K1)
+      S5_FAIL(S5_E_BADARG, "dense-tile block kernel: layer %d cannot join the single launch", l);
+    if ((rc = tc_glu_fill(*devs[l], args[l], &mp.layer[l], &grid, st))) return rc;
+  }
+  const size_t tiles = (size_t)mp.layer[0].B * mp.layer[0].tiles_per_clip;
+  if (n > 1) {
+    if (!done || done_bytes < (size_t)(n - 1) * tiles * sizeof(uint32_t)) S5_FAIL(S5_E_BADARG, "dense-tile block kernel: done-flag workspace too small");
+    S5_CUDA(cudaMemsetAsync(done, 0, (size_t)(n - 1) * tiles * sizeof(uint32_t), st));
+    mp.done = done;
+    // all layers' tiles share the pipelines
+    grid = (int)std::max<long long>(1, std::min<long long>(((long long)tiles * n + 1) / 2, (long long)sm_count()));
+  }
+  const size_t smem = devs[0]->smem_bpj;
+  switch (devs[0]->H >> 5) {
+    case 1: return tc_glu_go_multi<1, true, true>(mp, smem, grid, st);
+    case 2: return tc_glu_go_multi<2, true, true>(mp, smem, grid, st);
+    case 3: return tc_glu_go_multi<3, true, true>(mp, smem, grid, st);
+    default: return tc_glu_go_multi<4, true, true>(mp, smem, grid, st);
   }
 }
 

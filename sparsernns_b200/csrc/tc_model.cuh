@@ -39,6 +39,7 @@ int tc_glu_build(const float* C_tilde, const float* out2_kernel, int H, int P, f
 void tc_glu_free(TcGluDev* d);
 int tc_glu_launch(const TcGluDev& d, const TcGluArgs& a, cudaStream_t st);
 bool tc_glu_scan_ok(const TcGluDev& d);
+int tc_glu_launch_multi(const TcGluDev* const* devs, const TcGluArgs* args, int n, uint32_t* done, size_t done_bytes, cudaStream_t st);
 size_t tc_glu_scan_workspace_bytes(int B, int L, int P);
 int tc_linear_build(const float* W, int Kfull, int Nfull, float s_in, TcLinearDev* out);
 void tc_linear_free(TcLinearDev* d);

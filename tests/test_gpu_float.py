@@ -71,15 +71,17 @@ def test_float_layer_and_ssm_match_oracle(cuda_device, zoo):
         assert relerr(xs2.cpu().numpy(), xs_ref) <= TOL_F32
 
 
-@pytest.mark.parametrize("tc_min_rows,fuse_scan,fuse_bproj", [("1", "1", "1"), ("1", "1", "0"), ("1", "0", "0"), ("1000000000", "0", "0")],
-                         ids=["dense_tile_tcgen05_one_kernel_per_block", "dense_tile_tcgen05_fused_recurrence", "dense_tile_tcgen05",
-                              "compressed_cuda_cores"])
-def test_static_model_matches_oracle(cuda_device, zoo, tc_min_rows, fuse_scan, fuse_bproj, monkeypatch):
+@pytest.mark.parametrize("tc_min_rows,fuse_scan,fuse_bproj,fuse_layers",
+                         [("1", "1", "1", "1"), ("1", "1", "1", "0"), ("1", "1", "0", "0"), ("1", "0", "0", "0"), ("1000000000", "0", "0", "0")],
+                         ids=["dense_tile_tcgen05_all_blocks_one_launch", "dense_tile_tcgen05_one_kernel_per_block",
+                              "dense_tile_tcgen05_fused_recurrence", "dense_tile_tcgen05", "compressed_cuda_cores"])
+def test_static_model_matches_oracle(cuda_device, zoo, tc_min_rows, fuse_scan, fuse_bproj, fuse_layers, monkeypatch):
     import torch
 
     monkeypatch.setenv("S5B200_TC_MIN_ROWS", tc_min_rows)
     monkeypatch.setenv("S5B200_FUSE_SCAN", fuse_scan)
     monkeypatch.setenv("S5B200_FUSE_BPROJ", fuse_bproj)
+    monkeypatch.setenv("S5B200_FUSE_LAYERS", fuse_layers)
     m, var = _bound(zoo, static=True, relufication=True)
     x = torch.from_numpy(zoo["x"]).to(cuda_device)
     got = m(x).cpu().numpy()
@@ -180,4 +182,8 @@ def test_block_kernel_is_bit_reproducible_and_batch_invariant(cuda_device, zoo, 
     assert torch.equal(m(x[1:4]), y[1:4])
     perm = torch.randperm(x.shape[0], generator=torch.Generator().manual_seed(0)).to(cuda_device)
     assert torch.equal(m(x[perm]), y[perm])
+    # all blocks in one launch vs one launch per block: the same arithmetic, the same bits
+    monkeypatch.setenv("S5B200_FUSE_LAYERS", "0")
+    m2, _ = _bound(zoo, static=True, relufication=True)
+    assert torch.equal(m2(x), y)
 
