@@ -948,10 +948,12 @@ __global__ void __launch_bounds__(kGluThreads, 1) tc_glu_kernel(const __grid_con
       rv = min(p0.R, p0.L - chunk * p0.R);
       if (layer > 0) {
         // The rows of this tile come from the same tile one layer down, possibly written by another SM.  Acquire load of
-        // its done flag by one thread (which also drops this SM's stale L1 lines), then a barrier: every later load of
+        // its done flag by one thread (relaxed polling + one acquire fence, which also drops this SM's stale L1 lines), then a barrier: every later load of
         // the pipeline is ordered after the producer's stores.
-        if (htid == 0)
-          while (ld_acquire_u32(mp.done + (size_t)(layer - 1) * ntiles + it) == 0u) {}
+        if (htid == 0) {
+          while (ld_relaxed_u32(mp.done + (size_t)(layer - 1) * ntiles + it) == 0u) {}
+          fence_acquire_gpu();
+        }
         half_barrier(half);
       }
     } else {
@@ -1086,11 +1088,12 @@ __global__ void __launch_bounds__(kGluThreads, 1) tc_glu_kernel(const __grid_con
           const int n = chunk - a0;                           // records to read: incl[a0], agg[a0 + 1 .. chunk - 1]
           uint32_t f[kStride];
 #pragma unroll
-          for (int w = 0; w < kStride; ++w) f[w] = w < n ? ld_acquire_u32(flag_row + a0 + w) : 2u;
-          while (f[0] != 2u) f[0] = ld_acquire_u32(flag_row + a0);
+          for (int w = 0; w < kStride; ++w) f[w] = w < n ? ld_relaxed_u32(flag_row + a0 + w) : 2u;
+          while (f[0] != 2u) f[0] = ld_relaxed_u32(flag_row + a0);
 #pragma unroll
           for (int w = 1; w < kStride; ++w)
-            while (f[w] == 0u) f[w] = ld_acquire_u32(flag_row + a0 + w);
+            while (f[w] == 0u) f[w] = ld_relaxed_u32(flag_row + a0 + w);
+          fence_acquire_gpu();                                // one acquire for the whole walk
           float2 rec[kStride];
 #pragma unroll
           for (int w = 0; w < kStride; ++w)
@@ -1582,7 +1585,17 @@ static int tc_glu_go_multi(const TcGluMulti& mp, size_t smem, int grid, cudaStre
   auto kernel = tc_glu_kernel<HJ, SCAN, BPJ>;
   S5_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   ProfScope prof(BPJ ? S5_K_BLOCK : SCAN ? S5_K_GLU_SCAN : S5_K_GLU, st);
-  kernel<<<grid, kGluThreads, smem, st>>>(mp);
+  if constexpr (SCAN) {
+    // The fused recurrence spins on tiles owned by other CTAs (look-back, done flags) and its persistent round-robin
+    // schedule lets a CTA wait for a HIGHER-numbered one (previous round), so every CTA of the grid must be resident.
+    // A cooperative launch guarantees exactly that (grid <= SM count, 1 CTA per SM); with a plain launch two such
+    // kernels on different streams (the host pipeline runs two forward streams) could each become partially resident
+    // and wait for their own unscheduled CTAs forever.
+    void* args[] = {const_cast<TcGluMulti*>(&mp)};
+    S5_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(kernel), dim3(grid), dim3(kGluThreads), args, smem, st));
+  } else {
+    kernel<<<grid, kGluThreads, smem, st>>>(mp);
+  }
   S5_LAUNCH_CHECK();
   return S5_OK;
 }
