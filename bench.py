@@ -333,9 +333,13 @@ def main():
     for i, name in enumerate(_abi.KERNEL_CLASSES):
         if n_cls[i]:
             per = ms_cls[i] / n_cls[i]
-            gbs = alg.get(name, 0) / (per * 1e-3) / 1e9 if name in alg else None
+            ab = alg.get(name)
+            if name == "block" and ab:
+                # all blocks may share one launch: algorithmic bytes of a launch = blocks per launch x (input + output)
+                ab = ab * dims.n_layers / max(1.0, n_cls[i] / K)
+            gbs = ab / (per * 1e-3) / 1e9 if ab else None
             kernels[name] = {"launches_per_step": n_cls[i] / K, "ms_per_launch": per, "ms_per_step": ms_cls[i] / K,
-                             "alg_bytes_per_launch": alg.get(name), "achieved_gbs": gbs, "frac": gbs / peak if gbs else None}
+                             "alg_bytes_per_launch": ab, "achieved_gbs": gbs, "frac": gbs / peak if gbs else None}
     dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"])
     traffic = None
     try:
@@ -347,9 +351,9 @@ def main():
                 "frac": kernels[dom]["frac"], "traffic": traffic, "peak_source": peak_src,
                 "share_of_step": kernels[dom]["ms_per_step"] / sum(k["ms_per_step"] for k in kernels.values())}
     if dom in ("block", "glu_scan"):
-        roofline["note"] = ("fused kernel: Bu and the recurrence states never leave the SM, so its algorithmic bytes are only the "
-                            "block input and output; it is bound by issue slots (CUDA-core fake-quant arithmetic around the "
-                            "tcgen05 MMAs, profiles/), not by HBM")
+        roofline["note"] = ("fused kernel (all S5 blocks in one launch): Bu and the recurrence states never leave the SM, so its "
+                            "algorithmic bytes are only each block's input and output; it is bound by issue slots (CUDA-core "
+                            "fake-quant arithmetic around the tcgen05 MMAs, profiles/), not by HBM")
     step_bytes = sum(k["alg_bytes_per_launch"] * k["launches_per_step"] for k in kernels.values() if k["alg_bytes_per_launch"])
     roofline["step_alg_bytes"] = step_bytes
     roofline["step_achieved_gbs"] = step_bytes / (ms_total / K * 1e-3) / 1e9
