@@ -417,7 +417,7 @@ struct BlockPlan {
 static BlockPlan block_plan(const s5_model* m, const LayerDev& ld, long long rows, bool ssm_only, bool want_xs) {
   const bool sq = m->desc.flavour == S5_STATIC;
   BlockPlan bp;
-  bp.glu_tc = sq && ld.tg.ok && !ssm_only && rows >= m->tc_min_rows && is_pow2(ld.sc.s_ut) && is_pow2(ld.sc.s_yt) &&
+  bp.glu_tc = sq && (ld.tg.ok || ld.tg.wide_ok) && !ssm_only && rows >= m->tc_min_rows && is_pow2(ld.sc.s_ut) && is_pow2(ld.sc.s_yt) &&
               is_pow2(ld.sc.s_out2_act) && is_pow2(ld.sc.s_out2_out) && is_pow2(ld.sc.s_gate_left) && is_pow2(ld.sc.s_gate_right);
   // the recurrence runs inside the GLU kernel (states never leave the SM) unless the caller wants to see them,
   // and so does the B projection: the whole block is then one kernel

@@ -1318,6 +1318,290 @@ __global__ void __launch_bounds__(kGluThreads, 1) tc_glu_kernel(const __grid_con
   if (tid < 32) tc_dealloc(tmem_slot, 512);
 }
 
+// ------------------------------------------------------------------------------------------- wide C projection + GLU
+// The same block tail for models whose weight tiles do not fit next to two tile pipelines (dim_scale 1.0: H = 192,
+// 2P = 256: C alone is 99 KB in bf16, one tile's state planes 132 KB).  One 512-thread pipeline per SM; the C
+// projection is K-CHUNKED: the scan output arrives in chunks of 64 real columns (32 states), each chunk's two bf16
+// planes and the matching [H][64] slice of C (streamed from L2 by ONE bulk copy, pre-arranged in the operand layout by
+// the host) sit in one of two buffers, and the tensor core accumulates chunk after chunk into the same TMEM columns
+// while the warps stage the next chunk.  Afterwards the buffers are dead and hold the fp32 tile T of the passes P1 / E2 /
+// P2, which are those of tc_glu_kernel.  out2's K order: column lane + 32 j sits at byte 4 lane + j of the first
+// 128-byte block (j < 4) and at byte 128 + w lane + (j - 4) of the second (w = 1, 2 or 4 bytes per lane).
+constexpr int kGluwThreads = 512;
+constexpr int kGluwKC = 64;        // real columns of the scan output per chunk
+
+__host__ __device__ constexpr int gluw_w1(int HJ) { return HJ <= 4 ? 0 : HJ == 5 ? 1 : HJ == 6 ? 2 : 4; }   // bytes per lane, second block
+__host__ __device__ constexpr int gluw_k2(int HJ) { return 128 + 32 * gluw_w1(HJ); }
+// physical byte of out2 input column k
+static inline int gluw_kpos(int k, int HJ) {
+  const int lane = k & 31, j = k >> 5;
+  return j < 4 ? 4 * lane + j : 128 + gluw_w1(HJ) * lane + (j - 4);
+}
+
+template <int HJ>
+__global__ void __launch_bounds__(kGluwThreads, 1) tc_gluw_kernel(const __grid_constant__ TcGluParams p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  constexpr int H = 32 * HJ, K2 = gluw_k2(HJ), W1 = gluw_w1(HJ);
+  constexpr int PB = HJ > 4 ? 4 : 8;                          // rows per warp batch in the lanes-along-columns passes
+  const int K1 = p.K1, NC = K1 / kGluwKC;
+  constexpr int ldT = H + 4;
+  const size_t wo_bytes = tc_tile_bytes8(H, K2);
+  const size_t pl_bytes = tc_tile_bytes(kTcRows, kGluwKC);    // one bf16 plane of one chunk
+  const size_t wck_bytes = tc_tile_bytes(H, kGluwKC);         // one chunk of C
+  const size_t buf_bytes = 2 * pl_bytes + wck_bytes;
+  const size_t t_bytes = (size_t)kTcRows * ldT * 4;
+  const size_t a2_bytes = tc_tile_bytes8(kTcRows, K2);
+  unsigned char* Wo = smem;
+  float* ob = reinterpret_cast<float*>(Wo + wo_bytes);        // [H] out2 bias / s_o_out
+  float* lcst = ob + H;                                       // [4][H]
+  unsigned char* R = reinterpret_cast<unsigned char*>(ob) + (((size_t)(5 * H) * 4 + 127) & ~(size_t)127);
+  float* T = reinterpret_cast<float*>(R);                     // aliases the two chunk buffers
+  unsigned char* A2h = R + max(t_bytes, 2 * buf_bytes);
+  unsigned char* A2l = A2h + a2_bytes;
+  __shared__ __align__(8) uint64_t full[2], mdone[2], bar;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr int NW = kGluwThreads / 32;
+  if (warp == 0) tc_alloc(&tmem_slot, 512);
+  if (tid == 0) {
+    mbar_init(&full[0], 1); mbar_init(&full[1], 1); mbar_init(&mdone[0], 1); mbar_init(&mdone[1], 1); mbar_init(&bar, 1);
+    fence_mbar_init();
+  }
+  tc_load_weights8(Wo, p.Wo, H, K2);
+  for (int n = tid; n < H; n += kGluwThreads) {
+    ob[n] = p.o_bias[n] * p.oo_inv;
+    lcst[n] = p.bn_sub ? p.bn_sub[n] : 0.f;
+    lcst[H + n] = (p.bn_sub ? p.bn_mul[n] : 1.f) * p.ut_inv;
+    lcst[2 * H + n] = (p.bn_sub ? p.bn_add[n] : 0.f) * p.ut_inv;
+    lcst[3 * H + n] = p.D[n] * p.ut_s * p.yt_inv;
+  }
+  for (size_t i = (size_t)tid * 16; i < 2 * a2_bytes; i += kGluwThreads * 16) *reinterpret_cast<int4*>(A2h + i) = make_int4(0, 0, 0, 0);
+  const long long last_row = p.rows - 1;
+  const uint32_t lbo = tc_lbo(kTcRows);
+  // chunk staging: 16 lanes per row (float4 = 4 real columns each), 32 rows per pass, 4 passes per tile
+  const int srow = tid >> 4, l16 = tid & 15;
+  const uint32_t soff = (uint32_t)(l16 >> 1) * lbo + (uint32_t)(l16 & 1) * 8u;
+  const uint32_t aoff0 = (uint32_t)(lane >> 2) * lbo + 4u * (lane & 3);
+  const uint32_t aoff1 = W1 == 4 ? (uint32_t)(8 + (lane >> 2)) * lbo + 4u * (lane & 3)
+                       : W1 == 2 ? (uint32_t)(8 + (lane >> 3)) * lbo + 2u * (lane & 7)
+                                 : (uint32_t)(8 + (lane >> 4)) * lbo + (uint32_t)(lane & 15);
+  const int erow0 = (warp & 3) * 32, erow = erow0 + lane;
+  const uint32_t lane_base = (uint32_t)erow0 << 16;
+  constexpr int cw = H >> 2;                                  // 4 column groups in the TMEM passes (multiple of 8)
+  const int cbeg = (warp >> 2) * cw;
+  const float qs_min = p.qs_min, qs_max = p.qs_max, qn_min = p.qn_min, qn_max = p.qn_max;
+  const float qrelu_min = fmaxf(qs_min, 0.f);
+  const float k_c = p.c_scale * p.yt_inv, a_o = p.o_col_scale * p.oo_inv, k_e = -p.oo_s * 1.4426950408889634f;
+  const float y_to_gl = p.yt_s * p.gl_inv, y_to_oa = p.yt_s * p.oa_inv, xs_odd_mul = p.xs_odd_mul;
+  const float gl_s = p.gl_s, gr_s = p.gr_s, gr_inv = p.gr_inv, out_floor = p.relu_out ? 0.f : -INFINITY;
+  const unsigned char* WcG = reinterpret_cast<const unsigned char*>(p.Wc);
+  uint32_t ph_full[2] = {0, 0}, ph_done[2] = {0, 0}, phase = 0;
+  __syncthreads();
+  const uint32_t tcol = tmem_slot;
+  const long long row_begin = p.rows * blockIdx.x / gridDim.x, row_end = p.rows * (blockIdx.x + 1) / gridDim.x;
+  float4 raw[4];
+  auto load_chunk = [&](long long row0, int c) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      raw[q] = *reinterpret_cast<const float4*>(p.XS + (size_t)min(row0 + 32 * q + srow, last_row) * K1 + c * kGluwKC + 4 * l16);
+  };
+  if (row_begin < row_end) load_chunk(row_begin, 0);
+  for (long long row0 = row_begin; row0 < row_end; row0 += kTcRows) {
+    const int rv = (int)min((long long)kTcRows, row_end - row0);
+    // ---- S + MMA 1, chunk by chunk
+    for (int c = 0; c < NC; ++c) {
+      const int b = c & 1;
+      unsigned char* buf = R + (size_t)b * buf_bytes;
+      if (c >= 2) {                                           // the MMAs of chunk c - 2 have read this buffer
+        mbar_wait(&mdone[b], ph_done[b]);
+        ph_done[b] ^= 1;
+      }
+      if (tid == 0) {
+        fence_proxy_async_smem();                             // earlier generic accesses (T of the previous tile) before the bulk write
+        mbar_expect_tx(&full[b], (uint32_t)wck_bytes);
+        bulk_g2s(buf + 2 * pl_bytes, WcG + (size_t)c * wck_bytes, (uint32_t)wck_bytes, &full[b]);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float v0 = raw[q].x, v1 = raw[q].y * xs_odd_mul, v2 = raw[q].z, v3 = raw[q].w * xs_odd_mul;
+        const uint32_t h01 = pack_bf2(v0, v1), h23 = pack_bf2(v2, v3);
+        const uint32_t l01 = pack_bf2(v0 - __uint_as_float(h01 << 16), v1 - __uint_as_float(h01 & 0xFFFF0000u));
+        const uint32_t l23 = pack_bf2(v2 - __uint_as_float(h23 << 16), v3 - __uint_as_float(h23 & 0xFFFF0000u));
+        const uint32_t o = soff + (uint32_t)(32 * q + srow) * 16u;
+        *reinterpret_cast<uint2*>(buf + o) = make_uint2(h01, h23);
+        *reinterpret_cast<uint2*>(buf + pl_bytes + o) = make_uint2(l01, l23);
+      }
+      // the next chunk (or the first chunk of the next tile) travels while this one is multiplied
+      if (c + 1 < NC) load_chunk(row0, c + 1);
+      else if (row0 + kTcRows < row_end) load_chunk(row0 + kTcRows, 0);
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncthreads();
+      tc_fence_after();
+      if (tid == 0) {
+        mbar_wait(&full[b], ph_full[b]);                      // this chunk of C has landed
+        tc_issue(tcol, buf, buf + 2 * pl_bytes, kGluwKC, H, c > 0, true);
+        tc_issue(tcol, buf + pl_bytes, buf + 2 * pl_bytes, kGluwKC, H, true, true);
+        tc_commit(&mdone[b]);
+      }
+      ph_full[b] ^= 1;
+    }
+    // the block-input rows of the first P1 batch travel while the tensor core finishes
+    float xin[PB][HJ];
+#pragma unroll
+    for (int q = 0; q < PB; ++q) {
+      const float* xr = p.X + (size_t)min(row0 + warp * PB + q, last_row) * H;
+#pragma unroll
+      for (int j = 0; j < HJ; ++j) xin[q][j] = xr[lane + 32 * j];
+    }
+    for (int c = max(0, NC - 2); c < NC; ++c) {               // the last commit on each buffer
+      mbar_wait(&mdone[c & 1], ph_done[c & 1]);
+      ph_done[c & 1] ^= 1;
+    }
+    tc_fence_after();
+    // ---- E1: raw accumulators -> T (the chunk buffers are dead)
+    if (erow0 < rv) {
+      for (int c0 = cbeg; c0 < cbeg + cw; c0 += 8) {
+        uint32_t v[8];
+        tc_ld8(tcol + lane_base + c0, v);
+        tc_wait_ld();
+        float* dst = T + (size_t)erow * ldT + c0;
+        *reinterpret_cast<uint4*>(dst) = make_uint4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<uint4*>(dst + 4) = make_uint4(v[4], v[5], v[6], v[7]);
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+    // ---- P1: one warp per row, PB rows in flight
+    float bsub[HJ], bmulq[HJ], baddq[HJ], ddq[HJ];
+#pragma unroll
+    for (int j = 0; j < HJ; ++j) {
+      bsub[j] = lcst[lane + 32 * j]; bmulq[j] = lcst[H + lane + 32 * j]; baddq[j] = lcst[2 * H + lane + 32 * j];
+      ddq[j] = lcst[3 * H + lane + 32 * j];
+    }
+    for (int rb = warp * PB; rb < rv; rb += NW * PB) {
+      float tin[PB][HJ];
+      if (rb != warp * PB) {
+#pragma unroll
+        for (int q = 0; q < PB; ++q) {
+          const float* xr = p.X + (size_t)min(row0 + rb + q, last_row) * H;
+#pragma unroll
+          for (int j = 0; j < HJ; ++j) xin[q][j] = xr[lane + 32 * j];
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < PB; ++q)
+#pragma unroll
+        for (int j = 0; j < HJ; ++j) tin[q][j] = T[(size_t)(rb + q) * ldT + lane + 32 * j];
+      __syncwarp();   // every lane holds its raw values of these rows before the rows are overwritten with codes
+#pragma unroll
+      for (int q = 0; q < PB; ++q) {
+        const int r = rb + q;
+        uint32_t ob8[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+        unsigned short* trow = reinterpret_cast<unsigned short*>(T + (size_t)r * ldT);
+#pragma unroll
+        for (int j = 0; j < HJ; ++j) {
+          const float uc = round_clip((xin[q][j] - bsub[j]) * bmulq[j] + baddq[j], qs_min, qs_max);   // code of u = FQ(BN(x))
+          const float cy = round_clip(fmaf(ddq[j], uc, tin[q][j] * k_c), qrelu_min, qs_max);          // code of x1 = ReLU(FQ(y))
+          trow[lane + 32 * j] = (unsigned short)__float_as_uint(fminf(cy * y_to_gl, qn_max) + kRoundMagic);   // left gate (>= 0)
+          ob8[j] = __float_as_uint(fminf(cy * y_to_oa, qn_max) + kRoundMagic);                        // out2 input code (>= 0)
+        }
+        uint32_t lo, hi;
+        split_planes(ob8[0], ob8[1], ob8[2], ob8[3], lo, hi);
+        *reinterpret_cast<uint32_t*>(A2h + aoff0 + (uint32_t)r * 16u) = hi;
+        *reinterpret_cast<uint32_t*>(A2l + aoff0 + (uint32_t)r * 16u) = lo;
+        if constexpr (W1 == 4) {
+          split_planes(ob8[4], ob8[5], ob8[6], ob8[7], lo, hi);
+          *reinterpret_cast<uint32_t*>(A2h + aoff1 + (uint32_t)r * 16u) = hi;
+          *reinterpret_cast<uint32_t*>(A2l + aoff1 + (uint32_t)r * 16u) = lo;
+        } else if constexpr (W1 == 2) {
+          *reinterpret_cast<unsigned short*>(A2h + aoff1 + (uint32_t)r * 16u) = (unsigned short)__byte_perm(ob8[4], ob8[5], 0x0051);
+          *reinterpret_cast<unsigned short*>(A2l + aoff1 + (uint32_t)r * 16u) = (unsigned short)__byte_perm(ob8[4], ob8[5], 0x0040);
+        } else if constexpr (W1 == 1) {
+          A2h[aoff1 + (uint32_t)r * 16u] = (unsigned char)(ob8[4] >> 8);
+          A2l[aoff1 + (uint32_t)r * 16u] = (unsigned char)ob8[4];
+        }
+      }
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (tid == 0) {
+      tc_issue8(tcol, A2h, Wo, K2, H, H, true);
+      tc_issue8(tcol + 256, A2l, Wo, K2, H, H, false);
+      tc_commit(&bar);
+    }
+    // skip-connection rows of the first P2 batch (L2 hits) travel during the second product and E2
+#pragma unroll
+    for (int q = 0; q < PB; ++q) {
+      const float* xr = p.X + (size_t)min(row0 + warp * PB + q, last_row) * H;
+#pragma unroll
+      for (int j = 0; j < HJ; ++j) xin[q][j] = xr[lane + 32 * j];
+    }
+    mbar_wait(&bar, phase);
+    phase ^= 1;
+    tc_fence_after();
+    // ---- E2: o = FQ(out2(x1)); right-gate code FQ(sigmoid(o)) -> second half of the T row
+    if (erow0 < rv) {
+      for (int c0 = cbeg; c0 < cbeg + cw; c0 += 8) {
+        uint32_t vh[8], vl[8];
+        tc_ld8(tcol + lane_base + c0, vh);
+        tc_ld8(tcol + lane_base + 256 + c0, vl);
+        tc_wait_ld();
+        uint32_t sb[8];
+#pragma unroll
+        for (int j = 0; j < 8; j += 4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(ob + c0 + j);
+          const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float f = __int2float_rn((int)vh[j + e] * 256 + (int)vl[j + e]);
+            const float oc = round_clip(fmaf(f, a_o, bb[e]), qn_min, qn_max);                 // code of o = FQ(out2(x1))
+            float ex, sg;
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(oc * k_e));
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(sg) : "f"(1.0f + ex));
+            sb[j + e] = __float_as_uint(fminf(sg * gr_inv, qn_max) + kRoundMagic);           // right gate (> 0)
+          }
+        }
+        uint4 pk;
+        pk.x = __byte_perm(sb[0], sb[1], 0x5410); pk.y = __byte_perm(sb[2], sb[3], 0x5410);
+        pk.z = __byte_perm(sb[4], sb[5], 0x5410); pk.w = __byte_perm(sb[6], sb[7], 0x5410);
+        *reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(T + (size_t)erow * ldT) + 2 * H + 2 * c0) = pk;
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+    // ---- P2: out = ReLU(FQ_gl(x1) * FQ(sigmoid) + x), coalesced
+    for (int rb = warp * PB; rb < rv; rb += NW * PB) {
+      if (rb != warp * PB) {
+#pragma unroll
+        for (int q = 0; q < PB; ++q) {
+          const float* xr = p.X + (size_t)min(row0 + rb + q, last_row) * H;
+#pragma unroll
+          for (int j = 0; j < HJ; ++j) xin[q][j] = xr[lane + 32 * j];
+        }
+      }
+      const unsigned short* trow = reinterpret_cast<const unsigned short*>(T + (size_t)rb * ldT) + lane;
+      float* yr = p.OUT + (size_t)(row0 + rb) * H + lane;
+#pragma unroll
+      for (int q = 0; q < PB; ++q) {
+        if (rb + q >= rv) break;                              // warp-uniform
+#pragma unroll
+        for (int j = 0; j < HJ; ++j) {
+          const float l = (__uint_as_float(0x4B400000u + trow[(size_t)q * 2 * ldT + 32 * j]) - kRoundMagic) * gl_s;
+          const float sg = (__uint_as_float(0x4B400000u + trow[(size_t)q * 2 * ldT + H + 32 * j]) - kRoundMagic) * gr_s;
+          yr[(size_t)q * H + 32 * j] = fmaxf(fmaf(l, sg, xin[q][j]), out_floor);
+        }
+      }
+    }
+    __syncthreads();                                          // T is free: the next tile's chunks may overwrite it
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc_dealloc(tmem_slot, 512);
+}
+
 // ------------------------------------------------------------------------------------------- host side
 
 static int upload_f(const std::vector<float>& h, float** d) {
@@ -1511,11 +1795,59 @@ static size_t tc_glu_smem(int H, int K1, bool scan, bool bpj) {
          (((size_t)(5 * H + K1) * 4 + 127) & ~(size_t)127) + 2 * r_bytes;
 }
 
+static size_t tc_gluw_smem(int H, int K1) {
+  const int HJ = H >> 5, K2 = gluw_k2(HJ);
+  const size_t buf = 2 * tc_tile_bytes(kTcRows, kGluwKC) + tc_tile_bytes(H, kGluwKC);
+  (void)K1;
+  return tc_tile_bytes8(H, K2) + (((size_t)(5 * H) * 4 + 127) & ~(size_t)127) + std::max((size_t)kTcRows * (H + 4) * 4, 2 * buf) +
+         2 * tc_tile_bytes8(kTcRows, K2);
+}
+
+// wide form: chunked C, wide out2 K order; GLU only (B projection and recurrence run as their own kernels)
+static int tc_gluw_build(const float* C_tilde, const float* out2_kernel, int H, int P, float conj_mul, float s_o_act, TcGluDev* out) {
+  const int K1 = 2 * P, HJ = H >> 5;
+  if ((H & 31) || H > 256 || (K1 % kGluwKC) || K1 > 512 || !is_pow2(s_o_act)) return S5_OK;
+  const size_t smem = tc_gluw_smem(H, K1);
+  if (smem + 2048 > 227 * 1024) return S5_OK;
+  const size_t nC = (size_t)H * P * 2;
+  const float s_re = pow2_grid(C_tilde, nC, 0, 2), s_im = pow2_grid(C_tilde, nC, 1, 2);
+  const float s_w = pow2_grid(out2_kernel, (size_t)H * H, 0, 1);
+  const int K2 = gluw_k2(HJ), NC = K1 / kGluwKC;
+  const size_t lboH = tc_lbo(H), wck = tc_tile_bytes(H, kGluwKC);
+  std::vector<__nv_bfloat16> wc(NC * wck / 2, __float2bfloat16_rn(0.f));
+  std::vector<signed char> wo((size_t)H * K2, 0);
+  for (int h = 0; h < H; ++h)
+    for (int k = 0; k < K1; ++k) {
+      const int p = k >> 1;
+      const float s = (k & 1) ? s_im : s_re;
+      const float c = std::nearbyint(C_tilde[((size_t)h * P + p) * 2 + (k & 1)] / s);
+      if (std::fabs(c) > 256.f) return S5_OK;                  // not exact in bf16
+      const int ch = k / kGluwKC, kk = k % kGluwKC;
+      const size_t byte = (size_t)ch * wck + (size_t)(kk >> 3) * lboH + (size_t)h * 16 + (size_t)(kk & 7) * 2;
+      wc[byte / 2] = __float2bfloat16_rn((k & 1) ? -c : c);    // Re(C x) = C_re x_re - C_im x_im
+    }
+  for (int n = 0; n < H; ++n)
+    for (int k = 0; k < H; ++k) {
+      const float c = std::nearbyint(out2_kernel[(size_t)k * H + n] / s_w);
+      if (c < -128.f || c > 127.f) return S5_OK;
+      wo[(size_t)n * K2 + gluw_kpos(k, HJ)] = (signed char)c;
+    }
+  out->H = H; out->K1 = K1; out->smem_wide = smem;
+  out->xs_odd_mul = s_im / s_re; out->c_scale = conj_mul * s_re; out->o_col_scale = s_o_act * s_w;
+  S5_CUDA(cudaMalloc(&out->Wc, wc.size() * sizeof(__nv_bfloat16)));
+  S5_CUDA(cudaMemcpy(out->Wc, wc.data(), wc.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
+  S5_CUDA(cudaMalloc(&out->Wo, wo.size()));
+  S5_CUDA(cudaMemcpy(out->Wo, wo.data(), wo.size(), cudaMemcpyHostToDevice));
+  out->wide_ok = true;
+  return S5_OK;
+}
+
 int tc_glu_build(const float* C_tilde /*[H][P][2] quantised*/, const float* out2_kernel /*[H][H] quantised*/, int H, int P,
                  float conj_mul, float s_o_act, const float* B_bar /*[H][2P] quantised, nullable*/, float s_ut, TcGluDev* out) {
   out->ok = false;
   const int K1 = 2 * P;
-  if ((H & 31) || H > 128 || (K1 & 15) || K1 > 128 || !is_pow2(s_o_act)) return S5_OK;
+  if ((H & 31) || (K1 & 15) || !is_pow2(s_o_act)) return S5_OK;
+  if (H > 128 || K1 > 128) return tc_gluw_build(C_tilde, out2_kernel, H, P, conj_mul, s_o_act, out);
   const size_t smem = tc_glu_smem(H, K1, false, false);
   if (smem > 226 * 1024) return S5_OK;
   const size_t nC = (size_t)H * P * 2;
@@ -1663,9 +1995,35 @@ static int tc_glu_fill(const TcGluDev& d, const TcGluArgs& a, TcGluParams* out, 
   return S5_OK;
 }
 
+template <int HJ>
+static int tc_gluw_go(const TcGluParams& p, size_t smem, int grid, cudaStream_t st) {
+  auto kernel = tc_gluw_kernel<HJ>;
+  S5_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ProfScope prof(S5_K_GLU, st);
+  kernel<<<grid, kGluwThreads, smem, st>>>(p);
+  S5_LAUNCH_CHECK();
+  return S5_OK;
+}
+
 int tc_glu_launch(const TcGluDev& d, const TcGluArgs& a, cudaStream_t st) {
   TcGluParams p{};
   int grid = 1, rc;
+  if (!d.ok && d.wide_ok) {
+    if (a.lam) S5_FAIL(S5_E_BADARG, "dense-tile glu (wide): the recurrence is not fused at this size");
+    TcGluDev d1 = d;
+    d1.ok = true;                                              // the parameter block is filled the same way
+    if ((rc = tc_glu_fill(d1, a, &p, &grid, st))) return rc;
+    grid = (int)std::max<long long>(1, std::min<long long>((p.rows + 63) / 64, (long long)sm_count()));
+    switch (d.H >> 5) {
+      case 1: return tc_gluw_go<1>(p, d.smem_wide, grid, st);
+      case 2: return tc_gluw_go<2>(p, d.smem_wide, grid, st);
+      case 3: return tc_gluw_go<3>(p, d.smem_wide, grid, st);
+      case 4: return tc_gluw_go<4>(p, d.smem_wide, grid, st);
+      case 5: return tc_gluw_go<5>(p, d.smem_wide, grid, st);
+      case 6: return tc_gluw_go<6>(p, d.smem_wide, grid, st);
+      default: S5_FAIL(S5_E_BADSHAPE, "dense-tile glu (wide): H = %d not covered", d.H);
+    }
+  }
   if ((rc = tc_glu_fill(d, a, &p, &grid, st))) return rc;
   const int HJ = d.H >> 5;
   if (!a.lam) {

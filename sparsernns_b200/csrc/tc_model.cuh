@@ -21,6 +21,8 @@ struct TcGluDev {
   void* Wc = nullptr; void* Wo = nullptr;   // bf16 [H][2P] and int8 [H][128] (lane-interleaved K) weight codes
   float xs_odd_mul = 1.f, c_scale = 1.f, o_col_scale = 1.f;
   bool ok = false;
+  // wide form (H > 128 or 2P > 128, e.g. dim_scale 1.0): C in 64-column chunks of the operand layout, out2 in the wide K order
+  bool wide_ok = false; size_t smem_wide = 0;
 };
 struct TcGluArgs {
   const float* XS; const float* X; float* OUT; long long rows;

@@ -101,6 +101,35 @@ def test_static_model_matches_oracle(cuda_device, zoo, tc_min_rows, fuse_scan, f
         h = ref_i
 
 
+@pytest.fixture(scope="module")
+def zoo_wide():
+    return Z.build_sparse_calibrated(1.0, n_clips=2, n_frames=331)
+
+
+@pytest.mark.parametrize("tc_min_rows", ["1", "1000000000"], ids=["dense_tile_tcgen05_wide", "compressed_cuda_cores"])
+def test_static_model_dim_scale_1_matches_oracle(cuda_device, zoo_wide, tc_min_rows, monkeypatch):
+    """BASELINE config 4 shapes (H 192, P 128): the K-chunked wide GLU kernel and the CUDA-core path vs the oracle."""
+    import torch
+
+    monkeypatch.setenv("S5B200_TC_MIN_ROWS", tc_min_rows)
+    zoo = zoo_wide
+    m, var = _bound(zoo, static=True, relufication=True)
+    x = torch.from_numpy(zoo["x"]).to(cuda_device)
+    got = m(x).cpu().numpy()
+    ocfg = Z.oracle_cfg(zoo["dims"], relufication=True, static_quant=True)
+    taps = {}
+    ref = OM.model_forward(zoo["x"], var, ocfg, dtype=np.float32, taps=taps)
+    e = relerr(got, ref)
+    print(f"static w8a16 model, dim_scale 1.0: rel err {e:.2e}, bit-identical outputs {float((got == ref).mean()):.4f}")
+    assert e <= TOL_W8A16
+    h = taps["encoder_output"]
+    for i in range(zoo["dims"].n_layers):
+        y = m.layer(i, torch.from_numpy(h).to(cuda_device)).cpu().numpy()
+        ref_i = taps[f"layers_{i}"]["output"]
+        assert relerr(y, ref_i) <= TOL_W8A16
+        h = ref_i
+
+
 def test_sparse_index_sets_bit_exact(cuda_device, zoo):
     """The compressed weights hold exactly the non-zeros of the QUANTISED matrices."""
     import ctypes as C
