@@ -278,6 +278,33 @@ int s5b200_fxp_relu(const int32_t* x, int32_t* y, long long n, void* stream);   
 int s5b200_fxp_sigmoid(const int32_t* x, int32_t* y, long long n, int bits, int exp, int x_exp, int y_exp,
                        const int32_t* lut8_host, void* stream);                                                            /* fxpmodel.py:70-144 */
 
+/* ------------------------------------------------------------------------------------------------
+ * (5) NDNS pre/post-processing either side of the model forward.
+ * Boxcar STFT with nperseg = nfft = 512, hop 128, one-sided (257 bins), zero boundary extension,
+ * scaling 1/512 - the jax.scipy.signal.stft / istft calls of sparseRNNs/train_helpers.py.
+ *   layout_blf != 0: spectra are (B, L, 257) (the model's layout); 0: (B, 257, L) (what the reference's
+ *   stft_splitter returns and stft_mixer takes).
+ * ---------------------------------------------------------------------------------------------- */
+/* frames L of the transform for T audio samples (480000 -> 3751) */
+int s5b200_stft_frames(int T);
+/* stft_splitter, train_helpers.py:1381-1396: audio [B][T] -> mag, phase (each nullable).  model_in (nullable,
+ * always (B, L, 257)) receives mag - mag_sub, the model input of train_helpers.py:1570-1573. */
+int s5b200_stft(const float* audio, int B, int T, float* mag, float* phase, int layout_blf, float* model_in,
+                float mag_sub, void* stream);
+/* stft_mixer, train_helpers.py:1399-1412, with the mask apply of :1605-1606 fused in: mask_blf (nullable) is the model
+ * output (B, L, 257) and the spectrum magnitude becomes mag * (1 + mask); audio_out [B][(L - 1) * 128];
+ * cleaned_mag_out (nullable, layout of mag) receives mag * (1 + mask). */
+int s5b200_istft(const float* mag, const float* phase, int layout_blf, const float* mask_blf, int B, int L,
+                 float* audio_out, float* cleaned_mag_out, void* stream);
+/* workspace of the two per-clip reductions below */
+size_t s5b200_reduce_workspace_bytes(int B, long long n_per_clip);
+/* si_snr_jax, train_helpers.py:16-53: target, estimate [B][T] -> out_db [B] (sums accumulated in float64, fixed order) */
+int s5b200_si_snr(const float* target, const float* estimate, int B, long long T, float* out_db, void* workspace,
+                  size_t workspace_bytes, void* stream);
+/* mean((a - b)^2) over the n_per_clip values of every clip: the magnitude term of the loss, train_helpers.py:1609-1611 */
+int s5b200_mse_clips(const float* a, const float* b, int B, long long n_per_clip, float* out, void* workspace,
+                     size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

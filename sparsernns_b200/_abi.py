@@ -131,6 +131,12 @@ PROTOTYPES = {
     "s5b200_fxp_mul_compute_best": (_I, [_V, _V, _V, _LL, _LL, _I, _I, _I, C.POINTER(_I), _V]),
     "s5b200_fxp_relu": (_I, [_V, _V, _LL, _V]),
     "s5b200_fxp_sigmoid": (_I, [_V, _V, _LL, _I, _I, _I, _I, _V, _V]),
+    "s5b200_stft_frames": (_I, [_I]),
+    "s5b200_stft": (_I, [_V, _I, _I, _V, _V, _I, _V, C.c_float, _V]),
+    "s5b200_istft": (_I, [_V, _V, _I, _V, _I, _I, _V, _V, _V]),
+    "s5b200_reduce_workspace_bytes": (_SZ, [_I, _LL]),
+    "s5b200_si_snr": (_I, [_V, _V, _I, _LL, _V, _V, _SZ, _V]),
+    "s5b200_mse_clips": (_I, [_V, _V, _I, _LL, _V, _V, _SZ, _V]),
 }
 
 _lib = None

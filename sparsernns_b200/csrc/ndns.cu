@@ -1,0 +1,368 @@
+// ndns.cu - NDNS pre/post-processing either side of the model forward.
+//
+//   s5b200_stft      : stft_splitter, train_helpers.py:1381-1396 (jax.scipy.signal.stft: boxcar, nperseg = nfft = 512,
+//                      hop 128, one-sided, boundary='zeros', padded=True, scaling='spectrum' = 1 / 512) -> magnitude, angle
+//                      and, fused, the model input  mag - 0.0007  in the model's (B, L, 257) layout (:1570-1573)
+//   s5b200_istft     : mask apply  mag * (1 + mask)  (:1605-1606) + stft_mixer, :1399-1412 (un-normalised inverse real
+//                      DFT per frame, overlap-add, division by the number of covering frames, 256 samples trimmed)
+//   s5b200_si_snr    : si_snr_jax, :16-53
+//   s5b200_mse_clips : mean((a - b)^2) per clip, the magnitude term of the loss (:1609-1611)
+//
+// All of it is HBM-bound streaming work: 61 MB of audio against 2 x 123 MB of spectra per 32-clip batch.  A 512-point
+// real transform is one 256-point complex Stockham radix-2 FFT per warp in shared memory (x[2n] + i x[2n+1]) plus the
+// split / merge pass; twiddles come from one sincospif table per CTA.
+#include <cmath>
+
+#include "common.cuh"
+
+namespace s5 {
+
+constexpr int kNfft = 512, kHop = 128, kBins = 257;
+constexpr int kFB = 32;            // frames (STFT) / hops (iSTFT) per CTA
+constexpr int kNdThreads = 256;
+
+__device__ __forceinline__ float2 cmul2(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+
+// 256-point complex FFT, one warp, ping-pong buffers in shared memory; 8 stages, so the result ends in `a`.
+// tw[k] = exp(-2 pi i k / 512), k < 256.  INV: conjugated twiddles (un-normalised inverse).
+template <bool INV>
+__device__ __forceinline__ void fft256_warp(float2* a, float2* b, const float2* tw, int lane) {
+  float2* in = a;
+  float2* out = b;
+#pragma unroll
+  for (int s = 0; s < 8; ++s) {
+    const int Ns = 1 << s;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int j = lane + 32 * q, r = j & (Ns - 1);
+      const float2 u = in[j];
+      float2 w = tw[r << (8 - s)];
+      if (INV) w.y = -w.y;
+      const float2 v = cmul2(in[j + 128], w);
+      const int j0 = ((j - r) << 1) + r;
+      out[j0] = make_float2(u.x + v.x, u.y + v.y);
+      out[j0 + Ns] = make_float2(u.x - v.x, u.y - v.y);
+    }
+    __syncwarp();
+    float2* t = in; in = out; out = t;
+  }
+}
+
+__device__ __forceinline__ void make_twiddles(float2* tw) {
+  for (int k = threadIdx.x; k < 256; k += blockDim.x) {
+    float s, c;
+    sincospif((float)k * (1.0f / 256.0f), &s, &c);            // exp(-i pi k / 256)
+    tw[k] = make_float2(c, -s);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- STFT
+struct StftParams {
+  const float* audio; int B, T, L;
+  float* mag; float* phase; int blf;   // blf: outputs (B, L, 257); else the reference's (B, 257, L)
+  float* model_in; float mag_sub;      // (B, L, 257) = mag - mag_sub
+};
+
+__global__ void __launch_bounds__(kNdThreads) stft_kernel(StftParams p) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  constexpr int kSeg = (kFB - 1) * kHop + kNfft;              // samples the CTA's frames cover
+  float* seg = reinterpret_cast<float*>(smem);
+  float2* tw = reinterpret_cast<float2*>(seg + kSeg);
+  float2* work = tw + 256;                                    // [8 warps][2][256]
+  float* omag = reinterpret_cast<float*>(work + 8 * 512);     // [kFB][257]
+  float* oph = omag + kFB * kBins;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.y, k0 = blockIdx.x * kFB, nf = min(kFB, p.L - k0);
+  make_twiddles(tw);
+  const float* au = p.audio + (size_t)b * p.T;
+  const long long t0 = (long long)k0 * kHop - kNfft / 2;      // audio index of the segment's first sample
+  for (int i = tid; i < kSeg; i += kNdThreads) {
+    const long long t = t0 + i;
+    seg[i] = (t >= 0 && t < p.T) ? au[t] : 0.f;
+  }
+  __syncthreads();
+  float2* za = work + warp * 512;
+  float2* zb = za + 256;
+  for (int f = warp; f < nf; f += 8) {
+    const float2* x2 = reinterpret_cast<const float2*>(seg + f * kHop);   // z[n] = x[2n] + i x[2n+1]
+#pragma unroll
+    for (int q = 0; q < 8; ++q) za[lane + 32 * q] = x2[lane + 32 * q];
+    __syncwarp();
+    fft256_warp<false>(za, zb, tw, lane);
+    // split: X[k] = E + W^k O,  E = (Z[k] + conj Z[256 - k]) / 2,  O = -i (Z[k] - conj Z[256 - k]) / 2;  scaled by 1 / 512
+    for (int k = lane; k < kBins; k += 32) {
+      const float2 zk = za[k & 255], zc = za[(256 - k) & 255];
+      const float2 E = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y - zc.y));
+      const float2 O = make_float2(0.5f * (zk.y + zc.y), -0.5f * (zk.x - zc.x));
+      const float2 w = k < 256 ? tw[k] : make_float2(-1.f, 0.f);
+      const float2 wo = cmul2(w, O);
+      const float re = (E.x + wo.x) * (1.0f / kNfft), im = (E.y + wo.y) * (1.0f / kNfft);
+      omag[f * kBins + k] = hypotf(re, im);
+      oph[f * kBins + k] = atan2f(im, re);
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  // ---- write-out: rows of 257 floats (BLF, model input) are contiguous per frame; BFL is 32 consecutive frames per bin
+  const size_t clip_off = (size_t)b * p.L * kBins;
+  if (p.model_in) {
+    float* dst = p.model_in + clip_off + (size_t)k0 * kBins;
+    for (int i = tid; i < nf * kBins; i += kNdThreads) dst[i] = omag[i] - p.mag_sub;
+  }
+  if (p.blf) {
+    if (p.mag) { float* dst = p.mag + clip_off + (size_t)k0 * kBins; for (int i = tid; i < nf * kBins; i += kNdThreads) dst[i] = omag[i]; }
+    if (p.phase) { float* dst = p.phase + clip_off + (size_t)k0 * kBins; for (int i = tid; i < nf * kBins; i += kNdThreads) dst[i] = oph[i]; }
+  } else {
+    for (int k = warp; k < kBins; k += 8) {
+      if (lane < nf) {
+        const size_t o = clip_off + (size_t)k * p.L + k0 + lane;
+        if (p.mag) p.mag[o] = omag[lane * kBins + k];
+        if (p.phase) p.phase[o] = oph[lane * kBins + k];
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- iSTFT
+struct IstftParams {
+  const float* mag; const float* phase; int blf;
+  const float* mask;                   // model output (B, L, 257), nullable: cleaned_mag = mag * (1 + mask)
+  int B, L;
+  float* audio;                        // (B, (L - 1) * 128)
+  float* cleaned_mag;                  // nullable, layout of mag
+};
+
+__global__ void __launch_bounds__(kNdThreads) istft_kernel(IstftParams p) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  constexpr int kFr = kFB + 3;                                // frames that touch the CTA's 32 hops of output
+  constexpr int kRow = 260;                                   // float2 per spectrum row (257 bins, padded); 512 floats of time fit too
+  float2* S = reinterpret_cast<float2*>(smem);                // [kFr][kRow] spectra, then (in place) the frames' time samples
+  float2* tw = S + kFr * kRow;
+  float2* work = tw + 256;                                    // [8][2][256]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.y, h0 = blockIdx.x * kFB;            // output hops h0 .. h0 + 31 (padded coordinates)
+  const int f_lo = h0 - 3;                                    // frame of S row 0
+  make_twiddles(tw);
+  const size_t clip_off = (size_t)b * p.L * kBins;
+  // ---- load: magnitude (* (1 + mask)), angle -> complex spectrum rows
+  if (p.blf) {
+    for (int i = tid; i < kFr * kBins; i += kNdThreads) {
+      const int r = i / kBins, k = i - r * kBins, f = f_lo + r;
+      if (f < 0 || f >= p.L) continue;
+      const size_t o = clip_off + (size_t)f * kBins + k;
+      float m = p.mag[o];
+      if (p.mask) m *= 1.0f + p.mask[o];
+      // this CTA owns the cleaned magnitude of the frames that START in its hops (f >= h0)
+      if (p.cleaned_mag && f >= h0 && f < h0 + kFB) p.cleaned_mag[o] = m;
+      float s, c;
+      sincosf(p.phase[o], &s, &c);
+      S[r * kRow + k] = make_float2(m * c, m * s);
+    }
+  } else {
+    for (int i = tid; i < kBins * 64; i += kNdThreads) {      // lanes along frames (contiguous in the (B, 257, L) layout)
+      const int k = i >> 6, r = i & 63, f = f_lo + r;
+      if (r >= kFr || f < 0 || f >= p.L) continue;
+      const size_t o = clip_off + (size_t)k * p.L + f;
+      float m = p.mag[o];
+      if (p.mask) m *= 1.0f + p.mask[clip_off + (size_t)f * kBins + k];
+      if (p.cleaned_mag && f >= h0 && f < h0 + kFB) p.cleaned_mag[o] = m;
+      float s, c;
+      sincosf(p.phase[o], &s, &c);
+      S[r * kRow + k] = make_float2(m * c, m * s);
+    }
+  }
+  __syncthreads();
+  // ---- per frame: merge to the 256-point spectrum of x[2n] + i x[2n+1], inverse FFT, time samples back into the row
+  float2* za = work + warp * 512;
+  float2* zb = za + 256;
+  for (int r = warp; r < kFr; r += 8) {
+    const int f = f_lo + r;
+    if (f < 0 || f >= p.L) continue;                          // warp-uniform
+    float2* row = S + r * kRow;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int k = lane + 32 * q;
+      float2 xk = row[k], xc = row[256 - k];
+      if (k == 0) { xk.y = 0.f; xc.y = 0.f; }                 // irfft ignores the imaginary parts of DC and Nyquist
+      const float2 E = make_float2(0.5f * (xk.x + xc.x), 0.5f * (xk.y - xc.y));
+      const float2 D = make_float2(0.5f * (xk.x - xc.x), 0.5f * (xk.y + xc.y));
+      const float2 w = make_float2(tw[k].x, -tw[k].y);       // exp(+2 pi i k / 512)
+      const float2 O = cmul2(D, w);
+      za[k] = make_float2(E.x - O.y, E.y + O.x);              // Z = E + i O
+    }
+    __syncwarp();
+    fft256_warp<true>(za, zb, tw, lane);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float2 z = za[lane + 32 * q];
+      row[lane + 32 * q] = make_float2(2.f * z.x, 2.f * z.y);   // x[2n], x[2n + 1] of irfft * 512
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  // ---- overlap-add in frame order, divide by the number of covering frames, trim 256 samples either side
+  const int out_len = (p.L - 1) * kHop;
+  const float* Sf = reinterpret_cast<const float*>(S);
+  for (int i = tid; i < kFB * kHop; i += kNdThreads) {
+    const int h = h0 + (i >> 7), within = i & 127;
+    const long long t = (long long)h * kHop + within - kNfft / 2;   // output index
+    if (t < 0 || t >= out_len) continue;
+    float acc = 0.f;
+    int cnt = 0;
+#pragma unroll
+    for (int d = 3; d >= 0; --d) {                            // frames h - 3 .. h, increasing
+      const int f = h - d;
+      if (f < 0 || f >= p.L) continue;
+      acc += Sf[(size_t)(f - f_lo) * (2 * kRow) + d * kHop + within];
+      ++cnt;
+    }
+    p.audio[(size_t)b * out_len + t] = acc / (float)cnt;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- per-clip reductions
+// partials[b][chunk][5] (double): sum t, sum e, sum t^2, sum e^2, sum t e over one chunk; fixed-order finalisation.
+constexpr int kRedChunk = 16384;
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <int NS>
+__device__ __forceinline__ void block_sums(double (&v)[NS], double* out) {
+  __shared__ double sh[NS][8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int s = 0; s < NS; ++s) {
+    v[s] = warp_sum(v[s]);
+    if (lane == 0) sh[s][warp] = v[s];
+  }
+  __syncthreads();
+  if (threadIdx.x < NS) {
+    double a = 0;
+    for (int w = 0; w < 8; ++w) a += sh[threadIdx.x][w];
+    out[threadIdx.x] = a;
+  }
+}
+
+__global__ void __launch_bounds__(kNdThreads) snr_partial_kernel(const float* target, const float* est, long long T, int nchunk, double* partials) {
+  const int b = blockIdx.y, c = blockIdx.x;
+  const long long i0 = (long long)c * kRedChunk, i1 = min(T, i0 + kRedChunk);
+  const float* t = target + (size_t)b * T;
+  const float* e = est + (size_t)b * T;
+  double v[5] = {0, 0, 0, 0, 0};
+  for (long long i = i0 + threadIdx.x; i < i1; i += kNdThreads) {
+    const double a = t[i], x = e[i];
+    v[0] += a; v[1] += x; v[2] += a * a; v[3] += x * x; v[4] += a * x;
+  }
+  block_sums<5>(v, partials + ((size_t)b * nchunk + c) * 5);
+}
+
+__global__ void snr_final_kernel(const double* partials, long long T, int nchunk, int B, float* out_db) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  double s[5] = {0, 0, 0, 0, 0};
+  for (int c = 0; c < nchunk; ++c)
+    for (int j = 0; j < 5; ++j) s[j] += partials[((size_t)b * nchunk + c) * 5 + j];
+  // zero-mean signals: dot = sum te - T mt me, |s_t|^2 = sum t^2 - T mt^2, |s_e|^2 likewise;
+  // |proj|^2 = dot^2 / |s_t|^2, |noise|^2 = |s_e|^2 - dot^2 / |s_t|^2   (train_helpers.py:39-53)
+  const double n = (double)T, mt = s[0] / n, me = s[1] / n;
+  const double dot = s[4] - n * mt * me, tt = s[2] - n * mt * mt, ee = s[3] - n * me * me;
+  const double proj2 = dot * dot / tt, noise2 = fmax(ee - proj2, 0.0);
+  out_db[b] = (float)(10.0 * log10(proj2 / (noise2 + 1e-8) + 1e-8));
+}
+
+__global__ void __launch_bounds__(kNdThreads) mse_partial_kernel(const float* a, const float* bb, long long n, int nchunk, double* partials) {
+  const int b = blockIdx.y, c = blockIdx.x;
+  const long long i0 = (long long)c * kRedChunk, i1 = min(n, i0 + kRedChunk);
+  double v[1] = {0};
+  for (long long i = i0 + threadIdx.x; i < i1; i += kNdThreads) {
+    const double d = (double)a[(size_t)b * n + i] - (double)bb[(size_t)b * n + i];
+    v[0] += d * d;
+  }
+  block_sums<1>(v, partials + (size_t)b * nchunk + c);
+}
+__global__ void mse_final_kernel(const double* partials, long long n, int nchunk, int B, float* out) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  double s = 0;
+  for (int c = 0; c < nchunk; ++c) s += partials[(size_t)b * nchunk + c];
+  out[b] = (float)(s / (double)n);
+}
+
+static int red_chunks(long long n) { return (int)((n + kRedChunk - 1) / kRedChunk); }
+
+}  // namespace s5
+
+using namespace s5;
+
+extern "C" int s5b200_stft_frames(int T) {
+  if (T <= 0) return 0;
+  const long long ext = (long long)T + kNfft;
+  const long long pad = (kHop - (ext - kNfft) % kHop) % kHop;
+  return (int)((ext + pad - kNfft) / kHop + 1);
+}
+
+extern "C" int s5b200_stft(const float* audio, int B, int T, float* mag, float* phase, int layout_blf, float* model_in, float mag_sub,
+                           void* stream) {
+  if (!audio || (!mag && !phase && !model_in)) S5_FAIL(S5_E_BADARG, "stft: null pointer");
+  if (B <= 0 || T <= 0 || B > 65535) S5_FAIL(S5_E_BADSHAPE, "stft: B=%d T=%d outside the supported range", B, T);
+  StftParams p{audio, B, T, s5b200_stft_frames(T), mag, phase, layout_blf, model_in, mag_sub};
+  const size_t smem = (size_t)((kFB - 1) * kHop + kNfft) * 4 + 256 * 8 + 8 * 512 * 8 + 2 * (size_t)kFB * kBins * 4;
+  S5_CUDA(cudaFuncSetAttribute(stft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ProfScope prof(S5_K_OTHER, (cudaStream_t)stream);
+  stft_kernel<<<dim3((p.L + kFB - 1) / kFB, B), kNdThreads, smem, (cudaStream_t)stream>>>(p);
+  S5_LAUNCH_CHECK();
+  return S5_OK;
+}
+
+extern "C" int s5b200_istft(const float* mag, const float* phase, int layout_blf, const float* mask_blf, int B, int L, float* audio_out,
+                            float* cleaned_mag_out, void* stream) {
+  if (!mag || !phase || !audio_out) S5_FAIL(S5_E_BADARG, "istft: null pointer");
+  if (B <= 0 || L < 2 || B > 65535) S5_FAIL(S5_E_BADSHAPE, "istft: B=%d L=%d outside the supported range", B, L);
+  IstftParams p{mag, phase, layout_blf, mask_blf, B, L, audio_out, cleaned_mag_out};
+  const size_t smem = (size_t)(kFB + 3) * 260 * 8 + 256 * 8 + 8 * 512 * 8;
+  S5_CUDA(cudaFuncSetAttribute(istft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // hops 0 .. L + 2 carry output samples (frame L - 1 ends at hop L + 2)
+  ProfScope prof(S5_K_OTHER, (cudaStream_t)stream);
+  istft_kernel<<<dim3((L + 3 + kFB - 1) / kFB, B), kNdThreads, smem, (cudaStream_t)stream>>>(p);
+  S5_LAUNCH_CHECK();
+  return S5_OK;
+}
+
+extern "C" size_t s5b200_reduce_workspace_bytes(int B, long long n_per_clip) {
+  if (B <= 0 || n_per_clip <= 0) return 0;
+  return (size_t)B * red_chunks(n_per_clip) * 5 * sizeof(double);
+}
+
+extern "C" int s5b200_si_snr(const float* target, const float* estimate, int B, long long T, float* out_db, void* workspace,
+                             size_t workspace_bytes, void* stream) {
+  if (!target || !estimate || !out_db || !workspace) S5_FAIL(S5_E_BADARG, "si_snr: null pointer");
+  if (B <= 0 || T <= 0 || B > 65535) S5_FAIL(S5_E_BADSHAPE, "si_snr: B=%d T=%lld outside the supported range", B, T);
+  if (workspace_bytes < s5b200_reduce_workspace_bytes(B, T)) S5_FAIL(S5_E_BADARG, "si_snr: workspace too small");
+  const int nchunk = red_chunks(T);
+  cudaStream_t st = (cudaStream_t)stream;
+  ProfScope prof(S5_K_OTHER, st);
+  snr_partial_kernel<<<dim3(nchunk, B), kNdThreads, 0, st>>>(target, estimate, T, nchunk, reinterpret_cast<double*>(workspace));
+  S5_LAUNCH_CHECK();
+  snr_final_kernel<<<(B + 127) / 128, 128, 0, st>>>(reinterpret_cast<const double*>(workspace), T, nchunk, B, out_db);
+  S5_LAUNCH_CHECK();
+  return S5_OK;
+}
+
+extern "C" int s5b200_mse_clips(const float* a, const float* b, int B, long long n_per_clip, float* out, void* workspace,
+                                size_t workspace_bytes, void* stream) {
+  if (!a || !b || !out || !workspace) S5_FAIL(S5_E_BADARG, "mse_clips: null pointer");
+  if (B <= 0 || n_per_clip <= 0 || B > 65535) S5_FAIL(S5_E_BADSHAPE, "mse_clips: B=%d n=%lld outside the supported range", B, n_per_clip);
+  if (workspace_bytes < s5b200_reduce_workspace_bytes(B, n_per_clip)) S5_FAIL(S5_E_BADARG, "mse_clips: workspace too small");
+  const int nchunk = red_chunks(n_per_clip);
+  cudaStream_t st = (cudaStream_t)stream;
+  ProfScope prof(S5_K_OTHER, st);
+  mse_partial_kernel<<<dim3(nchunk, B), kNdThreads, 0, st>>>(a, b, n_per_clip, nchunk, reinterpret_cast<double*>(workspace));
+  S5_LAUNCH_CHECK();
+  mse_final_kernel<<<(B + 127) / 128, 128, 0, st>>>(reinterpret_cast<const double*>(workspace), n_per_clip, nchunk, B, out);
+  S5_LAUNCH_CHECK();
+  return S5_OK;
+}
