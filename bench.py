@@ -241,6 +241,9 @@ def main():
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout for the single JSON line
         dist.init_process_group("nccl", device_id=dev)
 
+    from sparsernns_b200.dist import bind_to_gpu_numa_node
+    numa = bind_to_gpu_numa_node(local_rank)   # pinned host buffers of the e2e leg land on the GPU's NUMA node
+
     dims = synth.ndns_dims(args.dim_scale)
     params, batch_stats, cal_stats = load_fixture(args.dim_scale)
     cfg = S5Config(n_layers=dims.n_layers, d_model=dims.d_model, ssm_size=dims.ssm_size, relufication=True,
@@ -389,7 +392,7 @@ def main():
             "clocks": clock_info,
             "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": rows * D_IO * 4, "d2h_bytes_per_step": rows * D_IO * 4,
                     "steps": ke, "mode": "host-synchronous s5b200_model_forward_host per step (pinned host buffers)",
-                    "stream_ordered_value": e2e_async_fps},
+                    "stream_ordered_value": e2e_async_fps, "numa": numa},
             "gpu_launches": launches,
             "roofline": roofline,
             "kernels": kernels,

@@ -115,22 +115,27 @@ def main():
               "frac": by / ms / 1e6 / peak, "state_steps_per_s": B * L * P / ms * 1e3})
 
     # ---- sparse projection, (K + N) * 4 bytes per row
-    def spmm(rows, K, N, density):
+    def spmm(rows, K, N, density, act_zero=0.0, dead=0.0, skip=0):
+        """act_zero: fraction of activations zeroed element-wise (ReLU); dead: fraction of input channels that never fire."""
         W = rng.standard_normal((K, N)).astype(np.float32)
         W[rng.random((K, N)) > density] = 0.0
         h = C.c_void_p()
         _abi.check(lib.s5b200_sparse_create(W.ctypes.data, K, N, 0, 0, C.byref(h)), "sparse_create")
         X = torch.randn(rows, K, device=dev)
+        if act_zero > 0:
+            X = X * (torch.rand(rows, K, device=dev) >= act_zero)
+        if dead > 0:
+            X = X * (torch.rand(K, device=dev) >= dead)
         Y = torch.empty(rows, N, device=dev)
 
         def fn():
-            _abi.check(lib.s5b200_spmm_f32(h, X.data_ptr(), None, Y.data_ptr(), rows, 0, st), "spmm_f32")
+            _abi.check(lib.s5b200_spmm_f32(h, X.data_ptr(), None, Y.data_ptr(), rows, skip, st), "spmm_f32")
 
         ms = timed(fn, args.reps)
         lib.s5b200_sparse_destroy(h)
         by = 4.0 * rows * (K + N)
-        emit({"kernel": "spmm_f32", "rows": rows, "K": K, "N": N, "density": density, "us": ms * 1e3, "alg_bytes": by,
-              "gbs": by / ms / 1e6, "frac": by / ms / 1e6 / peak})
+        emit({"kernel": "spmm_f32", "rows": rows, "K": K, "N": N, "density": density, "act_zero": act_zero, "dead_channels": dead,
+              "skip_zero": skip, "us": ms * 1e3, "alg_bytes": by, "gbs": by / ms / 1e6, "frac": by / ms / 1e6 / peak})
 
     # ---- PCIe ceiling for the e2e number: pinned 123 MB each way, alone and concurrently
     def pcie():
@@ -186,6 +191,11 @@ def main():
     for rows in ((120032,) if args.quick else (128, 4096, 120032, 4096 * 1024)):
         for (K, N, d) in ((96, 128, 0.1), (128, 96, 0.1), (257, 96, 0.1), (96, 128, 1.0)):
             spmm(rows, K, N, d)
+    # zero-activation skipping (per input column x 32-row group): element-wise ReLU zeros alone rarely empty a group,
+    # channels that never fire always do
+    for (az, dead) in ((0.0, 0.0), (0.5, 0.0), (0.9, 0.0), (0.99, 0.0), (0.5, 0.5), (0.5, 0.9)):
+        for skip in (0, 1):
+            spmm(120032, 128, 96, 0.1, az, dead, skip)
     if args.out:
         with open(os.path.join(ROOT, args.out), "w") as f:
             json.dump(results, f, indent=1)

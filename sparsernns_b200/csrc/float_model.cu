@@ -81,6 +81,7 @@ struct LinearParams {
   const float* bias;
   int out_quant; float out_scale0, out_scale1, out_qmin, out_qmax;  // scale0 for even n, scale1 for odd n
   int relu;
+  int skip_zero;   // zero-activation skipping per (input column, 32-row group), proj.cuh:zero_group_mask
 };
 
 template <int TR>
@@ -93,6 +94,7 @@ __global__ void __launch_bounds__(kProjThreads) linear_f32_kernel(LinearParams p
   const WSmem w = wsmem_load(smem_i, p.w);
   float* xt = reinterpret_cast<float*>(smem_i + ww);
   float* yt = xt + (size_t)K * (TR + 1);
+  uint32_t* zmask = p.skip_zero ? reinterpret_cast<uint32_t*>(yt + (size_t)N * (TR + 1)) : nullptr;   // [K]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long ntiles = (p.rows + TR - 1) / TR;
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -104,9 +106,13 @@ __global__ void __launch_bounds__(kProjThreads) linear_f32_kernel(LinearParams p
       return v;
     });
     __syncthreads();
+    if (zmask) {
+      zero_group_mask<float, R, TR>(xt, K, zmask);
+      __syncthreads();
+    }
     for (int n = warp; n < N; n += kProjWarps) {
       float acc[R];
-      column_dot<float, R, TR>(w, K, n, xt, lane, acc);
+      column_dot<float, R, TR>(w, K, n, xt, lane, acc, zmask);
       const float bn = p.bias ? p.bias[n] : 0.f;
       const float sc = (n & 1) ? p.out_scale1 : p.out_scale0;
 #pragma unroll
@@ -147,9 +153,10 @@ static int persistent_grid(KernelT kernel, size_t smem, long long ntiles, int* g
 static int launch_linear(LinearParams p, cudaStream_t st, int kclass = S5_K_OTHER) {
   if (p.rows <= 0) S5_FAIL(S5_E_BADSHAPE, "linear: rows=%lld must be positive", p.rows);
   const size_t wbytes = ((wsmem_words_host(p.w)) * 4);
-  const int tr = pick_tr(wbytes, (size_t)(p.w.K + p.w.N) * 4);
+  const size_t zbytes = p.skip_zero ? (size_t)p.w.K * 4 : 0;
+  const int tr = pick_tr(wbytes + zbytes, (size_t)(p.w.K + p.w.N) * 4);
   if (!tr) S5_FAIL(S5_E_BADSHAPE, "linear: K=%d N=%d weights (%zu B) do not fit in shared memory", p.w.K, p.w.N, wbytes);
-  const size_t smem = wbytes + (size_t)(p.w.K + p.w.N) * (tr + 1) * 4;
+  const size_t smem = wbytes + (size_t)(p.w.K + p.w.N) * (tr + 1) * 4 + zbytes;
   const long long ntiles = (p.rows + tr - 1) / tr;
   int grid = 1, rc;
   ProfScope prof(kclass, st);
@@ -183,6 +190,7 @@ struct GluParams {
   int static_q; float s_ut, s_yt, s_o_act, s_o_out, s_gl, s_gr;
   float qs_min, qs_max, qn_min, qn_max;  // SSM-activation / non-SSM-activation integer ranges
   int act, relu_out, ssm_only;
+  int skip_zero;   // zero-activation skipping for the C projection (ReLU-ified states) and out2 (x1 >= 0)
 };
 
 __device__ __forceinline__ float gelu_tanh_f(float x) {
@@ -207,6 +215,7 @@ __global__ void __launch_bounds__(kProjThreads) glu_f32_kernel(GluParams p) {
   float* bufA = reinterpret_cast<float*>(smem_i + w1 + w2);  // xs tile, later g
   float* bufB = bufA + (size_t)rowsA * LD;                   // x tile (u source), later FQ(x1) for out2
   float* bufC = bufB + (size_t)H * LD;                       // x1
+  uint32_t* zmask = p.skip_zero ? reinterpret_cast<uint32_t*>(bufC + (size_t)H * LD) : nullptr;   // [max(K1, H)]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long ntiles = (p.rows + TR - 1) / TR;
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -220,10 +229,14 @@ __global__ void __launch_bounds__(kProjThreads) glu_f32_kernel(GluParams p) {
       return v;  // u (u_q for the static flavour), ssm.py:230
     });
     __syncthreads();
+    if (zmask) {
+      zero_group_mask<float, R, TR>(bufA, K1, zmask);
+      __syncthreads();
+    }
     // y = conj_mul * Re(C x) + D * u  [-> FQ]  -> x1 = act(y)
     for (int n = warp; n < H; n += kProjWarps) {
       float acc[R];
-      column_dot<float, R, TR>(wc, K1, n, bufA, lane, acc);
+      column_dot<float, R, TR>(wc, K1, n, bufA, lane, acc, zmask);
       const float dn = p.D[n];
 #pragma unroll
       for (int j = 0; j < R; ++j) {
@@ -244,10 +257,14 @@ __global__ void __launch_bounds__(kProjThreads) glu_f32_kernel(GluParams p) {
       unstage_rows<float, float, TR>(p.OUT + row0 * H, bufC, rv, H, [](float v, int, int) { return v; });
       continue;
     }
+    if (zmask) {
+      zero_group_mask<float, R, TR>(bufB, H, zmask);
+      __syncthreads();
+    }
     // o = out2(x1) ; g = FQ(x1) * FQ(sigmoid(o))
     for (int n = warp; n < H; n += kProjWarps) {
       float acc[R];
-      column_dot<float, R, TR>(wo, H, n, bufB, lane, acc);
+      column_dot<float, R, TR>(wo, H, n, bufB, lane, acc, zmask);
       const float bn = p.out2_bias[n];
 #pragma unroll
       for (int j = 0; j < R; ++j) {
@@ -278,9 +295,10 @@ static int launch_glu(GluParams p, cudaStream_t st) {
   const int K1 = p.wc.K, H = p.wc.N;
   const size_t wbytes = (wsmem_words_host(p.wc) + (p.ssm_only ? 0 : wsmem_words_host(p.wo))) * 4;
   const size_t per_row = (size_t)(std::max(K1, H) + 2 * H) * 4;
-  const int tr = pick_tr(wbytes, per_row);
+  const size_t zbytes = p.skip_zero ? (size_t)std::max(K1, H) * 4 : 0;
+  const int tr = pick_tr(wbytes + zbytes, per_row);
   if (!tr) S5_FAIL(S5_E_BADSHAPE, "glu: H=%d 2P=%d weights (%zu B) do not fit in shared memory", H, K1, wbytes);
-  const size_t smem = wbytes + per_row * (tr + 1);
+  const size_t smem = wbytes + per_row * (tr + 1) + zbytes;
   const long long ntiles = (p.rows + tr - 1) / tr;
   int grid = 1, rc;
   ProfScope prof(S5_K_GLU, st);
@@ -331,6 +349,8 @@ struct s5_model {
   bool fuse_scan = true;         // static dense-tile path: run the recurrence inside the GLU kernel (S5B200_FUSE_SCAN=0 disables)
   bool fuse_bproj = true;        // ... and the B projection as well: one kernel per block (S5B200_FUSE_BPROJ=0 disables)
   bool fuse_layers = true;       // ... and all blocks in one launch (S5B200_FUSE_LAYERS=0 disables)
+  bool skip_zero = false;        // CUDA-core kernels skip all-zero (input column, 32-row group) pairs of ReLU-ified inputs (S5B200_SKIP_ZERO=1
+                                 // enables; exact, but measured slower on B200 - the kernels are issue bound, not multiply bound)
   float *enc_bias = nullptr, *dec_bias = nullptr;
   std::vector<s5::LayerDev> layers;
   // host-buffer entry point: ring of device buffers, three streams (H2D | forward | D2H) and their events
@@ -408,6 +428,8 @@ static GluParams glu_params(const s5_model* m, const LayerDev& ld, const float* 
   qrange(m->desc.ssm_act_bits, &p.qs_min, &p.qs_max);
   qrange(m->desc.non_ssm_act_bits, &p.qn_min, &p.qn_max);
   p.act = m->desc.activation; p.relu_out = m->desc.relufication; p.ssm_only = ssm_only;
+  // the states are ReLU-ified only with relufication; x1 >= 0 is sparse only behind a ReLU activation
+  p.skip_zero = m->skip_zero && m->desc.relufication && m->desc.activation == S5_ACT_RELU;
   return p;
 }
 
@@ -476,6 +498,7 @@ static LinearParams dense_params(const s5_model* m, const SparseDev& w, const fl
   p.out_quant = sq; p.out_scale0 = p.out_scale1 = s_out;
   qrange(m->desc.non_ssm_act_bits, &p.out_qmin, &p.out_qmax);
   p.relu = relu;
+  p.skip_zero = m->skip_zero && m->desc.relufication && relu == 0;   // decoder input: the ReLU-ified block output
   return p;
 }
 
@@ -504,11 +527,10 @@ extern "C" int s5b200_sparse_export(const s5_sparse* w, int32_t* k_idx_host, int
 }
 extern "C" int s5b200_spmm_f32(const s5_sparse* w, const float* X, const float* bias, float* Y, long long rows,
                                int skip_zero_cols, void* stream) {
-  (void)skip_zero_cols;
   if (!w || !X || !Y) S5_FAIL(S5_E_BADARG, "spmm_f32: null pointer");
   if (w->d.dtype != S5_F32) S5_FAIL(S5_E_BADARG, "spmm_f32: handle holds int32 weights");
   s5::LinearParams p{};
-  p.X = X; p.Y = Y; p.rows = rows; p.w = s5::wview(w->d); p.bias = bias;
+  p.X = X; p.Y = Y; p.rows = rows; p.w = s5::wview(w->d); p.bias = bias; p.skip_zero = skip_zero_cols != 0;
   return s5::launch_linear(p, (cudaStream_t)stream);
 }
 
@@ -531,6 +553,7 @@ extern "C" int s5b200_model_create(const s5_model_desc* d, s5_model** out) {
   if (const char* e = getenv("S5B200_FUSE_SCAN")) m->fuse_scan = atoi(e) != 0;
   if (const char* e = getenv("S5B200_FUSE_BPROJ")) m->fuse_bproj = atoi(e) != 0;
   if (const char* e = getenv("S5B200_FUSE_LAYERS")) m->fuse_layers = atoi(e) != 0;
+  if (const char* e = getenv("S5B200_SKIP_ZERO")) m->skip_zero = atoi(e) != 0;
   const int H = d->H, P = d->P, dense = d->use_sparse ? 0 : 1;
   int rc = S5_OK;
   auto fail = [&](int code) { s5b200_model_destroy(m); return code; };

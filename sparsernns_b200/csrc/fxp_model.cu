@@ -13,6 +13,7 @@
 // kernels separated by grid-wide reductions.  No host round trip: maxima and exponents live in a small
 // device state block; each kernel re-derives the exponent plans it needs in its prologue and re-applies the
 // cheap element-wise BatchNorm chain from the block input instead of materialising the intermediates.
+#include <cstdlib>
 #include <algorithm>
 #include <mutex>
 #include <vector>
@@ -158,6 +159,12 @@ __global__ void __launch_bounds__(256) fxp_bn_apply_kernel(BnApplyParams p) {
   }
 }
 
+// the integer model is always ReLU-ified (fxpmodel.py:1316): C projection, out2 and decoder inputs are post-ReLU
+static bool fxp_skip_zero() {
+  static const bool on = [] { const char* e = getenv("S5B200_SKIP_ZERO"); return e && atoi(e) != 0; }();   // off by default: exact but measured slower on B200
+  return on;
+}
+
 // ------------------------------------------------------------------------------------------- linear kernels
 enum { LIN_ENC = 0, LIN_BPROJ = 1, LIN_DEC = 2, LIN_PLAIN = 3 };
 
@@ -177,6 +184,7 @@ struct FxpLinearParams {
   const int* next_mmean; int next_e_mean; unsigned* next_fm; int out_exp;
   // DEC: dynamic input exponent (ex[E_IN]) versus the static FxpDense input config
   int dec_inp_bits, dec_inp_exp, dec_w_exp, dec_out_exp;
+  int skip_zero;   // proj.cuh:zero_group_mask (exact: a zero activation contributes 0 to the wrapping int32 sum)
 };
 
 template <int TR>
@@ -191,6 +199,7 @@ __global__ void __launch_bounds__(kProjThreads) fxp_linear_kernel(FxpLinearParam
   const WSmem w = wsmem_load(smem_i, p.w);
   int* xt = smem_i + ww;
   int* yt = xt + (size_t)K * (TR + 1);
+  uint32_t* zmask = p.skip_zero ? reinterpret_cast<uint32_t*>(yt + (size_t)N * (TR + 1)) : nullptr;   // [K]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     if (p.mode == LIN_BPROJ) {
@@ -234,10 +243,14 @@ __global__ void __launch_bounds__(kProjThreads) fxp_linear_kernel(FxpLinearParam
       stage_rows<int, int, TR>(xt, reinterpret_cast<const int*>(p.X) + row0 * K, rv, K, [](int v, int) { return v; });
     }
     __syncthreads();
+    if (zmask) {
+      zero_group_mask<int, R, TR>(xt, K, zmask);
+      __syncthreads();
+    }
     const int rs_dyn = p.mode == LIN_DEC ? dyn[2] : 0;
     for (int n = warp; n < N; n += kProjWarps) {
       int acc[R];
-      column_dot<int, R, TR>(w, K, n, xt, lane, acc);
+      column_dot<int, R, TR>(w, K, n, xt, lane, acc, zmask);
       const int rs = p.mode == LIN_DEC ? rs_dyn : ((n & 1) ? p.rshift1 : p.rshift0);
       const int bn = p.bias_aligned ? p.bias_aligned[n] : 0;
 #pragma unroll
@@ -296,9 +309,10 @@ static int pgrid(KernelT kernel, size_t smem, long long ntiles, int* grid_out) {
 static int launch_fxp_linear(const FxpLinearParams& p, cudaStream_t st, int kclass = S5_K_OTHER) {
   if (p.rows <= 0) S5_FAIL(S5_E_BADSHAPE, "fxp linear: rows=%lld must be positive", p.rows);
   const size_t wbytes = wwords_h(p.w) * 4;
-  const int tr = pick_tr_f(wbytes, (size_t)(p.w.K + p.w.N) * 4);
+  const size_t zbytes = p.skip_zero ? (size_t)p.w.K * 4 : 0;
+  const int tr = pick_tr_f(wbytes + zbytes, (size_t)(p.w.K + p.w.N) * 4);
   if (!tr) S5_FAIL(S5_E_BADSHAPE, "fxp linear: K=%d N=%d weights do not fit in shared memory", p.w.K, p.w.N);
-  const size_t smem = wbytes + (size_t)(p.w.K + p.w.N) * (tr + 1) * 4;
+  const size_t smem = wbytes + (size_t)(p.w.K + p.w.N) * (tr + 1) * 4 + zbytes;
   const long long ntiles = (p.rows + tr - 1) / tr;
   int grid = 1, rc;
   ProfScope prof(kclass, st);
@@ -333,6 +347,7 @@ struct FxpGluParams {
   // sigmoid + gate
   int sig_x_exp, sig_y_exp; int lut[8];
   int gl_bits, gl_exp, gr_bits, gr_exp, g_rs, g_bits, g_exp;
+  int skip_zero;
 };
 
 template <int TR>
@@ -354,6 +369,7 @@ __global__ void __launch_bounds__(kProjThreads) fxp_glu_kernel(FxpGluParams p) {
   int* bufA = smem_i + w1 + w2 + w3;       // xs tile, later g
   int* bufB = bufA + (size_t)rowsA * LD;   // block input tile, later out2 input
   int* bufC = bufB + (size_t)H * LD;       // x1
+  uint32_t* zmask = p.skip_zero ? reinterpret_cast<uint32_t*>(bufC + (size_t)H * LD) : nullptr;   // [max(K1, H)]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) bn_make_plan(pl, p.c, p.fm, p.ex, 4);
   if (threadIdx.x < 8) lut_s[threadIdx.x] = p.lut[threadIdx.x];
@@ -371,10 +387,14 @@ __global__ void __launch_bounds__(kProjThreads) fxp_glu_kernel(FxpGluParams p) {
       return fx_change_cfg(v, pl.rb4, pl.e4, p.c.u_bits, p.c.u_exp, S5_ROUND_FLOOR);  // u, fxpmodel.py:620-624
     });
     __syncthreads();
+    if (zmask) {
+      zero_group_mask<int, R, TR>(bufA, K1, zmask);
+      __syncthreads();
+    }
     for (int n = warp; n < H; n += kProjWarps) {
       int a1[R], a2[R];
-      column_dot<int, R, TR>(wcr, K1, n, bufA, lane, a1);
-      column_dot<int, R, TR>(wci, K1, n, bufA, lane, a2);
+      column_dot<int, R, TR>(wcr, K1, n, bufA, lane, a1, zmask);
+      column_dot<int, R, TR>(wci, K1, n, bufA, lane, a2, zmask);
       const int dn = p.D[n];
 #pragma unroll
       for (int j = 0; j < R; ++j) {
@@ -391,9 +411,13 @@ __global__ void __launch_bounds__(kProjThreads) fxp_glu_kernel(FxpGluParams p) {
       }
     }
     __syncthreads();
+    if (zmask) {
+      zero_group_mask<int, R, TR>(bufB, H, zmask);
+      __syncthreads();
+    }
     for (int n = warp; n < H; n += kProjWarps) {
       int acc[R];
-      column_dot<int, R, TR>(wo, H, n, bufB, lane, acc);
+      column_dot<int, R, TR>(wo, H, n, bufB, lane, acc, zmask);
       const int bn = p.o_bias_aligned[n];
 #pragma unroll
       for (int j = 0; j < R; ++j) {
@@ -424,9 +448,10 @@ static int launch_fxp_glu(const FxpGluParams& p, cudaStream_t st) {
   const int K1 = p.wcr.K, H = p.wcr.N;
   const size_t wbytes = (wwords_h(p.wcr) + wwords_h(p.wci) + wwords_h(p.wo)) * 4;
   const size_t per_row = (size_t)(std::max(K1, H) + 2 * H) * 4;
-  const int tr = pick_tr_f(wbytes, per_row);
+  const size_t zbytes = p.skip_zero ? (size_t)std::max(K1, H) * 4 : 0;
+  const int tr = pick_tr_f(wbytes + zbytes, per_row);
   if (!tr) S5_FAIL(S5_E_BADSHAPE, "fxp glu: H=%d 2P=%d weights do not fit in shared memory", H, K1);
-  const size_t smem = wbytes + per_row * (tr + 1);
+  const size_t smem = wbytes + per_row * (tr + 1) + zbytes;
   const long long ntiles = (p.rows + tr - 1) / tr;
   int grid = 1, rc;
   ProfScope prof(S5_K_FXP_GLU, st);
@@ -644,7 +669,7 @@ static int fxp_run(const FxpRun& r, const void* x, bool x_is_float, int upto_lay
     if (stop_stage == 2 && li == upto_layer) { *cur_out = bu; *other_out = a; return S5_OK; }
     {  // C projection, D feed-through, out2, sigmoid, mult_gate
       FxpGluParams p{};
-      p.XS = bu; p.X = a; p.G = g; p.rows = rows;
+      p.XS = bu; p.X = a; p.G = g; p.rows = rows; p.skip_zero = fxp_skip_zero();
       p.wcr = wview(l.wcr); p.wci = wview(l.wci); p.wo = wview(l.out2.w);
       p.c = c; p.fm = r.fm(li); p.ex = r.ex(li); p.status = r.status();
       p.D = l.D; p.rs_cre = l.q.x_re_exp + l.q.eC_re - l.q.y_exp; p.rs_cim = l.q.x_im_exp + l.q.eC_im - l.q.y_exp;
@@ -693,6 +718,7 @@ static int fxp_forward_impl(const s5_fxp_model* m, const void* x, bool x_is_floa
   const s5_fxp_dense_desc& q = m->dec.q;
   FxpLinearParams p{};
   p.X = cur; p.Y = y_int; p.Yf = y_float; p.rows = (long long)B * L; p.w = wview(m->dec.w); p.mode = LIN_DEC;
+  p.skip_zero = fxp_skip_zero();
   p.round_mode = S5_ROUND_FLOOR; p.out_bits = q.out_bits; p.bias_aligned = m->dec.bias_aligned; p.relu = 0;
   p.out_scale = 1.0f / (float)(1ll << q.out_exp);
   p.ex = r.ex(m->desc.n_layers); p.status = r.status();
@@ -845,7 +871,6 @@ extern "C" int s5b200_fxp_model_tap(const s5_fxp_model* m, const int32_t* x_int,
 
 extern "C" int s5b200_spmm_i32(const s5_sparse* w, const int32_t* X, int32_t* Y, long long rows, int rshift, int round_mode,
                                int bits, int skip_zero_cols, void* stream) {
-  (void)skip_zero_cols;
   if (!w || !X || !Y) S5_FAIL(S5_E_BADARG, "spmm_i32: null pointer");
   if (w->d.dtype != S5_I32) S5_FAIL(S5_E_BADARG, "spmm_i32: handle holds float32 weights");
   if (rshift < 0 || rshift > 31 || (round_mode == S5_ROUND_HALF_UP && rshift < 1))
@@ -853,6 +878,6 @@ extern "C" int s5b200_spmm_i32(const s5_sparse* w, const int32_t* X, int32_t* Y,
   if (bits < 1 || bits > 32) S5_FAIL(S5_E_BADARG, "spmm_i32: bits %d outside [1, 32]", bits);
   s5::FxpLinearParams p{};
   p.X = X; p.Y = Y; p.rows = rows; p.w = s5::wview(w->d); p.mode = s5::LIN_PLAIN;
-  p.rshift0 = p.rshift1 = rshift; p.round_mode = round_mode; p.out_bits = bits;
+  p.rshift0 = p.rshift1 = rshift; p.round_mode = round_mode; p.out_bits = bits; p.skip_zero = skip_zero_cols != 0;
   return s5::launch_fxp_linear(p, (cudaStream_t)stream);
 }

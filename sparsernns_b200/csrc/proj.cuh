@@ -88,12 +88,58 @@ __device__ __forceinline__ WSmem wsmem_load(int* dst, const WView& w) {
 __device__ __forceinline__ void mac(float& acc, int wbits, float x) { acc = fmaf(__int_as_float(wbits), x, acc); }
 __device__ __forceinline__ void mac(int& acc, int wbits, int x) { acc = (int)((unsigned)acc + (unsigned)wbits * (unsigned)x); }
 
-// One output column n for the R rows a lane owns.  T is float or int.
+// Zero-activation skipping on the CUDA-core path.  After a tile is staged, bit j of zmask[k] says whether input column k
+// holds ANY non-zero among the 32 rows lane + 32 j of the tile (one ballot per 32-row group).  column_dot then skips the
+// shared-memory load and the multiply-add of every (entry, row group) whose activations are all zero - a warp-uniform
+// predicate, so it saves exactly the resource the compressed kernels are bound by (shared-memory reads).  ReLU-ified
+// activations are sparse per element and whole groups vanish for rarely firing channels; per-ELEMENT skipping has no
+// SIMT form with lanes along rows, and on the tensor-core path a zero costs nothing.
 template <typename T, int R, int TR>
-__device__ __forceinline__ void column_dot(const WSmem& w, int K, int n, const T* __restrict__ xt, int lane, T (&acc)[R]) {
+__device__ __forceinline__ void zero_group_mask(const T* __restrict__ xt, int K, uint32_t* zmask) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int k = warp; k < K; k += nw) {
+    uint32_t m = 0;
+#pragma unroll
+    for (int j = 0; j < R; ++j)
+      if (__ballot_sync(0xffffffffu, xt[(size_t)k * (TR + 1) + lane + 32 * j] != T(0))) m |= 1u << j;
+    if (lane == 0) zmask[k] = m;
+  }
+}
+
+// One output column n for the R rows a lane owns.  T is float or int.  zmask: nullable, see zero_group_mask.
+template <typename T, int R, int TR>
+__device__ __forceinline__ void column_dot(const WSmem& w, int K, int n, const T* __restrict__ xt, int lane, T (&acc)[R],
+                                           const uint32_t* __restrict__ zmask = nullptr) {
 #pragma unroll
   for (int j = 0; j < R; ++j) acc[j] = T(0);
   const T* xl = xt + lane;
+  if (zmask) {
+    if (w.wdense) {
+      const int* wr = w.wdense + (size_t)n * K;
+#pragma unroll 4
+      for (int k = 0; k < K; ++k) {
+        const uint32_t m = zmask[k];
+        if (!m) continue;
+        const int wb = wr[k];
+        const T* xp = xl + (size_t)k * (TR + 1);
+#pragma unroll
+        for (int j = 0; j < R; ++j)
+          if ((m >> j) & 1u) mac(acc[j], wb, xp[32 * j]);
+      }
+    } else {
+      const int e0 = w.colptr[n], e1 = w.colptr[n + 1];
+#pragma unroll 4
+      for (int e = e0; e < e1; ++e) {
+        const int2 en = *reinterpret_cast<const int2*>(w.ent + e);
+        const uint32_t m = zmask[en.x];
+        const T* xp = xl + (size_t)en.x * (TR + 1);
+#pragma unroll
+        for (int j = 0; j < R; ++j)
+          if ((m >> j) & 1u) mac(acc[j], en.y, xp[32 * j]);
+      }
+    }
+    return;
+  }
   if (w.wdense) {
     const int* wr = w.wdense + (size_t)n * K;
 #pragma unroll 4
@@ -117,26 +163,44 @@ __device__ __forceinline__ void column_dot(const WSmem& w, int K, int n, const T
 
 // Stage TR rows of a row-major [rows][K] matrix into the transposed tile xt[K][TR+1]; rows past
 // `rows_valid` are zero-filled.  f(value, k) is the per-element input transform.
+// Every warp owns blocks of kStageRows consecutive rows and requests all of them before it converts and stores any:
+// eight independent global loads in flight per lane instead of one DRAM round trip per row (the staging used to be
+// the latency bottleneck of every CUDA-core kernel: time did not depend on how much arithmetic was skipped).
+constexpr int kStageRows = 8;
 template <typename Tin, typename T, int TR, typename F>
 __device__ __forceinline__ void stage_rows(T* xt, const Tin* __restrict__ src, int rows_valid, int K, F f) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nw = blockDim.x >> 5;
-  for (int r = warp; r < TR; r += nw) {
-    const bool ok = r < rows_valid;
-    const Tin* row = src + (size_t)r * K;
-    for (int k = lane; k < K; k += 32) xt[(size_t)k * (TR + 1) + r] = ok ? f(row[k], k) : T(0);
+  for (int r0 = warp * kStageRows; r0 < TR; r0 += nw * kStageRows) {
+    for (int k = lane; k < K; k += 32) {
+      Tin v[kStageRows];
+#pragma unroll
+      for (int q = 0; q < kStageRows; ++q) v[q] = r0 + q < rows_valid ? src[(size_t)(r0 + q) * K + k] : Tin(0);
+#pragma unroll
+      for (int q = 0; q < kStageRows; ++q)
+        if (r0 + q < TR) xt[(size_t)k * (TR + 1) + r0 + q] = r0 + q < rows_valid ? f(v[q], k) : T(0);
+    }
   }
 }
 
 // Write the transposed tile yt[N][TR+1] to a row-major [rows][N] matrix; g(value, r, n) is the final
-// per-element transform (e.g. residual add with a coalesced read of the skip tensor).
+// per-element transform (e.g. residual add with a coalesced read of the skip tensor).  g is evaluated for a block of
+// rows before any of them is stored, so the global reads inside g (skip connection) are not serialised behind the
+// stores they cannot be proven independent of.
 template <typename T, typename Tout, int TR, typename G>
 __device__ __forceinline__ void unstage_rows(Tout* dst, const T* yt, int rows_valid, int N, G g) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nw = blockDim.x >> 5;
-  for (int r = warp; r < rows_valid; r += nw) {
-    Tout* row = dst + (size_t)r * N;
-    for (int n = lane; n < N; n += 32) row[n] = g(yt[(size_t)n * (TR + 1) + r], r, n);
+  for (int r0 = warp * kStageRows; r0 < rows_valid; r0 += nw * kStageRows) {
+    for (int n = lane; n < N; n += 32) {
+      Tout v[kStageRows];
+#pragma unroll
+      for (int q = 0; q < kStageRows; ++q)
+        if (r0 + q < rows_valid) v[q] = g(yt[(size_t)n * (TR + 1) + r0 + q], r0 + q, n);
+#pragma unroll
+      for (int q = 0; q < kStageRows; ++q)
+        if (r0 + q < rows_valid) dst[(size_t)(r0 + q) * N + n] = v[q];
+    }
   }
 }
 

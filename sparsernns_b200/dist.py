@@ -58,3 +58,43 @@ def reduce_metrics(values, op: str = "sum", group=None):
     out = values.clone()
     dist.all_reduce(out, op=ops[op], group=group)
     return out
+
+
+def parse_cpulist(text: str) -> list:
+    """'0-3,8,10-11' -> [0, 1, 2, 3, 8, 10, 11] (the format of /sys/.../local_cpulist)."""
+    cpus = []
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.extend(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_to_gpu_numa_node(device_index: int) -> dict:
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off (best effort; returns what was done).
+
+    Pinned host buffers are placed by first touch, so a rank that runs on its GPU's node gets host memory on that
+    node and its H2D / D2H copies do not cross the socket interconnect.  Matters for the end-to-end number when
+    8 ranks stream 2 x 50 GB/s each; has no effect on the device-resident numbers.
+    """
+    import os
+
+    import torch
+
+    info = {"bound": False}
+    try:
+        p = torch.cuda.get_device_properties(device_index)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        base = f"/sys/bus/pci/devices/{bdf}"
+        with open(f"{base}/numa_node") as f:
+            info["numa_node"] = int(f.read().strip())
+        with open(f"{base}/local_cpulist") as f:
+            cpus = parse_cpulist(f.read())
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            info.update(bound=True, n_cpus=len(allowed))
+    except Exception as e:  # no sysfs entry (virtualised PCI), no permission, ...: run unbound
+        info["error"] = f"{type(e).__name__}: {e}"
+    return info

@@ -50,3 +50,12 @@ def test_gloo_world_size_2(n_clips):
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def test_parse_cpulist_and_numa_binding_is_best_effort():
+    from sparsernns_b200.dist import bind_to_gpu_numa_node, parse_cpulist
+
+    assert parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
+    assert parse_cpulist("") == []
+    info = bind_to_gpu_numa_node(0)          # no GPU here: reports the reason, never raises
+    assert info["bound"] is False and "error" in info

@@ -175,6 +175,63 @@ def test_spmm_f32_ragged_rows(cuda_device):
         lib.s5b200_sparse_destroy(h)
 
 
+def test_spmm_zero_activation_skipping_is_exact(cuda_device):
+    """skip_zero_cols=1 (per input column x 32-row group, proj.cuh) gives bit-identical results: dead channels, dead
+    row groups, ragged tail; float and int32 weights, compressed and dense forms."""
+    import ctypes as C
+    import torch
+    from sparsernns_b200 import _abi
+
+    lib = _abi.lib()
+    rng = np.random.default_rng(5)
+    st = lambda: C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for (rows, K, N, dens, dense_fmt) in [(333, 96, 128, 0.1, 0), (257, 128, 96, 0.15, 0), (70, 64, 40, 1.0, 1), (1, 7, 5, 1.0, 1)]:
+        W = (rng.standard_normal((K, N)) * (rng.uniform(size=(K, N)) < dens)).astype(np.float32)
+        X = np.maximum(rng.standard_normal((rows, K)), 0).astype(np.float32)      # ReLU-ified activations
+        X[:, rng.uniform(size=K) < 0.3] = 0                                        # dead channels
+        X[32:96] *= (rng.uniform(size=K) < 0.5)                                    # columns that vanish for two row groups
+        X[200:] = 0
+        h = C.c_void_p()
+        _abi.check(lib.s5b200_sparse_create(W.ctypes.data, K, N, _abi.F32, dense_fmt, C.byref(h)))
+        dX = torch.from_numpy(X).to(cuda_device)
+        out = []
+        for skip in (0, 1):
+            dY = torch.empty(rows, N, device=cuda_device)
+            _abi.check(lib.s5b200_spmm_f32(h, dX.data_ptr(), None, dY.data_ptr(), rows, skip, st()))
+            out.append(dY.cpu().numpy())
+        assert np.array_equal(out[0], out[1])
+        assert relerr(out[1], X.astype(np.float64) @ W.astype(np.float64)) <= TOL_F32
+        lib.s5b200_sparse_destroy(h)
+        Wi = np.round(W * 20).astype(np.int32)
+        Xi = np.round(X * 1000).astype(np.int32)
+        _abi.check(lib.s5b200_sparse_create(Wi.ctypes.data, K, N, _abi.I32, dense_fmt, C.byref(h)))
+        dXi = torch.from_numpy(Xi).to(cuda_device)
+        outi = []
+        for skip in (0, 1):
+            dY = torch.empty(rows, N, dtype=torch.int32, device=cuda_device)
+            _abi.check(lib.s5b200_spmm_i32(h, dXi.data_ptr(), dY.data_ptr(), rows, 3, _abi.ROUND_FLOOR, 16, skip, st()))
+            outi.append(dY.cpu().numpy())
+        assert np.array_equal(outi[0], outi[1])
+        ref = np.clip((Xi.astype(np.int64) @ Wi.astype(np.int64)) >> 3, -32768, 32767)
+        assert np.array_equal(outi[1], ref)
+        lib.s5b200_sparse_destroy(h)
+
+
+def test_model_zero_skipping_changes_no_bit(cuda_device, zoo, monkeypatch):
+    """CUDA-core model path with and without zero-activation skipping (S5B200_SKIP_ZERO): identical outputs."""
+    import torch
+
+    monkeypatch.setenv("S5B200_TC_MIN_ROWS", "1000000000")
+    x = torch.from_numpy(zoo["x"]).to(cuda_device)
+    outs = []
+    for flag in ("1", "0"):   # default is off (measured slower on B200); both must agree bit for bit
+        monkeypatch.setenv("S5B200_SKIP_ZERO", flag)
+        m, _ = _bound(zoo, static=True, relufication=True)
+        mf, _ = _bound(zoo, static=False, relufication=True)
+        outs.append((m(x).cpu().numpy(), mf(x).cpu().numpy()))
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+
+
 def test_forward_host_matches_device_path(cuda_device, zoo, monkeypatch):
     import torch
 
