@@ -391,7 +391,7 @@ __global__ void __launch_bounds__(256) scan_i32_ring_kernel(ScanI32Params q, int
 constexpr int kWsMaxHalves = 8;
 
 template <bool INTERLEAVED>
-__global__ void __launch_bounds__(384) scan_i32_ws_kernel(ScanI32Params q, int S) {
+__global__ void __launch_bounds__(384) scan_i32_ws_kernel(ScanI32Params q, int S, int npost) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t full[kRingMaxStages];
   __shared__ __align__(8) uint64_t aligned[kRingMaxStages][kWsMaxHalves];
@@ -399,7 +399,7 @@ __global__ void __launch_bounds__(384) scan_i32_ws_kernel(ScanI32Params q, int S
   const int P = q.P, L = q.L;
   const int nh = P >> 5;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int role = warp / nh, h = warp % nh;   // 0 pre, 1 chain, 2 post
+  const int role = warp / nh, h = warp % nh;   // 0 pre, 1 chain, 2 .. 1 + npost post (post warp k owns the 8-row batches k, k + npost, ..)
   const int p = h * 32 + lane;
   const long long b = blockIdx.x;
   const size_t tile_elems = (size_t)kRingSteps * P;
@@ -444,16 +444,28 @@ __global__ void __launch_bounds__(384) scan_i32_ws_kernel(ScanI32Params q, int S
     int2* c2 = reinterpret_cast<int2*>(tre) + p;
     if (role == 0) {
       mbar_wait(&full[s], par);
-#pragma unroll 8
-      for (int t = 0; t < rows; ++t) {
-        if (INTERLEAVED) {
-          int2 v = c2[(size_t)t * P];
-          v.x = (int)((unsigned)v.x << sl_re) >> sr_re;
-          v.y = (int)((unsigned)v.y << sl_im) >> sr_im;
-          c2[(size_t)t * P] = v;
-        } else {
-          tre[(size_t)t * P + p] = (int)((unsigned)tre[(size_t)t * P + p] << sl_re) >> sr_re;
-          tim[(size_t)t * P + p] = (int)((unsigned)tim[(size_t)t * P + p] << sl_im) >> sr_im;
+      // eight rows are read before any is written back: one shared-memory round trip per batch, not per row
+      // (rows past the end of the clip are stale ring contents; shifting them is harmless and nobody reads them)
+#pragma unroll
+      for (int t0 = 0; t0 < kRingSteps; t0 += 8) {
+        if (t0 >= rows) break;
+        int a[8], c[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const size_t o = (size_t)(t0 + j) * P;
+          if (INTERLEAVED) { const int2 v = c2[o]; a[j] = v.x; c[j] = v.y; }
+          else { a[j] = tre[o + p]; c[j] = tim[o + p]; }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          a[j] = (int)((unsigned)a[j] << sl_re) >> sr_re;
+          c[j] = (int)((unsigned)c[j] << sl_im) >> sr_im;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const size_t o = (size_t)(t0 + j) * P;
+          if (INTERLEAVED) c2[o] = make_int2(a[j], c[j]);
+          else { tre[o + p] = a[j]; tim[o + p] = c[j]; }
         }
       }
       __syncwarp();
@@ -463,11 +475,10 @@ __global__ void __launch_bounds__(384) scan_i32_ws_kernel(ScanI32Params q, int S
       int vr[kRingSteps], vi[kRingSteps];
 #pragma unroll
       for (int t = 0; t < kRingSteps; ++t) {
-        vr[t] = 0; vi[t] = 0;
-        if (t < rows) {
-          if (INTERLEAVED) { const int2 v = c2[(size_t)t * P]; vr[t] = v.x; vi[t] = v.y; }
-          else { vr[t] = tre[(size_t)t * P + p]; vi[t] = tim[(size_t)t * P + p]; }
-        }
+        // unpredicated: rows past the end of the clip (last tile only) hold stale ring contents; the steps computed
+        // from them come after the clip's last state and are never stored to global memory
+        if (INTERLEAVED) { const int2 v = c2[(size_t)t * P]; vr[t] = v.x; vi[t] = v.y; }
+        else { vr[t] = tre[(size_t)t * P + p]; vi[t] = tim[(size_t)t * P + p]; }
       }
 #pragma unroll
       for (int t = 0; t < kRingSteps; ++t) {
@@ -478,34 +489,46 @@ __global__ void __launch_bounds__(384) scan_i32_ws_kernel(ScanI32Params q, int S
       }
 #pragma unroll
       for (int t = 0; t < kRingSteps; ++t) {
-        if (t < rows) {
-          if (INTERLEAVED) c2[(size_t)t * P] = make_int2(vr[t], vi[t]);
-          else { tre[(size_t)t * P + p] = vr[t]; tim[(size_t)t * P + p] = vi[t]; }
-        }
+        if (INTERLEAVED) c2[(size_t)t * P] = make_int2(vr[t], vi[t]);
+        else { tre[(size_t)t * P + p] = vr[t]; tim[(size_t)t * P + p] = vi[t]; }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&scanned[s][h]);
     } else {
       mbar_wait(&scanned[s][h], par);
       if (q.relu) {
-#pragma unroll 8
-        for (int t = 0; t < rows; ++t) {
-          int orr, oi;
-          if (INTERLEAVED) { const int2 v = c2[(size_t)t * P]; orr = v.x; oi = v.y; }
-          else { orr = tre[(size_t)t * P + p]; oi = tim[(size_t)t * P + p]; }
-          const bool small = ((unsigned)(orr + (1 << 24)) < (1u << 25)) && ((unsigned)(oi + (1 << 24)) < (1u << 25));
-          if (small) {
-            const bool keep = orr > 0 || (orr == 0 && oi > 0);
-            orr = keep ? orr : 0; oi = keep ? oi : 0;
-          } else {
-            fxp_relu_complex(orr, oi);
+        for (int t0 = 8 * (role - 2); t0 < rows; t0 += 8 * npost) {
+          int a[8], c[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const size_t o = (size_t)(t0 + j) * P;
+            if (INTERLEAVED) { const int2 v = c2[o]; a[j] = v.x; c[j] = v.y; }
+            else { a[j] = tre[o + p]; c[j] = tim[o + p]; }
           }
-          if (INTERLEAVED) c2[(size_t)t * P] = make_int2(orr, oi);
-          else { tre[(size_t)t * P + p] = orr; tim[(size_t)t * P + p] = oi; }
+          // Branch-free: the lexicographic test on the float32 images equals the test on the integers themselves (int ->
+          // float keeps sign and zero-ness); only the VALUES of kept entries with |v| >= 2^24 change in the float round
+          // trip, and a whole batch takes that exact path when any lane saw one (warp vote, practically never).
+          unsigned big = 0;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            big |= ((unsigned)(a[j] + (1 << 24)) | (unsigned)(c[j] + (1 << 24))) >> 25;
+            const bool keep = a[j] > 0 || (a[j] == 0 && c[j] > 0);
+            a[j] = keep ? a[j] : 0; c[j] = keep ? c[j] : 0;
+          }
+          if (__any_sync(0xffffffffu, big != 0)) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) fxp_relu_complex(a[j], c[j]);   // idempotent on the already ReLU-ed pair
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const size_t o = (size_t)(t0 + j) * P;
+            if (INTERLEAVED) c2[o] = make_int2(a[j], c[j]);
+            else { tre[o + p] = a[j]; tim[o + p] = c[j]; }
+          }
         }
       }
       fence_proxy_async_smem();
-      asm volatile("bar.sync 1, %0;" ::"r"(nh * 32) : "memory");   // all post warps of this tile
+      asm volatile("bar.sync 1, %0;" ::"r"(nh * 32 * npost) : "memory");   // all post warps of this tile
       if (leader) {
         const uint32_t bytes = (uint32_t)rows * P * 4u;
         const size_t off = clip_off + (size_t)i * tile_elems;
@@ -543,7 +566,10 @@ int launch_scan_i32(const ScanI32Params& q, bool interleaved, cudaStream_t st) {
     if (q.P % 32 == 0 && q.P / 32 <= kWsMaxHalves && 3 * q.P <= 384) {
       auto kernel = interleaved ? scan_i32_ws_kernel<true> : scan_i32_ws_kernel<false>;
       S5_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      kernel<<<(unsigned)B, 3 * q.P, smem, st>>>(q, stages);
+      // the post-processing (complex ReLU) is the slowest role with one warp per 32 states: up to four post warps
+      // share a tile's rows when the thread budget allows (P = 64: 2 + 4 roles x 64 threads)
+      const int npost = q.relu ? std::max(1, std::min(4, 384 / q.P - 2)) : 1;
+      kernel<<<(unsigned)B, (2 + npost) * q.P, smem, st>>>(q, stages, npost);
       S5_LAUNCH_CHECK();
       return S5_OK;
     }
