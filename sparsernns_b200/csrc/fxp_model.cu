@@ -90,6 +90,15 @@ __device__ __forceinline__ int bn_apply(int v, int k, const BnChain& c, const Bn
   return v;
 }
 
+// the same with the per-column parameters already in registers (kernels whose threads own fixed columns)
+__device__ __forceinline__ int bn_apply_v(int v, int mm, int inv, int sc, int bi, const BnChain& c, const BnPlan& pl, int upto) {
+  v = fx_add_cb_apply(v, c.x_bits, pl.e_in, mm, c.b_mean, c.e_mean, pl.p1, pl.rb1);
+  if (upto >= 2) v = fx_mul_apply(v, inv, pl.rs2 & 31, S5_ROUND_FLOOR, pl.rb2);
+  if (upto >= 3 && c.has_scale) v = fx_mul_apply(v, sc, pl.rs3 & 31, S5_ROUND_FLOOR, pl.rb3);
+  if (upto >= 4 && c.has_bias) v = fx_add_cb_apply(v, pl.rb3, pl.e3, bi, c.b_bias, c.e_bias, pl.p4, pl.rb4);
+  return v;
+}
+
 // ------------------------------------------------------------------------------------------- BN reduce
 // Applies stages 1..upto of the BatchNorm chain to x and accumulates the float maxima stage upto+1 needs.
 struct BnReduceParams {
@@ -116,19 +125,34 @@ __global__ void __launch_bounds__(256) fxp_bn_reduce_kernel(BnReduceParams p) {
   const int* pv = p.next == 2 ? p.c.inv : (p.next == 3 ? p.c.scale : p.c.bias);
   const float s_par = exp2f((float)-(p.next == 2 ? p.c.e_inv : (p.next == 3 ? p.c.e_scale : p.c.e_bias)));
   const bool is_mul = p.next != 4;
-  if ((p.H & 3) == 0) {
-    const long long n4 = p.n >> 2;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-      const int4 xv = reinterpret_cast<const int4*>(p.X)[i];
-      const int k = (int)((i << 2) % p.H);
-      const int xs4[4] = {xv.x, xv.y, xv.z, xv.w};
+  const int cgn = p.H >> 2;                                   // int4 column groups per row
+  if ((p.H & 3) == 0 && cgn <= 256) {
+    // Column-resident form: a thread owns four fixed columns and strides over rows, so the per-column parameters sit in
+    // registers (no modulo, no parameter loads in the loop); consecutive threads still read consecutive int4.
+    const int rpb = 256 / cgn;                                // rows per block and iteration
+    const int cg = threadIdx.x % cgn, rl = threadIdx.x / cgn;
+    if (rl < rpb) {
+      int mm[4], iv[4], sc[4], bi[4];
+      float g4[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const int v = bn_apply(xs4[e], k + e, p.c, pl, p.upto);
-        const float f = __int2float_rn(v) * s_prev;
-        const float g = __int2float_rn(pv[k + e]) * s_par;
-        m0 = fmaxf(m0, fabsf(is_mul ? f * g : f + g));
-        m1 = fmaxf(m1, fabsf(f));
+        const int k = 4 * cg + e;
+        mm[e] = p.c.mmean[k]; iv[e] = p.c.inv[k];
+        sc[e] = p.c.has_scale ? p.c.scale[k] : 0; bi[e] = p.c.has_bias ? p.c.bias[k] : 0;
+        g4[e] = __int2float_rn(pv[k]) * s_par;
+      }
+      const long long rows = p.n / p.H;
+      const int4* X4 = reinterpret_cast<const int4*>(p.X);
+      for (long long r = (long long)blockIdx.x * rpb + rl; r < rows; r += (long long)gridDim.x * rpb) {
+        const int4 xv = X4[r * cgn + cg];
+        const int xs4[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int v = bn_apply_v(xs4[e], mm[e], iv[e], sc[e], bi[e], p.c, pl, p.upto);
+          const float f = __int2float_rn(v) * s_prev;
+          m0 = fmaxf(m0, fabsf(is_mul ? f * g4[e] : f + g4[e]));
+          m1 = fmaxf(m1, fabsf(f));
+        }
       }
     }
   } else {
@@ -502,6 +526,39 @@ __global__ void __launch_bounds__(256) fxp_resid_kernel(FxpResidParams p) {
   const int e_in = e_in_s;
   const float so = exp2f((float)-pl.res_exp), sm = exp2f((float)-p.next_e_mean);
   float m0 = 0.f, m1 = 0.f;
+  const int cgn = p.H >> 2;
+  if ((p.H & 3) == 0 && cgn <= 256) {
+    // column-resident, 16-byte accesses (see fxp_bn_reduce_kernel)
+    const int rpb = 256 / cgn, cg = threadIdx.x % cgn, rl = threadIdx.x / cgn;
+    if (rl < rpb) {
+      float mmf[4] = {0.f, 0.f, 0.f, 0.f};
+      if (p.next_fm) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) mmf[e] = __int2float_rn(p.next_mmean[4 * cg + e]) * sm;
+      }
+      const long long rows = p.n / p.H;
+      const int4* G4 = reinterpret_cast<const int4*>(p.G);
+      const int4* X4 = reinterpret_cast<const int4*>(p.X);
+      int4* O4 = reinterpret_cast<int4*>(p.OUT);
+      for (long long r = (long long)blockIdx.x * rpb + rl; r < rows; r += (long long)gridDim.x * rpb) {
+        const int4 gv = G4[r * cgn + cg], xv = X4[r * cgn + cg];
+        const int g4[4] = {gv.x, gv.y, gv.z, gv.w}, x4[4] = {xv.x, xv.y, xv.z, xv.w};
+        int o4[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          int v = fx_add_cb_apply(g4[e], p.g_bits, p.g_exp, x4[e], p.x_bits, e_in, pl, p.res_bits);
+          v = v > 0 ? v : 0;
+          o4[e] = v;
+          if (p.next_fm) {
+            const float f = __int2float_rn(v) * so;
+            m0 = fmaxf(m0, fabsf(f + mmf[e]));
+            m1 = fmaxf(m1, fabsf(f));
+          }
+        }
+        O4[r * cgn + cg] = make_int4(o4[0], o4[1], o4[2], o4[3]);
+      }
+    }
+  } else
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += (long long)gridDim.x * blockDim.x) {
     int v = fx_add_cb_apply(p.G[i], p.g_bits, p.g_exp, p.X[i], p.x_bits, e_in, pl, p.res_bits);
     v = v > 0 ? v : 0;

@@ -47,6 +47,9 @@ __device__ __forceinline__ unsigned long long gtime() {
 #define TC_TRACE_PRINT(cond, name)
 #endif
 
+#ifndef S5_LOOKBACK_STRIDE
+#define S5_LOOKBACK_STRIDE 4   // every S5_LOOKBACK_STRIDE-th tile of a clip publishes its inclusive prefix (fused recurrence)
+#endif
 constexpr int kTcThreads = 256;
 constexpr int kTcRows = 128;
 constexpr int kTcKI = 8;  // K <= 256: each lane stages at most 8 input columns
@@ -1072,7 +1075,7 @@ __global__ void __launch_bounds__(kGluThreads, 1) tc_glu_kernel(const __grid_con
         // so the floating-point association is fixed: results do not depend on timing, batching or sharding (a classic
         // decoupled look-back takes whatever prefix happens to be published and is not bit-reproducible).  All flags
         // and records of the walk (<= kStride of each) are requested together: two round trips, not 2 per predecessor.
-        constexpr int kStride = 4;
+        constexpr int kStride = S5_LOOKBACK_STRIDE;
         const bool last = chunk + 1 >= p0.tiles_per_clip;      // nobody looks back at the last tile of a clip
         const bool anchor = (chunk % kStride) == 0;
         float2 carry = make_float2(0.f, 0.f);
