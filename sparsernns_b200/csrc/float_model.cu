@@ -328,6 +328,7 @@ struct LayerDev {
   SparseDev wb, wc, wo;
   TcLinearDev tb;  // dense-tile form of the B projection (static flavour)
   TcGluDev tg;     // dense-tile form of the C projection + GLU
+  TcF32Dev fb, fc, fo;   // float flavour: 3 x TF32 dense-tile forms of B_bar, C_tilde (real form) and the out2 kernel
   float *lam = nullptr, *D = nullptr, *bn_mean = nullptr, *bn_mul = nullptr, *bn_bias = nullptr, *o_bias = nullptr;
   s5_layer_desc sc;  // scales only (pointers unused)
 };
@@ -345,10 +346,12 @@ struct s5_model {
   s5_model_desc desc;
   s5::SparseDev enc, dec;
   s5::TcLinearDev enc_tc, dec_tc;
+  s5::TcF32Dev enc_f32, dec_f32;   // float flavour
   long long tc_min_rows = 512;   // below this the compressed CUDA-core kernels are used (one 3751-frame clip: 141 us dense-tile, 312 us CUDA-core)
   bool fuse_scan = true;         // static dense-tile path: run the recurrence inside the GLU kernel (S5B200_FUSE_SCAN=0 disables)
   bool fuse_bproj = true;        // ... and the B projection as well: one kernel per block (S5B200_FUSE_BPROJ=0 disables)
   bool fuse_layers = true;       // ... and all blocks in one launch (S5B200_FUSE_LAYERS=0 disables)
+  int f32_tc = 3;                // float flavour on 3 x TF32 dense tiles: bit 0 encoder / decoder, bit 1 the blocks (S5B200_F32_TC)
   bool skip_zero = false;        // CUDA-core kernels skip all-zero (input column, 32-row group) pairs of ReLU-ified inputs (S5B200_SKIP_ZERO=1
                                  // enables; exact, but measured slower on B200 - the kernels are issue bound, not multiply bound)
   float *enc_bias = nullptr, *dec_bias = nullptr;
@@ -472,6 +475,23 @@ static int run_block(const s5_model* m, int li, const float* x, float* out, floa
   const long long rows = (long long)B * L;
   int rc;
   const bool sq = m->desc.flavour == S5_STATIC;
+  if (!sq && !ssm_only && (m->f32_tc & 2) && rows >= m->tc_min_rows && ld.fb.ok && ld.fc.ok && ld.fo.ok) {
+    // float flavour, throughput batch: B projection | scan | C projection + SSM tail | out2 + gate, the three products
+    // as 3 x TF32 dense tiles (tc_f32.cu); the gate kernel reads x1 and writes the block output in place
+    TcF32Args a;
+    a.X = x; a.Y = bu; a.rows = rows;
+    if (bn) { a.in_sub = ld.bn_mean; a.in_mul = ld.bn_mul; a.in_add = ld.bn_bias; }
+    if ((rc = tc_f32_launch(ld.fb, a, S5_K_BPROJ, st))) return rc;
+    if ((rc = launch_scan_c64(bu, ld.lam, bu, B, L, m->desc.P, m->desc.relufication, scan_ws, scan_ws_bytes, st))) return rc;
+    TcF32Args c;
+    c.X = bu; c.Y = out; c.rows = rows; c.epi = 1; c.X2 = x; c.D = ld.D;
+    if (bn) { c.bn_sub = ld.bn_mean; c.bn_mul = ld.bn_mul; c.bn_add = ld.bn_bias; }
+    c.conj_mul = m->desc.conj_sym ? 2.f : 1.f; c.act = m->desc.activation;
+    if ((rc = tc_f32_launch(ld.fc, c, S5_K_GLU, st))) return rc;
+    TcF32Args o;
+    o.X = out; o.Y = out; o.rows = rows; o.epi = 2; o.bias = ld.o_bias; o.X1 = out; o.SKIP = x; o.relu = m->desc.relufication;
+    return tc_f32_launch(ld.fo, o, S5_K_GLU, st);
+  }
   const BlockPlan bp = block_plan(m, ld, rows, ssm_only, want_xs);
   if (bp.fuse_bproj) {
     // nothing to launch here
@@ -507,14 +527,16 @@ static LinearParams dense_params(const s5_model* m, const SparseDev& w, const fl
 extern "C" int s5b200_sparse_create(const void* W_host, int K, int N, int dtype, int dense_format, s5_sparse** out) {
   if (!out) S5_FAIL(S5_E_BADARG, "sparse_create: null out");
   s5_sparse* h = new s5_sparse();
-  const int rc = s5::sparse_build(W_host, K, N, dtype, dense_format, &h->d);
-  if (rc) { s5::sparse_free(&h->d); delete h; return rc; }
+  int rc = s5::sparse_build(W_host, K, N, dtype, dense_format, &h->d);
+  if (!rc && dtype == S5_F32) rc = s5::tc_f32_build(reinterpret_cast<const float*>(W_host), K, N, &h->tc);
+  if (rc) { s5::sparse_free(&h->d); s5::tc_f32_free(&h->tc); delete h; return rc; }
   *out = h;
   return S5_OK;
 }
 extern "C" int s5b200_sparse_destroy(s5_sparse* w) {
   if (!w) return S5_OK;
   s5::sparse_free(&w->d);
+  s5::tc_f32_free(&w->tc);
   delete w;
   return S5_OK;
 }
@@ -529,6 +551,14 @@ extern "C" int s5b200_spmm_f32(const s5_sparse* w, const float* X, const float* 
                                int skip_zero_cols, void* stream) {
   if (!w || !X || !Y) S5_FAIL(S5_E_BADARG, "spmm_f32: null pointer");
   if (w->d.dtype != S5_F32) S5_FAIL(S5_E_BADARG, "spmm_f32: handle holds int32 weights");
+  // throughput batches: the projection is a genuine dense contraction -> 3 x TF32 dense tiles on the tensor cores
+  // (S5B200_TC_MIN_ROWS, default 512); below that, and when zero skipping is asked for, the compressed CUDA-core kernel
+  static const long long tc_min = [] { const char* e = getenv("S5B200_TC_MIN_ROWS"); return e ? atoll(e) : 512LL; }();
+  if (w->tc.ok && rows >= tc_min && !skip_zero_cols) {
+    s5::TcF32Args a;
+    a.X = X; a.Y = Y; a.rows = rows; a.bias = bias;
+    return s5::tc_f32_launch(w->tc, a, S5_K_OTHER, (cudaStream_t)stream);
+  }
   s5::LinearParams p{};
   p.X = X; p.Y = Y; p.rows = rows; p.w = s5::wview(w->d); p.bias = bias; p.skip_zero = skip_zero_cols != 0;
   return s5::launch_linear(p, (cudaStream_t)stream);
@@ -554,6 +584,7 @@ extern "C" int s5b200_model_create(const s5_model_desc* d, s5_model** out) {
   if (const char* e = getenv("S5B200_FUSE_BPROJ")) m->fuse_bproj = atoi(e) != 0;
   if (const char* e = getenv("S5B200_FUSE_LAYERS")) m->fuse_layers = atoi(e) != 0;
   if (const char* e = getenv("S5B200_SKIP_ZERO")) m->skip_zero = atoi(e) != 0;
+  if (const char* e = getenv("S5B200_F32_TC")) m->f32_tc = atoi(e);
   const int H = d->H, P = d->P, dense = d->use_sparse ? 0 : 1;
   int rc = S5_OK;
   auto fail = [&](int code) { s5b200_model_destroy(m); return code; };
@@ -564,6 +595,9 @@ extern "C" int s5b200_model_create(const s5_model_desc* d, s5_model** out) {
   if (d->flavour == S5_STATIC) {
     if ((rc = tc_linear_build(d->enc_kernel_host, d->d_input, H, d->s_enc_act, &m->enc_tc))) return fail(rc);
     if ((rc = tc_linear_build(d->dec_kernel_host, H, d->d_output, d->s_dec_act, &m->dec_tc))) return fail(rc);
+  } else {
+    if ((rc = tc_f32_build(d->enc_kernel_host, d->d_input, H, &m->enc_f32))) return fail(rc);
+    if ((rc = tc_f32_build(d->dec_kernel_host, H, d->d_output, &m->dec_f32))) return fail(rc);
   }
   m->layers.resize(d->n_layers);
   for (int i = 0; i < d->n_layers; ++i) {
@@ -587,6 +621,11 @@ extern "C" int s5b200_model_create(const s5_model_desc* d, s5_model** out) {
       return fail(rc);
     if ((rc = sparse_build(wc.data(), 2 * P, H, S5_F32, dense, &ld.wc))) return fail(rc);
     if ((rc = sparse_build(l.out2_kernel_host, H, H, S5_F32, dense, &ld.wo))) return fail(rc);
+    if (d->flavour == S5_FLOAT) {
+      if ((rc = tc_f32_build(wb.data(), H, 2 * P, &ld.fb))) return fail(rc);
+      if ((rc = tc_f32_build(wc.data(), 2 * P, H, &ld.fc))) return fail(rc);
+      if (l.out2_kernel_host && (rc = tc_f32_build(l.out2_kernel_host, H, H, &ld.fo))) return fail(rc);
+    }
     if ((rc = upload(l.lambda_bar_host, 2 * P, &ld.lam))) return fail(rc);
     if ((rc = upload(l.D_host, H, &ld.D))) return fail(rc);
     if ((rc = upload(l.bn_mean_host, H, &ld.bn_mean))) return fail(rc);
@@ -602,11 +641,13 @@ extern "C" int s5b200_model_destroy(s5_model* m) {
   if (!m) return S5_OK;
   s5::sparse_free(&m->enc); s5::sparse_free(&m->dec);
   s5::tc_linear_free(&m->enc_tc); s5::tc_linear_free(&m->dec_tc);
+  s5::tc_f32_free(&m->enc_f32); s5::tc_f32_free(&m->dec_f32);
   cudaFree(m->enc_bias); cudaFree(m->dec_bias);
   for (auto& l : m->layers) {
     s5::sparse_free(&l.wb); s5::sparse_free(&l.wc); s5::sparse_free(&l.wo);
     s5::tc_linear_free(&l.tb);
     s5::tc_glu_free(&l.tg);
+    s5::tc_f32_free(&l.fb); s5::tc_f32_free(&l.fc); s5::tc_f32_free(&l.fo);
     cudaFree(l.lam); cudaFree(l.D); cudaFree(l.bn_mean); cudaFree(l.bn_mul); cudaFree(l.bn_bias); cudaFree(l.o_bias);
   }
   for (int i = 0; i < s5_model::kSlots; ++i) {
@@ -647,6 +688,10 @@ extern "C" int s5b200_model_forward(const s5_model* m, const float* x, float* y,
   if (tc && m->enc_tc.ok && is_pow2(d.s_enc_act) && is_pow2(d.s_enc_out)) {
     if ((rc = tc_linear_launch(m->enc_tc, x, a, rows, nullptr, nullptr, nullptr, d.s_enc_act, nlo, nhi, m->enc_bias, d.s_enc_out,
                                d.s_enc_out, nlo, nhi, d.relufication, S5_K_ENC, st))) return rc;
+  } else if (d.flavour == S5_FLOAT && (m->f32_tc & 1) && rows >= m->tc_min_rows && m->enc_f32.ok) {
+    TcF32Args e;
+    e.X = x; e.Y = a; e.rows = rows; e.bias = m->enc_bias; e.relu = d.relufication;
+    if ((rc = tc_f32_launch(m->enc_f32, e, S5_K_ENC, st))) return rc;
   } else if ((rc = launch_linear(dense_params(m, m->enc, m->enc_bias, x, a, rows, d.s_enc_act, d.s_enc_out, d.relufication), st, S5_K_ENC))) return rc;
   // all blocks in ONE launch when every layer runs the block kernel (S5B200_FUSE_LAYERS=0: one launch per block)
   bool one_launch = m->fuse_layers && d.n_layers >= 2 && d.n_layers <= 4;
@@ -674,6 +719,11 @@ extern "C" int s5b200_model_forward(const s5_model* m, const float* x, float* y,
   if (tc && m->dec_tc.ok && is_pow2(d.s_dec_act) && is_pow2(d.s_dec_out))
     return tc_linear_launch(m->dec_tc, a, y, rows, nullptr, nullptr, nullptr, d.s_dec_act, nlo, nhi, m->dec_bias, d.s_dec_out,
                             d.s_dec_out, nlo, nhi, 0, S5_K_DEC, st);
+  if (d.flavour == S5_FLOAT && (m->f32_tc & 1) && rows >= m->tc_min_rows && m->dec_f32.ok) {
+    TcF32Args e;
+    e.X = a; e.Y = y; e.rows = rows; e.bias = m->dec_bias;
+    return tc_f32_launch(m->dec_f32, e, S5_K_DEC, st);
+  }
   return launch_linear(dense_params(m, m->dec, m->dec_bias, a, y, rows, d.s_dec_act, d.s_dec_out, 0), st, S5_K_DEC);
 }
 

@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "tc_f32.cuh"
 
 namespace s5 {
 
@@ -37,6 +38,7 @@ struct SparseDev {
 // public opaque handle of s5b200_sparse_create
 struct s5_sparse {
   s5::SparseDev d;
+  s5::TcF32Dev tc;   // float weights: 3 x TF32 dense-tile form for throughput batches (tc_f32.cu)
 };
 
 namespace s5 {

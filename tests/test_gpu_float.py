@@ -33,9 +33,12 @@ def _bound(zoo, *, static, relufication, use_sparse=True, variables=None):
     return BoundModel(cfg, variables), variables
 
 
+@pytest.mark.parametrize("tc_min_rows", ["1", "1000000000"], ids=["dense_tile_3xtf32", "cuda_cores"])
 @pytest.mark.parametrize("relufication,use_sparse", [(False, False), (False, True), (True, True)])
-def test_float_model_matches_oracle(cuda_device, zoo, relufication, use_sparse):
+def test_float_model_matches_oracle(cuda_device, zoo, relufication, use_sparse, tc_min_rows, monkeypatch):
     import torch
+
+    monkeypatch.setenv("S5B200_TC_MIN_ROWS", tc_min_rows)
 
     m, var = _bound(zoo, static=False, relufication=relufication, use_sparse=use_sparse)
     x = torch.from_numpy(zoo["x"]).to(cuda_device)
@@ -172,6 +175,36 @@ def test_spmm_f32_ragged_rows(cuda_device):
                                        C.c_void_p(torch.cuda.current_stream().cuda_stream)))
         ref = X.astype(np.float64) @ W.astype(np.float64) + bias
         assert relerr(dY.cpu().numpy(), ref) <= TOL_F32
+        lib.s5b200_sparse_destroy(h)
+
+
+def test_spmm_f32_dense_tile_3xtf32(cuda_device):
+    """Throughput batches of s5b200_spmm_f32 run as 3 x TF32 dense tiles (tc_f32.cu): fp32-level accuracy, odd shapes
+    (257-wide rows either side, ragged last tile, more than one M block), bias."""
+    import ctypes as C
+    import torch
+    from sparsernns_b200 import _abi
+
+    lib = _abi.lib()
+    rng = np.random.default_rng(12)
+    for (rows, K, N, dens) in [(1000, 257, 96, 0.1), (700, 96, 257, 0.1), (513, 96, 128, 1.0), (2051, 128, 96, 0.2), (640, 200, 300, 0.5), (4096, 192, 256, 0.1)]:
+        W = (rng.standard_normal((K, N)) * (rng.uniform(size=(K, N)) < dens)).astype(np.float32)
+        X = (rng.standard_normal((rows, K)) * np.exp(rng.uniform(-6, 6, (rows, 1)))).astype(np.float32)   # wide dynamic range
+        bias = rng.standard_normal(N).astype(np.float32)
+        h = C.c_void_p()
+        _abi.check(lib.s5b200_sparse_create(W.ctypes.data, K, N, _abi.F32, 0, C.byref(h)))
+        dX, db = torch.from_numpy(X).to(cuda_device), torch.from_numpy(bias).to(cuda_device)
+        dY = torch.empty(rows, N, device=cuda_device)
+        _abi.check(lib.s5b200_spmm_f32(h, dX.data_ptr(), db.data_ptr(), dY.data_ptr(), rows, 0,
+                                       C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        got = dY.cpu().numpy()
+        ref = X.astype(np.float64) @ W.astype(np.float64) + bias
+        # per row: error relative to the row's own scale (each row has its own dynamic range)
+        err = np.abs(got - ref).max(1) / np.maximum(np.abs(ref).max(1), 1e-30)
+        ref32 = (X @ W + bias).astype(np.float64)
+        err32 = np.abs(ref32 - ref).max(1) / np.maximum(np.abs(ref).max(1), 1e-30)
+        print(f"spmm 3xTF32 rows={rows} K={K} N={N}: max row-rel err {err.max():.2e} (numpy fp32: {err32.max():.2e})")
+        assert err.max() <= TOL_F32
         lib.s5b200_sparse_destroy(h)
 
 
