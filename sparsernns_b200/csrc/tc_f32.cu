@@ -29,7 +29,8 @@ namespace s5 {
 constexpr int kF32Threads = 256;
 constexpr int kF32Rows = 128;
 constexpr int kF32KC = 16;                                    // fp32 columns per K chunk
-constexpr uint32_t kF32Lbo = kF32Rows * 16 + 16;              // padded K-chunk stride of a [128][.] operand tile
+constexpr uint32_t kF32Lbo = kF32Rows * 16 + 32;              // padded K-chunk stride of a [128][.] operand tile: with 32 bytes
+                                                              // both staging patterns below are bank-conflict free
 constexpr uint32_t kF32Plane = (kF32KC / 4) * kF32Lbo;        // bytes of one [128][16] fp32 plane
 
 enum { EPI_BIAS = 0, EPI_SSM = 1, EPI_GATE = 2 };
@@ -63,84 +64,131 @@ __device__ __forceinline__ float f32_gelu_tanh(float x) {     // jax.nn.gelu(app
   return x * (0.5f * (1.0f + tanhf(c * (x + 0.044715f * (x * x * x)))));
 }
 
+// VEC4: input rows are 16-byte aligned and K % 4 == 0 - a lane stages four consecutive columns (one 16-byte load, one
+// 16-byte store per plane) instead of one.
+template <bool VEC4>
 __global__ void __launch_bounds__(kF32Threads, 2) tc_f32_kernel(const __grid_constant__ TcF32Params p) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int MB = p.MB, NC = p.NC;
-  const uint32_t wbytes = (uint32_t)MB * 2u * kF32Plane;      // W part of a buffer
-  const uint32_t buf_bytes = wbytes + 2u * kF32Plane;         // + hi / lo planes of the X chunk
-  __shared__ __align__(8) uint64_t full[2], mdone[2], tdone;
+  const uint32_t wbytes = (uint32_t)MB * 2u * kF32Plane;      // one chunk of W (all M blocks, hi + lo)
+  const uint32_t xbytes = 2u * kF32Plane;                     // hi / lo planes of one X chunk
+  unsigned char* Wring = smem;                                // three W slots: chunk g + 1 is requested while chunk g is staged
+  unsigned char* Xbuf = smem + 3u * wbytes;                   // two X buffers
+  __shared__ __align__(8) uint64_t full[3], mdone[2], tdone;
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // The tensor core truncates when it adds a product group to the running fp32 sum (a bias that grows with the number of
-  // accumulation steps), so with one M block the K chunks alternate between TWO accumulators that are added in fp32
-  // (round to nearest) in the epilogue: half the steps per accumulator, still 256 TMEM columns = two CTAs per SM.
+  // accumulation steps), so with one M block there are TWO accumulators, one for the large hi x hi products and one for
+  // the small cross terms, added in fp32 (round to nearest) in the epilogue: a third of the steps on the accumulator
+  // that matters, still 256 TMEM columns = two CTAs per SM.
   const int NACC = MB == 1 ? 2 : 1;
   const uint32_t tmem_cols = MB <= 2 ? 256u : 512u;
   if (warp == 0) tc_alloc(&tmem_slot, tmem_cols);
   if (tid == 0) {
-    mbar_init(&full[0], 1); mbar_init(&full[1], 1); mbar_init(&mdone[0], 1); mbar_init(&mdone[1], 1); mbar_init(&tdone, 1);
+    mbar_init(&full[0], 1); mbar_init(&full[1], 1); mbar_init(&full[2], 1); mbar_init(&mdone[0], 1); mbar_init(&mdone[1], 1); mbar_init(&tdone, 1);
     fence_mbar_init();
   }
   __syncthreads();
   const uint32_t taddr = tmem_slot;
   const long long row_begin = p.rows * blockIdx.x / gridDim.x, row_end = p.rows * (blockIdx.x + 1) / gridDim.x;
   const long long last_row = p.rows - 1;
-  // staging: half a warp per row (16 columns of the chunk), 8 warps x 2 rows per pass, 8 passes per tile
-  // the two half-warps of a store take rows 4 apart: their bank sets (4 words per row) do not overlap
-  const int srow = (warp & 3) + 4 * (lane >> 4) + 8 * (warp >> 2), l16 = lane & 15;
+  // staging, scalar form: half a warp per row (16 columns of the chunk), 8 warps x 2 rows per pass, 8 passes per tile
+  // VEC4 form: four lanes per row, 8 rows per warp, 64 rows per pass, 2 passes per tile
+  const int srow = VEC4 ? (tid >> 2) : 2 * warp + (lane >> 4), l16 = VEC4 ? 4 * (lane & 3) : (lane & 15);
   const uint32_t soff = (uint32_t)(l16 >> 2) * kF32Lbo + 4u * (l16 & 3);
+  constexpr int NV = VEC4 ? 2 : 8;                            // loads per lane and chunk
+  constexpr int RSTEP = VEC4 ? 64 : 16;
   const uint32_t idesc = tc_idesc_tf32(kF32Rows, kF32Rows);
   const int q4 = warp & 3, grp = warp >> 2;                   // epilogue: TMEM lane quadrant, item group
   long long g = 0;                                            // running chunk counter (buffers alternate across tiles)
+  const long long total_chunks = (row_end - row_begin + kF32Rows - 1) / kF32Rows * NC;
   uint32_t tile_par = 0;
+  float4 v[NV];                                               // the NEXT chunk's raw values travel while the current one is multiplied (scalar form: .x only)
+  auto load_chunk = [&](long long r0, int c) {
+    const int kc = min(c * kF32KC + l16, p.K - (VEC4 ? 4 : 1));   // pad columns meet zero weights
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+      const float* src = p.X + (size_t)min(r0 + RSTEP * q + srow, last_row) * p.x_stride + kc;
+      if constexpr (VEC4) v[q] = *reinterpret_cast<const float4*>(src);
+      else v[q].x = *src;
+    }
+  };
+  if (row_begin < row_end) load_chunk(row_begin, 0);
   for (long long row0 = row_begin; row0 < row_end; row0 += kF32Rows) {
     const int rv = (int)min((long long)kF32Rows, row_end - row0);
     for (int c = 0; c < NC; ++c, ++g) {
       const int b = (int)(g & 1);
-      unsigned char* buf = smem + (size_t)b * buf_bytes;
-      if (g >= 2) mbar_wait(&mdone[b], (uint32_t)((g - 2) >> 1) & 1u);   // the MMAs of chunk g - 2 have read this buffer
+      if (g >= 2) mbar_wait(&mdone[b], (uint32_t)((g - 2) >> 1) & 1u);   // the MMAs of chunk g - 2 are done: X buffer b and W slot (g + 1) % 3 are free
       if (tid == 0) {
-        fence_proxy_async_smem();
-        mbar_expect_tx(&full[b], wbytes);
-        bulk_g2s(buf, p.Wg + (size_t)c * wbytes, wbytes, &full[b]);
+        auto request = [&](long long gg) {                    // W chunk of running chunk gg -> slot gg % 3
+          const int s3 = (int)(gg % 3);
+          mbar_expect_tx(&full[s3], wbytes);
+          bulk_g2s(Wring + (size_t)s3 * wbytes, p.Wg + (size_t)(gg % NC) * wbytes, wbytes, &full[s3]);
+        };
+        if (g == 0) request(0);
+        if (g + 1 < total_chunks) request(g + 1);
       }
       const int k = c * kF32KC + l16;
-      const int kc = min(k, p.K - 1);                         // pad columns meet zero weights
-      const float bsub = (p.in_sub && k < p.K) ? p.in_sub[kc] : 0.f;
-      const float bmul = (p.in_sub && k < p.K) ? p.in_mul[kc] : 1.f;
-      const float badd = (p.in_sub && k < p.K) ? p.in_add[kc] : 0.f;
-      float v[8];
+      unsigned char* xh = Xbuf + (size_t)b * xbytes;
+      if constexpr (VEC4) {
+        float bsub[4], bmul[4], badd[4];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) v[q] = p.X[(size_t)min(row0 + 16 * q + srow, last_row) * p.x_stride + kc];
-      unsigned char* xh = buf + wbytes;
+        for (int e = 0; e < 4; ++e) {
+          const bool in = p.in_sub && k + e < p.K;
+          const int ke = min(k + e, p.K - 1);
+          bsub[e] = in ? p.in_sub[ke] : 0.f; bmul[e] = in ? p.in_mul[ke] : 1.f; badd[e] = in ? p.in_add[ke] : 0.f;
+        }
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        float x = v[q];
-        if (p.in_sub) x = (x - bsub) * bmul + badd;
-        const float hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);   // nearest tf32: |lo| <= 2^-12 |x|
-        const uint32_t o = soff + (uint32_t)(16 * q + srow) * 16u;
-        *reinterpret_cast<float*>(xh + o) = hi;
-        *reinterpret_cast<float*>(xh + kF32Plane + o) = x - hi;
+        for (int q = 0; q < NV; ++q) {
+          float x[4] = {v[q].x, v[q].y, v[q].z, v[q].w}, hi[4], lo[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            if (p.in_sub) x[e] = (x[e] - bsub[e]) * bmul[e] + badd[e];
+            hi[e] = __uint_as_float((__float_as_uint(x[e]) + 0x1000u) & 0xFFFFE000u);   // nearest tf32: |lo| <= 2^-12 |x|
+            lo[e] = x[e] - hi[e];
+          }
+          const uint32_t o = soff + (uint32_t)(RSTEP * q + srow) * 16u;
+          *reinterpret_cast<float4*>(xh + o) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<float4*>(xh + kF32Plane + o) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+        }
+      } else {
+        const int kc = min(k, p.K - 1);
+        const float bsub = (p.in_sub && k < p.K) ? p.in_sub[kc] : 0.f;
+        const float bmul = (p.in_sub && k < p.K) ? p.in_mul[kc] : 1.f;
+        const float badd = (p.in_sub && k < p.K) ? p.in_add[kc] : 0.f;
+#pragma unroll
+        for (int q = 0; q < NV; ++q) {
+          float x = v[q].x;
+          if (p.in_sub) x = (x - bsub) * bmul + badd;
+          const float hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);   // nearest tf32: |lo| <= 2^-12 |x|
+          const uint32_t o = soff + (uint32_t)(RSTEP * q + srow) * 16u;
+          *reinterpret_cast<float*>(xh + o) = hi;
+          *reinterpret_cast<float*>(xh + kF32Plane + o) = x - hi;
+        }
       }
+      if (c + 1 < NC) load_chunk(row0, c + 1);
+      else if (row0 + kF32Rows < row_end) load_chunk(row0 + kF32Rows, 0);
       fence_proxy_async_smem();
       tc_fence_before();
       __syncthreads();
       tc_fence_after();
       if (tid == 0) {
-        mbar_wait(&full[b], (uint32_t)(g >> 1) & 1u);         // this chunk of W has landed
-        const uint32_t x0 = smem_u32(xh), w0 = smem_u32(buf);
+        mbar_wait(&full[g % 3], (uint32_t)(g / 3) & 1u);      // this chunk of W has landed (requested one iteration ago)
+        const uint32_t x0 = smem_u32(xh), w0 = smem_u32(Wring + (size_t)(g % 3) * wbytes);
         for (int mb = 0; mb < MB; ++mb) {
-          const uint32_t d = taddr + 128u * mb + (NACC == 2 ? 128u * (uint32_t)(c & 1) : 0u);
-          const bool first = NACC == 2 ? c < 2 : c == 0;
+          // one M block: the large products (hi x hi) go to accumulator 0, the two small cross terms to accumulator 1, issued
+          // alternately so that back-to-back MMAs never target the same TMEM columns
+          const uint32_t d0 = taddr + 128u * mb, d1 = NACC == 2 ? d0 + 128u : d0;
           const uint32_t wh = w0 + (uint32_t)(2 * mb) * kF32Plane, wl = wh + kF32Plane;
 #pragma unroll
           for (int j = 0; j < kF32KC / 8; ++j) {
             const uint32_t ko = (uint32_t)j * 2u * kF32Lbo;
             const uint64_t dwh = tc_smem_desc(wh + ko, kF32Lbo, 128), dwl = tc_smem_desc(wl + ko, kF32Lbo, 128);
             const uint64_t dxh = tc_smem_desc(x0 + ko, kF32Lbo, 128), dxl = tc_smem_desc(x0 + kF32Plane + ko, kF32Lbo, 128);
-            tc_mma_tf32(d, dwl, dxh, idesc, !first || j > 0);  // small terms first
-            tc_mma_tf32(d, dwh, dxl, idesc, true);
-            tc_mma_tf32(d, dwh, dxh, idesc, true);
+            const bool first = c == 0 && j == 0;
+            tc_mma_tf32(d1, dwl, dxh, idesc, !first);          // small terms first (NACC == 1: same accumulator)
+            tc_mma_tf32(d0, dwh, dxh, idesc, NACC == 2 ? !first : true);
+            tc_mma_tf32(d1, dwh, dxl, idesc, true);
           }
         }
         tc_commit(&mdone[b]);
@@ -158,7 +206,7 @@ __global__ void __launch_bounds__(kF32Threads, 2) tc_f32_kernel(const __grid_con
       uint32_t acc[32];
       tc_ld32(taddr + ((uint32_t)(32 * q4) << 16) + (uint32_t)(128 * mb + 32 * rc), acc);
       tc_wait_ld();
-      if (NACC == 2 && NC > 1) {                              // second accumulator (odd chunks)
+      if (NACC == 2) {                                        // second accumulator (the small cross terms)
         uint32_t acc2[32];
         tc_ld32(taddr + ((uint32_t)(32 * q4) << 16) + (uint32_t)(128 + 32 * rc), acc2);
         tc_wait_ld();
@@ -269,13 +317,15 @@ int tc_f32_launch(const TcF32Dev& d, const TcF32Args& a, int kclass, cudaStream_
   p.X1 = a.X1; p.SKIP = a.SKIP;
   if (a.epi == EPI_SSM && (!a.X2 || !a.D)) S5_FAIL(S5_E_BADARG, "dense-tile f32 linear: SSM epilogue needs x and D");
   if (a.epi == EPI_GATE && (!a.X1 || !a.SKIP || !a.bias)) S5_FAIL(S5_E_BADARG, "dense-tile f32 linear: gate epilogue needs x1, skip and bias");
-  const size_t smem = 2 * ((size_t)d.MB * 2 * kF32Plane + 2 * kF32Plane);
-  S5_CUDA(cudaFuncSetAttribute(tc_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  S5_CUDA(cudaFuncSetAttribute(tc_f32_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  const size_t smem = 3 * ((size_t)d.MB * 2 * kF32Plane) + 2 * (2 * (size_t)kF32Plane);   // W ring + X double buffer
+  const bool vec4 = (d.K & 3) == 0 && aligned16(a.X);
+  auto kernel = vec4 ? tc_f32_kernel<true> : tc_f32_kernel<false>;
+  S5_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  S5_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   const int per_sm = (d.MB <= 2 && 2 * (smem + 2048) <= 227 * 1024) ? 2 : 1;
   const int grid = (int)std::max<long long>(1, std::min<long long>((a.rows + 63) / 64, (long long)per_sm * sm_count()));
   ProfScope prof(kclass, st);
-  tc_f32_kernel<<<grid, kF32Threads, smem, st>>>(p);
+  kernel<<<grid, kF32Threads, smem, st>>>(p);
   S5_LAUNCH_CHECK();
   return S5_OK;
 }
