@@ -100,10 +100,18 @@ class FxpRegressionModel:
         d.bias_host = _ip(self._k(from_fp_round(md["bias"], q["b_bits"], q["b_exp"])))
         d.w_exp, d.b_exp, d.b_bits = q["w_exp"], q["b_exp"], q["b_bits"]
         d.inp_bits, d.inp_exp, d.out_bits, d.out_exp = q["inp_bits"], q["inp_exp"], q["out_bits"], q["out_exp"]
+        # FxpDense.export (fxpmodel.py:368-393)
+        return dict(
+            params=dict(weight=self._keep[-2].copy(), bias=self._keep[-1].copy()),
+            qconfig=dict(weight_exp=q["w_exp"], weight_bits=q["w_bits"], weight_signed=True, bias_exp=q["b_exp"],
+                         bias_bits=q["b_bits"], bias_signed=True, inp_bits=q["inp_bits"], inp_exp=q["inp_exp"],
+                         out_bits=q["out_bits"], out_exp=q["out_exp"]))
 
     def _describe(self, md: dict, use_sparse: bool) -> _abi.FxpModelDesc:
         q = self.q
         layers = (_abi.FxpLayerDesc * self.n_layers)()
+        exp_params = {"encoder": {}, "decoder": None}
+        exp_qcfg = {"encoder": {}, "decoder": None}
         for i in range(self.n_layers):
             lq = q["blocks"]
             if any(k.startswith("layers_") for k in lq):  # per-layer exponents (fxpmodel.py:988-993)
@@ -139,7 +147,32 @@ class FxpRegressionModel:
             d.Bu_im_bits, d.Bu_im_exp = a["Bu_im"]["bits"], a["Bu_im"]["exp"]
             d.x_re_exp, d.x_im_exp = a["x_re"]["exp"], a["x_im"]["exp"]
             d.y_bits, d.y_exp = a["y"]["bits"], a["y"]["exp"]
-            self._dense(lm["out2"], lq["out2"], d.out2)
+            # FxpSSM.export (fxpmodel.py:819-847) / FxpBatchNorm.export (:946-967): integer payloads and their formats
+            g = lambda ptr_arr: ptr_arr.copy()
+            names = ("A_real", "A_imag", "B_real", "B_imag", "C_real", "C_imag", "D")
+            keys = ("A_re", "A_im", "B_re", "B_im", "C_re", "C_im", "D")
+            vals = (Lb.real, Lb.imag, Bb.real, Bb.imag, Ct.real, Ct.imag, D)
+            mp, mq = {}, {}
+            for nme, k, v in zip(names, keys, vals):
+                mp[nme] = from_fp_round(v, w[k]["bits"], w[k]["exp"])
+                mq[f"{nme}_bits"], mq[f"{nme}_exp"], mq[f"{nme}_signed"] = w[k]["bits"], w[k]["exp"], True
+            for k in ("u", "Bu_re", "Bu_im", "x_re", "x_im", "y"):
+                mq[f"{k}_bits"], mq[f"{k}_exp"] = a[k]["bits"], a[k]["exp"]
+            np_, nq_ = dict(mean=-from_fp_round(F32(-1) * np.asarray(nm["mean"], F32), nq["mean"]["bits"], nq["mean"]["exp"]),
+                            invsq_var=from_fp_round(invsq, nq["invsq_var"]["bits"], nq["invsq_var"]["exp"])), \
+                dict(mean_bits=nq["mean"]["bits"], mean_exp=nq["mean"]["exp"], invsq_var_bits=nq["invsq_var"]["bits"],
+                     invsq_var_exp=nq["invsq_var"]["exp"])
+            for k in ("bias", "scale"):
+                if k in nm:
+                    np_[k] = from_fp_round(nm[k], nq[k]["bits"], nq[k]["exp"])
+                    nq_[f"{k}_bits"], nq_[f"{k}_exp"] = nq[k]["bits"], nq[k]["exp"]
+            o2 = self._dense(lm["out2"], lq["out2"], d.out2)
+            mgq = lq["multgate"]
+            exp_params["encoder"][f"layers_{i}"] = dict(mixer=mp, out2=o2["params"], norm=np_)
+            exp_qcfg["encoder"][f"layers_{i}"] = dict(
+                mixer=mq, out2=o2["qconfig"], norm=nq_,
+                multgate={k: mgq[k] for k in ("l_bits", "l_exp", "r_bits", "r_exp", "res_bits", "res_exp")},
+                sigmoid=dict(x_exp=min(lq["out2"]["out_exp"], 6), y_exp=lq["out2"]["out_bits"] - 2, x_extra=3, n_exp=3))
             # sigmoid + mult_gate (fxpmodel.py:1075-1108)
             d.sig_x_exp = min(lq["out2"]["out_exp"], 6)
             d.sig_y_exp = lq["out2"]["out_bits"] - 2
@@ -153,10 +186,48 @@ class FxpRegressionModel:
         desc = _abi.FxpModelDesc()
         desc.n_layers, desc.H, desc.P = self.n_layers, self.H, self.P
         desc.d_input, desc.d_output, desc.use_sparse = self.d_input, self.d_output, int(use_sparse)
-        self._dense(md["encoder"]["encoder"], q["encoder"], desc.encoder)
-        self._dense(md["decoder"], q["decoder"], desc.decoder)
+        e = self._dense(md["encoder"]["encoder"], q["encoder"], desc.encoder)
+        dd = self._dense(md["decoder"], q["decoder"], desc.decoder)
+        exp_params["encoder"]["encoder"], exp_qcfg["encoder"]["encoder"] = e["params"], e["qconfig"]
+        exp_params["decoder"], exp_qcfg["decoder"] = dd["params"], dd["qconfig"]
+        self._export = dict(params=exp_params, qconfig=exp_qcfg)
+        self.modeldict = md
         desc.layers = layers
         return desc
+
+    # ------------------------------------------------------------------ export
+    def export(self, fxp_x=None) -> dict:
+        """``FxpRegressionModel.export()`` (fxpmodel.py:1441-1458): ``dict(params, qconfig, intermediates)`` with the
+        reference's nesting (encoder / layers_i / mixer | out2 | norm, decoder).  Integer payloads are NumPy int32 arrays.
+        ``intermediates`` holds what the library can tap after a forward on ``fxp_x``: per block ``ssm_input``, ``pre_s5``,
+        ``post_GLU``, ``output`` and ``mixer/xs_relu``, plus ``encoder/pre_encoder`` and ``decoder/__call__``; every entry is
+        ``dict(data, bits, exp, signed)`` (the reference pickles ``FxpArray`` objects, whose class lives in its own
+        package; the fields are the same)."""
+        out = dict(params=self._export["params"], qconfig=self._export["qconfig"], intermediates={})
+        if fxp_x is not None:
+            fa = lambda t: dict(data=t.data.cpu().numpy(), bits=t.bits, exp=t.exp, signed=True)
+            enc = {"encoder": {"pre_encoder": fa(fxp_x)}}
+            for i in range(self.n_layers):
+                enc[f"layers_{i}"] = dict(ssm_input=fa(self.tap(fxp_x, i, TAP_LAYER_INPUT)), pre_s5=fa(self.tap(fxp_x, i, TAP_PRE_S5)),
+                                          post_GLU=fa(self.tap(fxp_x, i, TAP_POST_GLU)), output=fa(self.tap(fxp_x, i, TAP_OUTPUT)),
+                                          mixer=dict(xs_relu=fa(self.tap(fxp_x, i, TAP_XS))))
+            out["intermediates"] = dict(encoder=enc, decoder={"__call__": fa(self(fxp_x))})
+        return out
+
+    def export_files(self, folder: str, fxp_x) -> None:
+        """The five pickles ``fxprun.py --export`` writes (fxprun.py:476-495), same file names and top-level keys."""
+        import os
+        import pickle
+
+        data = self.export(fxp_x)
+        os.makedirs(folder, exist_ok=True)
+        dump = lambda name, obj: pickle.dump(obj, open(os.path.join(folder, name), "wb"))
+        dump("fxpmodel_modeldict.pkl", self.modeldict)
+        dump("fxpmodel_fxp_qconfig.pkl", self.q)
+        dump("fxpmodel_io.pkl", dict(input=data["intermediates"]["encoder"]["encoder"]["pre_encoder"],
+                                     output=data["intermediates"]["decoder"]["__call__"]))
+        dump("fxpmodel.pkl", {k: v for k, v in data.items() if k != "intermediates"})
+        dump("fxpmodel_activations.pkl", {"intermediates": data["intermediates"]})
 
     # ------------------------------------------------------------------ plumbing
     def close(self):

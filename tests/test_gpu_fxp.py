@@ -179,3 +179,42 @@ def test_fxp_model_batch_of_one_and_dense_tiles(cuda_device, fxp_case):
         pm = PF.FxpRegressionModel(md, q, n_layers, use_sparse=use_sparse)
         y = pm(pm.quantize_input(torch.from_numpy(x1).to(cuda_device)))
         assert np.array_equal(y.data.cpu().numpy(), ref.data)
+
+
+def test_fxp_export_matches_oracle_and_writes_the_reference_files(cuda_device, fxp_case, tmp_path):
+    """FxpRegressionModel.export / export_files (fxpmodel.py:1441-1458, fxprun.py:476-495): the reference's nesting, integer
+    payloads equal to the oracle model's parameters, intermediates equal to the oracle's taps, five pickles."""
+    import pickle
+    import torch
+    from sparsernns_b200 import fxpmodel as PF
+
+    zoo, md, q = fxp_case
+    n_layers = zoo["dims"].n_layers
+    om = OFM.FxpRegressionModel(md, q, n_layers)
+    pm = PF.FxpRegressionModel(md, q, n_layers)
+    xq = pm.quantize_input(torch.from_numpy(zoo["x"]).to(cuda_device))
+    data = pm.export(xq)
+    assert set(data) == {"params", "qconfig", "intermediates"}
+    assert set(data["params"]) == {"encoder", "decoder"} and set(data["params"]["encoder"]) == {"encoder"} | {f"layers_{i}" for i in range(n_layers)}
+    assert np.array_equal(data["params"]["decoder"]["weight"], om.decoder.weight.data)
+    assert np.array_equal(data["params"]["encoder"]["encoder"]["bias"], om.encoder.bias.data)
+    taps = {}
+    y_ref = om(om.quantize_input(zoo["x"]), taps)
+    for i in range(n_layers):
+        lp, lq = data["params"]["encoder"][f"layers_{i}"], data["qconfig"]["encoder"][f"layers_{i}"]
+        ol = om.layers[i]
+        assert np.array_equal(lp["mixer"]["A_real"], ol.mixer.A.real.data) and np.array_equal(lp["mixer"]["C_imag"], ol.mixer.C.imag.data)
+        assert np.array_equal(lp["mixer"]["D"], ol.mixer.D.data) and lq["mixer"]["A_real_exp"] == ol.mixer.A.real.exp
+        assert np.array_equal(lp["norm"]["mean"], -ol.norm.minus_mean.data)
+        assert np.array_equal(lp["out2"]["weight"], ol.out2.weight.data)
+        assert set(lq) == {"mixer", "out2", "norm", "multgate", "sigmoid"}
+        it = data["intermediates"]["encoder"][f"layers_{i}"]
+        assert np.array_equal(it["output"]["data"], taps[f"layers_{i}"]["output"].data) and it["output"]["exp"] == taps[f"layers_{i}"]["output"].exp
+        assert np.array_equal(it["post_GLU"]["data"], taps[f"layers_{i}"]["post_GLU"].data)
+    assert np.array_equal(data["intermediates"]["decoder"]["__call__"]["data"], y_ref.data)
+    pm.export_files(str(tmp_path), xq)
+    names = {"fxpmodel_modeldict.pkl", "fxpmodel_fxp_qconfig.pkl", "fxpmodel_io.pkl", "fxpmodel.pkl", "fxpmodel_activations.pkl"}
+    assert names == {p.name for p in tmp_path.iterdir()}
+    io = pickle.load(open(tmp_path / "fxpmodel_io.pkl", "rb"))
+    assert np.array_equal(io["output"]["data"], y_ref.data) and np.array_equal(io["input"]["data"], xq.data.cpu().numpy())
+    assert set(pickle.load(open(tmp_path / "fxpmodel.pkl", "rb"))) == {"params", "qconfig"}
