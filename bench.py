@@ -323,7 +323,12 @@ def main():
     e2e_fps = world * rows * ke / float(e2e_s.item())
     e2e_async_fps = world * rows * ke / float(e2e_async_s.item())
 
-    # per-kernel device time (events recorded by the library around each launch)
+    # per-kernel device time (events recorded by the library around each launch); the end-to-end leg above leaves copies
+    # on other streams behind: drain them and re-warm before timing single launches
+    torch.cuda.synchronize()
+    for i in range(3):
+        step(i)
+    torch.cuda.synchronize()
     lib.s5b200_profile_begin()
     for i in range(K):
         step(i)
