@@ -15,10 +15,12 @@ SparseRNNs) for the three numerics flavours of the S5 NDNS model forward:
 * ``model``      - S5 block + regression model shell   (model/layers.py:180-241, model/seq_model.py:100-115, 439-456)
 * ``fxpmodel``   - integer-only model                  (sparseRNNs/fxpmodel.py)
 * ``fxpconfig``  - fxp_qconfig construction            (sparseRNNs/fxputils.py:121-142, 155-285, 351-401, 453-786)
+* ``ndns``       - STFT / iSTFT / SI-SNR / loss tail      (sparseRNNs/train_helpers.py:16-53, 1381-1412, 1570-1614);
+                   PINNED against scipy.signal.stft / istft (tests/test_oracle_ndns.py)
 * ``synth``      - recipe-shaped random model, ERK magnitude masks, one-batch
                    calibration
 
-PARITY PIN STATUS: **parity unpinned by the reference**.  The reference ships no
+PARITY PIN STATUS: **parity unpinned by the reference** (model path; the ``ndns`` module is pinned against SciPy).  The reference ships no
 tests directory, golden vectors or fixtures for this path (SURVEY.md section 4,
 section 8c) and JAX/Flax are not importable in the build container, so the
 reference itself cannot be executed to generate vectors.  The oracle is pinned
