@@ -305,6 +305,23 @@ int s5b200_si_snr(const float* target, const float* estimate, int B, long long T
 int s5b200_mse_clips(const float* a, const float* b, int B, long long n_per_clip, float* out, void* workspace,
                      size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * (6) Static-quant calibration pass: the `calibrating=True` graph of the reference
+ * (quantization.py:428-436, 730-745, 793-811; ssm.py:230-337; layers.py:217-238; driven by convert.py:881-971) on one batch.
+ * Every FakeQuant / QuantizedDense site passes its value through unchanged and records min / max; `m` must be a
+ * FLOAT-flavour handle of the (pruned) float weights.  minmax (device) receives s5b200_calibrate_sites(m) pairs (min, max):
+ *   0 encoder input, 1 encoder output (before the ReLU);
+ *   2 + 9 i + {0: u = BN(h), 1: Re Bu, 2: Im Bu, 3: Re x, 4: Im x (states before the ReLU), 5: y = ys + D u,
+ *              6: x1 (out2 input = left gate), 7: out2 output, 8: sigmoid (right gate)}  for block i;
+ *   sites - 2: decoder input, sites - 1: decoder output.
+ * y [B][L][d_output] receives the float model output.  First-call semantics: no in-loop re-quantisation of the states (the
+ * `quant_xt` observer does not exist yet when the loop is built, ssm.py:254, :314).  Scales are derived on the host
+ * (quantization.py:352-370; sparsernns_b200/calibrate.py).
+ * ---------------------------------------------------------------------------------------------- */
+int s5b200_calibrate_sites(const s5_model* m);
+int s5b200_model_calibrate(const s5_model* m, const float* x, float* y, float* minmax, int B, int L, void* workspace,
+                           size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -137,6 +137,8 @@ PROTOTYPES = {
     "s5b200_reduce_workspace_bytes": (_SZ, [_I, _LL]),
     "s5b200_si_snr": (_I, [_V, _V, _I, _LL, _V, _V, _SZ, _V]),
     "s5b200_mse_clips": (_I, [_V, _V, _I, _LL, _V, _V, _SZ, _V]),
+    "s5b200_calibrate_sites": (_I, [_V]),
+    "s5b200_model_calibrate": (_I, [_V, _V, _V, _V, _I, _I, _V, _SZ, _V]),
 }
 
 _lib = None

@@ -19,6 +19,7 @@
 #include "proj.cuh"
 #include "scan.cuh"
 #include "tc_model.cuh"
+#include "calib.cuh"
 
 namespace s5 {
 
@@ -751,6 +752,79 @@ extern "C" int s5b200_ssm_forward(const s5_model* m, int layer, const float* u, 
   float* bu = xs_out ? xs_out : reinterpret_cast<float*>(base + w.off_bu);
   if (!aligned16(bu)) S5_FAIL(S5_E_BADARG, "ssm_forward: xs_out must be 16-byte aligned");
   return run_block(m, layer, u, y, bu, B, L, base + w.off_scan, w.scan_bytes, false, true, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------- calibration pass
+extern "C" int s5b200_calibrate_sites(const s5_model* m) { return m ? 4 + 9 * m->desc.n_layers : 0; }
+
+extern "C" int s5b200_model_calibrate(const s5_model* m, const float* x, float* y, float* minmax, int B, int L, void* workspace,
+                                      size_t workspace_bytes, void* stream) {
+  using namespace s5;
+  int rc;
+  if ((rc = check_model_args(m, x, y, B, L, workspace, workspace_bytes, "model_calibrate"))) return rc;
+  if (!minmax) S5_FAIL(S5_E_BADARG, "model_calibrate: null minmax");
+  const s5_model_desc& d = m->desc;
+  if (d.flavour != S5_FLOAT) S5_FAIL(S5_E_BADARG, "model_calibrate: needs a float-flavour handle (the calibrating graph passes values through unchanged)");
+  if (2 * d.P < d.H) S5_FAIL(S5_E_UNSUPPORTED, "model_calibrate: needs 2P >= H (scratch reuse)");
+  cudaStream_t st = (cudaStream_t)stream;
+  const WsLayout w = ws_layout(m, B, L);
+  unsigned char* base = reinterpret_cast<unsigned char*>(workspace);
+  float* a = reinterpret_cast<float*>(base + w.off_a);
+  float* b = reinterpret_cast<float*>(base + w.off_b);
+  float* bu = reinterpret_cast<float*>(base + w.off_bu);
+  const long long rows = (long long)B * L;
+  const int sites = s5b200_calibrate_sites(m);
+  uint32_t* mm = reinterpret_cast<uint32_t*>(minmax);
+  const int grid = (int)std::min<long long>((rows * 32 + 255) / 256, (long long)sm_count() * 8);
+  ProfScope prof(S5_K_OTHER, st);
+  calib_init_kernel<<<(sites + 127) / 128, 128, 0, st>>>(mm, sites);
+  S5_LAUNCH_CHECK();
+  auto observe = [&](int site, const float* t, long long n, int stride, int offset, const LayerDev* bn) -> int {
+    calib_minmax_kernel<<<grid, 256, 0, st>>>(t, n, stride, offset, d.H, bn ? bn->bn_mean : nullptr, bn ? bn->bn_mul : nullptr,
+                                              bn ? bn->bn_bias : nullptr, mm + 2 * site);
+    S5_LAUNCH_CHECK();
+    return S5_OK;
+  };
+  auto ew = [&](int mode, float* t, const float* u, const float* v, long long n) -> int {
+    calib_ew_kernel<<<grid, 256, 0, st>>>(mode, t, u, v, n);
+    S5_LAUNCH_CHECK();
+    return S5_OK;
+  };
+  // encoder QuantizedDense (quantization.py:730-745, 793-811: input and output observers), then ReLU (seq_model.py:100-115)
+  if ((rc = observe(0, x, rows * d.d_input, 1, 0, nullptr))) return rc;
+  if ((rc = launch_linear(dense_params(m, m->enc, m->enc_bias, x, a, rows, 1.f, 1.f, 0), st, S5_K_ENC))) return rc;
+  if ((rc = observe(1, a, rows * d.H, 1, 0, nullptr))) return rc;
+  if (d.relufication && (rc = ew(CAL_RELU, a, nullptr, nullptr, rows * d.H))) return rc;
+  for (int i = 0; i < d.n_layers; ++i) {
+    const LayerDev& ld = m->layers[i];
+    const int s0 = 2 + 9 * i;
+    // u = BN(h) (quant_ut); Bu (quant_But); states before the ReLU (quant_xt); y = ys + D u (quant_yt)      ssm.py:230-337, 594-601
+    if ((rc = observe(s0 + 0, a, rows * d.H, 1, 0, &ld))) return rc;
+    if ((rc = launch_linear(bproj_params(m, ld, a, bu, rows, true), st, S5_K_BPROJ))) return rc;
+    if ((rc = observe(s0 + 1, bu, rows * d.P, 2, 0, nullptr)) || (rc = observe(s0 + 2, bu, rows * d.P, 2, 1, nullptr))) return rc;
+    if ((rc = launch_scan_c64(bu, ld.lam, bu, B, L, d.P, 0, base + w.off_scan, w.scan_bytes, st))) return rc;
+    if ((rc = observe(s0 + 3, bu, rows * d.P, 2, 0, nullptr)) || (rc = observe(s0 + 4, bu, rows * d.P, 2, 1, nullptr))) return rc;
+    if (d.relufication && (rc = ew(CAL_CRELU, bu, nullptr, nullptr, rows * d.P))) return rc;
+    if ((rc = launch_glu(glu_params(m, ld, bu, a, b, rows, true, true), st))) return rc;          // ssm_only: y before the activation
+    if ((rc = observe(s0 + 5, b, rows * d.H, 1, 0, nullptr))) return rc;
+    if ((rc = ew(d.activation == S5_ACT_RELU ? CAL_RELU : CAL_GELU, b, nullptr, nullptr, rows * d.H))) return rc;
+    // out2 QuantizedDense on x1, sigmoid, mult_gate observers (layers.py:217-238)
+    if ((rc = observe(s0 + 6, b, rows * d.H, 1, 0, nullptr))) return rc;
+    LinearParams o{};
+    o.X = b; o.Y = bu; o.rows = rows; o.w = wview(ld.wo); o.bias = ld.o_bias;
+    if ((rc = launch_linear(o, st, S5_K_GLU))) return rc;
+    if ((rc = observe(s0 + 7, bu, rows * d.H, 1, 0, nullptr))) return rc;
+    if ((rc = ew(CAL_SIGMOID, bu, nullptr, nullptr, rows * d.H))) return rc;
+    if ((rc = observe(s0 + 8, bu, rows * d.H, 1, 0, nullptr))) return rc;
+    if ((rc = ew(d.relufication ? CAL_GATE_RELU : CAL_GATE, b, bu, a, rows * d.H))) return rc;      // x1 * sg + skip (+ ReLU)
+    std::swap(a, b);
+  }
+  if ((rc = observe(sites - 2, a, rows * d.H, 1, 0, nullptr))) return rc;
+  if ((rc = launch_linear(dense_params(m, m->dec, m->dec_bias, a, y, rows, 1.f, 1.f, 0), st, S5_K_DEC))) return rc;
+  if ((rc = observe(sites - 1, y, rows * d.d_output, 1, 0, nullptr))) return rc;
+  calib_decode_kernel<<<(2 * sites + 127) / 128, 128, 0, st>>>(mm, 2 * sites);
+  S5_LAUNCH_CHECK();
+  return S5_OK;
 }
 
 static int forward_host_impl(const s5_model* mc, const float* x_host, float* y_host, int B, int L, void* stream, bool sync) {

@@ -306,3 +306,46 @@ def test_block_kernel_is_bit_reproducible_and_batch_invariant(cuda_device, zoo, 
     m2, _ = _bound(zoo, static=True, relufication=True)
     assert torch.equal(m2(x), y)
 
+
+
+def test_gpu_calibration_matches_oracle(cuda_device):
+    """s5b200_model_calibrate + host scale derivation against the oracle's one-batch calibration: every
+    observer within 1e-5 of the tensor's range, every power-of-two scale EQUAL, and the static model built from the GPU
+    calibration bit-identical to the one built from the oracle's."""
+    import torch
+    from sparsernns_b200 import calibrate as PC
+    from sparsernns_b200 import synth
+    from sparsernns_b200.model import BoundModel, S5Config
+
+    zoo = Z.build_sparse_calibrated(0.5, n_clips=2, n_frames=280)
+    d = zoo["dims"]
+    cfg = S5Config(n_layers=d.n_layers, d_model=d.d_model, ssm_size=d.ssm_size, relufication=True, quantization="w8a16")
+    x = torch.from_numpy(zoo["x"]).to(cuda_device)
+    P, stats, y = PC.calibrate(x, zoo["variables"], cfg)
+    ref_P, ref_S = zoo["cal_params"], zoo["cal_stats"]
+
+    n_scales = 0
+
+    def walk(a, b, path=""):
+        nonlocal n_scales
+        assert set(a) == set(b), (path, sorted(set(a) ^ set(b)))
+        for k in a:
+            if isinstance(a[k], dict):
+                walk(a[k], b[k], f"{path}/{k}")
+            elif "scale" in k and np.ndim(a[k]) == 0 and "norm" not in path:
+                assert np.float32(a[k]) == np.float32(b[k]), (path, k, a[k], b[k])
+                n_scales += 1
+            elif "observer" in k:
+                assert abs(float(a[k]) - float(b[k])) <= 1e-5 * max(abs(float(b[k])), 1e-3), (path, k, a[k], b[k])
+            else:
+                assert np.array_equal(np.asarray(a[k]), np.asarray(b[k])), (path, k)
+
+    walk(stats, ref_S, "stats")
+    walk(P, ref_P, "params")
+    assert n_scales == 2 * (6 + 18 * d.n_layers)     # every scale of both trees was compared (18 per block, 3 per Dense)
+    ocfg = Z.oracle_cfg(d, relufication=True, static_quant=False)
+    assert relerr(y.cpu().numpy(), OM.model_forward(zoo["x"], zoo["variables"], ocfg, dtype=np.float64)) <= TOL_F32
+    bs = zoo["variables"]["batch_stats"]
+    y1 = BoundModel(cfg, {"params": P, "batch_stats": bs})(x)
+    y2 = BoundModel(cfg, {"params": ref_P, "batch_stats": bs})(x)
+    assert torch.equal(y1, y2)
