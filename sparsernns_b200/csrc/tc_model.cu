@@ -1712,13 +1712,26 @@ static int tc_linear_go(const TcLinParams& p0, int kclass, cudaStream_t st) {
   // output columns per pass: as wide as possible while two CTAs (2 x 8 warps, 2 x 256 TMEM columns) share an SM
   size_t smem = 0;
   auto fits2 = [&](size_t b) { return 2 * (b + 1024 + 64) <= (size_t)227 * 1024; };
-  for (int NP : {128, 64, 32, 16}) {
+  auto smem_for = [&](int NP) {
     p.NP = std::min(NP, p.Np);
     p.alias_out = p.NP >= p.Np;                               // single pass: the output tile reuses the dead planes
     const size_t out_bytes = (size_t)kTcRows * (p.NP + 4) * 4;
-    smem = w_bytes + (p.alias_out ? std::max(a2, out_bytes) : a2 + out_bytes) + (size_t)p.Np * sizeof(float2);
-    if (fits2(smem)) break;
+    return w_bytes + (p.alias_out ? std::max(a2, out_bytes) : a2 + out_bytes) + (size_t)p.Np * sizeof(float2);
+  };
+  // S5B200_LIN_MIN_NP (default 64): narrower passes than this are not worth a second CTA per SM (a pass is an MMA, an
+  // epilogue, two barriers and a write-out of NP-float row segments) - one CTA per SM with 128-column passes instead
+  static const int min_np = [] { const char* e = getenv("S5B200_LIN_MIN_NP"); return e ? atoi(e) : 64; }();
+  bool two = false;
+  for (int NP : {128, 64, 32, 16}) {
+    smem = smem_for(NP);
+    if (fits2(smem) && (NP >= min_np || NP >= p.Np)) { two = true; break; }
+    if (NP < min_np) break;
   }
+  if (!two)
+    for (int NP : {128, 64, 32, 16}) {
+      smem = smem_for(NP);
+      if (smem + 1024 + 64 <= (size_t)227 * 1024) break;
+    }
   if (smem + 64 > 227 * 1024) S5_FAIL(S5_E_BADSHAPE, "dense-tile linear: tile does not fit in shared memory");
   S5_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   S5_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
