@@ -14,6 +14,8 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
+#include <mutex>
 #include <vector>
 
 #include "proj.cuh"
@@ -740,6 +742,9 @@ struct TcGluParams {
   const signed char* WB;       // [K1][128] int8 codes of B_bar (rows = (re, im) interleaved outputs), lane-interleaved K
   const float* b_col_scale;    // [K1] s_u * s_w[n]
   float b_out_scale0, b_out_scale1, b_out_inv0, b_out_inv1;   // FQ grid of Re(Bu) / Im(Bu)
+  // BPJ: the layer's shared-memory image (weight tiles in the operand layout + per-column constants), built once per handle by
+  // tc_glu_image_kernel; a layer switch is then ONE bulk copy instead of ~55 KB of strided loads with index arithmetic
+  const unsigned char* img; uint32_t img_bytes;
 };
 
 // All blocks of the model in ONE launch (block kernel only): the tiles of layer l + 1 follow those of layer l in the same
@@ -767,6 +772,39 @@ __device__ __forceinline__ void half_barrier(int half) {
 __device__ __forceinline__ uint32_t pack_bf2(float a, float b) {   // {lo half = bf16(a), hi half = bf16(b)}, round to nearest even
   const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+// The per-layer image of the block kernel, laid out exactly as in its shared memory: C tile | out2 tile | B tile (BPJ) |
+// out2 bias / s_o_out [H] | B column scales [K1] | per-column constants [4][H].  `dst` is shared memory (direct fill) or the
+// handle's global image (tc_glu_image_kernel).  All scales are powers of two, so folding them into the constants changes
+// no rounding: (x - sub) * (mul / s_u) + add / s_u == BN(x) / s_u.
+__host__ __device__ inline size_t tc_glu_image_bytes(int H, int K1, bool bpj) {
+  return tc_tile_bytes(H, K1) + tc_tile_bytes8(H, kGluK2) + (bpj ? tc_tile_bytes8(K1, kGluK2) : 0) + (size_t)(5 * H + K1) * 4;
+}
+template <bool BPJ>
+__device__ __forceinline__ void tc_glu_fill_image(unsigned char* dst, const TcGluParams& p, int H, int K1, int tid, int nthreads) {
+  unsigned char* Wc = dst;
+  unsigned char* Wo = Wc + tc_tile_bytes(H, K1);
+  unsigned char* WB = Wo + tc_tile_bytes8(H, kGluK2);
+  float* ob = reinterpret_cast<float*>(WB + (BPJ ? tc_tile_bytes8(K1, kGluK2) : 0));
+  float* cstB = ob + H;
+  float* lcst = cstB + K1;
+  tc_load_weights(Wc, reinterpret_cast<const __half*>(p.Wc), H, K1);
+  tc_load_weights8(Wo, p.Wo, H, kGluK2);
+  if constexpr (BPJ) {
+    tc_load_weights8(WB, p.WB, K1, kGluK2);
+    for (int n = tid; n < K1; n += nthreads) cstB[n] = p.b_col_scale[n] * ((n & 1) ? p.b_out_inv1 : p.b_out_inv0);
+  }
+  for (int n = tid; n < H; n += nthreads) ob[n] = p.o_bias[n] * p.oo_inv;
+  for (int c = tid; c < H; c += nthreads) {
+    lcst[c] = p.bn_sub ? p.bn_sub[c] : 0.f;
+    lcst[H + c] = (p.bn_sub ? p.bn_mul[c] : 1.f) * p.ut_inv;
+    lcst[2 * H + c] = (p.bn_sub ? p.bn_add[c] : 0.f) * p.ut_inv;
+    lcst[3 * H + c] = p.D[c] * p.ut_s * p.yt_inv;             // D u / s_y = (D s_u / s_y) * code(u)
+  }
+}
+__global__ void tc_glu_image_kernel(TcGluParams p, unsigned char* img) {
+  tc_glu_fill_image<true>(img, p, p.H, p.K1, threadIdx.x, blockDim.x);
 }
 
 // Per 128-row tile (HJ = H / 32 columns per lane in the lanes-along-columns passes):
@@ -853,20 +891,25 @@ __global__ void __launch_bounds__(kGluThreads, 1) tc_glu_kernel(const __grid_con
   // All scales are powers of two, so folding them into the BatchNorm / feed-through constants changes no rounding:
   // (x - sub) * (mul / s_u) + add / s_u == BN(x) / s_u.
   float2 lam = make_float2(0.f, 0.f), lamR = make_float2(1.f, 0.f), lamS = make_float2(1.f, 0.f);
+  __shared__ __align__(8) uint64_t wbar;                      // BPJ: completion of the layer-image bulk copy
+  uint32_t wpar = 0;
+  if (tid == 0) {
+    mbar_init(&wbar, 1);
+    fence_mbar_init();
+  }
   auto load_layer = [&](int l) {                              // called by all threads of the CTA, between two __syncthreads
     const TcGluParams& p = mp.layer[l];
-    tc_load_weights(Wc, reinterpret_cast<const __half*>(p.Wc), H, K1);
-    tc_load_weights8(Wo, p.Wo, H, kGluK2);
-    if constexpr (BPJ) {
-      tc_load_weights8(WB, p.WB, K1, kGluK2);
-      for (int n = tid; n < K1; n += kGluThreads) cstB[n] = p.b_col_scale[n] * ((n & 1) ? p.b_out_inv1 : p.b_out_inv0);
-    }
-    for (int n = tid; n < H; n += kGluThreads) ob[n] = p.o_bias[n] * p.oo_inv;
-    for (int c = tid; c < H; c += kGluThreads) {
-      lcst[c] = p.bn_sub ? p.bn_sub[c] : 0.f;
-      lcst[H + c] = (p.bn_sub ? p.bn_mul[c] : 1.f) * p.ut_inv;
-      lcst[2 * H + c] = (p.bn_sub ? p.bn_add[c] : 0.f) * p.ut_inv;
-      lcst[3 * H + c] = p.D[c] * p.ut_s * p.yt_inv;           // D u / s_y = (D s_u / s_y) * code(u)
+    if (BPJ && p.img) {
+      __syncthreads();                                        // (first call) the mbarrier is initialised
+      if (tid == 0) {
+        fence_proxy_async_smem();
+        mbar_expect_tx(&wbar, p.img_bytes);
+        bulk_g2s(Wc, p.img, p.img_bytes, &wbar);
+      }
+      mbar_wait(&wbar, wpar);
+      wpar ^= 1u;
+    } else {
+      tc_glu_fill_image<BPJ>(Wc, p, H, K1, tid, kGluThreads);
     }
     if constexpr (SCAN) {
       lam = p.lam[sp];
@@ -1924,7 +1967,7 @@ int tc_glu_build(const float* C_tilde /*[H][P][2] quantised*/, const float* out2
 }
 
 void tc_glu_free(TcGluDev* d) {
-  cudaFree(d->Wc); cudaFree(d->Wo); cudaFree(d->WB); cudaFree(d->b_col_scale);
+  cudaFree(d->Wc); cudaFree(d->Wo); cudaFree(d->WB); cudaFree(d->b_col_scale); cudaFree(d->img);
   *d = TcGluDev();
 }
 
@@ -1957,6 +2000,35 @@ static int tc_glu_go(const TcGluParams& p, size_t smem, int grid, cudaStream_t s
 size_t tc_glu_scan_workspace_bytes(int B, int L, int P) {
   const int cmax = (L + 31) / 32 + 1;                          // upper bound on tiles per clip
   return round_up((size_t)B * cmax * sizeof(uint32_t), 256) + (size_t)B * cmax * 2 * P * sizeof(float2);
+}
+
+// Builds (once per handle and set of scales) the block kernel's per-layer image in global memory.  The first call
+// synchronises the stream so that the image is complete before any other stream uses the handle.
+static int tc_glu_ensure_image(const TcGluDev& d, TcGluParams* p, cudaStream_t st) {
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
+  struct Key {
+    const void *Wc, *Wo, *WB, *bcs, *bn_sub, *bn_mul, *bn_add, *D, *o_bias;
+    float ut_s, ut_inv, yt_inv, oo_inv, b_inv0, b_inv1;
+  } key{p->Wc, p->Wo, p->WB, p->b_col_scale, p->bn_sub, p->bn_mul, p->bn_add, p->D, p->o_bias,
+        p->ut_s, p->ut_inv, p->yt_inv, p->oo_inv, p->b_out_inv0, p->b_out_inv1};
+  static_assert(sizeof(Key) <= sizeof(d.img_key), "image key too large");
+  const size_t bytes = tc_glu_image_bytes(d.H, d.K1, true);
+  if (!d.img_ok || std::memcmp(d.img_key, &key, sizeof(Key)) != 0) {
+    if (!d.img) S5_CUDA(cudaMalloc(&d.img, bytes));
+    S5_CUDA(cudaMemsetAsync(d.img, 0, bytes, st));
+    TcGluParams q = *p;
+    q.img = nullptr;
+    tc_glu_image_kernel<<<1, 512, 0, st>>>(q, reinterpret_cast<unsigned char*>(d.img));
+    S5_LAUNCH_CHECK();
+    S5_CUDA(cudaStreamSynchronize(st));
+    std::memset(d.img_key, 0, sizeof(d.img_key));
+    std::memcpy(d.img_key, &key, sizeof(Key));
+    d.img_ok = true;
+  }
+  p->img = reinterpret_cast<const unsigned char*>(d.img);
+  p->img_bytes = (uint32_t)bytes;
+  return S5_OK;
 }
 
 // fills the kernel parameters of one layer; *grid_out = grid size this layer alone would use
@@ -2006,6 +2078,9 @@ static int tc_glu_fill(const TcGluDev& d, const TcGluArgs& a, TcGluParams* out, 
     if (!d.bpj_ok || !is_pow2(a.s_bu_re) || !is_pow2(a.s_bu_im)) S5_FAIL(S5_E_BADARG, "dense-tile glu: fused B projection not eligible");
     p.WB = reinterpret_cast<const signed char*>(d.WB); p.b_col_scale = d.b_col_scale;
     p.b_out_scale0 = a.s_bu_re; p.b_out_scale1 = a.s_bu_im; p.b_out_inv0 = 1.f / a.s_bu_re; p.b_out_inv1 = 1.f / a.s_bu_im;
+    static const bool use_img = [] { const char* e = getenv("S5B200_LAYER_IMAGE"); return !e || atoi(e) != 0; }();
+    int rc;
+    if (use_img && (rc = tc_glu_ensure_image(d, &p, st))) return rc;
   }
   *out = p;
   return S5_OK;

@@ -23,6 +23,8 @@ struct TcGluDev {
   bool ok = false;
   // wide form (H > 128 or 2P > 128, e.g. dim_scale 1.0): C in 64-column chunks of the operand layout, out2 in the wide K order
   bool wide_ok = false; size_t smem_wide = 0;
+  // block kernel: the layer's shared-memory image in global memory, built on first use (tc_model.cu:tc_glu_ensure_image)
+  mutable void* img = nullptr; mutable bool img_ok = false; mutable unsigned char img_key[160] = {};
 };
 struct TcGluArgs {
   const float* XS; const float* X; float* OUT; long long rows;
