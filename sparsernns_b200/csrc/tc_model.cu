@@ -957,7 +957,7 @@ __global__ void __launch_bounds__(kGluThreads, 1) tc_glu_kernel(const __grid_con
       const long long g0 = iter * npipe + 2LL * blockIdx.x;   // CTA-uniform
       long long g = g0 + half;
       bool active = g < total;
-      layer = (int)(min(g0, total - 1) / ntp);
+      layer = (int)((uint32_t)min(g0, total - 1) / (uint32_t)ntp);   // tile counts are far below 2^31: 32-bit division
       if (iter == full_rounds && spread) {
         g = full_rounds * npipe + last_j;
         active = last_j < rem;
@@ -988,8 +988,8 @@ __global__ void __launch_bounds__(kGluThreads, 1) tc_glu_kernel(const __grid_con
     int rv;
     int clip = 0, chunk = 0;
     if constexpr (SCAN) {
-      chunk = (int)(it / p0.B);
-      clip = (int)(it - (long long)chunk * p0.B);
+      chunk = (int)((uint32_t)it / (uint32_t)p0.B);
+      clip = (int)it - chunk * p0.B;
       row0 = (long long)clip * p0.L + (long long)chunk * p0.R;
       rv = min(p0.R, p0.L - chunk * p0.R);
       if (layer > 0) {
