@@ -59,9 +59,13 @@ __device__ __forceinline__ double2 zfma(double2 a, double2 x, double2 v) {
 }
 __device__ __forceinline__ double2 f2z(float2 v) { return make_double2((double)v.x, (double)v.y); }
 
+// LB_FIXED: fixed-stride look-back (bit-reproducible, two round trips per chunk) for grids larger than one resident wave;
+// otherwise the classic walk (lowest latency when a whole clip is co-resident, e.g. batch 1).
+template <bool LB_FIXED>
 __global__ void __launch_bounds__(kScanThreads, 4)
 scan_c64_kernel(const float2* __restrict__ Bu, const float2* __restrict__ lam, float2* xs, int L, int P, int nsub,
                 int nchunks, int relu, uint32_t* flags, double2* recs, int rec_stride) {
+  constexpr bool lb_fixed = LB_FIXED;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int TL = nsub * kScanT;
   float2* tile = reinterpret_cast<float2*>(smem_raw);        // [TL][P]
@@ -133,7 +137,50 @@ scan_c64_kernel(const float2* __restrict__ Bu, const float2* __restrict__ lam, f
       asm volatile("bar.sync 1, %0;" ::"r"(carry_threads) : "memory");
       if (tid == 0) st_release_u32(flag_row + c, c == 0 ? 2u : 1u);
     }
-    if (c > 0) {
+    if constexpr (lb_fixed) if (c > 0) {
+      // Fixed-stride look-back (as in the fused block kernel, tc_model.cu).  Every chunk publishes its aggregate (flag 1),
+      // every kLbStride-th chunk (an "anchor") also its inclusive prefix (flag 2).  The carry-in of chunk c is ALWAYS
+      //     incl[a], then Horner over agg[a + 1 .. c - 1],     a = the last anchor before c,
+      // so (i) the floating-point association depends on c only - results are bit-reproducible - and (ii) all flags and
+      // all records of the walk are requested together: two memory round trips per chunk instead of two per
+      // predecessor, and only every kLbStride-th chunk sits on the serial anchor chain (118 chunks per 3751-frame clip
+      // used to be 118 dependent hops: the kernel was latency bound at 32 clips).
+      constexpr int kLbStride = 8;
+      const int a0 = ((c - 1) / kLbStride) * kLbStride;
+      const int n = c - a0;                                   // records to read: incl[a0], agg[a0 + 1 .. c - 1]
+      const bool anchor = (c % kLbStride) == 0;
+      double2 acc = make_double2(0., 0.);
+      if (tid < P) {
+        uint32_t f[kLbStride];
+#pragma unroll
+        for (int w = 0; w < kLbStride; ++w) f[w] = w < n ? ld_relaxed_u32(flag_row + a0 + w) : 2u;
+        while (f[0] != 2u) f[0] = ld_relaxed_u32(flag_row + a0);
+#pragma unroll
+        for (int w = 1; w < kLbStride; ++w)
+          while (f[w] == 0u) f[w] = ld_relaxed_u32(flag_row + a0 + w);
+        fence_acquire_gpu();                                  // one acquire for the whole walk
+        double2 rec[kLbStride];
+#pragma unroll
+        for (int w = 0; w < kLbStride; ++w)
+          if (w < n) rec[w] = __ldcg(rec_row + (size_t)(a0 + w) * rec_stride + (w == 0 ? half : 0) + p);
+        acc = rec[0];
+#pragma unroll
+        for (int w = 1; w < kLbStride; ++w)
+          if (w < n) acc = zfma(aTL, acc, rec[w]);
+        carry_s[p] = acc;
+        if (publish && anchor) {
+          __stcg(rec_row + (size_t)c * rec_stride + half + p, zfma(aTL, acc, e));
+          __threadfence();
+        }
+      }
+      if (publish && anchor) {
+        asm volatile("bar.sync 1, %0;" ::"r"(carry_threads) : "memory");
+        if (tid == 0) st_release_u32(flag_row + c, 2u);
+      }
+    }
+    // classic decoupled look-back (whole clips co-resident, e.g. batch 1: a chunk may walk past predecessors on
+    // aggregates alone instead of waiting for the anchor's inclusive prefix - lower latency, timing-dependent association)
+    if constexpr (!lb_fixed) if (c > 0) {
       if (tid < P) {
         // decoupled look-back: walk predecessors until one has published its inclusive prefix
         double2 mult = make_double2(1., 0.);
@@ -613,7 +660,8 @@ int launch_scan_c64(const float* Bu, const float* lam, float* xs, int B, int L, 
   const ScanGeom g = scan_geom(L, P);
   static bool attr_set = false;
   if (!attr_set) {
-    S5_CUDA(cudaFuncSetAttribute(scan_c64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    S5_CUDA(cudaFuncSetAttribute(scan_c64_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    S5_CUDA(cudaFuncSetAttribute(scan_c64_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     attr_set = true;
   }
   const size_t flags_bytes = round_up((size_t)B * g.nchunks * sizeof(uint32_t), 256);
@@ -623,10 +671,10 @@ int launch_scan_c64(const float* Bu, const float* lam, float* xs, int B, int L, 
   if (g.nchunks > 65535) S5_FAIL(S5_E_BADSHAPE, "scan_c64: L=%d needs more than 65535 chunks", L);
   dim3 grid(B, g.nchunks);
   ProfScope prof(S5_K_SCAN_C64, st);
-  scan_c64_kernel<<<grid, g.threads, g.smem_bytes, st>>>(reinterpret_cast<const float2*>(Bu),
-                                                         reinterpret_cast<const float2*>(lam),
-                                                         reinterpret_cast<float2*>(xs), L, P, g.nsub, g.nchunks, relu,
-                                                         flags, recs, (int)g.rec_floats2);
+  auto kernel = (long long)B * g.nchunks > 4LL * sm_count() ? scan_c64_kernel<true> : scan_c64_kernel<false>;
+  kernel<<<grid, g.threads, g.smem_bytes, st>>>(reinterpret_cast<const float2*>(Bu), reinterpret_cast<const float2*>(lam),
+                                                reinterpret_cast<float2*>(xs), L, P, g.nsub, g.nchunks, relu, flags, recs,
+                                                (int)g.rec_floats2);
   S5_LAUNCH_CHECK();
   return S5_OK;
 }
