@@ -841,6 +841,7 @@ static int forward_host_impl(const s5_model* mc, const float* x_host, float* y_h
   // Chunk schedule (S5B200_E2E_CHUNKS=n forces n equal chunks, "a,b,c" explicit clip counts).
   std::vector<int> sched;
   const char* e = getenv("S5B200_E2E_CHUNKS");
+  if (e && !*e) e = nullptr;                     // an empty value means "not set"
   if (e && strchr(e, ',')) {                    // explicit clip counts, e.g. "6,6,6,6,4,4"; the rest goes into a last chunk
     int used = 0;
     for (const char* q = e; *q && used < B;) {
