@@ -1006,6 +1006,9 @@ __global__ void __launch_bounds__(kGluThreads, 1) tc_glu_kernel(const __grid_con
       row0 = it;
       rv = (int)min((long long)kTcRows, row_end - row0);
     }
+    // per-tile base pointer and 32-bit row clamp: loads are never predicated, rows past the end re-read the last row
+    const float* xtile = pX + (size_t)row0 * H;
+    const int rlim = (int)min((long long)kTcRows, last_row - row0);
     TC_TRACE_MARK(tid == 0);
     if constexpr (SCAN) {
       // ---- S (fused recurrence): Bu -> registers -> local aggregate -> look-back -> states -> bf16 planes
@@ -1022,7 +1025,7 @@ __global__ void __launch_bounds__(kGluThreads, 1) tc_glu_kernel(const __grid_con
           float xr8[8][HJ];
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
-            const float* xr = pX + (size_t)min(row0 + rb + q, last_row) * H;
+            const float* xr = xtile + min(rb + q, rlim) * H;
 #pragma unroll
             for (int j = 0; j < HJ; ++j) xr8[q][j] = xr[lane + 32 * j];
           }
@@ -1210,7 +1213,7 @@ __global__ void __launch_bounds__(kGluThreads, 1) tc_glu_kernel(const __grid_con
     float xin[PB][HJ];
 #pragma unroll
     for (int q = 0; q < PB; ++q) {
-      const float* xr = pX + (size_t)min(row0 + warp * PB + q, last_row) * H;
+      const float* xr = xtile + min(warp * PB + q, rlim) * H;
 #pragma unroll
       for (int j = 0; j < HJ; ++j) xin[q][j] = xr[lane + 32 * j];
     }
@@ -1244,7 +1247,7 @@ __global__ void __launch_bounds__(kGluThreads, 1) tc_glu_kernel(const __grid_con
       if (rb != warp * PB) {
 #pragma unroll
         for (int q = 0; q < PB; ++q) {
-          const float* xr = pX + (size_t)min(row0 + rb + q, last_row) * H;
+          const float* xr = xtile + min(rb + q, rlim) * H;
 #pragma unroll
           for (int j = 0; j < HJ; ++j) xin[q][j] = xr[lane + 32 * j];
         }
@@ -1285,7 +1288,7 @@ __global__ void __launch_bounds__(kGluThreads, 1) tc_glu_kernel(const __grid_con
     // skip-connection rows of the first P2 batch (L2 hits) travel during the second product and E2
 #pragma unroll
     for (int q = 0; q < PB; ++q) {
-      const float* xr = pX + (size_t)min(row0 + warp * PB + q, last_row) * H;
+      const float* xr = xtile + min(warp * PB + q, rlim) * H;
 #pragma unroll
       for (int j = 0; j < HJ; ++j) xin[q][j] = xr[lane + 32 * j];
     }
@@ -1330,7 +1333,7 @@ __global__ void __launch_bounds__(kGluThreads, 1) tc_glu_kernel(const __grid_con
       if (rb != warp * PB) {
 #pragma unroll
         for (int q = 0; q < PB; ++q) {
-          const float* xr = pX + (size_t)min(row0 + rb + q, last_row) * H;
+          const float* xr = xtile + min(rb + q, rlim) * H;
 #pragma unroll
           for (int j = 0; j < HJ; ++j) xin[q][j] = xr[lane + 32 * j];
         }
@@ -1454,6 +1457,8 @@ __global__ void __launch_bounds__(kGluwThreads, 1) tc_gluw_kernel(const __grid_c
   if (row_begin < row_end) load_chunk(row_begin, 0);
   for (long long row0 = row_begin; row0 < row_end; row0 += kTcRows) {
     const int rv = (int)min((long long)kTcRows, row_end - row0);
+    const float* xtile = p.X + (size_t)row0 * H;
+    const int rlim = (int)min((long long)kTcRows, last_row - row0);
     // ---- S + MMA 1, chunk by chunk
     for (int c = 0; c < NC; ++c) {
       const int b = c & 1;
@@ -1496,7 +1501,7 @@ __global__ void __launch_bounds__(kGluwThreads, 1) tc_gluw_kernel(const __grid_c
     float xin[PB][HJ];
 #pragma unroll
     for (int q = 0; q < PB; ++q) {
-      const float* xr = p.X + (size_t)min(row0 + warp * PB + q, last_row) * H;
+      const float* xr = xtile + min(warp * PB + q, rlim) * H;
 #pragma unroll
       for (int j = 0; j < HJ; ++j) xin[q][j] = xr[lane + 32 * j];
     }
@@ -1530,7 +1535,7 @@ __global__ void __launch_bounds__(kGluwThreads, 1) tc_gluw_kernel(const __grid_c
       if (rb != warp * PB) {
 #pragma unroll
         for (int q = 0; q < PB; ++q) {
-          const float* xr = p.X + (size_t)min(row0 + rb + q, last_row) * H;
+          const float* xr = xtile + min(rb + q, rlim) * H;
 #pragma unroll
           for (int j = 0; j < HJ; ++j) xin[q][j] = xr[lane + 32 * j];
         }
@@ -1581,7 +1586,7 @@ __global__ void __launch_bounds__(kGluwThreads, 1) tc_gluw_kernel(const __grid_c
     // skip-connection rows of the first P2 batch (L2 hits) travel during the second product and E2
 #pragma unroll
     for (int q = 0; q < PB; ++q) {
-      const float* xr = p.X + (size_t)min(row0 + warp * PB + q, last_row) * H;
+      const float* xr = xtile + min(warp * PB + q, rlim) * H;
 #pragma unroll
       for (int j = 0; j < HJ; ++j) xin[q][j] = xr[lane + 32 * j];
     }
@@ -1623,7 +1628,7 @@ __global__ void __launch_bounds__(kGluwThreads, 1) tc_gluw_kernel(const __grid_c
       if (rb != warp * PB) {
 #pragma unroll
         for (int q = 0; q < PB; ++q) {
-          const float* xr = p.X + (size_t)min(row0 + rb + q, last_row) * H;
+          const float* xr = xtile + min(rb + q, rlim) * H;
 #pragma unroll
           for (int j = 0; j < HJ; ++j) xin[q][j] = xr[lane + 32 * j];
         }
