@@ -323,6 +323,41 @@ def main():
     e2e_fps = world * rows * ke / float(e2e_s.item())
     e2e_async_fps = world * rows * ke / float(e2e_async_s.item())
 
+    # informational: the application's own end to end (the forward of the reference's NDNS eval step, train_helpers.py:1570-1614):
+    # noisy AUDIO in pinned host memory -> H2D -> STFT -> model -> mask apply + iSTFT -> D2H of the cleaned audio.  A quarter of
+    # the PCIe bytes of the tensor-level e2e above, because spectra never cross the bus.  Only when L is the STFT of whole hops.
+    e2e_audio = None
+    if not args.no_extras and L >= 2:
+        from sparsernns_b200 import ndns
+        n_samp = (L - 1) * 128
+        ah = [(0.05 * torch.randn(B, n_samp)).pin_memory() for _ in range(2)]
+        oh = [torch.empty(B, n_samp).pin_memory() for _ in range(2)]
+        nch = 4 if B % 4 == 0 else 1                                       # clip chunks over two streams: copies overlap kernels
+        streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+
+        def audio_step(i):
+            for c in range(nch):
+                with torch.cuda.stream(streams[c % 2]):
+                    sl = slice(c * B // nch, (c + 1) * B // nch)
+                    a = ah[i % 2][sl].to(dev, non_blocking=True)
+                    mag, ph, xin = ndns.stft_splitter(a, blf=True, model_input=True)
+                    cleaned = ndns.stft_mixer(mag, ph, blf=True, mask=model(xin))
+                    oh[i % 2][sl].copy_(cleaned, non_blocking=True)
+
+        for i in range(2):
+            audio_step(i)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(ke):
+            audio_step(i)
+        torch.cuda.synchronize()
+        ea_s = torch.tensor([time.perf_counter() - t0], device=dev)
+        if dist is not None:
+            dist.all_reduce(ea_s, op=dist.ReduceOp.MAX)
+        e2e_audio = {"value": world * rows * ke / float(ea_s.item()), "unit": "frames/s", "h2d_bytes_per_step": B * n_samp * 4,
+                     "d2h_bytes_per_step": B * n_samp * 4,
+                     "what": "audio -> STFT -> model -> mask apply + iSTFT -> audio, %d clip chunks on two streams (sparsernns_b200.ndns)" % nch}
+
     # per-kernel device time (events recorded by the library around each launch); the end-to-end leg above leaves copies
     # on other streams behind: drain them and re-warm before timing single launches
     torch.cuda.synchronize()
@@ -397,7 +432,7 @@ def main():
             "clocks": clock_info,
             "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": rows * D_IO * 4, "d2h_bytes_per_step": rows * D_IO * 4,
                     "steps": ke, "mode": "host-synchronous s5b200_model_forward_host per step (pinned host buffers)",
-                    "stream_ordered_value": e2e_async_fps, "numa": numa},
+                    "stream_ordered_value": e2e_async_fps, "numa": numa, "audio_to_audio": e2e_audio},
             "gpu_launches": launches,
             "roofline": roofline,
             "kernels": kernels,
