@@ -174,3 +174,29 @@ def test_batch_dependence_of_compute_best():
     a = m(m.quantize_input(x[:1])).data
     b = m(m.quantize_input(x)).data[:1]
     assert a.shape == b.shape  # both are valid "shard-local" results; they need not be equal
+
+
+def test_calibration_scale_formula_matches_oracle():
+    """sparsernns_b200.calibrate.calculate_qparams (quantization.py:352-370) against the oracle's restatement."""
+    from oracle.quant import calculate_qparams as ref
+    from sparsernns_b200.calibrate import calculate_qparams
+
+    rng = np.random.default_rng(0)
+    for bits in (8, 16):
+        for _ in range(500):
+            lo, hi = np.sort(rng.standard_normal(2) * 10.0 ** rng.uniform(-8, 4))
+            assert calculate_qparams(lo, hi, bits) == ref(lo, hi, bits)
+        for v in (0.0, 1e-12, 127.0, 128.0, 32767.0, 2.0 ** -20):        # eps floor and exact powers of two
+            assert calculate_qparams(-v, v, bits) == ref(-v, v, bits)
+
+
+def test_ndns_and_calibrate_fail_loudly_without_cuda():
+    import torch
+    from sparsernns_b200 import ndns
+
+    if torch.cuda.is_available():
+        pytest.skip("needs a machine without CUDA")
+    with pytest.raises(ValueError):
+        ndns.stft_splitter(torch.zeros(2, 1024))        # CPU tensors are rejected: there is no CPU path
+    with pytest.raises(ValueError):
+        ndns.si_snr(torch.zeros(2, 1024), torch.zeros(2, 1024))
