@@ -54,12 +54,21 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read().strip() == digest:
         return LIB
     nvcc = _nvcc()
-    objs = []
-    logs = []
-    for src in _sources():
+    srcs = _sources()
+
+    def compile_one(src):
         obj = os.path.join(LIBDIR, os.path.basename(src)[:-3] + ".o")
         cmd = [nvcc, *ARCH, *FLAGS, *_extra_flags(), "-c", src, "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
+        return src, obj, cmd, r
+
+    # one nvcc process per translation unit, side by side (the largest file bounds the build time)
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=min(len(srcs), os.cpu_count() or 1)) as pool:
+        results = list(pool.map(compile_one, srcs))
+    objs = []
+    logs = []
+    for src, obj, cmd, r in results:
         logs.append(f"$ {' '.join(cmd)}\n{r.stdout}{r.stderr}")
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}:\n{r.stdout}\n{r.stderr}")
