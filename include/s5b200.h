@@ -245,6 +245,15 @@ int s5b200_fxp_model_forward(const s5_fxp_model* m, const float* x, int32_t* y_i
 int s5b200_fxp_model_forward_int(const s5_fxp_model* m, const int32_t* x_int, int32_t* y_int, float* y_float,
                                  int B, int L, void* workspace, size_t workspace_bytes, int32_t* status_dev,
                                  void* stream);
+/* Global-batch parity when clips are sharded over GPUs (option B).  `compute_best` exponents are functions
+ * of float maxima over the WHOLE tensor a model sees (fxparray.py:420-448, 601-609), so a shard-local run is bit-exact with the
+ * reference run on that shard only.  With a sync function installed, every kernel that produced running maxima is followed by
+ * fn(user, maxima_dev, count, stream): the caller max-all-reduces `count` uint32 words in place (bit patterns of non-negative
+ * floats, so an integer max is the float max), stream-ordered - e.g. ncclAllReduce(ncclMax) / torch.distributed.all_reduce.
+ * 1 + 5 n_layers calls per forward (16 for NDNS); every rank then computes exactly what one process would on the union batch. */
+typedef void (*s5_fxp_sync_fn)(void* user, uint32_t* maxima_dev, int count, void* stream);
+int s5b200_fxp_model_set_maxima_sync(s5_fxp_model* m, s5_fxp_sync_fn fn, void* user);
+
 /* Intermediate tap after a forward: copies the named per-layer tensor out of the workspace for
  * verification (names follow the `sow` keys of fxpmodel.py).  tap ids: */
 enum s5_fxp_tap {

@@ -19,6 +19,7 @@ F32, I32 = 0, 1
 KERNEL_CLASSES = ["enc", "bproj", "scan_c64", "glu", "dec", "fxp_enc", "fxp_bn", "fxp_bproj", "scan_i32", "fxp_glu",
                   "fxp_resid", "fxp_dec", "other", "glu_scan", "block"]
 
+FXP_SYNC_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p)   # s5_fxp_sync_fn
 c_float_p = C.POINTER(C.c_float)
 c_int32_p = C.POINTER(C.c_int32)
 
@@ -137,6 +138,7 @@ PROTOTYPES = {
     "s5b200_reduce_workspace_bytes": (_SZ, [_I, _LL]),
     "s5b200_si_snr": (_I, [_V, _V, _I, _LL, _V, _V, _SZ, _V]),
     "s5b200_mse_clips": (_I, [_V, _V, _I, _LL, _V, _V, _SZ, _V]),
+    "s5b200_fxp_model_set_maxima_sync": (_I, [_V, _V, _V]),
     "s5b200_calibrate_sites": (_I, [_V]),
     "s5b200_model_calibrate": (_I, [_V, _V, _V, _V, _I, _I, _V, _SZ, _V]),
 }

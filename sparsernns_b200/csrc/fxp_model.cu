@@ -624,6 +624,8 @@ struct s5_fxp_model {
   s5_fxp_model_desc desc;
   s5::FxpDenseDev enc, dec;
   std::vector<s5::FxpLayerDev> layers;
+  s5_fxp_sync_fn sync = nullptr;   // global-batch parity under sharding: max-all-reduce of the running maxima (s5b200.h)
+  void* sync_user = nullptr;
 };
 
 namespace s5 {
@@ -673,6 +675,11 @@ static int fxp_run(const FxpRun& r, const void* x, bool x_is_float, int upto_lay
   int* g = reinterpret_cast<int*>(r.base + r.w.off_g);
   int* bu = reinterpret_cast<int*>(r.base + r.w.off_bu);
   int rc;
+  // Sharded runs with global-batch parity: every kernel that produced running maxima is followed by the caller's
+  // max-all-reduce over all blocks' maxima (max is idempotent, so reducing the whole region every time is exact).
+  auto sync_maxima = [&]() {
+    if (m->sync) m->sync(m->sync_user, r.fm(0), (int)((d.n_layers + 1) * kStateStride), r.st);
+  };
   S5_CUDA(cudaMemsetAsync(r.base + r.w.off_state, 0, r.w.state_ints * 4, r.st));
   {  // encoder FxpDense + fxp_relu (fxpmodel.py:1262-1266) + maxima for block 0
     const s5_fxp_dense_desc& q = m->enc.q;
@@ -685,6 +692,7 @@ static int fxp_run(const FxpRun& r, const void* x, bool x_is_float, int upto_lay
     p.status = r.status();
     S5_CUDA(cudaMemcpyAsync(r.ex(0) + E_IN, &m->enc.q.out_exp, sizeof(int), cudaMemcpyHostToDevice, r.st));
     if ((rc = launch_fxp_linear(p, r.st, S5_K_FXP_ENC))) return rc;
+    sync_maxima();
   }
   for (int li = 0; li <= upto_layer; ++li) {
     const FxpLayerDev& l = m->layers[li];
@@ -695,6 +703,7 @@ static int fxp_run(const FxpRun& r, const void* x, bool x_is_float, int upto_lay
       ProfScope prof(S5_K_FXP_BN, r.st);
       fxp_bn_reduce_kernel<<<ew_grid(n), 256, 0, r.st>>>(p);
       S5_LAUNCH_CHECK();
+      sync_maxima();
       return S5_OK;
     };
     if ((rc = reduce(1, 2))) return rc;
@@ -742,6 +751,7 @@ static int fxp_run(const FxpRun& r, const void* x, bool x_is_float, int upto_lay
       p.gl_bits = l.q.gate_l_bits; p.gl_exp = l.q.gate_l_exp; p.gr_bits = l.q.gate_r_bits; p.gr_exp = l.q.gate_r_exp;
       p.g_rs = l.q.gate_l_exp + l.q.gate_r_exp - l.q.gate_res_exp; p.g_bits = l.q.gate_res_bits; p.g_exp = l.q.gate_res_exp;
       if ((rc = launch_fxp_glu(p, r.st))) return rc;
+      sync_maxima();
     }
     if (stop_stage == 3 && li == upto_layer) { *cur_out = g; *other_out = a; return S5_OK; }
     {  // residual add (compute_best) + fxp_relu, maxima for the next block
@@ -756,6 +766,7 @@ static int fxp_run(const FxpRun& r, const void* x, bool x_is_float, int upto_lay
       ProfScope prof(S5_K_FXP_RESID, r.st);
       fxp_resid_kernel<<<ew_grid(n), 256, 0, r.st>>>(p);
       S5_LAUNCH_CHECK();
+      sync_maxima();
     }
     std::swap(a, b);
   }
@@ -786,6 +797,13 @@ static int fxp_forward_impl(const s5_fxp_model* m, const void* x, bool x_is_floa
 }
 
 }  // namespace s5
+
+extern "C" int s5b200_fxp_model_set_maxima_sync(s5_fxp_model* m, s5_fxp_sync_fn fn, void* user) {
+  if (!m) S5_FAIL(S5_E_BADARG, "fxp_model_set_maxima_sync: null model");
+  m->sync = fn;
+  m->sync_user = user;
+  return S5_OK;
+}
 
 extern "C" int s5b200_fxp_model_create(const s5_fxp_model_desc* d, s5_fxp_model** out) {
   using namespace s5;

@@ -61,7 +61,7 @@ class FxpRegressionModel:
     """fxpmodel.py:1380-1439 bound to one weight set; ``__call__`` is ``model(fxp_x)`` of fxprun.py:76."""
 
     def __init__(self, modeldict: dict, fxp_qconfig: dict, n_layers: int, step_rescale: float = 1.0,
-                 use_sparse: bool = True):
+                 use_sparse: bool = True, global_batch: bool = False, group=None):
         import torch
 
         if not torch.cuda.is_available():
@@ -87,6 +87,28 @@ class FxpRegressionModel:
         self.out_exp = fxp_qconfig["decoder"]["out_exp"]
         self.inp_bits = fxp_qconfig["encoder"]["inp_bits"]
         self.inp_exp = fxp_qconfig["encoder"]["inp_exp"]
+        self._sync_cb = None
+        if global_batch:
+            self._install_global_batch_sync(group)
+
+    def _install_global_batch_sync(self, group):
+        """Sharded clips, result bit-exact with ONE process on the union batch (SURVEY section 8e option B): the running float
+        maxima behind the ``compute_best`` exponents are max-all-reduced (NCCL) after every kernel that produces them."""
+        import torch.distributed as dist
+
+        if not (dist.is_available() and dist.is_initialized()):
+            raise _abi.S5Error("global_batch=True needs an initialised torch.distributed process group")
+        t = self._torch
+
+        def cb(_user, ptr, count, _stream):
+            ws = self._ws                                    # the maxima live in the caller-provided workspace
+            off = int(ptr) - ws.data_ptr()
+            view = ws[off:off + 4 * count].view(t.int32)      # bit patterns of non-negative floats: integer max == float max
+            dist.all_reduce(view, op=dist.ReduceOp.MAX, group=group)
+
+        self._sync_cb = _abi.FXP_SYNC_FN(cb)                  # keep the thunk alive as long as the handle
+        _abi.check(self._lib.s5b200_fxp_model_set_maxima_sync(self._handle, C.cast(self._sync_cb, C.c_void_p), None),
+                   "s5b200_fxp_model_set_maxima_sync")
 
     # ------------------------------------------------------------------ descriptor
     def _k(self, a: np.ndarray) -> np.ndarray:

@@ -218,3 +218,52 @@ def test_fxp_export_matches_oracle_and_writes_the_reference_files(cuda_device, f
     io = pickle.load(open(tmp_path / "fxpmodel_io.pkl", "rb"))
     assert np.array_equal(io["output"]["data"], y_ref.data) and np.array_equal(io["input"]["data"], xq.data.cpu().numpy())
     assert set(pickle.load(open(tmp_path / "fxpmodel.pkl", "rb"))) == {"params", "qconfig"}
+
+
+def _global_batch_worker(rank, world, port):
+    """One rank of test_fxp_global_batch_parity_two_gpus (module level: torch.multiprocessing.spawn pickles it)."""
+    import os
+    import torch
+    import torch.distributed as dist
+    from sparsernns_b200 import fxpmodel as PF
+    from sparsernns_b200.dist import shard_range
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        zoo = Z.build_sparse_calibrated(0.5, n_clips=4, n_frames=160)
+        md, q = Z.fxp_setup(zoo)
+        n_layers = zoo["dims"].n_layers
+        # clips of very different loudness: the shards' own maxima differ, so shard-local exponents differ from the union's
+        xn = zoo["x"].copy()
+        xn[2:] *= 0.05
+        x = torch.from_numpy(xn).cuda()
+        one = PF.FxpRegressionModel(md, q, n_layers)                         # ONE process on the union batch
+        y_full = one(one.quantize_input(x))
+        lo, hi = shard_range(4, rank, world)
+        glob = PF.FxpRegressionModel(md, q, n_layers, global_batch=True)     # sharded, maxima all-reduced over NCCL
+        y_g = glob(glob.quantize_input(x[lo:hi]))
+        assert y_g.exp == y_full.exp and torch.equal(y_g.data, y_full.data[lo:hi]), f"rank {rank}: global-batch parity"
+        for i in range(n_layers):
+            t_g, t_f = glob.tap(x_q := glob.quantize_input(x[lo:hi]), i, PF.TAP_OUTPUT), one.tap(one.quantize_input(x), i, PF.TAP_OUTPUT)
+            assert t_g.exp == t_f.exp and torch.equal(t_g.data, t_f.data[lo:hi]), f"rank {rank}: block {i} output"
+        local = PF.FxpRegressionModel(md, q, n_layers)                       # shard-local parity (the default)
+        y_l = local(local.quantize_input(x[lo:hi]))
+        differs = torch.tensor([int(not torch.equal(y_l.data, y_full.data[lo:hi]))], device="cuda")
+        dist.all_reduce(differs)
+        assert int(differs.item()) >= 1, "the test batch should make shard-local and global-batch results differ somewhere"
+    finally:
+        dist.destroy_process_group()
+
+
+def test_fxp_global_batch_parity_two_gpus(cuda_device):
+    """SURVEY 8e option B: clips sharded over 2 GPUs with the maxima all-reduced (NCCL) give, bit for bit, what one process gives
+    on the union batch - output and every block output; the default shard-local mode does not (and is not meant to)."""
+    import torch
+    import torch.multiprocessing as mp
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    mp.spawn(_global_batch_worker, args=(2, 29641), nprocs=2, join=True)
