@@ -334,6 +334,8 @@ def main():
         oh = [torch.empty(B, n_samp).pin_memory() for _ in range(2)]
         nch = 4 if B % 4 == 0 else 1                                       # clip chunks over two streams: copies overlap kernels
         streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+        # one handle per stream: a BoundModel owns ONE workspace (look-back flags included), so two forwards in flight need two
+        models = [model, BoundModel(cfg, {"params": params, "batch_stats": batch_stats})]
 
         def audio_step(i):
             for c in range(nch):
@@ -341,7 +343,7 @@ def main():
                     sl = slice(c * B // nch, (c + 1) * B // nch)
                     a = ah[i % 2][sl].to(dev, non_blocking=True)
                     mag, ph, xin = ndns.stft_splitter(a, blf=True, model_input=True)
-                    cleaned = ndns.stft_mixer(mag, ph, blf=True, mask=model(xin))
+                    cleaned = ndns.stft_mixer(mag, ph, blf=True, mask=models[c % 2](xin))
                     oh[i % 2][sl].copy_(cleaned, non_blocking=True)
 
         for i in range(2):

@@ -81,8 +81,8 @@ __global__ void __launch_bounds__(kF32Threads, 2) tc_f32_kernel(const __grid_con
   // accumulation steps), so with one M block there are TWO accumulators, one for the large hi x hi products and one for
   // the small cross terms, added in fp32 (round to nearest) in the epilogue: a third of the steps on the accumulator
   // that matters, still 256 TMEM columns = two CTAs per SM.
-  const int NACC = MB == 1 ? 2 : 1;
-  const uint32_t tmem_cols = MB <= 2 ? 256u : 512u;
+  const int NACC = MB <= 2 ? 2 : 1;                           // MB == 2 runs one CTA per SM (shared memory): all 512 columns are its own
+  const uint32_t tmem_cols = MB == 1 ? 256u : 512u;
   if (warp == 0) tc_alloc(&tmem_slot, tmem_cols);
   if (tid == 0) {
     mbar_init(&full[0], 1); mbar_init(&full[1], 1); mbar_init(&full[2], 1); mbar_init(&mdone[0], 1); mbar_init(&mdone[1], 1); mbar_init(&tdone, 1);
@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(kF32Threads, 2) tc_f32_kernel(const __grid_con
         for (int mb = 0; mb < MB; ++mb) {
           // one M block: the large products (hi x hi) go to accumulator 0, the two small cross terms to accumulator 1, issued
           // alternately so that back-to-back MMAs never target the same TMEM columns
-          const uint32_t d0 = taddr + 128u * mb, d1 = NACC == 2 ? d0 + 128u : d0;
+          const uint32_t d0 = taddr + 128u * mb, d1 = NACC == 2 ? d0 + 128u * MB : d0;
           const uint32_t wh = w0 + (uint32_t)(2 * mb) * kF32Plane, wl = wh + kF32Plane;
 #pragma unroll
           for (int j = 0; j < kF32KC / 8; ++j) {
@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(kF32Threads, 2) tc_f32_kernel(const __grid_con
       tc_wait_ld();
       if (NACC == 2) {                                        // second accumulator (the small cross terms)
         uint32_t acc2[32];
-        tc_ld32(taddr + ((uint32_t)(32 * q4) << 16) + (uint32_t)(128 + 32 * rc), acc2);
+        tc_ld32(taddr + ((uint32_t)(32 * q4) << 16) + (uint32_t)(128 * MB + 128 * mb + 32 * rc), acc2);
         tc_wait_ld();
 #pragma unroll
         for (int j = 0; j < 32; ++j) acc[j] = __float_as_uint(__uint_as_float(acc[j]) + __uint_as_float(acc2[j]));

@@ -123,7 +123,11 @@ def _fp(a: np.ndarray):
 
 
 class BoundModel:
-    """A model handle bound to one weight set (the product of ``model.apply`` with fixed variables)."""
+    """A model handle bound to one weight set (the product of ``model.apply`` with fixed variables).
+
+    The handle owns ONE device workspace (activations, look-back flags and records), sized on demand: calls on the same
+    instance must be stream-ordered.  For forwards in flight on several streams use one ``BoundModel`` per stream (the C
+    handle itself is immutable and could be shared; the workspace cannot)."""
 
     def __init__(self, cfg: S5Config, variables: dict):
         import torch  # device memory / stream plumbing only

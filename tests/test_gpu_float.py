@@ -308,7 +308,23 @@ def test_block_kernel_is_bit_reproducible_and_batch_invariant(cuda_device, zoo, 
 
 
 
-def test_gpu_calibration_matches_oracle(cuda_device):
+@pytest.mark.parametrize("tc_min_rows", ["1", "1000000000"], ids=["dense_tile_3xtf32", "cuda_cores"])
+def test_float_model_dim_scale_1_matches_oracle(cuda_device, zoo_wide, tc_min_rows, monkeypatch):
+    """Float flavour at H 192, P 128: two M blocks per product on the 3 x TF32 path, and the CUDA-core path."""
+    import torch
+
+    monkeypatch.setenv("S5B200_TC_MIN_ROWS", tc_min_rows)
+    m, var = _bound(zoo_wide, static=False, relufication=True)
+    x = torch.from_numpy(zoo_wide["x"]).to(cuda_device)
+    got = m(x).cpu().numpy()
+    ocfg = Z.oracle_cfg(zoo_wide["dims"], relufication=True, static_quant=False, associative_scan=True)
+    e = relerr(got, OM.model_forward(zoo_wide["x"], var, ocfg, dtype=np.float64))
+    print(f"float model dim_scale 1.0 ({tc_min_rows}): cuda vs f64 {e:.2e}")
+    assert e <= TOL_F32
+
+
+@pytest.mark.parametrize("dim_scale", [0.5, 1.0])
+def test_gpu_calibration_matches_oracle(cuda_device, dim_scale):
     """s5b200_model_calibrate + host scale derivation against the oracle's one-batch calibration: every
     observer within 1e-5 of the tensor's range, every power-of-two scale EQUAL, and the static model built from the GPU
     calibration bit-identical to the one built from the oracle's."""
@@ -317,7 +333,7 @@ def test_gpu_calibration_matches_oracle(cuda_device):
     from sparsernns_b200 import synth
     from sparsernns_b200.model import BoundModel, S5Config
 
-    zoo = Z.build_sparse_calibrated(0.5, n_clips=2, n_frames=280)
+    zoo = Z.build_sparse_calibrated(dim_scale, n_clips=2, n_frames=280)
     d = zoo["dims"]
     cfg = S5Config(n_layers=d.n_layers, d_model=d.d_model, ssm_size=d.ssm_size, relufication=True, quantization="w8a16")
     x = torch.from_numpy(zoo["x"]).to(cuda_device)
