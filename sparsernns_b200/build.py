@@ -47,17 +47,43 @@ def _digest() -> str:
     return h.hexdigest()
 
 
+def _up_to_date(stamp: str, digest: str) -> bool:
+    try:
+        with open(stamp) as f:
+            return os.path.exists(LIB) and f.read().strip() == digest
+    except OSError:
+        return False
+
+
 def build_library(force: bool = False, verbose: bool = False) -> str:
+    """Build (or reuse) the library.  Safe to call from several processes at once (one rank per GPU under torchrun):
+    the build runs under an exclusive file lock, objects go to a per-process directory, and the .so and its stamp are
+    moved into place with os.replace, so nobody can dlopen a half-written file."""
+    import fcntl
+
     os.makedirs(LIBDIR, exist_ok=True)
     stamp = os.path.join(LIBDIR, "build.stamp")
     digest = _digest()
-    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read().strip() == digest:
+    if not force and _up_to_date(stamp, digest):
         return LIB
+    with open(os.path.join(LIBDIR, "build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and _up_to_date(stamp, digest):      # another process built it while we waited
+                return LIB
+            return _build_locked(stamp, digest, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(stamp: str, digest: str, verbose: bool) -> str:
     nvcc = _nvcc()
+    objdir = os.path.join(LIBDIR, f"obj.{os.getpid()}")
+    os.makedirs(objdir, exist_ok=True)
     srcs = _sources()
 
     def compile_one(src):
-        obj = os.path.join(LIBDIR, os.path.basename(src)[:-3] + ".o")
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
         cmd = [nvcc, *ARCH, *FLAGS, *_extra_flags(), "-c", src, "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         return src, obj, cmd, r
@@ -73,14 +99,21 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}:\n{r.stdout}\n{r.stderr}")
         objs.append(obj)
-    cmd = [nvcc, *ARCH, "-shared", "-o", LIB, *objs]
+    tmp_lib = os.path.join(objdir, "libs5b200.so")
+    cmd = [nvcc, *ARCH, "-shared", "-o", tmp_lib, *objs]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
     with open(os.path.join(LIBDIR, "build.log"), "w") as f:
         f.write("\n".join(logs))
-    with open(stamp, "w") as f:
+    if os.path.exists(stamp):
+        os.remove(stamp)                                       # never a new .so beside an old stamp or vice versa
+    os.replace(tmp_lib, LIB)
+    tmp_stamp = os.path.join(objdir, "build.stamp")
+    with open(tmp_stamp, "w") as f:
         f.write(digest)
+    os.replace(tmp_stamp, stamp)
+    shutil.rmtree(objdir, ignore_errors=True)
     if verbose:
         print("\n".join(logs))
     return LIB
