@@ -258,7 +258,7 @@ int s5b200_fxp_model_set_maxima_sync(s5_fxp_model* m, s5_fxp_sync_fn fn, void* u
  * verification (names follow the `sow` keys of fxpmodel.py).  tap ids: */
 enum s5_fxp_tap {
   S5_TAP_LAYER_INPUT = 0,  /* "ssm_input"  int32 [B][L][H]  + exponent */
-  S5_TAP_PRE_S5 = 1,       /* "pre_s5" (u after change_cfg) int32 [B][L][H] */
+  S5_TAP_PRE_S5 = 1,       /* the mixer input u = change_cfg("pre_s5") (fxpmodel.py:620-624) int32 [B][L][H] + exponent */
   S5_TAP_XS = 2,           /* "xs_relu"  int32 [B][L][P][2] interleaved (re, im) */
   S5_TAP_POST_GLU = 3,     /* "post_GLU" int32 [B][L][H] */
   S5_TAP_OUTPUT = 4        /* "output"   int32 [B][L][H] + exponent */

@@ -29,14 +29,19 @@ def calculate_qparams(minval, maxval, precision: int, pow2scale: bool = True, ep
 
 
 def quantdequant(x, scale, precision: int, dtype=F32):
-    """quantization.py:386-400 with zero_point = 0: clip(round(x/s), -2^(b-1), 2^(b-1)-1) * s."""
+    """quantization.py:386-400 with zero_point = 0: xdq = clip(round(x/s), -2^(b-1), 2^(b-1)-1) * s, returned through the
+    straight-through form ``x + stop_gradient(xdq - x)`` (:398-399).  In floating point that sum IS xdq whenever
+    xdq / 2 <= x <= 2 xdq (Sterbenz: the difference is exact) and, beyond that, as long as ulp(x) <= scale; only an
+    outlier more than 2^23 scales away from zero comes back within one ulp(x) of xdq instead of on the grid (pinned by
+    tests/test_oracle_vs_reference.py::test_quantdequant_and_qparams_bit_exact)."""
     x = np.asarray(x, dtype=dtype)
     s = dtype(scale)
     qmin = -(2 ** (precision - 1))
     qmax = 2 ** (precision - 1) - 1
     xq = np.round(x / s)
     xq = np.clip(xq, qmin, qmax)
-    return (xq * s).astype(dtype)
+    xdq = (xq * s).astype(dtype)
+    return (x + (xdq - x).astype(dtype)).astype(dtype)
 
 
 def quant_int(x, scale, precision: int):

@@ -17,14 +17,19 @@ void set_error(const char* fmt, ...) {
 
 long long& launch_counter() { return g_launches; }
 
+// SM count of the current device.  If the query fails the error is recorded (s5b200_last_error) and 1 is returned: every
+// grid sized from it stays valid - in particular a cooperative launch can never be over-subscribed by a guess - and the
+// caller's next CUDA call reports the underlying failure.
 int sm_count() {
   static thread_local int cached_dev = -1, cached = 0;
   int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) { set_error("sm_count: cudaGetDevice: %s", cudaGetErrorString(e)); return 1; }
   if (dev != cached_dev) {
-    cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return 148;
-    cached = prop.multiProcessorCount;
+    int n = 0;
+    e = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess || n < 1) { set_error("sm_count: cudaDeviceGetAttribute: %s", cudaGetErrorString(e)); return 1; }
+    cached = n;
     cached_dev = dev;
   }
   return cached;

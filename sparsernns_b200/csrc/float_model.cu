@@ -471,7 +471,7 @@ static TcGluArgs glu_args(const s5_model* m, const LayerDev& ld, const BlockPlan
 
 // One S5 block: x [rows][H] -> out [rows][H]; bu is the [rows][P] complex scratch (Bu, then xs in place).
 static int run_block(const s5_model* m, int li, const float* x, float* out, float* bu, int B, int L, void* scan_ws,
-                     size_t scan_ws_bytes, bool bn, bool ssm_only, cudaStream_t st, bool want_xs = false) {
+                     size_t scan_ws_bytes, bool bn, bool ssm_only, cudaStream_t st, bool want_xs = false, bool unfused = false) {
   const LayerDev& ld = m->layers[li];
   const long long rows = (long long)B * L;
   int rc;
@@ -493,7 +493,8 @@ static int run_block(const s5_model* m, int li, const float* x, float* out, floa
     o.X = out; o.Y = out; o.rows = rows; o.epi = 2; o.bias = ld.o_bias; o.X1 = out; o.SKIP = x; o.relu = m->desc.relufication;
     return tc_f32_launch(ld.fo, o, S5_K_GLU, st);
   }
-  const BlockPlan bp = block_plan(m, ld, rows, ssm_only, want_xs);
+  BlockPlan bp = block_plan(m, ld, rows, ssm_only, want_xs);
+  if (unfused) bp.fuse_scan = bp.fuse_bproj = false;          // retry after a refused cooperative launch
   if (bp.fuse_bproj) {
     // nothing to launch here
   } else if (sq && ld.tb.ok && rows >= m->tc_min_rows && is_pow2(ld.sc.s_ut) && is_pow2(ld.sc.s_But_re) && is_pow2(ld.sc.s_But_im)) {
@@ -504,7 +505,14 @@ static int run_block(const s5_model* m, int li, const float* x, float* out, floa
       return rc;
   } else if ((rc = launch_linear(bproj_params(m, ld, x, bu, rows, bn), st, S5_K_BPROJ))) return rc;
   if (!bp.fuse_scan && (rc = launch_scan_c64(bu, ld.lam, bu, B, L, m->desc.P, m->desc.relufication, scan_ws, scan_ws_bytes, st))) return rc;
-  if (bp.glu_tc) return tc_glu_launch(ld.tg, glu_args(m, ld, bp, x, out, bu, B, L, scan_ws, scan_ws_bytes, bn), st);
+  if (bp.glu_tc) {
+    rc = tc_glu_launch(ld.tg, glu_args(m, ld, bp, x, out, bu, B, L, scan_ws, scan_ws_bytes, bn), st);
+    // the fused recurrence needs a cooperative launch; where the device refuses it (SM limit under MPS, ...) the
+    // separate B projection | scan_c64 | GLU kernels compute the same block
+    if (rc == kCoopRefused && bp.fuse_scan && !unfused)
+      return run_block(m, li, x, out, bu, B, L, scan_ws, scan_ws_bytes, bn, ssm_only, st, want_xs, true);
+    return rc;
+  }
   return launch_glu(glu_params(m, ld, bu, x, out, rows, bn, ssm_only), st);
 }
 
@@ -633,6 +641,12 @@ extern "C" int s5b200_model_create(const s5_model_desc* d, s5_model** out) {
     if ((rc = upload(l.bn_mul_host, H, &ld.bn_mul))) return fail(rc);
     if ((rc = upload(l.bn_bias_host, H, &ld.bn_bias))) return fail(rc);
     if ((rc = upload(l.out2_bias_host, H, &ld.o_bias))) return fail(rc);
+    if (d->flavour == S5_STATIC && ld.tg.ok) {
+      // the block kernel's per-layer image is built here, once, so that the forward neither allocates, synchronises
+      // nor touches the handle (run_block and the single launch pass exactly these vectors and scales)
+      const BlockPlan all{true, true, true};
+      if ((rc = tc_glu_prepare_image(ld.tg, glu_args(m, ld, all, nullptr, nullptr, nullptr, 1, 1, nullptr, 0, true)))) return fail(rc);
+    }
   }
   *out = m;
   return S5_OK;
@@ -703,15 +717,20 @@ extern "C" int s5b200_model_forward(const s5_model* m, const float* x, float* y,
     const size_t glu_ws = round_up(tc_glu_scan_workspace_bytes(B, L, d.P), 256);
     const TcGluDev* devs[4];
     TcGluArgs args[4];
+    float *pa = a, *pb = b;
     for (int i = 0; i < d.n_layers; ++i) {
       const LayerDev& ld = m->layers[i];
       devs[i] = &ld.tg;
-      args[i] = glu_args(m, ld, block_plan(m, ld, rows, false, false), a, b, bu, B, L, base + w.off_scan + (size_t)i * glu_ws, glu_ws, true);
-      std::swap(a, b);
+      args[i] = glu_args(m, ld, block_plan(m, ld, rows, false, false), pa, pb, bu, B, L, base + w.off_scan + (size_t)i * glu_ws, glu_ws, true);
+      std::swap(pa, pb);
     }
-    if ((rc = tc_glu_launch_multi(devs, args, d.n_layers, reinterpret_cast<uint32_t*>(base + w.off_scan + (size_t)d.n_layers * glu_ws),
-                                  glu_ws, st))) return rc;
-  } else {
+    rc = tc_glu_launch_multi(devs, args, d.n_layers, reinterpret_cast<uint32_t*>(base + w.off_scan + (size_t)d.n_layers * glu_ws),
+                             glu_ws, st);
+    if (rc == kCoopRefused) one_launch = false;               // per-block launches below (each falls back further on its own)
+    else if (rc) return rc;
+    else { a = pa; b = pb; }
+  }
+  if (!one_launch) {
     for (int i = 0; i < d.n_layers; ++i) {
       if ((rc = run_block(m, i, a, b, bu, B, L, base + w.off_scan, w.scan_bytes, true, false, st))) return rc;
       std::swap(a, b);

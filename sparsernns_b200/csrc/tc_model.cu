@@ -1987,8 +1987,25 @@ static int tc_glu_go_multi(const TcGluMulti& mp, size_t smem, int grid, cudaStre
     // A cooperative launch guarantees exactly that (grid <= SM count, 1 CTA per SM); with a plain launch two such
     // kernels on different streams (the host pipeline runs two forward streams) could each become partially resident
     // and wait for their own unscheduled CTAs forever.
+    // The grid is clamped to what the device can keep resident for THIS shared-memory size (an MPS SM limit or another
+    // carve-out can make that less than one CTA per SM; the round-robin tile schedule works for any grid).  If the
+    // launch is refused all the same, kCoopRefused tells the caller to run the unfused kernels instead.
+    int per_sm = 0;
+    S5_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kGluThreads, smem));
+    if (const char* e = getenv("S5B200_TEST_REFUSE_COOP")) per_sm = atoi(e) ? 0 : per_sm;   // test hook for the fallback
+    if (per_sm < 1) {
+      set_error("dense-tile block kernel: no CTA fits an SM with %zu bytes of shared memory", smem);
+      return kCoopRefused;
+    }
+    grid = std::min(grid, sm_count());                       // one CTA per SM: the two tile pipelines share its weights
     void* args[] = {const_cast<TcGluMulti*>(&mp)};
-    S5_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(kernel), dim3(grid), dim3(kGluThreads), args, smem, st));
+    const cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(kernel), dim3(grid), dim3(kGluThreads), args, smem, st);
+    if (e == cudaErrorCooperativeLaunchTooLarge || e == cudaErrorLaunchOutOfResources) {
+      (void)cudaGetLastError();                               // not sticky: clear it, the fallback launches next
+      set_error("dense-tile block kernel: cooperative launch of %d CTAs refused (%s)", grid, cudaGetErrorString(e));
+      return kCoopRefused;
+    }
+    S5_CUDA(e);
   } else {
     kernel<<<grid, kGluThreads, smem, st>>>(mp);
   }
@@ -2034,6 +2051,26 @@ static int tc_glu_ensure_image(const TcGluDev& d, TcGluParams* p, cudaStream_t s
   p->img = reinterpret_cast<const unsigned char*>(d.img);
   p->img_bytes = (uint32_t)bytes;
   return S5_OK;
+}
+
+// Builds the block kernel's image for the scales / per-column vectors the model will use, at model-create time (the
+// forward then finds a matching key: no allocation, no synchronisation and no handle mutation on the hot path, which
+// also keeps it capturable in a CUDA graph).  Only the image-relevant fields of `a` are read.
+int tc_glu_prepare_image(const TcGluDev& d, const TcGluArgs& a) {
+  if (!d.ok || !d.bpj_ok || !tc_glu_scan_ok(d) || !is_pow2(a.s_ut) || !is_pow2(a.s_yt) || !is_pow2(a.s_o_out) || !is_pow2(a.s_bu_re) ||
+      !is_pow2(a.s_bu_im))
+    return S5_OK;                                             // this layer never runs the block kernel
+  TcGluParams p{};
+  p.H = d.H; p.K1 = d.K1;
+  p.Wc = reinterpret_cast<const __nv_bfloat16*>(d.Wc); p.Wo = reinterpret_cast<const signed char*>(d.Wo);
+  p.xs_odd_mul = d.xs_odd_mul; p.c_scale = d.c_scale; p.o_col_scale = d.o_col_scale;
+  p.bn_sub = a.bn_sub; p.bn_mul = a.bn_mul; p.bn_add = a.bn_add; p.D = a.D; p.o_bias = a.o_bias;
+  p.ut_s = a.s_ut; p.ut_inv = 1.f / a.s_ut; p.yt_s = a.s_yt; p.yt_inv = 1.f / a.s_yt; p.oa_inv = 1.f / a.s_o_act;
+  p.oo_s = a.s_o_out; p.oo_inv = 1.f / a.s_o_out; p.gl_s = a.s_gl; p.gl_inv = 1.f / a.s_gl; p.gr_s = a.s_gr; p.gr_inv = 1.f / a.s_gr;
+  p.qs_min = a.qs_min; p.qs_max = a.qs_max; p.qn_min = a.qn_min; p.qn_max = a.qn_max; p.relu_out = a.relu_out;
+  p.WB = reinterpret_cast<const signed char*>(d.WB); p.b_col_scale = d.b_col_scale;
+  p.b_out_scale0 = a.s_bu_re; p.b_out_scale1 = a.s_bu_im; p.b_out_inv0 = 1.f / a.s_bu_re; p.b_out_inv1 = 1.f / a.s_bu_im;
+  return tc_glu_ensure_image(d, &p, nullptr);
 }
 
 // fills the kernel parameters of one layer; *grid_out = grid size this layer alone would use

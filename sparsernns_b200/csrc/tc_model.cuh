@@ -23,7 +23,8 @@ struct TcGluDev {
   bool ok = false;
   // wide form (H > 128 or 2P > 128, e.g. dim_scale 1.0): C in 64-column chunks of the operand layout, out2 in the wide K order
   bool wide_ok = false; size_t smem_wide = 0;
-  // block kernel: the layer's shared-memory image in global memory, built on first use (tc_model.cu:tc_glu_ensure_image)
+  // block kernel: the layer's shared-memory image in global memory, built by tc_glu_prepare_image at model-create time
+  // (rebuilt by tc_glu_ensure_image only if a caller passes other scales / vectors than the ones prepared)
   mutable void* img = nullptr; mutable bool img_ok = false; mutable unsigned char img_key[160] = {};
 };
 struct TcGluArgs {
@@ -36,11 +37,16 @@ struct TcGluArgs {
   bool fuse_bproj = false; float s_bu_re = 0.f, s_bu_im = 0.f;
 };
 
+// returned by tc_glu_launch / tc_glu_launch_multi when the device refuses the cooperative launch of the fused
+// recurrence (the error text is set); the caller then runs the unfused kernels
+constexpr int kCoopRefused = -100;
+
 bool is_pow2(float s);
 float pow2_grid(const float* w, size_t n, size_t start, size_t stride);
 int tc_glu_build(const float* C_tilde, const float* out2_kernel, int H, int P, float conj_mul, float s_o_act, const float* B_bar,
                  float s_ut, TcGluDev* out);
 void tc_glu_free(TcGluDev* d);
+int tc_glu_prepare_image(const TcGluDev& d, const TcGluArgs& a);
 int tc_glu_launch(const TcGluDev& d, const TcGluArgs& a, cudaStream_t st);
 bool tc_glu_scan_ok(const TcGluDev& d);
 int tc_glu_launch_multi(const TcGluDev* const* devs, const TcGluArgs* args, int n, uint32_t* done, size_t done_bytes, cudaStream_t st);

@@ -221,8 +221,10 @@ class FxpRegressionModel:
     def export(self, fxp_x=None) -> dict:
         """``FxpRegressionModel.export()`` (fxpmodel.py:1441-1458): ``dict(params, qconfig, intermediates)`` with the
         reference's nesting (encoder / layers_i / mixer | out2 | norm, decoder).  Integer payloads are NumPy int32 arrays.
-        ``intermediates`` holds what the library can tap after a forward on ``fxp_x``: per block ``ssm_input``, ``pre_s5``,
-        ``post_GLU``, ``output`` and ``mixer/xs_relu``, plus ``encoder/pre_encoder`` and ``decoder/__call__``; every entry is
+        ``intermediates`` holds what the library can tap after a forward on ``fxp_x``: per block ``ssm_input``,
+        ``post_GLU``, ``output``, ``mixer/xs_relu`` and ``mixer/u`` (the mixer's input AFTER its change_cfg to the ``u``
+        format, fxpmodel.py:620-624 - the reference sows the value before that step as ``pre_s5`` and has no key for this
+        one), plus ``encoder/pre_encoder`` and ``decoder/__call__``; every entry is
         ``dict(data, bits, exp, signed)`` (the reference pickles ``FxpArray`` objects, whose class lives in its own
         package; the fields are the same)."""
         out = dict(params=self._export["params"], qconfig=self._export["qconfig"], intermediates={})
@@ -230,9 +232,9 @@ class FxpRegressionModel:
             fa = lambda t: dict(data=t.data.cpu().numpy(), bits=t.bits, exp=t.exp, signed=True)
             enc = {"encoder": {"pre_encoder": fa(fxp_x)}}
             for i in range(self.n_layers):
-                enc[f"layers_{i}"] = dict(ssm_input=fa(self.tap(fxp_x, i, TAP_LAYER_INPUT)), pre_s5=fa(self.tap(fxp_x, i, TAP_PRE_S5)),
+                enc[f"layers_{i}"] = dict(ssm_input=fa(self.tap(fxp_x, i, TAP_LAYER_INPUT)),
                                           post_GLU=fa(self.tap(fxp_x, i, TAP_POST_GLU)), output=fa(self.tap(fxp_x, i, TAP_OUTPUT)),
-                                          mixer=dict(xs_relu=fa(self.tap(fxp_x, i, TAP_XS))))
+                                          mixer=dict(xs_relu=fa(self.tap(fxp_x, i, TAP_XS)), u=fa(self.tap(fxp_x, i, TAP_PRE_S5))))
             out["intermediates"] = dict(encoder=enc, decoder={"__call__": fa(self(fxp_x))})
         return out
 

@@ -292,12 +292,27 @@ class BoundModel:
         after enqueueing and ``out`` is complete after the current stream has been synchronised; keep ``x_host`` and
         ``out`` alive (and unmodified) until then.  Back-to-back calls then overlap across batches."""
         t = self._torch
-        if not (isinstance(x_host, t.Tensor) and not x_host.is_cuda and x_host.dtype == t.float32 and x_host.dim() == 3):
-            raise ValueError("expected a float32 CPU tensor of shape (B, L, d_input)")
-        x_host = x_host.contiguous()
+        cfg = self.cfg
+        if not (isinstance(x_host, t.Tensor) and not x_host.is_cuda and x_host.dtype == t.float32 and x_host.dim() == 3
+                and x_host.shape[-1] == cfg.d_input):
+            raise ValueError(f"expected a float32 CPU tensor of shape (B, L, {cfg.d_input})")
+        if not x_host.is_contiguous():
+            if not sync:
+                # a temporary contiguous copy would be freed while the H2D copies are still queued
+                raise ValueError("forward_host(sync=False) needs a contiguous input (it is read after the call returns)")
+            x_host = x_host.contiguous()
         B, L, _ = x_host.shape
         if out is None:
-            out = t.empty((B, L, self.cfg.d_output), dtype=t.float32, pin_memory=True)
+            out = t.empty((B, L, cfg.d_output), dtype=t.float32, pin_memory=True)
+        elif not (isinstance(out, t.Tensor) and not out.is_cuda and out.dtype == t.float32 and out.is_contiguous()
+                  and tuple(out.shape) == (B, L, cfg.d_output)):
+            raise ValueError(f"out must be a contiguous float32 CPU tensor of shape ({B}, {L}, {cfg.d_output})")
+        if not sync and not (x_host.is_pinned() and out.is_pinned()):
+            # cudaMemcpyAsync from / to pageable memory is staged synchronously by the driver: still correct, but the call
+            # then blocks; say so instead of silently losing the overlap
+            import warnings
+            warnings.warn("forward_host(sync=False) with pageable host buffers: copies are not asynchronous; pin both "
+                          "buffers (tensor.pin_memory()) for stream-ordered overlap", RuntimeWarning, stacklevel=2)
         fn = self._lib.s5b200_model_forward_host if sync else self._lib.s5b200_model_forward_host_async
         _abi.check(fn(self._handle, x_host.data_ptr(), out.data_ptr(), B, L, self._stream()), "s5b200_model_forward_host")
         return out

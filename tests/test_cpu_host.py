@@ -200,3 +200,27 @@ def test_ndns_and_calibrate_fail_loudly_without_cuda():
         ndns.stft_splitter(torch.zeros(2, 1024))        # CPU tensors are rejected: there is no CPU path
     with pytest.raises(ValueError):
         ndns.si_snr(torch.zeros(2, 1024), torch.zeros(2, 1024))
+
+
+def test_product_fxputils_equals_the_reference_qconfig():
+    """sparsernns_b200.fxputils against the qconfig the reference's own fxputils.py produced on the golden models
+    (tests/golden/reference_fxp_model.npz, see tests/golden/make_reference_golden.py): shared and per-layer exponents."""
+    import json
+    from sparsernns_b200 import fxputils as PU
+    from sparsernns_b200.checkpoint import load_npz
+
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    with np.load(os.path.join(gold, "reference_fxp_model.npz")) as z:
+        ref = {k: json.loads(str(z[f"{k}/qconfig_json"])) for k in ("A", "C", "E")}
+
+    def plain(t):      # the informational sign-bit entries (never read by the model) are not carried by the product
+        if isinstance(t, dict):
+            return {str(k): plain(v) for k, v in t.items() if not (str(k).endswith("signbit") or str(k).endswith("signbits"))}
+        if isinstance(t, (np.ndarray, np.generic)):
+            return np.asarray(t).tolist()
+        return t
+
+    for case, ds, shared in (("A", 0.5, True), ("C", 0.5, False), ("E", 1.0, True)):
+        tree = load_npz(os.path.join(gold, f"ndns_ds{ds}_sparse_w8a16.npz"))
+        q = PU.create_fxp_qconfig(PU.load_modeldict(tree["params"], tree["cal_stats"]), "w8a16", shared_exp=shared)
+        assert plain(q) == plain(ref[case]), case

@@ -448,3 +448,21 @@ def test_static_ssm_states_long_clip_match_oracle(cuda_device, zoo_long, monkeyp
     assert relerr(y.cpu().numpy(), t0["output"]) <= TOL_W8A16
     y_fused = m.layer(0, h)
     assert relerr(y_fused.cpu().numpy(), y.cpu().numpy()) <= TOL_W8A16
+
+
+def test_refused_cooperative_launch_falls_back_to_unfused_kernels(cuda_device, zoo, monkeypatch):
+    """The fused recurrence needs a cooperative launch.  Where the device refuses it (S5B200_TEST_REFUSE_COOP simulates
+    an SM limit) the model and layer entry points run the unfused kernels: same result as S5B200_FUSE_SCAN=0."""
+    import torch
+
+    monkeypatch.setenv("S5B200_TC_MIN_ROWS", "1")
+    x = torch.from_numpy(zoo["x"]).to(cuda_device)
+    monkeypatch.setenv("S5B200_FUSE_SCAN", "0")
+    m0, _ = _bound(zoo, static=True, relufication=True)
+    y0 = m0(x)
+    monkeypatch.delenv("S5B200_FUSE_SCAN")
+    monkeypatch.setenv("S5B200_TEST_REFUSE_COOP", "1")
+    m1, _ = _bound(zoo, static=True, relufication=True)
+    assert torch.equal(m1(x), y0)
+    h = torch.relu(torch.randn(2, 300, zoo["dims"].d_model, device=cuda_device))
+    assert torch.equal(m1.layer(1, h), m0.layer(1, h))
