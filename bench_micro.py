@@ -41,6 +41,7 @@ def main():
     ap.add_argument("--out", default=None)
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--reps", type=int, default=9)
+    ap.add_argument("--only", default=None, help="comma-separated kernel names (scan_c64, scan_i32, spmm_f32, pcie)")
     args = ap.parse_args()
 
     import torch
@@ -81,20 +82,29 @@ def main():
 
     # ---- complex scan: 16 bytes per state-step (8 in, 8 out)
     def scan_c64(B, L, P):
-        Bu = torch.randn(B, L, P, 2, device=dev)
-        out = torch.empty_like(Bu)
+        by = 16.0 * B * L * P
+        # small problems: several buffer sets (together larger than L2) so that launches can also be timed back to back
+        nbuf = 1 if by > 1e9 else int(min(8, max(2, -(-400e6 // by))))
+        Bu = [torch.randn(B, L, P, 2, device=dev) for _ in range(nbuf)]
+        out = [torch.empty_like(Bu[0]) for _ in range(nbuf)]
         lam = torch.from_numpy(lam_of(P)).to(dev)
         wsb = lib.s5b200_scan_c64_workspace_bytes(B, L, P)
-        ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+        ws = [torch.empty(wsb, dtype=torch.uint8, device=dev) for _ in range(nbuf)]
 
-        def fn():
-            _abi.check(lib.s5b200_scan_c64(Bu.data_ptr(), lam.data_ptr(), out.data_ptr(), B, L, P, 0, ws.data_ptr(), wsb, st),
+        def one(i):
+            _abi.check(lib.s5b200_scan_c64(Bu[i].data_ptr(), lam.data_ptr(), out[i].data_ptr(), B, L, P, 0, ws[i].data_ptr(), wsb, st),
                        "scan_c64")
 
-        ms = timed(fn, args.reps)
-        by = 16.0 * B * L * P
-        emit({"kernel": "scan_c64", "B": B, "L": L, "P": P, "us": ms * 1e3, "alg_bytes": by, "gbs": by / ms / 1e6,
-              "frac": by / ms / 1e6 / peak, "state_steps_per_s": B * L * P / ms * 1e3})
+        ms = timed(lambda: one(0), args.reps)
+        rec = {"kernel": "scan_c64", "B": B, "L": L, "P": P, "us": ms * 1e3, "alg_bytes": by, "gbs": by / ms / 1e6,
+               "frac": by / ms / 1e6 / peak, "state_steps_per_s": B * L * P / ms * 1e3}
+        if nbuf > 1:
+            # the same launch repeated over `nbuf` distinct buffer sets inside ONE event pair: launch latency overlaps the
+            # previous kernel, as it does inside the model; every launch still reads data that is not in L2
+            msb = timed(lambda: [one(i) for i in range(nbuf)], args.reps) / nbuf
+            rec.update({"us_back_to_back": msb * 1e3, "gbs_back_to_back": by / msb / 1e6, "frac_back_to_back": by / msb / 1e6 / peak,
+                        "buffers": nbuf})
+        emit(rec)
 
     # ---- integer scan (planar int32), 16 bytes per state-step
     def scan_i32(B, L, P):
@@ -173,6 +183,10 @@ def main():
         emit({"kernel": "pcie", "bytes_each_way": by, "h2d_ms": a, "h2d_gbs": by / a / 1e6, "d2h_ms": b, "d2h_gbs": by / b / 1e6,
               "both_ms": c, "both_gbs_each_way": by / c / 1e6, "e2e_ceiling_frames_per_s": 32 * 3751 / c * 1e3})
 
+    only = set(args.only.split(",")) if args.only else None
+    if only is not None:   # run just the named sweeps
+        keep = lambda f, name: f if name in only else (lambda *a, **k: None)
+        pcie, scan_c64, scan_i32, spmm = keep(pcie, "pcie"), keep(scan_c64, "scan_c64"), keep(scan_i32, "scan_i32"), keep(spmm, "spmm_f32")
     emit({"hbm_peak_gbs": peak, "peak_source": peak_src, "device": torch.cuda.get_device_name(0)})
     pcie()
     if args.quick:

@@ -1,41 +1,26 @@
 // scan.cu - diagonal linear recurrences of the S5 SSM.
 //
 //  (1) scan_c64: x_k = lam * x_{k-1} + Bu_k in complex64, replacing jax.lax.associative_scan /
-//      jax.lax.scan (reference sparseRNNs/model/ssm.py:127, :150, :313).  Single pass over HBM:
-//      each CTA owns one time chunk [TL][P] of one clip, brought in by one 1-D bulk async copy (TMA
-//      engine, UBLKCP) and written back by one bulk store.  Inside the chunk every thread owns one
-//      state p of one sub-chunk of T consecutive steps; sub-chunk and chunk carries are combined with
-//      Horner steps on lam^T / lam^TL, the cross-chunk carry travels through a decoupled look-back
-//      (aggregate / inclusive records + flags in a caller-provided workspace).
+//      jax.lax.scan (reference sparseRNNs/model/ssm.py:127, :150, :313).  One CTA per (clip, time
+//      segment), one thread per state; the segment streams through a ring of shared-memory tiles
+//      filled by 1-D bulk async copies (TMA engine, UBLKCP) and drained by bulk stores.  Throughput
+//      batches are a pure single-pass stream (98-103 % of the measured HBM copy peak at batch 4096);
+//      few clips are cut into segments that exchange ONE carry each through a decoupled look-back
+//      (segment aggregates + flags in a caller-provided workspace, Horner on lam^len in fp64).
 //  (2) scan_i32: the integer recurrence of fxpmodel.py:147-208.  It floors every product separately, so it
 //      is not associative and must be sequential in time; one lane per (clip, state), register
 //      prefetch ring over time.
 #include <algorithm>
+#include <cmath>
 
 #include "scan.cuh"
 
 namespace s5 {
 
-constexpr int kScanT = 16;        // steps a thread scans sequentially (sub-chunk length)
-constexpr int kScanThreads = 256;  // upper bound for nsub * P
-
-struct ScanGeom {
-  int nsub, threads, TL, nchunks;
-  size_t flags_bytes, rec_floats2;  // per-(clip, chunk) record: agg[P] + incl[P] (double2 each)
-  size_t smem_bytes;
-};
-
-static ScanGeom scan_geom(int L, int P) {
-  ScanGeom g;
-  g.nsub = kScanThreads / P;
-  if (g.nsub < 1) g.nsub = 1;
-  g.threads = g.nsub * P;
-  g.TL = g.nsub * kScanT;
-  g.nchunks = (L + g.TL - 1) / g.TL;
-  g.rec_floats2 = 2 * (size_t)round_up((size_t)P, 16);
-  g.smem_bytes = (size_t)g.TL * P * 8 + (size_t)g.nsub * P * 8 + (size_t)P * 16 + 16;
-  return g;
-}
+constexpr int kScanThreads = 256;   // one thread per state: P <= 256
+constexpr int kSegRows = 16;         // time steps per shared-memory tile (one bulk copy of 16 * P * 8 bytes)
+constexpr int kSegMaxStages = 12;
+constexpr int kSegMaxCtas = 1024;    // upper bound on resident CTAs the plan may assume (sizes the workspace)
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
   return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
@@ -49,8 +34,8 @@ __device__ __forceinline__ float2 relu_lex(float2 z) {
   return keep ? z : make_float2(0.f, 0.f);
 }
 
-// double-precision complex helpers: chunk carries are combined in fp64 so that the powers lam^T, lam^TL,
-// lam^(k*TL) do not accumulate an O(k * eps_f32) error (the states themselves stay fp32 like the reference).
+// double-precision complex helpers: segment carries are combined in fp64 so that the powers lam^len do not
+// accumulate an O(n * eps_f32) error (the states themselves stay fp32 like the reference).
 __device__ __forceinline__ double2 zmul(double2 a, double2 b) {
   return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
@@ -59,176 +44,255 @@ __device__ __forceinline__ double2 zfma(double2 a, double2 x, double2 v) {
 }
 __device__ __forceinline__ double2 f2z(float2 v) { return make_double2((double)v.x, (double)v.y); }
 
-// LB_FIXED: fixed-stride look-back (bit-reproducible, two round trips per chunk) for grids larger than one resident wave;
-// otherwise the classic walk (lowest latency when a whole clip is co-resident, e.g. batch 1).
-template <bool LB_FIXED>
-__global__ void __launch_bounds__(kScanThreads, 4)
-scan_c64_kernel(const float2* __restrict__ Bu, const float2* __restrict__ lam, float2* xs, int L, int P, int nsub,
-                int nchunks, int relu, uint32_t* flags, double2* recs, int rec_stride) {
-  constexpr bool lb_fixed = LB_FIXED;
+// NUMERICS (fixed by L alone - never by the batch, the grid or timing).  A clip is divided into BLOCKS of `vlen` steps,
+// vlen = scan_vlen(L).  Inside a block the recurrence is the sequential fp32 chain of the reference's lax.scan; the state
+// that enters block k is float(c_k) with  c_k = lam^vlen c_(k-1) + agg_(k-1)  in fp64 (Horner), agg_j = the fp32 chain of
+// block j started from zero.  Every scheduling mode below evaluates exactly this expression, so a clip's bits do not
+// depend on how many clips are in the batch, on host chunking or on sharding over GPUs.
+//
+// SCHEDULING.  One CTA per (clip, segment), a segment being `gblocks` consecutive blocks.  Throughput batches (B >= 96)
+// are not cut (one segment per clip): a pure stream.  Few clips are cut so that all resident CTA slots have work; the
+// segments of a clip then exchange their block aggregates ONCE (decoupled look-back), not once per tile.
+constexpr int kSegMaxBlocks = 512;   // blocks per clip (bounds the look-back and the workspace)
+static int scan_vlen(int L) {       // block length: >= 128 steps, a multiple of the tile height, at most 512 blocks per clip
+  const int per = (L + kSegMaxBlocks - 1) / kSegMaxBlocks;
+  return std::max(128, ((per + kSegRows - 1) / kSegRows) * kSegRows);
+}
+struct ScanPlan {
+  int nseg, gblocks, vlen, nblocks, stages, threads;
+  size_t tile_bytes, smem_bytes;
+};
+static int scan_nseg_bound(int B, int L) {
+  if (B >= 96) return 1;
+  const int nblocks = (L + scan_vlen(L) - 1) / scan_vlen(L);
+  return std::max(1, std::min(nblocks, kSegMaxCtas / B));
+}
+static ScanPlan scan_plan(int B, int L, int P, int resident_ctas) {
+  ScanPlan g;
+  g.threads = (P + 31) & ~31;
+  g.tile_bytes = (size_t)kSegRows * P * 8;
+  // Small rings, many CTAs per SM: one warp per 32 states runs a dependent chain and cannot hide its own latencies, so
+  // an SM needs many such warps (P = 64: 8 KB tiles x 4 stages = 32 KB per CTA, 7 CTAs = 14 warps per SM).
+  static const int env_stages = [] { const char* e = getenv("S5B200_SCAN_STAGES"); return e ? atoi(e) : 0; }();
+  g.stages = env_stages > 0 ? std::max(3, std::min(kSegMaxStages, env_stages)) : 4;
+  g.smem_bytes = (size_t)g.stages * g.tile_bytes;
+  g.vlen = scan_vlen(L);
+  g.nblocks = (L + g.vlen - 1) / g.vlen;
+  // Few clips: cut until the resident CTA slots are full (at most one segment per block).
+  int nseg = std::min(scan_nseg_bound(B, L), std::max(1, resident_ctas / std::max(1, B)));
+  static const int forced = [] { const char* e = getenv("S5B200_SCAN_NSEG"); return e ? atoi(e) : 0; }();
+  if (forced > 0) nseg = std::min(forced, scan_nseg_bound(B, L));
+  g.gblocks = (g.nblocks + nseg - 1) / nseg;
+  g.nseg = (g.nblocks + g.gblocks - 1) / g.gblocks;          // no empty segment
+  return g;
+}
+
+// One CTA per (clip, segment), one thread per state, the segment streamed through a ring of shared-memory tiles:
+// every tile [16][P] is contiguous in the [B][L][P] layout, so ONE 1-D bulk async copy (TMA engine, SASS UBLKCP) brings
+// it in `stages - 2` tiles ahead of the recurrence and ONE bulk store takes the finished tile back; the warps issue no
+// global load or store for the data.  A thread pulls its state's 16 values of a tile into registers (independent,
+// conflict-free 8-byte shared loads), runs the dependent chains - the true states and, beside them, the block aggregate
+// from zero: two independent FMA chains, the second one free on an HBM-bound kernel - and writes the states back in place.
+//   nseg == 1 (throughput batches): a pure stream, 16 bytes of HBM traffic per state-step, no inter-CTA protocol at all.
+//   nseg  > 1 (few clips): segment 0 streams once and publishes its block aggregates as it goes; an inner segment first
+//   streams its rows READ-ONLY to get its block aggregates, publishes them, combines the aggregates of all earlier
+//   blocks (ONE exchange per CTA - the first version paid a flag / record round trip per 8 KB tile and was latency
+//   bound at 36 % of the HBM roofline for 32 clips), and streams its rows a second time with the true carry-in; the last
+//   segment publishes nothing and only waits.  The second read of an inner segment comes out of L2 when the batch is
+//   small enough to be cut (the ring keeps requesting tiles across the phase change, so the exchange overlaps the
+//   prefetch).  All CTAs of a cut grid must be co-resident: cooperative launch.
+// The first version of this kernel (one CTA per 8 KB chunk, load -> scan -> store in series) reached 51-63 % of the
+// measured HBM peak at batch 4096; this one 98-103 %.
+#ifdef S5_SCAN_TRACE
+#include <cstdio>
+__device__ __forceinline__ unsigned long long scan_gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define SCAN_T(i) do { if (p == 0) tr[i] = scan_gtime(); } while (0)
+#else
+#define SCAN_T(i)
+#endif
+template <int CP, bool RELU>
+__global__ void __launch_bounds__(kScanThreads)
+scan_c64_seg_kernel(const float2* __restrict__ Bu, const float2* __restrict__ lam, float2* xs, int L, int P_rt, int nseg,
+                    int gblocks, int vlen, int nblocks, uint32_t* flags, double2* recs, int stages) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int TL = nsub * kScanT;
-  float2* tile = reinterpret_cast<float2*>(smem_raw);        // [TL][P]
-  float2* sub_agg = tile + (size_t)TL * P;                    // [nsub][P]
-  double2* carry_s = reinterpret_cast<double2*>(sub_agg + (size_t)nsub * P);  // [P]
-  uint64_t* bar = reinterpret_cast<uint64_t*>(carry_s + P);
-
-  // Block order is clip-fastest: all clips' chunk c are dispatched before any chunk c+1, so by the time a chunk
-  // starts, its predecessors are usually finished and the look-back finds an inclusive prefix after 1-2 steps.
-  const int c = blockIdx.y, b = blockIdx.x;
-  const int tid = threadIdx.x;
-  const int p = tid % P, s = tid / P;
-  const int t0 = c * TL;
-  const int rows = min(TL, L - t0);
+  __shared__ __align__(8) uint64_t full[kSegMaxStages];
+  const int P = CP ? CP : P_rt;                               // compile-time row stride for the usual state sizes
+  const int p = threadIdx.x;
+#ifdef S5_SCAN_TRACE
+  unsigned long long tr[6] = {0, 0, 0, 0, 0, 0};
+#endif
+  SCAN_T(0);
+  const bool active = p < P;
+  const int b = blockIdx.x / nseg, sidx = blockIdx.x - b * nseg;
+  const int blk0 = sidx * gblocks;                             // first block of this segment
+  const int t0 = blk0 * vlen, rows_total = min(L, t0 + gblocks * vlen) - t0;
+  const int ntiles = (rows_total + kSegRows - 1) / kSegRows;
+  const int last_rows = rows_total - (ntiles - 1) * kSegRows;
+  const int tiles_per_block = vlen / kSegRows;
+  const size_t tile_elems = (size_t)kSegRows * P;
   const size_t base = ((size_t)b * L + t0) * P;
-  const uint32_t bytes = (uint32_t)rows * P * 8u;
+  float2* tiles = reinterpret_cast<float2*>(smem_raw);
+  const bool two_pass = sidx > 0 && sidx + 1 < nseg;          // inner segment: aggregate pass, then the real one
+  const bool publishes = nseg > 1 && sidx + 1 < nseg;         // its block aggregates are read by later segments
+  const int njobs = two_pass ? 2 * ntiles : ntiles;           // job i streams tile i % ntiles
 
-  if (tid == 0) {
-    mbar_init(bar, 1);
+  if (p == 0) {
+    for (int s = 0; s < stages; ++s) mbar_init(&full[s], 1);
     fence_mbar_init();
   }
   __syncthreads();
-  if (tid == 0) {
-    mbar_expect_tx(bar, bytes);
-    bulk_g2s(tile, Bu + base, bytes, bar);
+  // a stage is reloaded two jobs after it was read (its store, if any, has had a whole job to read the tile out)
+  const int ahead = stages - 2;
+  // producer state (thread 0): next job to request, its tile and stage - counters instead of divisions in the loop
+  int lj = 0, lt = 0, ls = 0;
+  auto issue_load = [&]() {                                    // thread 0 only
+    const int rows = lt + 1 == ntiles ? last_rows : kSegRows;
+    const uint32_t bytes = (uint32_t)rows * P * 8u;
+    mbar_expect_tx(&full[ls], bytes);
+    bulk_g2s(tiles + ls * tile_elems, Bu + base + (size_t)lt * tile_elems, bytes, &full[ls]);
+    ++lj;
+    if (++lt == ntiles) lt = 0;
+    if (++ls == stages) ls = 0;
+  };
+  if (p == 0)
+    for (int i = 0; i < min(ahead, njobs); ++i) issue_load();
+
+  const float2 a = active ? lam[p] : make_float2(0.f, 0.f);
+  // lam^vlen in fp64 by binary powers
+  double2 aV = make_double2(1., 0.);
+  {
+    double2 sq = f2z(a);
+    for (int n = vlen; n > 0; n >>= 1) {
+      if (n & 1) aV = zmul(aV, sq);
+      sq = zmul(sq, sq);
+    }
   }
 
-  // lam^T and lam^TL (fp64) while the tile is in flight
-  const float2 a = lam[p];
-  double2 aT = f2z(a);
+  uint32_t* flag_row = flags + (size_t)b * nseg;
+  double2* rec_row = recs + (size_t)b * nblocks * P;           // [block][P] aggregates of this clip
+  auto raise_flag = [&]() {                                    // all threads: the aggregates of this segment are complete
+    __syncthreads();                                           // the release below is cumulative over the barrier
+    if (p == 0) st_release_u32(flag_row + sidx, 1u);
+  };
+  auto look_back = [&]() -> double2 {                          // c entering block blk0: Horner over the blocks 0 .. blk0 - 1
+    // every thread polls its own share of the segment flags (all requests in flight together), then the CTA meets
+    for (int j0 = p; j0 < sidx; j0 += 4 * (int)blockDim.x) {
+      uint32_t f[4];
 #pragma unroll
-  for (int i = 1; i < kScanT; i <<= 1) aT = zmul(aT, aT);
-  double2 aTL = aT;
-  for (int i = 1; i < nsub; ++i) aTL = zmul(aTL, aT);
-
-  mbar_wait(bar, 0);
-
-  // pass 1: local recurrence from zero -> sub-chunk aggregate
-  const int ts = s * kScanT;
-  float2 x = make_float2(0.f, 0.f);
+      for (int w = 0; w < 4; ++w) f[w] = j0 + w * (int)blockDim.x < sidx ? ld_relaxed_u32(flag_row + j0 + w * blockDim.x) : 1u;
 #pragma unroll
-  for (int j = 0; j < kScanT; ++j) {
-    const int t = ts + j;
-    if (t < rows) x = cfma(a, x, tile[(size_t)t * P + p]);
-  }
-  sub_agg[s * P + p] = x;
-  __syncthreads();
-
-  // Only the first P threads (the "carry warps") take part in the aggregate / look-back / publish protocol;
-  // they synchronise among themselves on named barrier 1 and the rest of the CTA waits at the barrier below.
-  uint32_t* flag_row = flags + (size_t)b * nchunks;
-  double2* rec_row = recs + (size_t)b * nchunks * rec_stride;
-  const int half = rec_stride >> 1;
-  const bool publish = (c + 1 < nchunks);  // nobody looks back at the last chunk
-  const int carry_threads = (P + 31) & ~31;
-  if (tid < carry_threads) {
-    double2 e = make_double2(0., 0.);
-    if (tid < P) {
-      e = f2z(sub_agg[p]);
-      for (int q = 1; q < nsub; ++q) e = zfma(aT, e, f2z(sub_agg[q * P + p]));
-      if (publish) {
-        double2* rec = rec_row + (size_t)c * rec_stride;
-        __stcg(rec + (c == 0 ? half : 0) + p, e);  // chunk 0: aggregate == inclusive prefix
-        __threadfence();
+      for (int w = 0; w < 4; ++w)
+        while (f[w] == 0u) f[w] = ld_relaxed_u32(flag_row + j0 + w * blockDim.x);
+    }
+    __syncthreads();
+    fence_acquire_gpu();
+    double2 c = make_double2(0., 0.);
+    if (active) {
+      for (int j0 = 0; j0 < blk0; j0 += 16) {                  // 16 records in flight per thread, Horner in order
+        double2 r[16];
+#pragma unroll
+        for (int w = 0; w < 16; ++w)
+          if (j0 + w < blk0) r[w] = __ldcg(rec_row + (size_t)(j0 + w) * P + p);
+#pragma unroll
+        for (int w = 0; w < 16; ++w)
+          if (j0 + w < blk0) c = zfma(aV, c, r[w]);
       }
-      if (c == 0) carry_s[p] = make_double2(0., 0.);
     }
-    if (publish) {
-      asm volatile("bar.sync 1, %0;" ::"r"(carry_threads) : "memory");
-      if (tid == 0) st_release_u32(flag_row + c, c == 0 ? 2u : 1u);
+    return c;
+  };
+
+  double2 c = make_double2(0., 0.);                            // fp64 carry at the start of the current block
+  if (sidx > 0 && !two_pass) c = look_back();                  // last segment: nothing to publish, wait for the carry
+  float2 x = make_float2((float)c.x, (float)c.y);              // true state
+  float2 xa = make_float2(0.f, 0.f);                           // block aggregate (the chain from zero)
+
+  int st = 0, tix = 0, tib = 0, blk = blk0;                    // consumer state: stage, tile, tile within block, block
+  uint32_t par = 0;
+  for (int i = 0; i < njobs; ++i) {
+    const bool write = !two_pass || i >= ntiles;
+    if (two_pass && i == ntiles) {                             // phase change of an inner segment (tiles keep arriving meanwhile)
+      SCAN_T(2);
+      raise_flag();
+      c = look_back();
+      x = make_float2((float)c.x, (float)c.y);
+      xa = make_float2(0.f, 0.f);
+      tib = 0; blk = blk0;
+      SCAN_T(3);
     }
-    if constexpr (lb_fixed) if (c > 0) {
-      // Fixed-stride look-back (as in the fused block kernel, tc_model.cu).  Every chunk publishes its aggregate (flag 1),
-      // every kLbStride-th chunk (an "anchor") also its inclusive prefix (flag 2).  The carry-in of chunk c is ALWAYS
-      //     incl[a], then Horner over agg[a + 1 .. c - 1],     a = the last anchor before c,
-      // so (i) the floating-point association depends on c only - results are bit-reproducible - and (ii) all flags and
-      // all records of the walk are requested together: two memory round trips per chunk instead of two per
-      // predecessor, and only every kLbStride-th chunk sits on the serial anchor chain (118 chunks per 3751-frame clip
-      // used to be 118 dependent hops: the kernel was latency bound at 32 clips).
-      constexpr int kLbStride = 8;
-      const int a0 = ((c - 1) / kLbStride) * kLbStride;
-      const int n = c - a0;                                   // records to read: incl[a0], agg[a0 + 1 .. c - 1]
-      const bool anchor = (c % kLbStride) == 0;
-      double2 acc = make_double2(0., 0.);
-      if (tid < P) {
-        uint32_t f[kLbStride];
+    if (i == 1) SCAN_T(1);
+    if (p == 0 && lj < njobs) {
+      bulk_wait_read1();                                       // the store that last used stage `ls` (job i - 2) has read it
+      issue_load();
+    }
+    mbar_wait(&full[st], par);
+    const int rows = tix + 1 == ntiles ? last_rows : kSegRows;
+    float2* tile = tiles + st * tile_elems;
+    if (active) {
+      float2 v[kSegRows];
+      const float2* src = tile + p;
+      if (rows == kSegRows) {                                  // full tile: no predicates
 #pragma unroll
-        for (int w = 0; w < kLbStride; ++w) f[w] = w < n ? ld_relaxed_u32(flag_row + a0 + w) : 2u;
-        while (f[0] != 2u) f[0] = ld_relaxed_u32(flag_row + a0);
+        for (int t = 0; t < kSegRows; ++t) v[t] = src[t * P];
+        if (write) {
 #pragma unroll
-        for (int w = 1; w < kLbStride; ++w)
-          while (f[w] == 0u) f[w] = ld_relaxed_u32(flag_row + a0 + w);
-        fence_acquire_gpu();                                  // one acquire for the whole walk
-        double2 rec[kLbStride];
+          for (int t = 0; t < kSegRows; ++t) {
+            xa = cfma(a, xa, v[t]);
+            x = cfma(a, x, v[t]);
+            v[t] = x;
+          }
 #pragma unroll
-        for (int w = 0; w < kLbStride; ++w)
-          if (w < n) rec[w] = __ldcg(rec_row + (size_t)(a0 + w) * rec_stride + (w == 0 ? half : 0) + p);
-        acc = rec[0];
+          for (int t = 0; t < kSegRows; ++t) tile[t * P + p] = RELU ? relu_lex(v[t]) : v[t];
+        } else {
 #pragma unroll
-        for (int w = 1; w < kLbStride; ++w)
-          if (w < n) acc = zfma(aTL, acc, rec[w]);
-        carry_s[p] = acc;
-        if (publish && anchor) {
-          __stcg(rec_row + (size_t)c * rec_stride + half + p, zfma(aTL, acc, e));
-          __threadfence();
+          for (int t = 0; t < kSegRows; ++t) xa = cfma(a, xa, v[t]);
         }
-      }
-      if (publish && anchor) {
-        asm volatile("bar.sync 1, %0;" ::"r"(carry_threads) : "memory");
-        if (tid == 0) st_release_u32(flag_row + c, 2u);
-      }
-    }
-    // classic decoupled look-back (whole clips co-resident, e.g. batch 1: a chunk may walk past predecessors on
-    // aggregates alone instead of waiting for the anchor's inclusive prefix - lower latency, timing-dependent association)
-    if constexpr (!lb_fixed) if (c > 0) {
-      if (tid < P) {
-        // decoupled look-back: walk predecessors until one has published its inclusive prefix
-        double2 mult = make_double2(1., 0.);
-        double2 acc = make_double2(0., 0.);
-        for (int j = c - 1; j >= 0; --j) {
-          uint32_t f;
-          do {
-            f = ld_acquire_u32(flag_row + j);
-          } while (f == 0u);
-          const double2* rec = rec_row + (size_t)j * rec_stride;
-          const double2 v = __ldcg(rec + (f == 2u ? half : 0) + p);
-          acc = zfma(mult, v, acc);
-          if (f == 2u) break;
-          mult = zmul(mult, aTL);
-        }
-        carry_s[p] = acc;
-        if (publish) {
-          __stcg(rec_row + (size_t)c * rec_stride + half + p, zfma(aTL, acc, e));
-          __threadfence();
-        }
-      }
-      if (publish) {
-        asm volatile("bar.sync 1, %0;" ::"r"(carry_threads) : "memory");
-        if (tid == 0) st_release_u32(flag_row + c, 2u);
-      }
-    }
-  }
-  __syncthreads();
-
-  // pass 2: recurrence with the true carry-in, results in place
-  double2 cin = carry_s[p];
-  for (int q = 0; q < s; ++q) cin = zfma(aT, cin, f2z(sub_agg[q * P + p]));
-  x = make_float2((float)cin.x, (float)cin.y);
+      } else {
 #pragma unroll
-  for (int j = 0; j < kScanT; ++j) {
-    const int t = ts + j;
-    if (t < rows) {
-      x = cfma(a, x, tile[(size_t)t * P + p]);
-      tile[(size_t)t * P + p] = relu ? relu_lex(x) : x;
+        for (int t = 0; t < kSegRows; ++t) v[t] = t < rows ? src[t * P] : make_float2(0.f, 0.f);
+#pragma unroll
+        for (int t = 0; t < kSegRows; ++t)
+          if (t < rows) {
+            xa = cfma(a, xa, v[t]);
+            if (write) {
+              x = cfma(a, x, v[t]);
+              tile[t * P + p] = RELU ? relu_lex(x) : x;
+            }
+          }
+      }
+      if (++tib == tiles_per_block) {                          // block boundary: the next block starts from float(c)
+        tib = 0;
+        // an aggregate is published once: by the read-only pass of an inner segment, by the only pass of segment 0
+        if (publishes && (!write || !two_pass)) __stcg(rec_row + (size_t)blk * P + p, f2z(xa));
+        if (write) {
+          c = zfma(aV, c, f2z(xa));
+          x = make_float2((float)c.x, (float)c.y);
+        }
+        xa = make_float2(0.f, 0.f);
+        ++blk;
+      }
     }
+    if (write) fence_proxy_async_smem();
+    __syncthreads();                                           // every thread is done with the stage
+    if (write && p == 0) {
+      bulk_s2g(xs + base + (size_t)tix * tile_elems, tile, (uint32_t)rows * P * 8u);
+      bulk_commit();
+    }
+    if (++st == stages) { st = 0; par ^= 1u; }
+    if (++tix == ntiles) tix = 0;
   }
-  fence_proxy_async_smem();
-  __syncthreads();
-  if (tid == 0) {
-    bulk_s2g(xs + base, tile, bytes);
-    bulk_commit();
-    bulk_wait_read0();
-  }
+  SCAN_T(4);
+  if (sidx == 0 && nseg > 1) raise_flag();                     // segment 0 published its aggregates while streaming
+  if (p == 0) bulk_wait0();
+  SCAN_T(5);
+#ifdef S5_SCAN_TRACE
+  if (p == 0 && b == 1 && (sidx < 3 || sidx + 2 >= nseg || sidx == nseg / 2))
+    printf("[scan trace] seg %d/%d tiles %d: first tile %llu, phase1 end %llu, exchange %llu, phase2 %llu, drain %llu ns\n", sidx, nseg, ntiles,
+           tr[1] - tr[0], tr[2] ? tr[2] - tr[0] : 0ull, tr[3] ? tr[3] - tr[2] : 0ull, tr[4] - (tr[3] ? tr[3] : tr[0]), tr[5] - tr[4]);
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------- int
@@ -657,24 +721,33 @@ int launch_scan_c64(const float* Bu, const float* lam, float* xs, int B, int L, 
   if (!aligned16(Bu) || !aligned16(xs) || !aligned16(workspace)) S5_FAIL(S5_E_BADARG, "scan_c64: pointers must be 16-byte aligned");
   const size_t need = s5b200_scan_c64_workspace_bytes(B, L, P);
   if (workspace_bytes < need) S5_FAIL(S5_E_BADARG, "scan_c64: workspace %zu < %zu bytes", workspace_bytes, need);
-  const ScanGeom g = scan_geom(L, P);
-  static bool attr_set = false;
-  if (!attr_set) {
-    S5_CUDA(cudaFuncSetAttribute(scan_c64_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    S5_CUDA(cudaFuncSetAttribute(scan_c64_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    attr_set = true;
-  }
-  const size_t flags_bytes = round_up((size_t)B * g.nchunks * sizeof(uint32_t), 256);
+  // resident CTA slots for this tile size (the cut grid must be co-resident)
+  using Kern = void (*)(const float2*, const float2*, float2*, int, int, int, int, int, int, uint32_t*, double2*, int);
+  Kern kern;
+  if (P == 64) kern = relu ? scan_c64_seg_kernel<64, true> : scan_c64_seg_kernel<64, false>;
+  else if (P == 128) kern = relu ? scan_c64_seg_kernel<128, true> : scan_c64_seg_kernel<128, false>;
+  else kern = relu ? scan_c64_seg_kernel<0, true> : scan_c64_seg_kernel<0, false>;
+  ScanPlan g = scan_plan(B, L, P, 1);
+  S5_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
+  int per_sm = 0;
+  S5_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, g.threads, g.smem_bytes));
+  if (per_sm < 1) S5_FAIL(S5_E_CUDA, "scan_c64: no CTA fits an SM (%zu bytes of shared memory)", g.smem_bytes);
+  g = scan_plan(B, L, P, std::min(kSegMaxCtas, per_sm * sm_count()));
+  const size_t flags_bytes = round_up((size_t)B * scan_nseg_bound(B, L) * sizeof(uint32_t), 256);
   uint32_t* flags = reinterpret_cast<uint32_t*>(workspace);
   double2* recs = reinterpret_cast<double2*>(reinterpret_cast<unsigned char*>(workspace) + flags_bytes);
-  S5_CUDA(cudaMemsetAsync(flags, 0, flags_bytes, st));
-  if (g.nchunks > 65535) S5_FAIL(S5_E_BADSHAPE, "scan_c64: L=%d needs more than 65535 chunks", L);
-  dim3 grid(B, g.nchunks);
+  if (g.nseg > 1) S5_CUDA(cudaMemsetAsync(flags, 0, (size_t)B * g.nseg * sizeof(uint32_t), st));
+  if ((long long)B * g.nseg > 0x7fffffffLL) S5_FAIL(S5_E_BADSHAPE, "scan_c64: too many clips");
   ProfScope prof(S5_K_SCAN_C64, st);
-  auto kernel = (long long)B * g.nchunks > 4LL * sm_count() ? scan_c64_kernel<true> : scan_c64_kernel<false>;
-  kernel<<<grid, g.threads, g.smem_bytes, st>>>(reinterpret_cast<const float2*>(Bu), reinterpret_cast<const float2*>(lam),
-                                                reinterpret_cast<float2*>(xs), L, P, g.nsub, g.nchunks, relu, flags, recs,
-                                                (int)g.rec_floats2);
+  const float2* bu2 = reinterpret_cast<const float2*>(Bu);
+  const float2* lam2 = reinterpret_cast<const float2*>(lam);
+  float2* xs2 = reinterpret_cast<float2*>(xs);
+  if (g.nseg > 1) {
+    void* args[] = {&bu2, &lam2, &xs2, &L, &P, &g.nseg, &g.gblocks, &g.vlen, &g.nblocks, &flags, &recs, &g.stages};
+    S5_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(kern), dim3(B * g.nseg), dim3(g.threads), args, g.smem_bytes, st));
+  } else {
+    kern<<<B, g.threads, g.smem_bytes, st>>>(bu2, lam2, xs2, L, P, 1, g.gblocks, g.vlen, g.nblocks, flags, recs, g.stages);
+  }
   S5_LAUNCH_CHECK();
   return S5_OK;
 }
@@ -683,8 +756,9 @@ int launch_scan_c64(const float* Bu, const float* lam, float* xs, int B, int L, 
 
 extern "C" size_t s5b200_scan_c64_workspace_bytes(int B, int L, int P) {
   if (B <= 0 || L <= 0 || P <= 0 || P > s5::kScanThreads) return 0;
-  const s5::ScanGeom g = s5::scan_geom(L, P);
-  return s5::round_up((size_t)B * g.nchunks * sizeof(uint32_t), 256) + (size_t)B * g.nchunks * g.rec_floats2 * sizeof(double2);
+  const size_t nseg = (size_t)s5::scan_nseg_bound(B, L);      // flags [B][nseg] + block aggregates [B][nblocks][P] double2 (cut grids only)
+  const size_t nblocks = nseg > 1 ? (size_t)((L + s5::scan_vlen(L) - 1) / s5::scan_vlen(L)) : 0;
+  return s5::round_up((size_t)B * nseg * sizeof(uint32_t), 256) + (size_t)B * nblocks * P * sizeof(double2);
 }
 
 extern "C" int s5b200_scan_c64(const float* Bu, const float* lam, float* xs, int B, int L, int P, int relu,

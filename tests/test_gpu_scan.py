@@ -18,7 +18,11 @@ def _lam(rng, P):
 
 @pytest.mark.parametrize("B,L,P,relu", [(1, 1, 16, 0), (1, 5, 16, 0), (2, 100, 64, 0), (3, 3751, 64, 1), (2, 3751, 128, 0),
                                         (1, 777, 256, 0), (2, 1000, 16, 1), (2, 513, 96, 0), (1, 16, 2, 0),
-                                        (1, 65536, 64, 0)])
+                                        (1, 65536, 64, 0),
+                                        # throughput batches (B >= 96): one CTA per clip, pure stream, ragged last tile
+                                        (128, 50, 64, 1), (300, 77, 16, 0), (97, 1000, 128, 1), (160, 16, 256, 0),
+                                        # few clips cut into segments: two-pass inner segments, ReLU, odd state counts
+                                        (5, 4000, 64, 1), (40, 333, 6, 0), (7, 2049, 48, 1), (33, 31, 64, 0)])
 def test_scan_c64_matches_oracle(cuda_device, B, L, P, relu):
     import torch
     from sparsernns_b200.model import scan_c64
@@ -52,6 +56,16 @@ def test_scan_c64_in_place_and_linearity(cuda_device):
     buf = a.clone()
     scan_c64(buf, lam, out=buf)                                          # xs may alias Bu
     assert torch.equal(buf, ya)
+    big = torch.randn(130, 200, P, dtype=torch.complex64, device=cuda_device)   # the one-CTA-per-clip path, in place too
+    yb2 = scan_c64(big, lam)
+    scan_c64(big, lam, out=big)
+    assert torch.equal(big, yb2)
+    # a clip's bits do not depend on the batch it is in, nor on how the grid is cut (the numerics are fixed by L alone):
+    # 4 clips (cut into segments, two-pass inner segments), 1 clip (finer cut), 100 / 200 clips (one CTA per clip, pure stream)
+    assert torch.equal(scan_c64(a[:1], lam)[0], ya[0])
+    assert torch.equal(scan_c64(torch.cat([a[:1]] * 100), lam)[0], ya[0])
+    assert torch.equal(scan_c64(torch.cat([a[:1]] * 200), lam)[7], ya[0])
+    assert torch.equal(scan_c64(torch.cat([a[1:3]] * 20), lam)[1], ya[2])
     # recurrence identity x_t - lam x_{t-1} == Bu_t at full NDNS size
     resid = ya[:, 1:] - lam * ya[:, :-1] - a[:, 1:]
     assert resid.abs().max() <= 1e-4 * ya.abs().max()
