@@ -580,6 +580,238 @@ __global__ void __launch_bounds__(kEncThreads, 1) tc_enc_kernel(TcLinParams p) {
   if (warp == 0) tc_dealloc(tmem_slot, 256);
 }
 
+// ------------------------------------------------------------------------------------------- encoder, warp-specialised
+// Same layer as tc_enc_kernel (contiguous input rows that are not 16-byte aligned: 257 floats per frame), but no phase of
+// the tile ever waits for another one.  The product is formed TRANSPOSED - the weights are the A operand (M = 128 output
+// columns, zero padded), a 96-row activation tile the B operand - so the accumulator has TMEM lane = output column and
+// TMEM column = row: an epilogue thread owns ONE output column, keeps its scale / bias in registers and stores
+// Y[row][column] coalesced across the warp straight from registers (no shared output tile, no write-out pass).  Roles:
+//   warp 8        TMA producer: raw rows -> ring of three 32-row slots (1-D bulk copies, mbarrier complete_tx)
+//   warps 10..25  converters: ring slot -> FQ16 codes -> hi / lo int8 planes of tile buffer t & 1 (double buffered)
+//   warp 9        MMA issuer: tcgen05.mma kind::i8 of both planes into accumulator buffer t & 1 (2 x 64 TMEM columns each)
+//   warps 0..7    epilogue (lane quadrant w % 4, row half w / 4): tcgen05.ld -> 256 hi + lo -> scale, bias, fake-quant, ReLU -> global
+// linked by mbarriers (raw_full / raw_free per slot, planes_full / mma_done / tmem_free per buffer).  HBM reads never stop
+// while a tile is multiplied or written, which the first version (all 16 warps convert -> multiply -> post-process ->
+// write in turn) paid with 49 % of the HBM roofline.
+constexpr int kEnc2Rows = 64;      // rows per tile (MMA N)
+constexpr int kEnc2Sub = 32;       // rows per ring slot: 32 rows of 257 floats are a multiple of 128 bytes
+constexpr int kEnc2Ring = 3;
+constexpr int kEnc2Conv = 16;      // converter warps
+constexpr int kEnc2Epi = 8;        // epilogue warps: TMEM lane quadrant w % 4, row half w / 4
+constexpr int kEnc2Threads = 32 * (kEnc2Epi + 2 + kEnc2Conv);
+constexpr int kEnc2SubPerTile = kEnc2Rows / kEnc2Sub;
+
+template <int KV>
+__global__ void __launch_bounds__(kEnc2Threads, 1) tc_enc2_kernel(TcLinParams p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int Kp = p.Kp, Np = p.Np, Kf = p.Kfull;
+  const size_t w_bytes = tc_tile_bytes8(kTcRows, Kp);         // A operand: 128 rows (output columns), zero padded
+  const size_t a_bytes = tc_tile_bytes8(kEnc2Rows, Kp);       // one plane of one tile buffer
+  const size_t raw_bytes = (((size_t)kEnc2Sub * Kf * 4) + 127) & ~(size_t)127;
+  unsigned char* Wt = smem;
+  unsigned char* planes = Wt + w_bytes;                       // [buf][hi | lo]
+  unsigned char* rawb = planes + 4 * a_bytes;
+  __shared__ __align__(8) uint64_t raw_full[kEnc2Ring], raw_free[kEnc2Ring], planes_full[2], mma_done[2], tmem_free[2];
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+#ifdef S5_ENC2_TRACE
+  long long tw[3] = {0, 0, 0};
+  const long long tstart = clock64();
+#define E2_WAIT(i, stmt) do { const long long t_ = clock64(); stmt; tw[i] += clock64() - t_; } while (0)
+#else
+#define E2_WAIT(i, stmt) stmt
+#endif
+  const int n_quad = min(4, (p.Nfull + 31) >> 5);             // TMEM lane quadrants that hold real output columns
+  const int n_epi = 2 * n_quad;
+  if (warp == 0) tc_alloc(&tmem_slot, 512);
+  if (tid == 0) {
+    for (int i = 0; i < kEnc2Ring; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_free[i], kEnc2Conv); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&planes_full[i], kEnc2Conv); mbar_init(&mma_done[i], 1); mbar_init(&tmem_free[i], n_epi); }
+    fence_mbar_init();
+  }
+  {   // weights: rows < Np from global (K already in the staging order), the rest zero; planes: zero (pad bytes stay zero)
+    const int kchunks = Kp >> 4;
+    const uint32_t lbw = tc_lbo(kTcRows);
+    for (int i = tid; i < kTcRows * kchunks; i += kEnc2Threads) {
+      const int r = i / kchunks, kc = i - r * kchunks;
+      const int4 v = r < Np ? *reinterpret_cast<const int4*>(p.W8 + (size_t)r * Kp + kc * 16) : make_int4(0, 0, 0, 0);
+      *reinterpret_cast<int4*>(Wt + (size_t)kc * lbw + (size_t)r * 16) = v;
+    }
+    for (size_t i = (size_t)tid * 16; i < 4 * a_bytes; i += kEnc2Threads * 16) *reinterpret_cast<int4*>(planes + i) = make_int4(0, 0, 0, 0);
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t taddr = tmem_slot;
+  // contiguous row range per CTA, boundaries on multiples of 4 rows (16-byte alignment of the bulk copies)
+  // (32-row boundaries: every bulk copy then starts on a 128-byte boundary when X does)
+  const long long rb4 = (p.rows * blockIdx.x / gridDim.x) & ~31LL;
+  const long long re4 = blockIdx.x + 1 == gridDim.x ? p.rows : (p.rows * (blockIdx.x + 1) / gridDim.x) & ~31LL;
+  const int nsub = (int)((re4 - rb4 + kEnc2Sub - 1) / kEnc2Sub);
+  const int ntiles = (nsub + kEnc2SubPerTile - 1) / kEnc2SubPerTile;
+
+  if (warp == kEnc2Epi) {
+    // ---------------------------------------------------------------- TMA producer
+    if (lane == 0) {
+      for (int s = 0; s < nsub; ++s) {
+        const int slot = s % kEnc2Ring;
+        if (s >= kEnc2Ring) E2_WAIT(0, mbar_wait(&raw_free[slot], (uint32_t)((s / kEnc2Ring) - 1) & 1u));
+        const long long r0 = rb4 + (long long)s * kEnc2Sub;
+        const int nr = (int)min((long long)kEnc2Sub, re4 - r0) & ~3;   // whole groups of 4 rows; the rest is copied by hand
+        const uint32_t bytes = (uint32_t)nr * Kf * 4u;
+        if (bytes) {
+          mbar_expect_tx(&raw_full[slot], bytes);
+          bulk_g2s(rawb + (size_t)slot * raw_bytes, p.X + (size_t)r0 * Kf, bytes, &raw_full[slot]);
+        } else {
+          mbar_arrive(&raw_full[slot]);
+        }
+      }
+    }
+  } else if (warp == kEnc2Epi + 1) {
+    // ---------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      const uint32_t a0 = smem_u32(Wt), la = tc_lbo(kTcRows), lb = tc_lbo(kEnc2Rows);
+      for (int t = 0; t < ntiles; ++t) {
+        const int buf = t & 1;
+        const uint32_t k = (uint32_t)(t >> 1);
+        E2_WAIT(0, mbar_wait(&planes_full[buf], k & 1u));
+        if (t >= 2) E2_WAIT(1, mbar_wait(&tmem_free[buf], (k - 1u) & 1u));
+        tc_fence_after();
+        const uint32_t d0 = taddr + (uint32_t)buf * (2 * kEnc2Rows);
+        for (int pl = 0; pl < 2; ++pl) {
+          const uint32_t b0 = smem_u32(planes + (size_t)(2 * buf + pl) * a_bytes);
+          const uint32_t idesc = tc_idesc_i8(kTcRows, kEnc2Rows, true, pl == 0);   // weights signed; hi plane signed, lo unsigned
+          for (int j = 0; j < (Kp >> 5); ++j)
+            tc_mma_i8(d0 + (uint32_t)pl * kEnc2Rows, tc_smem_desc(a0 + j * 2 * la, la, 128), tc_smem_desc(b0 + j * 2 * lb, lb, 128), idesc, j > 0);
+        }
+        tc_commit(&mma_done[buf]);
+      }
+    }
+  } else if (warp >= kEnc2Epi + 2) {
+    // ---------------------------------------------------------------- converters
+    const int cw = warp - (kEnc2Epi + 2);
+    const uint32_t lbo = tc_lbo(kEnc2Rows);
+    uint32_t loff[KV];
+    int kq[KV][4];
+#pragma unroll
+    for (int i = 0; i < KV; ++i) {
+      loff[i] = (uint32_t)(8 * i + (lane >> 2)) * lbo + 4u * (lane & 3);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) kq[i][e] = min(128 * i + lane + 32 * e, Kf - 1);   // pad columns meet zero weights
+    }
+    const bool tail = Kf > 128 * KV;
+    const float inv = p.in_inv, qmin = p.in_qmin, qmax = p.in_qmax;
+    for (int s = 0; s < nsub; ++s) {
+      const int t = s / kEnc2SubPerTile, ts = s - t * kEnc2SubPerTile, buf = t & 1, slot = s % kEnc2Ring;
+      if (ts == 0 && t >= 2) E2_WAIT(1, mbar_wait(&mma_done[buf], (uint32_t)((t >> 1) - 1) & 1u));   // the MMAs of tile t - 2 have read these planes
+      unsigned char* Ah = planes + (size_t)(2 * buf) * a_bytes;
+      unsigned char* Al = Ah + a_bytes;
+      const long long r0 = rb4 + (long long)s * kEnc2Sub;
+      const int nr = (int)min((long long)kEnc2Sub, re4 - r0);
+      float* raw = reinterpret_cast<float*>(rawb + (size_t)slot * raw_bytes);
+      E2_WAIT(0, mbar_wait(&raw_full[slot], (uint32_t)(s / kEnc2Ring) & 1u));
+      if (nr & 3) {                                           // <= 3 rows at the very end of the input: plain loads
+        if (cw < (nr & 3)) {
+          const int rr = (nr & ~3) + cw;
+          for (int k = lane; k < Kf; k += 32) raw[(size_t)rr * Kf + k] = p.X[(size_t)(r0 + rr) * Kf + k];
+        }
+        asm volatile("bar.sync 1, %0;" ::"r"(32 * kEnc2Conv) : "memory");
+      }
+      // all shared loads of this warp's rows first, then the arithmetic and the plane stores: a load behind a store it
+      // may alias with (raw ring and planes are both shared memory) is never hoisted by the compiler
+      constexpr int RPW = kEnc2Sub / kEnc2Conv;
+      float xv[RPW][KV][4], xt[RPW];
+#pragma unroll
+      for (int q = 0; q < RPW; ++q) {
+        const float* xr = raw + (size_t)min(cw * RPW + q, nr - 1) * Kf;
+#pragma unroll
+        for (int i = 0; i < KV; ++i)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) xv[q][i][e] = xr[kq[i][e]];
+        xt[q] = xr[min(128 * KV, Kf - 1)];
+      }
+#pragma unroll
+      for (int q = 0; q < RPW; ++q) {
+        const uint32_t roff = (uint32_t)(ts * kEnc2Sub + cw * RPW + q) * 16u;
+#pragma unroll
+        for (int i = 0; i < KV; ++i) {
+          uint32_t b[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) b[e] = quant_bits(xv[q][i][e], inv, qmin, qmax);
+          uint32_t lo, hi;
+          split_planes(b[0], b[1], b[2], b[3], lo, hi);
+          *reinterpret_cast<uint32_t*>(Ah + loff[i] + roff) = hi;
+          *reinterpret_cast<uint32_t*>(Al + loff[i] + roff) = lo;
+        }
+        const uint32_t bt = quant_bits(xt[q], inv, qmin, qmax);
+        if (tail && lane == 0) {
+          *reinterpret_cast<uint32_t*>(Ah + (size_t)(8 * KV) * lbo + roff) = (bt >> 8) & 0xFFu;
+          *reinterpret_cast<uint32_t*>(Al + (size_t)(8 * KV) * lbo + roff) = bt & 0xFFu;
+        }
+      }
+      const bool tile_done = ts == kEnc2SubPerTile - 1 || s + 1 == nsub;
+      if (tile_done) fence_proxy_async_smem();                // the planes are read by the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&raw_free[slot]);
+        if (tile_done) mbar_arrive(&planes_full[buf]);
+      }
+    }
+  } else if ((warp & 3) < n_quad) {
+    // ---------------------------------------------------------------- epilogue: lane = output column, warp / 4 = row half
+    const int quad = warp & 3, half = warp >> 2;
+    const int n = 32 * quad + lane;
+    const bool ncol = n < p.Nfull;
+    const float oinv = (n & 1) ? p.out_inv1 : p.out_inv0, os = (n & 1) ? p.out_scale1 : p.out_scale0;
+    const float cs = ncol ? p.col_scale[n] * oinv : 0.f, cb = ncol && p.bias ? p.bias[n] * oinv : 0.f;
+    const float oqmin = p.relu ? fmaxf(p.out_qmin, 0.f) : p.out_qmin, oqmax = p.out_qmax;
+    const uint32_t lane_base = (uint32_t)(32 * quad) << 16;
+    constexpr int kHalfRows = kEnc2Rows / 2;
+    const size_t ystride = (size_t)p.y_stride;
+    for (int t = 0; t < ntiles; ++t) {
+      const int buf = t & 1;
+      const long long row0 = rb4 + (long long)t * kEnc2Rows;
+      const int rv = (int)min((long long)kEnc2Rows, re4 - row0);
+      E2_WAIT(0, mbar_wait(&mma_done[buf], (uint32_t)(t >> 1) & 1u));
+      tc_fence_after();
+      const uint32_t d0 = taddr + (uint32_t)buf * (2 * kEnc2Rows) + lane_base;
+      float* yr = p.Y + (size_t)row0 * p.y_stride + n;
+      for (int c0 = half * kHalfRows; c0 < min(rv, (half + 1) * kHalfRows); c0 += 16) {
+        uint32_t vh[16], vl[16];
+        tc_ld16(d0 + c0, vh);
+        tc_ld16(d0 + kEnc2Rows + c0, vl);
+        tc_wait_ld();
+        // all 16 values first (independent chains), then the stores: a predicate per element would serialise the chains
+        float o[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) o[j] = round_clip(fmaf(__int2float_rn((int)vh[j] * 256 + (int)vl[j]), cs, cb), oqmin, oqmax) * os;
+        float* q = yr + (size_t)c0 * ystride;
+        if (ncol) {
+          if (c0 + 16 <= rv) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j, q += ystride) *q = o[j];
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j, q += ystride)
+              if (c0 + j < rv) *q = o[j];
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_free[buf]);
+    }
+  }
+#ifdef S5_ENC2_TRACE
+  if (blockIdx.x == 3 && lane == 0 && (warp == 0 || warp == 4 || warp == 8 || warp == 9 || warp == 10 || warp == 25))
+    printf("[enc2 trace] warp %d: total %lld cyc, wait0 %lld, wait1 %lld (tiles %d, subs %d)\n", warp, clock64() - tstart, tw[0], tw[1], ntiles, nsub);
+#endif
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc_dealloc(tmem_slot, 512);
+}
+
 // ------------------------------------------------------------------------------------------- decoder (wide, odd N)
 // Dense layer with K <= 128 aligned input columns and Nfull = Np + 1 <= 257 output columns whose rows are contiguous
 // in memory (decoder: 96 -> 257).  The 1028-byte output rows are not 16-byte aligned, but a 128-row tile of them is one
@@ -1830,6 +2062,19 @@ int tc_linear_launch(const TcLinearDev& d, const float* X, float* Y, long long r
   if (enc_tma && !vec4 && !bn && aligned16(X) && aligned16(Y) && d.Np <= 128 && (d.Np & 31) == 0 && (d.Nfull & 3) == 0 && d.Nfull <= d.Np) {
     const size_t raw_bytes = (((size_t)kEncSub * d.Kfull * 4) + 127) & ~(size_t)127;
     const size_t esm = tc_tile_bytes8(d.Np, p.Kp) + 2 * tc_tile_bytes8(kTcRows, p.Kp) + kEncRing * raw_bytes + (size_t)d.Np * sizeof(float2);
+    // warp-specialised version (S5B200_ENC_V2=0 selects the first one)
+    static const bool enc_v2 = [] { const char* e = getenv("S5B200_ENC_V2"); return !e || atoi(e) != 0; }();
+    const size_t raw2 = (((size_t)kEnc2Sub * d.Kfull * 4) + 127) & ~(size_t)127;
+    const size_t esm2 = tc_tile_bytes8(kTcRows, p.Kp) + 4 * tc_tile_bytes8(kEnc2Rows, p.Kp) + kEnc2Ring * raw2;
+    if (enc_v2 && esm2 + 2048 <= 227 * 1024) {
+      auto kernel = d.KV == 1 ? tc_enc2_kernel<1> : tc_enc2_kernel<2>;
+      S5_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esm2));
+      const int grid = (int)std::max<long long>(1, std::min<long long>((rows + 63) / 64, (long long)sm_count()));
+      ProfScope prof(kclass, st);
+      kernel<<<grid, kEnc2Threads, esm2, st>>>(p);
+      S5_LAUNCH_CHECK();
+      return S5_OK;
+    }
     if (esm + 2048 <= 227 * 1024 && 2 * tc_tile_bytes8(kTcRows, p.Kp) >= (size_t)kTcRows * (d.Np + 4) * 4) {
       auto kernel = d.KV == 1 ? tc_enc_kernel<1> : tc_enc_kernel<2>;
       S5_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esm));
