@@ -606,11 +606,14 @@ __global__ void __launch_bounds__(kEnc2Threads, 1) tc_enc2_kernel(TcLinParams p)
   extern __shared__ __align__(128) unsigned char smem[];
   const int Kp = p.Kp, Np = p.Np, Kf = p.Kfull;
   const size_t w_bytes = tc_tile_bytes8(kTcRows, Kp);         // A operand: 128 rows (output columns), zero padded
-  const size_t a_bytes = tc_tile_bytes8(kEnc2Rows, Kp);       // one plane of one tile buffer
+  // one tile buffer: hi plane (rows 0 .. 63) and lo plane (rows 64 .. 127) STACKED in one 128-row B operand, so that one
+  // MMA per K step multiplies both.  A single operand has one signedness: the low byte travels as lo - 128 (lo ^ 0x80 read
+  // as int8) and the epilogue adds 128 * sum_k W[n][k] back - an exact integer per output column.
+  const size_t a_bytes = tc_tile_bytes8(2 * kEnc2Rows, Kp);
   const size_t raw_bytes = (((size_t)kEnc2Sub * Kf * 4) + 127) & ~(size_t)127;
   unsigned char* Wt = smem;
   unsigned char* planes = Wt + w_bytes;                       // [buf][hi | lo]
-  unsigned char* rawb = planes + 4 * a_bytes;
+  unsigned char* rawb = planes + 2 * a_bytes;
   __shared__ __align__(8) uint64_t raw_full[kEnc2Ring], raw_free[kEnc2Ring], planes_full[2], mma_done[2], tmem_free[2];
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -623,7 +626,7 @@ __global__ void __launch_bounds__(kEnc2Threads, 1) tc_enc2_kernel(TcLinParams p)
 #endif
   const int n_quad = min(4, (p.Nfull + 31) >> 5);             // TMEM lane quadrants that hold real output columns
   const int n_epi = 2 * n_quad;
-  if (warp == 0) tc_alloc(&tmem_slot, 512);
+  if (warp == 0) tc_alloc(&tmem_slot, 256);
   if (tid == 0) {
     for (int i = 0; i < kEnc2Ring; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_free[i], kEnc2Conv); }
     for (int i = 0; i < 2; ++i) { mbar_init(&planes_full[i], kEnc2Conv); mbar_init(&mma_done[i], 1); mbar_init(&tmem_free[i], n_epi); }
@@ -637,7 +640,7 @@ __global__ void __launch_bounds__(kEnc2Threads, 1) tc_enc2_kernel(TcLinParams p)
       const int4 v = r < Np ? *reinterpret_cast<const int4*>(p.W8 + (size_t)r * Kp + kc * 16) : make_int4(0, 0, 0, 0);
       *reinterpret_cast<int4*>(Wt + (size_t)kc * lbw + (size_t)r * 16) = v;
     }
-    for (size_t i = (size_t)tid * 16; i < 4 * a_bytes; i += kEnc2Threads * 16) *reinterpret_cast<int4*>(planes + i) = make_int4(0, 0, 0, 0);
+    for (size_t i = (size_t)tid * 16; i < 2 * a_bytes; i += kEnc2Threads * 16) *reinterpret_cast<int4*>(planes + i) = make_int4(0, 0, 0, 0);
   }
   fence_proxy_async_smem();
   tc_fence_before();
@@ -671,7 +674,9 @@ __global__ void __launch_bounds__(kEnc2Threads, 1) tc_enc2_kernel(TcLinParams p)
   } else if (warp == kEnc2Epi + 1) {
     // ---------------------------------------------------------------- MMA issuer
     if (lane == 0) {
-      const uint32_t a0 = smem_u32(Wt), la = tc_lbo(kTcRows), lb = tc_lbo(kEnc2Rows);
+      const uint32_t la = tc_lbo(kTcRows);                     // A (weights) and B (stacked planes) are both 128-row tiles
+      const uint64_t a_desc = tc_smem_desc(smem_u32(Wt), la, 128), step = (uint64_t)((2 * la) >> 4);   // next 32 columns of K
+      const uint32_t idesc = tc_idesc_i8(kTcRows, 2 * kEnc2Rows, true, true);
       for (int t = 0; t < ntiles; ++t) {
         const int buf = t & 1;
         const uint32_t k = (uint32_t)(t >> 1);
@@ -679,19 +684,15 @@ __global__ void __launch_bounds__(kEnc2Threads, 1) tc_enc2_kernel(TcLinParams p)
         if (t >= 2) E2_WAIT(1, mbar_wait(&tmem_free[buf], (k - 1u) & 1u));
         tc_fence_after();
         const uint32_t d0 = taddr + (uint32_t)buf * (2 * kEnc2Rows);
-        for (int pl = 0; pl < 2; ++pl) {
-          const uint32_t b0 = smem_u32(planes + (size_t)(2 * buf + pl) * a_bytes);
-          const uint32_t idesc = tc_idesc_i8(kTcRows, kEnc2Rows, true, pl == 0);   // weights signed; hi plane signed, lo unsigned
-          for (int j = 0; j < (Kp >> 5); ++j)
-            tc_mma_i8(d0 + (uint32_t)pl * kEnc2Rows, tc_smem_desc(a0 + j * 2 * la, la, 128), tc_smem_desc(b0 + j * 2 * lb, lb, 128), idesc, j > 0);
-        }
+        const uint64_t b_desc = tc_smem_desc(smem_u32(planes + (size_t)buf * a_bytes), la, 128);
+        for (int j = 0; j < (Kp >> 5); ++j) tc_mma_i8(d0, a_desc + j * step, b_desc + j * step, idesc, j > 0);
         tc_commit(&mma_done[buf]);
       }
     }
   } else if (warp >= kEnc2Epi + 2) {
     // ---------------------------------------------------------------- converters
     const int cw = warp - (kEnc2Epi + 2);
-    const uint32_t lbo = tc_lbo(kEnc2Rows);
+    const uint32_t lbo = tc_lbo(2 * kEnc2Rows);
     uint32_t loff[KV];
     int kq[KV][4];
 #pragma unroll
@@ -705,8 +706,8 @@ __global__ void __launch_bounds__(kEnc2Threads, 1) tc_enc2_kernel(TcLinParams p)
     for (int s = 0; s < nsub; ++s) {
       const int t = s / kEnc2SubPerTile, ts = s - t * kEnc2SubPerTile, buf = t & 1, slot = s % kEnc2Ring;
       if (ts == 0 && t >= 2) E2_WAIT(1, mbar_wait(&mma_done[buf], (uint32_t)((t >> 1) - 1) & 1u));   // the MMAs of tile t - 2 have read these planes
-      unsigned char* Ah = planes + (size_t)(2 * buf) * a_bytes;
-      unsigned char* Al = Ah + a_bytes;
+      unsigned char* Ah = planes + (size_t)buf * a_bytes;
+      unsigned char* Al = Ah + kEnc2Rows * 16;                // rows 64 .. 127 of the same operand tile
       const long long r0 = rb4 + (long long)s * kEnc2Sub;
       const int nr = (int)min((long long)kEnc2Sub, re4 - r0);
       float* raw = reinterpret_cast<float*>(rawb + (size_t)slot * raw_bytes);
@@ -742,12 +743,12 @@ __global__ void __launch_bounds__(kEnc2Threads, 1) tc_enc2_kernel(TcLinParams p)
           uint32_t lo, hi;
           split_planes(b[0], b[1], b[2], b[3], lo, hi);
           *reinterpret_cast<uint32_t*>(Ah + loff[i] + roff) = hi;
-          *reinterpret_cast<uint32_t*>(Al + loff[i] + roff) = lo;
+          *reinterpret_cast<uint32_t*>(Al + loff[i] + roff) = lo ^ 0x80808080u;
         }
         const uint32_t bt = quant_bits(xt[q], inv, qmin, qmax);
         if (tail && lane == 0) {
           *reinterpret_cast<uint32_t*>(Ah + (size_t)(8 * KV) * lbo + roff) = (bt >> 8) & 0xFFu;
-          *reinterpret_cast<uint32_t*>(Al + (size_t)(8 * KV) * lbo + roff) = bt & 0xFFu;
+          *reinterpret_cast<uint32_t*>(Al + (size_t)(8 * KV) * lbo + roff) = (bt & 0xFFu) ^ 0x80808080u;
         }
       }
       const bool tile_done = ts == kEnc2SubPerTile - 1 || s + 1 == nsub;
@@ -768,6 +769,16 @@ __global__ void __launch_bounds__(kEnc2Threads, 1) tc_enc2_kernel(TcLinParams p)
     const float oqmin = p.relu ? fmaxf(p.out_qmin, 0.f) : p.out_qmin, oqmax = p.out_qmax;
     const uint32_t lane_base = (uint32_t)(32 * quad) << 16;
     constexpr int kHalfRows = kEnc2Rows / 2;
+    int corr = 0;                                             // 128 * sum_k W[n][k]: undoes the lo - 128 of the stacked low plane
+    if (n < Np) {
+      const int4* wr = reinterpret_cast<const int4*>(p.W8 + (size_t)n * Kp);
+      for (int c = 0; c < (Kp >> 4); ++c) {
+        const int4 w = wr[c];
+        corr = __dp4a(w.x, 0x01010101, corr); corr = __dp4a(w.y, 0x01010101, corr);
+        corr = __dp4a(w.z, 0x01010101, corr); corr = __dp4a(w.w, 0x01010101, corr);
+      }
+      corr *= 128;
+    }
     const size_t ystride = (size_t)p.y_stride;
     for (int t = 0; t < ntiles; ++t) {
       const int buf = t & 1;
@@ -785,7 +796,7 @@ __global__ void __launch_bounds__(kEnc2Threads, 1) tc_enc2_kernel(TcLinParams p)
         // all 16 values first (independent chains), then the stores: a predicate per element would serialise the chains
         float o[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) o[j] = round_clip(fmaf(__int2float_rn((int)vh[j] * 256 + (int)vl[j]), cs, cb), oqmin, oqmax) * os;
+        for (int j = 0; j < 16; ++j) o[j] = round_clip(fmaf(__int2float_rn((int)vh[j] * 256 + (int)vl[j] + corr), cs, cb), oqmin, oqmax) * os;
         float* q = yr + (size_t)c0 * ystride;
         if (ncol) {
           if (c0 + 16 <= rv) {
@@ -809,7 +820,7 @@ __global__ void __launch_bounds__(kEnc2Threads, 1) tc_enc2_kernel(TcLinParams p)
 #endif
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tc_dealloc(tmem_slot, 512);
+  if (warp == 0) tc_dealloc(tmem_slot, 256);
 }
 
 // ------------------------------------------------------------------------------------------- decoder (wide, odd N)
@@ -943,6 +954,254 @@ __global__ void __launch_bounds__(kDecThreads, 1) tc_dec_kernel(TcLinParams p) {
     for (int i = tid; i < (rv - rv4) * Nf; i += kDecThreads) p.Y[(size_t)(row0 + rv4) * Nf + i] = outT[(size_t)rv4 * Nf + i];
   }
   if (tid == 0) bulk_wait0();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc_dealloc(tmem_slot, 512);
+}
+
+// ------------------------------------------------------------------------------------------- decoder, warp-specialised
+// The decoder Dense (K <= 128 aligned input columns, Nfull = Np + 1 <= 257 output columns) in the organisation of
+// tc_enc2_kernel: TRANSPOSED product (A = weights, one 128-row operand tile per block of 128 output columns; B = a 64-row
+// activation tile whose hi / lo byte planes are stacked into one 128-row operand), double-buffered planes and accumulators
+// (2 x 256 TMEM columns), epilogue lane = output column with its scale / bias / low-plane correction in registers and
+// coalesced stores straight from registers - the 1028-byte output rows need no shared tile and no alignment.  Roles:
+//   warps 0..15   epilogue (TMEM lane quadrant w % 4, rows 16 (w / 4) .. + 15 of the tile), both column blocks; the
+//                 quadrant-0 warps also finish the extra output column (an integer dot formed by the converters)
+//   warp 16       MMA issuer
+//   warps 17..24  converters: 8 rows each per tile, loaded from global one tile ahead (16-byte loads), FQ16 -> planes
+constexpr int kDec2Rows = 64;
+constexpr int kDec2Epi = 16, kDec2Conv = 8, kDec2Ring = 6, kDec2Sub = 32;   // ring: six slots of 32 input rows (half a tile)
+constexpr int kDec2OutBufs = 3;    // output half-tiles (32 rows of Nf floats) in flight
+constexpr int kDec2Threads = 32 * (kDec2Epi + 2 + kDec2Conv);
+
+__global__ void __launch_bounds__(kDec2Threads, 1) tc_dec2_kernel(TcLinParams p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int Kp = p.Kp, Np = p.Np, Nf = p.Nfull;
+  const int nblk = (Np + 127) >> 7;                           // blocks of 128 output columns (<= 2)
+  const size_t w_bytes = tc_tile_bytes8(kTcRows, Kp);         // one A operand block
+  const size_t a_bytes = tc_tile_bytes8(2 * kDec2Rows, Kp);   // one tile buffer: hi rows 0 .. 63, lo - 128 rows 64 .. 127
+  unsigned char* Wt = smem;
+  unsigned char* planes = Wt + 2 * w_bytes;
+  const size_t raw_bytes = (size_t)kDec2Sub * p.Kfull * 4;    // one ring slot: 32 input rows (a multiple of 16 bytes)
+  unsigned char* rawb = planes + 2 * a_bytes;
+  // output tile with the pitch of the global rows: 64 rows of Nf floats are ONE contiguous block of global memory, which
+  // leaves as one bulk store (full lines; per-row warp stores of 128 bytes at a 4-byte alignment reach only half of the
+  // HBM write bandwidth: 3.5 of 6.8 TB/s measured, profiles/r02_hbm_write.md)
+  float* outT0 = reinterpret_cast<float*>(rawb + (size_t)kDec2Ring * raw_bytes);   // three half-tiles: one or two leave while the next is assembled
+  __shared__ __align__(8) uint64_t planes_full[2], mma_done[2], tmem_free[2], raw_full[kDec2Ring], raw_free[kDec2Ring];
+  __shared__ uint32_t tmem_slot;
+  __shared__ int extra_n[2][kDec2Rows];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+#ifdef S5_ENC2_TRACE
+  long long tw[3] = {0, 0, 0};
+  const long long tstart = clock64();
+#endif
+  if (warp == 0) tc_alloc(&tmem_slot, 512);
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) { mbar_init(&planes_full[i], kDec2Conv); mbar_init(&mma_done[i], 1); mbar_init(&tmem_free[i], kDec2Epi); }
+    for (int i = 0; i < kDec2Ring; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_free[i], kDec2Conv / 2); }
+    fence_mbar_init();
+  }
+  {
+    const int kchunks = Kp >> 4;
+    const uint32_t lbw = tc_lbo(kTcRows);
+    for (int i = tid; i < 2 * kTcRows * kchunks; i += kDec2Threads) {
+      const int r = i / kchunks, kc = i - r * kchunks;       // r = output column
+      const int4 v = r < Np ? *reinterpret_cast<const int4*>(p.W8 + (size_t)r * Kp + kc * 16) : make_int4(0, 0, 0, 0);
+      *reinterpret_cast<int4*>(Wt + (size_t)(r >> 7) * w_bytes + (size_t)kc * lbw + (size_t)(r & 127) * 16) = v;
+    }
+    for (size_t i = (size_t)tid * 16; i < 2 * a_bytes; i += kDec2Threads * 16) *reinterpret_cast<int4*>(planes + i) = make_int4(0, 0, 0, 0);
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t taddr = tmem_slot;
+  // row ranges on 32-row boundaries: every tile then starts on a 128-byte boundary of Y (32 x 257 floats = 257 x 128 bytes)
+  const long long rb = (p.rows * blockIdx.x / gridDim.x) & ~31LL;
+  const long long re = blockIdx.x + 1 == gridDim.x ? p.rows : (p.rows * (blockIdx.x + 1) / gridDim.x) & ~31LL;
+  const int ntiles = (int)((re - rb + kDec2Rows - 1) / kDec2Rows);
+  const uint32_t la = tc_lbo(kTcRows);
+
+  if (warp == kDec2Epi) {
+    // ---------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      const uint64_t step = (uint64_t)((2 * la) >> 4);
+      const uint32_t idesc = tc_idesc_i8(kTcRows, 2 * kDec2Rows, true, true);
+      for (int t = 0; t < ntiles; ++t) {
+        const int buf = t & 1;
+        const uint32_t k = (uint32_t)(t >> 1);
+        E2_WAIT(0, mbar_wait(&planes_full[buf], k & 1u));
+        if (t >= 2) E2_WAIT(1, mbar_wait(&tmem_free[buf], (k - 1u) & 1u));
+        tc_fence_after();
+        const uint64_t b_desc = tc_smem_desc(smem_u32(planes + (size_t)buf * a_bytes), la, 128);
+        for (int blk = 0; blk < nblk; ++blk) {
+          const uint64_t a_desc = tc_smem_desc(smem_u32(Wt + (size_t)blk * w_bytes), la, 128);
+          const uint32_t d0 = taddr + (uint32_t)buf * 256u + (uint32_t)blk * 128u;
+          for (int j = 0; j < (Kp >> 5); ++j) tc_mma_i8(d0, a_desc + j * step, b_desc + j * step, idesc, j > 0);
+        }
+        tc_commit(&mma_done[buf]);
+      }
+    }
+  } else if (warp == kDec2Epi + 1) {
+    // ---------------------------------------------------------------- TMA producer: half-tile s (32 input rows) -> ring slot s % 3
+    if (lane == 0) {
+      const int nhalf = (int)((re - rb + kDec2Sub - 1) / kDec2Sub);
+      for (int sh = 0; sh < nhalf; ++sh) {
+        const int slot = sh % kDec2Ring;
+        if (sh >= kDec2Ring) mbar_wait(&raw_free[slot], (uint32_t)((sh / kDec2Ring) - 1) & 1u);
+        const long long r0 = rb + (long long)sh * kDec2Sub;
+        const uint32_t bytes = (uint32_t)min((long long)kDec2Sub, re - r0) * p.Kfull * 4u;
+        mbar_expect_tx(&raw_full[slot], bytes);
+        bulk_g2s(rawb + (size_t)slot * raw_bytes, p.X + (size_t)r0 * p.x_stride, bytes, &raw_full[slot]);
+      }
+    }
+  } else if (warp > kDec2Epi + 1) {
+    // ---------------------------------------------------------------- converters
+    const int cw = warp - kDec2Epi - 2;
+    constexpr int RPW = kDec2Rows / kDec2Conv;
+    const uint32_t loff = (uint32_t)(lane >> 2) * la + 4u * (lane & 3);
+    const bool wval = 4 * lane < Kp;
+    const int kcol = 4 * lane < p.Kfull ? 4 * lane : 0;
+    int wn[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) wn[e] = wval && p.WN ? (int)p.WN[4 * lane + e] : 0;
+    const float inv = p.in_inv, qmin = p.in_qmin, qmax = p.in_qmax;
+    for (int t = 0; t < ntiles; ++t) {
+      const int buf = t & 1;
+      const int hh = cw / (kDec2Conv / 2), sh = 2 * t + hh, slot = sh % kDec2Ring;   // this warp's rows lie in half-tile sh
+      const int rvh = (int)min((long long)kDec2Sub, re - (rb + (long long)sh * kDec2Sub));   // rows of that half (<= 0: none)
+      if (t >= 2) {                                           // tile t - 2: its MMAs have read the planes, its epilogue the extra column
+        E2_WAIT(0, mbar_wait(&mma_done[buf], (uint32_t)((t >> 1) - 1) & 1u));
+        E2_WAIT(1, mbar_wait(&tmem_free[buf], (uint32_t)((t >> 1) - 1) & 1u));
+      }
+      unsigned char* Ah = planes + (size_t)buf * a_bytes;
+      unsigned char* Al = Ah + kDec2Rows * 16;
+      if (rvh > 0) {
+        E2_WAIT(2, mbar_wait(&raw_full[slot], (uint32_t)(sh / kDec2Ring) & 1u));
+        const float* rs = reinterpret_cast<const float*>(rawb + (size_t)slot * raw_bytes) + kcol;
+        const int lr0 = (cw - hh * (kDec2Conv / 2)) * RPW;     // first row of this warp inside the half-tile
+        // four rows at a time: enough independent work per lane, few enough live registers (no spills at 832 threads)
+#pragma unroll
+        for (int q0 = 0; q0 < RPW; q0 += 4) {
+          float4 raw[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) raw[q] = *reinterpret_cast<const float4*>(rs + (size_t)min(lr0 + q0 + q, rvh - 1) * p.Kfull);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int r = cw * RPW + q0 + q;
+            const float xv[4] = {raw[q].x, raw[q].y, raw[q].z, raw[q].w};
+            uint32_t b4[4];
+            int part = 0;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              b4[e] = quant_bits(xv[e], inv, qmin, qmax);
+              part += (int)(short)b4[e] * wn[e];
+            }
+            uint32_t lo, hi;
+            split_planes(b4[0], b4[1], b4[2], b4[3], lo, hi);
+            if (wval) {
+              *reinterpret_cast<uint32_t*>(Ah + loff + (uint32_t)r * 16u) = hi;
+              *reinterpret_cast<uint32_t*>(Al + loff + (uint32_t)r * 16u) = lo ^ 0x80808080u;
+            }
+            const int tot = __reduce_add_sync(0xffffffffu, part);
+            if (lane == 0) extra_n[buf][r] = tot;
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&raw_free[slot]);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&planes_full[buf]);
+    }
+  } else {
+    // ---------------------------------------------------------------- epilogue: lane = output column, warp / 4 = 16 rows of the tile
+    const int quad = warp & 3, rq = warp >> 2;
+    const float oqmin = p.relu ? fmaxf(p.out_qmin, 0.f) : p.out_qmin, oqmax = p.out_qmax;
+    const uint32_t lane_base = (uint32_t)(32 * quad) << 16;
+    const size_t ystride = (size_t)p.y_stride;
+    float cs[2], cb[2], os[2];
+    int corr[2];
+    bool ncol[2];
+#pragma unroll
+    for (int blk = 0; blk < 2; ++blk) {
+      const int n = 128 * blk + 32 * quad + lane;
+      ncol[blk] = blk < nblk && n < Np;
+      const float oinv = (n & 1) ? p.out_inv1 : p.out_inv0;
+      os[blk] = (n & 1) ? p.out_scale1 : p.out_scale0;
+      cs[blk] = ncol[blk] ? p.col_scale[n] * oinv : 0.f;
+      cb[blk] = ncol[blk] && p.bias ? p.bias[n] * oinv : 0.f;
+      int c = 0;                                              // 128 * sum_k W[n][k]: undoes the lo - 128 of the stacked low plane
+      if (ncol[blk]) {
+        const int4* wr = reinterpret_cast<const int4*>(p.W8 + (size_t)n * Kp);
+        for (int i = 0; i < (Kp >> 4); ++i) {
+          const int4 w = wr[i];
+          c = __dp4a(w.x, 0x01010101, c); c = __dp4a(w.y, 0x01010101, c); c = __dp4a(w.z, 0x01010101, c); c = __dp4a(w.w, 0x01010101, c);
+        }
+      }
+      corr[blk] = 128 * c;
+    }
+    // the extra column (Nf = Np + 1): (s_in s_w / s_out, bias / s_out) of column Nf - 1
+    const bool xn = Nf > Np;
+    const float xoinv = ((Nf - 1) & 1) ? p.out_inv1 : p.out_inv0, xos = ((Nf - 1) & 1) ? p.out_scale1 : p.out_scale0;
+    const float xcs = xn ? p.col_scale[Nf - 1] * xoinv : 0.f, xcb = xn && p.bias ? p.bias[Nf - 1] * xoinv : 0.f;
+    for (int t = 0; t < ntiles; ++t) {
+      const int buf = t & 1;
+      const long long row0 = rb + (long long)t * kDec2Rows;
+      const int rv = (int)min((long long)kDec2Rows, re - row0);
+      E2_WAIT(0, mbar_wait(&mma_done[buf], (uint32_t)(t >> 1) & 1u));
+      tc_fence_after();
+      if (tid == 0) bulk_wait_read1();                        // only the second half of the previous tile may still be leaving
+      asm volatile("bar.sync 2, %0;" ::"r"(32 * kDec2Epi) : "memory");
+      const int c0 = 16 * rq, hh = rq >> 1;                   // rows c0 .. c0 + 15 of the tile lie in half-tile 2 t + hh
+      float* outT = outT0 + (size_t)((2 * t + hh) % kDec2OutBufs) * kDec2Sub * Nf;
+      if (c0 < rv) {
+#pragma unroll
+        for (int blk = 0; blk < 2; ++blk) {
+          if (blk >= nblk) break;
+          const uint32_t d0 = taddr + (uint32_t)buf * 256u + (uint32_t)blk * 128u + lane_base;
+          uint32_t vh[16], vl[16];
+          tc_ld16(d0 + c0, vh);
+          tc_ld16(d0 + kDec2Rows + c0, vl);
+          tc_wait_ld();
+          float* q = outT + (size_t)(c0 - kDec2Sub * hh) * Nf + 128 * blk + 32 * quad + lane;   // lanes along columns: conflict-free
+          if (ncol[blk]) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              q[(size_t)j * Nf] = round_clip(fmaf(__int2float_rn((int)vh[j] * 256 + (int)vl[j] + corr[blk]), cs[blk], cb[blk]), oqmin, oqmax) * os[blk];
+          }
+        }
+        if (xn && quad == 0 && lane < 16)
+          outT[(size_t)(c0 - kDec2Sub * hh + lane) * Nf + Nf - 1] = round_clip(fmaf(__int2float_rn(extra_n[buf][c0 + lane]), xcs, xcb), oqmin, oqmax) * xos;
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_free[buf]);
+      asm volatile("bar.sync 2, %0;" ::"r"(32 * kDec2Epi) : "memory");
+      // one bulk copy per half-tile; up to 3 rows that would break the 16-byte size rule go by hand (end of the input)
+      const int rv4 = rv & ~3;
+      if (tid == 0) {
+        for (int h2 = 0; h2 < 2; ++h2) {
+          const int nr = min(kDec2Sub, rv4 - kDec2Sub * h2);
+          if (nr > 0) bulk_s2g(p.Y + (size_t)(row0 + kDec2Sub * h2) * ystride, outT0 + (size_t)((2 * t + h2) % kDec2OutBufs) * kDec2Sub * Nf, (uint32_t)((size_t)nr * Nf * 4));
+          bulk_commit();
+        }
+      }
+      if (rv4 != rv) {
+        const int h2 = rv4 / kDec2Sub;
+        const float* src = outT0 + (size_t)((2 * t + h2) % kDec2OutBufs) * kDec2Sub * Nf + (size_t)(rv4 - kDec2Sub * h2) * Nf;
+        for (int i = tid; i < (rv - rv4) * Nf; i += 32 * kDec2Epi) p.Y[(size_t)(row0 + rv4) * ystride + i] = src[i];
+        asm volatile("bar.sync 2, %0;" ::"r"(32 * kDec2Epi) : "memory");
+      }
+    }
+    if (tid == 0) bulk_wait0();
+  }
+#ifdef S5_ENC2_TRACE
+  if (blockIdx.x == 3 && lane == 0 && (warp == 0 || warp == 5 || warp == 15 || warp == 16 || warp == 18 || warp == 25))
+    printf("[dec2 trace] warp %d: total %lld cyc, wait0 %lld, wait1 %lld, wait2 %lld (tiles %d)\n", warp, clock64() - tstart, tw[0], tw[1], tw[2], ntiles);
+#endif
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tc_dealloc(tmem_slot, 512);
@@ -2047,6 +2306,20 @@ int tc_linear_launch(const TcLinearDev& d, const float* X, float* Y, long long r
     // wide decoder: contiguous output rows, the whole N in one MMA pass, one bulk copy per tile
     static const bool dec_tma = [] { const char* e = getenv("S5B200_DEC_TMA"); return !e || atoi(e) != 0; }();
     const size_t dsm = tc_tile_bytes8(d.Np, p.Kp) + 2 * tc_tile_bytes8(kTcRows, p.Kp) + (size_t)kTcRows * d.Nfull * 4 + (size_t)d.Nfull * sizeof(float2);
+    // warp-specialised version (S5B200_DEC_V2=0 selects the first one)
+    static const bool dec_v2 = [] { const char* e = getenv("S5B200_DEC_V2"); return !e || atoi(e) != 0; }();
+    if (dec_v2 && d.KV == 1 && d.Np <= 256 && (d.Np & 31) == 0 && (p.Kp & 31) == 0 && aligned16(Y) && d.Nfull == d.Np + 1 &&
+        2 * tc_tile_bytes8(kTcRows, p.Kp) + 2 * tc_tile_bytes8(2 * kDec2Rows, p.Kp) + (size_t)kDec2Ring * kDec2Sub * d.Kfull * 4 +
+                (size_t)kDec2OutBufs * kDec2Sub * d.Nfull * 4 + 2048 <= 227 * 1024) {
+      const size_t dsm2 = 2 * tc_tile_bytes8(kTcRows, p.Kp) + 2 * tc_tile_bytes8(2 * kDec2Rows, p.Kp) + (size_t)kDec2Ring * kDec2Sub * d.Kfull * 4 +
+                          (size_t)kDec2OutBufs * kDec2Sub * d.Nfull * 4;
+      S5_CUDA(cudaFuncSetAttribute(tc_dec2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm2));
+      const int grid = (int)std::max<long long>(1, std::min<long long>((rows + 63) / 64, (long long)sm_count()));
+      ProfScope prof(kclass, st);
+      tc_dec2_kernel<<<grid, kDec2Threads, dsm2, st>>>(p);
+      S5_LAUNCH_CHECK();
+      return S5_OK;
+    }
     if (dec_tma && d.KV == 1 && d.Np <= 256 && (d.Np & 31) == 0 && aligned16(Y) && dsm + 2048 <= 227 * 1024) {
       S5_CUDA(cudaFuncSetAttribute(tc_dec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
       const int grid = (int)std::max<long long>(1, std::min<long long>((rows + 63) / 64, (long long)sm_count()));
@@ -2065,7 +2338,7 @@ int tc_linear_launch(const TcLinearDev& d, const float* X, float* Y, long long r
     // warp-specialised version (S5B200_ENC_V2=0 selects the first one)
     static const bool enc_v2 = [] { const char* e = getenv("S5B200_ENC_V2"); return !e || atoi(e) != 0; }();
     const size_t raw2 = (((size_t)kEnc2Sub * d.Kfull * 4) + 127) & ~(size_t)127;
-    const size_t esm2 = tc_tile_bytes8(kTcRows, p.Kp) + 4 * tc_tile_bytes8(kEnc2Rows, p.Kp) + kEnc2Ring * raw2;
+    const size_t esm2 = tc_tile_bytes8(kTcRows, p.Kp) + 2 * tc_tile_bytes8(2 * kEnc2Rows, p.Kp) + kEnc2Ring * raw2;
     if (enc_v2 && esm2 + 2048 <= 227 * 1024) {
       auto kernel = d.KV == 1 ? tc_enc2_kernel<1> : tc_enc2_kernel<2>;
       S5_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esm2));
