@@ -405,11 +405,16 @@ def main():
 
     extras = {}
     cpu_baseline = None
+    scan_rf = None
     if rank == 0 and not args.no_extras:
         try:
             extras = secondary_flavours(torch, model, params, batch_stats, cal_stats, dims, xs, B, L, dev)
         except Exception as e:  # secondary numbers must never take the headline down
             extras = {"error": repr(e)}
+        try:
+            scan_rf = scan_roofline(torch, B, L, dims.ssm_size, dev, peak)
+        except Exception as e:
+            scan_rf = {"error": repr(e)}
         if world == 1:
             # bounded sample of the same workload: 8-clip slices of the step's batch, repeated until about 10 s of CPU work
             fwd = cpu_port_forward_fn(params, batch_stats, dims)
@@ -452,6 +457,8 @@ def main():
         }
         if extras:
             line["flavours"] = extras
+        if scan_rf:
+            line["scan_roofline"] = scan_rf
         emit(line)
     if dist is not None:
         dist.destroy_process_group()
@@ -469,6 +476,43 @@ def kernel_breakdown(fn, reps=3):
     n = (C.c_longlong * len(_abi.KERNEL_CLASSES))()
     _abi.check(lib.s5b200_profile_end(ms, n))
     return {name: round(ms[i] / reps, 4) for i, name in enumerate(_abi.KERNEL_CLASSES) if n[i]}
+
+
+def scan_roofline(torch, B, L, P, dev, peak):
+    """The second half of BASELINE.json's metric: the stand-alone diagonal recurrence (s5b200_scan_c64, the kernel that replaces
+    lax.associative_scan) against the HBM roofline, 16 bytes per state-step, on (a) the step's own shape and (b) the throughput
+    batch of BASELINE configs[4].  CUDA events; inputs rotate over buffer sets larger than L2 where one set is not."""
+    from sparsernns_b200 import _abi
+
+    lib = _abi.lib()
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    out = {}
+    for tag, (b, l) in (("step_shape", (B, L)), ("batch_4096", (4096, 1024))):
+        by = 16.0 * b * l * P
+        nbuf = 1 if by > 1e9 else int(min(8, max(2, -(-400e6 // by))))
+        bu = [torch.randn(b, l, P, 2, device=dev) for _ in range(nbuf)]
+        xo = [torch.empty_like(bu[0]) for _ in range(nbuf)]
+        lam = torch.view_as_real(torch.polar(torch.rand(P, device=dev) * 0.09 + 0.9, torch.rand(P, device=dev) * 2 - 1)).contiguous()
+        wsb = lib.s5b200_scan_c64_workspace_bytes(b, l, P)
+        ws = [torch.empty(max(wsb, 16), dtype=torch.uint8, device=dev) for _ in range(nbuf)]
+
+        def run(i):
+            _abi.check(lib.s5b200_scan_c64(bu[i].data_ptr(), lam.data_ptr(), xo[i].data_ptr(), b, l, P, 0, ws[i].data_ptr(), wsb, st), "scan_c64")
+
+        for i in range(3 * nbuf):
+            run(i % nbuf)
+        reps = 5
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(); e0.record()
+        for r in range(reps):
+            for i in range(nbuf):
+                run(i)
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / (reps * nbuf)
+        out[tag] = {"B": b, "L": l, "P": P, "us": ms * 1e3, "alg_bytes": by, "achieved_gbs": by / ms / 1e6, "frac": by / ms / 1e6 / peak,
+                    "buffers": nbuf}
+        del bu, xo, ws
+    return out
 
 
 def secondary_flavours(torch, model, params, batch_stats, cal_stats, dims, xs, B, L, dev):

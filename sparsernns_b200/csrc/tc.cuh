@@ -26,6 +26,13 @@ __device__ __forceinline__ uint64_t tc_smem_desc(uint32_t smem_addr, uint32_t lb
          ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
 }
 
+// the same descriptor `units` x 16 bytes further: only the 14-bit start-address field changes, and it WRAPS (the field holds
+// address bits 4..17; shared-window addresses of a large CTA do cross 2^18, so a plain 64-bit add would carry into the
+// reserved bits - measured: wrong products in the second tile pipeline of the block kernel)
+__device__ __forceinline__ uint64_t tc_desc_advance(uint64_t desc, uint32_t units) {
+  return (desc & ~0x3FFFull) | ((desc + units) & 0x3FFFull);
+}
+
 // instruction descriptor for kind::f16: A = B = F16, D = F32, both K-major, M x N tile (cute::UMMA::InstrDescriptor)
 __host__ __device__ __forceinline__ uint32_t tc_idesc_f16(int M, int N) {
   return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);

@@ -130,19 +130,22 @@ __device__ __forceinline__ void tc_load_weights8(unsigned char* dst, const signe
 // issue the K/16 MMAs of one [128 x K] x [K x N] product (A and B in the padded canonical layout)
 __device__ __forceinline__ void tc_issue(uint32_t d_tmem, const void* A, const void* B, int K, int N, bool accumulate_first,
                                          bool bf16 = false) {
-  const uint32_t a0 = smem_u32(A), b0 = smem_u32(B);
   const uint32_t la = tc_lbo(kTcRows), lb = tc_lbo(N);
   const uint32_t idesc = bf16 ? tc_idesc_bf16(kTcRows, N) : tc_idesc_f16(kTcRows, N);
+  // The descriptors of consecutive K steps differ only in the start-address field (low 14 bits, units of 16 bytes):
+  // build them once and add a constant per step - the issuing thread is alone on the critical path of the tile.
+  const uint64_t a_desc = tc_smem_desc(smem_u32(A), la, 128), b_desc = tc_smem_desc(smem_u32(B), lb, 128);
+  const uint32_t sa = (2 * la) >> 4, sb = (2 * lb) >> 4;
   for (int j = 0; j < (K >> 4); ++j)
-    tc_mma_f16(d_tmem, tc_smem_desc(a0 + j * 2 * la, la, 128), tc_smem_desc(b0 + j * 2 * lb, lb, 128), idesc, accumulate_first || j > 0);
+    tc_mma_f16(d_tmem, tc_desc_advance(a_desc, j * sa), tc_desc_advance(b_desc, j * sb), idesc, accumulate_first || j > 0);
 }
 // int8 form: K/32 MMAs of [128 x K] (8-bit, signed or unsigned) x [K x N] (int8; `brows` rows in the whole B tile)
 __device__ __forceinline__ void tc_issue8(uint32_t d_tmem, const void* A, const void* B, int K, int N, int brows, bool a_signed) {
-  const uint32_t a0 = smem_u32(A), b0 = smem_u32(B);
   const uint32_t la = tc_lbo(kTcRows), lb = tc_lbo(brows);
   const uint32_t idesc = tc_idesc_i8(kTcRows, N, a_signed, true);
-  for (int j = 0; j < (K >> 5); ++j)
-    tc_mma_i8(d_tmem, tc_smem_desc(a0 + j * 2 * la, la, 128), tc_smem_desc(b0 + j * 2 * lb, lb, 128), idesc, j > 0);
+  const uint64_t a_desc = tc_smem_desc(smem_u32(A), la, 128), b_desc = tc_smem_desc(smem_u32(B), lb, 128);
+  const uint32_t sa = (2 * la) >> 4, sb = (2 * lb) >> 4;
+  for (int j = 0; j < (K >> 5); ++j) tc_mma_i8(d_tmem, tc_desc_advance(a_desc, j * sa), tc_desc_advance(b_desc, j * sb), idesc, j > 0);
 }
 
 // Dense / B-projection tile kernel.  Per 128-row tile:
@@ -601,18 +604,20 @@ constexpr int kEnc2Epi = 8;        // epilogue warps: TMEM lane quadrant w % 4, 
 constexpr int kEnc2Threads = 32 * (kEnc2Epi + 2 + kEnc2Conv);
 constexpr int kEnc2SubPerTile = kEnc2Rows / kEnc2Sub;
 
-template <int KV>
+template <int KV, int NRING>
 __global__ void __launch_bounds__(kEnc2Threads, 1) tc_enc2_kernel(TcLinParams p) {
+  constexpr int nring = NRING;                                // ring slots: compile-time, the slot / phase arithmetic sits in every loop
   extern __shared__ __align__(128) unsigned char smem[];
   const int Kp = p.Kp, Np = p.Np, Kf = p.Kfull;
-  const size_t w_bytes = tc_tile_bytes8(kTcRows, Kp);         // A operand: 128 rows (output columns), zero padded
+  const int nblk = (Np + 127) >> 7;                           // blocks of 128 output columns (<= 2)
+  const size_t w_bytes = tc_tile_bytes8(kTcRows, Kp);         // one A operand block: 128 rows (output columns), zero padded
   // one tile buffer: hi plane (rows 0 .. 63) and lo plane (rows 64 .. 127) STACKED in one 128-row B operand, so that one
   // MMA per K step multiplies both.  A single operand has one signedness: the low byte travels as lo - 128 (lo ^ 0x80 read
   // as int8) and the epilogue adds 128 * sum_k W[n][k] back - an exact integer per output column.
   const size_t a_bytes = tc_tile_bytes8(2 * kEnc2Rows, Kp);
   const size_t raw_bytes = (((size_t)kEnc2Sub * Kf * 4) + 127) & ~(size_t)127;
   unsigned char* Wt = smem;
-  unsigned char* planes = Wt + w_bytes;                       // [buf][hi | lo]
+  unsigned char* planes = Wt + (size_t)nblk * w_bytes;        // [buf][hi | lo]
   unsigned char* rawb = planes + 2 * a_bytes;
   __shared__ __align__(8) uint64_t raw_full[kEnc2Ring], raw_free[kEnc2Ring], planes_full[2], mma_done[2], tmem_free[2];
   __shared__ uint32_t tmem_slot;
@@ -624,21 +629,20 @@ __global__ void __launch_bounds__(kEnc2Threads, 1) tc_enc2_kernel(TcLinParams p)
 #else
 #define E2_WAIT(i, stmt) stmt
 #endif
-  const int n_quad = min(4, (p.Nfull + 31) >> 5);             // TMEM lane quadrants that hold real output columns
-  const int n_epi = 2 * n_quad;
-  if (warp == 0) tc_alloc(&tmem_slot, 256);
+  const int n_epi = kEnc2Epi;                                 // every epilogue warp arrives (warps without real columns store nothing)
+  if (warp == 0) tc_alloc(&tmem_slot, nblk == 1 ? 256 : 512);
   if (tid == 0) {
-    for (int i = 0; i < kEnc2Ring; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_free[i], kEnc2Conv); }
+    for (int i = 0; i < nring; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_free[i], kEnc2Conv); }
     for (int i = 0; i < 2; ++i) { mbar_init(&planes_full[i], kEnc2Conv); mbar_init(&mma_done[i], 1); mbar_init(&tmem_free[i], n_epi); }
     fence_mbar_init();
   }
   {   // weights: rows < Np from global (K already in the staging order), the rest zero; planes: zero (pad bytes stay zero)
     const int kchunks = Kp >> 4;
     const uint32_t lbw = tc_lbo(kTcRows);
-    for (int i = tid; i < kTcRows * kchunks; i += kEnc2Threads) {
-      const int r = i / kchunks, kc = i - r * kchunks;
+    for (int i = tid; i < nblk * kTcRows * kchunks; i += kEnc2Threads) {
+      const int r = i / kchunks, kc = i - r * kchunks;       // r = output column
       const int4 v = r < Np ? *reinterpret_cast<const int4*>(p.W8 + (size_t)r * Kp + kc * 16) : make_int4(0, 0, 0, 0);
-      *reinterpret_cast<int4*>(Wt + (size_t)kc * lbw + (size_t)r * 16) = v;
+      *reinterpret_cast<int4*>(Wt + (size_t)(r >> 7) * w_bytes + (size_t)kc * lbw + (size_t)(r & 127) * 16) = v;
     }
     for (size_t i = (size_t)tid * 16; i < 2 * a_bytes; i += kEnc2Threads * 16) *reinterpret_cast<int4*>(planes + i) = make_int4(0, 0, 0, 0);
   }
@@ -658,8 +662,8 @@ __global__ void __launch_bounds__(kEnc2Threads, 1) tc_enc2_kernel(TcLinParams p)
     // ---------------------------------------------------------------- TMA producer
     if (lane == 0) {
       for (int s = 0; s < nsub; ++s) {
-        const int slot = s % kEnc2Ring;
-        if (s >= kEnc2Ring) E2_WAIT(0, mbar_wait(&raw_free[slot], (uint32_t)((s / kEnc2Ring) - 1) & 1u));
+        const int slot = s % nring;
+        if (s >= nring) E2_WAIT(0, mbar_wait(&raw_free[slot], (uint32_t)((s / nring) - 1) & 1u));
         const long long r0 = rb4 + (long long)s * kEnc2Sub;
         const int nr = (int)min((long long)kEnc2Sub, re4 - r0) & ~3;   // whole groups of 4 rows; the rest is copied by hand
         const uint32_t bytes = (uint32_t)nr * Kf * 4u;
@@ -675,7 +679,8 @@ __global__ void __launch_bounds__(kEnc2Threads, 1) tc_enc2_kernel(TcLinParams p)
     // ---------------------------------------------------------------- MMA issuer
     if (lane == 0) {
       const uint32_t la = tc_lbo(kTcRows);                     // A (weights) and B (stacked planes) are both 128-row tiles
-      const uint64_t a_desc = tc_smem_desc(smem_u32(Wt), la, 128), step = (uint64_t)((2 * la) >> 4);   // next 32 columns of K
+      const uint64_t a_desc = tc_smem_desc(smem_u32(Wt), la, 128);
+      const uint32_t step = (2 * la) >> 4;                    // next 32 columns of K, in units of 16 bytes
       const uint32_t idesc = tc_idesc_i8(kTcRows, 2 * kEnc2Rows, true, true);
       for (int t = 0; t < ntiles; ++t) {
         const int buf = t & 1;
@@ -683,9 +688,12 @@ __global__ void __launch_bounds__(kEnc2Threads, 1) tc_enc2_kernel(TcLinParams p)
         E2_WAIT(0, mbar_wait(&planes_full[buf], k & 1u));
         if (t >= 2) E2_WAIT(1, mbar_wait(&tmem_free[buf], (k - 1u) & 1u));
         tc_fence_after();
-        const uint32_t d0 = taddr + (uint32_t)buf * (2 * kEnc2Rows);
         const uint64_t b_desc = tc_smem_desc(smem_u32(planes + (size_t)buf * a_bytes), la, 128);
-        for (int j = 0; j < (Kp >> 5); ++j) tc_mma_i8(d0, a_desc + j * step, b_desc + j * step, idesc, j > 0);
+        for (int blk = 0; blk < nblk; ++blk) {
+          const uint32_t d0 = taddr + (uint32_t)(buf * nblk + blk) * (2 * kEnc2Rows);
+          const uint64_t ab = tc_desc_advance(a_desc, (uint32_t)(blk * (w_bytes >> 4)));
+          for (int j = 0; j < (Kp >> 5); ++j) tc_mma_i8(d0, tc_desc_advance(ab, j * step), tc_desc_advance(b_desc, j * step), idesc, j > 0);
+        }
         tc_commit(&mma_done[buf]);
       }
     }
@@ -704,14 +712,14 @@ __global__ void __launch_bounds__(kEnc2Threads, 1) tc_enc2_kernel(TcLinParams p)
     const bool tail = Kf > 128 * KV;
     const float inv = p.in_inv, qmin = p.in_qmin, qmax = p.in_qmax;
     for (int s = 0; s < nsub; ++s) {
-      const int t = s / kEnc2SubPerTile, ts = s - t * kEnc2SubPerTile, buf = t & 1, slot = s % kEnc2Ring;
+      const int t = s / kEnc2SubPerTile, ts = s - t * kEnc2SubPerTile, buf = t & 1, slot = s % nring;
       if (ts == 0 && t >= 2) E2_WAIT(1, mbar_wait(&mma_done[buf], (uint32_t)((t >> 1) - 1) & 1u));   // the MMAs of tile t - 2 have read these planes
       unsigned char* Ah = planes + (size_t)buf * a_bytes;
       unsigned char* Al = Ah + kEnc2Rows * 16;                // rows 64 .. 127 of the same operand tile
       const long long r0 = rb4 + (long long)s * kEnc2Sub;
       const int nr = (int)min((long long)kEnc2Sub, re4 - r0);
       float* raw = reinterpret_cast<float*>(rawb + (size_t)slot * raw_bytes);
-      E2_WAIT(0, mbar_wait(&raw_full[slot], (uint32_t)(s / kEnc2Ring) & 1u));
+      E2_WAIT(0, mbar_wait(&raw_full[slot], (uint32_t)(s / nring) & 1u));
       if (nr & 3) {                                           // <= 3 rows at the very end of the input: plain loads
         if (cw < (nr & 3)) {
           const int rr = (nr & ~3) + cw;
@@ -759,53 +767,64 @@ __global__ void __launch_bounds__(kEnc2Threads, 1) tc_enc2_kernel(TcLinParams p)
         if (tile_done) mbar_arrive(&planes_full[buf]);
       }
     }
-  } else if ((warp & 3) < n_quad) {
+  } else {
     // ---------------------------------------------------------------- epilogue: lane = output column, warp / 4 = row half
     const int quad = warp & 3, half = warp >> 2;
-    const int n = 32 * quad + lane;
-    const bool ncol = n < p.Nfull;
-    const float oinv = (n & 1) ? p.out_inv1 : p.out_inv0, os = (n & 1) ? p.out_scale1 : p.out_scale0;
-    const float cs = ncol ? p.col_scale[n] * oinv : 0.f, cb = ncol && p.bias ? p.bias[n] * oinv : 0.f;
     const float oqmin = p.relu ? fmaxf(p.out_qmin, 0.f) : p.out_qmin, oqmax = p.out_qmax;
     const uint32_t lane_base = (uint32_t)(32 * quad) << 16;
     constexpr int kHalfRows = kEnc2Rows / 2;
-    int corr = 0;                                             // 128 * sum_k W[n][k]: undoes the lo - 128 of the stacked low plane
-    if (n < Np) {
-      const int4* wr = reinterpret_cast<const int4*>(p.W8 + (size_t)n * Kp);
-      for (int c = 0; c < (Kp >> 4); ++c) {
-        const int4 w = wr[c];
-        corr = __dp4a(w.x, 0x01010101, corr); corr = __dp4a(w.y, 0x01010101, corr);
-        corr = __dp4a(w.z, 0x01010101, corr); corr = __dp4a(w.w, 0x01010101, corr);
-      }
-      corr *= 128;
-    }
     const size_t ystride = (size_t)p.y_stride;
+    float cs[2], cb[2], os[2];
+    int corr[2];                                              // 128 * sum_k W[n][k]: undoes the lo - 128 of the stacked low plane
+    bool ncol[2];
+#pragma unroll
+    for (int blk = 0; blk < 2; ++blk) {
+      const int n = 128 * blk + 32 * quad + lane;
+      ncol[blk] = blk < nblk && n < p.Nfull;
+      const float oinv = (n & 1) ? p.out_inv1 : p.out_inv0;
+      os[blk] = (n & 1) ? p.out_scale1 : p.out_scale0;
+      cs[blk] = ncol[blk] ? p.col_scale[n] * oinv : 0.f;
+      cb[blk] = ncol[blk] && p.bias ? p.bias[n] * oinv : 0.f;
+      int c = 0;
+      if (ncol[blk] && n < Np) {
+        const int4* wr = reinterpret_cast<const int4*>(p.W8 + (size_t)n * Kp);
+        for (int i = 0; i < (Kp >> 4); ++i) {
+          const int4 w = wr[i];
+          c = __dp4a(w.x, 0x01010101, c); c = __dp4a(w.y, 0x01010101, c); c = __dp4a(w.z, 0x01010101, c); c = __dp4a(w.w, 0x01010101, c);
+        }
+      }
+      corr[blk] = 128 * c;
+    }
     for (int t = 0; t < ntiles; ++t) {
       const int buf = t & 1;
       const long long row0 = rb4 + (long long)t * kEnc2Rows;
       const int rv = (int)min((long long)kEnc2Rows, re4 - row0);
       E2_WAIT(0, mbar_wait(&mma_done[buf], (uint32_t)(t >> 1) & 1u));
       tc_fence_after();
-      const uint32_t d0 = taddr + (uint32_t)buf * (2 * kEnc2Rows) + lane_base;
-      float* yr = p.Y + (size_t)row0 * p.y_stride + n;
       for (int c0 = half * kHalfRows; c0 < min(rv, (half + 1) * kHalfRows); c0 += 16) {
-        uint32_t vh[16], vl[16];
-        tc_ld16(d0 + c0, vh);
-        tc_ld16(d0 + kEnc2Rows + c0, vl);
-        tc_wait_ld();
-        // all 16 values first (independent chains), then the stores: a predicate per element would serialise the chains
-        float o[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) o[j] = round_clip(fmaf(__int2float_rn((int)vh[j] * 256 + (int)vl[j] + corr), cs, cb), oqmin, oqmax) * os;
-        float* q = yr + (size_t)c0 * ystride;
-        if (ncol) {
-          if (c0 + 16 <= rv) {
+        for (int blk = 0; blk < 2; ++blk) {
+          if (blk >= nblk) break;
+          const uint32_t d0 = taddr + (uint32_t)(buf * nblk + blk) * (2 * kEnc2Rows) + lane_base;
+          uint32_t vh[16], vl[16];
+          tc_ld16(d0 + c0, vh);
+          tc_ld16(d0 + kEnc2Rows + c0, vl);
+          tc_wait_ld();
+          // all 16 values first (independent chains), then the stores: a predicate per element would serialise the chains
+          float o[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j, q += ystride) *q = o[j];
-          } else {
+          for (int j = 0; j < 16; ++j)
+            o[j] = round_clip(fmaf(__int2float_rn((int)vh[j] * 256 + (int)vl[j] + corr[blk]), cs[blk], cb[blk]), oqmin, oqmax) * os[blk];
+          float* q = p.Y + (size_t)(row0 + c0) * ystride + 128 * blk + 32 * quad + lane;
+          if (ncol[blk]) {
+            if (c0 + 16 <= rv) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j, q += ystride)
-              if (c0 + j < rv) *q = o[j];
+              for (int j = 0; j < 16; ++j, q += ystride) *q = o[j];
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j, q += ystride)
+                if (c0 + j < rv) *q = o[j];
+            }
           }
         }
       }
@@ -820,7 +839,7 @@ __global__ void __launch_bounds__(kEnc2Threads, 1) tc_enc2_kernel(TcLinParams p)
 #endif
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tc_dealloc(tmem_slot, 256);
+  if (warp == 0) tc_dealloc(tmem_slot, nblk == 1 ? 256 : 512);
 }
 
 // ------------------------------------------------------------------------------------------- decoder (wide, odd N)
@@ -974,7 +993,9 @@ constexpr int kDec2Epi = 16, kDec2Conv = 8, kDec2Ring = 6, kDec2Sub = 32;   // r
 constexpr int kDec2OutBufs = 3;    // output half-tiles (32 rows of Nf floats) in flight
 constexpr int kDec2Threads = 32 * (kDec2Epi + 2 + kDec2Conv);
 
+template <int KV, int NRING, int NOUT>
 __global__ void __launch_bounds__(kDec2Threads, 1) tc_dec2_kernel(TcLinParams p) {
+  constexpr int nring = NRING, nout = NOUT;                   // compile-time: the slot / phase arithmetic sits in every loop
   extern __shared__ __align__(128) unsigned char smem[];
   const int Kp = p.Kp, Np = p.Np, Nf = p.Nfull;
   const int nblk = (Np + 127) >> 7;                           // blocks of 128 output columns (<= 2)
@@ -987,7 +1008,7 @@ __global__ void __launch_bounds__(kDec2Threads, 1) tc_dec2_kernel(TcLinParams p)
   // output tile with the pitch of the global rows: 64 rows of Nf floats are ONE contiguous block of global memory, which
   // leaves as one bulk store (full lines; per-row warp stores of 128 bytes at a 4-byte alignment reach only half of the
   // HBM write bandwidth: 3.5 of 6.8 TB/s measured, profiles/r02_hbm_write.md)
-  float* outT0 = reinterpret_cast<float*>(rawb + (size_t)kDec2Ring * raw_bytes);   // three half-tiles: one or two leave while the next is assembled
+  float* outT0 = reinterpret_cast<float*>(rawb + (size_t)nring * raw_bytes);   // three half-tiles: one or two leave while the next is assembled
   __shared__ __align__(8) uint64_t planes_full[2], mma_done[2], tmem_free[2], raw_full[kDec2Ring], raw_free[kDec2Ring];
   __shared__ uint32_t tmem_slot;
   __shared__ int extra_n[2][kDec2Rows];
@@ -999,7 +1020,7 @@ __global__ void __launch_bounds__(kDec2Threads, 1) tc_dec2_kernel(TcLinParams p)
   if (warp == 0) tc_alloc(&tmem_slot, 512);
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) { mbar_init(&planes_full[i], kDec2Conv); mbar_init(&mma_done[i], 1); mbar_init(&tmem_free[i], kDec2Epi); }
-    for (int i = 0; i < kDec2Ring; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_free[i], kDec2Conv / 2); }
+    for (int i = 0; i < nring; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_free[i], kDec2Conv / 2); }
     fence_mbar_init();
   }
   {
@@ -1026,7 +1047,7 @@ __global__ void __launch_bounds__(kDec2Threads, 1) tc_dec2_kernel(TcLinParams p)
   if (warp == kDec2Epi) {
     // ---------------------------------------------------------------- MMA issuer
     if (lane == 0) {
-      const uint64_t step = (uint64_t)((2 * la) >> 4);
+      const uint32_t step = (2 * la) >> 4;
       const uint32_t idesc = tc_idesc_i8(kTcRows, 2 * kDec2Rows, true, true);
       for (int t = 0; t < ntiles; ++t) {
         const int buf = t & 1;
@@ -1038,7 +1059,7 @@ __global__ void __launch_bounds__(kDec2Threads, 1) tc_dec2_kernel(TcLinParams p)
         for (int blk = 0; blk < nblk; ++blk) {
           const uint64_t a_desc = tc_smem_desc(smem_u32(Wt + (size_t)blk * w_bytes), la, 128);
           const uint32_t d0 = taddr + (uint32_t)buf * 256u + (uint32_t)blk * 128u;
-          for (int j = 0; j < (Kp >> 5); ++j) tc_mma_i8(d0, a_desc + j * step, b_desc + j * step, idesc, j > 0);
+          for (int j = 0; j < (Kp >> 5); ++j) tc_mma_i8(d0, tc_desc_advance(a_desc, j * step), tc_desc_advance(b_desc, j * step), idesc, j > 0);
         }
         tc_commit(&mma_done[buf]);
       }
@@ -1048,8 +1069,8 @@ __global__ void __launch_bounds__(kDec2Threads, 1) tc_dec2_kernel(TcLinParams p)
     if (lane == 0) {
       const int nhalf = (int)((re - rb + kDec2Sub - 1) / kDec2Sub);
       for (int sh = 0; sh < nhalf; ++sh) {
-        const int slot = sh % kDec2Ring;
-        if (sh >= kDec2Ring) mbar_wait(&raw_free[slot], (uint32_t)((sh / kDec2Ring) - 1) & 1u);
+        const int slot = sh % nring;
+        if (sh >= nring) mbar_wait(&raw_free[slot], (uint32_t)((sh / nring) - 1) & 1u);
         const long long r0 = rb + (long long)sh * kDec2Sub;
         const uint32_t bytes = (uint32_t)min((long long)kDec2Sub, re - r0) * p.Kfull * 4u;
         mbar_expect_tx(&raw_full[slot], bytes);
@@ -1060,16 +1081,22 @@ __global__ void __launch_bounds__(kDec2Threads, 1) tc_dec2_kernel(TcLinParams p)
     // ---------------------------------------------------------------- converters
     const int cw = warp - kDec2Epi - 2;
     constexpr int RPW = kDec2Rows / kDec2Conv;
-    const uint32_t loff = (uint32_t)(lane >> 2) * la + 4u * (lane & 3);
-    const bool wval = 4 * lane < Kp;
-    const int kcol = 4 * lane < p.Kfull ? 4 * lane : 0;
-    int wn[4];
+    // lane owns input columns 128 i + 4 lane .. + 3 of every 128-column block i (natural K order: one 32-bit plane store)
+    uint32_t loff[KV];
+    bool wval[KV];
+    int kcol[KV], wn[KV][4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) wn[e] = wval && p.WN ? (int)p.WN[4 * lane + e] : 0;
+    for (int i = 0; i < KV; ++i) {
+      loff[i] = (uint32_t)(8 * i + (lane >> 2)) * la + 4u * (lane & 3);
+      wval[i] = 128 * i + 4 * lane < Kp;
+      kcol[i] = 128 * i + 4 * lane < p.Kfull ? 128 * i + 4 * lane : 0;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) wn[i][e] = wval[i] && p.WN ? (int)p.WN[128 * i + 4 * lane + e] : 0;
+    }
     const float inv = p.in_inv, qmin = p.in_qmin, qmax = p.in_qmax;
     for (int t = 0; t < ntiles; ++t) {
       const int buf = t & 1;
-      const int hh = cw / (kDec2Conv / 2), sh = 2 * t + hh, slot = sh % kDec2Ring;   // this warp's rows lie in half-tile sh
+      const int hh = cw / (kDec2Conv / 2), sh = 2 * t + hh, slot = sh % nring;   // this warp's rows lie in half-tile sh
       const int rvh = (int)min((long long)kDec2Sub, re - (rb + (long long)sh * kDec2Sub));   // rows of that half (<= 0: none)
       if (t >= 2) {                                           // tile t - 2: its MMAs have read the planes, its epilogue the extra column
         E2_WAIT(0, mbar_wait(&mma_done[buf], (uint32_t)((t >> 1) - 1) & 1u));
@@ -1078,31 +1105,37 @@ __global__ void __launch_bounds__(kDec2Threads, 1) tc_dec2_kernel(TcLinParams p)
       unsigned char* Ah = planes + (size_t)buf * a_bytes;
       unsigned char* Al = Ah + kDec2Rows * 16;
       if (rvh > 0) {
-        E2_WAIT(2, mbar_wait(&raw_full[slot], (uint32_t)(sh / kDec2Ring) & 1u));
-        const float* rs = reinterpret_cast<const float*>(rawb + (size_t)slot * raw_bytes) + kcol;
+        E2_WAIT(2, mbar_wait(&raw_full[slot], (uint32_t)(sh / nring) & 1u));
+        const float* rs = reinterpret_cast<const float*>(rawb + (size_t)slot * raw_bytes);
         const int lr0 = (cw - hh * (kDec2Conv / 2)) * RPW;     // first row of this warp inside the half-tile
         // four rows at a time: enough independent work per lane, few enough live registers (no spills at 832 threads)
 #pragma unroll
         for (int q0 = 0; q0 < RPW; q0 += 4) {
-          float4 raw[4];
+          float4 raw[4][KV];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) raw[q] = *reinterpret_cast<const float4*>(rs + (size_t)min(lr0 + q0 + q, rvh - 1) * p.Kfull);
+          for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int i = 0; i < KV; ++i)
+              raw[q][i] = *reinterpret_cast<const float4*>(rs + (size_t)min(lr0 + q0 + q, rvh - 1) * p.Kfull + kcol[i]);
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int r = cw * RPW + q0 + q;
-            const float xv[4] = {raw[q].x, raw[q].y, raw[q].z, raw[q].w};
-            uint32_t b4[4];
             int part = 0;
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              b4[e] = quant_bits(xv[e], inv, qmin, qmax);
-              part += (int)(short)b4[e] * wn[e];
-            }
-            uint32_t lo, hi;
-            split_planes(b4[0], b4[1], b4[2], b4[3], lo, hi);
-            if (wval) {
-              *reinterpret_cast<uint32_t*>(Ah + loff + (uint32_t)r * 16u) = hi;
-              *reinterpret_cast<uint32_t*>(Al + loff + (uint32_t)r * 16u) = lo ^ 0x80808080u;
+            for (int i = 0; i < KV; ++i) {
+              const float xv[4] = {raw[q][i].x, raw[q][i].y, raw[q][i].z, raw[q][i].w};
+              uint32_t b4[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                b4[e] = quant_bits(xv[e], inv, qmin, qmax);
+                part += (int)(short)b4[e] * wn[i][e];
+              }
+              uint32_t lo, hi;
+              split_planes(b4[0], b4[1], b4[2], b4[3], lo, hi);
+              if (wval[i]) {
+                *reinterpret_cast<uint32_t*>(Ah + loff[i] + (uint32_t)r * 16u) = hi;
+                *reinterpret_cast<uint32_t*>(Al + loff[i] + (uint32_t)r * 16u) = lo ^ 0x80808080u;
+              }
             }
             const int tot = __reduce_add_sync(0xffffffffu, part);
             if (lane == 0) extra_n[buf][r] = tot;
@@ -1152,10 +1185,12 @@ __global__ void __launch_bounds__(kDec2Threads, 1) tc_dec2_kernel(TcLinParams p)
       const int rv = (int)min((long long)kDec2Rows, re - row0);
       E2_WAIT(0, mbar_wait(&mma_done[buf], (uint32_t)(t >> 1) & 1u));
       tc_fence_after();
-      if (tid == 0) bulk_wait_read1();                        // only the second half of the previous tile may still be leaving
+      if (tid == 0) {                                         // three buffers: the second half of the previous tile may still be leaving
+        if (nout >= 3) bulk_wait_read1(); else bulk_wait_read0();
+      }
       asm volatile("bar.sync 2, %0;" ::"r"(32 * kDec2Epi) : "memory");
       const int c0 = 16 * rq, hh = rq >> 1;                   // rows c0 .. c0 + 15 of the tile lie in half-tile 2 t + hh
-      float* outT = outT0 + (size_t)((2 * t + hh) % kDec2OutBufs) * kDec2Sub * Nf;
+      float* outT = outT0 + (size_t)((2 * t + hh) % nout) * kDec2Sub * Nf;
       if (c0 < rv) {
 #pragma unroll
         for (int blk = 0; blk < 2; ++blk) {
@@ -1185,13 +1220,13 @@ __global__ void __launch_bounds__(kDec2Threads, 1) tc_dec2_kernel(TcLinParams p)
       if (tid == 0) {
         for (int h2 = 0; h2 < 2; ++h2) {
           const int nr = min(kDec2Sub, rv4 - kDec2Sub * h2);
-          if (nr > 0) bulk_s2g(p.Y + (size_t)(row0 + kDec2Sub * h2) * ystride, outT0 + (size_t)((2 * t + h2) % kDec2OutBufs) * kDec2Sub * Nf, (uint32_t)((size_t)nr * Nf * 4));
+          if (nr > 0) bulk_s2g(p.Y + (size_t)(row0 + kDec2Sub * h2) * ystride, outT0 + (size_t)((2 * t + h2) % nout) * kDec2Sub * Nf, (uint32_t)((size_t)nr * Nf * 4));
           bulk_commit();
         }
       }
       if (rv4 != rv) {
         const int h2 = rv4 / kDec2Sub;
-        const float* src = outT0 + (size_t)((2 * t + h2) % kDec2OutBufs) * kDec2Sub * Nf + (size_t)(rv4 - kDec2Sub * h2) * Nf;
+        const float* src = outT0 + (size_t)((2 * t + h2) % nout) * kDec2Sub * Nf + (size_t)(rv4 - kDec2Sub * h2) * Nf;
         for (int i = tid; i < (rv - rv4) * Nf; i += 32 * kDec2Epi) p.Y[(size_t)(row0 + rv4) * ystride + i] = src[i];
         asm volatile("bar.sync 2, %0;" ::"r"(32 * kDec2Epi) : "memory");
       }
@@ -2308,17 +2343,24 @@ int tc_linear_launch(const TcLinearDev& d, const float* X, float* Y, long long r
     const size_t dsm = tc_tile_bytes8(d.Np, p.Kp) + 2 * tc_tile_bytes8(kTcRows, p.Kp) + (size_t)kTcRows * d.Nfull * 4 + (size_t)d.Nfull * sizeof(float2);
     // warp-specialised version (S5B200_DEC_V2=0 selects the first one)
     static const bool dec_v2 = [] { const char* e = getenv("S5B200_DEC_V2"); return !e || atoi(e) != 0; }();
-    if (dec_v2 && d.KV == 1 && d.Np <= 256 && (d.Np & 31) == 0 && (p.Kp & 31) == 0 && aligned16(Y) && d.Nfull == d.Np + 1 &&
-        2 * tc_tile_bytes8(kTcRows, p.Kp) + 2 * tc_tile_bytes8(2 * kDec2Rows, p.Kp) + (size_t)kDec2Ring * kDec2Sub * d.Kfull * 4 +
-                (size_t)kDec2OutBufs * kDec2Sub * d.Nfull * 4 + 2048 <= 227 * 1024) {
-      const size_t dsm2 = 2 * tc_tile_bytes8(kTcRows, p.Kp) + 2 * tc_tile_bytes8(2 * kDec2Rows, p.Kp) + (size_t)kDec2Ring * kDec2Sub * d.Kfull * 4 +
-                          (size_t)kDec2OutBufs * kDec2Sub * d.Nfull * 4;
-      S5_CUDA(cudaFuncSetAttribute(tc_dec2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm2));
-      const int grid = (int)std::max<long long>(1, std::min<long long>((rows + 63) / 64, (long long)sm_count()));
-      ProfScope prof(kclass, st);
-      tc_dec2_kernel<<<grid, kDec2Threads, dsm2, st>>>(p);
-      S5_LAUNCH_CHECK();
-      return S5_OK;
+    if (dec_v2 && d.Np <= 256 && (d.Np & 31) == 0 && (p.Kp & 31) == 0 && aligned16(Y) && d.Nfull == d.Np + 1) {
+      // the deepest input ring / most output half-tiles that fit: (3 out, >= 3 ring), (3, 2), (2, 2)
+      const size_t fixed = 2 * tc_tile_bytes8(kTcRows, p.Kp) + 2 * tc_tile_bytes8(2 * kDec2Rows, p.Kp);
+      const size_t slot = (size_t)kDec2Sub * d.Kfull * 4, ohalf = (size_t)kDec2Sub * d.Nfull * 4;
+      // instantiated shapes: (ring 6, 3 output half-tiles) where it fits (K <= 128), else (2, 2)
+      int nring = 0, nout = 0;
+      if (fixed + 6 * slot + 3 * ohalf + 2048 <= 227 * 1024) { nring = 6; nout = 3; }
+      else if (fixed + 2 * slot + 2 * ohalf + 2048 <= 227 * 1024) { nring = 2; nout = 2; }
+      if (nring) {
+        const size_t dsm2 = fixed + nring * slot + nout * ohalf;
+        auto kernel = nring == 6 ? (d.KV == 1 ? tc_dec2_kernel<1, 6, 3> : tc_dec2_kernel<2, 6, 3>) : (d.KV == 1 ? tc_dec2_kernel<1, 2, 2> : tc_dec2_kernel<2, 2, 2>);
+        S5_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm2));
+        const int grid = (int)std::max<long long>(1, std::min<long long>((rows + 63) / 64, (long long)sm_count()));
+        ProfScope prof(kclass, st);
+        kernel<<<grid, kDec2Threads, dsm2, st>>>(p);
+        S5_LAUNCH_CHECK();
+        return S5_OK;
+      }
     }
     if (dec_tma && d.KV == 1 && d.Np <= 256 && (d.Np & 31) == 0 && aligned16(Y) && dsm + 2048 <= 227 * 1024) {
       S5_CUDA(cudaFuncSetAttribute(tc_dec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
@@ -2332,15 +2374,21 @@ int tc_linear_launch(const TcLinearDev& d, const float* X, float* Y, long long r
   }
   // unaligned contiguous rows (encoder): TMA-fed raw-row ring, one CTA per SM
   static const bool enc_tma = [] { const char* e = getenv("S5B200_ENC_TMA"); return !e || atoi(e) != 0; }();
-  if (enc_tma && !vec4 && !bn && aligned16(X) && aligned16(Y) && d.Np <= 128 && (d.Np & 31) == 0 && (d.Nfull & 3) == 0 && d.Nfull <= d.Np) {
+  if (enc_tma && !vec4 && !bn && aligned16(X) && aligned16(Y) && d.Np <= 256 && (d.Np & 31) == 0 && (d.Nfull & 3) == 0 && d.Nfull <= d.Np) {
     const size_t raw_bytes = (((size_t)kEncSub * d.Kfull * 4) + 127) & ~(size_t)127;
     const size_t esm = tc_tile_bytes8(d.Np, p.Kp) + 2 * tc_tile_bytes8(kTcRows, p.Kp) + kEncRing * raw_bytes + (size_t)d.Np * sizeof(float2);
     // warp-specialised version (S5B200_ENC_V2=0 selects the first one)
     static const bool enc_v2 = [] { const char* e = getenv("S5B200_ENC_V2"); return !e || atoi(e) != 0; }();
     const size_t raw2 = (((size_t)kEnc2Sub * d.Kfull * 4) + 127) & ~(size_t)127;
-    const size_t esm2 = tc_tile_bytes8(kTcRows, p.Kp) + 2 * tc_tile_bytes8(2 * kEnc2Rows, p.Kp) + kEnc2Ring * raw2;
-    if (enc_v2 && esm2 + 2048 <= 227 * 1024) {
-      auto kernel = d.KV == 1 ? tc_enc2_kernel<1> : tc_enc2_kernel<2>;
+    const int nblk2 = (d.Np + 127) >> 7;
+    int nring = kEnc2Ring;
+    size_t esm2 = 0;
+    for (; nring >= 2; --nring) {                              // the deepest ring that fits
+      esm2 = (size_t)nblk2 * tc_tile_bytes8(kTcRows, p.Kp) + 2 * tc_tile_bytes8(2 * kEnc2Rows, p.Kp) + nring * raw2;
+      if (esm2 + 2048 <= 227 * 1024) break;
+    }
+    if (enc_v2 && nring >= 2) {
+      auto kernel = d.KV == 1 ? (nring == 3 ? tc_enc2_kernel<1, 3> : tc_enc2_kernel<1, 2>) : (nring == 3 ? tc_enc2_kernel<2, 3> : tc_enc2_kernel<2, 2>);
       S5_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esm2));
       const int grid = (int)std::max<long long>(1, std::min<long long>((rows + 63) / 64, (long long)sm_count()));
       ProfScope prof(kclass, st);
@@ -2348,7 +2396,7 @@ int tc_linear_launch(const TcLinearDev& d, const float* X, float* Y, long long r
       S5_LAUNCH_CHECK();
       return S5_OK;
     }
-    if (esm + 2048 <= 227 * 1024 && 2 * tc_tile_bytes8(kTcRows, p.Kp) >= (size_t)kTcRows * (d.Np + 4) * 4) {
+    if (d.Np <= 128 && esm + 2048 <= 227 * 1024 && 2 * tc_tile_bytes8(kTcRows, p.Kp) >= (size_t)kTcRows * (d.Np + 4) * 4) {
       auto kernel = d.KV == 1 ? tc_enc_kernel<1> : tc_enc_kernel<2>;
       S5_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esm));
       const int grid = (int)std::max<long long>(1, std::min<long long>((rows + 63) / 64, (long long)sm_count()));
