@@ -993,7 +993,9 @@ constexpr int kDec2Epi = 16, kDec2Conv = 8, kDec2Ring = 6, kDec2Sub = 32;   // r
 constexpr int kDec2OutBufs = 3;    // output half-tiles (32 rows of Nf floats) in flight
 constexpr int kDec2Threads = 32 * (kDec2Epi + 2 + kDec2Conv);
 
-template <int KV, int NRING, int NOUT>
+// BN: BatchNorm on the input (B projection).  DIRECT: output rows are line aligned (Nfull = Np, a multiple of 32 floats):
+// no extra column, no shared output tile - the epilogue stores from registers as in tc_enc2_kernel (NOUT is unused).
+template <int KV, int NRING, int NOUT, bool BN, bool DIRECT>
 __global__ void __launch_bounds__(kDec2Threads, 1) tc_dec2_kernel(TcLinParams p) {
   constexpr int nring = NRING, nout = NOUT;                   // compile-time: the slot / phase arithmetic sits in every loop
   extern __shared__ __align__(128) unsigned char smem[];
@@ -1094,6 +1096,17 @@ __global__ void __launch_bounds__(kDec2Threads, 1) tc_dec2_kernel(TcLinParams p)
       for (int e = 0; e < 4; ++e) wn[i][e] = wval[i] && p.WN ? (int)p.WN[128 * i + 4 * lane + e] : 0;
     }
     const float inv = p.in_inv, qmin = p.in_qmin, qmax = p.in_qmax;
+    // BatchNorm folded with the (power-of-two) input scale: ((x - sub) * mul + add) / s == (x - sub) * (mul / s) + add / s
+    float bsub[BN ? KV : 1][4], bmul[BN ? KV : 1][4], badd[BN ? KV : 1][4];
+    if constexpr (BN) {
+#pragma unroll
+      for (int i = 0; i < KV; ++i)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int k = min(128 * i + 4 * lane + e, p.Kfull - 1);
+          bsub[i][e] = p.in_sub[k]; bmul[i][e] = p.in_mul[k] * inv; badd[i][e] = p.in_add ? p.in_add[k] * inv : 0.f;
+        }
+    }
     for (int t = 0; t < ntiles; ++t) {
       const int buf = t & 1;
       const int hh = cw / (kDec2Conv / 2), sh = 2 * t + hh, slot = sh % nring;   // this warp's rows lie in half-tile sh
@@ -1127,8 +1140,9 @@ __global__ void __launch_bounds__(kDec2Threads, 1) tc_dec2_kernel(TcLinParams p)
               uint32_t b4[4];
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                b4[e] = quant_bits(xv[e], inv, qmin, qmax);
-                part += (int)(short)b4[e] * wn[i][e];
+                if constexpr (BN) b4[e] = quant_bits((xv[e] - bsub[i][e]) * bmul[i][e] + badd[i][e], 1.f, qmin, qmax);
+                else b4[e] = quant_bits(xv[e], inv, qmin, qmax);
+                if constexpr (!DIRECT) part += (int)(short)b4[e] * wn[i][e];
               }
               uint32_t lo, hi;
               split_planes(b4[0], b4[1], b4[2], b4[3], lo, hi);
@@ -1137,8 +1151,10 @@ __global__ void __launch_bounds__(kDec2Threads, 1) tc_dec2_kernel(TcLinParams p)
                 *reinterpret_cast<uint32_t*>(Al + loff[i] + (uint32_t)r * 16u) = lo ^ 0x80808080u;
               }
             }
-            const int tot = __reduce_add_sync(0xffffffffu, part);
-            if (lane == 0) extra_n[buf][r] = tot;
+            if constexpr (!DIRECT) {
+              const int tot = __reduce_add_sync(0xffffffffu, part);
+              if (lane == 0) extra_n[buf][r] = tot;
+            }
           }
         }
         __syncwarp();
@@ -1185,6 +1201,39 @@ __global__ void __launch_bounds__(kDec2Threads, 1) tc_dec2_kernel(TcLinParams p)
       const int rv = (int)min((long long)kDec2Rows, re - row0);
       E2_WAIT(0, mbar_wait(&mma_done[buf], (uint32_t)(t >> 1) & 1u));
       tc_fence_after();
+      if constexpr (DIRECT) {
+        const int c0 = 16 * rq;
+        if (c0 < rv) {
+#pragma unroll
+          for (int blk = 0; blk < 2; ++blk) {
+            if (blk >= nblk) break;
+            const uint32_t d0 = taddr + (uint32_t)buf * 256u + (uint32_t)blk * 128u + lane_base;
+            uint32_t vh[16], vl[16];
+            tc_ld16(d0 + c0, vh);
+            tc_ld16(d0 + kDec2Rows + c0, vl);
+            tc_wait_ld();
+            float o[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              o[j] = round_clip(fmaf(__int2float_rn((int)vh[j] * 256 + (int)vl[j] + corr[blk]), cs[blk], cb[blk]), oqmin, oqmax) * os[blk];
+            float* q = p.Y + (size_t)(row0 + c0) * ystride + 128 * blk + 32 * quad + lane;
+            if (ncol[blk]) {
+              if (c0 + 16 <= rv) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j, q += ystride) *q = o[j];
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j, q += ystride)
+                  if (c0 + j < rv) *q = o[j];
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_free[buf]);
+        continue;
+      }
       if (tid == 0) {                                         // three buffers: the second half of the previous tile may still be leaving
         if (nout >= 3) bulk_wait_read1(); else bulk_wait_read0();
       }
@@ -1231,7 +1280,7 @@ __global__ void __launch_bounds__(kDec2Threads, 1) tc_dec2_kernel(TcLinParams p)
         asm volatile("bar.sync 2, %0;" ::"r"(32 * kDec2Epi) : "memory");
       }
     }
-    if (tid == 0) bulk_wait0();
+    if (!DIRECT && tid == 0) bulk_wait0();
   }
 #ifdef S5_ENC2_TRACE
   if (blockIdx.x == 3 && lane == 0 && (warp == 0 || warp == 5 || warp == 15 || warp == 16 || warp == 18 || warp == 25))
@@ -2353,7 +2402,8 @@ int tc_linear_launch(const TcLinearDev& d, const float* X, float* Y, long long r
       else if (fixed + 2 * slot + 2 * ohalf + 2048 <= 227 * 1024) { nring = 2; nout = 2; }
       if (nring) {
         const size_t dsm2 = fixed + nring * slot + nout * ohalf;
-        auto kernel = nring == 6 ? (d.KV == 1 ? tc_dec2_kernel<1, 6, 3> : tc_dec2_kernel<2, 6, 3>) : (d.KV == 1 ? tc_dec2_kernel<1, 2, 2> : tc_dec2_kernel<2, 2, 2>);
+        auto kernel = nring == 6 ? (d.KV == 1 ? tc_dec2_kernel<1, 6, 3, false, false> : tc_dec2_kernel<2, 6, 3, false, false>)
+                                 : (d.KV == 1 ? tc_dec2_kernel<1, 2, 2, false, false> : tc_dec2_kernel<2, 2, 2, false, false>);
         S5_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm2));
         const int grid = (int)std::max<long long>(1, std::min<long long>((rows + 63) / 64, (long long)sm_count()));
         ProfScope prof(kclass, st);
@@ -2402,6 +2452,22 @@ int tc_linear_launch(const TcLinearDev& d, const float* X, float* Y, long long r
       const int grid = (int)std::max<long long>(1, std::min<long long>((rows + 63) / 64, (long long)sm_count()));
       ProfScope prof(kclass, st);
       kernel<<<grid, kEncThreads, esm, st>>>(p);
+      S5_LAUNCH_CHECK();
+      return S5_OK;
+    }
+  }
+  // aligned input rows, line-aligned output rows (B projection; any Dense with K % 4 == 0 and N % 32 == 0): the warp-specialised
+  // kernel with direct register stores (S5B200_LIN_V2=0 selects the first version)
+  static const bool lin_v2 = [] { const char* e = getenv("S5B200_LIN_V2"); return !e || atoi(e) != 0; }();
+  if (lin_v2 && vec4 && aligned16(Y) && d.Np <= 256 && (d.Np & 31) == 0 && d.Nfull == d.Np && (p.Kp & 31) == 0 && (!bn || in_mul)) {
+    const size_t lsm = 2 * tc_tile_bytes8(kTcRows, p.Kp) + 2 * tc_tile_bytes8(2 * kDec2Rows, p.Kp) + 4 * (size_t)kDec2Sub * d.Kfull * 4;
+    if (lsm + 2048 <= 227 * 1024) {
+      auto kernel = d.KV == 1 ? (bn ? tc_dec2_kernel<1, 4, 1, true, true> : tc_dec2_kernel<1, 4, 1, false, true>)
+                              : (bn ? tc_dec2_kernel<2, 4, 1, true, true> : tc_dec2_kernel<2, 4, 1, false, true>);
+      S5_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsm));
+      const int grid = (int)std::max<long long>(1, std::min<long long>((rows + 63) / 64, (long long)sm_count()));
+      ProfScope prof(kclass, st);
+      kernel<<<grid, kDec2Threads, lsm, st>>>(p);
       S5_LAUNCH_CHECK();
       return S5_OK;
     }
