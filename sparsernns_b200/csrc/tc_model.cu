@@ -1633,11 +1633,8 @@ __global__ void __launch_bounds__(kGluThreads, 1) tc_glu_kernel(const __grid_con
         // ---- E_B: Bu = FQ(acc * s_u s_w) -> shared tile (the planes are dead)
         if (erow0 < rv) {
           const int cwb = K1 >> 1, cb0 = (warp >> 2) * cwb;
-          for (int c0 = cb0; c0 < cb0 + cwb; c0 += 8) {
-            uint32_t vh[8], vl[8];
-            tc_ld8(tcol + lane_base + c0, vh);
-            tc_ld8(tcol + lane_base + 128 + c0, vl);
-            tc_wait_ld();
+          // two register sets: the TMEM loads of the next 8 columns are in flight while these 8 are post-processed
+          auto eb8 = [&](const uint32_t (&vh)[8], const uint32_t (&vl)[8], int c0) {
             float o[8];
 #pragma unroll
             for (int j = 0; j < 8; j += 4) {
@@ -1652,6 +1649,21 @@ __global__ void __launch_bounds__(kGluThreads, 1) tc_glu_kernel(const __grid_con
             float* dst = BuT + (size_t)erow * ldB + c0;
             *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
             *reinterpret_cast<float4*>(dst + 4) = make_float4(o[4], o[5], o[6], o[7]);
+          };
+          uint32_t ah[8], al[8], bh[8], bl[8];
+          tc_ld8(tcol + lane_base + cb0, ah);
+          tc_ld8(tcol + lane_base + 128 + cb0, al);
+          for (int c0 = cb0; c0 < cb0 + cwb; c0 += 16) {     // cwb is a multiple of 16
+            tc_wait_ld();
+            tc_ld8(tcol + lane_base + c0 + 8, bh);
+            tc_ld8(tcol + lane_base + 128 + c0 + 8, bl);
+            eb8(ah, al, c0);
+            tc_wait_ld();
+            if (c0 + 16 < cb0 + cwb) {
+              tc_ld8(tcol + lane_base + c0 + 16, ah);
+              tc_ld8(tcol + lane_base + 128 + c0 + 16, al);
+            }
+            eb8(bh, bl, c0 + 8);
           }
         }
         tc_fence_before();
@@ -1670,9 +1682,17 @@ __global__ void __launch_bounds__(kGluThreads, 1) tc_glu_kernel(const __grid_con
         for (int i = 0; i < 32; ++i, q += P) v[i] = *q;
       }
       float2 x = make_float2(0.f, 0.f), mm = lamS;
+      // full 32-frame segment (every segment of every tile but a clip's last one): straight-line code.  With a predicate
+      // per step the compiler wraps every step into its own branch region and re-derives the loop invariants inside it.
+      const bool full_seg = len == 32;
+      if (full_seg) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i)
-        if (i < len) x = cfmaf(lam, x, v[i]);
+        for (int i = 0; i < 32; ++i) x = cfmaf(lam, x, v[i]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (i < len) x = cfmaf(lam, x, v[i]);
+      }
       if (len != sr) {                                        // short segment (end of a clip): lam^len
         mm = make_float2(1.f, 0.f);
         for (int i = 0; i < len; ++i) mm = cmulf(mm, lam);
@@ -1740,18 +1760,32 @@ __global__ void __launch_bounds__(kGluThreads, 1) tc_glu_kernel(const __grid_con
       float2 cin = carry_s[sp];
       for (int q = 0; q < sseg; ++q) cin = cfmaf(seg_mul[q * P + sp], cin, seg_agg[q * P + sp]);
       x = cin;
+      auto emit_state = [&](float2 z, int i) {                // complex ReLU, bf16 hi / lo split, operand planes
+        const bool keep = !relu_scan || (z.x > 0.f) || (z.x == 0.f && z.y > 0.f);
+        const float v0 = keep ? z.x : 0.f, v1 = keep ? z.y * xs_odd_mul : 0.f;
+        const uint32_t h01 = pack_bf2(v0, v1);
+        const uint32_t l01 = pack_bf2(v0 - __uint_as_float(h01 << 16), v1 - __uint_as_float(h01 & 0xFFFF0000u));
+        const uint32_t o = poff + (uint32_t)(sseg * sr + i) * 16u;
+        *reinterpret_cast<uint32_t*>(P1h + o) = h01;
+        *reinterpret_cast<uint32_t*>(P1l + o) = l01;
+      };
+      if (full_seg) {
+        // the dependent chain first, the states back into v[]; the (independent) post-processing of the 32 states afterwards
 #pragma unroll
-      for (int i = 0; i < 32; ++i)
-        if (i < len) {
+        for (int i = 0; i < 32; ++i) {
           x = cfmaf(lam, x, v[i]);
-          const bool keep = !relu_scan || (x.x > 0.f) || (x.x == 0.f && x.y > 0.f);
-          const float v0 = keep ? x.x : 0.f, v1 = keep ? x.y * xs_odd_mul : 0.f;
-          const uint32_t h01 = pack_bf2(v0, v1);
-          const uint32_t l01 = pack_bf2(v0 - __uint_as_float(h01 << 16), v1 - __uint_as_float(h01 & 0xFFFF0000u));
-          const uint32_t o = poff + (uint32_t)(sseg * sr + i) * 16u;
-          *reinterpret_cast<uint32_t*>(P1h + o) = h01;
-          *reinterpret_cast<uint32_t*>(P1l + o) = l01;
+          v[i] = x;
         }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) emit_state(v[i], i);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (i < len) {
+            x = cfmaf(lam, x, v[i]);
+            emit_state(x, i);
+          }
+      }
     } else {
     // ---- S: xs -> two bf16 planes (value = hi + lo to 16 mantissa bits); 8 rows in flight per lane
     for (int rb = warp * 8; rb < rv; rb += NW * 8) {
@@ -1873,11 +1907,7 @@ __global__ void __launch_bounds__(kGluThreads, 1) tc_glu_kernel(const __grid_con
     TC_TRACE_MARK(tid == 0);
     // ---- E2: o = FQ(out2(x1)); right-gate code FQ(sigmoid(o)) -> second half of the T row
     if (erow0 < rv) {
-      for (int c0 = cbeg; c0 < cbeg + cw; c0 += 8) {
-        uint32_t vh[8], vl[8];
-        tc_ld8(tcol + lane_base + c0, vh);
-        tc_ld8(tcol + lane_base + 128 + c0, vl);
-        tc_wait_ld();
+      auto e2_8 = [&](const uint32_t (&vh)[8], const uint32_t (&vl)[8], int c0) {
         uint32_t sb[8];
 #pragma unroll
         for (int j = 0; j < 8; j += 4) {
@@ -1898,6 +1928,22 @@ __global__ void __launch_bounds__(kGluThreads, 1) tc_glu_kernel(const __grid_con
         pk.x = __byte_perm(sb[0], sb[1], 0x5410); pk.y = __byte_perm(sb[2], sb[3], 0x5410);
         pk.z = __byte_perm(sb[4], sb[5], 0x5410); pk.w = __byte_perm(sb[6], sb[7], 0x5410);
         *reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(T + (size_t)erow * ldT) + 2 * H + 2 * c0) = pk;
+      };
+      // two register sets: the TMEM loads of the next 8 columns are in flight while these 8 are post-processed
+      uint32_t ah[8], al[8], bh[8], bl[8];
+      tc_ld8(tcol + lane_base + cbeg, ah);
+      tc_ld8(tcol + lane_base + 128 + cbeg, al);
+      for (int c0 = cbeg; c0 < cbeg + cw; c0 += 16) {         // cw = 16 HJ
+        tc_wait_ld();
+        tc_ld8(tcol + lane_base + c0 + 8, bh);
+        tc_ld8(tcol + lane_base + 128 + c0 + 8, bl);
+        e2_8(ah, al, c0);
+        tc_wait_ld();
+        if (c0 + 16 < cbeg + cw) {
+          tc_ld8(tcol + lane_base + c0 + 16, ah);
+          tc_ld8(tcol + lane_base + 128 + c0 + 16, al);
+        }
+        e2_8(bh, bl, c0 + 8);
       }
     }
     tc_fence_before();
@@ -1915,16 +1961,40 @@ __global__ void __launch_bounds__(kGluThreads, 1) tc_glu_kernel(const __grid_con
       }
       const unsigned short* trow = reinterpret_cast<const unsigned short*>(T + (size_t)rb * ldT) + lane;
       float* yr = pOUT + (size_t)(row0 + rb) * H + lane;
+      if (rb + PB <= rv) {
+        // whole batch: four rows at a time, every code first, then the arithmetic, then the stores (a per-row exit test
+        // turns every row into its own dependent load -> multiply -> store chain)
 #pragma unroll
-      for (int q = 0; q < PB; ++q) {
-        if (rb + q >= rv) break;                              // warp-uniform
+        for (int q0 = 0; q0 < PB; q0 += 4) {
+          uint32_t lc[4][HJ], rc[4][HJ];
 #pragma unroll
-        for (int j = 0; j < HJ; ++j) {
-          // codes are non-negative: int -> float through the magic constant (no conversion pipe)
-          const float l = (__uint_as_float(0x4B400000u + trow[(size_t)q * 2 * ldT + 32 * j]) - kRoundMagic) * gl_s;
-          const float sg = (__uint_as_float(0x4B400000u + trow[(size_t)q * 2 * ldT + H + 32 * j]) - kRoundMagic) * gr_s;
-          const float out = fmaf(l, sg, xin[q][j]);
-          yr[(size_t)q * H + 32 * j] = fmaxf(out, out_floor);
+          for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int j = 0; j < HJ; ++j) {
+              lc[q][j] = trow[(size_t)(q0 + q) * 2 * ldT + 32 * j];
+              rc[q][j] = trow[(size_t)(q0 + q) * 2 * ldT + H + 32 * j];
+            }
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int j = 0; j < HJ; ++j) {
+              // codes are non-negative: int -> float through the magic constant (no conversion pipe)
+              const float l = (__uint_as_float(0x4B400000u + lc[q][j]) - kRoundMagic) * gl_s;
+              const float sg = (__uint_as_float(0x4B400000u + rc[q][j]) - kRoundMagic) * gr_s;
+              yr[(size_t)(q0 + q) * H + 32 * j] = fmaxf(fmaf(l, sg, xin[q0 + q][j]), out_floor);
+            }
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < PB; ++q) {
+          if (rb + q >= rv) break;                              // warp-uniform
+#pragma unroll
+          for (int j = 0; j < HJ; ++j) {
+            const float l = (__uint_as_float(0x4B400000u + trow[(size_t)q * 2 * ldT + 32 * j]) - kRoundMagic) * gl_s;
+            const float sg = (__uint_as_float(0x4B400000u + trow[(size_t)q * 2 * ldT + H + 32 * j]) - kRoundMagic) * gr_s;
+            const float out = fmaf(l, sg, xin[q][j]);
+            yr[(size_t)q * H + 32 * j] = fmaxf(out, out_floor);
+          }
         }
       }
     }
@@ -2735,8 +2805,11 @@ static int tc_glu_fill(const TcGluDev& d, const TcGluArgs& a, TcGluParams* out, 
   // 104 (a whole number of rounds over the 296 pipelines) -> 100.6 us, 96 -> 110.5 us, 64 -> 125 us.
   static const int tile_rows = [] { const char* e = getenv("S5B200_SCAN_TILE_ROWS"); return e ? std::max(8, std::min(kTcRows, atoi(e))) : kTcRows; }();
   const int nseg = kGluHalf / P, rmax = std::min(tile_rows, 32 * nseg);
+  // Full-height tiles (every clip ends with one short tile) rather than balanced ones: with P = 64 every segment of a full
+  // tile is 32 frames long and takes the kernel's straight-line recurrence path.  S5B200_SCAN_BALANCED=1: the old split.
+  static const bool balanced = [] { const char* e = getenv("S5B200_SCAN_BALANCED"); return e && atoi(e) != 0; }();
   const int c = (a.L + rmax - 1) / rmax;
-  p.R = (a.L + c - 1) / c;
+  p.R = balanced ? (a.L + c - 1) / c : std::min(rmax, a.L);
   p.tiles_per_clip = (a.L + p.R - 1) / p.R;
   const long long tiles = (long long)a.B * p.tiles_per_clip;
   *grid_out = (int)std::max<long long>(1, std::min<long long>((tiles + 1) / 2, (long long)sm_count()));
