@@ -18,7 +18,8 @@
 #include <mutex>
 #include <vector>
 
-#include "fxp_prims.cuh"
+#include "fxp_chain.cuh"
+#include "fxp_tc.cuh"
 #include "proj.cuh"
 #include "scan.cuh"
 
@@ -26,79 +27,6 @@ namespace s5 {
 
 
 constexpr size_t kSmemMaxF = 227 * 1024;
-constexpr int kStateStride = 8;  // per-layer slots in the device state block
-// fmax slots
-enum { M_S1 = 0, M_A1 = 1, M_2 = 2, M_3 = 3, M_S4 = 4, M_A4 = 5, M_SR = 6, M_G = 7 };
-// exponent slots
-enum { E_IN = 0, E_1 = 1, E_2 = 2, E_3 = 3, E_4 = 4, E_OUT = 5 };
-
-struct BnChain {
-  const int* mmean; const int* inv; const int* scale; const int* bias;  // device [H]
-  int e_mean, b_mean, e_inv, b_inv, e_scale, b_scale, e_bias, b_bias;
-  float pm_mean, pm_bias;  // max|to_float(param)|
-  int has_scale, has_bias;
-  int x_bits;              // width of the block input (16)
-  int u_bits, u_exp;
-};
-
-struct BnPlan {
-  AddPlan p1;
-  int e_in, e1, e2, rs2, e3, rs3, e4;
-  AddPlan p4;
-  int rb1, rb2, rb3, rb4;
-  int bad;
-};
-
-// exponent plans of the BatchNorm chain up to stage `upto` (1 add mean, 2 mul invsq, 3 mul scale, 4 add bias)
-__device__ inline void bn_make_plan(BnPlan& pl, const BnChain& c, const unsigned* fm, const int* ex, int upto) {
-  pl.bad = 0;
-  pl.e_in = ex[E_IN];
-  pl.rb1 = max(c.x_bits, c.b_mean);
-  pl.rb2 = max(pl.rb1, c.b_inv);
-  pl.rb3 = c.has_scale ? max(pl.rb2, c.b_scale) : pl.rb2;
-  pl.rb4 = c.has_bias ? max(pl.rb3, c.b_bias) : pl.rb3;
-  pl.p1 = fx_plan_add(__uint_as_float(fm[M_S1]), __uint_as_float(fm[M_A1]), c.pm_mean, pl.e_in, c.e_mean, pl.rb1);
-  pl.e1 = pl.p1.res_exp;
-  pl.e2 = pl.e1; pl.rs2 = 0; pl.e3 = pl.e1; pl.rs3 = 0; pl.e4 = pl.e1; pl.p4 = pl.p1;
-  if (upto >= 2) {
-    pl.e2 = fx_plan_mul(__uint_as_float(fm[M_2]), pl.rb2);
-    pl.rs2 = pl.e1 + c.e_inv - pl.e2;
-    if (pl.rs2 < 0 || pl.rs2 > 31) pl.bad = 1;
-    pl.e3 = pl.e2; pl.e4 = pl.e2;
-  }
-  if (upto >= 3 && c.has_scale) {
-    pl.e3 = fx_plan_mul(__uint_as_float(fm[M_3]), pl.rb3);
-    pl.rs3 = pl.e2 + c.e_scale - pl.e3;
-    if (pl.rs3 < 0 || pl.rs3 > 31) pl.bad = 1;
-    pl.e4 = pl.e3;
-  }
-  if (upto >= 4 && c.has_bias) {
-    pl.p4 = fx_plan_add(__uint_as_float(fm[M_S4]), __uint_as_float(fm[M_A4]), c.pm_bias, pl.e3, c.e_bias, pl.rb4);
-    pl.e4 = pl.p4.res_exp;
-  }
-  if (pl.p1.agg_bits > 32 || (upto >= 4 && c.has_bias && pl.p4.agg_bits > 32)) pl.bad = 1;
-  const int sh[4] = {pl.p1.agg_exp - pl.e_in, pl.p1.agg_exp - c.e_mean, pl.p1.res_exp - pl.p1.agg_exp, pl.p1.agg_exp - pl.p1.res_exp};
-  for (int i = 0; i < 4; ++i)
-    if (sh[i] > 31) pl.bad = 1;
-}
-
-__device__ __forceinline__ int bn_apply(int v, int k, const BnChain& c, const BnPlan& pl, int upto) {
-  v = fx_add_cb_apply(v, c.x_bits, pl.e_in, c.mmean[k], c.b_mean, c.e_mean, pl.p1, pl.rb1);
-  if (upto >= 2) v = fx_mul_apply(v, c.inv[k], pl.rs2 & 31, S5_ROUND_FLOOR, pl.rb2);
-  if (upto >= 3 && c.has_scale) v = fx_mul_apply(v, c.scale[k], pl.rs3 & 31, S5_ROUND_FLOOR, pl.rb3);
-  if (upto >= 4 && c.has_bias) v = fx_add_cb_apply(v, pl.rb3, pl.e3, c.bias[k], c.b_bias, c.e_bias, pl.p4, pl.rb4);
-  return v;
-}
-
-// the same with the per-column parameters already in registers (kernels whose threads own fixed columns)
-__device__ __forceinline__ int bn_apply_v(int v, int mm, int inv, int sc, int bi, const BnChain& c, const BnPlan& pl, int upto) {
-  v = fx_add_cb_apply(v, c.x_bits, pl.e_in, mm, c.b_mean, c.e_mean, pl.p1, pl.rb1);
-  if (upto >= 2) v = fx_mul_apply(v, inv, pl.rs2 & 31, S5_ROUND_FLOOR, pl.rb2);
-  if (upto >= 3 && c.has_scale) v = fx_mul_apply(v, sc, pl.rs3 & 31, S5_ROUND_FLOOR, pl.rb3);
-  if (upto >= 4 && c.has_bias) v = fx_add_cb_apply(v, pl.rb3, pl.e3, bi, c.b_bias, c.e_bias, pl.p4, pl.rb4);
-  return v;
-}
-
 // ------------------------------------------------------------------------------------------- BN reduce
 // Applies stages 1..upto of the BatchNorm chain to x and accumulates the float maxima stage upto+1 needs.
 struct BnReduceParams {
@@ -179,7 +107,7 @@ __global__ void __launch_bounds__(256) fxp_bn_apply_kernel(BnApplyParams p) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += (long long)gridDim.x * blockDim.x) {
     const int k = (int)(i % p.H);
     const int v = bn_apply(p.X[i], k, p.c, pl, 4);
-    p.U[i] = fx_change_cfg(v, pl.rb4, pl.e4, p.c.u_bits, p.c.u_exp, S5_ROUND_FLOOR);
+    p.U[i] = bn_to_u(v, pl);
   }
 }
 
@@ -190,7 +118,6 @@ static bool fxp_skip_zero() {
 }
 
 // ------------------------------------------------------------------------------------------- linear kernels
-enum { LIN_ENC = 0, LIN_BPROJ = 1, LIN_DEC = 2, LIN_PLAIN = 3 };
 
 struct FxpLinearParams {
   const void* X; int* Y; float* Yf; long long rows; WView w;
@@ -256,7 +183,7 @@ __global__ void __launch_bounds__(kProjThreads) fxp_linear_kernel(FxpLinearParam
     } else if (p.mode == LIN_BPROJ) {
       stage_rows<int, int, TR>(xt, reinterpret_cast<const int*>(p.X) + row0 * K, rv, K, [&](int v, int k) {
         v = bn_apply(v, k, p.c, pl, 4);
-        return fx_change_cfg(v, pl.rb4, pl.e4, p.c.u_bits, p.c.u_exp, S5_ROUND_FLOOR);  // fxpmodel.py:620-624
+        return bn_to_u(v, pl);  // fxpmodel.py:620-624
       });
     } else if (p.mode == LIN_DEC) {
       const int change = dyn[0], e = dyn[1];
@@ -330,6 +257,17 @@ static int pgrid(KernelT kernel, size_t smem, long long ntiles, int* grid_out) {
   return S5_OK;
 }
 
+static int launch_fxp_linear_tc(const FxpLinearParams& p, const FxpTcLinearDev& tc, cudaStream_t st, int kclass) {
+  FxpTcLinArgs a{};
+  a.X = p.X; a.Y = p.Y; a.Yf = p.Yf; a.rows = p.rows; a.mode = p.mode;
+  a.x_is_float = p.x_is_float; a.in_bits = p.in_bits; a.in_exp = p.in_exp;
+  a.rshift0 = p.rshift0; a.rshift1 = p.rshift1; a.out_bits = p.out_bits; a.bias_aligned = p.bias_aligned; a.relu = p.relu;
+  a.out_scale = p.out_scale; a.c = p.c; a.fm = p.fm; a.ex = p.ex; a.status = p.status;
+  a.next_mmean = p.next_mmean; a.next_e_mean = p.next_e_mean; a.next_fm = p.next_fm; a.out_exp = p.out_exp;
+  a.dec_inp_bits = p.dec_inp_bits; a.dec_inp_exp = p.dec_inp_exp; a.dec_w_exp = p.dec_w_exp; a.dec_out_exp = p.dec_out_exp;
+  return fxp_tc_linear_launch(tc, a, kclass, st);
+}
+
 static int launch_fxp_linear(const FxpLinearParams& p, cudaStream_t st, int kclass = S5_K_OTHER) {
   if (p.rows <= 0) S5_FAIL(S5_E_BADSHAPE, "fxp linear: rows=%lld must be positive", p.rows);
   const size_t wbytes = wwords_h(p.w) * 4;
@@ -372,12 +310,18 @@ struct FxpGluParams {
   int sig_x_exp, sig_y_exp; int lut[8];
   int gl_bits, gl_exp, gr_bits, gr_exp, g_rs, g_bits, g_exp;
   int skip_zero;
+  // fix-up pass behind the dense-tile kernel (fxp_tc.cu): only the listed row ranges (row0, count <= 128), i.e. the tiles
+  // whose states do not fit 16 bits; the count lives in device memory, a launch with an empty list returns at once
+  const int* bad_list; const int* bad_count;
 };
 
 template <int TR>
 __global__ void __launch_bounds__(kProjThreads) fxp_glu_kernel(FxpGluParams p) {
   constexpr int R = TR / 32;
   constexpr int LD = TR + 1;
+  constexpr int SUB = (128 + TR - 1) / TR;                      // sub-tiles per listed range
+  const int nbad = p.bad_list ? *p.bad_count : 0;
+  if (p.bad_list && nbad == 0) return;
   extern __shared__ __align__(16) int smem_i[];
   __shared__ BnPlan pl;
   __shared__ float red[32];
@@ -400,15 +344,21 @@ __global__ void __launch_bounds__(kProjThreads) fxp_glu_kernel(FxpGluParams p) {
   __syncthreads();
   const float sg = exp2f((float)-p.g_exp), sk = exp2f((float)-pl.e_in);
   float m0 = 0.f, m1 = 0.f;
-  const long long ntiles = (p.rows + TR - 1) / TR;
+  const long long ntiles = p.bad_list ? (long long)nbad * SUB : (p.rows + TR - 1) / TR;
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const long long row0 = tile * TR;
-    const int rv = (int)min((long long)TR, p.rows - row0);
+    long long row0 = tile * TR;
+    int rv = (int)min((long long)TR, p.rows - row0);
+    if (p.bad_list) {
+      const int ent = (int)(tile / SUB), sub = (int)(tile % SUB);
+      row0 = (long long)p.bad_list[2 * ent] + (long long)sub * TR;
+      rv = min(TR, p.bad_list[2 * ent + 1] - sub * TR);
+      if (rv <= 0) continue;                                    // CTA-uniform
+    }
     __syncthreads();
     stage_rows<int, int, TR>(bufA, p.XS + row0 * K1, rv, K1, [](int v, int) { return v; });
     stage_rows<int, int, TR>(bufB, p.X + row0 * H, rv, H, [&](int v, int k) {
       v = bn_apply(v, k, p.c, pl, 4);
-      return fx_change_cfg(v, pl.rb4, pl.e4, p.c.u_bits, p.c.u_exp, S5_ROUND_FLOOR);  // u, fxpmodel.py:620-624
+      return bn_to_u(v, pl);  // u, fxpmodel.py:620-624
     });
     __syncthreads();
     if (zmask) {
@@ -476,7 +426,8 @@ static int launch_fxp_glu(const FxpGluParams& p, cudaStream_t st) {
   const int tr = pick_tr_f(wbytes + zbytes, per_row);
   if (!tr) S5_FAIL(S5_E_BADSHAPE, "fxp glu: H=%d 2P=%d weights do not fit in shared memory", H, K1);
   const size_t smem = wbytes + per_row * (tr + 1) + zbytes;
-  const long long ntiles = (p.rows + tr - 1) / tr;
+  // fix-up mode: the number of listed ranges is only known on the device; one wave of CTAs walks the list
+  const long long ntiles = p.bad_list ? (long long)sm_count() * 4 : (p.rows + tr - 1) / tr;
   int grid = 1, rc;
   ProfScope prof(S5_K_FXP_GLU, st);
   switch (tr) {
@@ -583,6 +534,7 @@ static int ew_grid(long long n) { return (int)std::max<long long>(1, std::min<lo
 namespace s5 {
 struct FxpDenseDev {
   SparseDev w;
+  FxpTcLinearDev tc;   // dense-tile form of the same weights (fxp_tc.cu); !ok: CUDA-core kernels only
   int* bias_aligned = nullptr;
   s5_fxp_dense_desc q;
 };
@@ -590,6 +542,8 @@ struct FxpLayerDev {
   int *mmean = nullptr, *inv = nullptr, *scale = nullptr, *bias = nullptr;
   int *A_re = nullptr, *A_im = nullptr, *D = nullptr;
   SparseDev wb, wcr, wci;
+  FxpTcLinearDev tcb;  // B projection on the tensor cores
+  FxpTcGluDev tcg;     // C projection + out2 on the tensor cores
   FxpDenseDev out2;
   s5_fxp_layer_desc q;
   float pm_mean = 0.f, pm_bias = 0.f;
@@ -612,6 +566,7 @@ static int build_dense(const s5_fxp_dense_desc& q, int K, int N, int dense, FxpD
   out->q = q;
   if (!q.weight_host || !q.bias_host) S5_FAIL(S5_E_BADARG, "fxp_model_create: null dense parameters");
   if ((rc = sparse_build(q.weight_host, K, N, S5_I32, dense, &out->w))) return rc;
+  if ((rc = fxp_tc_linear_build(q.weight_host, K, N, &out->tc))) return rc;
   // fxp_add(wx, bias, result_exp=out_exp): bias.change_exp(out_exp) saturates at the bias width (fxparray.py:449-455)
   if (std::abs(q.out_exp - q.b_exp) > 31) S5_FAIL(S5_E_UNSUPPORTED, "fxp dense: bias/out exponent gap above 31");
   std::vector<int> b(N);
@@ -624,6 +579,11 @@ struct s5_fxp_model {
   s5_fxp_model_desc desc;
   s5::FxpDenseDev enc, dec;
   std::vector<s5::FxpLayerDev> layers;
+  // Dense-tile (tensor core) form of the integer projections: from S5B200_FXP_TC_MIN_ROWS (default 512) frame rows up, when
+  // the weights are 8-bit payloads and the activation operand is at most 16 bits wide (w8a16).  S5B200_FXP_TC=0: CUDA cores
+  // only.  Both are read when the handle is created.
+  bool tc_on = true; long long tc_min_rows = 512;
+  bool use_tc(long long rows) const { return tc_on && rows >= tc_min_rows; }
   s5_fxp_sync_fn sync = nullptr;   // global-batch parity under sharding: max-all-reduce of the running maxima (s5b200.h)
   void* sync_user = nullptr;
 };
@@ -631,7 +591,7 @@ struct s5_fxp_model {
 namespace s5 {
 
 struct FxpWs {
-  size_t off_a, off_b, off_g, off_bu, off_state, total;
+  size_t off_a, off_b, off_g, off_bu, off_state, off_bad, total;
   size_t state_ints;
 };
 static FxpWs fxp_ws(const s5_fxp_model* m, int B, int L) {
@@ -640,8 +600,11 @@ static FxpWs fxp_ws(const s5_fxp_model* m, int B, int L) {
   const size_t act = round_up(rows * m->desc.H * 4, 256);
   w.off_a = 0; w.off_b = act; w.off_g = 2 * act; w.off_bu = 3 * act;
   w.off_state = w.off_bu + round_up(rows * m->desc.P * 8, 256);
-  w.state_ints = (size_t)(m->desc.n_layers + 1) * kStateStride * 2 + 8;
-  w.total = w.off_state + round_up(w.state_ints * 4, 256);
+  // maxima | exponents | 8 status words | one bad-tile counter per block (dense-tile GLU, fxp_tc.cu)
+  w.state_ints = (size_t)(m->desc.n_layers + 1) * kStateStride * 2 + 8 + (size_t)m->desc.n_layers;
+  w.off_bad = w.off_state + round_up(w.state_ints * 4, 256);
+  // bad-tile list: (row0, count) per tile; tiles are at least 64 rows except one short tile per CTA
+  w.total = w.off_bad + round_up(((rows + 63) / 64 + 2048) * 8, 256);
   return w;
 }
 
@@ -661,6 +624,8 @@ struct FxpRun {
   unsigned* fm(int l) const { return reinterpret_cast<unsigned*>(base + w.off_state) + (size_t)l * kStateStride; }
   int* ex(int l) const { return reinterpret_cast<int*>(base + w.off_state) + (size_t)(m->desc.n_layers + 1) * kStateStride + (size_t)l * kStateStride; }
   int* status() const { return reinterpret_cast<int*>(base + w.off_state) + (size_t)(m->desc.n_layers + 1) * kStateStride * 2; }
+  int* bad_count(int l) const { return status() + 8 + l; }
+  int* bad_list() const { return reinterpret_cast<int*>(base + w.off_bad); }
 };
 
 // Runs encoder + blocks [0, upto_layer]; stop_stage: 0 full block, 1 stop after BN (pre_s5 materialised into g),
@@ -691,7 +656,8 @@ static int fxp_run(const FxpRun& r, const void* x, bool x_is_float, int upto_lay
     p.next_mmean = m->layers[0].mmean; p.next_e_mean = m->layers[0].q.bn_mean_exp; p.next_fm = r.fm(0); p.out_exp = q.out_exp;
     p.status = r.status();
     S5_CUDA(cudaMemcpyAsync(r.ex(0) + E_IN, &m->enc.q.out_exp, sizeof(int), cudaMemcpyHostToDevice, r.st));
-    if ((rc = launch_fxp_linear(p, r.st, S5_K_FXP_ENC))) return rc;
+    const bool tc = m->use_tc(rows) && m->enc.tc.ok && q.inp_bits <= 16 && p.round_mode == S5_ROUND_FLOOR;
+    if ((rc = tc ? launch_fxp_linear_tc(p, m->enc.tc, r.st, S5_K_FXP_ENC) : launch_fxp_linear(p, r.st, S5_K_FXP_ENC))) return rc;
     sync_maxima();
   }
   for (int li = 0; li <= upto_layer; ++li) {
@@ -722,7 +688,8 @@ static int fxp_run(const FxpRun& r, const void* x, bool x_is_float, int upto_lay
       p.rshift0 = l.q.u_exp + l.q.eB_re - l.q.Bu_re_exp; p.rshift1 = l.q.u_exp + l.q.eB_im - l.q.Bu_im_exp;
       p.round_mode = S5_ROUND_FLOOR; p.out_bits = l.q.Bu_re_bits;
       p.c = c; p.fm = r.fm(li); p.ex = r.ex(li); p.status = r.status();
-      if ((rc = launch_fxp_linear(p, r.st, S5_K_FXP_BPROJ))) return rc;
+      const bool tc = m->use_tc(rows) && l.tcb.ok && l.q.u_bits <= 16 && (d.H % 128) != 1;
+      if ((rc = tc ? launch_fxp_linear_tc(p, l.tcb, r.st, S5_K_FXP_BPROJ) : launch_fxp_linear(p, r.st, S5_K_FXP_BPROJ))) return rc;
     }
     {  // recurrent_loop + fxp_relu (fxpmodel.py:682-742)
       ScanI32Params q{};
@@ -750,6 +717,24 @@ static int fxp_run(const FxpRun& r, const void* x, bool x_is_float, int upto_lay
       for (int i = 0; i < 8; ++i) p.lut[i] = l.q.sig_lut[i];
       p.gl_bits = l.q.gate_l_bits; p.gl_exp = l.q.gate_l_exp; p.gr_bits = l.q.gate_r_bits; p.gr_exp = l.q.gate_r_exp;
       p.g_rs = l.q.gate_l_exp + l.q.gate_r_exp - l.q.gate_res_exp; p.g_bits = l.q.gate_res_bits; p.g_exp = l.q.gate_res_exp;
+      // dense tiles: 16-bit operands everywhere (w8a16); tiles whose states exceed 16 bits come back in the list and
+      // are redone by the CUDA-core kernel, which multiplies full int32 states
+      const bool tc = m->use_tc(rows) && l.tcg.ok && l.q.y_bits <= 16 && o.inp_bits <= 16 && o.out_bits <= 16 &&
+                      l.q.gate_l_bits <= 16 && l.q.gate_r_bits <= 16 && l.q.u_bits <= 16;
+      if (tc) {
+        FxpTcGluArgs t{};
+        t.XS = p.XS; t.X = p.X; t.G = p.G; t.rows = rows; t.c = c; t.fm = p.fm; t.ex = p.ex; t.status = p.status;
+        t.D = p.D; t.rs_cre = p.rs_cre; t.rs_cim = p.rs_cim; t.rs_D = p.rs_D; t.y_bits = p.y_bits; t.conj = p.conj;
+        t.o_in_change = p.o_in_change; t.y_exp = p.y_exp; t.o_inp_bits = p.o_inp_bits; t.o_inp_exp = p.o_inp_exp; t.o_rs = p.o_rs;
+        t.o_out_bits = p.o_out_bits; t.o_out_exp = p.o_out_exp; t.o_bias_aligned = p.o_bias_aligned;
+        t.sig_x_exp = p.sig_x_exp; t.sig_y_exp = p.sig_y_exp;
+        for (int i = 0; i < 8; ++i) t.lut[i] = p.lut[i];
+        t.gl_bits = p.gl_bits; t.gl_exp = p.gl_exp; t.gr_bits = p.gr_bits; t.gr_exp = p.gr_exp; t.g_rs = p.g_rs;
+        t.g_bits = p.g_bits; t.g_exp = p.g_exp;
+        t.bad_list = r.bad_list(); t.bad_count = r.bad_count(li);
+        if ((rc = fxp_tc_glu_launch(l.tcg, t, r.st))) return rc;
+        p.bad_list = r.bad_list(); p.bad_count = r.bad_count(li);
+      }
       if ((rc = launch_fxp_glu(p, r.st))) return rc;
       sync_maxima();
     }
@@ -791,7 +776,8 @@ static int fxp_forward_impl(const s5_fxp_model* m, const void* x, bool x_is_floa
   p.out_scale = 1.0f / (float)(1ll << q.out_exp);
   p.ex = r.ex(m->desc.n_layers); p.status = r.status();
   p.dec_inp_bits = q.inp_bits; p.dec_inp_exp = q.inp_exp; p.dec_w_exp = q.w_exp; p.dec_out_exp = q.out_exp;
-  if ((rc = launch_fxp_linear(p, r.st, S5_K_FXP_DEC))) return rc;
+  const bool tc = m->use_tc(p.rows) && m->dec.tc.ok && q.inp_bits <= 16 && (m->desc.H % 128) != 1 && (m->desc.H & 3) == 0;
+  if ((rc = tc ? launch_fxp_linear_tc(p, m->dec.tc, r.st, S5_K_FXP_DEC) : launch_fxp_linear(p, r.st, S5_K_FXP_DEC))) return rc;
   if (status_dev) S5_CUDA(cudaMemcpyAsync(status_dev, r.status(), 4 * sizeof(int), cudaMemcpyDeviceToDevice, r.st));
   return S5_OK;
 }
@@ -814,6 +800,8 @@ extern "C" int s5b200_fxp_model_create(const s5_fxp_model_desc* d, s5_fxp_model*
   s5_fxp_model* m = new s5_fxp_model();
   m->desc = *d;
   m->desc.layers = nullptr;
+  if (const char* e = getenv("S5B200_FXP_TC")) m->tc_on = atoi(e) != 0;
+  if (const char* e = getenv("S5B200_FXP_TC_MIN_ROWS")) m->tc_min_rows = atoll(e);
   const int H = d->H, P = d->P, dense = d->use_sparse ? 0 : 1;
   int rc = S5_OK;
   auto fail = [&](int code) { s5b200_fxp_model_destroy(m); return code; };
@@ -849,10 +837,12 @@ extern "C" int s5b200_fxp_model_create(const s5_fxp_model_desc* d, s5_fxp_model*
         wci[(size_t)(2 * p + 1) * H + h] = q.C_im_host[(size_t)h * P + p];
       }
     if ((rc = sparse_build(wb.data(), H, 2 * P, S5_I32, dense, &l.wb))) return fail(rc);
+    if ((rc = fxp_tc_linear_build(wb.data(), H, 2 * P, &l.tcb))) return fail(rc);
     // the C halves are always kept compressed: a dense tile would store the structural zeros of the other parity
     if ((rc = sparse_build(wcr.data(), 2 * P, H, S5_I32, 0, &l.wcr))) return fail(rc);
     if ((rc = sparse_build(wci.data(), 2 * P, H, S5_I32, 0, &l.wci))) return fail(rc);
     if ((rc = build_dense(q.out2, H, H, dense, &l.out2))) return fail(rc);
+    if ((rc = fxp_tc_glu_build(q.C_re_host, q.C_im_host, q.out2.weight_host, H, P, &l.tcg))) return fail(rc);
     const int eff_in = ((q.y_bits > q.out2.inp_bits) || (q.y_exp > q.out2.inp_exp)) ? q.out2.inp_exp : q.y_exp;
     const int shifts[] = {q.u_exp + q.eB_re - q.Bu_re_exp, q.u_exp + q.eB_im - q.Bu_im_exp, q.x_re_exp + q.eC_re - q.y_exp,
                           q.x_im_exp + q.eC_im - q.y_exp, q.eD + q.u_exp - q.y_exp, eff_in + q.out2.w_exp - q.out2.out_exp,
@@ -870,12 +860,14 @@ extern "C" int s5b200_fxp_model_create(const s5_fxp_model_desc* d, s5_fxp_model*
 
 extern "C" int s5b200_fxp_model_destroy(s5_fxp_model* m) {
   if (!m) return S5_OK;
-  auto fd = [](s5::FxpDenseDev& d) { s5::sparse_free(&d.w); cudaFree(d.bias_aligned); };
+  auto fd = [](s5::FxpDenseDev& d) { s5::sparse_free(&d.w); s5::fxp_tc_linear_free(&d.tc); cudaFree(d.bias_aligned); };
   fd(m->enc); fd(m->dec);
   for (auto& l : m->layers) {
     cudaFree(l.mmean); cudaFree(l.inv); cudaFree(l.scale); cudaFree(l.bias);
     cudaFree(l.A_re); cudaFree(l.A_im); cudaFree(l.D);
     s5::sparse_free(&l.wb); s5::sparse_free(&l.wcr); s5::sparse_free(&l.wci);
+    s5::fxp_tc_linear_free(&l.tcb);
+    s5::fxp_tc_glu_free(&l.tcg);
     fd(l.out2);
   }
   delete m;

@@ -53,7 +53,6 @@ __device__ __forceinline__ unsigned long long gtime() {
 #define S5_LOOKBACK_STRIDE 4   // every S5_LOOKBACK_STRIDE-th tile of a clip publishes its inclusive prefix (fused recurrence)
 #endif
 constexpr int kTcThreads = 256;
-constexpr int kTcRows = 128;
 constexpr int kTcKI = 8;  // K <= 256: each lane stages at most 8 input columns
 
 struct TcLinParams {
@@ -95,59 +94,6 @@ __device__ __forceinline__ uint32_t quant_bits(float v, float inv, float qmin, f
 __device__ __forceinline__ float round_clip(float t, float qmin, float qmax) {                  // clip(rint(t))
   return (fminf(fmaxf(t, qmin), qmax) + kRoundMagic) - kRoundMagic;
 }
-// four int16 codes (low halves of b0..b3) -> word of the four low bytes, word of the four high bytes
-__device__ __forceinline__ void split_planes(uint32_t b0, uint32_t b1, uint32_t b2, uint32_t b3, uint32_t& lo, uint32_t& hi) {
-  const uint32_t t01 = __byte_perm(b0, b1, 0x5140), t23 = __byte_perm(b2, b3, 0x5140);   // {lo0, lo1, hi0, hi1}
-  lo = __byte_perm(t01, t23, 0x5410);
-  hi = __byte_perm(t01, t23, 0x7632);
-}
-
-// Operand tiles use a padded leading-byte-offset (K-chunk stride = rows*16 + 16 bytes): with it the staging stores
-// (lanes along k) are bank-conflict free.
-__host__ __device__ __forceinline__ uint32_t tc_lbo(int rows) { return (uint32_t)rows * 16u + 16u; }
-__host__ __device__ __forceinline__ size_t tc_tile_bytes(int rows, int K) { return (size_t)(K >> 3) * tc_lbo(rows); }   // f16 / bf16
-__host__ __device__ __forceinline__ size_t tc_tile_bytes8(int rows, int K) { return (size_t)(K >> 4) * tc_lbo(rows); }  // 8-bit
-
-// copy a plain row-major [R][K] f16 matrix into the canonical operand layout
-__device__ __forceinline__ void tc_load_weights(unsigned char* dst, const __half* __restrict__ W, int R, int K) {
-  const int kchunks = K >> 3;
-  const uint32_t lbo = tc_lbo(R);
-  for (int i = threadIdx.x; i < R * kchunks; i += blockDim.x) {
-    const int r = i / kchunks, kc = i % kchunks;
-    *reinterpret_cast<int4*>(dst + (size_t)kc * lbo + (size_t)r * 16) = *reinterpret_cast<const int4*>(W + (size_t)r * K + kc * 8);
-  }
-}
-// same for a row-major [R][K] int8 matrix (16 codes per 16-byte chunk)
-__device__ __forceinline__ void tc_load_weights8(unsigned char* dst, const signed char* __restrict__ W, int R, int K) {
-  const int kchunks = K >> 4;
-  const uint32_t lbo = tc_lbo(R);
-  for (int i = threadIdx.x; i < R * kchunks; i += blockDim.x) {
-    const int r = i / kchunks, kc = i % kchunks;
-    *reinterpret_cast<int4*>(dst + (size_t)kc * lbo + (size_t)r * 16) = *reinterpret_cast<const int4*>(W + (size_t)r * K + kc * 16);
-  }
-}
-
-// issue the K/16 MMAs of one [128 x K] x [K x N] product (A and B in the padded canonical layout)
-__device__ __forceinline__ void tc_issue(uint32_t d_tmem, const void* A, const void* B, int K, int N, bool accumulate_first,
-                                         bool bf16 = false) {
-  const uint32_t la = tc_lbo(kTcRows), lb = tc_lbo(N);
-  const uint32_t idesc = bf16 ? tc_idesc_bf16(kTcRows, N) : tc_idesc_f16(kTcRows, N);
-  // The descriptors of consecutive K steps differ only in the start-address field (low 14 bits, units of 16 bytes):
-  // build them once and add a constant per step - the issuing thread is alone on the critical path of the tile.
-  const uint64_t a_desc = tc_smem_desc(smem_u32(A), la, 128), b_desc = tc_smem_desc(smem_u32(B), lb, 128);
-  const uint32_t sa = (2 * la) >> 4, sb = (2 * lb) >> 4;
-  for (int j = 0; j < (K >> 4); ++j)
-    tc_mma_f16(d_tmem, tc_desc_advance(a_desc, j * sa), tc_desc_advance(b_desc, j * sb), idesc, accumulate_first || j > 0);
-}
-// int8 form: K/32 MMAs of [128 x K] (8-bit, signed or unsigned) x [K x N] (int8; `brows` rows in the whole B tile)
-__device__ __forceinline__ void tc_issue8(uint32_t d_tmem, const void* A, const void* B, int K, int N, int brows, bool a_signed) {
-  const uint32_t la = tc_lbo(kTcRows), lb = tc_lbo(brows);
-  const uint32_t idesc = tc_idesc_i8(kTcRows, N, a_signed, true);
-  const uint64_t a_desc = tc_smem_desc(smem_u32(A), la, 128), b_desc = tc_smem_desc(smem_u32(B), lb, 128);
-  const uint32_t sa = (2 * la) >> 4, sb = (2 * lb) >> 4;
-  for (int j = 0; j < (K >> 5); ++j) tc_mma_i8(d_tmem, tc_desc_advance(a_desc, j * sa), tc_desc_advance(b_desc, j * sb), idesc, j > 0);
-}
-
 // Dense / B-projection tile kernel.  Per 128-row tile:
 //   stage   : rows -> (BatchNorm) -> int16 codes -> signed high-byte plane + unsigned low-byte plane (8-bit operands)
 //   MMA     : acc_hi = Ah * W^T, acc_lo = Al * W^T  (tcgen05 kind::i8, int32 in TMEM), NP output columns per pass

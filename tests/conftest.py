@@ -19,3 +19,15 @@ def cuda_device():
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     return torch.device("cuda:0")
+
+
+@pytest.fixture(params=["cuda_cores", "dense_tiles"])
+def fxp_path(request, monkeypatch):
+    """Both code paths of the integer model: the CUDA-core kernels (fxp_model.cu) and the tcgen05 kind::i8 dense-tile
+    kernels (fxp_tc.cu).  The switches are read when a model handle is created."""
+    if request.param == "cuda_cores":
+        monkeypatch.setenv("S5B200_FXP_TC", "0")
+    else:
+        monkeypatch.setenv("S5B200_FXP_TC", "1")
+        monkeypatch.setenv("S5B200_FXP_TC_MIN_ROWS", "1")
+    return request.param

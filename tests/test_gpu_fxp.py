@@ -128,7 +128,7 @@ def fxp_case(request):
     return zoo, md, q
 
 
-def test_fxp_model_bit_exact(cuda_device, fxp_case):
+def test_fxp_model_bit_exact(cuda_device, fxp_case, fxp_path):
     import torch
     from sparsernns_b200 import fxpmodel as PF
 
@@ -165,7 +165,7 @@ def test_fxp_model_bit_exact(cuda_device, fxp_case):
     assert np.array_equal(mask.cpu().numpy(), y_ref.to_float())
 
 
-def test_fxp_model_batch_of_one_and_dense_tiles(cuda_device, fxp_case):
+def test_fxp_model_batch_of_one_and_dense_tiles(cuda_device, fxp_case, fxp_path):
     """bsz = 1 (the reference's verification mode, fxprun.py:460-463) and the dense-tile weight format."""
     import torch
     from sparsernns_b200 import fxpmodel as PF

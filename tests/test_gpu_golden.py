@@ -35,7 +35,7 @@ def test_float_and_static_vs_golden(cuda_device, gold):
         assert err <= tol, (key, err)
 
 
-def test_fxp_vs_golden_bit_exact(cuda_device, gold):
+def test_fxp_vs_golden_bit_exact(cuda_device, gold, fxp_path):
     import torch
     from sparsernns_b200 import fxpmodel as PF
     from sparsernns_b200 import fxputils, synth

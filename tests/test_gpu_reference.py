@@ -47,7 +47,7 @@ def _rel(a, b):
 
 @pytest.mark.parametrize("case,dim_scale,shared", [("A", 0.5, True), ("B", 0.5, True), ("C", 0.5, False), ("E", 1.0, True)],
                          ids=["golden_input", "saturating_and_silent_input", "per_layer_exponents", "dim_scale_1.0"])
-def test_fxp_model_bit_exact_vs_reference(cuda_device, ref_model, case, dim_scale, shared):
+def test_fxp_model_bit_exact_vs_reference(cuda_device, ref_model, case, dim_scale, shared, fxp_path):
     """FxpRegressionModel.forward: decoder output and every block output equal the reference's integers and exponents."""
     import torch
 
@@ -65,7 +65,7 @@ def test_fxp_model_bit_exact_vs_reference(cuda_device, ref_model, case, dim_scal
         assert np.array_equal(t.data.cpu().numpy(), ref_model[f"{key}/data"]), (case, i)
 
 
-def test_fxp_model_taps_bit_exact_vs_reference(cuda_device, ref_model):
+def test_fxp_model_taps_bit_exact_vs_reference(cuda_device, ref_model, fxp_path):
     """The sow()-named intermediates the library can tap, per block: ssm_input, pre_s5, pre_C (states after the complex
     ReLU), post_GLU, output; plus the quantised input and the un-batched (L, 257) call."""
     import torch
