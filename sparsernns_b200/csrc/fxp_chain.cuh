@@ -67,6 +67,13 @@ __device__ __forceinline__ int add_fast_apply(int a, int b, const AddFast& f) {
   return sc_apply(fx_addw(sc_apply(a, f.a), sc_apply(b, f.b)), f.post);
 }
 
+// Order-preserving non-negative image of a payload (|v| < 2^30: block inputs are saturated to <= 30 bits, checked on the host),
+// so that per-column extremes can be accumulated with atomicMax on zero-initialised words (0 lies below every image) and
+// travel through the same max-all-reduce as the float maxima, whether the reducer reads the words as signed or unsigned.
+// A column's minimum is kept as the maximum of ~v (order reversing, no overflow).
+__host__ __device__ __forceinline__ unsigned ord_enc(int v) { return (unsigned)(v + 0x40000000); }
+__host__ __device__ __forceinline__ int ord_dec(unsigned u) { return (int)u - 0x40000000; }
+
 struct BnFast {
   AddFast s1, s4;
   int rs2, lo2, hi2, rs3, lo3, hi3;

@@ -98,6 +98,154 @@ __global__ void __launch_bounds__(256) fxp_bn_reduce_kernel(BnReduceParams p) {
   else { block_max_to(p.fm + M_S4, m0, red); block_max_to(p.fm + M_A4, m1, red); }
 }
 
+// ------------------------------------------------------------------------------------------- BN maxima from column extremes
+// Every stage of the chain is a monotone function of the block input for a fixed column (shifts, clamps, a product with a
+// per-column constant, a sum with a per-column constant), and so are the float images the "compute_best" maxima are taken of
+// (int -> float RN, times a power of two, times / plus a per-column constant, abs).  The maximum over all rows of a column is
+// therefore attained at the column's smallest or largest input: ONE CTA derives all six maxima of a block from the 2 H column
+// extremes the producing kernel left behind, instead of three full passes over the tensor (0.29 of 1.43 ms per forward).
+// Monotonicity needs wrap-free integer steps; every step is re-done in 64 bits and, should one wrap (never seen with
+// w8a16 payloads), this CTA falls back to the plain passes over the whole tensor - exact either way, only slow.
+struct BnDeriveParams {
+  const int* X; long long n; int H;
+  BnChain c; unsigned* fm; int* ex; int* status;
+  const unsigned* cmax; const unsigned* cmin;
+  int force_slow;
+};
+
+__device__ __forceinline__ float block_allmax(float v, float* red) {   // every thread gets the block-wide maximum
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float m = 0.f;
+  for (int i = 0; i < (int)((blockDim.x + 31) >> 5); ++i) m = fmaxf(m, red[i]);
+  return m;
+}
+__device__ __forceinline__ int sc_apply_chk(int v, const ShiftClamp& s, int& wrap) {
+  const long long t = (long long)v << s.shl;
+  if (t != (long long)(int)t) wrap = 1;
+  return sc_apply(v, s);
+}
+__device__ __forceinline__ int add_fast_chk(int a, int b, const AddFast& f, int& wrap) {
+  const int a1 = sc_apply_chk(a, f.a, wrap), b1 = sc_apply_chk(b, f.b, wrap);
+  const long long s = (long long)a1 + (long long)b1;
+  if (s != (long long)(int)s) wrap = 1;
+  return sc_apply_chk((int)s, f.post, wrap);
+}
+__device__ __forceinline__ int mul_chk(int a, int b, int rs, int lo, int hi, int& wrap) {
+  const long long t = (long long)a * (long long)b;
+  if (t != (long long)(int)t) wrap = 1;
+  return min(max(fx_mulw(a, b) >> rs, lo), hi);
+}
+
+__global__ void __launch_bounds__(1024) fxp_bn_derive_kernel(BnDeriveParams p) {
+  __shared__ BnPlan pl;
+  __shared__ float red[32];
+  const int k = threadIdx.x;
+  const bool act = k < p.H;
+  const BnChain& c = p.c;
+  int wrap = p.force_slow;
+  int lo = 0, hi = 0, mm = 0, iv = 0, scl = 0, bia = 0;
+  if (act) {
+    hi = ord_dec(p.cmax[k]);
+    lo = ~ord_dec(p.cmin[k]);
+    mm = c.mmean[k]; iv = c.inv[k];
+    scl = c.has_scale ? c.scale[k] : 0; bia = c.has_bias ? c.bias[k] : 0;
+  }
+  const int e_in = p.ex[E_IN];
+  {  // maxima of the first add: |x + (-mean)| and |x|
+    const float s = exp2f((float)-e_in), g = __int2float_rn(mm) * exp2f((float)-c.e_mean);
+    const float fl = __int2float_rn(lo) * s, fh = __int2float_rn(hi) * s;
+    const float mS = block_allmax(act ? fmaxf(fabsf(fl + g), fabsf(fh + g)) : 0.f, red);
+    const float mA = block_allmax(act ? fmaxf(fabsf(fl), fabsf(fh)) : 0.f, red);
+    if (k == 0) {
+      p.fm[M_S1] = __float_as_uint(mS); p.fm[M_A1] = __float_as_uint(mA);
+      bn_make_plan(pl, c, p.fm, p.ex, 1);
+    }
+    __syncthreads();
+  }
+  int bad = pl.bad;
+  {  // stage 1 -> maxima of the product with 1 / sqrt(var + eps)
+    const int a = add_fast_chk(lo, mm, pl.f.s1, wrap), b = add_fast_chk(hi, mm, pl.f.s1, wrap);
+    lo = min(a, b); hi = max(a, b);
+    const float s = exp2f((float)-pl.e1), g = __int2float_rn(iv) * exp2f((float)-c.e_inv);
+    const float m = block_allmax(act ? fmaxf(fabsf(__int2float_rn(lo) * s * g), fabsf(__int2float_rn(hi) * s * g)) : 0.f, red);
+    if (k == 0) {
+      p.fm[M_2] = __float_as_uint(m);
+      bn_make_plan(pl, c, p.fm, p.ex, 2);
+    }
+    __syncthreads();
+  }
+  bad |= pl.bad;
+  {  // stage 2
+    const int a = mul_chk(lo, iv, pl.f.rs2, pl.f.lo2, pl.f.hi2, wrap), b = mul_chk(hi, iv, pl.f.rs2, pl.f.lo2, pl.f.hi2, wrap);
+    lo = min(a, b); hi = max(a, b);
+  }
+  if (c.has_scale) {
+    const float s = exp2f((float)-pl.e2), g = __int2float_rn(scl) * exp2f((float)-c.e_scale);
+    const float m = block_allmax(act ? fmaxf(fabsf(__int2float_rn(lo) * s * g), fabsf(__int2float_rn(hi) * s * g)) : 0.f, red);
+    if (k == 0) {
+      p.fm[M_3] = __float_as_uint(m);
+      bn_make_plan(pl, c, p.fm, p.ex, 3);
+    }
+    __syncthreads();
+    bad |= pl.bad;
+    const int a = mul_chk(lo, scl, pl.f.rs3, pl.f.lo3, pl.f.hi3, wrap), b = mul_chk(hi, scl, pl.f.rs3, pl.f.lo3, pl.f.hi3, wrap);
+    lo = min(a, b); hi = max(a, b);
+  }
+  if (c.has_bias) {
+    const float s = exp2f((float)-pl.e3), g = __int2float_rn(bia) * exp2f((float)-c.e_bias);
+    const float fl = __int2float_rn(lo) * s, fh = __int2float_rn(hi) * s;
+    const float mS = block_allmax(act ? fmaxf(fabsf(fl + g), fabsf(fh + g)) : 0.f, red);
+    const float mA = block_allmax(act ? fmaxf(fabsf(fl), fabsf(fh)) : 0.f, red);
+    if (k == 0) {
+      p.fm[M_S4] = __float_as_uint(mS); p.fm[M_A4] = __float_as_uint(mA);
+      bn_make_plan(pl, c, p.fm, p.ex, 4);
+    }
+    __syncthreads();
+    // the second add is only range-checked here; its result is not needed for a maximum
+    if (act) { (void)add_fast_chk(lo, bia, pl.f.s4, wrap); (void)add_fast_chk(hi, bia, pl.f.s4, wrap); }
+  }
+  wrap = __syncthreads_or(act ? wrap : p.force_slow);
+  if (wrap) {
+    // plain passes over the whole tensor by this one CTA (the arithmetic of fxp_bn_reduce_kernel)
+    for (int upto = 1; upto <= 3; ++upto) {
+      const int next = upto + 1;
+      if ((next == 3 && !c.has_scale) || (next == 4 && !c.has_bias)) continue;
+      if (k == 0) {
+        if (next == 2) p.fm[M_2] = 0u; else if (next == 3) p.fm[M_3] = 0u; else { p.fm[M_S4] = 0u; p.fm[M_A4] = 0u; }
+        bn_make_plan(pl, c, p.fm, p.ex, upto);
+      }
+      __syncthreads();
+      const int e_prev = upto == 1 ? pl.e1 : (upto == 2 ? pl.e2 : pl.e3);
+      const float s_prev = exp2f((float)-e_prev);
+      const int* pv = next == 2 ? c.inv : (next == 3 ? c.scale : c.bias);
+      const float s_par = exp2f((float)-(next == 2 ? c.e_inv : (next == 3 ? c.e_scale : c.e_bias)));
+      float m0 = 0.f, m1 = 0.f;
+      for (long long i = threadIdx.x; i < p.n; i += blockDim.x) {
+        const int kk = (int)(i % p.H);
+        const float f = __int2float_rn(bn_apply(p.X[i], kk, c, pl, upto)) * s_prev, g = __int2float_rn(pv[kk]) * s_par;
+        m0 = fmaxf(m0, fabsf(next != 4 ? f * g : f + g));
+        m1 = fmaxf(m1, fabsf(f));
+      }
+      m0 = block_allmax(m0, red); m1 = block_allmax(m1, red);
+      if (k == 0) {
+        if (next == 2) p.fm[M_2] = __float_as_uint(m0); else if (next == 3) p.fm[M_3] = __float_as_uint(m0);
+        else { p.fm[M_S4] = __float_as_uint(m0); p.fm[M_A4] = __float_as_uint(m1); }
+      }
+      __syncthreads();
+    }
+    if (k == 0) bn_make_plan(pl, c, p.fm, p.ex, 4);
+    __syncthreads();
+    bad = pl.bad;
+  }
+  if (k == 0) {
+    p.ex[E_1] = pl.e1; p.ex[E_2] = pl.e2; p.ex[E_3] = pl.e3;
+    if (bad | pl.bad) atomicOr(p.status, 1);
+  }
+}
+
 // Materialises u = change_cfg(norm_output) (the "pre_s5" tap).
 struct BnApplyParams { const int* X; int* U; long long n; int H; BnChain c; unsigned* fm; int* ex; };
 __global__ void __launch_bounds__(256) fxp_bn_apply_kernel(BnApplyParams p) {
@@ -133,6 +281,7 @@ struct FxpLinearParams {
   BnChain c; unsigned* fm; int* ex; int* status;
   // ENC / RESID epilogue: maxima for the next block's first BatchNorm stage
   const int* next_mmean; int next_e_mean; unsigned* next_fm; int out_exp;
+  unsigned* next_cmax; unsigned* next_cmin;   // dense-tile encoder only: column extremes instead of the float maxima
   // DEC: dynamic input exponent (ex[E_IN]) versus the static FxpDense input config
   int dec_inp_bits, dec_inp_exp, dec_w_exp, dec_out_exp;
   int skip_zero;   // proj.cuh:zero_group_mask (exact: a zero activation contributes 0 to the wrapping int32 sum)
@@ -264,6 +413,7 @@ static int launch_fxp_linear_tc(const FxpLinearParams& p, const FxpTcLinearDev& 
   a.rshift0 = p.rshift0; a.rshift1 = p.rshift1; a.out_bits = p.out_bits; a.bias_aligned = p.bias_aligned; a.relu = p.relu;
   a.out_scale = p.out_scale; a.c = p.c; a.fm = p.fm; a.ex = p.ex; a.status = p.status;
   a.next_mmean = p.next_mmean; a.next_e_mean = p.next_e_mean; a.next_fm = p.next_fm; a.out_exp = p.out_exp;
+  a.next_cmax = p.next_cmax; a.next_cmin = p.next_cmin;
   a.dec_inp_bits = p.dec_inp_bits; a.dec_inp_exp = p.dec_inp_exp; a.dec_w_exp = p.dec_w_exp; a.dec_out_exp = p.dec_out_exp;
   return fxp_tc_linear_launch(tc, a, kclass, st);
 }
@@ -454,12 +604,17 @@ struct FxpResidParams {
   unsigned* fm; int* ex; int* status;     // this block's state
   int g_bits, g_exp, x_bits, res_bits;
   const int* next_mmean; int next_e_mean; unsigned* next_fm; int* next_ex;  // next block (or decoder: only next_ex)
+  unsigned* next_cmax; unsigned* next_cmin;   // column extremes of the output instead of float maxima (fxp_bn_derive_kernel)
 };
 
 __global__ void __launch_bounds__(256) fxp_resid_kernel(FxpResidParams p) {
   __shared__ AddPlan pl;
   __shared__ float red[32];
   __shared__ int e_in_s;
+  __shared__ unsigned scmax[1024], scmin[1024];                 // H <= 1024 (fxp_model_create)
+  const bool cstat = p.next_cmax != nullptr;
+  if (cstat)
+    for (int i = threadIdx.x; i < p.H; i += blockDim.x) { scmax[i] = 0u; scmin[i] = 0u; }
   if (threadIdx.x == 0) {
     const int e_in = p.ex[E_IN];
     pl = fx_plan_add(__uint_as_float(p.fm[M_SR]), __uint_as_float(p.fm[M_G]), __uint_as_float(p.fm[M_A1]), p.g_exp, e_in,
@@ -491,6 +646,7 @@ __global__ void __launch_bounds__(256) fxp_resid_kernel(FxpResidParams p) {
       const int4* G4 = reinterpret_cast<const int4*>(p.G);
       const int4* X4 = reinterpret_cast<const int4*>(p.X);
       int4* O4 = reinterpret_cast<int4*>(p.OUT);
+      int vmax[4] = {INT_MIN, INT_MIN, INT_MIN, INT_MIN}, vmin[4] = {INT_MAX, INT_MAX, INT_MAX, INT_MAX};
       for (long long r = (long long)blockIdx.x * rpb + rl; r < rows; r += (long long)gridDim.x * rpb) {
         const int4 gv = G4[r * cgn + cg], xv = X4[r * cgn + cg];
         const int g4[4] = {gv.x, gv.y, gv.z, gv.w}, x4[4] = {xv.x, xv.y, xv.z, xv.w};
@@ -500,6 +656,7 @@ __global__ void __launch_bounds__(256) fxp_resid_kernel(FxpResidParams p) {
           int v = fx_add_cb_apply(g4[e], p.g_bits, p.g_exp, x4[e], p.x_bits, e_in, pl, p.res_bits);
           v = v > 0 ? v : 0;
           o4[e] = v;
+          vmax[e] = max(vmax[e], v); vmin[e] = min(vmin[e], v);
           if (p.next_fm) {
             const float f = __int2float_rn(v) * so;
             m0 = fmaxf(m0, fabsf(f + mmf[e]));
@@ -508,12 +665,23 @@ __global__ void __launch_bounds__(256) fxp_resid_kernel(FxpResidParams p) {
         }
         O4[r * cgn + cg] = make_int4(o4[0], o4[1], o4[2], o4[3]);
       }
+      if (cstat && vmax[0] >= vmin[0]) {                         // this thread saw at least one row
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          atomicMax(&scmax[4 * cg + e], ord_enc(vmax[e]));
+          atomicMax(&scmin[4 * cg + e], ord_enc(~vmin[e]));
+        }
+      }
     }
   } else
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += (long long)gridDim.x * blockDim.x) {
     int v = fx_add_cb_apply(p.G[i], p.g_bits, p.g_exp, p.X[i], p.x_bits, e_in, pl, p.res_bits);
     v = v > 0 ? v : 0;
     p.OUT[i] = v;
+    if (cstat) {
+      atomicMax(&scmax[(int)(i % p.H)], ord_enc(v));
+      atomicMax(&scmin[(int)(i % p.H)], ord_enc(~v));
+    }
     if (p.next_fm) {
       const float f = __int2float_rn(v) * so;
       m0 = fmaxf(m0, fabsf(f + __int2float_rn(p.next_mmean[(int)(i % p.H)]) * sm));
@@ -523,6 +691,13 @@ __global__ void __launch_bounds__(256) fxp_resid_kernel(FxpResidParams p) {
   if (p.next_fm) {
     block_max_to(p.next_fm + M_S1, m0, red);
     block_max_to(p.next_fm + M_A1, m1, red);
+  }
+  if (cstat) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < p.H; i += blockDim.x) {
+      if (scmax[i]) atomicMax(p.next_cmax + i, scmax[i]);
+      if (scmin[i]) atomicMax(p.next_cmin + i, scmin[i]);
+    }
   }
 }
 
@@ -583,6 +758,9 @@ struct s5_fxp_model {
   // the weights are 8-bit payloads and the activation operand is at most 16 bits wide (w8a16).  S5B200_FXP_TC=0: CUDA cores
   // only.  Both are read when the handle is created.
   bool tc_on = true; long long tc_min_rows = 512;
+  // S5B200_FXP_BN_DERIVE=0: the three BatchNorm-reduce passes per block instead of fxp_bn_derive_kernel;
+  // S5B200_FXP_BN_FORCE_SLOW=1 (testing): the derive kernel takes its whole-tensor fallback
+  bool bn_derive = true, bn_force_slow = false;
   bool use_tc(long long rows) const { return tc_on && rows >= tc_min_rows; }
   s5_fxp_sync_fn sync = nullptr;   // global-batch parity under sharding: max-all-reduce of the running maxima (s5b200.h)
   void* sync_user = nullptr;
@@ -592,7 +770,7 @@ namespace s5 {
 
 struct FxpWs {
   size_t off_a, off_b, off_g, off_bu, off_state, off_bad, total;
-  size_t state_ints;
+  size_t state_ints, max_words;
 };
 static FxpWs fxp_ws(const s5_fxp_model* m, int B, int L) {
   const size_t rows = (size_t)B * L;
@@ -600,8 +778,10 @@ static FxpWs fxp_ws(const s5_fxp_model* m, int B, int L) {
   const size_t act = round_up(rows * m->desc.H * 4, 256);
   w.off_a = 0; w.off_b = act; w.off_g = 2 * act; w.off_bu = 3 * act;
   w.off_state = w.off_bu + round_up(rows * m->desc.P * 8, 256);
-  // maxima | exponents | 8 status words | one bad-tile counter per block (dense-tile GLU, fxp_tc.cu)
-  w.state_ints = (size_t)(m->desc.n_layers + 1) * kStateStride * 2 + 8 + (size_t)m->desc.n_layers;
+  // maxima | column extremes (max, ~min) of every block input | exponents | 8 status words | one bad-tile counter per block
+  // (dense-tile GLU, fxp_tc.cu).  Maxima and extremes are contiguous: one max-all-reduce covers both (global-batch parity).
+  w.max_words = (size_t)(m->desc.n_layers + 1) * kStateStride + (size_t)m->desc.n_layers * 2 * m->desc.H;
+  w.state_ints = w.max_words + (size_t)(m->desc.n_layers + 1) * kStateStride + 8 + (size_t)m->desc.n_layers;
   w.off_bad = w.off_state + round_up(w.state_ints * 4, 256);
   // bad-tile list: (row0, count) per tile; tiles are at least 64 rows except one short tile per CTA
   w.total = w.off_bad + round_up(((rows + 63) / 64 + 2048) * 8, 256);
@@ -622,8 +802,10 @@ static BnChain make_chain(const FxpLayerDev& l) {
 struct FxpRun {
   const s5_fxp_model* m; int B, L; unsigned char* base; FxpWs w; cudaStream_t st;
   unsigned* fm(int l) const { return reinterpret_cast<unsigned*>(base + w.off_state) + (size_t)l * kStateStride; }
-  int* ex(int l) const { return reinterpret_cast<int*>(base + w.off_state) + (size_t)(m->desc.n_layers + 1) * kStateStride + (size_t)l * kStateStride; }
-  int* status() const { return reinterpret_cast<int*>(base + w.off_state) + (size_t)(m->desc.n_layers + 1) * kStateStride * 2; }
+  unsigned* cmax(int l) const { return reinterpret_cast<unsigned*>(base + w.off_state) + (size_t)(m->desc.n_layers + 1) * kStateStride + (size_t)l * 2 * m->desc.H; }
+  unsigned* cmin(int l) const { return cmax(l) + m->desc.H; }
+  int* ex(int l) const { return reinterpret_cast<int*>(base + w.off_state) + w.max_words + (size_t)l * kStateStride; }
+  int* status() const { return reinterpret_cast<int*>(base + w.off_state) + w.max_words + (size_t)(m->desc.n_layers + 1) * kStateStride; }
   int* bad_count(int l) const { return status() + 8 + l; }
   int* bad_list() const { return reinterpret_cast<int*>(base + w.off_bad); }
 };
@@ -643,9 +825,13 @@ static int fxp_run(const FxpRun& r, const void* x, bool x_is_float, int upto_lay
   // Sharded runs with global-batch parity: every kernel that produced running maxima is followed by the caller's
   // max-all-reduce over all blocks' maxima (max is idempotent, so reducing the whole region every time is exact).
   auto sync_maxima = [&]() {
-    if (m->sync) m->sync(m->sync_user, r.fm(0), (int)((d.n_layers + 1) * kStateStride), r.st);
+    if (m->sync) m->sync(m->sync_user, r.fm(0), (int)r.w.max_words, r.st);
   };
   S5_CUDA(cudaMemsetAsync(r.base + r.w.off_state, 0, r.w.state_ints * 4, r.st));
+  // BatchNorm maxima from column extremes (fxp_bn_derive_kernel) instead of three passes per block: needs the dense-tile
+  // encoder (its write-out has lanes along columns) and a block width the derive CTA covers with one thread per column
+  bool cs = m->bn_derive && m->use_tc(rows) && m->enc.tc.ok && m->enc.q.inp_bits <= 16 && d.H <= 1024 && m->enc.q.out_bits <= 30;
+  for (const FxpLayerDev& l : m->layers) cs = cs && l.q.gate_res_bits <= 30;
   {  // encoder FxpDense + fxp_relu (fxpmodel.py:1262-1266) + maxima for block 0
     const s5_fxp_dense_desc& q = m->enc.q;
     FxpLinearParams p{};
@@ -657,6 +843,7 @@ static int fxp_run(const FxpRun& r, const void* x, bool x_is_float, int upto_lay
     p.status = r.status();
     S5_CUDA(cudaMemcpyAsync(r.ex(0) + E_IN, &m->enc.q.out_exp, sizeof(int), cudaMemcpyHostToDevice, r.st));
     const bool tc = m->use_tc(rows) && m->enc.tc.ok && q.inp_bits <= 16 && p.round_mode == S5_ROUND_FLOOR;
+    if (tc && cs) { p.next_fm = nullptr; p.next_cmax = r.cmax(0); p.next_cmin = r.cmin(0); }
     if ((rc = tc ? launch_fxp_linear_tc(p, m->enc.tc, r.st, S5_K_FXP_ENC) : launch_fxp_linear(p, r.st, S5_K_FXP_ENC))) return rc;
     sync_maxima();
   }
@@ -672,9 +859,16 @@ static int fxp_run(const FxpRun& r, const void* x, bool x_is_float, int upto_lay
       sync_maxima();
       return S5_OK;
     };
-    if ((rc = reduce(1, 2))) return rc;
-    if (c.has_scale && (rc = reduce(2, 3))) return rc;
-    if (c.has_bias && (rc = reduce(3, 4))) return rc;
+    if (cs) {
+      BnDeriveParams p{a, n, d.H, c, r.fm(li), r.ex(li), r.status(), r.cmax(li), r.cmin(li), m->bn_force_slow ? 1 : 0};
+      ProfScope prof(S5_K_FXP_BN, r.st);
+      fxp_bn_derive_kernel<<<1, 1024, 0, r.st>>>(p);
+      S5_LAUNCH_CHECK();
+    } else {
+      if ((rc = reduce(1, 2))) return rc;
+      if (c.has_scale && (rc = reduce(2, 3))) return rc;
+      if (c.has_bias && (rc = reduce(3, 4))) return rc;
+    }
     if (stop_stage == 1 && li == upto_layer) {
       BnApplyParams p{a, g, n, d.H, c, r.fm(li), r.ex(li)};
       fxp_bn_apply_kernel<<<ew_grid(n), 256, 0, r.st>>>(p);
@@ -747,6 +941,7 @@ static int fxp_run(const FxpRun& r, const void* x, bool x_is_float, int upto_lay
       p.next_ex = r.ex(li + 1);
       if (li + 1 < d.n_layers) {
         p.next_mmean = m->layers[li + 1].mmean; p.next_e_mean = m->layers[li + 1].q.bn_mean_exp; p.next_fm = r.fm(li + 1);
+        if (cs) { p.next_fm = nullptr; p.next_cmax = r.cmax(li + 1); p.next_cmin = r.cmin(li + 1); }
       }
       ProfScope prof(S5_K_FXP_RESID, r.st);
       fxp_resid_kernel<<<ew_grid(n), 256, 0, r.st>>>(p);
@@ -802,6 +997,8 @@ extern "C" int s5b200_fxp_model_create(const s5_fxp_model_desc* d, s5_fxp_model*
   m->desc.layers = nullptr;
   if (const char* e = getenv("S5B200_FXP_TC")) m->tc_on = atoi(e) != 0;
   if (const char* e = getenv("S5B200_FXP_TC_MIN_ROWS")) m->tc_min_rows = atoll(e);
+  if (const char* e = getenv("S5B200_FXP_BN_DERIVE")) m->bn_derive = atoi(e) != 0;
+  if (const char* e = getenv("S5B200_FXP_BN_FORCE_SLOW")) m->bn_force_slow = atoi(e) != 0;
   const int H = d->H, P = d->P, dense = d->use_sparse ? 0 : 1;
   int rc = S5_OK;
   auto fail = [&](int code) { s5b200_fxp_model_destroy(m); return code; };

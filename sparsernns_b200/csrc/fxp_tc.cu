@@ -55,8 +55,12 @@ __global__ void __launch_bounds__(kFtThreads, 2) fxp_tc_linear_kernel(const __gr
   __shared__ BnPlan pl;
   __shared__ float red[32];
   __shared__ int dyn[4];
+  __shared__ unsigned scmax[MODE == LIN_ENC ? 512 : 1], scmin[MODE == LIN_ENC ? 512 : 1];   // Nfull <= 512 (fxp_tc_linear_build)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   constexpr int NW = kFtThreads / 32;
+  const bool cstat = MODE == LIN_ENC && a.next_cmax != nullptr;
+  if (cstat)
+    for (int i = tid; i < p.Nfull; i += kFtThreads) { scmax[i] = 0u; scmin[i] = 0u; }
   if (warp == 0) tc_alloc(&tmem_slot, 256);
   if (tid == 0) {
     mbar_init(&bar, 1);
@@ -260,6 +264,7 @@ __global__ void __launch_bounds__(kFtThreads, 2) fxp_tc_linear_kernel(const __gr
         const int rpi = q4 >= 32 ? 1 : 32 / q4;
         const int lr = lane / q4, lc = lane - lr * q4;
         if (lr < rpi) {
+          int cmx[4] = {INT_MIN, INT_MIN, INT_MIN, INT_MIN}, cmn[4] = {INT_MAX, INT_MAX, INT_MAX, INT_MAX};
           for (int rb = warp * rpi + lr; rb < rv; rb += 4 * NW * rpi) {
             int4 v[4];
 #pragma unroll
@@ -267,12 +272,23 @@ __global__ void __launch_bounds__(kFtThreads, 2) fxp_tc_linear_kernel(const __gr
 #pragma unroll
             for (int q = 0; q < 4; ++q)
               if (rb + q * NW * rpi < rv) {
+                if (cstat) {
+                  cmx[0] = max(cmx[0], v[q].x); cmx[1] = max(cmx[1], v[q].y); cmx[2] = max(cmx[2], v[q].z); cmx[3] = max(cmx[3], v[q].w);
+                  cmn[0] = min(cmn[0], v[q].x); cmn[1] = min(cmn[1], v[q].y); cmn[2] = min(cmn[2], v[q].z); cmn[3] = min(cmn[3], v[q].w);
+                }
                 const size_t o = (size_t)(row0 + rb + q * NW * rpi) * p.Nfull + pass0 + 4 * lc;
                 if (a.Y) *reinterpret_cast<int4*>(a.Y + o) = v[q];
                 if (a.Yf)
                   *reinterpret_cast<float4*>(a.Yf + o) = make_float4(__int2float_rn(v[q].x) * a.out_scale, __int2float_rn(v[q].y) * a.out_scale,
                                                                      __int2float_rn(v[q].z) * a.out_scale, __int2float_rn(v[q].w) * a.out_scale);
               }
+          }
+          if (cstat && cmx[0] >= cmn[0]) {                       // this lane saw at least one row
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              atomicMax(&scmax[pass0 + 4 * lc + e], ord_enc(cmx[e]));
+              atomicMax(&scmin[pass0 + 4 * lc + e], ord_enc(~cmn[e]));
+            }
           }
         }
       } else {
@@ -288,6 +304,10 @@ __global__ void __launch_bounds__(kFtThreads, 2) fxp_tc_linear_kernel(const __gr
 #pragma unroll
             for (int j = 0; j < 4; ++j)
               if (rb + q < rv && lane + 32 * j < npv) {
+                if (cstat) {
+                  atomicMax(&scmax[pass0 + lane + 32 * j], ord_enc(v[q][j]));
+                  atomicMax(&scmin[pass0 + lane + 32 * j], ord_enc(~v[q][j]));
+                }
                 if (a.Y) a.Y[o + lane + 32 * j] = v[q][j];
                 if (a.Yf) a.Yf[o + lane + 32 * j] = __int2float_rn(v[q][j]) * a.out_scale;
               }
@@ -311,6 +331,13 @@ __global__ void __launch_bounds__(kFtThreads, 2) fxp_tc_linear_kernel(const __gr
   if (MODE == LIN_ENC && a.next_fm) {
     block_max_to(a.next_fm + M_S1, m0, red);
     block_max_to(a.next_fm + M_A1, m1, red);
+  }
+  if (cstat) {
+    __syncthreads();
+    for (int i = tid; i < p.Nfull; i += kFtThreads) {
+      if (scmax[i]) atomicMax(a.next_cmax + i, scmax[i]);
+      if (scmin[i]) atomicMax(a.next_cmin + i, scmin[i]);
+    }
   }
   tc_fence_before();
   __syncthreads();

@@ -27,6 +27,7 @@ struct FxpTcLinArgs {
   const int* bias_aligned; int relu; float out_scale;    // FxpDense bias at out_exp; 2^-out_exp for Yf
   BnChain c; unsigned* fm; int* ex; int* status;         // BPROJ: BatchNorm chain of the block
   const int* next_mmean; int next_e_mean; unsigned* next_fm; int out_exp;   // ENC: maxima for block 0's first BatchNorm stage
+  unsigned* next_cmax; unsigned* next_cmin;              // ENC: or per-column extremes of the output (fxp_bn_derive_kernel)
   int dec_inp_bits, dec_inp_exp, dec_w_exp, dec_out_exp; // DEC: dynamic input exponent against the static FxpDense config
 };
 

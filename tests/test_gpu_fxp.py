@@ -181,6 +181,41 @@ def test_fxp_model_batch_of_one_and_dense_tiles(cuda_device, fxp_case, fxp_path)
         assert np.array_equal(y.data.cpu().numpy(), ref.data)
 
 
+def test_fxp_states_beyond_16_bits(cuda_device, fxp_case, fxp_path):
+    """The integer recurrence does not saturate (fxpmodel.py:147-208): a loud input drives the states past 16 bits.  The
+    dense-tile GLU kernel splits states into two byte planes only, so it must hand such tiles to the CUDA-core kernel
+    (bad-tile list, fxp_tc.cu); the result stays bit-exact, tile by tile, including clips that stay small."""
+    import torch
+    from sparsernns_b200 import fxpmodel as PF
+
+    import copy
+
+    zoo, md, q = fxp_case
+    n_layers = zoo["dims"].n_layers
+    q = copy.deepcopy(q)
+    for name in ("x_re", "x_im"):          # three more fractional bits for the states: 8 x larger payloads
+        q["blocks"]["ssm"]["activations"][name]["exp"] += 3
+    om = OFM.FxpRegressionModel(md, q, n_layers)
+    pm = PF.FxpRegressionModel(md, q, n_layers)
+    x = zoo["x"].copy()
+    x[0] *= 400.0          # clip 0 loud, the others as they were: mixed tiles
+    x[1, 100:] *= 400.0    # clip 1 turns loud half way
+    xq_ref = om.quantize_input(x)
+    taps = {}
+    y_ref = om(xq_ref, taps)
+    per_clip = [[int(np.abs(taps[f"layers_{i}"]["pre_C"].real.data[c]).max()) for c in range(x.shape[0])] for i in range(n_layers)]
+    assert max(map(max, per_clip)) >= 1 << 15, f"test input does not drive the states past 16 bits ({per_clip})"
+    assert min(map(min, per_clip)) < 1 << 15, f"every clip is loud in every block: no dense-tile coverage ({per_clip})"
+    xq = pm.quantize_input(torch.from_numpy(x).to(cuda_device))
+    for i in range(n_layers):
+        t_xs = pm.tap(xq, i, PF.TAP_XS).data.cpu().numpy()
+        assert np.array_equal(t_xs[..., 0], taps[f"layers_{i}"]["pre_C"].real.data), f"layer {i} xs"
+        t_g = pm.tap(xq, i, PF.TAP_POST_GLU)
+        assert np.array_equal(t_g.data.cpu().numpy(), taps[f"layers_{i}"]["post_GLU"].data), f"layer {i} post_GLU"
+    y = pm(xq)
+    assert y.exp == y_ref.exp and np.array_equal(y.data.cpu().numpy(), y_ref.data)
+
+
 def test_fxp_export_matches_oracle_and_writes_the_reference_files(cuda_device, fxp_case, tmp_path):
     """FxpRegressionModel.export / export_files (fxpmodel.py:1441-1458, fxprun.py:476-495): the reference's nesting, integer
     payloads equal to the oracle model's parameters, intermediates equal to the oracle's taps, five pickles."""
@@ -267,3 +302,32 @@ def test_fxp_global_batch_parity_two_gpus(cuda_device):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
     mp.spawn(_global_batch_worker, args=(2, 29641), nprocs=2, join=True)
+
+
+@pytest.mark.gpu
+def test_fxp_bn_maxima_paths_agree(cuda_device, fxp_case, monkeypatch):
+    """BatchNorm `compute_best` maxima three ways: derived from column extremes (fxp_bn_derive_kernel, default with the
+    dense-tile kernels), the derive kernel's whole-tensor fallback, and the three reduce passes - same integers and exponents."""
+    import torch
+    from sparsernns_b200 import fxpmodel as PF
+
+    zoo, md, q = fxp_case
+    n_layers = zoo["dims"].n_layers
+    om = OFM.FxpRegressionModel(md, q, n_layers)
+    taps = {}
+    y_ref = om(om.quantize_input(zoo["x"]), taps)
+    monkeypatch.setenv("S5B200_FXP_TC_MIN_ROWS", "1")
+    for env in ({}, {"S5B200_FXP_BN_FORCE_SLOW": "1"}, {"S5B200_FXP_BN_DERIVE": "0"}):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        pm = PF.FxpRegressionModel(md, q, n_layers)
+        xq = pm.quantize_input(torch.from_numpy(zoo["x"]).to(cuda_device))
+        for i in range(n_layers):
+            t_u = pm.tap(xq, i, PF.TAP_PRE_S5)
+            assert np.array_equal(t_u.data.cpu().numpy(), taps[f"layers_{i}"]["mixer"]["u"].data), (env, i)
+            t_o = pm.tap(xq, i, PF.TAP_OUTPUT)
+            assert t_o.exp == taps[f"layers_{i}"]["output"].exp and np.array_equal(t_o.data.cpu().numpy(), taps[f"layers_{i}"]["output"].data), (env, i)
+        y = pm(xq)
+        assert y.exp == y_ref.exp and np.array_equal(y.data.cpu().numpy(), y_ref.data), env
+        for k in env:
+            monkeypatch.delenv(k)
