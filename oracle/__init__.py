@@ -20,14 +20,18 @@ SparseRNNs) for the three numerics flavours of the S5 NDNS model forward:
 * ``synth``      - recipe-shaped random model, ERK magnitude masks, one-batch
                    calibration
 
-PARITY PIN STATUS: **parity unpinned by the reference** (model path; the ``ndns`` module is pinned against SciPy).  The reference ships no
-tests directory, golden vectors or fixtures for this path (SURVEY.md section 4,
-section 8c) and JAX/Flax are not importable in the build container, so the
-reference itself cannot be executed to generate vectors.  The oracle is pinned
-instead by (i) the reference's own inline property checks for the quantiser
-(quantization.py:900-910) restated in ``tests/test_oracle_kat.py``, and (ii)
-hand-derived known-answer cases written from the reference source for every
-fixed-point primitive.  Every function cites the reference file:line it follows.
+PARITY PIN STATUS: pinned against outputs of the reference's OWN sources, executed in place
+from /root/reference under a NumPy-backed stand-in for the part of jax.numpy / jax.lax they use
+(tests/golden/jaxshim.py, tests/golden/make_reference_golden.py; vectors committed as
+tests/golden/reference_*.npz and checked by tests/test_oracle_vs_reference.py): 84 fixed-point op
+cases, the qconfigs, every sow()-named intermediate of FxpRegressionModel.forward, the float and
+static-quant SSM.  The ``ndns`` module is pinned against SciPy.  NOT pinned: XLA itself - the last
+ulp of its float32 log2 at a compute_best boundary and its fp32 dot accumulation order (the float
+flavours carry tolerances for that).  The reference ships no golden vectors of its own (SURVEY.md
+section 8c) and cannot be installed here.  Further pins: the reference's
+inline property check of the quantiser (quantization.py:900-910) and hand-derived known-answer
+cases for every fixed-point primitive (tests/test_oracle_kat.py).
+Every function cites the reference file:line it follows.
 
 JAX semantics that NumPy does not give for free and that are enforced here:
 int32 payloads that wrap on overflow, arithmetic ``>>``, round-half-to-even,
