@@ -761,6 +761,7 @@ struct s5_fxp_model {
   // S5B200_FXP_BN_DERIVE=0: the three BatchNorm-reduce passes per block instead of fxp_bn_derive_kernel;
   // S5B200_FXP_BN_FORCE_SLOW=1 (testing): the derive kernel takes its whole-tensor fallback
   bool bn_derive = true, bn_force_slow = false;
+  bool relu_in_glu = true;   // S5B200_FXP_RELU_IN_GLU=0: the scan applies fxp_relu itself even when the dense-tile GLU follows
   bool use_tc(long long rows) const { return tc_on && rows >= tc_min_rows; }
   s5_fxp_sync_fn sync = nullptr;   // global-batch parity under sharding: max-all-reduce of the running maxima (s5b200.h)
   void* sync_user = nullptr;
@@ -885,12 +886,20 @@ static int fxp_run(const FxpRun& r, const void* x, bool x_is_float, int upto_lay
       const bool tc = m->use_tc(rows) && l.tcb.ok && l.q.u_bits <= 16 && (d.H % 128) != 1;
       if ((rc = tc ? launch_fxp_linear_tc(p, l.tcb, r.st, S5_K_FXP_BPROJ) : launch_fxp_linear(p, r.st, S5_K_FXP_BPROJ))) return rc;
     }
+    // dense tiles: 16-bit operands everywhere (w8a16); tiles whose states exceed 16 bits come back in the list and
+    // are redone by the CUDA-core kernel, which multiplies full int32 states
+    const s5_fxp_dense_desc& o2 = l.out2.q;
+    const bool tc_glu = m->use_tc(rows) && l.tcg.ok && l.q.y_bits <= 16 && o2.inp_bits <= 16 && o2.out_bits <= 16 &&
+                        l.q.gate_l_bits <= 16 && l.q.gate_r_bits <= 16 && l.q.u_bits <= 16;
+    // fxp_relu of the states: in the scan's post role, or - cheaper, the scan is latency bound with few clips - while the
+    // dense-tile GLU kernel stages them (not when the states themselves are tapped)
+    const bool relu_in_glu = tc_glu && m->relu_in_glu && !(stop_stage == 2 && li == upto_layer);
     {  // recurrent_loop + fxp_relu (fxpmodel.py:682-742)
       ScanI32Params q{};
       q.Bu_re = bu; q.Bu_im = nullptr; q.A_re = l.A_re; q.A_im = l.A_im; q.xs_re = bu; q.xs_im = nullptr;
       q.L = r.L; q.P = d.P; q.lanes = (long long)r.B * d.P;
       q.eA_re = l.q.eA_re; q.eA_im = l.q.eA_im; q.eBu_re = l.q.Bu_re_exp; q.eBu_im = l.q.Bu_im_exp;
-      q.ex_re = l.q.x_re_exp; q.ex_im = l.q.x_im_exp; q.relu = 1;
+      q.ex_re = l.q.x_re_exp; q.ex_im = l.q.x_im_exp; q.relu = relu_in_glu ? 0 : 1;
       if ((rc = launch_scan_i32(q, true, r.st))) return rc;
     }
     if (stop_stage == 2 && li == upto_layer) { *cur_out = bu; *other_out = a; return S5_OK; }
@@ -911,13 +920,10 @@ static int fxp_run(const FxpRun& r, const void* x, bool x_is_float, int upto_lay
       for (int i = 0; i < 8; ++i) p.lut[i] = l.q.sig_lut[i];
       p.gl_bits = l.q.gate_l_bits; p.gl_exp = l.q.gate_l_exp; p.gr_bits = l.q.gate_r_bits; p.gr_exp = l.q.gate_r_exp;
       p.g_rs = l.q.gate_l_exp + l.q.gate_r_exp - l.q.gate_res_exp; p.g_bits = l.q.gate_res_bits; p.g_exp = l.q.gate_res_exp;
-      // dense tiles: 16-bit operands everywhere (w8a16); tiles whose states exceed 16 bits come back in the list and
-      // are redone by the CUDA-core kernel, which multiplies full int32 states
-      const bool tc = m->use_tc(rows) && l.tcg.ok && l.q.y_bits <= 16 && o.inp_bits <= 16 && o.out_bits <= 16 &&
-                      l.q.gate_l_bits <= 16 && l.q.gate_r_bits <= 16 && l.q.u_bits <= 16;
+      const bool tc = tc_glu;
       if (tc) {
         FxpTcGluArgs t{};
-        t.XS = p.XS; t.X = p.X; t.G = p.G; t.rows = rows; t.c = c; t.fm = p.fm; t.ex = p.ex; t.status = p.status;
+        t.XS = bu; t.relu_in = relu_in_glu ? 1 : 0; t.X = p.X; t.G = p.G; t.rows = rows; t.c = c; t.fm = p.fm; t.ex = p.ex; t.status = p.status;
         t.D = p.D; t.rs_cre = p.rs_cre; t.rs_cim = p.rs_cim; t.rs_D = p.rs_D; t.y_bits = p.y_bits; t.conj = p.conj;
         t.o_in_change = p.o_in_change; t.y_exp = p.y_exp; t.o_inp_bits = p.o_inp_bits; t.o_inp_exp = p.o_inp_exp; t.o_rs = p.o_rs;
         t.o_out_bits = p.o_out_bits; t.o_out_exp = p.o_out_exp; t.o_bias_aligned = p.o_bias_aligned;
@@ -998,6 +1004,7 @@ extern "C" int s5b200_fxp_model_create(const s5_fxp_model_desc* d, s5_fxp_model*
   if (const char* e = getenv("S5B200_FXP_TC")) m->tc_on = atoi(e) != 0;
   if (const char* e = getenv("S5B200_FXP_TC_MIN_ROWS")) m->tc_min_rows = atoll(e);
   if (const char* e = getenv("S5B200_FXP_BN_DERIVE")) m->bn_derive = atoi(e) != 0;
+  if (const char* e = getenv("S5B200_FXP_RELU_IN_GLU")) m->relu_in_glu = atoi(e) != 0;
   if (const char* e = getenv("S5B200_FXP_BN_FORCE_SLOW")) m->bn_force_slow = atoi(e) != 0;
   const int H = d->H, P = d->P, dense = d->use_sparse ? 0 : 1;
   int rc = S5_OK;

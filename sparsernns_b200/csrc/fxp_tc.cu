@@ -547,23 +547,27 @@ __global__ void __launch_bounds__(kFgThreads, 1) fxp_tc_glu_kernel(const __grid_
     const int rv = (int)min((long long)th, row_end - row0);
     // ---- S: 8 rows per warp, one 16-byte load per lane and row
     int bad = 0;
-    {
-      const int rb = warp * PB;
-      int4 raw[PB];
+    const int rb_s = warp * PB;
+    int4 raw[PB];
 #pragma unroll
-      for (int q = 0; q < PB; ++q)
-        raw[q] = *reinterpret_cast<const int4*>(a.XS + (size_t)min(row0 + rb + q, last_row) * K1 + xs_col);
-      if (kin && rb < rv) {
+    for (int q = 0; q < PB; ++q)
+      raw[q] = *reinterpret_cast<const int4*>(a.XS + (size_t)min(row0 + rb_s + q, last_row) * K1 + xs_col);
+    if (kin && rb_s < rv) {
 #pragma unroll
-        for (int q = 0; q < PB; ++q) {
-          const int4 v = raw[q];
-          if (rb + q < rv)
-            bad |= (int)((((uint32_t)v.x + 0x8000u) | ((uint32_t)v.y + 0x8000u) | ((uint32_t)v.z + 0x8000u) | ((uint32_t)v.w + 0x8000u)) >> 16);
-          uint32_t lo, hi;
-          split_planes((uint32_t)v.x, (uint32_t)v.y, (uint32_t)v.z, (uint32_t)v.w, lo, hi);
-          *reinterpret_cast<uint32_t*>(Ph + aoff + (uint32_t)(rb + q) * 16u) = hi;
-          *reinterpret_cast<uint32_t*>(Pl + aoff + (uint32_t)(rb + q) * 16u) = lo;
+      for (int q = 0; q < PB; ++q) {
+        int4 v = raw[q];
+        if (rb_s + q < rv)
+          bad |= (int)((((uint32_t)v.x + 0x8000u) | ((uint32_t)v.y + 0x8000u) | ((uint32_t)v.z + 0x8000u) | ((uint32_t)v.w + 0x8000u)) >> 16);
+        if (a.relu_in) {
+          // fxp_relu on the complex state (fxpmodel.py:30-45, :740-742) when the scan left it to this kernel: lexicographic
+          // test; the float32 round trip of the kept values is the identity below 2^24 (and a tile with such a value is bad)
+          const bool k0 = v.x > 0 || (v.x == 0 && v.y > 0), k1 = v.z > 0 || (v.z == 0 && v.w > 0);
+          v.x = k0 ? v.x : 0; v.y = k0 ? v.y : 0; v.z = k1 ? v.z : 0; v.w = k1 ? v.w : 0;
         }
+        uint32_t lo, hi;
+        split_planes((uint32_t)v.x, (uint32_t)v.y, (uint32_t)v.z, (uint32_t)v.w, lo, hi);
+        *reinterpret_cast<uint32_t*>(Ph + aoff + (uint32_t)(rb_s + q) * 16u) = hi;
+        *reinterpret_cast<uint32_t*>(Pl + aoff + (uint32_t)(rb_s + q) * 16u) = lo;
       }
     }
     fence_proxy_async_smem();
@@ -571,6 +575,17 @@ __global__ void __launch_bounds__(kFgThreads, 1) fxp_tc_glu_kernel(const __grid_
     bad = __syncthreads_or(bad);
     tc_fence_after();
     if (bad) {                                                  // CTA-uniform: leave the tile to the CUDA-core kernel
+      if (a.relu_in && kin) {
+        // that kernel expects ReLU-ed states in memory: write this tile back with the exact fxp_relu (float round trip)
+#pragma unroll
+        for (int q = 0; q < PB; ++q)
+          if (rb_s + q < rv) {
+            int4 v = raw[q];
+            fx_relu_complex(v.x, v.y);
+            fx_relu_complex(v.z, v.w);
+            *reinterpret_cast<int4*>(a.XS + (size_t)(row0 + rb_s + q) * K1 + xs_col) = v;
+          }
+      }
       if (tid == 0) {
         const int slot = atomicAdd(a.bad_count, 1);
         a.bad_list[2 * slot] = (int)row0;

@@ -46,7 +46,8 @@ struct FxpTcGluDev {
   bool ok = false;
 };
 struct FxpTcGluArgs {
-  const int* XS; const int* X; int* G; long long rows;
+  int* XS; const int* X; int* G; long long rows;
+  int relu_in;                     // the scan left fxp_relu of the states to this kernel (bad tiles are written back ReLU-ed)
   BnChain c; unsigned* fm; int* ex; int* status;
   const int* D; int rs_cre, rs_cim, rs_D, y_bits, conj;
   int o_in_change, y_exp, o_inp_bits, o_inp_exp, o_rs, o_out_bits, o_out_exp; const int* o_bias_aligned;

@@ -12,6 +12,9 @@
 //      prefetch ring over time.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
+
+#include <cuda.h>   // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
 
 #include "scan.cuh"
 
@@ -661,11 +664,183 @@ __global__ void __launch_bounds__(384) scan_i32_ws_kernel(ScanI32Params q, int S
   if (leader) bulk_wait0();
 }
 
+
+// ---- state-split variant for FEW clips.  One CTA per clip leaves most of the GPU idle when there are fewer clips than
+// SMs (32 clips: 32 of 148), and each of those SMs then has to stream its clip's whole Bu / xs (3.8 MB at L = 3751, P = 64)
+// through ONE SM's memory path (~50 GB/s): measured 127 us against ~36 us for the dependent chain.  The states of a clip
+// are independent, so a CTA takes 32 of them: P / 32 CTAs per clip.  Its tile is a [32 steps][32 states] column block of
+// the interleaved [B][L][P] array - a strided box, moved by 3-D TENSOR-MAP bulk copies (cp.async.bulk.tensor, dims
+// {2P ints, L, B}): rows past the end of a clip are zero-filled on load and clipped on store, so the last short tile
+// needs no special case.  Same three roles (pre-shift, chain, post / ReLU + store), one warp each, up to four post warps.
+constexpr int kSplitStates = 32;
+constexpr int kSplitMaxStages = 24;   // 8 KB per stage: a deep ring (look-ahead of ~20 tiles = several us) costs little shared memory
+__device__ __forceinline__ void tma3d_load(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(smem_u32(dst)),
+               "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tma3d_store(const CUtensorMap* tm, int c0, int c1, int c2, const void* src) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(reinterpret_cast<uint64_t>(tm)),
+               "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(src))
+               : "memory");
+}
+
+#ifdef S5_SCAN_TRACE
+#include <cstdio>
+#define SPLIT_TRACE_DECL long long tr_wait = 0; const long long tr_t0 = clock64();
+#define SPLIT_WAIT(stmt) do { const long long t_ = clock64(); stmt; tr_wait += clock64() - t_; } while (0)
+#define SPLIT_TRACE_PRINT if (blockIdx.x == 5 && lane == 0) printf("[split role %d] total %lld waiting %lld cycles, %d tiles\n", role, clock64() - tr_t0, tr_wait, ntiles);
+#else
+#define SPLIT_TRACE_DECL
+#define SPLIT_WAIT(stmt) stmt
+#define SPLIT_TRACE_PRINT
+#endif
+__global__ void __launch_bounds__(192) scan_i32_split_kernel(const __grid_constant__ CUtensorMap tin, const __grid_constant__ CUtensorMap tout,
+                                                             ScanI32Params q, int S, int npost, int nsplit) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t full[kSplitMaxStages], aligned[kSplitMaxStages], scanned[kSplitMaxStages];
+  const int L = q.L;
+  // Roles: 0 pre, 1 chain, 2 .. 1 + npost post.  Warp w issues on scheduler w % 4: the chain warp (its ~12 dependent
+  // ALU / FMA instructions per step are the critical path of the kernel) is warp 2, alone on its scheduler with up to six warps
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int role = wid == 2 ? 1 : (wid == 1 ? 2 : wid);    // warps 0, 1, 2, 3.. = pre, post 0, chain, post 1..
+  const int b = blockIdx.x / nsplit, sub = blockIdx.x - b * nsplit;
+  const int p = sub * kSplitStates + lane;
+  constexpr uint32_t stage_bytes = kRingSteps * kSplitStates * 8;
+  const int ntiles = (L + kRingSteps - 1) / kRingSteps;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&aligned[s], 1); mbar_init(&scanned[s], 1); }
+    fence_mbar_init();
+  }
+  __syncthreads();
+  auto issue_load = [&](int t) {
+    const int s = t % S;
+    mbar_expect_tx(&full[s], stage_bytes);
+    tma3d_load(smem_raw + (size_t)s * stage_bytes, &tin, 2 * kSplitStates * sub, t * kRingSteps, b, &full[s]);
+  };
+  const bool leader = role == 2 && lane == 0;
+  if (leader)
+    for (int t = 0; t < min(S, ntiles); ++t) issue_load(t);
+  const int sl_re = max(0, q.ex_re - q.eBu_re), sr_re = max(0, q.eBu_re - q.ex_re);
+  const int sl_im = max(0, q.ex_im - q.eBu_im), sr_im = max(0, q.eBu_im - q.ex_im);
+  const int ar = q.A_re[p], ai = q.A_im[p];
+  int xr = 0, xi = 0;
+  SPLIT_TRACE_DECL
+  for (int i = 0; i < ntiles; ++i) {
+    const int s = i % S;
+    const uint32_t par = (uint32_t)(i / S) & 1u;
+    const int rows = min(kRingSteps, L - i * kRingSteps);
+    int2* c2 = reinterpret_cast<int2*>(smem_raw + (size_t)s * stage_bytes) + lane;
+    if (role == 0) {
+      SPLIT_WAIT(mbar_wait(&full[s], par));
+#pragma unroll
+      for (int t0 = 0; t0 < kRingSteps; t0 += 8) {
+        int2 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = c2[(t0 + j) * kSplitStates];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          v[j].x = (int)((unsigned)v[j].x << sl_re) >> sr_re;
+          v[j].y = (int)((unsigned)v[j].y << sl_im) >> sr_im;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) c2[(t0 + j) * kSplitStates] = v[j];
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&aligned[s]);
+    } else if (role == 1) {
+      SPLIT_WAIT(mbar_wait(&aligned[s], par));
+      int vr[kRingSteps], vi[kRingSteps];
+#pragma unroll
+      for (int t = 0; t < kRingSteps; ++t) { const int2 v = c2[t * kSplitStates]; vr[t] = v.x; vi[t] = v.y; }
+#pragma unroll
+      for (int t = 0; t < kRingSteps; ++t) {
+        const int nr = (int)((unsigned)(mulw(ar, xr) >> q.eA_re) - (unsigned)(mulw(ai, xi) >> q.eA_re) + (unsigned)vr[t]);
+        const int ni = (int)((unsigned)(mulw(ar, xi) >> q.eA_im) + (unsigned)(mulw(ai, xr) >> q.eA_im) + (unsigned)vi[t]);
+        xr = nr; xi = ni;
+        vr[t] = nr; vi[t] = ni;
+      }
+#pragma unroll
+      for (int t = 0; t < kRingSteps; ++t) c2[t * kSplitStates] = make_int2(vr[t], vi[t]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&scanned[s]);
+    } else {
+      SPLIT_WAIT(mbar_wait(&scanned[s], par));
+      if (q.relu) {
+        for (int t0 = 8 * (role - 2); t0 < rows; t0 += 8 * npost) {
+          int a[8], c[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { const int2 v = c2[(t0 + j) * kSplitStates]; a[j] = v.x; c[j] = v.y; }
+          unsigned big = 0;   // see scan_i32_ws_kernel: only kept values with |v| >= 2^24 change in the float round trip
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            big |= ((unsigned)(a[j] + (1 << 24)) | (unsigned)(c[j] + (1 << 24))) >> 25;
+            const bool keep = a[j] > 0 || (a[j] == 0 && c[j] > 0);
+            a[j] = keep ? a[j] : 0; c[j] = keep ? c[j] : 0;
+          }
+          if (__any_sync(0xffffffffu, big != 0)) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) fxp_relu_complex(a[j], c[j]);
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) c2[(t0 + j) * kSplitStates] = make_int2(a[j], c[j]);
+        }
+      }
+      fence_proxy_async_smem();
+      SPLIT_WAIT(asm volatile("bar.sync 1, %0;" ::"r"(32 * npost) : "memory"));
+      if (leader) {
+        tma3d_store(&tout, 2 * kSplitStates * sub, i * kRingSteps, b, smem_raw + (size_t)s * stage_bytes);
+        bulk_commit();
+        if (i >= 1 && i - 1 + S < ntiles) {                    // the store of tile i-1 has released its stage
+          SPLIT_WAIT(bulk_wait_read1());
+          issue_load(i - 1 + S);
+        }
+      }
+    }
+  }
+  SPLIT_TRACE_PRINT
+  if (leader) bulk_wait0();
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (the library links the static runtime only)
+static int make_tmap3d_i32(CUtensorMap* tm, const void* base, int P, int L, long long B) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                               const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qr) != cudaSuccess || qr != cudaDriverEntryPointSuccess) f = nullptr;
+    return reinterpret_cast<EncodeFn>(f);
+  }();
+  if (!fn) return -1;
+  const cuuint64_t dims[3] = {(cuuint64_t)2 * P, (cuuint64_t)L, (cuuint64_t)B};
+  const cuuint64_t strides[2] = {(cuuint64_t)2 * P * 4, (cuuint64_t)L * 2 * P * 4};
+  const cuuint32_t box[3] = {2 * kSplitStates, kRingSteps, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_INT32, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -1;
+}
+
 int launch_scan_i32(const ScanI32Params& q, bool interleaved, cudaStream_t st) {
   const long long B = q.lanes / q.P;
   const bool ptr_ok = aligned16(q.Bu_re) && aligned16(q.xs_re) && (interleaved || (aligned16(q.Bu_im) && aligned16(q.xs_im)));
   const bool ring_ok = ptr_ok && q.P <= 256 && (interleaved ? (q.P % 2 == 0) : (q.P % 4 == 0)) && B <= 0x7fffffffLL;
   ProfScope prof(S5_K_SCAN_I32, st);
+  // fewer clips than SMs: 32 states per CTA (S5B200_SCAN_I32_SPLIT=0: one CTA per clip)
+  static const bool split_on = [] { const char* e = getenv("S5B200_SCAN_I32_SPLIT"); return !e || atoi(e) != 0; }();
+  if (split_on && ring_ok && interleaved && q.P % kSplitStates == 0 && q.P > kSplitStates && B < sm_count() && q.L < (1 << 30)) {
+    CUtensorMap tin, tout;
+    if (make_tmap3d_i32(&tin, q.Bu_re, q.P, q.L, B) == 0 && make_tmap3d_i32(&tout, q.xs_re, q.P, q.L, B) == 0) {
+      static const int split_stages = [] { const char* e = getenv("S5B200_SCAN_I32_STAGES"); return e ? std::max(3, std::min(kSplitMaxStages, atoi(e))) : 20; }();
+      const int nsplit = q.P / kSplitStates, npost = q.relu ? 4 : 1, stages = split_stages;
+      const size_t smem = (size_t)stages * kRingSteps * kSplitStates * 8;
+      S5_CUDA(cudaFuncSetAttribute(scan_i32_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      scan_i32_split_kernel<<<(unsigned)(B * nsplit), 32 * (2 + npost), smem, st>>>(tin, tout, q, stages, npost, nsplit);
+      S5_LAUNCH_CHECK();
+      return S5_OK;
+    }
+  }
   if (ring_ok) {
     // ring depth: ~8 tiles (6 in flight = 192 steps of look-ahead, about 2 us of dependent-chain time) when there are
     // few clips; shallower when many clips share an SM so that several CTAs stay resident
