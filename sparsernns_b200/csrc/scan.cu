@@ -673,7 +673,11 @@ __global__ void __launch_bounds__(384) scan_i32_ws_kernel(ScanI32Params q, int S
 // {2P ints, L, B}): rows past the end of a clip are zero-filled on load and clipped on store, so the last short tile
 // needs no special case.  Same three roles (pre-shift, chain, post / ReLU + store), one warp each, up to four post warps.
 constexpr int kSplitStates = 32;
-constexpr int kSplitMaxStages = 24;   // 8 KB per stage: a deep ring (look-ahead of ~20 tiles = several us) costs little shared memory
+#ifndef S5_SPLIT_STEPS
+#define S5_SPLIT_STEPS 64
+#endif
+constexpr int kSplitSteps = S5_SPLIT_STEPS;   // time steps per tile: the per-tile hand-over (mbarrier wait + arrive, ~200 cycles) is amortised over them
+constexpr int kSplitMaxStages = 12;   // 16 KB per stage (input tile + output tile)
 __device__ __forceinline__ void tma3d_load(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, uint64_t* bar) {
   asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(smem_u32(dst)),
                "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
@@ -706,35 +710,38 @@ __global__ void __launch_bounds__(192) scan_i32_split_kernel(const __grid_consta
   const int role = wid == 2 ? 1 : (wid == 1 ? 2 : wid);    // warps 0, 1, 2, 3.. = pre, post 0, chain, post 1..
   const int b = blockIdx.x / nsplit, sub = blockIdx.x - b * nsplit;
   const int p = sub * kSplitStates + lane;
-  constexpr uint32_t stage_bytes = kRingSteps * kSplitStates * 8;
-  const int ntiles = (L + kRingSteps - 1) / kRingSteps;
+  // A stage is an input tile and a separate output tile: the chain warp loads its 32 inputs from one and stores its 32 states
+  // to the other.  In place, the loads of later steps queue behind the stores of earlier ones: measured 36 cycles per step
+  // against 20-22 for the bare dependent chain (profiles/scripts/chain_rate.cu).
+  constexpr uint32_t tile_bytes = kSplitSteps * kSplitStates * 8, stage_bytes = 2 * tile_bytes;
+  const int ntiles = (L + kSplitSteps - 1) / kSplitSteps;
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&aligned[s], 1); mbar_init(&scanned[s], 1); }
     fence_mbar_init();
   }
   __syncthreads();
-  auto issue_load = [&](int t) {
-    const int s = t % S;
-    mbar_expect_tx(&full[s], stage_bytes);
-    tma3d_load(smem_raw + (size_t)s * stage_bytes, &tin, 2 * kSplitStates * sub, t * kRingSteps, b, &full[s]);
+  auto issue_load = [&](int t, int st) {                      // tile t into stage st (= t % S)
+    mbar_expect_tx(&full[st], tile_bytes);
+    tma3d_load(smem_raw + (size_t)st * stage_bytes, &tin, 2 * kSplitStates * sub, t * kSplitSteps, b, &full[st]);
   };
   const bool leader = role == 2 && lane == 0;
   if (leader)
-    for (int t = 0; t < min(S, ntiles); ++t) issue_load(t);
+    for (int t = 0; t < min(S, ntiles); ++t) issue_load(t, t);
   const int sl_re = max(0, q.ex_re - q.eBu_re), sr_re = max(0, q.eBu_re - q.ex_re);
   const int sl_im = max(0, q.ex_im - q.eBu_im), sr_im = max(0, q.eBu_im - q.ex_im);
   const int ar = q.A_re[p], ai = q.A_im[p];
   int xr = 0, xi = 0;
   SPLIT_TRACE_DECL
-  for (int i = 0; i < ntiles; ++i) {
-    const int s = i % S;
-    const uint32_t par = (uint32_t)(i / S) & 1u;
-    const int rows = min(kRingSteps, L - i * kRingSteps);
+  int s = 0;                                                  // stage and parity advance incrementally: S is a run-time
+  uint32_t par = 0;                                           // value, and i % S, i / S cost ~40 instructions per tile and role
+  for (int i = 0; i < ntiles; ++i, s = (s + 1 == S ? 0 : s + 1), par ^= (s == 0 ? 1u : 0u)) {
+    const int rows = min(kSplitSteps, L - i * kSplitSteps);
     int2* c2 = reinterpret_cast<int2*>(smem_raw + (size_t)s * stage_bytes) + lane;
+    int2* o2 = reinterpret_cast<int2*>(smem_raw + (size_t)s * stage_bytes + tile_bytes) + lane;
     if (role == 0) {
       SPLIT_WAIT(mbar_wait(&full[s], par));
 #pragma unroll
-      for (int t0 = 0; t0 < kRingSteps; t0 += 8) {
+      for (int t0 = 0; t0 < kSplitSteps; t0 += 8) {
         int2 v[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = c2[(t0 + j) * kSplitStates];
@@ -750,18 +757,16 @@ __global__ void __launch_bounds__(192) scan_i32_split_kernel(const __grid_consta
       if (lane == 0) mbar_arrive(&aligned[s]);
     } else if (role == 1) {
       SPLIT_WAIT(mbar_wait(&aligned[s], par));
-      int vr[kRingSteps], vi[kRingSteps];
+      int vr[kSplitSteps], vi[kSplitSteps];
 #pragma unroll
-      for (int t = 0; t < kRingSteps; ++t) { const int2 v = c2[t * kSplitStates]; vr[t] = v.x; vi[t] = v.y; }
+      for (int t = 0; t < kSplitSteps; ++t) { const int2 v = c2[t * kSplitStates]; vr[t] = v.x; vi[t] = v.y; }
 #pragma unroll
-      for (int t = 0; t < kRingSteps; ++t) {
+      for (int t = 0; t < kSplitSteps; ++t) {
         const int nr = (int)((unsigned)(mulw(ar, xr) >> q.eA_re) - (unsigned)(mulw(ai, xi) >> q.eA_re) + (unsigned)vr[t]);
         const int ni = (int)((unsigned)(mulw(ar, xi) >> q.eA_im) + (unsigned)(mulw(ai, xr) >> q.eA_im) + (unsigned)vi[t]);
         xr = nr; xi = ni;
-        vr[t] = nr; vi[t] = ni;
+        o2[t * kSplitStates] = make_int2(nr, ni);
       }
-#pragma unroll
-      for (int t = 0; t < kRingSteps; ++t) c2[t * kSplitStates] = make_int2(vr[t], vi[t]);
       __syncwarp();
       if (lane == 0) mbar_arrive(&scanned[s]);
     } else {
@@ -770,7 +775,7 @@ __global__ void __launch_bounds__(192) scan_i32_split_kernel(const __grid_consta
         for (int t0 = 8 * (role - 2); t0 < rows; t0 += 8 * npost) {
           int a[8], c[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) { const int2 v = c2[(t0 + j) * kSplitStates]; a[j] = v.x; c[j] = v.y; }
+          for (int j = 0; j < 8; ++j) { const int2 v = o2[(t0 + j) * kSplitStates]; a[j] = v.x; c[j] = v.y; }
           unsigned big = 0;   // see scan_i32_ws_kernel: only kept values with |v| >= 2^24 change in the float round trip
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -783,17 +788,17 @@ __global__ void __launch_bounds__(192) scan_i32_split_kernel(const __grid_consta
             for (int j = 0; j < 8; ++j) fxp_relu_complex(a[j], c[j]);
           }
 #pragma unroll
-          for (int j = 0; j < 8; ++j) c2[(t0 + j) * kSplitStates] = make_int2(a[j], c[j]);
+          for (int j = 0; j < 8; ++j) o2[(t0 + j) * kSplitStates] = make_int2(a[j], c[j]);
         }
       }
       fence_proxy_async_smem();
       SPLIT_WAIT(asm volatile("bar.sync 1, %0;" ::"r"(32 * npost) : "memory"));
       if (leader) {
-        tma3d_store(&tout, 2 * kSplitStates * sub, i * kRingSteps, b, smem_raw + (size_t)s * stage_bytes);
+        tma3d_store(&tout, 2 * kSplitStates * sub, i * kSplitSteps, b, smem_raw + (size_t)s * stage_bytes + tile_bytes);
         bulk_commit();
         if (i >= 1 && i - 1 + S < ntiles) {                    // the store of tile i-1 has released its stage
           SPLIT_WAIT(bulk_wait_read1());
-          issue_load(i - 1 + S);
+          issue_load(i - 1 + S, s == 0 ? S - 1 : s - 1);
         }
       }
     }
@@ -815,7 +820,7 @@ static int make_tmap3d_i32(CUtensorMap* tm, const void* base, int P, int L, long
   if (!fn) return -1;
   const cuuint64_t dims[3] = {(cuuint64_t)2 * P, (cuuint64_t)L, (cuuint64_t)B};
   const cuuint64_t strides[2] = {(cuuint64_t)2 * P * 4, (cuuint64_t)L * 2 * P * 4};
-  const cuuint32_t box[3] = {2 * kSplitStates, kRingSteps, 1};
+  const cuuint32_t box[3] = {2 * kSplitStates, kSplitSteps, 1};
   const cuuint32_t estr[3] = {1, 1, 1};
   const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_INT32, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -832,9 +837,9 @@ int launch_scan_i32(const ScanI32Params& q, bool interleaved, cudaStream_t st) {
   if (split_on && ring_ok && interleaved && q.P % kSplitStates == 0 && q.P > kSplitStates && B < sm_count() && q.L < (1 << 30)) {
     CUtensorMap tin, tout;
     if (make_tmap3d_i32(&tin, q.Bu_re, q.P, q.L, B) == 0 && make_tmap3d_i32(&tout, q.xs_re, q.P, q.L, B) == 0) {
-      static const int split_stages = [] { const char* e = getenv("S5B200_SCAN_I32_STAGES"); return e ? std::max(3, std::min(kSplitMaxStages, atoi(e))) : 20; }();
+      static const int split_stages = [] { const char* e = getenv("S5B200_SCAN_I32_STAGES"); return e ? std::max(3, std::min(kSplitMaxStages, atoi(e))) : (kSplitSteps >= 64 ? 6 : 10); }();
       const int nsplit = q.P / kSplitStates, npost = q.relu ? 4 : 1, stages = split_stages;
-      const size_t smem = (size_t)stages * kRingSteps * kSplitStates * 8;
+      const size_t smem = (size_t)stages * 2 * kSplitSteps * kSplitStates * 8;   // input + output tile per stage
       S5_CUDA(cudaFuncSetAttribute(scan_i32_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       scan_i32_split_kernel<<<(unsigned)(B * nsplit), 32 * (2 + npost), smem, st>>>(tin, tout, q, stages, npost, nsplit);
       S5_LAUNCH_CHECK();
