@@ -1346,13 +1346,16 @@ __global__ void tc_glu_image_kernel(TcGluParams p, unsigned char* img) {
 // BPJ (implies SCAN): the B projection runs in the kernel, too: x tile -> u codes -> int8 planes -> MMA -> FQ(Bu) -> a
 // shared-memory tile that the recurrence threads read column-wise.  A whole S5 block is then ONE kernel that reads
 // the block input and writes the block output; Bu and the states never leave the SM.
-template <int HJ, bool SCAN, bool BPJ>
+// KJ > 0: K1 = 2P = 32 KJ is a compile-time constant as well (the NDNS shapes), so that the column loops of the TMEM passes
+// unroll and every tile / plane / TMEM address in them is an immediate offset instead of run-time integer arithmetic.
+template <int HJ, bool SCAN, bool BPJ, int KJ = 0>
 __global__ void __launch_bounds__(kGluThreads, 1) tc_glu_kernel(const __grid_constant__ TcGluMulti mp) {
   static_assert(SCAN || !BPJ, "the fused B projection needs the fused recurrence");
   TC_TRACE_ENTRY
   extern __shared__ __align__(128) unsigned char smem[];
   const TcGluParams& p0 = mp.layer[0];
-  const int H = p0.H, K1 = p0.K1;                             // the same for every layer
+  constexpr int H = 32 * HJ;
+  const int K1 = KJ > 0 ? 32 * KJ : p0.K1;                    // the same for every layer
   const int ldT = H + 4;                                      // floats per row of T
   const size_t wc_bytes = tc_tile_bytes(H, K1), wo_bytes = tc_tile_bytes8(H, kGluK2);
   const size_t p1_bytes = tc_tile_bytes(kTcRows, K1);         // one bf16 plane of the xs tile
@@ -1406,7 +1409,8 @@ __global__ void __launch_bounds__(kGluThreads, 1) tc_glu_kernel(const __grid_con
   // SCAN per-thread constants: state, segment
   const int P = K1 >> 1;
   const int sp = SCAN ? htid % P : 0, sseg = SCAN ? htid / P : 0, nseg = SCAN ? kGluHalf / P : 1;
-  const int sr = SCAN ? (p0.R + nseg - 1) / nseg : 0;         // rows per segment (<= 32)
+  // rows per segment (<= 32); the KJ instantiations are only launched with full-height tiles (R = 128 = 32 nseg)
+  const int sr = !SCAN ? 0 : (KJ > 0 ? 32 : (p0.R + nseg - 1) / nseg);
   const uint32_t poff = (uint32_t)(sp >> 2) * lbo + 4u * (sp & 3);   // plane offset of column k = 2 sp
   // ---- per-layer state: weight tiles in shared memory, per-lane constants in registers
   // All scales are powers of two, so folding them into the BatchNorm / feed-through constants changes no rounding:
@@ -1618,7 +1622,7 @@ __global__ void __launch_bounds__(kGluThreads, 1) tc_glu_kernel(const __grid_con
         // the recurrence threads pick their 32 frames of one state out of the tile
 #pragma unroll
         for (int i = 0; i < 32; ++i)
-          v[i] = *reinterpret_cast<const float2*>(BuT + (size_t)min(sseg * sr + i, kTcRows - 1) * ldB + 2 * sp);
+          v[i] = *reinterpret_cast<const float2*>(BuT + (size_t)(KJ > 0 ? sseg * sr + i : min(sseg * sr + i, kTcRows - 1)) * ldB + 2 * sp);
       } else {
         const float2* bu = reinterpret_cast<const float2*>(pXS) + (size_t)row0 * P + sp;
         // 32 unpredicated, unclamped loads: rows past the segment are ignored, rows past the end of Bu fall into the
@@ -2624,9 +2628,9 @@ void tc_glu_free(TcGluDev* d) {
   *d = TcGluDev();
 }
 
-template <int HJ, bool SCAN, bool BPJ>
+template <int HJ, bool SCAN, bool BPJ, int KJ = 0>
 static int tc_glu_go_multi(const TcGluMulti& mp, size_t smem, int grid, cudaStream_t st) {
-  auto kernel = tc_glu_kernel<HJ, SCAN, BPJ>;
+  auto kernel = tc_glu_kernel<HJ, SCAN, BPJ, KJ>;
   S5_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   ProfScope prof(BPJ ? S5_K_BLOCK : SCAN ? S5_K_GLU_SCAN : S5_K_GLU, st);
   if constexpr (SCAN) {
@@ -2857,7 +2861,10 @@ int tc_glu_launch_multi(const TcGluDev* const* devs, const TcGluArgs* args, int 
   switch (devs[0]->H >> 5) {
     case 1: return tc_glu_go_multi<1, true, true>(mp, smem, grid, st);
     case 2: return tc_glu_go_multi<2, true, true>(mp, smem, grid, st);
-    case 3: return tc_glu_go_multi<3, true, true>(mp, smem, grid, st);
+    case 3:
+      // NDNS dim_scale 0.5: H 96, P 64, full-height tiles (every clip of at least 128 frames)
+      if (devs[0]->K1 == 128 && mp.layer[0].R == kTcRows) return tc_glu_go_multi<3, true, true, 4>(mp, smem, grid, st);
+      return tc_glu_go_multi<3, true, true>(mp, smem, grid, st);
     default: return tc_glu_go_multi<4, true, true>(mp, smem, grid, st);
   }
 }
