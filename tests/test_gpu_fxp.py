@@ -275,20 +275,23 @@ def _global_batch_worker(rank, world, port):
         xn = zoo["x"].copy()
         xn[2:] *= 0.05
         x = torch.from_numpy(xn).cuda()
-        one = PF.FxpRegressionModel(md, q, n_layers)                         # ONE process on the union batch
-        y_full = one(one.quantize_input(x))
-        lo, hi = shard_range(4, rank, world)
-        glob = PF.FxpRegressionModel(md, q, n_layers, global_batch=True)     # sharded, maxima all-reduced over NCCL
-        y_g = glob(glob.quantize_input(x[lo:hi]))
-        assert y_g.exp == y_full.exp and torch.equal(y_g.data, y_full.data[lo:hi]), f"rank {rank}: global-batch parity"
-        for i in range(n_layers):
-            t_g, t_f = glob.tap(x_q := glob.quantize_input(x[lo:hi]), i, PF.TAP_OUTPUT), one.tap(one.quantize_input(x), i, PF.TAP_OUTPUT)
-            assert t_g.exp == t_f.exp and torch.equal(t_g.data, t_f.data[lo:hi]), f"rank {rank}: block {i} output"
-        local = PF.FxpRegressionModel(md, q, n_layers)                       # shard-local parity (the default)
-        y_l = local(local.quantize_input(x[lo:hi]))
-        differs = torch.tensor([int(not torch.equal(y_l.data, y_full.data[lo:hi]))], device="cuda")
-        dist.all_reduce(differs)
-        assert int(differs.item()) >= 1, "the test batch should make shard-local and global-batch results differ somewhere"
+        # both code paths under sharding: the dense-tile kernels (column extremes travel in the all-reduce) and the CUDA-core ones
+        for min_rows in ("1", "1000000000"):
+            os.environ["S5B200_FXP_TC_MIN_ROWS"] = min_rows
+            one = PF.FxpRegressionModel(md, q, n_layers)                         # ONE process on the union batch
+            y_full = one(one.quantize_input(x))
+            lo, hi = shard_range(4, rank, world)
+            glob = PF.FxpRegressionModel(md, q, n_layers, global_batch=True)     # sharded, maxima all-reduced over NCCL
+            y_g = glob(glob.quantize_input(x[lo:hi]))
+            assert y_g.exp == y_full.exp and torch.equal(y_g.data, y_full.data[lo:hi]), f"rank {rank}: global-batch parity"
+            for i in range(n_layers):
+                t_g, t_f = glob.tap(x_q := glob.quantize_input(x[lo:hi]), i, PF.TAP_OUTPUT), one.tap(one.quantize_input(x), i, PF.TAP_OUTPUT)
+                assert t_g.exp == t_f.exp and torch.equal(t_g.data, t_f.data[lo:hi]), f"rank {rank}: block {i} output"
+            local = PF.FxpRegressionModel(md, q, n_layers)                       # shard-local parity (the default)
+            y_l = local(local.quantize_input(x[lo:hi]))
+            differs = torch.tensor([int(not torch.equal(y_l.data, y_full.data[lo:hi]))], device="cuda")
+            dist.all_reduce(differs)
+            assert int(differs.item()) >= 1, "the test batch should make shard-local and global-batch results differ somewhere"
     finally:
         dist.destroy_process_group()
 
