@@ -2190,11 +2190,7 @@ __global__ void __launch_bounds__(kGluwThreads, 1) tc_gluw_kernel(const __grid_c
     tc_fence_after();
     // ---- E2: o = FQ(out2(x1)); right-gate code FQ(sigmoid(o)) -> second half of the T row
     if (erow0 < rv) {
-      for (int c0 = cbeg; c0 < cbeg + cw; c0 += 8) {
-        uint32_t vh[8], vl[8];
-        tc_ld8(tcol + lane_base + c0, vh);
-        tc_ld8(tcol + lane_base + 256 + c0, vl);
-        tc_wait_ld();
+      auto e2_8 = [&](const uint32_t (&vh)[8], const uint32_t (&vl)[8], int c0) {
         uint32_t sb[8];
 #pragma unroll
         for (int j = 0; j < 8; j += 4) {
@@ -2214,6 +2210,27 @@ __global__ void __launch_bounds__(kGluwThreads, 1) tc_gluw_kernel(const __grid_c
         pk.x = __byte_perm(sb[0], sb[1], 0x5410); pk.y = __byte_perm(sb[2], sb[3], 0x5410);
         pk.z = __byte_perm(sb[4], sb[5], 0x5410); pk.w = __byte_perm(sb[6], sb[7], 0x5410);
         *reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(T + (size_t)erow * ldT) + 2 * H + 2 * c0) = pk;
+      };
+      // two register sets: the TMEM loads of the next 8 columns are in flight while these 8 are post-processed
+      uint32_t ah[8], al[8], bh[8], bl[8];
+      tc_ld8(tcol + lane_base + cbeg, ah);
+      tc_ld8(tcol + lane_base + 256 + cbeg, al);
+#pragma unroll
+      for (int c0 = 0; c0 < cw; c0 += 16) {                   // cw = 8 HJ: a multiple of 16 for even HJ, else one odd group of 8
+        tc_wait_ld();
+        if (c0 + 8 < cw) {
+          tc_ld8(tcol + lane_base + cbeg + c0 + 8, bh);
+          tc_ld8(tcol + lane_base + 256 + cbeg + c0 + 8, bl);
+        }
+        e2_8(ah, al, cbeg + c0);
+        if (c0 + 8 < cw) {
+          tc_wait_ld();
+          if (c0 + 16 < cw) {
+            tc_ld8(tcol + lane_base + cbeg + c0 + 16, ah);
+            tc_ld8(tcol + lane_base + 256 + cbeg + c0 + 16, al);
+          }
+          e2_8(bh, bl, cbeg + c0 + 8);
+        }
       }
     }
     tc_fence_before();
@@ -2230,14 +2247,38 @@ __global__ void __launch_bounds__(kGluwThreads, 1) tc_gluw_kernel(const __grid_c
       }
       const unsigned short* trow = reinterpret_cast<const unsigned short*>(T + (size_t)rb * ldT) + lane;
       float* yr = p.OUT + (size_t)(row0 + rb) * H + lane;
+      if (rb + PB <= rv) {
+        // whole batch: two rows at a time, every code first, then the arithmetic, then the stores (a per-row exit test turns
+        // every row into its own dependent load -> multiply -> store chain)
 #pragma unroll
-      for (int q = 0; q < PB; ++q) {
-        if (rb + q >= rv) break;                              // warp-uniform
+        for (int q0 = 0; q0 < PB; q0 += 2) {
+          uint32_t lc[2][HJ], rc[2][HJ];
 #pragma unroll
-        for (int j = 0; j < HJ; ++j) {
-          const float l = (__uint_as_float(0x4B400000u + trow[(size_t)q * 2 * ldT + 32 * j]) - kRoundMagic) * gl_s;
-          const float sg = (__uint_as_float(0x4B400000u + trow[(size_t)q * 2 * ldT + H + 32 * j]) - kRoundMagic) * gr_s;
-          yr[(size_t)q * H + 32 * j] = fmaxf(fmaf(l, sg, xin[q][j]), out_floor);
+          for (int q = 0; q < 2; ++q)
+#pragma unroll
+            for (int j = 0; j < HJ; ++j) {
+              lc[q][j] = trow[(size_t)(q0 + q) * 2 * ldT + 32 * j];
+              rc[q][j] = trow[(size_t)(q0 + q) * 2 * ldT + H + 32 * j];
+            }
+#pragma unroll
+          for (int q = 0; q < 2; ++q)
+#pragma unroll
+            for (int j = 0; j < HJ; ++j) {
+              const float l = (__uint_as_float(0x4B400000u + lc[q][j]) - kRoundMagic) * gl_s;
+              const float sg = (__uint_as_float(0x4B400000u + rc[q][j]) - kRoundMagic) * gr_s;
+              yr[(size_t)(q0 + q) * H + 32 * j] = fmaxf(fmaf(l, sg, xin[q0 + q][j]), out_floor);
+            }
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < PB; ++q) {
+          if (rb + q >= rv) break;                              // warp-uniform
+#pragma unroll
+          for (int j = 0; j < HJ; ++j) {
+            const float l = (__uint_as_float(0x4B400000u + trow[(size_t)q * 2 * ldT + 32 * j]) - kRoundMagic) * gl_s;
+            const float sg = (__uint_as_float(0x4B400000u + trow[(size_t)q * 2 * ldT + H + 32 * j]) - kRoundMagic) * gr_s;
+            yr[(size_t)q * H + 32 * j] = fmaxf(fmaf(l, sg, xin[q][j]), out_floor);
+          }
         }
       }
     }
