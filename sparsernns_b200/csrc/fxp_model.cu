@@ -282,6 +282,7 @@ struct FxpLinearParams {
   // ENC / RESID epilogue: maxima for the next block's first BatchNorm stage
   const int* next_mmean; int next_e_mean; unsigned* next_fm; int out_exp;
   unsigned* next_cmax; unsigned* next_cmin;   // dense-tile encoder only: column extremes instead of the float maxima
+  unsigned short* U16;                        // dense-tile B projection only: 16-bit copy of u for the GLU kernel
   // DEC: dynamic input exponent (ex[E_IN]) versus the static FxpDense input config
   int dec_inp_bits, dec_inp_exp, dec_w_exp, dec_out_exp;
   int skip_zero;   // proj.cuh:zero_group_mask (exact: a zero activation contributes 0 to the wrapping int32 sum)
@@ -413,7 +414,7 @@ static int launch_fxp_linear_tc(const FxpLinearParams& p, const FxpTcLinearDev& 
   a.rshift0 = p.rshift0; a.rshift1 = p.rshift1; a.out_bits = p.out_bits; a.bias_aligned = p.bias_aligned; a.relu = p.relu;
   a.out_scale = p.out_scale; a.c = p.c; a.fm = p.fm; a.ex = p.ex; a.status = p.status;
   a.next_mmean = p.next_mmean; a.next_e_mean = p.next_e_mean; a.next_fm = p.next_fm; a.out_exp = p.out_exp;
-  a.next_cmax = p.next_cmax; a.next_cmin = p.next_cmin;
+  a.next_cmax = p.next_cmax; a.next_cmin = p.next_cmin; a.U16 = p.U16;
   a.dec_inp_bits = p.dec_inp_bits; a.dec_inp_exp = p.dec_inp_exp; a.dec_w_exp = p.dec_w_exp; a.dec_out_exp = p.dec_out_exp;
   return fxp_tc_linear_launch(tc, a, kclass, st);
 }
@@ -761,6 +762,7 @@ struct s5_fxp_model {
   // S5B200_FXP_BN_DERIVE=0: the three BatchNorm-reduce passes per block instead of fxp_bn_derive_kernel;
   // S5B200_FXP_BN_FORCE_SLOW=1 (testing): the derive kernel takes its whole-tensor fallback
   bool bn_derive = true, bn_force_slow = false;
+  bool u16 = true;           // S5B200_FXP_U16=0: the dense-tile GLU kernel re-runs the BatchNorm chain instead of reading u from the B projection
   bool relu_in_glu = true;   // S5B200_FXP_RELU_IN_GLU=0: the scan applies fxp_relu itself even when the dense-tile GLU follows
   bool use_tc(long long rows) const { return tc_on && rows >= tc_min_rows; }
   s5_fxp_sync_fn sync = nullptr;   // global-batch parity under sharding: max-all-reduce of the running maxima (s5b200.h)
@@ -770,7 +772,7 @@ struct s5_fxp_model {
 namespace s5 {
 
 struct FxpWs {
-  size_t off_a, off_b, off_g, off_bu, off_state, off_bad, total;
+  size_t off_a, off_b, off_g, off_bu, off_state, off_bad, off_u16, total;
   size_t state_ints, max_words;
 };
 static FxpWs fxp_ws(const s5_fxp_model* m, int B, int L) {
@@ -785,7 +787,8 @@ static FxpWs fxp_ws(const s5_fxp_model* m, int B, int L) {
   w.state_ints = w.max_words + (size_t)(m->desc.n_layers + 1) * kStateStride + 8 + (size_t)m->desc.n_layers;
   w.off_bad = w.off_state + round_up(w.state_ints * 4, 256);
   // bad-tile list: (row0, count) per tile; tiles are at least 64 rows except one short tile per CTA
-  w.total = w.off_bad + round_up(((rows + 63) / 64 + 2048) * 8, 256);
+  w.off_u16 = w.off_bad + round_up(((rows + 63) / 64 + 2048) * 8, 256);
+  w.total = w.off_u16 + round_up(rows * m->desc.H * 2, 256);   // mixer input u as 16-bit payloads (B projection -> GLU, dense tiles)
   return w;
 }
 
@@ -809,6 +812,7 @@ struct FxpRun {
   int* status() const { return reinterpret_cast<int*>(base + w.off_state) + w.max_words + (size_t)(m->desc.n_layers + 1) * kStateStride; }
   int* bad_count(int l) const { return status() + 8 + l; }
   int* bad_list() const { return reinterpret_cast<int*>(base + w.off_bad); }
+  unsigned short* u16() const { return reinterpret_cast<unsigned short*>(base + w.off_u16); }
 };
 
 // Runs encoder + blocks [0, upto_layer]; stop_stage: 0 full block, 1 stop after BN (pre_s5 materialised into g),
@@ -877,20 +881,24 @@ static int fxp_run(const FxpRun& r, const void* x, bool x_is_float, int upto_lay
       *cur_out = g; *other_out = a;
       return S5_OK;
     }
+    // dense tiles: 16-bit operands everywhere (w8a16); tiles whose states exceed 16 bits come back in the list and
+    // are redone by the CUDA-core kernel, which multiplies full int32 states
+    const s5_fxp_dense_desc& o2 = l.out2.q;
+    const bool tc_glu = m->use_tc(rows) && l.tcg.ok && l.q.y_bits <= 16 && o2.inp_bits <= 16 && o2.out_bits <= 16 &&
+                        l.q.gate_l_bits <= 16 && l.q.gate_r_bits <= 16 && l.q.u_bits <= 16;
+    const bool tc_bproj = m->use_tc(rows) && l.tcb.ok && l.q.u_bits <= 16 && (d.H % 128) != 1;
+    // the dense-tile B projection leaves u behind as 16-bit payloads for the dense-tile GLU kernel (S5B200_FXP_U16=0: recompute)
+    unsigned short* u16 = (tc_bproj && tc_glu && m->u16 && (d.H & 3) == 0) ? r.u16() : nullptr;
     {  // Bu = fxp_matmul(u, B^T) for re / im (fxpmodel.py:631-644), interleaved
       FxpLinearParams p{};
       p.X = a; p.Y = bu; p.rows = rows; p.w = wview(l.wb); p.mode = LIN_BPROJ;
       p.rshift0 = l.q.u_exp + l.q.eB_re - l.q.Bu_re_exp; p.rshift1 = l.q.u_exp + l.q.eB_im - l.q.Bu_im_exp;
       p.round_mode = S5_ROUND_FLOOR; p.out_bits = l.q.Bu_re_bits;
       p.c = c; p.fm = r.fm(li); p.ex = r.ex(li); p.status = r.status();
-      const bool tc = m->use_tc(rows) && l.tcb.ok && l.q.u_bits <= 16 && (d.H % 128) != 1;
+      const bool tc = tc_bproj;
+      p.U16 = u16;
       if ((rc = tc ? launch_fxp_linear_tc(p, l.tcb, r.st, S5_K_FXP_BPROJ) : launch_fxp_linear(p, r.st, S5_K_FXP_BPROJ))) return rc;
     }
-    // dense tiles: 16-bit operands everywhere (w8a16); tiles whose states exceed 16 bits come back in the list and
-    // are redone by the CUDA-core kernel, which multiplies full int32 states
-    const s5_fxp_dense_desc& o2 = l.out2.q;
-    const bool tc_glu = m->use_tc(rows) && l.tcg.ok && l.q.y_bits <= 16 && o2.inp_bits <= 16 && o2.out_bits <= 16 &&
-                        l.q.gate_l_bits <= 16 && l.q.gate_r_bits <= 16 && l.q.u_bits <= 16;
     // fxp_relu of the states: in the scan's post role, or - cheaper, the scan is latency bound with few clips - while the
     // dense-tile GLU kernel stages them (not when the states themselves are tapped)
     const bool relu_in_glu = tc_glu && m->relu_in_glu && !(stop_stage == 2 && li == upto_layer);
@@ -923,7 +931,7 @@ static int fxp_run(const FxpRun& r, const void* x, bool x_is_float, int upto_lay
       const bool tc = tc_glu;
       if (tc) {
         FxpTcGluArgs t{};
-        t.XS = bu; t.relu_in = relu_in_glu ? 1 : 0; t.X = p.X; t.G = p.G; t.rows = rows; t.c = c; t.fm = p.fm; t.ex = p.ex; t.status = p.status;
+        t.XS = bu; t.relu_in = relu_in_glu ? 1 : 0; t.U16 = u16; t.X = p.X; t.G = p.G; t.rows = rows; t.c = c; t.fm = p.fm; t.ex = p.ex; t.status = p.status;
         t.D = p.D; t.rs_cre = p.rs_cre; t.rs_cim = p.rs_cim; t.rs_D = p.rs_D; t.y_bits = p.y_bits; t.conj = p.conj;
         t.o_in_change = p.o_in_change; t.y_exp = p.y_exp; t.o_inp_bits = p.o_inp_bits; t.o_inp_exp = p.o_inp_exp; t.o_rs = p.o_rs;
         t.o_out_bits = p.o_out_bits; t.o_out_exp = p.o_out_exp; t.o_bias_aligned = p.o_bias_aligned;
@@ -1005,6 +1013,7 @@ extern "C" int s5b200_fxp_model_create(const s5_fxp_model_desc* d, s5_fxp_model*
   if (const char* e = getenv("S5B200_FXP_TC_MIN_ROWS")) m->tc_min_rows = atoll(e);
   if (const char* e = getenv("S5B200_FXP_BN_DERIVE")) m->bn_derive = atoi(e) != 0;
   if (const char* e = getenv("S5B200_FXP_RELU_IN_GLU")) m->relu_in_glu = atoi(e) != 0;
+  if (const char* e = getenv("S5B200_FXP_U16")) m->u16 = atoi(e) != 0;
   if (const char* e = getenv("S5B200_FXP_BN_FORCE_SLOW")) m->bn_force_slow = atoi(e) != 0;
   const int H = d->H, P = d->P, dense = d->use_sparse ? 0 : 1;
   int rc = S5_OK;

@@ -165,6 +165,7 @@ __global__ void __launch_bounds__(kFtThreads, 2) fxp_tc_linear_kernel(const __gr
   };
   for (long long row0 = row_begin; row0 < row_end; row0 += kTcRows) {
     const int rv = (int)min((long long)kTcRows, row_end - row0);
+    unsigned short* utile = (MODE == LIN_BPROJ && VEC4 && a.U16) ? a.U16 + (size_t)row0 * p.Kfull + 4 * lane : nullptr;
     for (int rb = warp * RB; rb < rv; rb += NW * RB) {
       if (!(have_first && rb == warp * RB)) load_batch(row0, rb);
 #pragma unroll
@@ -185,6 +186,13 @@ __global__ void __launch_bounds__(kFtThreads, 2) fxp_tc_linear_kernel(const __gr
           if (wval[i]) {
             *reinterpret_cast<uint32_t*>(Ah + loff[i] + roff) = hi;
             *reinterpret_cast<uint32_t*>(Al + loff[i] + roff) = lo;
+          }
+          if constexpr (MODE == LIN_BPROJ && VEC4) {
+            // the GLU kernel of the same block needs u again (D u, fxpmodel.py:771-776): 2 bytes per element from here are
+            // cheaper than re-running the BatchNorm chain there
+            if (utile && 128 * i + 4 * lane < p.Kfull && rb + q < rv)
+              *reinterpret_cast<uint2*>(utile + (uint32_t)(rb + q) * (uint32_t)p.Kfull + 128 * i) =
+                  make_uint2(__byte_perm(b[0], b[1], 0x5410), __byte_perm(b[2], b[3], 0x5410));
           }
         }
         if (tail && lane == 0) {
@@ -602,11 +610,22 @@ __global__ void __launch_bounds__(kFgThreads, 1) fxp_tc_glu_kernel(const __grid_
     const int* xtile = a.X + (size_t)row0 * H;
     const int rlim = (int)min((long long)kTcRows, last_row - row0);
     int xin[PB][HJ];
+    unsigned short uin[PB][HJ];
+    if (a.U16) {                                                // u from the B projection (2 bytes per element)
+      const unsigned short* utile = a.U16 + (size_t)row0 * H;
 #pragma unroll
-    for (int q = 0; q < PB; ++q) {
-      const int* xr = xtile + (size_t)min(warp * PB + q, rlim) * H;
+      for (int q = 0; q < PB; ++q) {
+        const unsigned short* ur = utile + (size_t)min(warp * PB + q, rlim) * H;
 #pragma unroll
-      for (int j = 0; j < HJ; ++j) xin[q][j] = xr[lane + 32 * j];
+        for (int j = 0; j < HJ; ++j) uin[q][j] = ur[lane + 32 * j];
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < PB; ++q) {
+        const int* xr = xtile + (size_t)min(warp * PB + q, rlim) * H;
+#pragma unroll
+        for (int j = 0; j < HJ; ++j) { xin[q][j] = xr[lane + 32 * j]; uin[q][j] = 0; }
+      }
     }
     mbar_wait(&bar, phase);
     phase ^= 1;
@@ -655,7 +674,7 @@ __global__ void __launch_bounds__(kFgThreads, 1) fxp_tc_glu_kernel(const __grid_
           unsigned short* trow = reinterpret_cast<unsigned short*>(T + (size_t)r * ldT);
 #pragma unroll
           for (int j = 0; j < HJ; ++j) {
-            const int u = bn_to_u(bn_apply_v(xin[q][j], mm[j], iv[j], sc[j], bi[j], a.c, pl, 4), pl);
+            const int u = a.U16 ? (int)(short)uin[q][j] : bn_to_u(bn_apply_v(xin[q][j], mm[j], iv[j], sc[j], bi[j], a.c, pl, 4), pl);
             const int du = sat_lh(fx_mulw(dd[j], u) >> rs_D, ylo, yhi);                        // fxpmodel.py:771-776
             const int y = sat_lh(fx_addw(tin[q][j], du), ylo, yhi);                            // :778-783
             const int x1 = max(y, 0);                                                          // fxp_relu :1125
@@ -677,6 +696,14 @@ __global__ void __launch_bounds__(kFgThreads, 1) fxp_tc_glu_kernel(const __grid_
       tc_issue8(tcol, Ph, Wo, kFgK2, H, H, true);
       tc_issue8(tcol + 256, Pl, Wo, kFgK2, H, H, false);
       tc_commit(&bar);
+    }
+    if (a.U16) {                                                // the skip rows (maxima of the residual add) travel during MMA 2 / E2
+#pragma unroll
+      for (int q = 0; q < PB; ++q) {
+        const int* xr = xtile + (size_t)min(warp * PB + q, rlim) * H;
+#pragma unroll
+        for (int j = 0; j < HJ; ++j) xin[q][j] = xr[lane + 32 * j];
+      }
     }
     mbar_wait(&bar, phase);
     phase ^= 1;

@@ -28,6 +28,7 @@ struct FxpTcLinArgs {
   BnChain c; unsigned* fm; int* ex; int* status;         // BPROJ: BatchNorm chain of the block
   const int* next_mmean; int next_e_mean; unsigned* next_fm; int out_exp;   // ENC: maxima for block 0's first BatchNorm stage
   unsigned* next_cmax; unsigned* next_cmin;              // ENC: or per-column extremes of the output (fxp_bn_derive_kernel)
+  unsigned short* U16;                                   // BPROJ (16-byte aligned rows): also store the 16-bit mixer input u [rows][K]
   int dec_inp_bits, dec_inp_exp, dec_w_exp, dec_out_exp; // DEC: dynamic input exponent against the static FxpDense config
 };
 
@@ -48,6 +49,7 @@ struct FxpTcGluDev {
 struct FxpTcGluArgs {
   int* XS; const int* X; int* G; long long rows;
   int relu_in;                     // the scan left fxp_relu of the states to this kernel (bad tiles are written back ReLU-ed)
+  const unsigned short* U16;       // the mixer input u as 16-bit payloads [rows][H], written by the B projection (else recomputed)
   BnChain c; unsigned* fm; int* ex; int* status;
   const int* D; int rs_cre, rs_cim, rs_D, y_bits, conj;
   int o_in_change, y_exp, o_inp_bits, o_inp_exp, o_rs, o_out_bits, o_out_exp; const int* o_bias_aligned;
