@@ -140,6 +140,15 @@ __device__ __forceinline__ int bn_apply(int v, int k, const BnChain& c, const Bn
   return bn_apply_v(v, c.mmean[k], upto >= 2 ? c.inv[k] : 0, (upto >= 3 && c.has_scale) ? c.scale[k] : 0,
                     (upto >= 4 && c.has_bias) ? c.bias[k] : 0, c, pl, upto);
 }
+// the chain with the per-column operands of the two adds already aligned (sc_apply(param, f.b), once per column and launch)
+__device__ __forceinline__ int bn_apply_pre(int v, int mm_al, int inv, int sc, int bi_al, const BnChain& c, const BnPlan& pl) {
+  const BnFast& f = pl.f;
+  v = sc_apply(fx_addw(sc_apply(v, f.s1.a), mm_al), f.s1.post);
+  v = min(max(fx_mulw(v, inv) >> f.rs2, f.lo2), f.hi2);
+  if (c.has_scale) v = min(max(fx_mulw(v, sc) >> f.rs3, f.lo3), f.hi3);
+  if (c.has_bias) v = sc_apply(fx_addw(sc_apply(v, f.s4.a), bi_al), f.s4.post);
+  return v;
+}
 // u = change_cfg(BatchNorm(x)) to the mixer-input format: the whole chain + the final format change
 __device__ __forceinline__ int bn_to_u(int v, const BnPlan& pl) { return sc_apply(v, pl.f.u); }
 

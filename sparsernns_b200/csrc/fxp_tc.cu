@@ -125,6 +125,15 @@ __global__ void __launch_bounds__(kFtThreads, 2) fxp_tc_linear_kernel(const __gr
   float m0 = 0.f, m1 = 0.f;
   uint32_t phase = 0;
   __syncthreads();
+  if (MODE == LIN_BPROJ) {                                    // the plan is in shared memory now: align the add operands once
+#pragma unroll
+    for (int i = 0; i < KV; ++i)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        mm[i][e] = sc_apply(mm[i][e], pl.f.s1.b);
+        bi[i][e] = sc_apply(bi[i][e], pl.f.s4.b);
+      }
+  }
   const int change = MODE == LIN_DEC ? dyn[0] : 0, e_dyn = MODE == LIN_DEC ? dyn[1] : 0;
   const int rs0 = MODE == LIN_DEC ? dyn[2] : a.rshift0, rs1 = MODE == LIN_DEC ? dyn[2] : a.rshift1;
   // the conversion of one raw 32-bit word (float or int32 payload) of input column (i, e) to the 16-bit matmul operand
@@ -133,7 +142,7 @@ __global__ void __launch_bounds__(kFtThreads, 2) fxp_tc_linear_kernel(const __gr
       if (a.x_is_float) return fx_sat(__float2int_rd(__uint_as_float(raw) * in_sc), a.in_bits);   // fxp_from_fp FLOOR
       return (int)raw;
     } else if (MODE == LIN_BPROJ) {
-      int v = bn_apply_v((int)raw, mm[i][e], iv[i][e], sc[i][e], bi[i][e], a.c, pl, 4);
+      int v = bn_apply_pre((int)raw, mm[i][e], iv[i][e], sc[i][e], bi[i][e], a.c, pl);
       return bn_to_u(v, pl);             // fxpmodel.py:620-624
     } else {
       return change ? fx_change_cfg((int)raw, 16, e_dyn, a.dec_inp_bits, a.dec_inp_exp, S5_ROUND_FLOOR) : (int)raw;
