@@ -142,6 +142,12 @@ __device__ __forceinline__ int mul_chk(int a, int b, int rs, int lo, int hi, int
 __global__ void __launch_bounds__(1024) fxp_bn_derive_kernel(BnDeriveParams p) {
   __shared__ BnPlan pl;
   __shared__ float red[32];
+  // the maxima and the input exponent are staged in shared memory: thread 0 plans from there (four plans per launch) and the
+  // global state block is written once at the end - no global round trip between the stages
+  __shared__ unsigned fml[kStateStride];
+  __shared__ int exl[kStateStride];
+  if (threadIdx.x < kStateStride) { fml[threadIdx.x] = 0u; exl[threadIdx.x] = threadIdx.x == E_IN ? p.ex[E_IN] : 0; }
+  __syncthreads();
   const int k = threadIdx.x;
   const bool act = k < p.H;
   const BnChain& c = p.c;
@@ -153,15 +159,15 @@ __global__ void __launch_bounds__(1024) fxp_bn_derive_kernel(BnDeriveParams p) {
     mm = c.mmean[k]; iv = c.inv[k];
     scl = c.has_scale ? c.scale[k] : 0; bia = c.has_bias ? c.bias[k] : 0;
   }
-  const int e_in = p.ex[E_IN];
+  const int e_in = exl[E_IN];
   {  // maxima of the first add: |x + (-mean)| and |x|
     const float s = exp2f((float)-e_in), g = __int2float_rn(mm) * exp2f((float)-c.e_mean);
     const float fl = __int2float_rn(lo) * s, fh = __int2float_rn(hi) * s;
     const float mS = block_allmax(act ? fmaxf(fabsf(fl + g), fabsf(fh + g)) : 0.f, red);
     const float mA = block_allmax(act ? fmaxf(fabsf(fl), fabsf(fh)) : 0.f, red);
     if (k == 0) {
-      p.fm[M_S1] = __float_as_uint(mS); p.fm[M_A1] = __float_as_uint(mA);
-      bn_make_plan(pl, c, p.fm, p.ex, 1);
+      fml[M_S1] = __float_as_uint(mS); fml[M_A1] = __float_as_uint(mA);
+      bn_make_plan(pl, c, fml, exl, 1);
     }
     __syncthreads();
   }
@@ -172,8 +178,8 @@ __global__ void __launch_bounds__(1024) fxp_bn_derive_kernel(BnDeriveParams p) {
     const float s = exp2f((float)-pl.e1), g = __int2float_rn(iv) * exp2f((float)-c.e_inv);
     const float m = block_allmax(act ? fmaxf(fabsf(__int2float_rn(lo) * s * g), fabsf(__int2float_rn(hi) * s * g)) : 0.f, red);
     if (k == 0) {
-      p.fm[M_2] = __float_as_uint(m);
-      bn_make_plan(pl, c, p.fm, p.ex, 2);
+      fml[M_2] = __float_as_uint(m);
+      bn_make_plan(pl, c, fml, exl, 2);
     }
     __syncthreads();
   }
@@ -186,8 +192,8 @@ __global__ void __launch_bounds__(1024) fxp_bn_derive_kernel(BnDeriveParams p) {
     const float s = exp2f((float)-pl.e2), g = __int2float_rn(scl) * exp2f((float)-c.e_scale);
     const float m = block_allmax(act ? fmaxf(fabsf(__int2float_rn(lo) * s * g), fabsf(__int2float_rn(hi) * s * g)) : 0.f, red);
     if (k == 0) {
-      p.fm[M_3] = __float_as_uint(m);
-      bn_make_plan(pl, c, p.fm, p.ex, 3);
+      fml[M_3] = __float_as_uint(m);
+      bn_make_plan(pl, c, fml, exl, 3);
     }
     __syncthreads();
     bad |= pl.bad;
@@ -200,14 +206,16 @@ __global__ void __launch_bounds__(1024) fxp_bn_derive_kernel(BnDeriveParams p) {
     const float mS = block_allmax(act ? fmaxf(fabsf(fl + g), fabsf(fh + g)) : 0.f, red);
     const float mA = block_allmax(act ? fmaxf(fabsf(fl), fabsf(fh)) : 0.f, red);
     if (k == 0) {
-      p.fm[M_S4] = __float_as_uint(mS); p.fm[M_A4] = __float_as_uint(mA);
-      bn_make_plan(pl, c, p.fm, p.ex, 4);
+      fml[M_S4] = __float_as_uint(mS); fml[M_A4] = __float_as_uint(mA);
+      bn_make_plan(pl, c, fml, exl, 4);
     }
     __syncthreads();
     // the second add is only range-checked here; its result is not needed for a maximum
     if (act) { (void)add_fast_chk(lo, bia, pl.f.s4, wrap); (void)add_fast_chk(hi, bia, pl.f.s4, wrap); }
   }
   wrap = __syncthreads_or(act ? wrap : p.force_slow);
+  if (k < kStateStride && k != M_SR && k != M_G) p.fm[k] = fml[k];   // M_SR / M_G belong to the GLU kernel of this block
+  __syncthreads();
   if (wrap) {
     // plain passes over the whole tensor by this one CTA (the arithmetic of fxp_bn_reduce_kernel)
     for (int upto = 1; upto <= 3; ++upto) {
@@ -867,7 +875,7 @@ static int fxp_run(const FxpRun& r, const void* x, bool x_is_float, int upto_lay
     if (cs) {
       BnDeriveParams p{a, n, d.H, c, r.fm(li), r.ex(li), r.status(), r.cmax(li), r.cmin(li), m->bn_force_slow ? 1 : 0};
       ProfScope prof(S5_K_FXP_BN, r.st);
-      fxp_bn_derive_kernel<<<1, 1024, 0, r.st>>>(p);
+      fxp_bn_derive_kernel<<<1, (d.H <= 256 && !m->bn_force_slow) ? 256 : 1024, 0, r.st>>>(p);
       S5_LAUNCH_CHECK();
     } else {
       if ((rc = reduce(1, 2))) return rc;
