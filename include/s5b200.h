@@ -241,7 +241,8 @@ size_t s5b200_fxp_model_workspace_bytes(const s5_fxp_model* m, int B, int L);
  * (negative shift in fxp_mul, fxparray.py:619-621). */
 int s5b200_fxp_model_forward(const s5_fxp_model* m, const float* x, int32_t* y_int, float* y_float, int B,
                              int L, void* workspace, size_t workspace_bytes, int32_t* status_dev, void* stream);
-/* Same, taking an already quantised int32 input (model(fxp_x), fxprun.py:76). */
+/* Same, taking an already quantised int32 input (model(fxp_x), fxprun.py:76).  x_int must hold valid payloads of the encoder's
+ * input format (inp_bits wide, i.e. what fxp_from_fp produces): the dense-tile encoder splits them into two byte planes. */
 int s5b200_fxp_model_forward_int(const s5_fxp_model* m, const int32_t* x_int, int32_t* y_int, float* y_float,
                                  int B, int L, void* workspace, size_t workspace_bytes, int32_t* status_dev,
                                  void* stream);
