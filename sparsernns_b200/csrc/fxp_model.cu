@@ -20,6 +20,7 @@
 
 #include "fxp_chain.cuh"
 #include "fxp_tc.cuh"
+#include "tc_model.cuh"
 #include "proj.cuh"
 #include "scan.cuh"
 
@@ -770,6 +771,7 @@ struct s5_fxp_model {
   // S5B200_FXP_BN_DERIVE=0: the three BatchNorm-reduce passes per block instead of fxp_bn_derive_kernel;
   // S5B200_FXP_BN_FORCE_SLOW=1 (testing): the derive kernel takes its whole-tensor fallback
   bool bn_derive = true, bn_force_slow = false;
+  bool enc_ws = true;        // S5B200_FXP_ENC_WS=0: the generic dense-tile kernel for the encoder instead of the warp-specialised one
   bool u16 = true;           // S5B200_FXP_U16=0: the dense-tile GLU kernel re-runs the BatchNorm chain instead of reading u from the B projection
   bool relu_in_glu = true;   // S5B200_FXP_RELU_IN_GLU=0: the scan applies fxp_relu itself even when the dense-tile GLU follows
   bool use_tc(long long rows) const { return tc_on && rows >= tc_min_rows; }
@@ -857,7 +859,14 @@ static int fxp_run(const FxpRun& r, const void* x, bool x_is_float, int upto_lay
     S5_CUDA(cudaMemcpyAsync(r.ex(0) + E_IN, &m->enc.q.out_exp, sizeof(int), cudaMemcpyHostToDevice, r.st));
     const bool tc = m->use_tc(rows) && m->enc.tc.ok && q.inp_bits <= 16 && p.round_mode == S5_ROUND_FLOOR;
     if (tc && cs) { p.next_fm = nullptr; p.next_cmax = r.cmax(0); p.next_cmin = r.cmin(0); }
-    if ((rc = tc ? launch_fxp_linear_tc(p, m->enc.tc, r.st, S5_K_FXP_ENC) : launch_fxp_linear(p, r.st, S5_K_FXP_ENC))) return rc;
+    // the warp-specialised encoder (TMA input ring; the column extremes fall out of its lane = column epilogue) where the
+    // shape is covered and the maxima come from the extremes; else the generic dense-tile kernel / the CUDA cores
+    rc = S5_E_UNSUPPORTED;
+    if (tc && cs && m->enc_ws)
+      rc = tc_enc_fx_launch(m->enc.tc.W8[1], m->enc.tc.Kfull, m->enc.tc.Kp[1], m->enc.tc.Np, m->enc.tc.Nfull, m->enc.tc.KV, x, x_is_float ? 1 : 0,
+                            q.inp_bits, q.inp_exp, a, rows, p.rshift0, q.out_bits, m->enc.bias_aligned, 1, r.cmax(0), r.cmin(0), r.st);
+    if (rc == S5_E_UNSUPPORTED) rc = tc ? launch_fxp_linear_tc(p, m->enc.tc, r.st, S5_K_FXP_ENC) : launch_fxp_linear(p, r.st, S5_K_FXP_ENC);
+    if (rc) return rc;
     sync_maxima();
   }
   for (int li = 0; li <= upto_layer; ++li) {
@@ -1022,6 +1031,7 @@ extern "C" int s5b200_fxp_model_create(const s5_fxp_model_desc* d, s5_fxp_model*
   if (const char* e = getenv("S5B200_FXP_BN_DERIVE")) m->bn_derive = atoi(e) != 0;
   if (const char* e = getenv("S5B200_FXP_RELU_IN_GLU")) m->relu_in_glu = atoi(e) != 0;
   if (const char* e = getenv("S5B200_FXP_U16")) m->u16 = atoi(e) != 0;
+  if (const char* e = getenv("S5B200_FXP_ENC_WS")) m->enc_ws = atoi(e) != 0;
   if (const char* e = getenv("S5B200_FXP_BN_FORCE_SLOW")) m->bn_force_slow = atoi(e) != 0;
   const int H = d->H, P = d->P, dense = d->use_sparse ? 0 : 1;
   int rc = S5_OK;

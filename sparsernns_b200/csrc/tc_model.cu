@@ -18,6 +18,7 @@
 #include <mutex>
 #include <vector>
 
+#include "fxp_chain.cuh"
 #include "proj.cuh"
 #include "tc.cuh"
 #include <cuda_bf16.h>
@@ -69,6 +70,10 @@ struct TcLinParams {
   const float* col_scale;   // [Nfull] s_in * s_w[n]
   const float* bias;        // [Nfull] fake-quantised bias, nullable
   float out_scale0, out_scale1, out_inv0, out_inv1, out_qmin, out_qmax; int relu;
+  // FX instantiation of tc_enc2_kernel (integer encoder of the fixed-point model, fxpmodel.py:331-366, fxprun.py:69-75): X holds
+  // floats (quantised with FLOOR to fx_in_bits at 2^fx_in_exp) or int32 payloads, Y int32 payloads; the epilogue is
+  // shift, saturate, bias, saturate, ReLU, and it leaves the per-column extremes of the output behind (fxp_bn_derive_kernel)
+  int fx_x_is_float, fx_in_bits, fx_in_exp, fx_rs, fx_out_bits; const int* fx_bias; unsigned* fx_cmax; unsigned* fx_cmin;
 };
 
 // clip(round_half_even(x / s)) with 1/s passed in: exact for the power-of-two scales of the static recipe
@@ -550,7 +555,7 @@ constexpr int kEnc2Epi = 8;        // epilogue warps: TMEM lane quadrant w % 4, 
 constexpr int kEnc2Threads = 32 * (kEnc2Epi + 2 + kEnc2Conv);
 constexpr int kEnc2SubPerTile = kEnc2Rows / kEnc2Sub;
 
-template <int KV, int NRING>
+template <int KV, int NRING, bool FX = false>
 __global__ void __launch_bounds__(kEnc2Threads, 1) tc_enc2_kernel(TcLinParams p) {
   constexpr int nring = NRING;                                // ring slots: compile-time, the slot / phase arithmetic sits in every loop
   extern __shared__ __align__(128) unsigned char smem[];
@@ -657,6 +662,12 @@ __global__ void __launch_bounds__(kEnc2Threads, 1) tc_enc2_kernel(TcLinParams p)
     }
     const bool tail = Kf > 128 * KV;
     const float inv = p.in_inv, qmin = p.in_qmin, qmax = p.in_qmax;
+    // FX: fxp_from_fp FLOOR (fxprun.py:69-75) = floor(x 2^e), saturated - or the int32 payload as it is
+    const float fx_sc = FX ? exp2f((float)p.fx_in_exp) : 0.f;
+    auto code = [&](float x) -> uint32_t {
+      if constexpr (FX) return (uint32_t)(p.fx_x_is_float ? fx_sat(__float2int_rd(x * fx_sc), p.fx_in_bits) : __float_as_int(x));
+      else return quant_bits(x, inv, qmin, qmax);
+    };
     for (int s = 0; s < nsub; ++s) {
       const int t = s / kEnc2SubPerTile, ts = s - t * kEnc2SubPerTile, buf = t & 1, slot = s % nring;
       if (ts == 0 && t >= 2) E2_WAIT(1, mbar_wait(&mma_done[buf], (uint32_t)((t >> 1) - 1) & 1u));   // the MMAs of tile t - 2 have read these planes
@@ -693,13 +704,13 @@ __global__ void __launch_bounds__(kEnc2Threads, 1) tc_enc2_kernel(TcLinParams p)
         for (int i = 0; i < KV; ++i) {
           uint32_t b[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) b[e] = quant_bits(xv[q][i][e], inv, qmin, qmax);
+          for (int e = 0; e < 4; ++e) b[e] = code(xv[q][i][e]);
           uint32_t lo, hi;
           split_planes(b[0], b[1], b[2], b[3], lo, hi);
           *reinterpret_cast<uint32_t*>(Ah + loff[i] + roff) = hi;
           *reinterpret_cast<uint32_t*>(Al + loff[i] + roff) = lo ^ 0x80808080u;
         }
-        const uint32_t bt = quant_bits(xt[q], inv, qmin, qmax);
+        const uint32_t bt = code(xt[q]);
         if (tail && lane == 0) {
           *reinterpret_cast<uint32_t*>(Ah + (size_t)(8 * KV) * lbo + roff) = (bt >> 8) & 0xFFu;
           *reinterpret_cast<uint32_t*>(Al + (size_t)(8 * KV) * lbo + roff) = (bt & 0xFFu) ^ 0x80808080u;
@@ -729,8 +740,8 @@ __global__ void __launch_bounds__(kEnc2Threads, 1) tc_enc2_kernel(TcLinParams p)
       ncol[blk] = blk < nblk && n < p.Nfull;
       const float oinv = (n & 1) ? p.out_inv1 : p.out_inv0;
       os[blk] = (n & 1) ? p.out_scale1 : p.out_scale0;
-      cs[blk] = ncol[blk] ? p.col_scale[n] * oinv : 0.f;
-      cb[blk] = ncol[blk] && p.bias ? p.bias[n] * oinv : 0.f;
+      cs[blk] = (!FX && ncol[blk]) ? p.col_scale[n] * oinv : 0.f;
+      cb[blk] = (!FX && ncol[blk] && p.bias) ? p.bias[n] * oinv : 0.f;
       int c = 0;
       if (ncol[blk] && n < Np) {
         const int4* wr = reinterpret_cast<const int4*>(p.W8 + (size_t)n * Kp);
@@ -740,6 +751,12 @@ __global__ void __launch_bounds__(kEnc2Threads, 1) tc_enc2_kernel(TcLinParams p)
         }
       }
       corr[blk] = 128 * c;
+    }
+    int fbias[2] = {0, 0}, cmx[2] = {INT_MIN, INT_MIN}, cmn[2] = {INT_MAX, INT_MAX};
+    const int fhi = (FX && p.fx_out_bits < 32) ? (1 << (p.fx_out_bits - 1)) - 1 : INT_MAX, flo = -fhi - 1;
+    if constexpr (FX) {
+#pragma unroll
+      for (int blk = 0; blk < 2; ++blk) fbias[blk] = (ncol[blk] && p.fx_bias) ? p.fx_bias[128 * blk + 32 * quad + lane] : 0;
     }
     for (int t = 0; t < ntiles; ++t) {
       const int buf = t & 1;
@@ -758,9 +775,21 @@ __global__ void __launch_bounds__(kEnc2Threads, 1) tc_enc2_kernel(TcLinParams p)
           tc_wait_ld();
           // all 16 values first (independent chains), then the stores: a predicate per element would serialise the chains
           float o[16];
+          if constexpr (FX) {
+            // fxp_matmul + FxpDense bias + fxp_relu (fxparray.py:640-678, fxpmodel.py:352-364, :1262-1266) on the exact int32 sum
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            o[j] = round_clip(fmaf(__int2float_rn((int)vh[j] * 256 + (int)vl[j] + corr[blk]), cs[blk], cb[blk]), oqmin, oqmax) * os[blk];
+            for (int j = 0; j < 16; ++j) {
+              int v = min(max((int)(vh[j] * 256u + vl[j] + (uint32_t)corr[blk]) >> p.fx_rs, flo), fhi);
+              if (p.fx_bias) v = min(max(fx_addw(v, fbias[blk]), flo), fhi);
+              if (p.relu) v = max(v, 0);
+              if (c0 + j < rv) { cmx[blk] = max(cmx[blk], v); cmn[blk] = min(cmn[blk], v); }
+              o[j] = __int_as_float(v);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              o[j] = round_clip(fmaf(__int2float_rn((int)vh[j] * 256 + (int)vl[j] + corr[blk]), cs[blk], cb[blk]), oqmin, oqmax) * os[blk];
+          }
           float* q = p.Y + (size_t)(row0 + c0) * ystride + 128 * blk + 32 * quad + lane;
           if (ncol[blk]) {
             if (c0 + 16 <= rv) {
@@ -777,6 +806,16 @@ __global__ void __launch_bounds__(kEnc2Threads, 1) tc_enc2_kernel(TcLinParams p)
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_free[buf]);
+    }
+    if constexpr (FX) {                                       // per-column extremes: a lane owns one column per block
+      if (p.fx_cmax) {
+#pragma unroll
+        for (int blk = 0; blk < 2; ++blk)
+          if (ncol[blk] && cmx[blk] >= cmn[blk]) {
+            atomicMax(p.fx_cmax + 128 * blk + 32 * quad + lane, ord_enc(cmx[blk]));
+            atomicMax(p.fx_cmin + 128 * blk + 32 * quad + lane, ord_enc(~cmn[blk]));
+          }
+      }
     }
   }
 #ifdef S5_ENC2_TRACE
@@ -2541,6 +2580,36 @@ int tc_linear_launch(const TcLinearDev& d, const float* X, float* Y, long long r
   return bn ? tc_linear_go<false, 2, true, false>(p, kclass, st) : tc_linear_go<false, 2, false, false>(p, kclass, st);
 }
 
+
+// Integer encoder of the fixed-point model on the warp-specialised kernel (FX instantiation of tc_enc2_kernel).  W8: [Np][Kp] int8
+// payloads in the lane-interleaved K order (FxpTcLinearDev::W8[1]).  S5_E_UNSUPPORTED: shape not covered (the caller falls back).
+int tc_enc_fx_launch(const signed char* W8, int Kfull, int Kp, int Np, int Nfull, int KV, const void* X, int x_is_float, int in_bits, int in_exp,
+                     int* Y, long long rows, int rshift, int out_bits, const int* bias_aligned, int relu, unsigned* cmax, unsigned* cmin,
+                     cudaStream_t st) {
+  if (!(KV == 1 || KV == 2) || !aligned16(X) || !aligned16(Y) || Np > 256 || (Np & 31) || (Nfull & 3) || Nfull > Np || (Kp & 31))
+    return S5_E_UNSUPPORTED;
+  const size_t raw2 = (((size_t)kEnc2Sub * Kfull * 4) + 127) & ~(size_t)127;
+  const int nblk2 = (Np + 127) >> 7;
+  int nring = kEnc2Ring;
+  size_t esm2 = 0;
+  for (; nring >= 2; --nring) {
+    esm2 = (size_t)nblk2 * tc_tile_bytes8(kTcRows, Kp) + 2 * tc_tile_bytes8(2 * kEnc2Rows, Kp) + nring * raw2;
+    if (esm2 + 2048 <= 227 * 1024) break;
+  }
+  if (nring < 2) return S5_E_UNSUPPORTED;
+  TcLinParams p{};
+  p.X = reinterpret_cast<const float*>(X); p.Y = reinterpret_cast<float*>(Y); p.rows = rows;
+  p.Kfull = Kfull; p.Nfull = Nfull; p.Kp = Kp; p.Np = Np; p.x_stride = Kfull; p.y_stride = Nfull; p.W8 = W8; p.relu = relu;
+  p.fx_x_is_float = x_is_float; p.fx_in_bits = in_bits; p.fx_in_exp = in_exp; p.fx_rs = rshift; p.fx_out_bits = out_bits;
+  p.fx_bias = bias_aligned; p.fx_cmax = cmax; p.fx_cmin = cmin;
+  auto kernel = KV == 1 ? (nring == 3 ? tc_enc2_kernel<1, 3, true> : tc_enc2_kernel<1, 2, true>) : (nring == 3 ? tc_enc2_kernel<2, 3, true> : tc_enc2_kernel<2, 2, true>);
+  S5_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esm2));
+  const int grid = (int)std::max<long long>(1, std::min<long long>((rows + 63) / 64, (long long)sm_count()));
+  ProfScope prof(S5_K_FXP_ENC, st);
+  kernel<<<grid, kEnc2Threads, esm2, st>>>(p);
+  S5_LAUNCH_CHECK();
+  return S5_OK;
+}
 
 // ---- C projection + GLU handle
 static size_t tc_glu_smem(int H, int K1, bool scan, bool bpj) {

@@ -3,6 +3,7 @@
 #include <cuda_fp16.h>
 
 #include "common.cuh"
+#include "fxp_chain.cuh"
 
 namespace s5 {
 
@@ -51,6 +52,9 @@ int tc_glu_launch(const TcGluDev& d, const TcGluArgs& a, cudaStream_t st);
 bool tc_glu_scan_ok(const TcGluDev& d);
 int tc_glu_launch_multi(const TcGluDev* const* devs, const TcGluArgs* args, int n, uint32_t* done, size_t done_bytes, cudaStream_t st);
 size_t tc_glu_scan_workspace_bytes(int B, int L, int P);
+int tc_enc_fx_launch(const signed char* W8, int Kfull, int Kp, int Np, int Nfull, int KV, const void* X, int x_is_float, int in_bits, int in_exp,
+                     int* Y, long long rows, int rshift, int out_bits, const int* bias_aligned, int relu, unsigned* cmax, unsigned* cmin,
+                     cudaStream_t st);
 int tc_linear_build(const float* W, int Kfull, int Nfull, float s_in, TcLinearDev* out);
 void tc_linear_free(TcLinearDev* d);
 int tc_linear_launch(const TcLinearDev& d, const float* X, float* Y, long long rows, const float* in_sub, const float* in_mul,
