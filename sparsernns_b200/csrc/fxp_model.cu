@@ -771,6 +771,7 @@ struct s5_fxp_model {
   // S5B200_FXP_BN_DERIVE=0: the three BatchNorm-reduce passes per block instead of fxp_bn_derive_kernel;
   // S5B200_FXP_BN_FORCE_SLOW=1 (testing): the derive kernel takes its whole-tensor fallback
   bool bn_derive = true, bn_force_slow = false;
+  bool dec_ws = true;        // S5B200_FXP_DEC_WS=0: the generic dense-tile kernel for the decoder instead of the warp-specialised one
   bool enc_ws = true;        // S5B200_FXP_ENC_WS=0: the generic dense-tile kernel for the encoder instead of the warp-specialised one
   bool u16 = true;           // S5B200_FXP_U16=0: the dense-tile GLU kernel re-runs the BatchNorm chain instead of reading u from the B projection
   bool relu_in_glu = true;   // S5B200_FXP_RELU_IN_GLU=0: the scan applies fxp_relu itself even when the dense-tile GLU follows
@@ -1003,7 +1004,14 @@ static int fxp_forward_impl(const s5_fxp_model* m, const void* x, bool x_is_floa
   p.ex = r.ex(m->desc.n_layers); p.status = r.status();
   p.dec_inp_bits = q.inp_bits; p.dec_inp_exp = q.inp_exp; p.dec_w_exp = q.w_exp; p.dec_out_exp = q.out_exp;
   const bool tc = m->use_tc(p.rows) && m->dec.tc.ok && q.inp_bits <= 16 && (m->desc.H % 128) != 1 && (m->desc.H & 3) == 0;
-  if ((rc = tc ? launch_fxp_linear_tc(p, m->dec.tc, r.st, S5_K_FXP_DEC) : launch_fxp_linear(p, r.st, S5_K_FXP_DEC))) return rc;
+  // the warp-specialised decoder (TMA input ring, bulk stores of whole half-tiles of both outputs) where the shape is covered
+  rc = S5_E_UNSUPPORTED;
+  if (tc && m->dec_ws && m->dec.tc.xn)
+    rc = tc_dec_fx_launch(m->dec.tc.W8[0], m->dec.tc.WN[0], m->dec.tc.Kfull, m->dec.tc.Kp[0], m->dec.tc.Np, m->dec.tc.Nfull, m->dec.tc.KV, cur,
+                          y_int, y_float, p.rows, r.ex(m->desc.n_layers) + E_IN, q.inp_bits, q.inp_exp, q.w_exp, q.out_exp, q.out_bits,
+                          m->dec.bias_aligned, p.out_scale, r.status(), r.st);
+  if (rc == S5_E_UNSUPPORTED) rc = tc ? launch_fxp_linear_tc(p, m->dec.tc, r.st, S5_K_FXP_DEC) : launch_fxp_linear(p, r.st, S5_K_FXP_DEC);
+  if (rc) return rc;
   if (status_dev) S5_CUDA(cudaMemcpyAsync(status_dev, r.status(), 4 * sizeof(int), cudaMemcpyDeviceToDevice, r.st));
   return S5_OK;
 }
@@ -1032,6 +1040,7 @@ extern "C" int s5b200_fxp_model_create(const s5_fxp_model_desc* d, s5_fxp_model*
   if (const char* e = getenv("S5B200_FXP_RELU_IN_GLU")) m->relu_in_glu = atoi(e) != 0;
   if (const char* e = getenv("S5B200_FXP_U16")) m->u16 = atoi(e) != 0;
   if (const char* e = getenv("S5B200_FXP_ENC_WS")) m->enc_ws = atoi(e) != 0;
+  if (const char* e = getenv("S5B200_FXP_DEC_WS")) m->dec_ws = atoi(e) != 0;
   if (const char* e = getenv("S5B200_FXP_BN_FORCE_SLOW")) m->bn_force_slow = atoi(e) != 0;
   const int H = d->H, P = d->P, dense = d->use_sparse ? 0 : 1;
   int rc = S5_OK;

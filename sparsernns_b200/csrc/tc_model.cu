@@ -74,6 +74,9 @@ struct TcLinParams {
   // floats (quantised with FLOOR to fx_in_bits at 2^fx_in_exp) or int32 payloads, Y int32 payloads; the epilogue is
   // shift, saturate, bias, saturate, ReLU, and it leaves the per-column extremes of the output behind (fxp_bn_derive_kernel)
   int fx_x_is_float, fx_in_bits, fx_in_exp, fx_rs, fx_out_bits; const int* fx_bias; unsigned* fx_cmax; unsigned* fx_cmin;
+  // FX instantiation of tc_dec2_kernel (integer decoder, fxpmodel.py:331-366, :1431-1439): the input exponent is data dependent
+  // (read from *fx_ex_in on the device), Y receives the int32 payloads and fx_Yf their float image (either may be null)
+  float* fx_Yf; float fx_out_scale; const int* fx_ex_in; int fx_dec_inp_bits, fx_dec_inp_exp, fx_dec_w_exp, fx_dec_out_exp; int* fx_status;
 };
 
 // clip(round_half_even(x / s)) with 1/s passed in: exact for the power-of-two scales of the static recipe
@@ -980,8 +983,11 @@ constexpr int kDec2Threads = 32 * (kDec2Epi + 2 + kDec2Conv);
 
 // BN: BatchNorm on the input (B projection).  DIRECT: output rows are line aligned (Nfull = Np, a multiple of 32 floats):
 // no extra column, no shared output tile - the epilogue stores from registers as in tc_enc2_kernel (NOUT is unused).
-template <int KV, int NRING, int NOUT, bool BN, bool DIRECT>
+// FX (without BN, DIRECT): the integer decoder of the fixed-point model - integer converters and epilogue, and TWO outputs (payload
+// and float image), each half-tile of both leaving as its own bulk store (NOUT = 4: one tile's four buffers).
+template <int KV, int NRING, int NOUT, bool BN, bool DIRECT, bool FX = false>
 __global__ void __launch_bounds__(kDec2Threads, 1) tc_dec2_kernel(TcLinParams p) {
+  static_assert(!FX || (!BN && !DIRECT && NOUT == 4), "the integer instantiation is the decoder");
   constexpr int nring = NRING, nout = NOUT;                   // compile-time: the slot / phase arithmetic sits in every loop
   extern __shared__ __align__(128) unsigned char smem[];
   const int Kp = p.Kp, Np = p.Np, Nf = p.Nfull;
@@ -999,7 +1005,18 @@ __global__ void __launch_bounds__(kDec2Threads, 1) tc_dec2_kernel(TcLinParams p)
   __shared__ __align__(8) uint64_t planes_full[2], mma_done[2], tmem_free[2], raw_full[kDec2Ring], raw_free[kDec2Ring];
   __shared__ uint32_t tmem_slot;
   __shared__ int extra_n[2][kDec2Rows];
+  __shared__ ShiftClamp fx_in;                                // FX: change_cfg of the block output to the decoder's input format
+  __shared__ int fx_rs_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (FX && tid == 32) {
+    // FxpDense.forward input check (fxpmodel.py:335-347) with a data-dependent input exponent
+    const int e = *p.fx_ex_in;
+    const bool change = (16 > p.fx_dec_inp_bits) || (e > p.fx_dec_inp_exp);
+    const int rs = (change ? p.fx_dec_inp_exp : e) + p.fx_dec_w_exp - p.fx_dec_out_exp;
+    fx_in = change ? sc_change_cfg(16, e, p.fx_dec_inp_bits, p.fx_dec_inp_exp) : ShiftClamp{0, 0, INT_MIN, INT_MAX};
+    fx_rs_s = rs & 31;
+    if ((rs < 0 || rs > 31 || (change && e - p.fx_dec_inp_exp > 31)) && blockIdx.x == 0) atomicOr(p.fx_status, 1);
+  }
 #ifdef S5_ENC2_TRACE
   long long tw[3] = {0, 0, 0};
   const long long tstart = clock64();
@@ -1125,7 +1142,8 @@ __global__ void __launch_bounds__(kDec2Threads, 1) tc_dec2_kernel(TcLinParams p)
               uint32_t b4[4];
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                if constexpr (BN) b4[e] = quant_bits((xv[e] - bsub[i][e]) * bmul[i][e] + badd[i][e], 1.f, qmin, qmax);
+                if constexpr (FX) b4[e] = (uint32_t)sc_apply(__float_as_int(xv[e]), fx_in);
+                else if constexpr (BN) b4[e] = quant_bits((xv[e] - bsub[i][e]) * bmul[i][e] + badd[i][e], 1.f, qmin, qmax);
                 else b4[e] = quant_bits(xv[e], inv, qmin, qmax);
                 if constexpr (!DIRECT) part += (int)(short)b4[e] * wn[i][e];
               }
@@ -1164,8 +1182,8 @@ __global__ void __launch_bounds__(kDec2Threads, 1) tc_dec2_kernel(TcLinParams p)
       ncol[blk] = blk < nblk && n < Np;
       const float oinv = (n & 1) ? p.out_inv1 : p.out_inv0;
       os[blk] = (n & 1) ? p.out_scale1 : p.out_scale0;
-      cs[blk] = ncol[blk] ? p.col_scale[n] * oinv : 0.f;
-      cb[blk] = ncol[blk] && p.bias ? p.bias[n] * oinv : 0.f;
+      cs[blk] = (!FX && ncol[blk]) ? p.col_scale[n] * oinv : 0.f;
+      cb[blk] = (!FX && ncol[blk] && p.bias) ? p.bias[n] * oinv : 0.f;
       int c = 0;                                              // 128 * sum_k W[n][k]: undoes the lo - 128 of the stacked low plane
       if (ncol[blk]) {
         const int4* wr = reinterpret_cast<const int4*>(p.W8 + (size_t)n * Kp);
@@ -1179,7 +1197,22 @@ __global__ void __launch_bounds__(kDec2Threads, 1) tc_dec2_kernel(TcLinParams p)
     // the extra column (Nf = Np + 1): (s_in s_w / s_out, bias / s_out) of column Nf - 1
     const bool xn = Nf > Np;
     const float xoinv = ((Nf - 1) & 1) ? p.out_inv1 : p.out_inv0, xos = ((Nf - 1) & 1) ? p.out_scale1 : p.out_scale0;
-    const float xcs = xn ? p.col_scale[Nf - 1] * xoinv : 0.f, xcb = xn && p.bias ? p.bias[Nf - 1] * xoinv : 0.f;
+    const float xcs = (!FX && xn) ? p.col_scale[Nf - 1] * xoinv : 0.f, xcb = (!FX && xn && p.bias) ? p.bias[Nf - 1] * xoinv : 0.f;
+    // FX: fxp_matmul + FxpDense bias on the exact int32 sum (fxparray.py:640-678, fxpmodel.py:352-364)
+    const int frs = FX ? fx_rs_s : 0;
+    const int fhi = (FX && p.fx_out_bits < 32) ? (1 << (p.fx_out_bits - 1)) - 1 : INT_MAX, flo = -fhi - 1;
+    int fbias[2] = {0, 0};
+    if constexpr (FX) {
+#pragma unroll
+      for (int blk = 0; blk < 2; ++blk) fbias[blk] = (ncol[blk] && p.fx_bias) ? p.fx_bias[128 * blk + 32 * quad + lane] : 0;
+    }
+    const int fxbias = (FX && xn && p.fx_bias) ? p.fx_bias[Nf - 1] : 0;
+    auto fx_out = [&](int acc, int bias) -> int {
+      int v = min(max(acc >> frs, flo), fhi);
+      if (p.fx_bias) v = min(max(fx_addw(v, bias), flo), fhi);
+      return v;
+    };
+    const size_t half_elems = (size_t)kDec2Sub * Nf;
     for (int t = 0; t < ntiles; ++t) {
       const int buf = t & 1;
       const long long row0 = rb + (long long)t * kDec2Rows;
@@ -1220,11 +1253,11 @@ __global__ void __launch_bounds__(kDec2Threads, 1) tc_dec2_kernel(TcLinParams p)
         continue;
       }
       if (tid == 0) {                                         // three buffers: the second half of the previous tile may still be leaving
-        if (nout >= 3) bulk_wait_read1(); else bulk_wait_read0();
+        if (nout >= 3 && !FX) bulk_wait_read1(); else bulk_wait_read0();   // FX: the four buffers hold one tile (2 halves x 2 outputs)
       }
       asm volatile("bar.sync 2, %0;" ::"r"(32 * kDec2Epi) : "memory");
       const int c0 = 16 * rq, hh = rq >> 1;                   // rows c0 .. c0 + 15 of the tile lie in half-tile 2 t + hh
-      float* outT = outT0 + (size_t)((2 * t + hh) % nout) * kDec2Sub * Nf;
+      float* outT = outT0 + (size_t)(FX ? 2 * hh : (2 * t + hh) % nout) * half_elems;   // FX: payload buffer; its float image follows it
       if (c0 < rv) {
 #pragma unroll
         for (int blk = 0; blk < 2; ++blk) {
@@ -1236,13 +1269,30 @@ __global__ void __launch_bounds__(kDec2Threads, 1) tc_dec2_kernel(TcLinParams p)
           tc_wait_ld();
           float* q = outT + (size_t)(c0 - kDec2Sub * hh) * Nf + 128 * blk + 32 * quad + lane;   // lanes along columns: conflict-free
           if (ncol[blk]) {
+            if constexpr (FX) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-              q[(size_t)j * Nf] = round_clip(fmaf(__int2float_rn((int)vh[j] * 256 + (int)vl[j] + corr[blk]), cs[blk], cb[blk]), oqmin, oqmax) * os[blk];
+              for (int j = 0; j < 16; ++j) {
+                const int v = fx_out((int)(vh[j] * 256u + vl[j] + (uint32_t)corr[blk]), fbias[blk]);
+                q[(size_t)j * Nf] = __int_as_float(v);
+                q[half_elems + (size_t)j * Nf] = __int2float_rn(v) * p.fx_out_scale;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                q[(size_t)j * Nf] = round_clip(fmaf(__int2float_rn((int)vh[j] * 256 + (int)vl[j] + corr[blk]), cs[blk], cb[blk]), oqmin, oqmax) * os[blk];
+            }
           }
         }
-        if (xn && quad == 0 && lane < 16)
-          outT[(size_t)(c0 - kDec2Sub * hh + lane) * Nf + Nf - 1] = round_clip(fmaf(__int2float_rn(extra_n[buf][c0 + lane]), xcs, xcb), oqmin, oqmax) * xos;
+        if (xn && quad == 0 && lane < 16) {
+          float* qx = outT + (size_t)(c0 - kDec2Sub * hh + lane) * Nf + Nf - 1;
+          if constexpr (FX) {
+            const int v = fx_out(extra_n[buf][c0 + lane], fxbias);
+            qx[0] = __int_as_float(v);
+            qx[half_elems] = __int2float_rn(v) * p.fx_out_scale;
+          } else {
+            qx[0] = round_clip(fmaf(__int2float_rn(extra_n[buf][c0 + lane]), xcs, xcb), oqmin, oqmax) * xos;
+          }
+        }
       }
       fence_proxy_async_smem();
       tc_fence_before();
@@ -1254,14 +1304,22 @@ __global__ void __launch_bounds__(kDec2Threads, 1) tc_dec2_kernel(TcLinParams p)
       if (tid == 0) {
         for (int h2 = 0; h2 < 2; ++h2) {
           const int nr = min(kDec2Sub, rv4 - kDec2Sub * h2);
-          if (nr > 0) bulk_s2g(p.Y + (size_t)(row0 + kDec2Sub * h2) * ystride, outT0 + (size_t)((2 * t + h2) % nout) * kDec2Sub * Nf, (uint32_t)((size_t)nr * Nf * 4));
+          if constexpr (FX) {
+            if (nr > 0 && p.Y) bulk_s2g(p.Y + (size_t)(row0 + kDec2Sub * h2) * ystride, outT0 + (size_t)(2 * h2) * half_elems, (uint32_t)((size_t)nr * Nf * 4));
+            if (nr > 0 && p.fx_Yf) bulk_s2g(p.fx_Yf + (size_t)(row0 + kDec2Sub * h2) * ystride, outT0 + (size_t)(2 * h2 + 1) * half_elems, (uint32_t)((size_t)nr * Nf * 4));
+          } else {
+            if (nr > 0) bulk_s2g(p.Y + (size_t)(row0 + kDec2Sub * h2) * ystride, outT0 + (size_t)((2 * t + h2) % nout) * kDec2Sub * Nf, (uint32_t)((size_t)nr * Nf * 4));
+          }
           bulk_commit();
         }
       }
       if (rv4 != rv) {
         const int h2 = rv4 / kDec2Sub;
-        const float* src = outT0 + (size_t)((2 * t + h2) % nout) * kDec2Sub * Nf + (size_t)(rv4 - kDec2Sub * h2) * Nf;
-        for (int i = tid; i < (rv - rv4) * Nf; i += 32 * kDec2Epi) p.Y[(size_t)(row0 + rv4) * ystride + i] = src[i];
+        const float* src = outT0 + (size_t)(FX ? 2 * h2 : (2 * t + h2) % nout) * half_elems + (size_t)(rv4 - kDec2Sub * h2) * Nf;
+        for (int i = tid; i < (rv - rv4) * Nf; i += 32 * kDec2Epi) {
+          if (!FX || p.Y) p.Y[(size_t)(row0 + rv4) * ystride + i] = src[i];
+          if constexpr (FX) { if (p.fx_Yf) p.fx_Yf[(size_t)(row0 + rv4) * ystride + i] = src[half_elems + i]; }
+        }
         asm volatile("bar.sync 2, %0;" ::"r"(32 * kDec2Epi) : "memory");
       }
     }
@@ -2607,6 +2665,32 @@ int tc_enc_fx_launch(const signed char* W8, int Kfull, int Kp, int Np, int Nfull
   const int grid = (int)std::max<long long>(1, std::min<long long>((rows + 63) / 64, (long long)sm_count()));
   ProfScope prof(S5_K_FXP_ENC, st);
   kernel<<<grid, kEnc2Threads, esm2, st>>>(p);
+  S5_LAUNCH_CHECK();
+  return S5_OK;
+}
+
+// Integer decoder of the fixed-point model on the warp-specialised kernel (FX instantiation of tc_dec2_kernel).  W8 / WN: int8
+// payloads in the natural K order (FxpTcLinearDev::W8[0], WN[0]).  S5_E_UNSUPPORTED: shape not covered (the caller falls back).
+int tc_dec_fx_launch(const signed char* W8, const signed char* WN, int Kfull, int Kp, int Np, int Nfull, int KV, const int* X, int* Y, float* Yf,
+                     long long rows, const int* ex_in, int inp_bits, int inp_exp, int w_exp, int out_exp, int out_bits, const int* bias_aligned,
+                     float out_scale, int* status, cudaStream_t st) {
+  if (!(KV == 1 || KV == 2) || (Kfull & 3) || !aligned16(X) || (Y && !aligned16(Y)) || (Yf && !aligned16(Yf)) || Np > 256 || (Np & 31) ||
+      (Kp & 31) || Nfull != Np + 1)
+    return S5_E_UNSUPPORTED;
+  const size_t fixed = 2 * tc_tile_bytes8(kTcRows, Kp) + 2 * tc_tile_bytes8(2 * kDec2Rows, Kp);
+  const size_t slot = (size_t)kDec2Sub * Kfull * 4, ohalf = (size_t)kDec2Sub * Nfull * 4;
+  const size_t dsm = fixed + 3 * slot + 4 * ohalf;
+  if (dsm + 2048 > 227 * 1024) return S5_E_UNSUPPORTED;
+  TcLinParams p{};
+  p.X = reinterpret_cast<const float*>(X); p.Y = reinterpret_cast<float*>(Y); p.rows = rows;
+  p.Kfull = Kfull; p.Nfull = Nfull; p.Kp = Kp; p.Np = Np; p.x_stride = Kfull; p.y_stride = Nfull; p.W8 = W8; p.WN = WN;
+  p.fx_out_bits = out_bits; p.fx_bias = bias_aligned; p.fx_Yf = Yf; p.fx_out_scale = out_scale; p.fx_ex_in = ex_in;
+  p.fx_dec_inp_bits = inp_bits; p.fx_dec_inp_exp = inp_exp; p.fx_dec_w_exp = w_exp; p.fx_dec_out_exp = out_exp; p.fx_status = status;
+  auto kernel = KV == 1 ? tc_dec2_kernel<1, 3, 4, false, false, true> : tc_dec2_kernel<2, 3, 4, false, false, true>;
+  S5_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
+  const int grid = (int)std::max<long long>(1, std::min<long long>((rows + 63) / 64, (long long)sm_count()));
+  ProfScope prof(S5_K_FXP_DEC, st);
+  kernel<<<grid, kDec2Threads, dsm, st>>>(p);
   S5_LAUNCH_CHECK();
   return S5_OK;
 }

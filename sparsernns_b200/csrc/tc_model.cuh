@@ -55,6 +55,9 @@ size_t tc_glu_scan_workspace_bytes(int B, int L, int P);
 int tc_enc_fx_launch(const signed char* W8, int Kfull, int Kp, int Np, int Nfull, int KV, const void* X, int x_is_float, int in_bits, int in_exp,
                      int* Y, long long rows, int rshift, int out_bits, const int* bias_aligned, int relu, unsigned* cmax, unsigned* cmin,
                      cudaStream_t st);
+int tc_dec_fx_launch(const signed char* W8, const signed char* WN, int Kfull, int Kp, int Np, int Nfull, int KV, const int* X, int* Y, float* Yf,
+                     long long rows, const int* ex_in, int inp_bits, int inp_exp, int w_exp, int out_exp, int out_bits, const int* bias_aligned,
+                     float out_scale, int* status, cudaStream_t st);
 int tc_linear_build(const float* W, int Kfull, int Nfull, float s_in, TcLinearDev* out);
 void tc_linear_free(TcLinearDev* d);
 int tc_linear_launch(const TcLinearDev& d, const float* X, float* Y, long long rows, const float* in_sub, const float* in_mul,
