@@ -699,7 +699,11 @@ __device__ __forceinline__ void tma3d_store(const CUtensorMap* tm, int c0, int c
 #define SPLIT_WAIT(stmt) stmt
 #define SPLIT_TRACE_PRINT
 #endif
+// IL: interleaved (re, im) pairs in one array (the model's layout; tin / tout, box of 64 ints x steps); else planar arrays as at
+// the s5b200_scan_i32 ABI (tin / tout = real parts, tin2 / tout2 = imaginary parts, boxes of 32 ints x steps, two per tile)
+template <bool IL>
 __global__ void __launch_bounds__(192) scan_i32_split_kernel(const __grid_constant__ CUtensorMap tin, const __grid_constant__ CUtensorMap tout,
+                                                             const __grid_constant__ CUtensorMap tin2, const __grid_constant__ CUtensorMap tout2,
                                                              ScanI32Params q, int S, int npost, int nsplit) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t full[kSplitMaxStages], aligned[kSplitMaxStages], scanned[kSplitMaxStages];
@@ -722,7 +726,12 @@ __global__ void __launch_bounds__(192) scan_i32_split_kernel(const __grid_consta
   __syncthreads();
   auto issue_load = [&](int t, int st) {                      // tile t into stage st (= t % S)
     mbar_expect_tx(&full[st], tile_bytes);
-    tma3d_load(smem_raw + (size_t)st * stage_bytes, &tin, 2 * kSplitStates * sub, t * kSplitSteps, b, &full[st]);
+    if (IL) {
+      tma3d_load(smem_raw + (size_t)st * stage_bytes, &tin, 2 * kSplitStates * sub, t * kSplitSteps, b, &full[st]);
+    } else {
+      tma3d_load(smem_raw + (size_t)st * stage_bytes, &tin, kSplitStates * sub, t * kSplitSteps, b, &full[st]);
+      tma3d_load(smem_raw + (size_t)st * stage_bytes + tile_bytes / 2, &tin2, kSplitStates * sub, t * kSplitSteps, b, &full[st]);
+    }
   };
   const bool leader = role == 2 && lane == 0;
   if (leader)
@@ -736,22 +745,31 @@ __global__ void __launch_bounds__(192) scan_i32_split_kernel(const __grid_consta
   uint32_t par = 0;                                           // value, and i % S, i / S cost ~40 instructions per tile and role
   for (int i = 0; i < ntiles; ++i, s = (s + 1 == S ? 0 : s + 1), par ^= (s == 0 ? 1u : 0u)) {
     const int rows = min(kSplitSteps, L - i * kSplitSteps);
-    int2* c2 = reinterpret_cast<int2*>(smem_raw + (size_t)s * stage_bytes) + lane;
-    int2* o2 = reinterpret_cast<int2*>(smem_raw + (size_t)s * stage_bytes + tile_bytes) + lane;
+    int* cbase = reinterpret_cast<int*>(smem_raw + (size_t)s * stage_bytes);       // input tile, then the output tile
+    int* obase = reinterpret_cast<int*>(smem_raw + (size_t)s * stage_bytes + tile_bytes);
+    constexpr int kPlane = kSplitSteps * kSplitStates;        // ints per planar half-tile
+    auto ld2 = [&](const int* base, int t) -> int2 {
+      if (IL) return reinterpret_cast<const int2*>(base)[t * kSplitStates + lane];
+      return make_int2(base[t * kSplitStates + lane], base[kPlane + t * kSplitStates + lane]);
+    };
+    auto st2 = [&](int* base, int t, int2 v) {
+      if (IL) reinterpret_cast<int2*>(base)[t * kSplitStates + lane] = v;
+      else { base[t * kSplitStates + lane] = v.x; base[kPlane + t * kSplitStates + lane] = v.y; }
+    };
     if (role == 0) {
       SPLIT_WAIT(mbar_wait(&full[s], par));
 #pragma unroll
       for (int t0 = 0; t0 < kSplitSteps; t0 += 8) {
         int2 v[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = c2[(t0 + j) * kSplitStates];
+        for (int j = 0; j < 8; ++j) v[j] = ld2(cbase, t0 + j);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           v[j].x = (int)((unsigned)v[j].x << sl_re) >> sr_re;
           v[j].y = (int)((unsigned)v[j].y << sl_im) >> sr_im;
         }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) c2[(t0 + j) * kSplitStates] = v[j];
+        for (int j = 0; j < 8; ++j) st2(cbase, t0 + j, v[j]);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&aligned[s]);
@@ -759,13 +777,13 @@ __global__ void __launch_bounds__(192) scan_i32_split_kernel(const __grid_consta
       SPLIT_WAIT(mbar_wait(&aligned[s], par));
       int vr[kSplitSteps], vi[kSplitSteps];
 #pragma unroll
-      for (int t = 0; t < kSplitSteps; ++t) { const int2 v = c2[t * kSplitStates]; vr[t] = v.x; vi[t] = v.y; }
+      for (int t = 0; t < kSplitSteps; ++t) { const int2 v = ld2(cbase, t); vr[t] = v.x; vi[t] = v.y; }
 #pragma unroll
       for (int t = 0; t < kSplitSteps; ++t) {
         const int nr = (int)((unsigned)(mulw(ar, xr) >> q.eA_re) - (unsigned)(mulw(ai, xi) >> q.eA_re) + (unsigned)vr[t]);
         const int ni = (int)((unsigned)(mulw(ar, xi) >> q.eA_im) + (unsigned)(mulw(ai, xr) >> q.eA_im) + (unsigned)vi[t]);
         xr = nr; xi = ni;
-        o2[t * kSplitStates] = make_int2(nr, ni);
+        st2(obase, t, make_int2(nr, ni));
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&scanned[s]);
@@ -775,7 +793,7 @@ __global__ void __launch_bounds__(192) scan_i32_split_kernel(const __grid_consta
         for (int t0 = 8 * (role - 2); t0 < rows; t0 += 8 * npost) {
           int a[8], c[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) { const int2 v = o2[(t0 + j) * kSplitStates]; a[j] = v.x; c[j] = v.y; }
+          for (int j = 0; j < 8; ++j) { const int2 v = ld2(obase, t0 + j); a[j] = v.x; c[j] = v.y; }
           unsigned big = 0;   // see scan_i32_ws_kernel: only kept values with |v| >= 2^24 change in the float round trip
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -788,13 +806,18 @@ __global__ void __launch_bounds__(192) scan_i32_split_kernel(const __grid_consta
             for (int j = 0; j < 8; ++j) fxp_relu_complex(a[j], c[j]);
           }
 #pragma unroll
-          for (int j = 0; j < 8; ++j) o2[(t0 + j) * kSplitStates] = make_int2(a[j], c[j]);
+          for (int j = 0; j < 8; ++j) st2(obase, t0 + j, make_int2(a[j], c[j]));
         }
       }
       fence_proxy_async_smem();
       SPLIT_WAIT(asm volatile("bar.sync 1, %0;" ::"r"(32 * npost) : "memory"));
       if (leader) {
-        tma3d_store(&tout, 2 * kSplitStates * sub, i * kSplitSteps, b, smem_raw + (size_t)s * stage_bytes + tile_bytes);
+        if (IL) {
+          tma3d_store(&tout, 2 * kSplitStates * sub, i * kSplitSteps, b, obase);
+        } else {
+          tma3d_store(&tout, kSplitStates * sub, i * kSplitSteps, b, obase);
+          tma3d_store(&tout2, kSplitStates * sub, i * kSplitSteps, b, obase + kPlane);
+        }
         bulk_commit();
         if (i >= 1 && i - 1 + S < ntiles) {                    // the store of tile i-1 has released its stage
           SPLIT_WAIT(bulk_wait_read1());
@@ -808,7 +831,7 @@ __global__ void __launch_bounds__(192) scan_i32_split_kernel(const __grid_consta
 }
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (the library links the static runtime only)
-static int make_tmap3d_i32(CUtensorMap* tm, const void* base, int P, int L, long long B) {
+static int make_tmap3d_i32(CUtensorMap* tm, const void* base, int P, int L, long long B, bool interleaved) {
   typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
   static EncodeFn fn = [] {
@@ -818,9 +841,10 @@ static int make_tmap3d_i32(CUtensorMap* tm, const void* base, int P, int L, long
     return reinterpret_cast<EncodeFn>(f);
   }();
   if (!fn) return -1;
-  const cuuint64_t dims[3] = {(cuuint64_t)2 * P, (cuuint64_t)L, (cuuint64_t)B};
-  const cuuint64_t strides[2] = {(cuuint64_t)2 * P * 4, (cuuint64_t)L * 2 * P * 4};
-  const cuuint32_t box[3] = {2 * kSplitStates, kSplitSteps, 1};
+  const cuuint64_t W = interleaved ? 2ull * P : (cuuint64_t)P;   // ints per time step of one array
+  const cuuint64_t dims[3] = {W, (cuuint64_t)L, (cuuint64_t)B};
+  const cuuint64_t strides[2] = {W * 4, (cuuint64_t)L * W * 4};
+  const cuuint32_t box[3] = {(cuuint32_t)(interleaved ? 2 * kSplitStates : kSplitStates), kSplitSteps, 1};
   const cuuint32_t estr[3] = {1, 1, 1};
   const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_INT32, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -834,14 +858,18 @@ int launch_scan_i32(const ScanI32Params& q, bool interleaved, cudaStream_t st) {
   ProfScope prof(S5_K_SCAN_I32, st);
   // fewer clips than SMs: 32 states per CTA (S5B200_SCAN_I32_SPLIT=0: one CTA per clip)
   static const bool split_on = [] { const char* e = getenv("S5B200_SCAN_I32_SPLIT"); return !e || atoi(e) != 0; }();
-  if (split_on && ring_ok && interleaved && q.P % kSplitStates == 0 && q.P > kSplitStates && B < sm_count() && q.L < (1 << 30)) {
-    CUtensorMap tin, tout;
-    if (make_tmap3d_i32(&tin, q.Bu_re, q.P, q.L, B) == 0 && make_tmap3d_i32(&tout, q.xs_re, q.P, q.L, B) == 0) {
+  if (split_on && ring_ok && q.P % kSplitStates == 0 && q.P > kSplitStates && B < sm_count() && q.L < (1 << 30)) {
+    CUtensorMap tin, tout, tin2, tout2;
+    bool ok = make_tmap3d_i32(&tin, q.Bu_re, q.P, q.L, B, interleaved) == 0 && make_tmap3d_i32(&tout, q.xs_re, q.P, q.L, B, interleaved) == 0;
+    if (ok && !interleaved) ok = make_tmap3d_i32(&tin2, q.Bu_im, q.P, q.L, B, false) == 0 && make_tmap3d_i32(&tout2, q.xs_im, q.P, q.L, B, false) == 0;
+    if (ok) {
+      if (interleaved) { tin2 = tin; tout2 = tout; }
       static const int split_stages = [] { const char* e = getenv("S5B200_SCAN_I32_STAGES"); return e ? std::max(3, std::min(kSplitMaxStages, atoi(e))) : (kSplitSteps >= 64 ? 6 : 10); }();
       const int nsplit = q.P / kSplitStates, npost = q.relu ? 4 : 1, stages = split_stages;
       const size_t smem = (size_t)stages * 2 * kSplitSteps * kSplitStates * 8;   // input + output tile per stage
-      S5_CUDA(cudaFuncSetAttribute(scan_i32_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      scan_i32_split_kernel<<<(unsigned)(B * nsplit), 32 * (2 + npost), smem, st>>>(tin, tout, q, stages, npost, nsplit);
+      auto kernel = interleaved ? scan_i32_split_kernel<true> : scan_i32_split_kernel<false>;
+      S5_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      kernel<<<(unsigned)(B * nsplit), 32 * (2 + npost), smem, st>>>(tin, tout, tin2, tout2, q, stages, npost, nsplit);
       S5_LAUNCH_CHECK();
       return S5_OK;
     }
