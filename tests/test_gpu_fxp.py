@@ -334,3 +334,31 @@ def test_fxp_bn_maxima_paths_agree(cuda_device, fxp_case, monkeypatch):
         assert y.exp == y_ref.exp and np.array_equal(y.data.cpu().numpy(), y_ref.data), env
         for k in env:
             monkeypatch.delenv(k)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,L", [(1, 333), (5, 523), (2, 1030), (7, 129)])
+def test_fxp_dense_tile_path_equals_cuda_core_path_on_odd_shapes(cuda_device, fxp_case, monkeypatch, B, L):
+    """Row counts that are no multiple of 4, 32, 64 or 128 and do not split evenly over the CTAs: the dense-tile kernels
+    (balanced row ranges, 32-row TMA slots, half-tile bulk stores, tensor-map boxes that are clipped at the end of a clip)
+    give, bit for bit, what the CUDA-core kernels give - payloads, float image, and every block output."""
+    import torch
+    from sparsernns_b200 import fxpmodel as PF
+
+    zoo, md, q = fxp_case
+    n_layers = zoo["dims"].n_layers
+    rng = np.random.default_rng(B * 1000 + L)
+    x = np.abs(rng.standard_normal((B, L, zoo["x"].shape[-1]))).astype(np.float32) * np.float32(zoo["x"].std() * 3)
+    xt = torch.from_numpy(x).to(cuda_device)
+    outs = {}
+    for name, env in (("cuda_cores", {"S5B200_FXP_TC": "0"}), ("dense_tiles", {"S5B200_FXP_TC": "1", "S5B200_FXP_TC_MIN_ROWS": "1"})):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        pm = PF.FxpRegressionModel(md, q, n_layers)
+        y, mask = pm.forward_float(xt)
+        xq = pm.quantize_input(xt)
+        outs[name] = (y.data.clone(), y.exp, mask.clone(), [pm.tap(xq, i, PF.TAP_OUTPUT) for i in range(n_layers)])
+    a, b = outs["cuda_cores"], outs["dense_tiles"]
+    assert a[1] == b[1] and torch.equal(a[0], b[0]) and torch.equal(a[2], b[2])
+    for ta, tb in zip(a[3], b[3]):
+        assert ta.exp == tb.exp and torch.equal(ta.data, tb.data)
