@@ -17,8 +17,11 @@
 // K is processed in chunks of 16 columns: the chunk's hi / lo planes of X and of W (streamed from L2 by one bulk copy,
 // pre-arranged in the operand layout by the host) sit in one of two buffers; the tensor core accumulates chunk after
 // chunk while the warps stage the next one.  Two CTAs of 8 warps share an SM when the tile has <= 256 output columns.
+#include <cuda.h>   // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
+
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "tc.cuh"
@@ -59,9 +62,21 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, ui
       : "memory");
 }
 
+// logistic function from the two SFU approximations (ex2: 2 ulp, rcp: 1 ulp - a few 1e-7 relative, the flavour's tolerance is 1e-5);
+// exp overflow gives rcp(inf) = 0, underflow gives 1
+__device__ __forceinline__ float f32_sigmoid_fast(float z) {
+  float ex, sg;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(z * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(sg) : "f"(1.0f + ex));
+  return sg;
+}
 __device__ __forceinline__ float f32_gelu_tanh(float x) {     // jax.nn.gelu(approximate=True), layers.py:116-124
-  const float c = 0.7978845608028654f;
-  return x * (0.5f * (1.0f + tanhf(c * (x + 0.044715f * (x * x * x)))));
+  // 0.5 (1 + tanh z) = sigmoid(2 z), z = c (x + 0.044715 x^3): no tanhf (~50 instructions with its branch)
+  const float k0 = -2.0f * 0.7978845608028654f * 1.4426950408889634f, k1 = k0 * 0.044715f;
+  float ex, sg;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(x * fmaf(x * x, k1, k0)));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(sg) : "f"(1.0f + ex));
+  return x * sg;
 }
 
 // VEC4: input rows are 16-byte aligned and K % 4 == 0 - a lane stages four consecutive columns (one 16-byte load, one
@@ -238,7 +253,7 @@ __global__ void __launch_bounds__(kF32Threads, 2) tc_f32_kernel(const __grid_con
             for (int j = 0; j < 16; ++j)
               if (16 * h + j < nr) {
                 const float uu = p.bn_sub ? (u[j] - bs) * bm + ba : u[j];
-                const float y = p.conj_mul * __uint_as_float(acc[16 * h + j]) + dn * uu;
+                const float y = fmaf(p.conj_mul, __uint_as_float(acc[16 * h + j]), dn * uu);
                 p.Y[(size_t)(r0 + 16 * h + j) * p.y_stride + n] = p.act == S5_ACT_RELU ? fmaxf(y, 0.f) : f32_gelu_tanh(y);
               }
           }
@@ -255,8 +270,8 @@ __global__ void __launch_bounds__(kF32Threads, 2) tc_f32_kernel(const __grid_con
 #pragma unroll
             for (int j = 0; j < 16; ++j)
               if (16 * h + j < nr) {
-                const float sg = 1.0f / (1.0f + expf(-(__uint_as_float(acc[16 * h + j]) + bn)));
-                const float y = x1[j] * sg + sk[j];
+                const float sg = f32_sigmoid_fast(__uint_as_float(acc[16 * h + j]) + bn);
+                const float y = fmaf(x1[j], sg, sk[j]);
                 p.Y[(size_t)(r0 + 16 * h + j) * p.y_stride + n] = p.relu ? fmaxf(y, 0.f) : y;
               }
           }
@@ -270,6 +285,357 @@ __global__ void __launch_bounds__(kF32Threads, 2) tc_f32_kernel(const __grid_con
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tc_dealloc(tmem_slot, tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------- warp-specialised form
+// Same product, same operand images, same accumulators and epilogues as tc_f32_kernel - but no phase of a tile waits for
+// another one.  One CTA of 15 warps per SM:
+//   warp 8        TMA producer: the X tile arrives K chunk by K chunk as [128 rows][16 columns] boxes of a 2-D tensor map
+//                 (cp.async.bulk.tensor; columns past K and rows past the end are zero-filled by the copy engine) in a ring
+//                 of raw slots - HBM reads never stop while tiles are converted, multiplied or written
+//   warp 9        W producer: all K chunks of W once when they fit beside the rings (resident), else chunk by chunk from L2
+//                 into a ring of three slots (bulk copies)
+//   warp 10       MMA issuer: per chunk 2 K steps x 3 products x M blocks; tcgen05.commit frees the X unit (and the W slot)
+//   warps 11..14  converters (one warp per chunk): raw slot -> (BatchNorm) -> hi / lo planes of a ring of X units, operand layout
+//   warps 0..7    epilogue (TMEM lane quadrant w % 4, row half w / 4) as before, in batches of 16 rows; with one M block the
+//                 accumulators are double buffered (2 x 2 x 128 TMEM columns), so tile t is written while tile t + 1 is
+//                 multiplied
+// linked by mbarriers only.  Needs 16-byte aligned rows (K % 4 == 0, aligned base): the tensor map's row pitch.
+constexpr int kFwEpi = 8, kFwConv = 4;
+constexpr int kFwThreads = 32 * (kFwEpi + 3 + kFwConv);
+constexpr uint32_t kFwRaw = kF32Rows * kF32KC * 4;            // one raw slot: [128][16] fp32, row-major
+constexpr int kFwSupCols = kF32KC + 4;                        // SUPER: box width (16 columns + up to 3 of lead-in)
+constexpr uint32_t kFwRawSup = kF32Rows * kFwSupCols * 4;     // SUPER: [128][20] fp32
+constexpr uint32_t kFwUnit = 2 * kF32Plane;                   // hi / lo planes of one X chunk
+constexpr int kFwMaxRing = 8;
+constexpr int kFwSubRows = 32;                                // rows per box of the second tensor map (ragged last tile of a CTA)
+
+__device__ __forceinline__ void tma2d_load(void* dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(dst)),
+               "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+               : "memory");
+}
+
+struct FwRing {                                               // slot / phase of a running counter over a ring of n slots
+  int slot = 0; uint32_t par = 0;
+  __device__ __forceinline__ void next(int n) { if (++slot == n) { slot = 0; par ^= 1u; } }
+};
+
+// BNF: BatchNorm on the input columns (EPI_BIAS) / on the side input u (EPI_SSM); GELU: activation of the SSM tail
+// SUPER: rows whose pitch is not a multiple of 16 bytes (K = 257: the model input) cannot be the rows of a tensor map, but
+// q = 4 / gcd(K, 4) consecutive rows can: the maps describe [rows / q] super-rows of q K floats, and a chunk of a tile arrives as
+// q boxes, one per row i of the super-rows.  A box must START on a 16-byte boundary (measured: an unaligned inner coordinate
+// raises "illegal instruction"), so the boxes are 20 floats wide and begin at the multiple of 4 below i K + 16 c; the converter
+// skips the (i K) % 4 leading floats and clears the columns past K (they hold the next row).  Raw / operand row rr of a group
+// of G rows (G = 128, or 32 in a ragged tile) holds tile row G (rr / G) + q (rr % (G / q)) + (rr % G) / (G / q); the epilogue
+// undoes the permutation.  lq = log2(q); p.rows is a multiple of q.
+template <int EPI, bool BNF, bool GELU, bool SUPER>
+__global__ void __launch_bounds__(kFwThreads, 1) tc_f32w_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmx_sub,
+                                                                const __grid_constant__ TcF32Params p, int resident, int NW, int NU, int NRAW, int lq) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);   // tensor-map copies want 128-byte aligned boxes
+  const int MB = p.MB, NC = p.NC;
+  const uint32_t wbytes = (uint32_t)MB * 2u * kF32Plane;
+  unsigned char* Wbuf = smem;                                 // resident: NC chunks, else NW slots
+  unsigned char* Ubuf = Wbuf + (size_t)(resident ? NC : NW) * wbytes;
+  unsigned char* Rbuf = Ubuf + (size_t)NU * kFwUnit;
+  constexpr uint32_t raw_bytes = SUPER ? kFwRawSup : kFwRaw, raw_pitch = SUPER ? kFwSupCols * 4 : kF32KC * 4;
+  float4* bnp = reinterpret_cast<float4*>(Rbuf + (size_t)NRAW * raw_bytes);   // input BatchNorm: [sub | mul | add][NC * 16 columns]
+  __shared__ __align__(8) uint64_t raw_full[kFwMaxRing], raw_free[kFwMaxRing], unit_full[kFwMaxRing], unit_free[kFwMaxRing];
+  __shared__ __align__(8) uint64_t w_full[kFwMaxRing], w_free[kFwMaxRing], acc_full[2], acc_free[2];
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int NACC = MB <= 2 ? 2 : 1, NBUF = MB == 1 ? 2 : 1;   // as tc_f32_kernel: separate accumulator for the small cross terms
+  const uint32_t acc_cols = (uint32_t)(MB * NACC) * 128u;     // TMEM columns of one accumulator buffer
+  if (warp == 0) tc_alloc(&tmem_slot, 512);
+  if (tid == 0) {
+    for (int i = 0; i < kFwMaxRing; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_free[i], 1); mbar_init(&unit_full[i], 1); mbar_init(&unit_free[i], 1); }
+    for (int i = 0; i < kFwMaxRing; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_free[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_free[i], kFwEpi); }
+    fence_mbar_init();
+  }
+  if constexpr (EPI == EPI_BIAS && BNF) {                      // pad columns: identity (they meet zero weights)
+    float* b = reinterpret_cast<float*>(bnp);
+    const int Kp = NC * kF32KC;
+    for (int k = tid; k < Kp; k += kFwThreads) {
+      const bool in = k < p.K;
+      b[k] = in ? p.in_sub[k] : 0.f; b[Kp + k] = in ? p.in_mul[k] : 1.f; b[2 * Kp + k] = in ? p.in_add[k] : 0.f;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t taddr = tmem_slot;
+  const long long qmask = SUPER ? ~(long long)((1 << lq) - 1) : ~0LL;   // CTA boundaries on whole super-rows
+  const long long row_begin = (p.rows * blockIdx.x / gridDim.x) & qmask;
+  const long long row_end = blockIdx.x + 1 == gridDim.x ? p.rows : (p.rows * (blockIdx.x + 1) / gridDim.x) & qmask;
+  const int ntiles = (int)((row_end - row_begin + kF32Rows - 1) / kF32Rows);
+
+  if (warp == kFwEpi) {
+    // ---------------------------------------------------------------- TMA producer (X)
+    if (lane == 0) {
+      FwRing r;
+      long long g = 0;
+      for (int t = 0; t < ntiles; ++t) {
+        const long long row0 = row_begin + (long long)t * kF32Rows;
+        const int rv = (int)min((long long)kF32Rows, row_end - row0);
+        for (int c = 0; c < NC; ++c, ++g, r.next(NRAW)) {
+          if (g >= NRAW) mbar_wait(&raw_free[r.slot], r.par ^ 1u);
+          unsigned char* dst = Rbuf + (size_t)r.slot * raw_bytes;
+          if constexpr (SUPER) {
+            const int q = 1 << lq;
+            if (rv == kF32Rows) {
+              mbar_expect_tx(&raw_full[r.slot], kFwRawSup);
+              for (int i = 0; i < q; ++i)
+                tma2d_load(dst + (size_t)i * (kF32Rows >> lq) * raw_pitch, &tmx, (i * p.K + c * kF32KC) & ~3, (int)(row0 >> lq), &raw_full[r.slot]);
+            } else {
+              const int nb = (rv + kFwSubRows - 1) / kFwSubRows;
+              mbar_expect_tx(&raw_full[r.slot], (uint32_t)nb * kFwSubRows * raw_pitch);
+              for (int b = 0; b < nb; ++b)
+                for (int i = 0; i < q; ++i)
+                  tma2d_load(dst + (size_t)(b * kFwSubRows + i * (kFwSubRows >> lq)) * raw_pitch, &tmx_sub, (i * p.K + c * kF32KC) & ~3,
+                             (int)((row0 + b * kFwSubRows) >> lq), &raw_full[r.slot]);
+            }
+          } else if (rv == kF32Rows) {
+            mbar_expect_tx(&raw_full[r.slot], kFwRaw);
+            tma2d_load(dst, &tmx, c * kF32KC, (int)row0, &raw_full[r.slot]);
+          } else {                                            // ragged last tile: 32-row boxes, nothing beyond the CTA's rows but < 32 rows
+            const int nb = (rv + kFwSubRows - 1) / kFwSubRows;
+            mbar_expect_tx(&raw_full[r.slot], (uint32_t)nb * kFwSubRows * kF32KC * 4u);
+            for (int i = 0; i < nb; ++i)
+              tma2d_load(dst + (size_t)i * kFwSubRows * kF32KC * 4, &tmx_sub, c * kF32KC, (int)row0 + i * kFwSubRows, &raw_full[r.slot]);
+          }
+        }
+      }
+    }
+  } else if (warp == kFwEpi + 1) {
+    // ---------------------------------------------------------------- W producer
+    if (lane == 0) {
+      if (resident) {
+        mbar_expect_tx(&w_full[0], (uint32_t)NC * wbytes);
+        for (int c = 0; c < NC; ++c) bulk_g2s(Wbuf + (size_t)c * wbytes, p.Wg + (size_t)c * wbytes, wbytes, &w_full[0]);
+      } else {
+        FwRing w;
+        long long g = 0;
+        for (int t = 0; t < ntiles; ++t)
+          for (int c = 0; c < NC; ++c, ++g, w.next(NW)) {
+            if (g >= NW) mbar_wait(&w_free[w.slot], w.par ^ 1u);
+            mbar_expect_tx(&w_full[w.slot], wbytes);
+            bulk_g2s(Wbuf + (size_t)w.slot * wbytes, p.Wg + (size_t)c * wbytes, wbytes, &w_full[w.slot]);
+          }
+      }
+    }
+  } else if (warp == kFwEpi + 2) {
+    // ---------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      FwRing u, w;
+      if (resident) mbar_wait(&w_full[0], 0);
+      for (int t = 0; t < ntiles; ++t) {
+        const int ab = NBUF == 2 ? (t & 1) : 0, use = NBUF == 2 ? (t >> 1) : t;
+        const int rv = (int)min((long long)kF32Rows, row_end - (row_begin + (long long)t * kF32Rows));
+        const uint32_t idesc = tc_idesc_tf32(kF32Rows, SUPER ? (rv + 31) & ~31 : (rv + 15) & ~15);   // SUPER: whole 32-row groups (permuted rows)
+        if (use >= 1) mbar_wait(&acc_free[ab], (uint32_t)(use - 1) & 1u);
+        for (int c = 0; c < NC; ++c, u.next(NU)) {
+          mbar_wait(&unit_full[u.slot], u.par);
+          if (!resident) mbar_wait(&w_full[w.slot], w.par);
+          tc_fence_after();
+          const uint32_t x0 = smem_u32(Ubuf + (size_t)u.slot * kFwUnit), w0 = smem_u32(Wbuf + (size_t)(resident ? c : w.slot) * wbytes);
+          for (int mb = 0; mb < MB; ++mb) {
+            const uint32_t d0 = taddr + (uint32_t)ab * acc_cols + 128u * mb, d1 = NACC == 2 ? d0 + 128u * MB : d0;
+            const uint32_t wh = w0 + (uint32_t)(2 * mb) * kF32Plane, wl = wh + kF32Plane;
+#pragma unroll
+            for (int j = 0; j < kF32KC / 8; ++j) {
+              const uint32_t ko = (uint32_t)j * 2u * kF32Lbo;
+              const uint64_t dwh = tc_smem_desc(wh + ko, kF32Lbo, 128), dwl = tc_smem_desc(wl + ko, kF32Lbo, 128);
+              const uint64_t dxh = tc_smem_desc(x0 + ko, kF32Lbo, 128), dxl = tc_smem_desc(x0 + kF32Plane + ko, kF32Lbo, 128);
+              const bool first = c == 0 && j == 0;
+              tc_mma_tf32(d1, dwl, dxh, idesc, !first);        // same order as tc_f32_kernel: identical results
+              tc_mma_tf32(d0, dwh, dxh, idesc, NACC == 2 ? !first : true);
+              tc_mma_tf32(d1, dwh, dxl, idesc, true);
+            }
+          }
+          tc_commit(&unit_free[u.slot]);
+          if (!resident) { tc_commit(&w_free[w.slot]); w.next(NW); }
+        }
+        tc_commit(&acc_full[ab]);
+      }
+    }
+  } else if (warp >= kFwEpi + 3) {
+    // ---------------------------------------------------------------- converters: ONE warp per chunk, warp cw owns the chunks
+    // g = cw (mod NU), i.e. X unit cw and the raw slots = cw (mod NU) (NRAW is a multiple of NU): every barrier is waited on by one
+    // warp in phase order (a parity wait two phases ahead would pass), up to NU chunks are converted at the same time, and a lane
+    // has 16 independent 16-byte items per chunk.  Item f = 16-byte group f & 3 of row f >> 2: raw offset 16 f (row-major slot).
+    const int cw = warp - (kFwEpi + 3);
+    if (cw < NU) {
+      const int grp = lane & 3;
+      const long long total = (long long)ntiles * NC;
+      uint32_t rpar = 0, upar = 0;
+      int slot = cw, c = cw % NC, t = cw / NC;
+      unsigned char* const xu = Ubuf + (size_t)cw * kFwUnit + (uint32_t)grp * kF32Lbo + (uint32_t)(lane >> 2) * 16u;
+      for (long long g = cw; g < total; g += NU) {
+        float4 bsub, bmul, badd;
+        if constexpr (EPI == EPI_BIAS && BNF) {
+          const float4* b = bnp + (c * (kF32KC / 4) + grp);
+          bsub = b[0]; bmul = b[NC * (kF32KC / 4)]; badd = b[2 * NC * (kF32KC / 4)];
+        }
+        mbar_wait(&raw_full[slot], rpar);
+        if (g >= NU) mbar_wait(&unit_free[cw], upar ^ 1u);
+        const unsigned char* raw = Rbuf + (size_t)slot * raw_bytes + (SUPER ? 0u : 16u * lane);
+        // a CTA's last tile may be ragged: only the 32-row batches the MMA reads (it rounds the tile up to 16 rows)
+        const int rvt = t + 1 < ntiles ? kF32Rows : (int)(row_end - (row_begin + (long long)t * kF32Rows));
+        const int nbq = (rvt + 31) >> 5;
+#pragma unroll
+        for (int bq = 0; bq < 4; ++bq) {
+          if (bq >= nbq) break;
+          float4 v[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if constexpr (SUPER) {                            // row class of raw row rr -> lead-in of its box
+              const int rr = bq * 32 + i * 8 + (lane >> 2);
+              const int cls = rvt == kF32Rows ? rr >> (7 - lq) : (rr & 31) >> (5 - lq);
+              const float* src = reinterpret_cast<const float*>(raw + (uint32_t)rr * raw_pitch + 16u * grp) + ((cls * p.K) & 3);
+              v[i] = make_float4(src[0], src[1], src[2], src[3]);
+            } else {
+              v[i] = *reinterpret_cast<const float4*>(raw + (bq * 128 + i * 32) * 16);
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if constexpr (EPI == EPI_BIAS && BNF) {
+              v[i].x = (v[i].x - bsub.x) * bmul.x + badd.x; v[i].y = (v[i].y - bsub.y) * bmul.y + badd.y;
+              v[i].z = (v[i].z - bsub.z) * bmul.z + badd.z; v[i].w = (v[i].w - bsub.w) * bmul.w + badd.w;
+            }
+            if constexpr (SUPER) {                            // columns past K hold the next row, not zeros
+              const int k = c * kF32KC + 4 * grp;
+              if (k + 3 >= p.K) {
+                if (k >= p.K) v[i].x = 0.f;
+                if (k + 1 >= p.K) v[i].y = 0.f;
+                if (k + 2 >= p.K) v[i].z = 0.f;
+                v[i].w = 0.f;
+              }
+            }
+            float4 hi, lo;                                    // nearest tf32: |lo| <= 2^-12 |x|
+            hi.x = __uint_as_float((__float_as_uint(v[i].x) + 0x1000u) & 0xFFFFE000u); lo.x = v[i].x - hi.x;
+            hi.y = __uint_as_float((__float_as_uint(v[i].y) + 0x1000u) & 0xFFFFE000u); lo.y = v[i].y - hi.y;
+            hi.z = __uint_as_float((__float_as_uint(v[i].z) + 0x1000u) & 0xFFFFE000u); lo.z = v[i].z - hi.z;
+            hi.w = __uint_as_float((__float_as_uint(v[i].w) + 0x1000u) & 0xFFFFE000u); lo.w = v[i].w - hi.w;
+            unsigned char* dst = xu + (bq * 32 + i * 8) * 16;  // row (bq 32 + i 8 + lane / 4)
+            *reinterpret_cast<float4*>(dst) = hi;
+            *reinterpret_cast<float4*>(dst + kF32Plane) = lo;
+          }
+        }
+        fence_proxy_async_smem();                             // the planes are read by the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) { mbar_arrive(&raw_free[slot]); mbar_arrive(&unit_full[cw]); }
+        upar ^= 1u;
+        slot += NU;
+        if (slot >= NRAW) { slot -= NRAW; rpar ^= 1u; }
+        c += NU;
+        while (c >= NC) { c -= NC; ++t; }
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- epilogue: lane = output column, registers = 16 rows
+    const int q4 = warp & 3, half = warp >> 2;
+    const uint32_t lane_base = (uint32_t)(32 * q4) << 16;
+    for (int t = 0; t < ntiles; ++t) {
+      const int ab = NBUF == 2 ? (t & 1) : 0, use = NBUF == 2 ? (t >> 1) : t;
+      const long long row0 = row_begin + (long long)t * kF32Rows;
+      const int rv = (int)min((long long)kF32Rows, row_end - row0);
+      mbar_wait(&acc_full[ab], (uint32_t)use & 1u);
+      tc_fence_after();
+      for (int mb = 0; mb < MB; ++mb) {
+        const int n = 128 * mb + 32 * q4 + lane;
+        const bool ncol = n < p.N;
+        const int nc = min(n, p.N - 1);
+        const uint32_t d0 = taddr + (uint32_t)ab * acc_cols + 128u * mb + lane_base;
+        float cb = 0.f, dn = 0.f, bs = 0.f, bm = 1.f, ba = 0.f;
+        if constexpr (EPI == EPI_SSM) {
+          dn = p.D[nc];
+          if constexpr (BNF) { bs = p.bn_sub[nc]; bm = p.bn_mul[nc]; ba = p.bn_add[nc]; }
+        } else {
+          cb = p.bias ? p.bias[nc] : 0.f;
+        }
+        const bool relu = p.relu != 0;
+        if constexpr (SUPER) {                                // permuted rows (see above); bias epilogue only
+          const int lg = rv == kF32Rows ? 7 : 5, G = 1 << lg, ncov = (rv + 31) & ~31;
+          float* const yb = p.Y + (size_t)row0 * p.y_stride + n;
+          for (int c0 = half * 64; c0 < min(ncov, half * 64 + 64); c0 += 16) {
+            uint32_t acc[16], acc2[16];
+            tc_ld16(d0 + (uint32_t)c0, acc);
+            if (NACC == 2) tc_ld16(d0 + 128u * MB + (uint32_t)c0, acc2);
+            tc_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int rr = c0 + j, w = rr & (G - 1);
+              const int real = (rr & ~(G - 1)) + ((w & ((G >> lq) - 1)) << lq) + (w >> (lg - lq));
+              const float a = NACC == 2 ? __uint_as_float(acc[j]) + __uint_as_float(acc2[j]) : __uint_as_float(acc[j]);
+              const float v = a + cb;
+              if (ncol && real < rv) yb[(size_t)real * p.y_stride] = relu ? fmaxf(v, 0.f) : v;
+            }
+          }
+          continue;
+        }
+        for (int c0 = half * 64; c0 < min(rv, half * 64 + 64); c0 += 16) {
+          const long long r0 = row0 + c0;
+          const int nr = min(16, rv - c0);
+          uint32_t acc[16], acc2[16];
+          float s1[16], s2[16];
+          tc_ld16(d0 + (uint32_t)c0, acc);
+          if (NACC == 2) tc_ld16(d0 + 128u * MB + (uint32_t)c0, acc2);
+          // side reads of the whole batch BEFORE its stores (a load behind a store it may alias with is not hoisted);
+          // one 64-bit base per batch, 32-bit row offsets (rows past the batch repeat its last row)
+          if constexpr (EPI == EPI_SSM) {
+            const float* sp = p.X2 + (size_t)r0 * p.N + nc;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) s1[j] = sp[min(j, nr - 1) * p.N];
+          } else if constexpr (EPI == EPI_GATE) {
+            const float* sp1 = p.X1 + (size_t)r0 * p.N + nc;
+            const float* sp2 = p.SKIP + (size_t)r0 * p.N + nc;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int o = min(j, nr - 1) * p.N;
+              s1[j] = sp1[o]; s2[j] = sp2[o];
+            }
+          }
+          tc_wait_ld();
+          float y[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float a = NACC == 2 ? __uint_as_float(acc[j]) + __uint_as_float(acc2[j]) : __uint_as_float(acc[j]);
+            if constexpr (EPI == EPI_BIAS) {
+              const float v = a + cb;
+              y[j] = relu ? fmaxf(v, 0.f) : v;
+            } else if constexpr (EPI == EPI_SSM) {
+              const float uu = BNF ? (s1[j] - bs) * bm + ba : s1[j];
+              const float v = fmaf(p.conj_mul, a, dn * uu);
+              y[j] = GELU ? f32_gelu_tanh(v) : fmaxf(v, 0.f);
+            } else {
+              const float v = fmaf(s1[j], f32_sigmoid_fast(a + cb), s2[j]);
+              y[j] = relu ? fmaxf(v, 0.f) : v;
+            }
+          }
+          if (ncol) {
+            float* q = p.Y + (size_t)r0 * p.y_stride + n;
+            if (nr == 16) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j, q += p.y_stride) *q = y[j];
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j, q += p.y_stride)
+                if (j < nr) *q = y[j];
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_free[ab]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc_dealloc(tmem_slot, 512);
 }
 
 // ------------------------------------------------------------------------------------------- host side
@@ -305,6 +671,60 @@ void tc_f32_free(TcF32Dev* d) {
   *d = TcF32Dev();
 }
 
+// 2-D tensor map over X [rows][K] fp32 with boxes of [box_rows][16 columns]; out-of-range elements read as zero
+static int make_tmap2d_f32(CUtensorMap* tm, const float* base, long long K, long long rows, int box_rows, int box_cols = kF32KC) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                               const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qr) != cudaSuccess || qr != cudaDriverEntryPointSuccess) f = nullptr;
+    return reinterpret_cast<EncodeFn>(f);
+  }();
+  if (!fn) return -1;
+  const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)K * 4};
+  const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -1;
+}
+
+// ring sizes of the warp-specialised kernel for one weight set; false when nothing fits
+static bool tc_f32w_plan(const TcF32Dev& d, size_t raw_bytes, int* resident, int* NW, int* NU, int* NRAW, size_t* smem) {
+  const size_t budget = 227 * 1024 - 1536 - 128 - (size_t)3 * d.NC * kF32KC * 4;   // static shared memory (barriers), alignment slack, BatchNorm columns
+  const size_t wchunk = (size_t)d.MB * 2 * kF32Plane;
+  // X units (= converter warps) and raw slots (a multiple of the units): the most units that leave 48 KB of raw slots in flight
+  // (profiles/r02_pipe_rates.md: 64 KB in flight per SM saturate the memory system, 32 KB give 80 %), else the most raw slots
+  auto rings = [&](size_t left, int min_raw) {
+    int best = 0;
+    for (int nu = std::min(4, kFwConv); nu >= 2; --nu) {
+      if (left < (size_t)nu * kFwUnit) continue;
+      int nraw = (int)std::min<size_t>(kFwMaxRing, (left - (size_t)nu * kFwUnit) / raw_bytes);
+      nraw -= nraw % nu;
+      if (nraw >= 6) { *NU = nu; *NRAW = nraw; return true; }
+      if (nraw >= min_raw && nraw > best) { *NU = nu; *NRAW = nraw; best = nraw; }
+    }
+    return best > 0;
+  };
+  static const int force_stream = [] { const char* e = getenv("S5B200_F32_W_STREAM"); return e ? atoi(e) : 0; }();
+  const size_t wres = (size_t)d.NC * wchunk;
+  if (!force_stream && wres < budget && wres < (1u << 20) && rings(budget - wres, 4)) { *resident = 1; *NW = 0; }
+  else {
+    *resident = 0;
+    bool ok = false;
+    // a W chunk takes ~1.5 us to arrive from L2 and is multiplied in 0.2 us per M block: enough slots to cover that
+    // (measured, K = 257 -> 96: three slots 86 us, six slots see profiles/r03_f32w.md), as long as 48 KB of raw slots remain
+    const int nw_want = d.MB == 1 ? 6 : d.MB == 2 ? 4 : 3;
+    for (int nw = nw_want; nw >= 2 && !ok; --nw)
+      if ((size_t)nw * wchunk < budget && rings(budget - (size_t)nw * wchunk, nw > 3 ? 6 : nw == 3 ? 4 : 3)) { *NW = nw; ok = true; }
+    if (!ok) return false;
+  }
+  *smem = (size_t)(*resident ? d.NC : *NW) * wchunk + (size_t)*NU * kFwUnit + (size_t)*NRAW * raw_bytes + 128 + (size_t)3 * d.NC * kF32KC * 4;
+  return true;
+}
+
 int tc_f32_launch(const TcF32Dev& d, const TcF32Args& a, int kclass, cudaStream_t st) {
   if (!d.ok || !a.X || !a.Y || a.rows <= 0) S5_FAIL(S5_E_BADARG, "dense-tile f32 linear: not eligible");
   TcF32Params p{};
@@ -317,13 +737,51 @@ int tc_f32_launch(const TcF32Dev& d, const TcF32Args& a, int kclass, cudaStream_
   p.X1 = a.X1; p.SKIP = a.SKIP;
   if (a.epi == EPI_SSM && (!a.X2 || !a.D)) S5_FAIL(S5_E_BADARG, "dense-tile f32 linear: SSM epilogue needs x and D");
   if (a.epi == EPI_GATE && (!a.X1 || !a.SKIP || !a.bias)) S5_FAIL(S5_E_BADARG, "dense-tile f32 linear: gate epilogue needs x1, skip and bias");
-  const size_t smem = 3 * ((size_t)d.MB * 2 * kF32Plane) + 2 * (2 * (size_t)kF32Plane);   // W ring + X double buffer
   const bool vec4 = (d.K & 3) == 0 && aligned16(a.X);
-  auto kernel = vec4 ? tc_f32_kernel<true> : tc_f32_kernel<false>;
+  // warp-specialised kernel (S5B200_F32_V2=0: the first form): rows with a 16-byte pitch - or, for the plain bias epilogue,
+  // super-rows of q = 4 / gcd(K, 4) rows (K = 257); at most 2^31 rows.  The < q rows left over go to the first form.
+  const char* v2_env = getenv("S5B200_F32_V2");
+  const bool v2_on = !v2_env || atoi(v2_env) != 0;
+  const int lq = (d.K & 3) == 0 ? 0 : (d.K & 1) ? 2 : 1, q = 1 << lq;
+  const bool super_ok = lq == 0 || (a.epi == EPI_BIAS && !a.in_sub);
+  long long rows_old = a.rows, row_off = 0;                   // rows the first form processes, starting at row_off
+  if (v2_on && aligned16(a.X) && super_ok && d.K >= kF32KC && a.rows < (1LL << 31) && a.rows >= q && (a.epi == EPI_BIAS || !a.in_sub)) {
+    int resident = 0, NW = 0, NU = 0, NRAW = 0;
+    size_t smem = 0;
+    CUtensorMap tmx, tmx_sub;
+    const long long rows_main = a.rows & ~(long long)(q - 1);
+    const int bc = lq ? kFwSupCols : kF32KC;
+    if (tc_f32w_plan(d, lq ? kFwRawSup : kFwRaw, &resident, &NW, &NU, &NRAW, &smem) &&
+        make_tmap2d_f32(&tmx, a.X, (long long)q * d.K, rows_main >> lq, kF32Rows >> lq, bc) == 0 &&
+        make_tmap2d_f32(&tmx_sub, a.X, (long long)q * d.K, rows_main >> lq, kFwSubRows >> lq, bc) == 0) {
+      const bool gelu = a.act != S5_ACT_RELU, bn2 = a.bn_sub != nullptr;
+      auto kernel = a.epi == EPI_BIAS  ? (lq ? tc_f32w_kernel<EPI_BIAS, false, false, true>
+                                             : a.in_sub ? tc_f32w_kernel<EPI_BIAS, true, false, false> : tc_f32w_kernel<EPI_BIAS, false, false, false>)
+                    : a.epi == EPI_SSM ? (gelu ? (bn2 ? tc_f32w_kernel<EPI_SSM, true, true, false> : tc_f32w_kernel<EPI_SSM, false, true, false>)
+                                               : (bn2 ? tc_f32w_kernel<EPI_SSM, true, false, false> : tc_f32w_kernel<EPI_SSM, false, false, false>))
+                                       : tc_f32w_kernel<EPI_GATE, false, false, false>;
+      S5_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      const int grid = (int)std::max<long long>(1, std::min<long long>((rows_main + kF32Rows - 1) / kF32Rows, (long long)sm_count()));
+      TcF32Params pm = p;
+      pm.rows = rows_main;
+      {
+        ProfScope prof(kclass, st);
+        kernel<<<grid, kFwThreads, smem, st>>>(tmx, tmx_sub, pm, resident, NW, NU, NRAW, lq);
+        S5_LAUNCH_CHECK();
+      }
+      if (rows_main == a.rows) return S5_OK;
+      row_off = rows_main; rows_old = a.rows - rows_main;
+    }
+  }
+  if (row_off) {                                              // bias epilogue only: no side inputs to shift
+    p.X += (size_t)row_off * d.K; p.Y += (size_t)row_off * d.N; p.rows = rows_old;
+  }
+  const size_t smem = 3 * ((size_t)d.MB * 2 * kF32Plane) + 2 * (2 * (size_t)kF32Plane);   // W ring + X double buffer
+  auto kernel = (vec4 && !row_off) ? tc_f32_kernel<true> : tc_f32_kernel<false>;
   S5_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   S5_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   const int per_sm = (d.MB <= 2 && 2 * (smem + 2048) <= 227 * 1024) ? 2 : 1;
-  const int grid = (int)std::max<long long>(1, std::min<long long>((a.rows + 63) / 64, (long long)per_sm * sm_count()));
+  const int grid = (int)std::max<long long>(1, std::min<long long>((p.rows + 63) / 64, (long long)per_sm * sm_count()));
   ProfScope prof(kclass, st);
   kernel<<<grid, kF32Threads, smem, st>>>(p);
   S5_LAUNCH_CHECK();

@@ -187,7 +187,8 @@ def test_spmm_f32_dense_tile_3xtf32(cuda_device):
 
     lib = _abi.lib()
     rng = np.random.default_rng(12)
-    for (rows, K, N, dens) in [(1000, 257, 96, 0.1), (700, 96, 257, 0.1), (513, 96, 128, 1.0), (2051, 128, 96, 0.2), (640, 200, 300, 0.5), (4096, 192, 256, 0.1)]:
+    for (rows, K, N, dens) in [(1000, 257, 96, 0.1), (700, 96, 257, 0.1), (513, 96, 128, 1.0), (2051, 128, 96, 0.2), (640, 200, 300, 0.5), (4096, 192, 256, 0.1),
+                                 (1003, 257, 96, 0.3), (30011, 257, 192, 0.1), (777, 258, 64, 0.5), (20000, 130, 200, 0.5)]:   # row pitch not a multiple of 16 bytes: super-rows
         W = (rng.standard_normal((K, N)) * (rng.uniform(size=(K, N)) < dens)).astype(np.float32)
         X = (rng.standard_normal((rows, K)) * np.exp(rng.uniform(-6, 6, (rows, 1)))).astype(np.float32)   # wide dynamic range
         bias = rng.standard_normal(N).astype(np.float32)
@@ -466,3 +467,29 @@ def test_refused_cooperative_launch_falls_back_to_unfused_kernels(cuda_device, z
     assert torch.equal(m1(x), y0)
     h = torch.relu(torch.randn(2, 300, zoo["dims"].d_model, device=cuda_device))
     assert torch.equal(m1.layer(1, h), m0.layer(1, h))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("relufication", [False, True], ids=["gelu", "relu"])
+def test_float_dense_tile_kernels_agree_bit_for_bit(cuda_device, zoo, relufication, monkeypatch):
+    """The warp-specialised 3 x TF32 kernel (tc_f32w_kernel: tensor-map ring, one converter warp per chunk, decoupled epilogue)
+    issues the same products in the same order into the same accumulators as the first form (S5B200_F32_V2=0) and shares its
+    epilogue arithmetic: the float model must not change by a bit - ragged last tiles, BatchNorm in the converters, the SSM-tail
+    and gate epilogues, one and three M blocks included."""
+    import torch
+
+    monkeypatch.setenv("S5B200_TC_MIN_ROWS", "1")
+    m, _ = _bound(zoo, static=False, relufication=relufication)
+    x = torch.from_numpy(zoo["x"]).to(cuda_device)
+    monkeypatch.setenv("S5B200_F32_V2", "1")
+    y2 = m(x).clone()
+    monkeypatch.setenv("S5B200_F32_V2", "0")
+    y1 = m(x).clone()
+    assert torch.equal(y1, y2)
+    # a long batch: several tiles per CTA, every ring wraps
+    xl = torch.from_numpy(np.tile(zoo["x"], (40, 4, 1))).to(cuda_device)
+    monkeypatch.setenv("S5B200_F32_V2", "1")
+    y2 = m(xl).clone()
+    monkeypatch.setenv("S5B200_F32_V2", "0")
+    y1 = m(xl).clone()
+    assert torch.equal(y1, y2)
