@@ -484,6 +484,14 @@ static int run_block(const s5_model* m, int li, const float* x, float* out, floa
     if (bn) { a.in_sub = ld.bn_mean; a.in_mul = ld.bn_mul; a.in_add = ld.bn_bias; }
     if ((rc = tc_f32_launch(ld.fb, a, S5_K_BPROJ, st))) return rc;
     if ((rc = launch_scan_c64(bu, ld.lam, bu, B, L, m->desc.P, m->desc.relufication, scan_ws, scan_ws_bytes, st))) return rc;
+    {   // C projection + SSM tail + out2 + gate in one launch when one M block holds H (tc_f32g_kernel)
+      TcF32GluArgs g;
+      g.XS = bu; g.X = x; g.Y = out; g.rows = rows; g.D = ld.D; g.o_bias = ld.o_bias; g.relu = m->desc.relufication;
+      if (bn) { g.bn_sub = ld.bn_mean; g.bn_mul = ld.bn_mul; g.bn_add = ld.bn_bias; }
+      g.conj_mul = m->desc.conj_sym ? 2.f : 1.f; g.act = m->desc.activation;
+      rc = tc_f32_glu_launch(ld.fc, ld.fo, g, S5_K_GLU, st);
+      if (rc != S5_E_UNSUPPORTED) return rc;
+    }
     TcF32Args c;
     c.X = bu; c.Y = out; c.rows = rows; c.epi = 1; c.X2 = x; c.D = ld.D;
     if (bn) { c.bn_sub = ld.bn_mean; c.bn_mul = ld.bn_mul; c.bn_add = ld.bn_bias; }

@@ -638,6 +638,292 @@ __global__ void __launch_bounds__(kFwThreads, 1) tc_f32w_kernel(const __grid_con
   if (warp == 0) tc_dealloc(tmem_slot, 512);
 }
 
+// ------------------------------------------------------------------------------------------- C projection + SSM tail + out2 + gate in ONE launch
+// The block tail of the float flavour (ssm.py:179-185, 618-622; layers.py:217-238) as two chained products per 128-row tile:
+//   acc1 = C~ xs            (K1 = 2P chunks: the scan output through the tensor-map ring / converters of tc_f32w_kernel)
+//   E1   : x1 = act(conj acc1 + D BN(x))  -> hi / lo operand planes of x1 in shared memory (never written to HBM)
+//   acc2 = W_out2 x1        (operands: the x1 planes)
+//   E2   : out = x1 sigmoid(acc2 + b) + x -> global (x1 = hi + lo exactly, read back from the planes)
+// Against the two launches it replaces this saves writing x1, reading it twice and reading the block input twice: 153 instead of
+// 337 MB per block at the bench shape.  Both weight sets are streamed from L2 through one slot ring (C~ chunks, then out2 chunks, per
+// tile: the x1 planes take the room a resident W would need).  TMEM: acc1 = columns 0..255, acc2 = 256..511 (two accumulators each,
+// as everywhere in this file); the issuer alternates MMA1(t), MMA2(t), MMA1(t + 1) ... so E2(t) runs under MMA1(t + 1).
+// Same MMA order and epilogue arithmetic as the two launches: bit-identical (tested).  One M block: H <= 128.
+struct TcF32GluParams {
+  long long rows; int K1, H, NC1, NC2;
+  const unsigned char* Wc; const unsigned char* Wo;
+  const float* X; const float* bn_sub; const float* bn_mul; const float* bn_add; const float* D; float conj_mul;
+  const float* o_bias; int relu;
+  float* Y;
+};
+
+// 16 epilogue warps (TMEM lane quadrant x 32 rows) and the two converter warps the X-unit ring of this kernel can feed.  Measured at the
+// bench shape (us per launch; the two launches it replaces: 108): 8 epilogue warps with 16-row batches 92; + all 64 block-input values of a lane
+// requested before the wait for acc1 90; 16 warps with 8-row batches 87 (kept); 8 warps, both epilogues fed from 64 prefetched values,
+// 16-row TMEM round trips 103.  The critical path of a tile is MMA1 -> E1 -> MMA2 -> E2 with E1 of the next tile behind E2 (shared x1
+// planes): a cycle-counter trace gives 20 700 cycles per tile of which the issuer waits 7 900 for E1 and 2 300 for X units.
+constexpr int kFgEpi = 16, kFgConv = 2;
+constexpr int kFgThreads = 32 * (kFgEpi + 3 + kFgConv);
+
+template <bool BNF, bool GELU>
+__global__ void __launch_bounds__(kFgThreads, 1) tc_f32g_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmx_sub,
+                                                                const __grid_constant__ TcF32GluParams p, int NW, int NU, int NRAW) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
+  const int NC1 = p.NC1, NC2 = p.NC2, NCT = NC1 + NC2;
+  constexpr uint32_t wbytes = 2u * kF32Plane;                 // one chunk of either weight set (one M block, hi + lo)
+  unsigned char* X1buf = smem;                                // NC2 units: hi / lo planes of x1, chunk = 16 columns
+  unsigned char* Wbuf = X1buf + (size_t)NC2 * kFwUnit;
+  unsigned char* Ubuf = Wbuf + (size_t)NW * wbytes;
+  unsigned char* Rbuf = Ubuf + (size_t)NU * kFwUnit;
+  __shared__ __align__(8) uint64_t raw_full[kFwMaxRing], raw_free[kFwMaxRing], unit_full[kFwMaxRing], unit_free[kFwMaxRing];
+  __shared__ __align__(8) uint64_t w_full[kFwMaxRing], w_free[kFwMaxRing], acc1_full, acc1_free, acc2_full, acc2_free, x1_full;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (warp == 0) tc_alloc(&tmem_slot, 512);
+  if (tid == 0) {
+    for (int i = 0; i < kFwMaxRing; ++i) {
+      mbar_init(&raw_full[i], 1); mbar_init(&raw_free[i], 1); mbar_init(&unit_full[i], 1); mbar_init(&unit_free[i], 1);
+      mbar_init(&w_full[i], 1); mbar_init(&w_free[i], 1);
+    }
+    mbar_init(&acc1_full, 1); mbar_init(&acc1_free, kFgEpi); mbar_init(&acc2_full, 1); mbar_init(&acc2_free, kFgEpi); mbar_init(&x1_full, kFgEpi);
+    fence_mbar_init();
+  }
+  for (size_t i = (size_t)tid * 16; i < (size_t)NC2 * kFwUnit; i += kFgThreads * 16) *reinterpret_cast<int4*>(X1buf + i) = make_int4(0, 0, 0, 0);   // pad columns stay zero
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+#ifdef S5_F32G_TRACE
+  long long tw[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const long long tstart = clock64();
+#define FG_T(i, stmt) do { const long long t_ = clock64(); stmt; tw[i] += clock64() - t_; } while (0)
+#else
+#define FG_T(i, stmt) stmt
+#endif
+  const uint32_t taddr = tmem_slot;
+  const long long row_begin = p.rows * blockIdx.x / gridDim.x, row_end = p.rows * (blockIdx.x + 1) / gridDim.x;
+  const int ntiles = (int)((row_end - row_begin + kF32Rows - 1) / kF32Rows);
+
+  if (warp == kFgEpi) {
+    // ---------------------------------------------------------------- TMA producer (xs)
+    if (lane == 0) {
+      FwRing r;
+      long long g = 0;
+      for (int t = 0; t < ntiles; ++t) {
+        const long long row0 = row_begin + (long long)t * kF32Rows;
+        const int rv = (int)min((long long)kF32Rows, row_end - row0);
+        for (int c = 0; c < NC1; ++c, ++g, r.next(NRAW)) {
+          if (g >= NRAW) mbar_wait(&raw_free[r.slot], r.par ^ 1u);
+          unsigned char* dst = Rbuf + (size_t)r.slot * kFwRaw;
+          if (rv == kF32Rows) {
+            mbar_expect_tx(&raw_full[r.slot], kFwRaw);
+            tma2d_load(dst, &tmx, c * kF32KC, (int)row0, &raw_full[r.slot]);
+          } else {
+            const int nb = (rv + kFwSubRows - 1) / kFwSubRows;
+            mbar_expect_tx(&raw_full[r.slot], (uint32_t)nb * kFwSubRows * kF32KC * 4u);
+            for (int i = 0; i < nb; ++i)
+              tma2d_load(dst + (size_t)i * kFwSubRows * kF32KC * 4, &tmx_sub, c * kF32KC, (int)row0 + i * kFwSubRows, &raw_full[r.slot]);
+          }
+        }
+      }
+    }
+  } else if (warp == kFgEpi + 1) {
+    // ---------------------------------------------------------------- W producer: per tile the chunks of C~, then those of out2
+    if (lane == 0) {
+      FwRing w;
+      long long g = 0;
+      for (int t = 0; t < ntiles; ++t)
+        for (int c = 0; c < NCT; ++c, ++g, w.next(NW)) {
+          if (g >= NW) mbar_wait(&w_free[w.slot], w.par ^ 1u);
+          mbar_expect_tx(&w_full[w.slot], wbytes);
+          const unsigned char* src = c < NC1 ? p.Wc + (size_t)c * wbytes : p.Wo + (size_t)(c - NC1) * wbytes;
+          bulk_g2s(Wbuf + (size_t)w.slot * wbytes, src, wbytes, &w_full[w.slot]);
+        }
+    }
+  } else if (warp == kFgEpi + 2) {
+    // ---------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      FwRing u, w;
+      auto chunk = [&](uint32_t x0, uint32_t w0, uint32_t d0, uint32_t idesc, bool first_chunk) {
+        const uint32_t d1 = d0 + 128u, wh = w0, wl = w0 + kF32Plane;
+#pragma unroll
+        for (int j = 0; j < kF32KC / 8; ++j) {
+          const uint32_t ko = (uint32_t)j * 2u * kF32Lbo;
+          const uint64_t dwh = tc_smem_desc(wh + ko, kF32Lbo, 128), dwl = tc_smem_desc(wl + ko, kF32Lbo, 128);
+          const uint64_t dxh = tc_smem_desc(x0 + ko, kF32Lbo, 128), dxl = tc_smem_desc(x0 + kF32Plane + ko, kF32Lbo, 128);
+          const bool first = first_chunk && j == 0;
+          tc_mma_tf32(d1, dwl, dxh, idesc, !first);            // same order as tc_f32_kernel: identical results
+          tc_mma_tf32(d0, dwh, dxh, idesc, !first);
+          tc_mma_tf32(d1, dwh, dxl, idesc, true);
+        }
+      };
+      for (int t = 0; t < ntiles; ++t) {
+        const int rv = (int)min((long long)kF32Rows, row_end - (row_begin + (long long)t * kF32Rows));
+        const uint32_t idesc = tc_idesc_tf32(kF32Rows, (rv + 15) & ~15);
+        if (t >= 1) FG_T(0, mbar_wait(&acc1_free, (uint32_t)(t - 1) & 1u));
+        for (int c = 0; c < NC1; ++c, u.next(NU), w.next(NW)) {
+          FG_T(1, mbar_wait(&unit_full[u.slot], u.par));
+          FG_T(2, mbar_wait(&w_full[w.slot], w.par));
+          tc_fence_after();
+          chunk(smem_u32(Ubuf + (size_t)u.slot * kFwUnit), smem_u32(Wbuf + (size_t)w.slot * wbytes), taddr, idesc, c == 0);
+          tc_commit(&unit_free[u.slot]);
+          tc_commit(&w_free[w.slot]);
+        }
+        tc_commit(&acc1_full);
+        FG_T(3, mbar_wait(&x1_full, (uint32_t)t & 1u));                // E1(t) has written the x1 planes (and E2(t - 1) is over: same warps)
+        if (t >= 1) FG_T(4, mbar_wait(&acc2_free, (uint32_t)(t - 1) & 1u));
+        for (int c = 0; c < NC2; ++c, w.next(NW)) {
+          FG_T(5, mbar_wait(&w_full[w.slot], w.par));
+          tc_fence_after();
+          chunk(smem_u32(X1buf + (size_t)c * kFwUnit), smem_u32(Wbuf + (size_t)w.slot * wbytes), taddr + 256u, idesc, c == 0);
+          tc_commit(&w_free[w.slot]);
+        }
+        tc_commit(&acc2_full);
+      }
+    }
+  } else if (warp >= kFgEpi + 3) {
+    // ---------------------------------------------------------------- converters (xs chunks), as in tc_f32w_kernel
+    const int cw = warp - (kFgEpi + 3);
+    if (cw < NU) {
+      const int grp = lane & 3;
+      const long long total = (long long)ntiles * NC1;
+      uint32_t rpar = 0, upar = 0;
+      int slot = cw, c = cw % NC1, t = cw / NC1;
+      unsigned char* const xu = Ubuf + (size_t)cw * kFwUnit + (uint32_t)grp * kF32Lbo + (uint32_t)(lane >> 2) * 16u;
+      for (long long g = cw; g < total; g += NU) {
+        mbar_wait(&raw_full[slot], rpar);
+        if (g >= NU) mbar_wait(&unit_free[cw], upar ^ 1u);
+        const unsigned char* raw = Rbuf + (size_t)slot * kFwRaw + 16u * lane;
+        const int rvt = t + 1 < ntiles ? kF32Rows : (int)(row_end - (row_begin + (long long)t * kF32Rows));
+        const int nbq = (rvt + 31) >> 5;
+#pragma unroll
+        for (int bq = 0; bq < 4; ++bq) {
+          if (bq >= nbq) break;
+          float4 v[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) v[i] = *reinterpret_cast<const float4*>(raw + (bq * 128 + i * 32) * 16);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float4 hi, lo;                                    // nearest tf32: |lo| <= 2^-12 |x|
+            hi.x = __uint_as_float((__float_as_uint(v[i].x) + 0x1000u) & 0xFFFFE000u); lo.x = v[i].x - hi.x;
+            hi.y = __uint_as_float((__float_as_uint(v[i].y) + 0x1000u) & 0xFFFFE000u); lo.y = v[i].y - hi.y;
+            hi.z = __uint_as_float((__float_as_uint(v[i].z) + 0x1000u) & 0xFFFFE000u); lo.z = v[i].z - hi.z;
+            hi.w = __uint_as_float((__float_as_uint(v[i].w) + 0x1000u) & 0xFFFFE000u); lo.w = v[i].w - hi.w;
+            unsigned char* dst = xu + (bq * 32 + i * 8) * 16;
+            *reinterpret_cast<float4*>(dst) = hi;
+            *reinterpret_cast<float4*>(dst + kF32Plane) = lo;
+          }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) { mbar_arrive(&raw_free[slot]); mbar_arrive(&unit_full[cw]); }
+        upar ^= 1u;
+        slot += NU;
+        if (slot >= NRAW) { slot -= NRAW; rpar ^= 1u; }
+        c += NU;
+        while (c >= NC1) { c -= NC1; ++t; }
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- epilogues: lane = column n of the block, registers = 16 rows
+    const int q4 = warp & 3, part = warp >> 2;                // TMEM lane quadrant, rows [32 part, 32 part + 32) of the tile
+    const uint32_t d0 = taddr + ((uint32_t)(32 * q4) << 16);
+    const int n = 32 * q4 + lane, H = p.H;
+    const bool ncol = n < H;
+    const int nc = min(n, H - 1);
+    const float dn = p.D[nc], ob = p.o_bias[nc];
+    float bs = 0.f, bm = 1.f, ba = 0.f;
+    if constexpr (BNF) { bs = p.bn_sub[nc]; bm = p.bn_mul[nc]; ba = p.bn_add[nc]; }
+    const bool relu = p.relu != 0;
+    // element (row, column n) of the x1 planes: chunk n / 16, 16-byte group (n / 4) % 4, word n % 4
+    unsigned char* const x1p = X1buf + (size_t)(nc >> 4) * kFwUnit + (uint32_t)((nc >> 2) & 3) * kF32Lbo + 4u * (nc & 3);
+    for (int t = 0; t < ntiles; ++t) {
+      const long long row0 = row_begin + (long long)t * kF32Rows;
+      const int rv = (int)min((long long)kF32Rows, row_end - row0);
+      const int rbeg = 32 * part, rend = min(rv, rbeg + 32);
+      // ---- E1
+      FG_T(0, mbar_wait(&acc1_full, (uint32_t)t & 1u));
+      tc_fence_after();
+#ifdef S5_F32G_TRACE
+      const long long te1 = clock64();
+#endif
+      for (int c0 = rbeg; c0 < rend; c0 += 8) {
+        const int nr = min(8, rv - c0);
+        uint32_t acc[8], acc2[8];
+        float s1[8];
+        tc_ld8(d0 + (uint32_t)c0, acc);
+        tc_ld8(d0 + 128u + (uint32_t)c0, acc2);
+        const float* sp = p.X + (size_t)(row0 + c0) * H + nc;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s1[j] = sp[min(j, nr - 1) * H];
+        tc_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float a = __uint_as_float(acc[j]) + __uint_as_float(acc2[j]);
+          const float uu = BNF ? (s1[j] - bs) * bm + ba : s1[j];
+          const float v = fmaf(p.conj_mul, a, dn * uu);
+          const float x1 = GELU ? f32_gelu_tanh(v) : fmaxf(v, 0.f);
+          const float hi = __uint_as_float((__float_as_uint(x1) + 0x1000u) & 0xFFFFE000u);
+          if (ncol) {
+            *reinterpret_cast<float*>(x1p + (uint32_t)(c0 + j) * 16u) = hi;
+            *reinterpret_cast<float*>(x1p + kF32Plane + (uint32_t)(c0 + j) * 16u) = x1 - hi;
+          }
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async_smem();                               // the planes are read by the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(&acc1_free); mbar_arrive(&x1_full); }
+#ifdef S5_F32G_TRACE
+      tw[1] += clock64() - te1;
+#endif
+      // ---- E2
+      FG_T(2, mbar_wait(&acc2_full, (uint32_t)t & 1u));
+      tc_fence_after();
+#ifdef S5_F32G_TRACE
+      const long long te2 = clock64();
+#endif
+      for (int c0 = rbeg; c0 < rend; c0 += 8) {
+        const int nr = min(8, rv - c0);
+        uint32_t acc[8], acc2[8];
+        float s1[8], sk[8];
+        tc_ld8(d0 + 256u + (uint32_t)c0, acc);
+        tc_ld8(d0 + 384u + (uint32_t)c0, acc2);
+        const float* sp = p.X + (size_t)(row0 + c0) * H + nc;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sk[j] = sp[min(j, nr - 1) * H];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)                             // x1 = hi + lo, exact
+          s1[j] = *reinterpret_cast<const float*>(x1p + (uint32_t)(c0 + j) * 16u) + *reinterpret_cast<const float*>(x1p + kF32Plane + (uint32_t)(c0 + j) * 16u);
+        tc_wait_ld();
+        if (ncol) {
+          float* q = p.Y + (size_t)(row0 + c0) * H + n;
+#pragma unroll
+          for (int j = 0; j < 8; ++j, q += H) {
+            const float a = __uint_as_float(acc[j]) + __uint_as_float(acc2[j]);
+            const float v = fmaf(s1[j], f32_sigmoid_fast(a + ob), sk[j]);
+            if (j < nr) *q = relu ? fmaxf(v, 0.f) : v;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc2_free);
+#ifdef S5_F32G_TRACE
+      tw[3] += clock64() - te2;
+#endif
+    }
+  }
+#ifdef S5_F32G_TRACE
+  if (blockIdx.x == 3 && lane == 0 && (warp == 0 || warp == 7 || warp == kFgEpi + 2))
+    printf("[f32g trace] warp %d: total %lld cyc, tiles %d | %lld %lld %lld %lld %lld %lld\n", warp, clock64() - tstart, ntiles, tw[0], tw[1], tw[2], tw[3], tw[4], tw[5]);
+#endif
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc_dealloc(tmem_slot, 512);
+}
+
 // ------------------------------------------------------------------------------------------- host side
 int tc_f32_build(const float* W /*[K][N] row-major*/, int K, int N, TcF32Dev* out) {
   out->ok = false;
@@ -784,6 +1070,48 @@ int tc_f32_launch(const TcF32Dev& d, const TcF32Args& a, int kclass, cudaStream_
   const int grid = (int)std::max<long long>(1, std::min<long long>((p.rows + 63) / 64, (long long)per_sm * sm_count()));
   ProfScope prof(kclass, st);
   kernel<<<grid, kF32Threads, smem, st>>>(p);
+  S5_LAUNCH_CHECK();
+  return S5_OK;
+}
+
+// C projection + SSM tail + out2 + gate of one float block in one launch (tc_f32g_kernel); S5_E_UNSUPPORTED (no error text) when the
+// shapes do not qualify - the caller then runs the two launches
+int tc_f32_glu_launch(const TcF32Dev& fc, const TcF32Dev& fo, const TcF32GluArgs& a, int kclass, cudaStream_t st) {
+  const char* env = getenv("S5B200_F32_GLU_FUSED");
+  if (env && atoi(env) == 0) return S5_E_UNSUPPORTED;
+  const int H = fc.N;
+  if (!fc.ok || !fo.ok || fc.MB != 1 || fo.MB != 1 || fo.K != H || fo.N != H || (fc.K & 3) || fc.K < kF32KC || !aligned16(a.XS) ||
+      a.rows <= 0 || a.rows >= (1LL << 31) || !a.X || !a.Y || !a.D || !a.o_bias)
+    return S5_E_UNSUPPORTED;
+  const size_t budget = 227 * 1024 - 1536 - 128;
+  const size_t x1 = (size_t)fo.NC * kFwUnit;
+  int NW = 3, NU = 0, NRAW = 0;
+  bool ok = false;
+  for (; NW >= 2 && !ok; --NW) {
+    const size_t fixed = x1 + (size_t)NW * kFwUnit;
+    for (int nu = kFgConv; nu >= 2 && !ok; --nu) {
+      if (budget < fixed + (size_t)nu * kFwUnit) continue;
+      int nraw = (int)std::min<size_t>(kFwMaxRing, (budget - fixed - (size_t)nu * kFwUnit) / kFwRaw);
+      nraw -= nraw % nu;
+      if (nraw >= 4) { NU = nu; NRAW = nraw; ok = true; }
+    }
+    if (ok) break;
+  }
+  if (!ok) return S5_E_UNSUPPORTED;
+  CUtensorMap tmx, tmx_sub;
+  if (make_tmap2d_f32(&tmx, a.XS, fc.K, a.rows, kF32Rows) != 0 || make_tmap2d_f32(&tmx_sub, a.XS, fc.K, a.rows, kFwSubRows) != 0) return S5_E_UNSUPPORTED;
+  TcF32GluParams p{};
+  p.rows = a.rows; p.K1 = fc.K; p.H = H; p.NC1 = fc.NC; p.NC2 = fo.NC;
+  p.Wc = reinterpret_cast<const unsigned char*>(fc.Wg); p.Wo = reinterpret_cast<const unsigned char*>(fo.Wg);
+  p.X = a.X; p.bn_sub = a.bn_sub; p.bn_mul = a.bn_mul; p.bn_add = a.bn_add; p.D = a.D; p.conj_mul = a.conj_mul;
+  p.o_bias = a.o_bias; p.relu = a.relu; p.Y = a.Y;
+  const bool gelu = a.act != S5_ACT_RELU, bn = a.bn_sub != nullptr;
+  auto kernel = gelu ? (bn ? tc_f32g_kernel<true, true> : tc_f32g_kernel<false, true>) : (bn ? tc_f32g_kernel<true, false> : tc_f32g_kernel<false, false>);
+  const size_t smem = x1 + (size_t)NW * kFwUnit + (size_t)NU * kFwUnit + (size_t)NRAW * kFwRaw + 128;
+  S5_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = (int)std::max<long long>(1, std::min<long long>((a.rows + kF32Rows - 1) / kF32Rows, (long long)sm_count()));
+  ProfScope prof(kclass, st);
+  kernel<<<grid, kFgThreads, smem, st>>>(tmx, tmx_sub, p, NW, NU, NRAW);
   S5_LAUNCH_CHECK();
   return S5_OK;
 }

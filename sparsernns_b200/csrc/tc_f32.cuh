@@ -20,8 +20,17 @@ struct TcF32Args {
   const float* X1 = nullptr; const float* SKIP = nullptr;
 };
 
+// block tail of the float flavour in one launch: xs [rows][2P] -> out [rows][H] (tc_f32g_kernel)
+struct TcF32GluArgs {
+  const float* XS = nullptr; const float* X = nullptr; float* Y = nullptr; long long rows = 0;
+  const float* bn_sub = nullptr; const float* bn_mul = nullptr; const float* bn_add = nullptr;   // BatchNorm of the block input (u = BN(x))
+  const float* D = nullptr; float conj_mul = 1.f; int act = 0;
+  const float* o_bias = nullptr; int relu = 0;
+};
+
 int tc_f32_build(const float* W, int K, int N, TcF32Dev* out);
 void tc_f32_free(TcF32Dev* d);
 int tc_f32_launch(const TcF32Dev& d, const TcF32Args& a, int kclass, cudaStream_t st);
+int tc_f32_glu_launch(const TcF32Dev& fc, const TcF32Dev& fo, const TcF32GluArgs& a, int kclass, cudaStream_t st);   // S5_E_UNSUPPORTED: run the two launches
 
 }  // namespace s5

@@ -474,22 +474,19 @@ def test_refused_cooperative_launch_falls_back_to_unfused_kernels(cuda_device, z
 def test_float_dense_tile_kernels_agree_bit_for_bit(cuda_device, zoo, relufication, monkeypatch):
     """The warp-specialised 3 x TF32 kernel (tc_f32w_kernel: tensor-map ring, one converter warp per chunk, decoupled epilogue)
     issues the same products in the same order into the same accumulators as the first form (S5B200_F32_V2=0) and shares its
-    epilogue arithmetic: the float model must not change by a bit - ragged last tiles, BatchNorm in the converters, the SSM-tail
-    and gate epilogues, one and three M blocks included."""
+    epilogue arithmetic, and so does the one-launch block tail (tc_f32g_kernel: C projection + SSM tail + out2 + gate, x1 kept in
+    shared memory; S5B200_F32_GLU_FUSED=0 runs the two launches): the float model must not change by a bit - ragged last tiles,
+    BatchNorm in the converters, the SSM-tail and gate epilogues, one and three M blocks, super-rows (K = 257) included."""
     import torch
 
     monkeypatch.setenv("S5B200_TC_MIN_ROWS", "1")
     m, _ = _bound(zoo, static=False, relufication=relufication)
-    x = torch.from_numpy(zoo["x"]).to(cuda_device)
-    monkeypatch.setenv("S5B200_F32_V2", "1")
-    y2 = m(x).clone()
-    monkeypatch.setenv("S5B200_F32_V2", "0")
-    y1 = m(x).clone()
-    assert torch.equal(y1, y2)
-    # a long batch: several tiles per CTA, every ring wraps
-    xl = torch.from_numpy(np.tile(zoo["x"], (40, 4, 1))).to(cuda_device)
-    monkeypatch.setenv("S5B200_F32_V2", "1")
-    y2 = m(xl).clone()
-    monkeypatch.setenv("S5B200_F32_V2", "0")
-    y1 = m(xl).clone()
-    assert torch.equal(y1, y2)
+    # the zoo batch (2 - 3 tiles per CTA at most) and a long one: several tiles per CTA, every ring wraps
+    for x in (torch.from_numpy(zoo["x"]).to(cuda_device), torch.from_numpy(np.tile(zoo["x"], (40, 4, 1))).to(cuda_device)):
+        ys = []
+        for v2, fused in (("1", "1"), ("1", "0"), ("0", "0")):
+            monkeypatch.setenv("S5B200_F32_V2", v2)
+            monkeypatch.setenv("S5B200_F32_GLU_FUSED", fused)
+            ys.append(m(x).clone())
+        assert torch.equal(ys[0], ys[1]), "one-launch block tail differs from the two launches"
+        assert torch.equal(ys[1], ys[2]), "warp-specialised kernel differs from the first form"
