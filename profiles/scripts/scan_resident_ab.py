@@ -1,0 +1,63 @@
+"""scan_c64 with few clips: the resident form (one block of 128 steps per CTA, kept in shared memory) against the segmented
+ring kernel (S5B200_SCAN_RESIDENT=0) - bit identity of the two and CUDA-event times over rotating buffers, several shapes."""
+import json, os, sys, ctypes as C, numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+from sparsernns_b200 import _abi
+lib = _abi.lib(); dev = torch.device('cuda:0')
+lib.s5b200_scan_c64_workspace_bytes.restype = C.c_size_t
+st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+peak = 6541.8
+shapes = [(32, 3751, 64), (32, 3751, 128), (1, 65536, 64), (1, 4096, 64), (8, 3751, 64), (64, 3751, 64), (95, 3751, 64), (32, 3751, 16),
+          (3, 1000, 100), (32, 3751, 256), (1, 65536, 256)]
+if len(sys.argv) > 3:
+    shapes = [tuple(int(v) for v in sys.argv[1:4])]
+out = []
+for B, L, P in shapes:
+    need = lib.s5b200_scan_c64_workspace_bytes(B, L, P)
+    by = 16.0 * B * L * P
+    nb = int(min(8, max(2, -(-400e6 // by))))
+    ws = [torch.zeros(max(need, 16), dtype=torch.uint8, device=dev) for _ in range(nb)]
+    g = torch.Generator(device=dev); g.manual_seed(B * 1000 + P)
+    Bu = [torch.randn(B, L, P, 2, device=dev, generator=g) for _ in range(nb)]
+    xs = [torch.empty(B, L, P, 2, device=dev) for _ in range(nb)]
+    rng = np.random.default_rng(0)
+    lam = np.exp((-rng.uniform(1e-4, 1, P) + 1j * rng.uniform(-3, 3, P)) * 0.01).astype(np.complex64)
+    dlam = torch.from_numpy(np.stack([lam.real, lam.imag], -1).copy()).to(dev)
+
+    def run(i, relu=0):
+        _abi.check(lib.s5b200_scan_c64(Bu[i % nb].data_ptr(), dlam.data_ptr(), xs[i % nb].data_ptr(), B, L, P, relu, ws[i % nb].data_ptr(),
+                                       C.c_size_t(need), st))
+
+    rec = {"B": B, "L": L, "P": P}
+    ref = {}
+    for mode in ("0", "1"):
+        os.environ["S5B200_SCAN_RESIDENT"] = mode
+        for relu in (0, 1):
+            run(0, relu); torch.cuda.synchronize()
+            if mode == "0":
+                ref[relu] = xs[0].clone()
+            else:
+                rec[f"bit_identical_relu{relu}"] = bool(torch.equal(ref[relu], xs[0]))
+        # in place
+        if mode == "1":
+            tmp = Bu[1].clone()
+            _abi.check(lib.s5b200_scan_c64(tmp.data_ptr(), dlam.data_ptr(), tmp.data_ptr(), B, L, P, 0, ws[1].data_ptr(), C.c_size_t(need), st))
+            run(1); torch.cuda.synchronize()
+            rec["in_place_identical"] = bool(torch.equal(tmp, xs[1]))
+        for i in range(3): run(i)
+        reps = 20
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(); e0.record()
+        for i in range(reps): run(i)
+        e1.record(); torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) / reps * 1e3
+        key = "resident" if mode == "1" else "ring"
+        rec[key + "_us"] = round(us, 2)
+        rec[key + "_frac"] = round(by / us / 1e3 / peak, 3)
+    print(json.dumps(rec), flush=True)
+    out.append(rec)
+    del Bu, xs, ws
+os.environ.pop("S5B200_SCAN_RESIDENT", None)
+if len(sys.argv) <= 3:
+    os.makedirs("gpurun_out", exist_ok=True)
+    json.dump(out, open("gpurun_out/scan_resident_ab.json", "w"), indent=1)

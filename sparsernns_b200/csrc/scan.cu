@@ -70,6 +70,13 @@ static int scan_nseg_bound(int B, int L) {
   const int nblocks = (L + scan_vlen(L) - 1) / scan_vlen(L);
   return std::max(1, std::min(nblocks, kSegMaxCtas / B));
 }
+// flags of a launch: [B][nseg] for the segmented ring kernel, [B][groups of 64 states][nblocks] for the resident form
+static size_t scan_flag_count(int B, int L, int P) {
+  const size_t nseg = (size_t)scan_nseg_bound(B, L);
+  if (nseg <= 1) return (size_t)B;
+  const size_t nblocks = (size_t)((L + scan_vlen(L) - 1) / scan_vlen(L));
+  return (size_t)B * std::max(nseg, nblocks * (size_t)((P + 63) / 64));
+}
 static ScanPlan scan_plan(int B, int L, int P, int resident_ctas) {
   ScanPlan g;
   g.threads = (P + 31) & ~31;
@@ -296,6 +303,158 @@ scan_c64_seg_kernel(const float2* __restrict__ Bu, const float2* __restrict__ la
     printf("[scan trace] seg %d/%d tiles %d: first tile %llu, phase1 end %llu, exchange %llu, phase2 %llu, drain %llu ns\n", sidx, nseg, ntiles,
            tr[1] - tr[0], tr[2] ? tr[2] - tr[0] : 0ull, tr[3] ? tr[3] - tr[2] : 0ull, tr[4] - (tr[3] ? tr[3] : tr[0]), tr[5] - tr[4]);
 #endif
+}
+
+
+// FEW CLIPS, RESIDENT FORM (round 2, last session).  The ring kernel above, cut into segments, reads an inner segment twice
+// (aggregate pass, then the real one) through a ring that keeps only two 8 KB tiles in flight per CTA: at 32 clips x 3751
+// frames it was latency bound (ncu: 0.54 waves of 64-thread CTAs, 9 % of the warp slots, DRAM 71 MB in / 15 MB out in 37 us).
+// Here ONE block of `vlen` steps x (up to) 64 states is a CTA's whole job and stays RESIDENT in shared memory (64 KB, three
+// CTAs per SM): all of its bulk copies are issued at once, the aggregate pass runs as the tiles land, the block publishes its
+// aggregate, combines the aggregates of the earlier blocks of its clip (the same in-order fp64 Horner as above - every bit is
+// the same as in the other scheduling modes), and the second pass runs out of shared memory and leaves by bulk stores tile by
+// tile.  HBM sees every byte once in, once out.  The grid is block-major (all clips' block k before any block k + 1) and is
+// NOT co-resident: a CTA waits only on lower block indices, which were dispatched before it and publish without waiting on
+// anything (the usual decoupled look-back assumption of in-order CTA dispatch).  P > 64 is split into groups of 64 states per
+// CTA whose rows move as 512-byte bulk copies.
+constexpr int kResG = 64;            // states per CTA
+constexpr int kResMaxTiles = 16;     // vlen <= 256
+template <bool RELU>
+__global__ void __launch_bounds__(kResG)
+scan_c64_res_kernel(const float2* __restrict__ Bu, const float2* __restrict__ lam, float2* xs, int L, int P, int B, int groups,
+                    int vlen, int nblocks, uint32_t* flags, double2* recs) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t full[kResMaxTiles];
+  const int p = threadIdx.x;
+  const int per = B * groups;
+  const int sidx = blockIdx.x / per, rem = blockIdx.x - sidx * per;   // block-major
+  const int b = rem / groups, g = rem - b * groups;
+  const int gw = min(kResG, P - g * kResG);                    // states of this group (even)
+  const bool active = p < gw;
+  const int gp = g * kResG + p;                                // global state index
+  const int t0 = sidx * vlen, rows_total = min(L - t0, vlen);
+  const int ntiles = (rows_total + kSegRows - 1) / kSegRows;
+  float2* tiles = reinterpret_cast<float2*>(smem_raw);         // [rows][gw]
+  const size_t base = ((size_t)b * L + t0) * P + (size_t)g * kResG;
+  const bool first = sidx == 0, last = sidx + 1 == nblocks;
+
+  if (p == 0) {
+    for (int j = 0; j < ntiles; ++j) mbar_init(&full[j], 1);
+    fence_mbar_init();
+    for (int j = 0; j < ntiles; ++j) {
+      const int rows = min(kSegRows, rows_total - j * kSegRows);
+      const uint32_t bytes = (uint32_t)rows * gw * 8u;
+      mbar_expect_tx(&full[j], bytes);
+      if (groups == 1) bulk_g2s(tiles + (size_t)j * kSegRows * gw, Bu + base + (size_t)j * kSegRows * P, bytes, &full[j]);
+    }
+  }
+  if (groups > 1) {                                            // strided rows: one 8 * gw byte copy per row, spread over the threads
+    __syncthreads();
+    for (int r = p; r < rows_total; r += kResG) bulk_g2s(tiles + (size_t)r * gw, Bu + base + (size_t)r * P, (uint32_t)gw * 8u, &full[r / kSegRows]);
+  } else {
+    __syncthreads();                                           // the barriers are initialised before anybody waits on them
+  }
+
+  const float2 a = active ? lam[gp] : make_float2(0.f, 0.f);
+  double2 aV = make_double2(1., 0.);
+  {
+    double2 sq = f2z(a);
+    for (int n = vlen; n > 0; n >>= 1) {
+      if (n & 1) aV = zmul(aV, sq);
+      sq = zmul(sq, sq);
+    }
+  }
+  uint32_t* flag_row = flags + ((size_t)b * groups + g) * nblocks;
+  double2* rec_row = recs + (size_t)b * nblocks * P;           // [block][P] aggregates of this clip
+
+  float2 xa = make_float2(0.f, 0.f);
+  if (!first && !last) {                                       // aggregate pass (inner blocks are always full)
+    for (int j = 0; j < ntiles; ++j) {
+      mbar_wait(&full[j], 0);
+      if (active) {
+        float2 v[kSegRows];
+        const float2* src = tiles + (size_t)j * kSegRows * gw + p;
+#pragma unroll
+        for (int t = 0; t < kSegRows; ++t) v[t] = src[t * gw];
+#pragma unroll
+        for (int t = 0; t < kSegRows; ++t) xa = cfma(a, xa, v[t]);
+      }
+    }
+    if (active) __stcg(rec_row + (size_t)sidx * P + gp, f2z(xa));
+    __syncthreads();                                           // the release below is cumulative over the barrier
+    if (p == 0) st_release_u32(flag_row + sidx, 1u);
+  }
+  double2 c = make_double2(0., 0.);
+  if (!first) {                                                // carry entering this block: Horner over the blocks 0 .. sidx - 1
+    for (int j0 = p; j0 < sidx; j0 += 4 * kResG) {
+      uint32_t f[4];
+#pragma unroll
+      for (int w = 0; w < 4; ++w) f[w] = j0 + w * kResG < sidx ? ld_relaxed_u32(flag_row + j0 + w * kResG) : 1u;
+#pragma unroll
+      for (int w = 0; w < 4; ++w)
+        while (f[w] == 0u) f[w] = ld_relaxed_u32(flag_row + j0 + w * kResG);
+    }
+    __syncthreads();
+    fence_acquire_gpu();
+    if (active) {
+      for (int j0 = 0; j0 < sidx; j0 += 16) {
+        double2 r[16];
+#pragma unroll
+        for (int w = 0; w < 16; ++w)
+          if (j0 + w < sidx) r[w] = __ldcg(rec_row + (size_t)(j0 + w) * P + gp);
+#pragma unroll
+        for (int w = 0; w < 16; ++w)
+          if (j0 + w < sidx) c = zfma(aV, c, r[w]);
+      }
+    }
+  }
+  float2 x = make_float2((float)c.x, (float)c.y);
+  for (int j = 0; j < ntiles; ++j) {
+    mbar_wait(&full[j], 0);                                    // returns at once when the aggregate pass has been here already
+    const int rows = min(kSegRows, rows_total - j * kSegRows);
+    float2* tile = tiles + (size_t)j * kSegRows * gw;
+    if (active) {
+      float2 v[kSegRows];
+      const float2* src = tile + p;
+      if (rows == kSegRows) {
+#pragma unroll
+        for (int t = 0; t < kSegRows; ++t) v[t] = src[t * gw];
+#pragma unroll
+        for (int t = 0; t < kSegRows; ++t) {
+          x = cfma(a, x, v[t]);
+          v[t] = x;
+        }
+#pragma unroll
+        for (int t = 0; t < kSegRows; ++t) tile[t * gw + p] = RELU ? relu_lex(v[t]) : v[t];
+      } else {
+#pragma unroll
+        for (int t = 0; t < kSegRows; ++t) v[t] = t < rows ? src[t * gw] : make_float2(0.f, 0.f);
+#pragma unroll
+        for (int t = 0; t < kSegRows; ++t)
+          if (t < rows) {
+            x = cfma(a, x, v[t]);
+            tile[t * gw + p] = RELU ? relu_lex(x) : x;
+          }
+      }
+    }
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (groups == 1) {
+      if (p == 0) {
+        bulk_s2g(xs + base + (size_t)j * kSegRows * P, tile, (uint32_t)rows * gw * 8u);
+        bulk_commit();
+      }
+    } else if (p < rows) {
+      bulk_s2g(xs + base + (size_t)(j * kSegRows + p) * P, tile + (size_t)p * gw, (uint32_t)gw * 8u);
+      bulk_commit();
+    }
+  }
+  if (first && !last) {                                        // block 0: its states from zero ARE its aggregate
+    if (active) __stcg(rec_row + gp, f2z(x));
+    __syncthreads();
+    if (p == 0) st_release_u32(flag_row, 1u);
+  }
+  bulk_wait_read0();                                           // the stores have read the tile (shared memory goes away at exit)
 }
 
 // ---------------------------------------------------------------------------------------------- int
@@ -941,9 +1100,28 @@ int launch_scan_c64(const float* Bu, const float* lam, float* xs, int B, int L, 
   S5_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, g.threads, g.smem_bytes));
   if (per_sm < 1) S5_FAIL(S5_E_CUDA, "scan_c64: no CTA fits an SM (%zu bytes of shared memory)", g.smem_bytes);
   g = scan_plan(B, L, P, std::min(kSegMaxCtas, per_sm * sm_count()));
-  const size_t flags_bytes = round_up((size_t)B * scan_nseg_bound(B, L) * sizeof(uint32_t), 256);
+  const size_t flags_bytes = round_up(scan_flag_count(B, L, P) * sizeof(uint32_t), 256);
   uint32_t* flags = reinterpret_cast<uint32_t*>(workspace);
   double2* recs = reinterpret_cast<double2*>(reinterpret_cast<unsigned char*>(workspace) + flags_bytes);
+  // Few clips: one resident block per CTA when a block fits shared memory (S5B200_SCAN_RESIDENT=0: the segmented ring kernel)
+  const char* res_env = getenv("S5B200_SCAN_RESIDENT");
+  // Measured (profiles/r02_scan_resident.md): 5-14 % faster than the ring kernel for P <= 64 and up to ~64 blocks per clip, slower for
+  // wider states (512-byte row copies) and for very long single clips (every CTA walks the whole look-back); S5B200_SCAN_RESIDENT=1 forces it.
+  const bool res_auto = P <= kResG && g.nblocks <= 64;
+  if (g.nseg > 1 && g.vlen <= kResMaxTiles * kSegRows && (res_env ? res_env[0] != '0' : res_auto)) {
+    const int groups = (P + kResG - 1) / kResG;
+    const long long grid = (long long)g.nblocks * B * groups;
+    if (grid > 0x7fffffffLL) S5_FAIL(S5_E_BADSHAPE, "scan_c64: too many clips");
+    const size_t smem = (size_t)g.vlen * std::min(P, kResG) * 8;
+    auto rk = relu ? scan_c64_res_kernel<true> : scan_c64_res_kernel<false>;
+    S5_CUDA(cudaFuncSetAttribute(rk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    S5_CUDA(cudaMemsetAsync(flags, 0, (size_t)B * groups * g.nblocks * sizeof(uint32_t), st));
+    ProfScope prof(S5_K_SCAN_C64, st);
+    rk<<<(unsigned)grid, kResG, smem, st>>>(reinterpret_cast<const float2*>(Bu), reinterpret_cast<const float2*>(lam),
+                                            reinterpret_cast<float2*>(xs), L, P, B, groups, g.vlen, g.nblocks, flags, recs);
+    S5_LAUNCH_CHECK();
+    return S5_OK;
+  }
   if (g.nseg > 1) S5_CUDA(cudaMemsetAsync(flags, 0, (size_t)B * g.nseg * sizeof(uint32_t), st));
   if ((long long)B * g.nseg > 0x7fffffffLL) S5_FAIL(S5_E_BADSHAPE, "scan_c64: too many clips");
   ProfScope prof(S5_K_SCAN_C64, st);
@@ -964,9 +1142,9 @@ int launch_scan_c64(const float* Bu, const float* lam, float* xs, int B, int L, 
 
 extern "C" size_t s5b200_scan_c64_workspace_bytes(int B, int L, int P) {
   if (B <= 0 || L <= 0 || P <= 0 || P > s5::kScanThreads) return 0;
-  const size_t nseg = (size_t)s5::scan_nseg_bound(B, L);      // flags [B][nseg] + block aggregates [B][nblocks][P] double2 (cut grids only)
+  const size_t nseg = (size_t)s5::scan_nseg_bound(B, L);      // flags + block aggregates [B][nblocks][P] double2 (cut grids only)
   const size_t nblocks = nseg > 1 ? (size_t)((L + s5::scan_vlen(L) - 1) / s5::scan_vlen(L)) : 0;
-  return s5::round_up((size_t)B * nseg * sizeof(uint32_t), 256) + (size_t)B * nblocks * P * sizeof(double2);
+  return s5::round_up(s5::scan_flag_count(B, L, P) * sizeof(uint32_t), 256) + (size_t)B * nblocks * P * sizeof(double2);
 }
 
 extern "C" int s5b200_scan_c64(const float* Bu, const float* lam, float* xs, int B, int L, int P, int relu,

@@ -71,6 +71,31 @@ def test_scan_c64_in_place_and_linearity(cuda_device):
     assert resid.abs().max() <= 1e-4 * ya.abs().max()
 
 
+@pytest.mark.parametrize("B,L,P,relu", [(32, 3751, 64, 0), (3, 1000, 100, 1), (2, 3751, 128, 1), (5, 300, 16, 0), (1, 20000, 64, 1),
+                                        (4, 3751, 256, 0), (7, 257, 2, 0)])
+def test_scan_c64_resident_equals_ring(cuda_device, monkeypatch, B, L, P, relu):
+    """Few clips: the resident form (one 128-step block per CTA kept in shared memory, scan_c64_res_kernel) and the segmented ring
+    kernel evaluate the same expression - equal bits, also in place, for state groups (P > 64), ragged last blocks and narrow states."""
+    import torch
+    from sparsernns_b200.model import scan_c64
+
+    rng = np.random.default_rng(B + L + P)
+    lam = torch.from_numpy(_lam(rng, P)).to(cuda_device)
+    Bu = torch.randn(B, L, P, dtype=torch.complex64, device=cuda_device)
+    monkeypatch.setenv("S5B200_SCAN_RESIDENT", "0")
+    ring = scan_c64(Bu, lam, relu=bool(relu))
+    monkeypatch.setenv("S5B200_SCAN_RESIDENT", "1")
+    res = scan_c64(Bu, lam, relu=bool(relu))
+    assert torch.equal(ring, res)
+    buf = Bu.clone()
+    scan_c64(buf, lam, out=buf, relu=bool(relu))
+    assert torch.equal(buf, ring)
+    ref = OS.scan_sequential(lam.cpu().numpy().astype(np.complex128), Bu[:1].cpu().numpy().astype(np.complex128))
+    if not relu:
+        assert np.abs(res[:1].cpu().numpy() - ref).max() <= TOL_C64 * np.abs(ref).max()
+
+
+
 def test_scan_c64_rejects_bad_shapes(cuda_device):
     import torch
     from sparsernns_b200 import _abi
