@@ -366,6 +366,8 @@ struct s5_model {
   cudaStream_t hs[4] = {nullptr, nullptr, nullptr, nullptr};   // H2D, D2H, two forward streams
   cudaEvent_t ev_h2d[kSlots] = {}, ev_cmp[kSlots] = {}, ev_d2h[kSlots] = {}, ev_user = nullptr, ev_done = nullptr;
   unsigned long long chunk_seq = 0;
+  void* last_user = nullptr;          // caller stream of the previous forward_host call
+  bool done_recorded = false;
 };
 
 namespace s5 {
@@ -884,6 +886,20 @@ static int forward_host_impl(const s5_model* mc, const float* x_host, float* y_h
     const int n = std::max(1, std::min(B, atoi(e)));
     const int cbu = (B + n - 1) / n;
     for (int b0 = 0; b0 < B; b0 += cbu) sched.push_back(std::min(cbu, B - b0));
+  } else if (!sync && m->done_recorded && m->last_user != stream && cudaEventQuery(m->ev_done) == cudaErrorNotReady) {
+    // The pipeline is already busy with the previous call, queued on ANOTHER caller stream (batches in flight on alternating
+    // streams): this call's first copy overlaps that call's tail, so the ramp-up below has nothing to hide and only costs
+    // small copies and small forwards.  Chunks of about 64 MB of input (16 NDNS clips) then run closest to the copy-only
+    // ceiling: 2.68-2.73 ms per 32-clip batch against 2.99 with the ramp and 2.59 copy-only (profiles/r02_e2e_pipelined.md).
+    const size_t clip_bytes = (size_t)L * m->desc.d_input * sizeof(float);
+    const int per = (int)std::max<size_t>(1, std::min<size_t>((size_t)B, ((size_t)64 << 20) / std::max<size_t>(1, clip_bytes)));
+    const int n = (B + per - 1) / per;
+    int rem = B;
+    for (int i = 0; i < n; ++i) {
+      const int take = (rem + (n - i) - 1) / (n - i);
+      sched.push_back(take);
+      rem -= take;
+    }
   } else {
     // The device-to-host direction is the bottleneck of the pipeline (measured: ~42 GB/s under bidirectional load),
     // so it should start as early as possible: ramp up 1, 1, 2, 4 clips, then chunks of about 6 that amortise the
@@ -969,6 +985,8 @@ static int forward_host_impl(const s5_model* mc, const float* x_host, float* y_h
   // the caller's stream continues after the last device-to-host copy (which is after everything else)
   S5_CUDA(cudaEventRecord(m->ev_done, s_out));
   S5_CUDA(cudaStreamWaitEvent(user, m->ev_done, 0));
+  m->done_recorded = true;
+  m->last_user = stream;
   if (sync || trace) {
     S5_CUDA(cudaStreamSynchronize(s_out));
     S5_CUDA(cudaStreamSynchronize(m->hs[2]));
