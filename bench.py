@@ -354,18 +354,19 @@ def main():
         n_samp = (L - 1) * 128
         ah = [(0.05 * torch.randn(B, n_samp)).pin_memory() for _ in range(2)]
         oh = [torch.empty(B, n_samp).pin_memory() for _ in range(2)]
-        nch = 4 if B % 4 == 0 else 1                                       # clip chunks over two streams: copies overlap kernels
-        streams = [torch.cuda.Stream(), torch.cuda.Stream()]
-        # one handle per stream: a BoundModel owns ONE workspace (look-back flags included), so two forwards in flight need two
-        models = [model, BoundModel(cfg, {"params": params, "batch_stats": batch_stats})]
+        nch = 4 if B % 4 == 0 else 1                                       # clip chunks, one stream each: copies overlap kernels
+        nst = 4 if nch == 4 else 1
+        streams = [torch.cuda.Stream() for _ in range(nst)]
+        # one handle per stream: a BoundModel owns ONE workspace (look-back flags included), so forwards in flight need their own
+        models = [model] + [BoundModel(cfg, {"params": params, "batch_stats": batch_stats}) for _ in range(nst - 1)]
 
         def audio_step(i):
             for c in range(nch):
-                with torch.cuda.stream(streams[c % 2]):
+                with torch.cuda.stream(streams[c % nst]):
                     sl = slice(c * B // nch, (c + 1) * B // nch)
                     a = ah[i % 2][sl].to(dev, non_blocking=True)
                     mag, ph, xin = ndns.stft_splitter(a, blf=True, model_input=True)
-                    cleaned = ndns.stft_mixer(mag, ph, blf=True, mask=models[c % 2](xin))
+                    cleaned = ndns.stft_mixer(mag, ph, blf=True, mask=models[c % nst](xin))
                     oh[i % 2][sl].copy_(cleaned, non_blocking=True)
 
         for i in range(2):
@@ -380,7 +381,7 @@ def main():
             dist.all_reduce(ea_s, op=dist.ReduceOp.MAX)
         e2e_audio = {"value": world * rows * ke / float(ea_s.item()), "unit": "frames/s", "h2d_bytes_per_step": B * n_samp * 4,
                      "d2h_bytes_per_step": B * n_samp * 4,
-                     "what": "audio -> STFT -> model -> mask apply + iSTFT -> audio, %d clip chunks on two streams (sparsernns_b200.ndns)" % nch}
+                     "what": "audio -> STFT -> model -> mask apply + iSTFT -> audio, %d clip chunks on %d streams (sparsernns_b200.ndns)" % (nch, nst)}
 
     # per-kernel device time (events recorded by the library around each launch); the end-to-end leg above leaves copies
     # on other streams behind: drain them and re-warm before timing single launches

@@ -181,14 +181,17 @@ int s5b200_layer_forward(const s5_model* m, int layer, const float* x, float* y,
 int s5b200_ssm_forward(const s5_model* m, int layer, const float* u, float* y, float* xs_out, int B, int L,
                        void* workspace, size_t workspace_bytes, void* stream);
 /* Same as s5b200_model_forward with HOST buffers (pinned for full speed): the batch flows in clip chunks through an
- * internal H2D | forward | D2H pipeline.  Host-synchronous: y_host is complete on return.  This is the call the
- * end-to-end benchmark times (bench.py "e2e"). */
+ * internal H2D | forward | D2H pipeline.  Host-synchronous: y_host is complete on return (bench.py
+ * "e2e.host_synchronous_value"). */
 int s5b200_model_forward_host(const s5_model* m, const float* x_host, float* y_host, int B, int L,
                               void* stream);
 /* Stream-ordered form of the same call: returns after enqueueing; `stream` is made to wait for the last
  * device-to-host copy, so y_host is complete once work queued on `stream` after this call has run (e.g. after
- * cudaStreamSynchronize(stream)).  x_host / y_host must stay valid until then.  Back-to-back calls overlap the
- * drain of one batch with the fill of the next. */
+ * cudaStreamSynchronize(stream)).  x_host / y_host must stay valid until then.  Calls on ONE stream are ordered
+ * like any CUDA work (batch i + 1 is copied in after batch i has been copied out); to keep both PCIe directions
+ * busy across batches, queue consecutive batches on two alternating streams - the library then sees that the
+ * previous call is still in flight and switches from its ramp-up chunk schedule to large chunks.  This is the loop the
+ * end-to-end benchmark times (bench.py "e2e.value": 44 M frames/s against 32 M host-synchronous on one B200). */
 int s5b200_model_forward_host_async(const s5_model* m, const float* x_host, float* y_host, int B, int L,
                                     void* stream);
 
@@ -303,7 +306,7 @@ int s5b200_stft(const float* audio, int B, int T, float* mag, float* phase, int 
                 float mag_sub, void* stream);
 /* stft_mixer, train_helpers.py:1399-1412, with the mask apply of :1605-1606 fused in: mask_blf (nullable) is the model
  * output (B, L, 257) and the spectrum magnitude becomes mag * (1 + mask); audio_out [B][(L - 1) * 128];
- * cleaned_mag_out (nullable, layout of mag) receives mag * (1 + mask). */
+ * cleaned_mag_out (nullable, layout of mag, must not alias an input) receives mag * (1 + mask). */
 int s5b200_istft(const float* mag, const float* phase, int layout_blf, const float* mask_blf, int B, int L,
                  float* audio_out, float* cleaned_mag_out, void* stream);
 /* workspace of the two per-clip reductions below */

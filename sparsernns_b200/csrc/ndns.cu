@@ -63,13 +63,18 @@ struct StftParams {
   float* model_in; float mag_sub;      // (B, L, 257) = mag - mag_sub
 };
 
-__global__ void __launch_bounds__(kNdThreads) stft_kernel(StftParams p) {
+// BLF (the model's (B, L, 257) layout): a frame's 257 bins are one contiguous row, so the warp that transformed the frame writes
+// magnitude, angle and model input straight from the split pass - no staging tile, 52 KB of shared memory per CTA, four CTAs
+// (32 warps) per SM instead of one (the first version staged every layout: 118 KB, 8 warps per SM, latency bound).  The
+// reference's (B, 257, L) layout still goes through the [32][257] staging tiles for its transposed write-out.
+template <bool BLF>
+__global__ void __launch_bounds__(kNdThreads, BLF ? 4 : 1) stft_kernel(StftParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   constexpr int kSeg = (kFB - 1) * kHop + kNfft;              // samples the CTA's frames cover
   float* seg = reinterpret_cast<float*>(smem);
   float2* tw = reinterpret_cast<float2*>(seg + kSeg);
   float2* work = tw + 256;                                    // [8 warps][2][256]
-  float* omag = reinterpret_cast<float*>(work + 8 * 512);     // [kFB][257]
+  float* omag = reinterpret_cast<float*>(work + 8 * 512);     // [kFB][257] (not BLF only)
   float* oph = omag + kFB * kBins;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.y, k0 = blockIdx.x * kFB, nf = min(kFB, p.L - k0);
@@ -81,6 +86,7 @@ __global__ void __launch_bounds__(kNdThreads) stft_kernel(StftParams p) {
     seg[i] = (t >= 0 && t < p.T) ? au[t] : 0.f;
   }
   __syncthreads();
+  const size_t clip_off = (size_t)b * p.L * kBins;
   float2* za = work + warp * 512;
   float2* zb = za + 256;
   for (int f = warp; f < nf; f += 8) {
@@ -97,22 +103,27 @@ __global__ void __launch_bounds__(kNdThreads) stft_kernel(StftParams p) {
       const float2 w = k < 256 ? tw[k] : make_float2(-1.f, 0.f);
       const float2 wo = cmul2(w, O);
       const float re = (E.x + wo.x) * (1.0f / kNfft), im = (E.y + wo.y) * (1.0f / kNfft);
-      omag[f * kBins + k] = hypotf(re, im);
-      oph[f * kBins + k] = atan2f(im, re);
+      const float mg = hypotf(re, im);
+      if (BLF) {
+        const size_t o = clip_off + (size_t)(k0 + f) * kBins + k;
+        if (p.mag) p.mag[o] = mg;
+        if (p.phase) p.phase[o] = atan2f(im, re);
+        if (p.model_in) p.model_in[o] = mg - p.mag_sub;
+      } else {
+        omag[f * kBins + k] = mg;
+        oph[f * kBins + k] = atan2f(im, re);
+      }
     }
     __syncwarp();
   }
+  if (BLF) return;
   __syncthreads();
-  // ---- write-out: rows of 257 floats (BLF, model input) are contiguous per frame; BFL is 32 consecutive frames per bin
-  const size_t clip_off = (size_t)b * p.L * kBins;
+  // ---- write-out: the model input is contiguous per frame; BFL is 32 consecutive frames per bin
   if (p.model_in) {
     float* dst = p.model_in + clip_off + (size_t)k0 * kBins;
     for (int i = tid; i < nf * kBins; i += kNdThreads) dst[i] = omag[i] - p.mag_sub;
   }
-  if (p.blf) {
-    if (p.mag) { float* dst = p.mag + clip_off + (size_t)k0 * kBins; for (int i = tid; i < nf * kBins; i += kNdThreads) dst[i] = omag[i]; }
-    if (p.phase) { float* dst = p.phase + clip_off + (size_t)k0 * kBins; for (int i = tid; i < nf * kBins; i += kNdThreads) dst[i] = oph[i]; }
-  } else {
+  {
     for (int k = warp; k < kBins; k += 8) {
       if (lane < nf) {
         const size_t o = clip_off + (size_t)k * p.L + k0 + lane;
@@ -132,40 +143,64 @@ struct IstftParams {
   float* cleaned_mag;                  // nullable, layout of mag
 };
 
-__global__ void __launch_bounds__(kNdThreads) istft_kernel(IstftParams p) {
+// 29 hops of output per CTA = 32 frames (rows) = two rounds of 16 warps; a warp's second FFT buffer is the spectrum row it has
+// just consumed, so the CTA needs 100 KB and two CTAs (32 warps) share an SM (first version: 35 rows over 8 warps, 16 warps per SM).
+constexpr int kIB = 29;            // hops per CTA (iSTFT)
+constexpr int kIsThreads = 512;
+__global__ void __launch_bounds__(kIsThreads, 2) istft_kernel(IstftParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
-  constexpr int kFr = kFB + 3;                                // frames that touch the CTA's 32 hops of output
+  constexpr int kFr = kIB + 3;                                // frames that touch the CTA's 29 hops of output
   constexpr int kRow = 260;                                   // float2 per spectrum row (257 bins, padded); 512 floats of time fit too
   float2* S = reinterpret_cast<float2*>(smem);                // [kFr][kRow] spectra, then (in place) the frames' time samples
   float2* tw = S + kFr * kRow;
-  float2* work = tw + 256;                                    // [8][2][256]
+  float2* work = tw + 256;                                    // [16][256]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int b = blockIdx.y, h0 = blockIdx.x * kFB;            // output hops h0 .. h0 + 31 (padded coordinates)
+  const int b = blockIdx.y, h0 = blockIdx.x * kIB;            // output hops h0 .. h0 + 28 (padded coordinates)
   const int f_lo = h0 - 3;                                    // frame of S row 0
   make_twiddles(tw);
   const size_t clip_off = (size_t)b * p.L * kBins;
   // ---- load: magnitude (* (1 + mask)), angle -> complex spectrum rows
   if (p.blf) {
-    for (int i = tid; i < kFr * kBins; i += kNdThreads) {
-      const int r = i / kBins, k = i - r * kBins, f = f_lo + r;
-      if (f < 0 || f >= p.L) continue;
-      const size_t o = clip_off + (size_t)f * kBins + k;
-      float m = p.mag[o];
-      if (p.mask) m *= 1.0f + p.mask[o];
-      // this CTA owns the cleaned magnitude of the frames that START in its hops (f >= h0)
-      if (p.cleaned_mag && f >= h0 && f < h0 + kFB) p.cleaned_mag[o] = m;
-      float s, c;
-      sincosf(p.phase[o], &s, &c);
-      S[r * kRow + k] = make_float2(m * c, m * s);
+    // four elements per thread and pass, all of their loads issued before the first sincos (12 requests in flight per thread)
+    constexpr int kU = 4;
+    const float* __restrict__ gmag = p.mag;
+    const float* __restrict__ gph = p.phase;
+    const float* __restrict__ gmask = p.mask;
+    for (int i0 = tid; i0 < kFr * kBins; i0 += kIsThreads * kU) {
+      float m[kU], ph[kU], mk[kU];
+      int f[kU], sidx[kU];
+      size_t o[kU];
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const int i = i0 + u * kIsThreads, r = i / kBins, k = i - r * kBins;
+        f[u] = i < kFr * kBins ? f_lo + r : -1;
+        sidx[u] = r * kRow + k;
+        o[u] = clip_off + (size_t)max(f[u], 0) * kBins + k;
+        const bool ok = f[u] >= 0 && f[u] < p.L;
+        m[u] = ok ? gmag[o[u]] : 0.f;
+        ph[u] = ok ? gph[o[u]] : 0.f;
+        mk[u] = ok && gmask ? gmask[o[u]] : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        if (f[u] < 0 || f[u] >= p.L) continue;
+        float mm = m[u];
+        if (gmask) mm *= 1.0f + mk[u];
+        // this CTA owns the cleaned magnitude of the frames that START in its hops (f >= h0)
+        if (p.cleaned_mag && f[u] >= h0 && f[u] < h0 + kIB) p.cleaned_mag[o[u]] = mm;
+        float sn, cs;
+        sincosf(ph[u], &sn, &cs);
+        S[sidx[u]] = make_float2(mm * cs, mm * sn);
+      }
     }
   } else {
-    for (int i = tid; i < kBins * 64; i += kNdThreads) {      // lanes along frames (contiguous in the (B, 257, L) layout)
+    for (int i = tid; i < kBins * 64; i += kIsThreads) {      // lanes along frames (contiguous in the (B, 257, L) layout)
       const int k = i >> 6, r = i & 63, f = f_lo + r;
       if (r >= kFr || f < 0 || f >= p.L) continue;
       const size_t o = clip_off + (size_t)k * p.L + f;
       float m = p.mag[o];
       if (p.mask) m *= 1.0f + p.mask[clip_off + (size_t)f * kBins + k];
-      if (p.cleaned_mag && f >= h0 && f < h0 + kFB) p.cleaned_mag[o] = m;
+      if (p.cleaned_mag && f >= h0 && f < h0 + kIB) p.cleaned_mag[o] = m;
       float s, c;
       sincosf(p.phase[o], &s, &c);
       S[r * kRow + k] = make_float2(m * c, m * s);
@@ -173,12 +208,12 @@ __global__ void __launch_bounds__(kNdThreads) istft_kernel(IstftParams p) {
   }
   __syncthreads();
   // ---- per frame: merge to the 256-point spectrum of x[2n] + i x[2n+1], inverse FFT, time samples back into the row
-  float2* za = work + warp * 512;
-  float2* zb = za + 256;
-  for (int r = warp; r < kFr; r += 8) {
+  float2* za = work + warp * 256;
+  for (int r = warp; r < kFr; r += kIsThreads / 32) {
     const int f = f_lo + r;
     if (f < 0 || f >= p.L) continue;                          // warp-uniform
     float2* row = S + r * kRow;
+    float2* zb = row;                                         // the row is dead once it has been merged into za
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
       const int k = lane + 32 * q;
@@ -203,7 +238,7 @@ __global__ void __launch_bounds__(kNdThreads) istft_kernel(IstftParams p) {
   // ---- overlap-add in frame order, divide by the number of covering frames, trim 256 samples either side
   const int out_len = (p.L - 1) * kHop;
   const float* Sf = reinterpret_cast<const float*>(S);
-  for (int i = tid; i < kFB * kHop; i += kNdThreads) {
+  for (int i = tid; i < kIB * kHop; i += kIsThreads) {
     const int h = h0 + (i >> 7), within = i & 127;
     const long long t = (long long)h * kHop + within - kNfft / 2;   // output index
     if (t < 0 || t >= out_len) continue;
@@ -310,10 +345,11 @@ extern "C" int s5b200_stft(const float* audio, int B, int T, float* mag, float* 
   if (!audio || (!mag && !phase && !model_in)) S5_FAIL(S5_E_BADARG, "stft: null pointer");
   if (B <= 0 || T <= 0 || B > 65535) S5_FAIL(S5_E_BADSHAPE, "stft: B=%d T=%d outside the supported range", B, T);
   StftParams p{audio, B, T, s5b200_stft_frames(T), mag, phase, layout_blf, model_in, mag_sub};
-  const size_t smem = (size_t)((kFB - 1) * kHop + kNfft) * 4 + 256 * 8 + 8 * 512 * 8 + 2 * (size_t)kFB * kBins * 4;
-  S5_CUDA(cudaFuncSetAttribute(stft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const size_t smem = (size_t)((kFB - 1) * kHop + kNfft) * 4 + 256 * 8 + 8 * 512 * 8 + (layout_blf ? 0 : 2 * (size_t)kFB * kBins * 4);
+  auto kern = layout_blf ? stft_kernel<true> : stft_kernel<false>;
+  S5_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   ProfScope prof(S5_K_OTHER, (cudaStream_t)stream);
-  stft_kernel<<<dim3((p.L + kFB - 1) / kFB, B), kNdThreads, smem, (cudaStream_t)stream>>>(p);
+  kern<<<dim3((p.L + kFB - 1) / kFB, B), kNdThreads, smem, (cudaStream_t)stream>>>(p);
   S5_LAUNCH_CHECK();
   return S5_OK;
 }
@@ -322,12 +358,15 @@ extern "C" int s5b200_istft(const float* mag, const float* phase, int layout_blf
                             float* cleaned_mag_out, void* stream) {
   if (!mag || !phase || !audio_out) S5_FAIL(S5_E_BADARG, "istft: null pointer");
   if (B <= 0 || L < 2 || B > 65535) S5_FAIL(S5_E_BADSHAPE, "istft: B=%d L=%d outside the supported range", B, L);
+  // a CTA also reads the three frames before its own hops, which another CTA owns and would overwrite
+  if (cleaned_mag_out && (cleaned_mag_out == mag || cleaned_mag_out == phase || cleaned_mag_out == mask_blf))
+    S5_FAIL(S5_E_BADARG, "istft: cleaned_mag_out must not alias an input");
   IstftParams p{mag, phase, layout_blf, mask_blf, B, L, audio_out, cleaned_mag_out};
-  const size_t smem = (size_t)(kFB + 3) * 260 * 8 + 256 * 8 + 8 * 512 * 8;
+  const size_t smem = (size_t)(kIB + 3) * 260 * 8 + 256 * 8 + (kIsThreads / 32) * 256 * 8;
   S5_CUDA(cudaFuncSetAttribute(istft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // hops 0 .. L + 2 carry output samples (frame L - 1 ends at hop L + 2)
   ProfScope prof(S5_K_OTHER, (cudaStream_t)stream);
-  istft_kernel<<<dim3((L + 3 + kFB - 1) / kFB, B), kNdThreads, smem, (cudaStream_t)stream>>>(p);
+  istft_kernel<<<dim3((L + 3 + kIB - 1) / kIB, B), kIsThreads, smem, (cudaStream_t)stream>>>(p);
   S5_LAUNCH_CHECK();
   return S5_OK;
 }
