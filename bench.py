@@ -160,6 +160,12 @@ def reference_arm(args, rank, world):
     import numpy as np
     from sparsernns_b200 import synth
 
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; the reference arm runs alone on rank 0 and may use every host core
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=os.cpu_count() or 1)
+    except Exception:
+        pass
     dims = synth.ndns_dims(args.dim_scale)
     params, batch_stats, _ = load_fixture(args.dim_scale)
     fwd = cpu_port_forward_fn(params, batch_stats, dims)
