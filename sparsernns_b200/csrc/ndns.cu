@@ -24,7 +24,12 @@ constexpr int kNdThreads = 256;
 __device__ __forceinline__ float2 cmul2(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 
 // 256-point complex FFT, one warp, ping-pong buffers in shared memory; 8 stages, so the result ends in `a`.
-// tw[k] = exp(-2 pi i k / 512), k < 256.  INV: conjugated twiddles (un-normalised inverse).
+// Twiddles: ONE TABLE PER STAGE, stage s (Ns = 2^s butterflies wide) at offset Ns - 1 with entry r = exp(-i pi r / Ns), so the
+// lanes of a warp read consecutive (or repeated) words.  The first version indexed one table exp(-2 pi i k / 512) with
+// k = r << (8 - s): a stride of 2^(8 - s) entries, up to 16 lanes on one bank - ncu showed the iSTFT at 79 % of the
+// shared-memory wavefront peak with 36.6 M bank conflicts.  The values are the same bits (same sincospif argument).
+// INV: conjugated twiddles (un-normalised inverse).  kTwFull: the stage-8 table = exp(-2 pi i k / 512), k < 256 (split / merge).
+constexpr int kTwEntries = 511, kTwFull = 255;
 template <bool INV>
 __device__ __forceinline__ void fft256_warp(float2* a, float2* b, const float2* tw, int lane) {
   float2* in = a;
@@ -36,12 +41,16 @@ __device__ __forceinline__ void fft256_warp(float2* a, float2* b, const float2* 
     for (int q = 0; q < 4; ++q) {
       const int j = lane + 32 * q, r = j & (Ns - 1);
       const float2 u = in[j];
-      float2 w = tw[r << (8 - s)];
+      float2 w = tw[(Ns - 1) + r];
       if (INV) w.y = -w.y;
       const float2 v = cmul2(in[j + 128], w);
       const int j0 = ((j - r) << 1) + r;
-      out[j0] = make_float2(u.x + v.x, u.y + v.y);
-      out[j0 + Ns] = make_float2(u.x - v.x, u.y - v.y);
+      if (s == 0) {                                            // out[2 j], out[2 j + 1]: one 16-byte store
+        *reinterpret_cast<float4*>(out + j0) = make_float4(u.x + v.x, u.y + v.y, u.x - v.x, u.y - v.y);
+      } else {
+        out[j0] = make_float2(u.x + v.x, u.y + v.y);
+        out[j0 + Ns] = make_float2(u.x - v.x, u.y - v.y);
+      }
     }
     __syncwarp();
     float2* t = in; in = out; out = t;
@@ -49,10 +58,11 @@ __device__ __forceinline__ void fft256_warp(float2* a, float2* b, const float2* 
 }
 
 __device__ __forceinline__ void make_twiddles(float2* tw) {
-  for (int k = threadIdx.x; k < 256; k += blockDim.x) {
-    float s, c;
-    sincospif((float)k * (1.0f / 256.0f), &s, &c);            // exp(-i pi k / 256)
-    tw[k] = make_float2(c, -s);
+  for (int i = threadIdx.x; i < kTwEntries; i += blockDim.x) {
+    const int s = 31 - __clz(i + 1), r = i + 1 - (1 << s);    // stage and entry
+    float sn, cs;
+    sincospif((float)(r << (8 - s)) * (1.0f / 256.0f), &sn, &cs);   // exp(-i pi k / 256), k = r 2^(8 - s)
+    tw[i] = make_float2(cs, -sn);
   }
 }
 
@@ -73,7 +83,7 @@ __global__ void __launch_bounds__(kNdThreads, BLF ? 4 : 1) stft_kernel(StftParam
   constexpr int kSeg = (kFB - 1) * kHop + kNfft;              // samples the CTA's frames cover
   float* seg = reinterpret_cast<float*>(smem);
   float2* tw = reinterpret_cast<float2*>(seg + kSeg);
-  float2* work = tw + 256;                                    // [8 warps][2][256]
+  float2* work = tw + 512;                                    // [8 warps][2][256]
   float* omag = reinterpret_cast<float*>(work + 8 * 512);     // [kFB][257] (not BLF only)
   float* oph = omag + kFB * kBins;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -100,7 +110,7 @@ __global__ void __launch_bounds__(kNdThreads, BLF ? 4 : 1) stft_kernel(StftParam
       const float2 zk = za[k & 255], zc = za[(256 - k) & 255];
       const float2 E = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y - zc.y));
       const float2 O = make_float2(0.5f * (zk.y + zc.y), -0.5f * (zk.x - zc.x));
-      const float2 w = k < 256 ? tw[k] : make_float2(-1.f, 0.f);
+      const float2 w = k < 256 ? tw[kTwFull + k] : make_float2(-1.f, 0.f);
       const float2 wo = cmul2(w, O);
       const float re = (E.x + wo.x) * (1.0f / kNfft), im = (E.y + wo.y) * (1.0f / kNfft);
       const float mg = hypotf(re, im);
@@ -153,7 +163,7 @@ __global__ void __launch_bounds__(kIsThreads, 2) istft_kernel(IstftParams p) {
   constexpr int kRow = 260;                                   // float2 per spectrum row (257 bins, padded); 512 floats of time fit too
   float2* S = reinterpret_cast<float2*>(smem);                // [kFr][kRow] spectra, then (in place) the frames' time samples
   float2* tw = S + kFr * kRow;
-  float2* work = tw + 256;                                    // [16][256]
+  float2* work = tw + 512;                                    // [16][256]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.y, h0 = blockIdx.x * kIB;            // output hops h0 .. h0 + 28 (padded coordinates)
   const int f_lo = h0 - 3;                                    // frame of S row 0
@@ -221,7 +231,7 @@ __global__ void __launch_bounds__(kIsThreads, 2) istft_kernel(IstftParams p) {
       if (k == 0) { xk.y = 0.f; xc.y = 0.f; }                 // irfft ignores the imaginary parts of DC and Nyquist
       const float2 E = make_float2(0.5f * (xk.x + xc.x), 0.5f * (xk.y - xc.y));
       const float2 D = make_float2(0.5f * (xk.x - xc.x), 0.5f * (xk.y + xc.y));
-      const float2 w = make_float2(tw[k].x, -tw[k].y);       // exp(+2 pi i k / 512)
+      const float2 w = make_float2(tw[kTwFull + k].x, -tw[kTwFull + k].y);   // exp(+2 pi i k / 512)
       const float2 O = cmul2(D, w);
       za[k] = make_float2(E.x - O.y, E.y + O.x);              // Z = E + i O
     }
@@ -345,7 +355,7 @@ extern "C" int s5b200_stft(const float* audio, int B, int T, float* mag, float* 
   if (!audio || (!mag && !phase && !model_in)) S5_FAIL(S5_E_BADARG, "stft: null pointer");
   if (B <= 0 || T <= 0 || B > 65535) S5_FAIL(S5_E_BADSHAPE, "stft: B=%d T=%d outside the supported range", B, T);
   StftParams p{audio, B, T, s5b200_stft_frames(T), mag, phase, layout_blf, model_in, mag_sub};
-  const size_t smem = (size_t)((kFB - 1) * kHop + kNfft) * 4 + 256 * 8 + 8 * 512 * 8 + (layout_blf ? 0 : 2 * (size_t)kFB * kBins * 4);
+  const size_t smem = (size_t)((kFB - 1) * kHop + kNfft) * 4 + 512 * 8 + 8 * 512 * 8 + (layout_blf ? 0 : 2 * (size_t)kFB * kBins * 4);
   auto kern = layout_blf ? stft_kernel<true> : stft_kernel<false>;
   S5_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   ProfScope prof(S5_K_OTHER, (cudaStream_t)stream);
@@ -362,7 +372,7 @@ extern "C" int s5b200_istft(const float* mag, const float* phase, int layout_blf
   if (cleaned_mag_out && (cleaned_mag_out == mag || cleaned_mag_out == phase || cleaned_mag_out == mask_blf))
     S5_FAIL(S5_E_BADARG, "istft: cleaned_mag_out must not alias an input");
   IstftParams p{mag, phase, layout_blf, mask_blf, B, L, audio_out, cleaned_mag_out};
-  const size_t smem = (size_t)(kIB + 3) * 260 * 8 + 256 * 8 + (kIsThreads / 32) * 256 * 8;
+  const size_t smem = (size_t)(kIB + 3) * 260 * 8 + 512 * 8 + (kIsThreads / 32) * 256 * 8;
   S5_CUDA(cudaFuncSetAttribute(istft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // hops 0 .. L + 2 carry output samples (frame L - 1 ends at hop L + 2)
   ProfScope prof(S5_K_OTHER, (cudaStream_t)stream);
