@@ -30,16 +30,18 @@ for B, L, P in shapes:
 
     rec = {"B": B, "L": L, "P": P}
     ref = {}
-    for mode in ("0", "1"):
+    for mode, resg in (("0", None), ("1", "64")):
         os.environ["S5B200_SCAN_RESIDENT"] = mode
+        if resg:
+            os.environ["S5B200_SCAN_RES_G"] = resg
         for relu in (0, 1):
             run(0, relu); torch.cuda.synchronize()
             if mode == "0":
                 ref[relu] = xs[0].clone()
             else:
-                rec[f"bit_identical_relu{relu}"] = bool(torch.equal(ref[relu], xs[0]))
+                rec[f"bit_identical_relu{relu}"] = rec.get(f"bit_identical_relu{relu}", True) and bool(torch.equal(ref[relu], xs[0]))
         # in place
-        if mode == "1":
+        if mode == "1" and resg == "64":
             tmp = Bu[1].clone()
             _abi.check(lib.s5b200_scan_c64(tmp.data_ptr(), dlam.data_ptr(), tmp.data_ptr(), B, L, P, 0, ws[1].data_ptr(), C.c_size_t(need), st))
             run(1); torch.cuda.synchronize()
@@ -51,13 +53,14 @@ for B, L, P in shapes:
         for i in range(reps): run(i)
         e1.record(); torch.cuda.synchronize()
         us = e0.elapsed_time(e1) / reps * 1e3
-        key = "resident" if mode == "1" else "ring"
+        key = ("resident" + resg) if mode == "1" else "ring"
         rec[key + "_us"] = round(us, 2)
         rec[key + "_frac"] = round(by / us / 1e3 / peak, 3)
     print(json.dumps(rec), flush=True)
     out.append(rec)
     del Bu, xs, ws
 os.environ.pop("S5B200_SCAN_RESIDENT", None)
+os.environ.pop("S5B200_SCAN_RES_G", None)
 if len(sys.argv) <= 3:
     os.makedirs("gpurun_out", exist_ok=True)
     json.dump(out, open("gpurun_out/scan_resident_ab.json", "w"), indent=1)

@@ -75,7 +75,7 @@ static size_t scan_flag_count(int B, int L, int P) {
   const size_t nseg = (size_t)scan_nseg_bound(B, L);
   if (nseg <= 1) return (size_t)B;
   const size_t nblocks = (size_t)((L + scan_vlen(L) - 1) / scan_vlen(L));
-  return (size_t)B * std::max(nseg, nblocks * (size_t)((P + 63) / 64));
+  return (size_t)B * std::max(nseg, nblocks * (size_t)((P + 31) / 32));
 }
 static ScanPlan scan_plan(int B, int L, int P, int resident_ctas) {
   ScanPlan g;
@@ -305,157 +305,6 @@ scan_c64_seg_kernel(const float2* __restrict__ Bu, const float2* __restrict__ la
 #endif
 }
 
-
-// FEW CLIPS, RESIDENT FORM (round 2, last session).  The ring kernel above, cut into segments, reads an inner segment twice
-// (aggregate pass, then the real one) through a ring that keeps only two 8 KB tiles in flight per CTA: at 32 clips x 3751
-// frames it was latency bound (ncu: 0.54 waves of 64-thread CTAs, 9 % of the warp slots, DRAM 71 MB in / 15 MB out in 37 us).
-// Here ONE block of `vlen` steps x (up to) 64 states is a CTA's whole job and stays RESIDENT in shared memory (64 KB, three
-// CTAs per SM): all of its bulk copies are issued at once, the aggregate pass runs as the tiles land, the block publishes its
-// aggregate, combines the aggregates of the earlier blocks of its clip (the same in-order fp64 Horner as above - every bit is
-// the same as in the other scheduling modes), and the second pass runs out of shared memory and leaves by bulk stores tile by
-// tile.  HBM sees every byte once in, once out.  The grid is block-major (all clips' block k before any block k + 1) and is
-// NOT co-resident: a CTA waits only on lower block indices, which were dispatched before it and publish without waiting on
-// anything (the usual decoupled look-back assumption of in-order CTA dispatch).  P > 64 is split into groups of 64 states per
-// CTA whose rows move as 512-byte bulk copies.
-constexpr int kResG = 64;            // states per CTA
-constexpr int kResMaxTiles = 16;     // vlen <= 256
-template <bool RELU>
-__global__ void __launch_bounds__(kResG)
-scan_c64_res_kernel(const float2* __restrict__ Bu, const float2* __restrict__ lam, float2* xs, int L, int P, int B, int groups,
-                    int vlen, int nblocks, uint32_t* flags, double2* recs) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ __align__(8) uint64_t full[kResMaxTiles];
-  const int p = threadIdx.x;
-  const int per = B * groups;
-  const int sidx = blockIdx.x / per, rem = blockIdx.x - sidx * per;   // block-major
-  const int b = rem / groups, g = rem - b * groups;
-  const int gw = min(kResG, P - g * kResG);                    // states of this group (even)
-  const bool active = p < gw;
-  const int gp = g * kResG + p;                                // global state index
-  const int t0 = sidx * vlen, rows_total = min(L - t0, vlen);
-  const int ntiles = (rows_total + kSegRows - 1) / kSegRows;
-  float2* tiles = reinterpret_cast<float2*>(smem_raw);         // [rows][gw]
-  const size_t base = ((size_t)b * L + t0) * P + (size_t)g * kResG;
-  const bool first = sidx == 0, last = sidx + 1 == nblocks;
-
-  if (p == 0) {
-    for (int j = 0; j < ntiles; ++j) mbar_init(&full[j], 1);
-    fence_mbar_init();
-    for (int j = 0; j < ntiles; ++j) {
-      const int rows = min(kSegRows, rows_total - j * kSegRows);
-      const uint32_t bytes = (uint32_t)rows * gw * 8u;
-      mbar_expect_tx(&full[j], bytes);
-      if (groups == 1) bulk_g2s(tiles + (size_t)j * kSegRows * gw, Bu + base + (size_t)j * kSegRows * P, bytes, &full[j]);
-    }
-  }
-  if (groups > 1) {                                            // strided rows: one 8 * gw byte copy per row, spread over the threads
-    __syncthreads();
-    for (int r = p; r < rows_total; r += kResG) bulk_g2s(tiles + (size_t)r * gw, Bu + base + (size_t)r * P, (uint32_t)gw * 8u, &full[r / kSegRows]);
-  } else {
-    __syncthreads();                                           // the barriers are initialised before anybody waits on them
-  }
-
-  const float2 a = active ? lam[gp] : make_float2(0.f, 0.f);
-  double2 aV = make_double2(1., 0.);
-  {
-    double2 sq = f2z(a);
-    for (int n = vlen; n > 0; n >>= 1) {
-      if (n & 1) aV = zmul(aV, sq);
-      sq = zmul(sq, sq);
-    }
-  }
-  uint32_t* flag_row = flags + ((size_t)b * groups + g) * nblocks;
-  double2* rec_row = recs + (size_t)b * nblocks * P;           // [block][P] aggregates of this clip
-
-  float2 xa = make_float2(0.f, 0.f);
-  if (!first && !last) {                                       // aggregate pass (inner blocks are always full)
-    for (int j = 0; j < ntiles; ++j) {
-      mbar_wait(&full[j], 0);
-      if (active) {
-        float2 v[kSegRows];
-        const float2* src = tiles + (size_t)j * kSegRows * gw + p;
-#pragma unroll
-        for (int t = 0; t < kSegRows; ++t) v[t] = src[t * gw];
-#pragma unroll
-        for (int t = 0; t < kSegRows; ++t) xa = cfma(a, xa, v[t]);
-      }
-    }
-    if (active) __stcg(rec_row + (size_t)sidx * P + gp, f2z(xa));
-    __syncthreads();                                           // the release below is cumulative over the barrier
-    if (p == 0) st_release_u32(flag_row + sidx, 1u);
-  }
-  double2 c = make_double2(0., 0.);
-  if (!first) {                                                // carry entering this block: Horner over the blocks 0 .. sidx - 1
-    for (int j0 = p; j0 < sidx; j0 += 4 * kResG) {
-      uint32_t f[4];
-#pragma unroll
-      for (int w = 0; w < 4; ++w) f[w] = j0 + w * kResG < sidx ? ld_relaxed_u32(flag_row + j0 + w * kResG) : 1u;
-#pragma unroll
-      for (int w = 0; w < 4; ++w)
-        while (f[w] == 0u) f[w] = ld_relaxed_u32(flag_row + j0 + w * kResG);
-    }
-    __syncthreads();
-    fence_acquire_gpu();
-    if (active) {
-      for (int j0 = 0; j0 < sidx; j0 += 16) {
-        double2 r[16];
-#pragma unroll
-        for (int w = 0; w < 16; ++w)
-          if (j0 + w < sidx) r[w] = __ldcg(rec_row + (size_t)(j0 + w) * P + gp);
-#pragma unroll
-        for (int w = 0; w < 16; ++w)
-          if (j0 + w < sidx) c = zfma(aV, c, r[w]);
-      }
-    }
-  }
-  float2 x = make_float2((float)c.x, (float)c.y);
-  for (int j = 0; j < ntiles; ++j) {
-    mbar_wait(&full[j], 0);                                    // returns at once when the aggregate pass has been here already
-    const int rows = min(kSegRows, rows_total - j * kSegRows);
-    float2* tile = tiles + (size_t)j * kSegRows * gw;
-    if (active) {
-      float2 v[kSegRows];
-      const float2* src = tile + p;
-      if (rows == kSegRows) {
-#pragma unroll
-        for (int t = 0; t < kSegRows; ++t) v[t] = src[t * gw];
-#pragma unroll
-        for (int t = 0; t < kSegRows; ++t) {
-          x = cfma(a, x, v[t]);
-          v[t] = x;
-        }
-#pragma unroll
-        for (int t = 0; t < kSegRows; ++t) tile[t * gw + p] = RELU ? relu_lex(v[t]) : v[t];
-      } else {
-#pragma unroll
-        for (int t = 0; t < kSegRows; ++t) v[t] = t < rows ? src[t * gw] : make_float2(0.f, 0.f);
-#pragma unroll
-        for (int t = 0; t < kSegRows; ++t)
-          if (t < rows) {
-            x = cfma(a, x, v[t]);
-            tile[t * gw + p] = RELU ? relu_lex(x) : x;
-          }
-      }
-    }
-    fence_proxy_async_smem();
-    __syncthreads();
-    if (groups == 1) {
-      if (p == 0) {
-        bulk_s2g(xs + base + (size_t)j * kSegRows * P, tile, (uint32_t)rows * gw * 8u);
-        bulk_commit();
-      }
-    } else if (p < rows) {
-      bulk_s2g(xs + base + (size_t)(j * kSegRows + p) * P, tile + (size_t)p * gw, (uint32_t)gw * 8u);
-      bulk_commit();
-    }
-  }
-  if (first && !last) {                                        // block 0: its states from zero ARE its aggregate
-    if (active) __stcg(rec_row + gp, f2z(x));
-    __syncthreads();
-    if (p == 0) st_release_u32(flag_row, 1u);
-  }
-  bulk_wait_read0();                                           // the stores have read the tile (shared memory goes away at exit)
-}
 
 // ---------------------------------------------------------------------------------------------- int
 // int32 product with two's-complement wrap-around (what jnp gives in 32-bit mode)
@@ -848,6 +697,147 @@ __device__ __forceinline__ void tma3d_store(const CUtensorMap* tm, int c0, int c
                : "memory");
 }
 
+// FEW CLIPS, RESIDENT FORM (round 2, last session).  The ring kernel above, cut into segments, reads an inner segment twice
+// (aggregate pass, then the real one) through a ring that keeps only two 8 KB tiles in flight per CTA: at 32 clips x 3751
+// frames it was latency bound (ncu: 0.54 waves of 64-thread CTAs, 9 % of the warp slots, DRAM 71 MB in / 15 MB out in 37 us).
+// Here ONE block of `vlen` steps x (up to) 64 states is a CTA's whole job and stays RESIDENT in shared memory (64 KB, three
+// CTAs per SM): all of its bulk copies are issued at once, the aggregate pass runs as the tiles land, the block publishes its
+// aggregate, combines the aggregates of the earlier blocks of its clip (the same in-order fp64 Horner as above - every bit is
+// the same as in the other scheduling modes), and the second pass runs out of shared memory and leaves by bulk stores tile by
+// tile.  HBM sees every byte once in, once out.  The grid is block-major (all clips' block k before any block k + 1) and is
+// NOT co-resident: a CTA waits only on lower block indices, which were dispatched before it and publish without waiting on
+// anything (the usual decoupled look-back assumption of in-order CTA dispatch).  P > 64 is split into groups of 64 states per
+// CTA.  A [16 steps][64 states] tile is a box of the [B][L][P] array and moves by 3-D TENSOR-MAP bulk copies (dims {2P floats, L, B}):
+// one instruction per tile whatever P is (512-byte row copies made the P = 128 case slower than the ring kernel), rows past the
+// end of a clip and states past P are zero-filled on load and clipped on store.
+constexpr int kResG = 64;            // states per CTA (at most; 32 when that saves a wave of CTAs)
+constexpr int kResMaxTiles = 16;     // vlen <= 256
+template <bool RELU, int G>
+__global__ void __launch_bounds__(G)
+scan_c64_res_kernel(const __grid_constant__ CUtensorMap tin, const __grid_constant__ CUtensorMap tout, const float2* __restrict__ lam, int L,
+                    int P, int B, int groups, int gw, int vlen, int nblocks, uint32_t* flags, double2* recs) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t full[kResMaxTiles];
+  const int p = threadIdx.x;
+  const int per = B * groups;
+  const int sidx = blockIdx.x / per, rem = blockIdx.x - sidx * per;   // block-major
+  const int b = rem / groups, g = rem - b * groups;
+  const int gp = g * G + p;                                // global state index; gw = states per tile row = min(P, 64)
+  const bool active = p < gw && gp < P;
+  const int t0 = sidx * vlen, rows_total = min(L - t0, vlen);
+  const int ntiles = (rows_total + kSegRows - 1) / kSegRows;
+  float2* tiles = reinterpret_cast<float2*>(smem_raw);         // [rows][gw]
+  const int c0 = 2 * g * G;                                // first float of the group within a time step
+  const bool first = sidx == 0, last = sidx + 1 == nblocks;
+
+  if (p == 0) {
+    for (int j = 0; j < ntiles; ++j) mbar_init(&full[j], 1);
+    fence_mbar_init();
+    for (int j = 0; j < ntiles; ++j) {                         // the whole box always arrives (zero fill past L and past P)
+      mbar_expect_tx(&full[j], (uint32_t)kSegRows * gw * 8u);
+      tma3d_load(tiles + (size_t)j * kSegRows * gw, &tin, c0, t0 + j * kSegRows, b, &full[j]);
+    }
+  }
+  __syncthreads();                                             // the barriers are initialised before anybody waits on them
+
+  const float2 a = active ? lam[gp] : make_float2(0.f, 0.f);
+  double2 aV = make_double2(1., 0.);
+  {
+    double2 sq = f2z(a);
+    for (int n = vlen; n > 0; n >>= 1) {
+      if (n & 1) aV = zmul(aV, sq);
+      sq = zmul(sq, sq);
+    }
+  }
+  uint32_t* flag_row = flags + ((size_t)b * groups + g) * nblocks;
+  double2* rec_row = recs + (size_t)b * nblocks * P;           // [block][P] aggregates of this clip
+
+  float2 xa = make_float2(0.f, 0.f);
+  if (!first && !last) {                                       // aggregate pass (inner blocks are always full)
+    for (int j = 0; j < ntiles; ++j) {
+      mbar_wait(&full[j], 0);
+      if (active) {
+        float2 v[kSegRows];
+        const float2* src = tiles + (size_t)j * kSegRows * gw + p;
+#pragma unroll
+        for (int t = 0; t < kSegRows; ++t) v[t] = src[t * gw];
+#pragma unroll
+        for (int t = 0; t < kSegRows; ++t) xa = cfma(a, xa, v[t]);
+      }
+    }
+    if (active) __stcg(rec_row + (size_t)sidx * P + gp, f2z(xa));
+    __syncthreads();                                           // the release below is cumulative over the barrier
+    if (p == 0) st_release_u32(flag_row + sidx, 1u);
+  }
+  double2 c = make_double2(0., 0.);
+  if (!first) {                                                // carry entering this block: Horner over the blocks 0 .. sidx - 1
+    for (int j0 = p; j0 < sidx; j0 += 4 * G) {
+      uint32_t f[4];
+#pragma unroll
+      for (int w = 0; w < 4; ++w) f[w] = j0 + w * G < sidx ? ld_relaxed_u32(flag_row + j0 + w * G) : 1u;
+#pragma unroll
+      for (int w = 0; w < 4; ++w)
+        while (f[w] == 0u) f[w] = ld_relaxed_u32(flag_row + j0 + w * G);
+    }
+    __syncthreads();
+    fence_acquire_gpu();
+    if (active) {
+      for (int j0 = 0; j0 < sidx; j0 += 16) {
+        double2 r[16];
+#pragma unroll
+        for (int w = 0; w < 16; ++w)
+          if (j0 + w < sidx) r[w] = __ldcg(rec_row + (size_t)(j0 + w) * P + gp);
+#pragma unroll
+        for (int w = 0; w < 16; ++w)
+          if (j0 + w < sidx) c = zfma(aV, c, r[w]);
+      }
+    }
+  }
+  float2 x = make_float2((float)c.x, (float)c.y);
+  for (int j = 0; j < ntiles; ++j) {
+    mbar_wait(&full[j], 0);                                    // returns at once when the aggregate pass has been here already
+    const int rows = min(kSegRows, rows_total - j * kSegRows);
+    float2* tile = tiles + (size_t)j * kSegRows * gw;
+    if (active) {
+      float2 v[kSegRows];
+      const float2* src = tile + p;
+      if (rows == kSegRows) {
+#pragma unroll
+        for (int t = 0; t < kSegRows; ++t) v[t] = src[t * gw];
+#pragma unroll
+        for (int t = 0; t < kSegRows; ++t) {
+          x = cfma(a, x, v[t]);
+          v[t] = x;
+        }
+#pragma unroll
+        for (int t = 0; t < kSegRows; ++t) tile[t * gw + p] = RELU ? relu_lex(v[t]) : v[t];
+      } else {
+#pragma unroll
+        for (int t = 0; t < kSegRows; ++t) v[t] = t < rows ? src[t * gw] : make_float2(0.f, 0.f);
+#pragma unroll
+        for (int t = 0; t < kSegRows; ++t)
+          if (t < rows) {
+            x = cfma(a, x, v[t]);
+            tile[t * gw + p] = RELU ? relu_lex(x) : x;
+          }
+      }
+    }
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (p == 0) {
+      tma3d_store(&tout, c0, t0 + j * kSegRows, b, tile);      // rows past L and states past P are clipped
+      bulk_commit();
+    }
+  }
+  if (first && !last) {                                        // block 0: its states from zero ARE its aggregate
+    if (active) __stcg(rec_row + gp, f2z(x));
+    __syncthreads();
+    if (p == 0) st_release_u32(flag_row, 1u);
+  }
+  bulk_wait_read0();                                           // the stores have read the tile (shared memory goes away at exit)
+}
+
+
 #ifdef S5_SCAN_TRACE
 #include <cstdio>
 #define SPLIT_TRACE_DECL long long tr_wait = 0; const long long tr_t0 = clock64();
@@ -1010,6 +1000,27 @@ static int make_tmap3d_i32(CUtensorMap* tm, const void* base, int P, int L, long
   return r == CUDA_SUCCESS ? 0 : -1;
 }
 
+// [B][L][P] complex64 as a 3-D tensor of floats {2P, L, B}; box = {2 * gw floats, kSegRows steps, 1 clip}
+static int make_tmap3d_c64(CUtensorMap* tm, const void* base, int P, int L, long long B, int gw) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                               const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qr) != cudaSuccess || qr != cudaDriverEntryPointSuccess) f = nullptr;
+    return reinterpret_cast<EncodeFn>(f);
+  }();
+  if (!fn) return -1;
+  const cuuint64_t W = 2ull * P;
+  const cuuint64_t dims[3] = {W, (cuuint64_t)L, (cuuint64_t)B};
+  const cuuint64_t strides[2] = {W * 4, (cuuint64_t)L * W * 4};
+  const cuuint32_t box[3] = {(cuuint32_t)(2 * gw), (cuuint32_t)kSegRows, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -1;
+}
+
 int launch_scan_i32(const ScanI32Params& q, bool interleaved, cudaStream_t st) {
   const long long B = q.lanes / q.P;
   const bool ptr_ok = aligned16(q.Bu_re) && aligned16(q.xs_re) && (interleaved || (aligned16(q.Bu_im) && aligned16(q.xs_im)));
@@ -1106,19 +1117,25 @@ int launch_scan_c64(const float* Bu, const float* lam, float* xs, int B, int L, 
   // Few clips: one resident block per CTA when a block fits shared memory (S5B200_SCAN_RESIDENT=0: the segmented ring kernel)
   const char* res_env = getenv("S5B200_SCAN_RESIDENT");
   // Measured (profiles/r02_scan_resident.md): 5-14 % faster than the ring kernel for P <= 64 and up to ~64 blocks per clip, slower for
-  // wider states (512-byte row copies) and for very long single clips (every CTA walks the whole look-back); S5B200_SCAN_RESIDENT=1 forces it.
-  const bool res_auto = P <= kResG && g.nblocks <= 64;
-  if (g.nseg > 1 && g.vlen <= kResMaxTiles * kSegRows && (res_env ? res_env[0] != '0' : res_auto)) {
-    const int groups = (P + kResG - 1) / kResG;
+  // very long single clips (every CTA walks the whole look-back); S5B200_SCAN_RESIDENT=1 forces it.
+  // wider states: at par with the ring kernel (66.5 against 65.6 us at 32 x 3751 x 128), ahead of it while the grid is one wave
+  const bool res_auto = g.nblocks <= 64 && (P <= kResG || (long long)B * ((P + kResG - 1) / kResG) * g.nblocks <= 3LL * sm_count());
+  CUtensorMap tin, tout;
+  // 32 states per CTA (32 KB blocks, seven CTAs per SM) were measured too: no faster than 64 at any shape (profiles/r02_scan_resident.md)
+  constexpr int G = kResG;
+  const int gw = std::min(P, G);
+  if (g.nseg > 1 && g.vlen <= kResMaxTiles * kSegRows && (res_env ? res_env[0] != '0' : res_auto) && L < (1 << 30) &&
+      make_tmap3d_c64(&tin, Bu, P, L, B, gw) == 0 && make_tmap3d_c64(&tout, xs, P, L, B, gw) == 0) {
+    const int groups = (P + G - 1) / G;
     const long long grid = (long long)g.nblocks * B * groups;
     if (grid > 0x7fffffffLL) S5_FAIL(S5_E_BADSHAPE, "scan_c64: too many clips");
-    const size_t smem = (size_t)g.vlen * std::min(P, kResG) * 8;
-    auto rk = relu ? scan_c64_res_kernel<true> : scan_c64_res_kernel<false>;
+    const size_t smem = (size_t)g.vlen * gw * 8;
+    using ResKern = void (*)(const CUtensorMap, const CUtensorMap, const float2*, int, int, int, int, int, int, int, uint32_t*, double2*);
+    ResKern rk = relu ? scan_c64_res_kernel<true, G> : scan_c64_res_kernel<false, G>;
     S5_CUDA(cudaFuncSetAttribute(rk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     S5_CUDA(cudaMemsetAsync(flags, 0, (size_t)B * groups * g.nblocks * sizeof(uint32_t), st));
     ProfScope prof(S5_K_SCAN_C64, st);
-    rk<<<(unsigned)grid, kResG, smem, st>>>(reinterpret_cast<const float2*>(Bu), reinterpret_cast<const float2*>(lam),
-                                            reinterpret_cast<float2*>(xs), L, P, B, groups, g.vlen, g.nblocks, flags, recs);
+    rk<<<(unsigned)grid, G, smem, st>>>(tin, tout, reinterpret_cast<const float2*>(lam), L, P, B, groups, gw, g.vlen, g.nblocks, flags, recs);
     S5_LAUNCH_CHECK();
     return S5_OK;
   }
