@@ -309,6 +309,15 @@ int s5b200_stft(const float* audio, int B, int T, float* mag, float* phase, int 
  * cleaned_mag_out (nullable, layout of mag, must not alias an input) receives mag * (1 + mask). */
 int s5b200_istft(const float* mag, const float* phase, int layout_blf, const float* mask_blf, int B, int L,
                  float* audio_out, float* cleaned_mag_out, void* stream);
+/* Forward of the reference's NDNS evaluation step (train_helpers.py:1570-1606) on HOST audio: noisy audio [B][T] (pinned for full
+ * speed) -> H2D -> stft_splitter -> model input mag - mag_sub (0.0007 in the reference) -> model -> mag * (1 + mask) -> stft_mixer -> D2H
+ * of the cleaned audio [B][(s5b200_stft_frames(T) - 1) * 128].  Same clip-chunk pipeline, chunk schedule and stream semantics as
+ * s5b200_model_forward_host / _async; spectra never cross the bus (a quarter of the PCIe bytes of the tensor-level call).  The model
+ * must map 257 -> 257 features.  Results equal s5b200_stft + s5b200_model_forward + s5b200_istft on the whole batch bit for bit. */
+int s5b200_ndns_denoise_host(const s5_model* m, const float* noisy_host, float* cleaned_host, int B, int T, float mag_sub,
+                             void* stream);
+int s5b200_ndns_denoise_host_async(const s5_model* m, const float* noisy_host, float* cleaned_host, int B, int T,
+                                   float mag_sub, void* stream);
 /* workspace of the two per-clip reductions below */
 size_t s5b200_reduce_workspace_bytes(int B, long long n_per_clip);
 /* si_snr_jax, train_helpers.py:16-53: target, estimate [B][T] -> out_db [B] (sums accumulated in float64, fixed order) */

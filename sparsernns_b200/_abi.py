@@ -135,6 +135,8 @@ PROTOTYPES = {
     "s5b200_stft_frames": (_I, [_I]),
     "s5b200_stft": (_I, [_V, _I, _I, _V, _V, _I, _V, C.c_float, _V]),
     "s5b200_istft": (_I, [_V, _V, _I, _V, _I, _I, _V, _V, _V]),
+    "s5b200_ndns_denoise_host": (_I, [_V, _V, _V, _I, _I, C.c_float, _V]),
+    "s5b200_ndns_denoise_host_async": (_I, [_V, _V, _V, _I, _I, C.c_float, _V]),
     "s5b200_reduce_workspace_bytes": (_SZ, [_I, _LL]),
     "s5b200_si_snr": (_I, [_V, _V, _I, _LL, _V, _V, _SZ, _V]),
     "s5b200_mse_clips": (_I, [_V, _V, _I, _LL, _V, _V, _SZ, _V]),

@@ -362,7 +362,8 @@ struct s5_model {
   std::mutex mu;
   float* hx[kSlots] = {}; float* hy[kSlots] = {};
   void* hws[kSlots] = {};
-  size_t hx_cap[kSlots] = {}, hy_cap[kSlots] = {}, hws_cap[kSlots] = {};
+  void* ha[kSlots] = {};              // audio mode: audio in | magnitude | angle | audio out of the slot's chunk
+  size_t hx_cap[kSlots] = {}, hy_cap[kSlots] = {}, hws_cap[kSlots] = {}, ha_cap[kSlots] = {};
   cudaStream_t hs[4] = {nullptr, nullptr, nullptr, nullptr};   // H2D, D2H, two forward streams
   cudaEvent_t ev_h2d[kSlots] = {}, ev_cmp[kSlots] = {}, ev_d2h[kSlots] = {}, ev_user = nullptr, ev_done = nullptr;
   unsigned long long chunk_seq = 0;
@@ -676,7 +677,7 @@ extern "C" int s5b200_model_destroy(s5_model* m) {
     cudaFree(l.lam); cudaFree(l.D); cudaFree(l.bn_mean); cudaFree(l.bn_mul); cudaFree(l.bn_bias); cudaFree(l.o_bias);
   }
   for (int i = 0; i < s5_model::kSlots; ++i) {
-    cudaFree(m->hx[i]); cudaFree(m->hy[i]); cudaFree(m->hws[i]);
+    cudaFree(m->hx[i]); cudaFree(m->hy[i]); cudaFree(m->hws[i]); cudaFree(m->ha[i]);
     if (m->ev_h2d[i]) cudaEventDestroy(m->ev_h2d[i]);
     if (m->ev_cmp[i]) cudaEventDestroy(m->ev_cmp[i]);
     if (m->ev_d2h[i]) cudaEventDestroy(m->ev_d2h[i]);
@@ -856,7 +857,16 @@ extern "C" int s5b200_model_calibrate(const s5_model* m, const float* x, float* 
   return S5_OK;
 }
 
-static int forward_host_impl(const s5_model* mc, const float* x_host, float* y_host, int B, int L, void* stream, bool sync) {
+// NDNS pre / post-processing (ndns.cu)
+extern "C" int s5b200_stft_frames(int T);
+extern "C" int s5b200_stft(const float* audio, int B, int T, float* mag, float* phase, int layout_blf, float* model_in, float mag_sub, void* stream);
+extern "C" int s5b200_istft(const float* mag, const float* phase, int layout_blf, const float* mask_blf, int B, int L, float* audio_out,
+                            float* cleaned_mag_out, void* stream);
+
+// audio_T > 0: AUDIO mode (s5b200_ndns_denoise_host) - x_host is noisy audio [B][audio_T], y_host the cleaned audio [B][(L - 1) * 128],
+// L = s5b200_stft_frames(audio_T); a chunk's forward is STFT -> model -> mask apply + iSTFT and spectra never cross the bus.
+static int forward_host_impl(const s5_model* mc, const float* x_host, float* y_host, int B, int L, void* stream, bool sync, int audio_T = 0,
+                             float mag_sub = 0.f) {
   // End-to-end entry point: the batch is cut into clip chunks that flow through a three-stage pipeline
   // (H2D copy | forward | D2H copy) on four internal streams (two alternating forward streams) with a ring of kSlots device buffers, so that
   // the two PCIe directions and the kernels overlap.  Clips are independent, so chunking does not change results.
@@ -937,10 +947,15 @@ static int forward_host_impl(const s5_model* mc, const float* x_host, float* y_h
     S5_CUDA(cudaEventCreateWithFlags(&m->ev_user, cudaEventDisableTiming));
     S5_CUDA(cudaEventCreateWithFlags(&m->ev_done, cudaEventDisableTiming));
   }
+  const size_t out_len = audio_T > 0 ? (size_t)(L - 1) * 128 : 0;
+  // audio-mode scratch of a slot: audio in | magnitude | angle | audio out, each rounded up to 256 bytes
+  const size_t a_in_b = round_up((size_t)cb * (size_t)std::max(audio_T, 0) * sizeof(float), 256), a_sp_b = round_up(xb, 256);
+  const size_t a_out_b = round_up((size_t)cb * out_len * sizeof(float), 256);
   for (int i = 0; i < kSlots; ++i) {
     if ((rc = grow(reinterpret_cast<void**>(&m->hx[i]), &m->hx_cap[i], xb))) return rc;
     if ((rc = grow(reinterpret_cast<void**>(&m->hy[i]), &m->hy_cap[i], yb))) return rc;
     if ((rc = grow(&m->hws[i], &m->hws_cap[i], wsb))) return rc;
+    if (audio_T > 0 && (rc = grow(&m->ha[i], &m->ha_cap[i], a_in_b + 2 * a_sp_b + a_out_b))) return rc;
   }
   cudaStream_t s_in = m->hs[0], s_out = m->hs[1];
   S5_CUDA(cudaEventRecord(m->ev_user, user));  // order after whatever the caller queued before
@@ -968,17 +983,32 @@ static int forward_host_impl(const s5_model* mc, const float* x_host, float* y_h
     const size_t xoff = (size_t)b0 * L * m->desc.d_input, yoff = (size_t)b0 * L * m->desc.d_output;
     const size_t xbytes = (size_t)nb * L * m->desc.d_input * sizeof(float), ybytes = (size_t)nb * L * m->desc.d_output * sizeof(float);
     if (seq >= (unsigned long long)kSlots) S5_CUDA(cudaStreamWaitEvent(s_in, m->ev_d2h[slot], 0));  // slot buffers are free again
-    S5_CUDA(cudaMemcpyAsync(m->hx[slot], x_host + xoff, xbytes, cudaMemcpyHostToDevice, s_in));
+    unsigned char* ab = reinterpret_cast<unsigned char*>(m->ha[slot]);
+    float* a_in = reinterpret_cast<float*>(ab);
+    float* a_mag = reinterpret_cast<float*>(ab + a_in_b);
+    float* a_ph = reinterpret_cast<float*>(ab + a_in_b + a_sp_b);
+    float* a_out = reinterpret_cast<float*>(ab + a_in_b + 2 * a_sp_b);
+    if (audio_T > 0) {
+      S5_CUDA(cudaMemcpyAsync(a_in, x_host + (size_t)b0 * audio_T, (size_t)nb * audio_T * sizeof(float), cudaMemcpyHostToDevice, s_in));
+    } else {
+      S5_CUDA(cudaMemcpyAsync(m->hx[slot], x_host + xoff, xbytes, cudaMemcpyHostToDevice, s_in));
+    }
     S5_CUDA(cudaEventRecord(m->ev_h2d[slot], s_in));
     mark(s_in);
     S5_CUDA(cudaStreamWaitEvent(s_cmp, m->ev_h2d[slot], 0));
     mark(s_cmp);
+    if (audio_T > 0 && (rc = s5b200_stft(a_in, nb, audio_T, a_mag, a_ph, 1, m->hx[slot], mag_sub, s_cmp))) return rc;
     if (!(trace && getenv("S5B200_E2E_TRACE_COPY_ONLY")) &&   // debug: measure the copy pipeline alone
         (rc = s5b200_model_forward(m, m->hx[slot], m->hy[slot], nb, L, m->hws[slot], m->hws_cap[slot], s_cmp))) return rc;
+    if (audio_T > 0 && (rc = s5b200_istft(a_mag, a_ph, 1, m->hy[slot], nb, L, a_out, nullptr, s_cmp))) return rc;
     S5_CUDA(cudaEventRecord(m->ev_cmp[slot], s_cmp));
     mark(s_cmp);
     S5_CUDA(cudaStreamWaitEvent(s_out, m->ev_cmp[slot], 0));
-    S5_CUDA(cudaMemcpyAsync(y_host + yoff, m->hy[slot], ybytes, cudaMemcpyDeviceToHost, s_out));
+    if (audio_T > 0) {
+      S5_CUDA(cudaMemcpyAsync(y_host + (size_t)b0 * out_len, a_out, (size_t)nb * out_len * sizeof(float), cudaMemcpyDeviceToHost, s_out));
+    } else {
+      S5_CUDA(cudaMemcpyAsync(y_host + yoff, m->hy[slot], ybytes, cudaMemcpyDeviceToHost, s_out));
+    }
     S5_CUDA(cudaEventRecord(m->ev_d2h[slot], s_out));
     mark(s_out);
   }
@@ -1014,4 +1044,22 @@ extern "C" int s5b200_model_forward_host(const s5_model* m, const float* x_host,
 extern "C" int s5b200_model_forward_host_async(const s5_model* m, const float* x_host, float* y_host, int B, int L,
                                                void* stream) {
   return forward_host_impl(m, x_host, y_host, B, L, stream, false);
+}
+
+static int denoise_host(const s5_model* m, const float* noisy_host, float* cleaned_host, int B, int T, float mag_sub, void* stream, bool sync) {
+  if (!m) S5_FAIL(S5_E_BADARG, "ndns_denoise_host: null model");
+  if (m->desc.d_input != 257 || m->desc.d_output != 257)
+    S5_FAIL(S5_E_BADSHAPE, "ndns_denoise_host: the model maps %d -> %d features, the NDNS spectra have 257 bins", m->desc.d_input, m->desc.d_output);
+  if (T < 129) S5_FAIL(S5_E_BADSHAPE, "ndns_denoise_host: T=%d (at least two frames are needed)", T);
+  const int L = s5b200_stft_frames(T);
+  if (L < 2) S5_FAIL(S5_E_BADSHAPE, "ndns_denoise_host: T=%d gives %d frame(s)", T, L);
+  return forward_host_impl(m, noisy_host, cleaned_host, B, L, stream, sync, T, mag_sub);
+}
+extern "C" int s5b200_ndns_denoise_host(const s5_model* m, const float* noisy_host, float* cleaned_host, int B, int T, float mag_sub,
+                                        void* stream) {
+  return denoise_host(m, noisy_host, cleaned_host, B, T, mag_sub, stream, true);
+}
+extern "C" int s5b200_ndns_denoise_host_async(const s5_model* m, const float* noisy_host, float* cleaned_host, int B, int T, float mag_sub,
+                                              void* stream) {
+  return denoise_host(m, noisy_host, cleaned_host, B, T, mag_sub, stream, false);
 }

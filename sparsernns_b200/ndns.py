@@ -103,6 +103,36 @@ def mse_clips(a, b):
     return _reduce("s5b200_mse_clips", a, b)
 
 
+def denoise_host(model, noisy_host, out=None, sync=True):
+    """Forward of the NDNS evaluation step on HOST audio (CPU tensors, ideally pinned): (B, T) noisy -> (B, (L - 1) * 128) cleaned.
+
+    One call of ``s5b200_ndns_denoise_host``: the batch flows in clip chunks through H2D | STFT -> model -> mask apply + iSTFT | D2H
+    inside the library (``model`` is a float / static ``BoundModel``).  ``sync=False`` is stream-ordered like
+    ``BoundModel.forward_host(sync=False)``: keep both buffers alive until the current stream has been synchronised; consecutive
+    batches on two alternating streams keep both PCIe directions busy."""
+    import torch
+
+    lib = _abi.lib()
+    if not (isinstance(noisy_host, torch.Tensor) and not noisy_host.is_cuda and noisy_host.dtype == torch.float32 and noisy_host.dim() == 2
+            and noisy_host.is_contiguous()):
+        raise ValueError("noisy_host must be a contiguous float32 CPU tensor of shape (B, T)")
+    B, T = noisy_host.shape
+    L = lib.s5b200_stft_frames(T)
+    if out is None:
+        out = torch.empty((B, (L - 1) * HOP), dtype=torch.float32)
+        if noisy_host.is_pinned():
+            out = out.pin_memory()
+    if not (isinstance(out, torch.Tensor) and not out.is_cuda and out.dtype == torch.float32 and out.is_contiguous()
+            and tuple(out.shape) == (B, (L - 1) * HOP)):
+        raise ValueError("out must be a contiguous float32 CPU tensor of shape (B, (L - 1) * 128)")
+    if not sync and not (noisy_host.is_pinned() and out.is_pinned()):
+        import warnings
+        warnings.warn("denoise_host(sync=False) with pageable host buffers: copies are not asynchronous; pin both buffers")
+    fn = lib.s5b200_ndns_denoise_host if sync else lib.s5b200_ndns_denoise_host_async
+    _abi.check(fn(model._handle, noisy_host.data_ptr(), out.data_ptr(), B, T, STFT_MAG_MEAN, _stream()), "s5b200_ndns_denoise_host")
+    return out
+
+
 def denoise_eval(model, noisy_audio, clean_audio):
     """Forward of the reference's NDNS evaluation step: returns (losses, si_snr, cleaned audio).
 

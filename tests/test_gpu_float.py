@@ -288,6 +288,39 @@ def test_forward_host_matches_device_path(cuda_device, zoo, monkeypatch):
         assert torch.equal(o, y_host if i % 2 == 0 else y_flip)
 
 
+def test_ndns_denoise_host_equals_device_composition(cuda_device, zoo, monkeypatch):
+    """s5b200_ndns_denoise_host (noisy audio on the host -> H2D | STFT -> model -> mask apply + iSTFT | D2H in clip chunks) equals
+    stft_splitter -> BoundModel -> stft_mixer on the whole batch bit for bit; also stream-ordered, with batches in flight on two
+    alternating streams (the library then switches to large chunks), and the reference-shaped argument checks."""
+    import torch
+    from sparsernns_b200 import ndns
+
+    monkeypatch.setenv("S5B200_TC_MIN_ROWS", "1")
+    m, _ = _bound(zoo, static=True, relufication=True)
+    g = torch.Generator().manual_seed(5)
+    noisy = [(0.05 * torch.randn(11, 128 * 299, generator=g)).pin_memory() for _ in range(2)]   # 11 clips: ragged chunk schedule, L = 300
+    ref = []
+    for a in noisy:
+        mag, ph, xin = ndns.stft_splitter(a.to(cuda_device), blf=True, model_input=True)
+        ref.append(ndns.stft_mixer(mag, ph, blf=True, mask=m(xin)).cpu())
+    out = ndns.denoise_host(m, noisy[0])
+    assert out.shape == ref[0].shape and torch.equal(out, ref[0])
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    outs = [torch.full_like(out, float("nan")).pin_memory() for _ in range(6)]
+    for i, o in enumerate(outs):
+        with torch.cuda.stream(streams[i % 2]):
+            ndns.denoise_host(m, noisy[i % 2], out=o, sync=False)
+    torch.cuda.synchronize()
+    for i, o in enumerate(outs):
+        assert torch.equal(o, ref[i % 2])
+    with pytest.raises(ValueError):
+        ndns.denoise_host(m, noisy[0].to(cuda_device))
+    with pytest.raises(ValueError):
+        ndns.denoise_host(m, noisy[0], out=torch.empty(11, 5))
+    with pytest.raises(Exception):
+        ndns.denoise_host(m, torch.zeros(2, 64))          # fewer than two frames
+
+
 def test_block_kernel_is_bit_reproducible_and_batch_invariant(cuda_device, zoo, monkeypatch):
     """One kernel per block (fused recurrence): repeated runs, sub-batches and clip order give identical bits."""
     import torch
