@@ -983,11 +983,14 @@ static int forward_host_impl(const s5_model* mc, const float* x_host, float* y_h
     const size_t xoff = (size_t)b0 * L * m->desc.d_input, yoff = (size_t)b0 * L * m->desc.d_output;
     const size_t xbytes = (size_t)nb * L * m->desc.d_input * sizeof(float), ybytes = (size_t)nb * L * m->desc.d_output * sizeof(float);
     if (seq >= (unsigned long long)kSlots) S5_CUDA(cudaStreamWaitEvent(s_in, m->ev_d2h[slot], 0));  // slot buffers are free again
-    unsigned char* ab = reinterpret_cast<unsigned char*>(m->ha[slot]);
-    float* a_in = reinterpret_cast<float*>(ab);
-    float* a_mag = reinterpret_cast<float*>(ab + a_in_b);
-    float* a_ph = reinterpret_cast<float*>(ab + a_in_b + a_sp_b);
-    float* a_out = reinterpret_cast<float*>(ab + a_in_b + 2 * a_sp_b);
+    float *a_in = nullptr, *a_mag = nullptr, *a_ph = nullptr, *a_out = nullptr;
+    if (audio_T > 0) {
+      unsigned char* ab = reinterpret_cast<unsigned char*>(m->ha[slot]);
+      a_in = reinterpret_cast<float*>(ab);
+      a_mag = reinterpret_cast<float*>(ab + a_in_b);
+      a_ph = reinterpret_cast<float*>(ab + a_in_b + a_sp_b);
+      a_out = reinterpret_cast<float*>(ab + a_in_b + 2 * a_sp_b);
+    }
     if (audio_T > 0) {
       S5_CUDA(cudaMemcpyAsync(a_in, x_host + (size_t)b0 * audio_T, (size_t)nb * audio_T * sizeof(float), cudaMemcpyHostToDevice, s_in));
     } else {
@@ -1050,8 +1053,8 @@ static int denoise_host(const s5_model* m, const float* noisy_host, float* clean
   if (!m) S5_FAIL(S5_E_BADARG, "ndns_denoise_host: null model");
   if (m->desc.d_input != 257 || m->desc.d_output != 257)
     S5_FAIL(S5_E_BADSHAPE, "ndns_denoise_host: the model maps %d -> %d features, the NDNS spectra have 257 bins", m->desc.d_input, m->desc.d_output);
-  if (T < 129) S5_FAIL(S5_E_BADSHAPE, "ndns_denoise_host: T=%d (at least two frames are needed)", T);
-  const int L = s5b200_stft_frames(T);
+  if (T <= 0) S5_FAIL(S5_E_BADSHAPE, "ndns_denoise_host: T=%d must be positive", T);
+  const int L = s5b200_stft_frames(T);                        // >= 2 for every positive T (boundary padding of nfft / 2 either side)
   if (L < 2) S5_FAIL(S5_E_BADSHAPE, "ndns_denoise_host: T=%d gives %d frame(s)", T, L);
   return forward_host_impl(m, noisy_host, cleaned_host, B, L, stream, sync, T, mag_sub);
 }
