@@ -463,6 +463,7 @@ def main():
     extras = {}
     cpu_baseline = None
     scan_rf = None
+    tput = None
     if rank == 0 and not args.no_extras:
         try:
             extras = secondary_flavours(torch, model, params, batch_stats, cal_stats, dims, xs, B, L, dev)
@@ -472,6 +473,11 @@ def main():
             scan_rf = scan_roofline(torch, B, L, dims.ssm_size, dev, peak)
         except Exception as e:
             scan_rf = {"error": repr(e)}
+        if world == 1:
+            try:
+                tput = throughput_batch(torch, lib, _abi, model, dims, L, dev, peak)
+            except Exception as e:
+                tput = {"error": repr(e)}
         if world == 1:
             # bounded sample of the same workload: 8-clip slices of the step's batch, repeated until about 10 s of CPU work
             fwd = cpu_port_forward_fn(params, batch_stats, dims)
@@ -519,6 +525,8 @@ def main():
             line["flavours"] = extras
         if scan_rf:
             line["scan_roofline"] = scan_rf
+        if tput:
+            line["throughput_batch"] = tput
         emit(line)
     if dist is not None:
         dist.destroy_process_group()
@@ -536,6 +544,49 @@ def kernel_breakdown(fn, reps=3):
     n = (C.c_longlong * len(_abi.KERNEL_CLASSES))()
     _abi.check(lib.s5b200_profile_end(ms, n))
     return {name: round(ms[i] / reps, 4) for i, name in enumerate(_abi.KERNEL_CLASSES) if n[i]}
+
+
+def throughput_batch(torch, lib, _abi, model, dims, L, dev, peak, clips=256, steps=5):
+    """The same forward at the throughput batch SURVEY section 8d names for weak scaling (256 clips per GPU): the 40-60 us launches of
+    the 32-clip step are dominated by ramp and tail, here the memory-bound kernels show their steady-state fraction of the roofline."""
+    import ctypes as C
+
+    free, _ = torch.cuda.mem_get_info()
+    per_clip = L * D_IO * 4
+    if free < 6 * clips * per_clip:
+        return {"skipped": "not enough free device memory"}
+    xs = synth_inputs(torch, 2, clips, L, 4242, dev)              # 2 x 987 MB: every step reads an input that is not in L2
+    rows = clips * L
+    for i in range(2):
+        y = model(xs[i % 2])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        y = model(xs[i % 2])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    lib.s5b200_profile_begin()
+    for i in range(steps):
+        y = model(xs[i % 2])
+    ms_cls = (C.c_double * len(_abi.KERNEL_CLASSES))()
+    n_cls = (C.c_longlong * len(_abi.KERNEL_CLASSES))()
+    _abi.check(lib.s5b200_profile_end(ms_cls, n_cls))
+    alg = algorithmic_bytes(rows, dims.d_model, dims.ssm_size)
+    kern = {}
+    for i, name in enumerate(_abi.KERNEL_CLASSES):
+        if n_cls[i]:
+            per = ms_cls[i] / n_cls[i]
+            ab = alg.get(name)
+            if name == "block" and ab:
+                ab = ab * dims.n_layers / max(1.0, n_cls[i] / steps)
+            kern[name] = {"ms_per_launch": per, "launches_per_step": n_cls[i] / steps,
+                          "frac": (ab / (per * 1e-3) / 1e9 / peak) if ab else None}
+    del xs, y
+    torch.cuda.empty_cache()
+    return {"clips": clips, "frames_per_s": rows / (ms * 1e-3), "ms_per_step": ms, "steps": steps, "kernels": kern,
+            "l2": "inputs alternate over 2 batches (%.0f MB each) > 126 MB L2" % (clips * per_clip / 1e6)}
 
 
 def scan_roofline(torch, B, L, P, dev, peak):
