@@ -307,6 +307,11 @@ constexpr uint32_t kFwRaw = kF32Rows * kF32KC * 4;            // one raw slot: [
 constexpr int kFwSupCols = kF32KC + 4;                        // SUPER: box width (16 columns + up to 3 of lead-in)
 constexpr uint32_t kFwRawSup = kF32Rows * kFwSupCols * 4;     // SUPER: [128][20] fp32
 constexpr uint32_t kFwUnit = 2 * kF32Plane;                   // hi / lo planes of one X chunk
+// tc_f32g_kernel's x1 units: an epilogue warp writes 32 consecutive columns = two units at the same row; kFwUnit is a multiple of
+// 128 bytes, which put lanes l and l + 16 on one bank (ncu: 42 % of the kernel's shared-memory wavefronts were conflicts) - 16 bytes
+// of padding per unit move the second unit by four banks.  The region is rounded up to 128 bytes for what follows it.
+constexpr uint32_t kFgX1Unit = kFwUnit + 16;
+__host__ __device__ constexpr size_t fg_x1_bytes(int nc2) { return ((size_t)nc2 * kFgX1Unit + 127) & ~(size_t)127; }
 constexpr int kFwMaxRing = 8;
 constexpr int kFwSubRows = 32;                                // rows per box of the second tensor map (ragged last tile of a CTA)
 
@@ -494,6 +499,9 @@ __global__ void __launch_bounds__(kFwThreads, 1) tc_f32w_kernel(const __grid_con
               const int rr = bq * 32 + i * 8 + (lane >> 2);
               const int cls = rvt == kF32Rows ? rr >> (7 - lq) : (rr & 31) >> (5 - lq);
               const float* src = reinterpret_cast<const float*>(raw + (uint32_t)rr * raw_pitch + 16u * grp) + ((cls * p.K) & 3);
+              // (four 4-byte loads whose addresses are all congruent mod 4 words: a 4-way bank conflict each.  Starting every lane at
+              // word `lane & 3` and rotating the registers back by selects removes it - 4.7 M -> 1.2 M conflicts - but the converters
+              // are bound by instruction issue: 30.3 M -> 34.1 M warp instructions, 82.9 -> 89.4 us.  Measured, not kept.)
               v[i] = make_float4(src[0], src[1], src[2], src[3]);
             } else {
               v[i] = *reinterpret_cast<const float4*>(raw + (bq * 128 + i * 32) * 16);
@@ -673,7 +681,7 @@ __global__ void __launch_bounds__(kFgThreads, 1) tc_f32g_kernel(const __grid_con
   const int NC1 = p.NC1, NC2 = p.NC2, NCT = NC1 + NC2;
   constexpr uint32_t wbytes = 2u * kF32Plane;                 // one chunk of either weight set (one M block, hi + lo)
   unsigned char* X1buf = smem;                                // NC2 units: hi / lo planes of x1, chunk = 16 columns
-  unsigned char* Wbuf = X1buf + (size_t)NC2 * kFwUnit;
+  unsigned char* Wbuf = X1buf + fg_x1_bytes(NC2);
   unsigned char* Ubuf = Wbuf + (size_t)NW * wbytes;
   unsigned char* Rbuf = Ubuf + (size_t)NU * kFwUnit;
   __shared__ __align__(8) uint64_t raw_full[kFwMaxRing], raw_free[kFwMaxRing], unit_full[kFwMaxRing], unit_free[kFwMaxRing];
@@ -689,7 +697,7 @@ __global__ void __launch_bounds__(kFgThreads, 1) tc_f32g_kernel(const __grid_con
     mbar_init(&acc1_full, 1); mbar_init(&acc1_free, kFgEpi); mbar_init(&acc2_full, 1); mbar_init(&acc2_free, kFgEpi); mbar_init(&x1_full, kFgEpi);
     fence_mbar_init();
   }
-  for (size_t i = (size_t)tid * 16; i < (size_t)NC2 * kFwUnit; i += kFgThreads * 16) *reinterpret_cast<int4*>(X1buf + i) = make_int4(0, 0, 0, 0);   // pad columns stay zero
+  for (size_t i = (size_t)tid * 16; i < fg_x1_bytes(NC2); i += kFgThreads * 16) *reinterpret_cast<int4*>(X1buf + i) = make_int4(0, 0, 0, 0);   // pad columns stay zero
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -776,7 +784,7 @@ __global__ void __launch_bounds__(kFgThreads, 1) tc_f32g_kernel(const __grid_con
         for (int c = 0; c < NC2; ++c, w.next(NW)) {
           FG_T(5, mbar_wait(&w_full[w.slot], w.par));
           tc_fence_after();
-          chunk(smem_u32(X1buf + (size_t)c * kFwUnit), smem_u32(Wbuf + (size_t)w.slot * wbytes), taddr + 256u, idesc, c == 0);
+          chunk(smem_u32(X1buf + (size_t)c * kFgX1Unit), smem_u32(Wbuf + (size_t)w.slot * wbytes), taddr + 256u, idesc, c == 0);
           tc_commit(&w_free[w.slot]);
         }
         tc_commit(&acc2_full);
@@ -837,7 +845,7 @@ __global__ void __launch_bounds__(kFgThreads, 1) tc_f32g_kernel(const __grid_con
     if constexpr (BNF) { bs = p.bn_sub[nc]; bm = p.bn_mul[nc]; ba = p.bn_add[nc]; }
     const bool relu = p.relu != 0;
     // element (row, column n) of the x1 planes: chunk n / 16, 16-byte group (n / 4) % 4, word n % 4
-    unsigned char* const x1p = X1buf + (size_t)(nc >> 4) * kFwUnit + (uint32_t)((nc >> 2) & 3) * kF32Lbo + 4u * (nc & 3);
+    unsigned char* const x1p = X1buf + (size_t)(nc >> 4) * kFgX1Unit + (uint32_t)((nc >> 2) & 3) * kF32Lbo + 4u * (nc & 3);
     for (int t = 0; t < ntiles; ++t) {
       const long long row0 = row_begin + (long long)t * kF32Rows;
       const int rv = (int)min((long long)kF32Rows, row_end - row0);
@@ -1084,7 +1092,7 @@ int tc_f32_glu_launch(const TcF32Dev& fc, const TcF32Dev& fo, const TcF32GluArgs
       a.rows <= 0 || a.rows >= (1LL << 31) || !a.X || !a.Y || !a.D || !a.o_bias)
     return S5_E_UNSUPPORTED;
   const size_t budget = 227 * 1024 - 1536 - 128;
-  const size_t x1 = (size_t)fo.NC * kFwUnit;
+  const size_t x1 = fg_x1_bytes(fo.NC);
   int NW = 3, NU = 0, NRAW = 0;
   bool ok = false;
   for (; NW >= 2 && !ok; --NW) {
