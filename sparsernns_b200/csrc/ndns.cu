@@ -23,45 +23,68 @@ constexpr int kNdThreads = 256;
 
 __device__ __forceinline__ float2 cmul2(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 
-// 256-point complex FFT, one warp, ping-pong buffers in shared memory; 8 stages, so the result ends in `a`.
-// Twiddles: ONE TABLE PER STAGE, stage s (Ns = 2^s butterflies wide) at offset Ns - 1 with entry r = exp(-i pi r / Ns), so the
-// lanes of a warp read consecutive (or repeated) words.  The first version indexed one table exp(-2 pi i k / 512) with
-// k = r << (8 - s): a stride of 2^(8 - s) entries, up to 16 lanes on one bank - ncu showed the iSTFT at 79 % of the
-// shared-memory wavefront peak with 36.6 M bank conflicts.  The values are the same bits (same sincospif argument).
-// INV: conjugated twiddles (un-normalised inverse).  kTwFull: the stage-8 table = exp(-2 pi i k / 512), k < 256 (split / merge).
+// 256-point complex FFT, one warp, ping-pong buffers in shared memory: RADIX-4 Stockham, 4 stages (the result ends in `a`), two
+// butterflies per lane and stage.  Stage s (Ns = 4^s): v_m = in[j + 64 m] * exp(-2 pi i m r / (4 Ns)), r = j mod Ns, a 4-point DFT,
+// out[4 (j - r) + r + m Ns].  The first version was radix 2 (8 stages): ncu showed both transforms between the issue limit (71 %)
+// and the shared-memory limit (62-70 % of the wavefront peak); radix 4 halves the passes over shared memory (88 instead of 160
+// accesses per lane and transform) and the butterfly instructions.
+// Twiddles: ONE TABLE PER STAGE at offset 4^s - 1, entry (m - 1) Ns + r, so the lanes of a warp read consecutive (or repeated)
+// words - indexing one table exp(-2 pi i k / 512) with a stride put up to 16 lanes on one bank (ncu: the iSTFT at 79 % of the
+// shared-memory wavefront peak with 36.6 M bank conflicts).  INV: conjugated twiddles and butterflies (un-normalised inverse).
+// kTwFull: exp(-2 pi i k / 512), k < 256, for the split / merge passes.
 constexpr int kTwEntries = 511, kTwFull = 255;
 template <bool INV>
 __device__ __forceinline__ void fft256_warp(float2* a, float2* b, const float2* tw, int lane) {
   float2* in = a;
   float2* out = b;
 #pragma unroll
-  for (int s = 0; s < 8; ++s) {
-    const int Ns = 1 << s;
+  for (int s = 0; s < 4; ++s) {
+    const int Ns = 1 << (2 * s);
+    const float2* t = tw + (Ns - 1);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < 2; ++q) {
       const int j = lane + 32 * q, r = j & (Ns - 1);
-      const float2 u = in[j];
-      float2 w = tw[(Ns - 1) + r];
-      if (INV) w.y = -w.y;
-      const float2 v = cmul2(in[j + 128], w);
-      const int j0 = ((j - r) << 1) + r;
-      if (s == 0) {                                            // out[2 j], out[2 j + 1]: one 16-byte store
-        *reinterpret_cast<float4*>(out + j0) = make_float4(u.x + v.x, u.y + v.y, u.x - v.x, u.y - v.y);
+      const float2 v0 = in[j];
+      float2 v1 = in[j + 64], v2 = in[j + 128], v3 = in[j + 192];
+      if (s > 0) {                                             // stage 0: all twiddles are 1
+        float2 w1 = t[r], w2 = t[Ns + r], w3 = t[2 * Ns + r];
+        if (INV) { w1.y = -w1.y; w2.y = -w2.y; w3.y = -w3.y; }
+        v1 = cmul2(v1, w1); v2 = cmul2(v2, w2); v3 = cmul2(v3, w3);
+      }
+      const float2 A = make_float2(v0.x + v2.x, v0.y + v2.y), B = make_float2(v0.x - v2.x, v0.y - v2.y);
+      const float2 Cs = make_float2(v1.x + v3.x, v1.y + v3.y), D = make_float2(v1.x - v3.x, v1.y - v3.y);
+      const float2 y0 = make_float2(A.x + Cs.x, A.y + Cs.y), y2 = make_float2(A.x - Cs.x, A.y - Cs.y);
+      // forward: y1 = B - i D, y3 = B + i D; inverse: the other way round
+      const float2 bm = make_float2(B.x + D.y, B.y - D.x), bp = make_float2(B.x - D.y, B.y + D.x);
+      const float2 y1 = INV ? bp : bm, y3 = INV ? bm : bp;
+      const int j0 = ((j - r) << 2) + r;
+      if (s == 0) {                                            // out[4 j .. 4 j + 3]: two 16-byte stores
+        *reinterpret_cast<float4*>(out + j0) = make_float4(y0.x, y0.y, y1.x, y1.y);
+        *reinterpret_cast<float4*>(out + j0 + 2) = make_float4(y2.x, y2.y, y3.x, y3.y);
       } else {
-        out[j0] = make_float2(u.x + v.x, u.y + v.y);
-        out[j0 + Ns] = make_float2(u.x - v.x, u.y - v.y);
+        out[j0] = y0;
+        out[j0 + Ns] = y1;
+        out[j0 + 2 * Ns] = y2;
+        out[j0 + 3 * Ns] = y3;
       }
     }
     __syncwarp();
-    float2* t = in; in = out; out = t;
+    float2* tmp = in; in = out; out = tmp;
   }
 }
 
 __device__ __forceinline__ void make_twiddles(float2* tw) {
   for (int i = threadIdx.x; i < kTwEntries; i += blockDim.x) {
-    const int s = 31 - __clz(i + 1), r = i + 1 - (1 << s);    // stage and entry
+    float x;                                                   // entry = exp(-i pi x)
+    if (i < kTwFull) {
+      const int s = (31 - __clz(i + 1)) >> 1, Ns = 1 << (2 * s), off = i - (Ns - 1);
+      const int m = off / Ns + 1, r = off - (m - 1) * Ns;
+      x = (float)(m * r) / (float)(2 * Ns);                    // exp(-2 pi i m r / (4 Ns)); exact in fp32
+    } else {
+      x = (float)(i - kTwFull) * (1.0f / 256.0f);             // exp(-2 pi i k / 512)
+    }
     float sn, cs;
-    sincospif((float)(r << (8 - s)) * (1.0f / 256.0f), &sn, &cs);   // exp(-i pi k / 256), k = r 2^(8 - s)
+    sincospif(x, &sn, &cs);
     tw[i] = make_float2(cs, -sn);
   }
 }
